@@ -1,0 +1,255 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Same names and argument meaning as ``namespace cvGS`` (reference include/cvGPUSpeedup.cuh):
+``resize``, ``cvtColor``, ``multiply``, ``subtract``, ``divide``, ``add``, ``convertTo``,
+``split``, ``splitT``, ``write``, ``executeOperations`` and ``CircularTensor``.  The functions
+build small descriptor objects (the reference builds operation-struct PODs) and
+``executeOperations`` turns the chain into ONE call of the C-ABI, i.e. one kernel launch.
+
+torch is used only as the owner of device memory and streams (``GpuMat`` wraps a uint8 CUDA
+tensor the way cv::cuda::GpuMat wraps a device allocation).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+from . import _abi
+from ._abi import (CT_NEWEST_FIRST, CT_OLDEST_FIRST, CT_STANDARD, CT_TRANSPOSED, FP_REFERENCE_FUSED,
+                   FP_SEPARATE, IGNORE_AR, INTERP_FLOAT, INTERP_ROUND_U8, OUT_CNHW, OUT_NCHW, OUT_NHWC,
+                   PRESERVE_AR, PRESERVE_AR_LEFT, PRESERVE_AR_RN_EVEN, CvgsError)
+
+# cv::ColorConversionCodes values used by the reference tests (cv2cuda_types.cuh:77-86)
+COLOR_BGR2RGB = 4
+COLOR_RGB2BGR = 4
+INTER_LINEAR = 1
+CV_8UC3 = _abi.CVGS_8UC3
+CV_32FC3 = _abi.CVGS_32FC3
+
+
+class GpuMat:
+    """Minimal cv::cuda::GpuMat stand-in: the wrapper only ever touches data/cols/rows/step
+    (reference include/cvGPUSpeedup.cuh:36,42,69)."""
+
+    __slots__ = ("data", "cols", "rows", "step", "_owner")
+
+    def __init__(self, data: int, cols: int, rows: int, step: int, owner=None):
+        self.data, self.cols, self.rows, self.step, self._owner = int(data), int(cols), int(rows), int(step), owner
+
+    @classmethod
+    def from_tensor(cls, t) -> "GpuMat":
+        """t: uint8 CUDA tensor [H, W, 3] whose rows are contiguous (stride(1)==3, stride(2)==1)."""
+        if t.dim() != 3 or t.shape[2] != 3 or t.stride(2) != 1 or t.stride(1) != 3 or not t.is_cuda:
+            raise ValueError("expected a CUDA uint8 HxWx3 tensor with packed pixels")
+        return cls(t.data_ptr(), t.shape[1], t.shape[0], t.stride(0), owner=t)
+
+    def roi(self, x: int, y: int, w: int, h: int) -> "GpuMat":
+        """d_input(cv::Rect(x, y, w, h))"""
+        if x < 0 or y < 0 or w <= 0 or h <= 0 or x + w > self.cols or y + h > self.rows:
+            raise ValueError("ROI outside the image")
+        return GpuMat(self.data + y * self.step + 3 * x, w, h, self.step, owner=self._owner)
+
+
+def _scalar3(s) -> Tuple[float, float, float]:
+    if isinstance(s, (int, float)):
+        return (float(s),) * 3
+    s = tuple(float(v) for v in s)
+    if len(s) < 3:
+        raise ValueError("a 3-channel cv::Scalar is required")
+    return s[:3]
+
+
+@dataclass
+class _Resize:
+    crops: List[GpuMat]
+    dsize: Tuple[int, int]  # (width, height) like cv::Size
+    used: int
+    background: Tuple[float, float, float]
+    aspect: int
+
+
+@dataclass
+class _Op:
+    kind: int
+    v: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    perm: Tuple[int, int, int] = (0, 1, 2)
+
+
+@dataclass
+class _Write:
+    out_ptr: int
+    layout: int
+    plane_stride: int = 0
+    owner: object = None
+
+
+def resize(crops: Sequence[GpuMat], dsize: Tuple[int, int], usedPlanes: Optional[int] = None,
+           backgroundValue=(0.0, 0.0, 0.0), aspect: int = IGNORE_AR) -> _Resize:
+    """cvGS::resize<CV_8UC3, INTER_LINEAR, N, AR>(array<GpuMat,N>, Size, usedPlanes, bg)
+    (reference include/cvGPUSpeedup.cuh:218-245)."""
+    crops = list(crops)
+    return _Resize(crops, (int(dsize[0]), int(dsize[1])), len(crops) if usedPlanes is None else int(usedPlanes),
+                   _scalar3(backgroundValue), int(aspect))
+
+
+def multiply(s) -> _Op:   # cvGS::multiply<CV_32FC3>(Scalar) :131
+    return _Op(_abi.OP_MUL, _scalar3(s))
+
+
+def subtract(s) -> _Op:   # cvGS::subtract :136
+    return _Op(_abi.OP_SUB, _scalar3(s))
+
+
+def divide(s) -> _Op:     # cvGS::divide :141
+    return _Op(_abi.OP_DIV, _scalar3(s))
+
+
+def add(s) -> _Op:        # cvGS::add :146
+    return _Op(_abi.OP_ADD, _scalar3(s))
+
+
+def convertTo(alpha: Optional[float] = None, beta: Optional[float] = None) -> List[_Op]:
+    """cvGS::convertTo<CV_8UC3, CV_32FC3>([alpha[, beta]]) :74-129 -- the cast itself is implicit
+    (the resize already yields float), alpha is a Mul, beta an Add."""
+    ops: List[_Op] = []
+    if alpha is not None:
+        ops.append(multiply(alpha))
+    if beta is not None:
+        ops.append(add(beta))
+    return ops
+
+
+def cvtColor(code: int = COLOR_RGB2BGR) -> _Op:
+    """cvGS::cvtColor<COLOR_RGB2BGR / COLOR_BGR2RGB, CV_32FC3>() :151-161 = VectorReorder<2,1,0>."""
+    if code != COLOR_RGB2BGR:
+        raise CvgsError("only the 3-channel R<->B swap is on this path")
+    return _Op(_abi.OP_REORDER, perm=(2, 1, 0))
+
+
+def split(out, planeDims: Optional[Tuple[int, int]] = None, plane_stride: int = 0) -> _Write:
+    """cvGS::split<CV_32FC3>(GpuMat out, Size plane) :185-192 -> fk::TensorSplit (NCHW)."""
+    return _Write(out.data_ptr(), OUT_NCHW, plane_stride, out)
+
+
+def splitT(out, plane_stride: int = 0) -> _Write:
+    """cvGS::splitT<CV_32FC3>(RawPtr<T3D>) :199-202 -> fk::TensorTSplit (CNHW)."""
+    return _Write(out.data_ptr(), OUT_CNHW, plane_stride, out)
+
+
+def write(out, plane_stride: int = 0) -> _Write:
+    """cvGS::write<CV_32FC3>(GpuMat, Size) :454-457 -> packed NHWC."""
+    return _Write(out.data_ptr(), OUT_NHWC, plane_stride, out)
+
+
+def _stream_ptr(stream) -> int:
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(stream, int):
+        return stream
+    return stream.cuda_stream
+
+
+def _flatten(ops):
+    for o in ops:
+        if isinstance(o, (list, tuple)):
+            yield from _flatten(o)
+        else:
+            yield o
+
+
+def build_pipeline(dsize, ops: Sequence[_Op], background=(0, 0, 0), aspect=IGNORE_AR,
+                   fp_contract=FP_REFERENCE_FUSED, interp_mode=INTERP_FLOAT, out_ptr=0, layout=OUT_NCHW,
+                   plane_stride=0) -> _abi.Pipeline:
+    p = _abi.Pipeline()
+    p.src_type = _abi.CVGS_8UC3
+    p.dst_width, p.dst_height = int(dsize[0]), int(dsize[1])
+    p.aspect_mode, p.interp_mode, p.fp_contract = int(aspect), int(interp_mode), int(fp_contract)
+    bg = _scalar3(background)
+    for c in range(3):
+        p.background[c] = bg[c]
+    ops = list(_flatten(ops))
+    if len(ops) > _abi.MAX_OPS:
+        raise CvgsError(f"at most {_abi.MAX_OPS} operations between resize and write")
+    p.n_ops = len(ops)
+    for i, o in enumerate(ops):
+        p.ops[i].kind = o.kind
+        for c in range(3):
+            p.ops[i].v[c] = o.v[c]
+            p.ops[i].perm[c] = o.perm[c]
+    p.out_layout, p.out, p.out_plane_stride = int(layout), out_ptr, int(plane_stride)
+    return p
+
+
+def make_crops(mats: Sequence[GpuMat]):
+    arr = (_abi.Crop * max(1, len(mats)))()
+    for i, m in enumerate(mats):
+        arr[i].data, arr[i].width, arr[i].height, arr[i].pitch, arr[i].reserved = m.data, m.cols, m.rows, m.step, 0
+    return arr
+
+
+def executeOperations(stream, *iops, fp_contract: int = FP_REFERENCE_FUSED, interp_mode: int = INTERP_FLOAT) -> None:
+    """cvGS::executeOperations(stream, resize(...), ops..., split(...)) :464-473: ONE kernel launch,
+    asynchronous on `stream`.  Raises CvgsError (the reference throws std::runtime_error)."""
+    iops = list(_flatten(iops))
+    if len(iops) < 2 or not isinstance(iops[0], _Resize) or not isinstance(iops[-1], _Write):
+        raise CvgsError("chain must start with resize(...) and end with split/splitT/write(...)")
+    rs, wr, mid = iops[0], iops[-1], iops[1:-1]
+    if any(not isinstance(o, _Op) for o in mid):
+        raise CvgsError("only multiply/subtract/divide/add/convertTo/cvtColor may sit between read and write")
+    p = build_pipeline(rs.dsize, mid, rs.background, rs.aspect, fp_contract, interp_mode, wr.out_ptr, wr.layout,
+                       wr.plane_stride)
+    crops = make_crops(rs.crops[:rs.used])
+    lib = _abi.load()
+    _abi.check(lib.cvgs_b200_preproc_launch(crops, len(rs.crops), rs.used, C.byref(p), _stream_ptr(stream)))
+
+
+class CircularTensor:
+    """cvGS::CircularTensor<CV_8UC3, CV_32F, 3, BATCH, ORDER, MODE> (reference
+    include/cvGPUSpeedup.cuh:600-627): ``update(stream, frame, ops...)`` processes the new frame into
+    the newest plane and shifts the others; ``data()`` is the dense time-ordered tensor."""
+
+    def __init__(self, width: int, height: int, batch: int, order: int = CT_NEWEST_FIRST,
+                 mode: int = CT_STANDARD, color_planes: int = 3, device: int = 0):
+        self._lib = _abi.load()
+        self._h = C.c_void_p()
+        self.width, self.height, self.batch, self.order, self.mode, self.color_planes = (
+            width, height, batch, order, mode, color_planes)
+        _abi.check(self._lib.cvgs_b200_ct_create(C.byref(self._h), width, height, color_planes, batch, order, mode,
+                                                 device))
+
+    def update(self, stream, frame: GpuMat, *ops, fp_contract: int = FP_REFERENCE_FUSED,
+               interp_mode: int = INTERP_FLOAT) -> None:
+        p = build_pipeline((self.width, self.height), list(_flatten(ops)), fp_contract=fp_contract,
+                           interp_mode=interp_mode)
+        crop = make_crops([frame])
+        _abi.check(self._lib.cvgs_b200_ct_update(self._h, crop, C.byref(p), _stream_ptr(stream)))
+
+    def data_ptr(self) -> int:
+        return int(self._lib.cvgs_b200_ct_data(self._h) or 0)
+
+    def data(self):
+        """Dense tensor as a torch view (no copy) of the library-owned memory."""
+        import torch
+        shape = ((self.batch, self.color_planes, self.height, self.width) if self.mode == CT_STANDARD
+                 else (self.color_planes, self.batch, self.height, self.width))
+
+        class _Holder:
+            pass
+
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (self.data_ptr(), False),
+                                      "version": 2, "strides": None}
+        return torch.as_tensor(h, device="cuda")
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.cvgs_b200_ct_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,177 @@
+// cvgs_device.cuh -- device-side data structures and arithmetic shared by the sm_100a kernels.
+//
+// Arithmetic contract (DESIGN.md "Parity"): every float operation is written with an explicit
+// rounding intrinsic so that nvcc can neither contract nor reassociate it.  The sequences are
+// the ones the reference's fused kernel executes (reference
+// fkl/include/fused_kernel/algorithms/image_processing/interpolation.cuh:57-92,
+// resize.cuh:178-189, basic_ops/arithmetic.cuh:43-68), pinned from its sm_100a SASS.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cvgs {
+
+// One source crop plus the resize geometry the host derived for it
+// (= fk::RawPtr<_2D,uchar3> + fk::ResizeReadParams, reference resize.cuh:43-58).
+struct __align__(16) DevCrop {
+    const uint8_t* data;  // first pixel of the ROI
+    int32_t w, h;         // source size in pixels
+    int32_t pitch;        // bytes between rows
+    float fx, fy;         // src_conv_factors
+    int32_t bx1, by1;     // band that receives the image (aspect-ratio modes); whole plane otherwise
+    int32_t bx2, by2;
+    int32_t pad;
+};
+static_assert(sizeof(DevCrop) == 48, "DevCrop layout");
+
+// Normalised op chain.  Channel reorders are folded into out_perm, SUB is ADD of the negated
+// constant (exact), and under the reference-fused contract MUL followed by ADD/SUB is one FMA.
+// Constants are indexed by SOURCE channel ("register space").
+enum DevOpKind : int32_t { DOP_MUL = 1, DOP_ADD = 2, DOP_DIV = 3, DOP_FMA = 4 };
+struct DevOp {
+    int32_t kind;
+    float a[3];
+    float b[3];
+};
+struct DevProgram {
+    int32_t n_ops;
+    int32_t round_u8;     // CVGS_INTERP_ROUND_U8
+    int32_t dst_chan[3];  // source channel r is written to output channel dst_chan[r]
+    DevOp ops[8];
+};
+
+struct OutDesc {
+    float* base;
+    long long z_stride;  // floats between batch planes
+    long long c_stride;  // floats between colour planes
+    int32_t px_stride;   // floats between x-adjacent pixels (1 planar, 3 packed)
+    int32_t vec4;        // 1: planar rows are 16-byte aligned and W % 4 == 0
+};
+
+struct PreprocParams {
+    const DevCrop* crops;  // device table (nullptr when the table rides in the kernel params)
+    int32_t n_planes, used;
+    int32_t W, H;          // destination size
+    int32_t band_test;     // 1 for the aspect-ratio preserving modes
+    float bg[3];           // background / default value (source channel order)
+    DevProgram prog;
+    OutDesc out;
+};
+
+constexpr int kParamCrops = 64;  // batches up to this size carry their descriptors as kernel params
+struct ParamCropTable {
+    DevCrop c[kParamCrops];
+};
+
+// ---------------------------------------------------------------------------------------------
+// exact u8 -> f32: byte k of `w` is placed in the mantissa of 2^23, then 2^23 is subtracted.
+// One PRMT (alu pipe) + one FADD (fma pipe) instead of a quarter-rate I2F.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float u8_to_f32(uint32_t w, uint32_t k) {
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | k)), 8388608.0f);
+}
+
+// Bilinear weights of one axis: s = i*f, i1 = floor(s), w1 = s - i1, w0 = (i1+1) - s
+// (reference resize.cuh:178-189 + interpolation.cuh:57-70,88-91).
+struct AxisTap {
+    int32_t i1;
+    float w0, w1;
+};
+__device__ __forceinline__ AxisTap axis_tap(int i, float f) {
+    const float s = __fmul_rn((float)i, f);
+    AxisTap t;
+    t.i1 = __float2int_rd(s);
+    const float fl = (float)t.i1;
+    t.w1 = __fsub_rn(s, fl);
+    t.w0 = __fsub_rn(__fadd_rn(fl, 1.0f), s);  // (float)(i1+1) == fl + 1 exactly for |i1| < 2^24
+    return t;
+}
+
+// One channel of Interpolate<INTER_LINEAR>::exec in the order nvcc emits for the reference:
+// FMUL(p10*w10), FFMA(p00,w00), FFMA(p01,w01), FFMA(p11,w11).
+__device__ __forceinline__ float bilerp(float p00, float p10, float p01, float p11, float w00, float w10,
+                                        float w01, float w11) {
+    float t = __fmul_rn(p10, w10);
+    t = __fmaf_rn(p00, w00, t);
+    t = __fmaf_rn(p01, w01, t);
+    t = __fmaf_rn(p11, w11, t);
+    return t;
+}
+
+// SaturateCast<float, uchar> then back to float (reference saturate.cuh:127-147).
+__device__ __forceinline__ float round_sat_u8(float v) {
+    const unsigned u = __float2uint_rn(v);
+    return (float)(u > 255u ? 255u : u);
+}
+
+// Apply the normalised chain to N values laid out as v[pixel][channel].
+template <int NPIX>
+__device__ __forceinline__ void apply_program(const DevProgram& prog, float (&v)[NPIX][3]) {
+    if (prog.round_u8) {
+#pragma unroll
+        for (int p = 0; p < NPIX; ++p)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[p][c] = round_sat_u8(v[p][c]);
+    }
+    for (int i = 0; i < prog.n_ops; ++i) {
+        const DevOp& op = prog.ops[i];
+        switch (op.kind) {
+            case DOP_FMA:
+#pragma unroll
+                for (int p = 0; p < NPIX; ++p)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[p][c] = __fmaf_rn(v[p][c], op.a[c], op.b[c]);
+                break;
+            case DOP_MUL:
+#pragma unroll
+                for (int p = 0; p < NPIX; ++p)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[p][c] = __fmul_rn(v[p][c], op.a[c]);
+                break;
+            case DOP_ADD:
+#pragma unroll
+                for (int p = 0; p < NPIX; ++p)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[p][c] = __fadd_rn(v[p][c], op.a[c]);
+                break;
+            case DOP_DIV:
+#pragma unroll
+                for (int p = 0; p < NPIX; ++p)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[p][c] = __fdiv_rn(v[p][c], op.a[c]);
+                break;
+            default:
+                break;
+        }
+    }
+}
+
+__device__ __forceinline__ void st_cs_f32x4(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void st_cs_f32(float* p, float a) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+
+// Store NPIX x-adjacent pixels (first one at column x) of row y, plane z.
+template <int NPIX>
+__device__ __forceinline__ void store_pixels(const PreprocParams& P, int z, int y, int x, int nvalid,
+                                             const float (&v)[NPIX][3]) {
+    const OutDesc& o = P.out;
+    float* row = o.base + (long long)z * o.z_stride + ((long long)y * P.W + x) * o.px_stride;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        // the channel reorder costs nothing: it only changes which plane register r goes to
+        float* dst = row + (long long)P.prog.dst_chan[r] * o.c_stride;
+        if (NPIX == 4 && o.vec4 && nvalid == 4) {
+            st_cs_f32x4(dst, v[0][r], v[1][r], v[2][r], v[3][r]);
+        } else {
+#pragma unroll
+            for (int p = 0; p < NPIX; ++p)
+                if (p < nvalid) st_cs_f32(dst + (long long)p * o.px_stride, v[p][r]);
+        }
+    }
+}
+
+}  // namespace cvgs

@@ -1,0 +1,319 @@
+// preproc.cu -- the fused crop -> bilinear resize -> op chain -> planar split path for sm_100a.
+//
+// Replaces the one instantiation of fk::launchTransformDPP_Kernel that
+// cvGS::executeOperations(stream, resize<CV_8UC3,...>(crops...), ops..., split<CV_32FC3>(...)) produces
+// (reference fkl/include/fused_kernel/core/execution_model/data_parallel_patterns.cuh:157-197,256-260;
+// launch logic executors.cuh:109-158).  Batch size, aspect mode and the op chain are runtime data
+// here (they are template parameters in the reference, capped at 255 planes -- SURVEY.md F7).
+//
+// Two kernels:
+//   preproc_direct_kernel  gathers the bilinear taps straight from global memory with aligned word
+//                          loads; works for any pitch / alignment / size.  Fallback + small batches.
+//   preproc_tma_kernel     (preproc_tma.cuh) persistent, warp-specialised; source rows are staged
+//                          into shared memory by the TMA engine (cp.async.bulk, mbarrier pipeline).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "cvgs_device.cuh"
+#include "cvgs_runtime.hpp"
+#include "preproc_host.hpp"
+#include "preproc_direct.cuh"
+#include "preproc_tma.cuh"
+
+namespace cvgs {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string t_last_error;
+static thread_local int64_t t_launch_count = 0;
+static std::atomic<int> g_variant{0};
+
+void set_error(const std::string& msg) { t_last_error = msg; }
+int fail(int code, const std::string& msg) {
+    t_last_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    t_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return static_cast<int>(e);
+}
+void count_launch() { ++t_launch_count; }
+
+// ------------------------------------------------------------------------------------------------
+// direct-gather kernel
+// ------------------------------------------------------------------------------------------------
+struct NoTable {};
+
+template <typename Table>
+__device__ __forceinline__ const DevCrop& crop_of(const PreprocParams& P, const Table& T, int z);
+template <>
+__device__ __forceinline__ const DevCrop& crop_of<NoTable>(const PreprocParams& P, const NoTable&, int z) {
+    return P.crops[z];
+}
+template <>
+__device__ __forceinline__ const DevCrop& crop_of<ParamCropTable>(const PreprocParams&, const ParamCropTable& T,
+                                                                  int z) {
+    return T.c[z];
+}
+
+// block = 256 threads = (1 << bw_log2) quads in x  X  (256 >> bw_log2) rows; a quad = 4 output pixels.
+template <typename Table>
+__global__ void __launch_bounds__(256)
+preproc_direct_kernel(const __grid_constant__ PreprocParams P, const __grid_constant__ Table T, int bw_log2) {
+    const int tid = threadIdx.x;
+    const int tx = tid & ((1 << bw_log2) - 1);
+    const int ty = tid >> bw_log2;
+    const int x0 = ((blockIdx.x << bw_log2) + tx) * 4;
+    const int y = blockIdx.y * (256 >> bw_log2) + ty;
+    const int z = blockIdx.z;
+    if (x0 >= P.W || y >= P.H) return;
+    const int nvalid = min(4, P.W - x0);
+
+    float v[4][3];
+    if (z < P.used) {
+        gather_quad(P, crop_of<Table>(P, T, z), y, x0, nvalid, v);
+    } else {
+        fill_background(P, v);
+    }
+    apply_program<4>(P.prog, v);
+    store_pixels<4>(P, z, y, x0, nvalid, v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-thread context: descriptor staging ring (pinned host + device) for batches that do not fit
+// the kernel parameters, and the device buffers of the host-buffer entry point.
+// ------------------------------------------------------------------------------------------------
+struct Ring {
+    static constexpr int kSlots = 8;
+    DevCrop* h[kSlots] = {};
+    DevCrop* d[kSlots] = {};
+    cudaEvent_t ev[kSlots] = {};
+    bool pending[kSlots] = {};
+    size_t cap = 0;  // crops per slot
+    int next = 0;
+    int device = -1;
+};
+struct HostPath {
+    void* d_img = nullptr;
+    size_t img_cap = 0;
+    float* d_out = nullptr;
+    size_t out_cap = 0;
+    int device = -1;
+};
+struct Ctx {
+    Ring ring;
+    HostPath host;
+    int sm_count = 0;
+    int sm_count_device = -1;
+    ~Ctx() {
+        // process teardown: the CUDA context may already be gone, so errors are ignored
+        for (int i = 0; i < Ring::kSlots; ++i) {
+            if (ring.h[i]) cudaFreeHost(ring.h[i]);
+            if (ring.d[i]) cudaFree(ring.d[i]);
+            if (ring.ev[i]) cudaEventDestroy(ring.ev[i]);
+        }
+        if (host.d_img) cudaFree(host.d_img);
+        if (host.d_out) cudaFree(host.d_out);
+    }
+};
+static thread_local Ctx t_ctx;
+
+static int ring_reserve(Ring& r, size_t n, int device) {
+    if (r.device == device && n <= r.cap) return CVGS_OK;
+    for (int i = 0; i < Ring::kSlots; ++i) {
+        if (r.pending[i]) { CVGS_CUDA(cudaEventSynchronize(r.ev[i])); r.pending[i] = false; }
+        if (r.h[i]) { CVGS_CUDA(cudaFreeHost(r.h[i])); r.h[i] = nullptr; }
+        if (r.d[i]) { CVGS_CUDA(cudaFree(r.d[i])); r.d[i] = nullptr; }
+        if (!r.ev[i]) CVGS_CUDA(cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming));
+    }
+    size_t cap = 256;
+    while (cap < n) cap *= 2;
+    for (int i = 0; i < Ring::kSlots; ++i) {
+        CVGS_CUDA(cudaMallocHost(&r.h[i], cap * sizeof(DevCrop)));
+        CVGS_CUDA(cudaMalloc(&r.d[i], cap * sizeof(DevCrop)));
+    }
+    r.cap = cap;
+    r.device = device;
+    return CVGS_OK;
+}
+
+int sm_count_of(int device) {
+    Ctx& c = t_ctx;
+    if (c.sm_count_device != device) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+        c.sm_count = n;
+        c.sm_count_device = device;
+    }
+    return c.sm_count;
+}
+
+static int pick_bw_log2(int W) {
+    const int qw = (W + 3) / 4;
+    int best = 3, best_pad = 1 << 30;
+    for (int l = 3; l <= 6; ++l) {
+        const int bw = 1 << l;
+        const int padded = (qw + bw - 1) / bw * bw;
+        if (padded <= best_pad) { best_pad = padded; best = l; }
+    }
+    return best;
+}
+
+static int launch_direct(const PreprocParams& P, const ParamCropTable* table, cudaStream_t stream) {
+    const int l = pick_bw_log2(P.W);
+    const int qw = (P.W + 3) / 4;
+    const int rows = 256 >> l;
+    const dim3 grid((qw + (1 << l) - 1) >> l, (P.H + rows - 1) / rows, P.n_planes);
+    if (grid.y > 65535u || grid.z > 65535u) return fail(CVGS_ERR_INVALID_VALUE, "batch or height too large for one launch");
+    if (table) {
+        preproc_direct_kernel<ParamCropTable><<<grid, 256, 0, stream>>>(P, *table, l);
+    } else {
+        preproc_direct_kernel<NoTable><<<grid, 256, 0, stream>>>(P, NoTable{}, l);
+    }
+    count_launch();
+    CVGS_CUDA(cudaGetLastError());
+    return CVGS_OK;
+}
+
+// Shared by the batch entry point and the host-buffer entry point.
+static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_pipeline_t* pipe,
+                               float* out, cudaStream_t stream) {
+    if (int rc = validate_pipeline(pipe)) return rc;
+    if (!out) return fail(CVGS_ERR_INVALID_VALUE, "output pointer is NULL");
+    if (n_planes <= 0) return fail(CVGS_ERR_INVALID_VALUE, "n_planes must be positive");
+    if (used < 0) return fail(CVGS_ERR_INVALID_VALUE, "used must be non-negative");
+    if (used > n_planes) used = n_planes;
+    if (used > 0 && !crops) return fail(CVGS_ERR_INVALID_VALUE, "crops is NULL");
+
+    PreprocParams P;
+    if (int rc = build_params(*pipe, n_planes, used, out, P)) return rc;
+
+    int device = 0;
+    CVGS_CUDA(cudaGetDevice(&device));
+    const int variant = g_variant.load(std::memory_order_relaxed);
+
+    if (used <= kParamCrops) {
+        // small batch: descriptors ride in the kernel parameters (no staging copy, graph-capturable)
+        ParamCropTable table;
+        std::memset(&table, 0, sizeof table);
+        for (int i = 0; i < used; ++i)
+            if (int rc = fill_crop(crops[i], *pipe, i, table.c[i])) return rc;
+        if (variant != 1 && tma_supported(P, table.c, used)) return launch_tma(P, &table, table.c, used, device, stream);
+        if (variant == 2) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
+        return launch_direct(P, &table, stream);
+    }
+
+    Ring& r = t_ctx.ring;
+    if (int rc = ring_reserve(r, static_cast<size_t>(used), device)) return rc;
+    const int slot = r.next;
+    r.next = (r.next + 1) % Ring::kSlots;
+    if (r.pending[slot]) { CVGS_CUDA(cudaEventSynchronize(r.ev[slot])); r.pending[slot] = false; }
+    for (int i = 0; i < used; ++i)
+        if (int rc = fill_crop(crops[i], *pipe, i, r.h[slot][i])) return rc;
+    CVGS_CUDA(cudaMemcpyAsync(r.d[slot], r.h[slot], static_cast<size_t>(used) * sizeof(DevCrop),
+                              cudaMemcpyHostToDevice, stream));
+    P.crops = r.d[slot];
+    int rc;
+    if (variant != 1 && tma_supported(P, r.h[slot], used)) {
+        rc = launch_tma(P, nullptr, r.h[slot], used, device, stream);
+    } else if (variant == 2) {
+        rc = fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
+    } else {
+        rc = launch_direct(P, nullptr, stream);
+    }
+    CVGS_CUDA(cudaEventRecord(r.ev[slot], stream));
+    r.pending[slot] = true;
+    return rc;
+}
+
+static int host_reserve(HostPath& h, size_t img_bytes, size_t out_bytes, int device) {
+    if (h.device != device) { h.img_cap = h.out_cap = 0; h.d_img = nullptr; h.d_out = nullptr; h.device = device; }
+    if (img_bytes > h.img_cap) {
+        if (h.d_img) { CVGS_CUDA(cudaDeviceSynchronize()); CVGS_CUDA(cudaFree(h.d_img)); }
+        CVGS_CUDA(cudaMalloc(&h.d_img, img_bytes));
+        h.img_cap = img_bytes;
+    }
+    if (out_bytes > h.out_cap) {
+        if (h.d_out) { CVGS_CUDA(cudaDeviceSynchronize()); CVGS_CUDA(cudaFree(h.d_out)); }
+        CVGS_CUDA(cudaMalloc(reinterpret_cast<void**>(&h.d_out), out_bytes));
+        h.out_cap = out_bytes;
+    }
+    return CVGS_OK;
+}
+
+}  // namespace cvgs
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+using namespace cvgs;
+
+extern "C" {
+
+int cvgs_b200_version(void) { return CVGS_B200_VERSION; }
+const char* cvgs_b200_last_error(void) { return t_last_error.c_str(); }
+int cvgs_b200_set_kernel_variant(int variant) { return g_variant.exchange(variant); }
+int64_t cvgs_b200_launch_count(void) { return t_launch_count; }
+
+int cvgs_b200_preproc_launch(const cvgs_crop_t* crops, int32_t n_planes, int32_t used,
+                             const cvgs_pipeline_t* pipeline, void* stream) {
+    if (!pipeline) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
+    return preproc_launch_impl(crops, n_planes, used, pipeline, static_cast<float*>(pipeline->out),
+                               static_cast<cudaStream_t>(stream));
+}
+
+int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t image_height, int32_t image_pitch,
+                           const cvgs_rect_t* rects, int32_t n_planes, int32_t used,
+                           const cvgs_pipeline_t* pipeline, float* host_out, void* stream_) {
+    if (int rc = validate_pipeline(pipeline)) return rc;
+    if (!host_image || !host_out || !rects) return fail(CVGS_ERR_INVALID_VALUE, "NULL host buffer");
+    if (image_width <= 0 || image_height <= 0 || image_pitch < 3 * image_width)
+        return fail(CVGS_ERR_INVALID_VALUE, "bad host image geometry");
+    if (n_planes <= 0 || used < 0) return fail(CVGS_ERR_INVALID_VALUE, "bad batch size");
+    if (used > n_planes) used = n_planes;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int device = 0;
+    CVGS_CUDA(cudaGetDevice(&device));
+    // device copy keeps rows 512-byte aligned like cudaMallocPitch would
+    const size_t d_pitch = (static_cast<size_t>(3) * image_width + 511) / 512 * 512;
+    const size_t img_bytes = d_pitch * image_height;
+    const size_t out_floats = static_cast<size_t>(3) * pipeline->dst_width * pipeline->dst_height * n_planes;
+    if (int rc = host_reserve(t_ctx.host, img_bytes, out_floats * sizeof(float), device)) return rc;
+    HostPath& h = t_ctx.host;
+
+    // upload only the rows some crop touches
+    int y_lo = image_height, y_hi = 0;
+    std::vector<cvgs_crop_t> crops(static_cast<size_t>(used));
+    for (int i = 0; i < used; ++i) {
+        const cvgs_rect_t& r = rects[i];
+        if (r.x < 0 || r.y < 0 || r.width <= 0 || r.height <= 0 || r.x + r.width > image_width ||
+            r.y + r.height > image_height)
+            return fail(CVGS_ERR_INVALID_VALUE, "rect " + std::to_string(i) + " outside the image");
+        y_lo = std::min(y_lo, r.y);
+        y_hi = std::max(y_hi, r.y + r.height);
+        crops[i].data = static_cast<const uint8_t*>(h.d_img) + static_cast<size_t>(r.y) * d_pitch + 3 * static_cast<size_t>(r.x);
+        crops[i].width = r.width;
+        crops[i].height = r.height;
+        crops[i].pitch = static_cast<int32_t>(d_pitch);
+        crops[i].reserved = 0;
+    }
+    if (used > 0) {
+        CVGS_CUDA(cudaMemcpy2DAsync(static_cast<uint8_t*>(h.d_img) + static_cast<size_t>(y_lo) * d_pitch, d_pitch,
+                                    static_cast<const uint8_t*>(host_image) + static_cast<size_t>(y_lo) * image_pitch,
+                                    static_cast<size_t>(image_pitch), static_cast<size_t>(3) * image_width,
+                                    static_cast<size_t>(y_hi - y_lo), cudaMemcpyHostToDevice, stream));
+    }
+    cvgs_pipeline_t p = *pipeline;
+    p.out_plane_stride = 0;
+    if (int rc = preproc_launch_impl(crops.data(), n_planes, used, &p, h.d_out, stream)) return rc;
+    CVGS_CUDA(cudaMemcpyAsync(host_out, h.d_out, out_floats * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    return CVGS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+// preproc_direct.cuh -- direct-gather computation of one quad (4 x-adjacent output pixels):
+// bilinear taps are fetched straight from global memory with aligned 32-bit loads.
+// Used by preproc_direct_kernel and by the CircularTensor update kernel.
+#pragma once
+#include "cvgs_device.cuh"
+
+namespace cvgs {
+
+// 6-byte window [p(x1) | p(x1+1)] of one source row, fetched with aligned 32-bit loads.
+// Only words that contain at least one needed byte are touched.
+struct Window {
+    uint32_t lo, hi;  // lo = bytes 0..3, hi = bytes 4..5
+};
+__device__ __forceinline__ Window load_window(const uint8_t* p, int nbytes) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t mis = static_cast<uint32_t>(a & 3u);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a - mis);
+    const uint32_t w0 = __ldg(wp);
+    const uint32_t w1 = (mis + nbytes > 4) ? __ldg(wp + 1) : 0u;
+    const uint32_t w2 = (mis + nbytes > 8) ? __ldg(wp + 2) : 0u;
+    Window w;
+    w.lo = __funnelshift_r(w0, w1, mis * 8);
+    w.hi = __funnelshift_r(w1, w2, mis * 8);
+    return w;
+}
+
+__device__ __forceinline__ void fill_background(const PreprocParams& P, float (&v)[4][3]) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[p][c] = P.bg[c];
+}
+
+// Resize::exec + Interpolate::exec for output pixels (x0..x0+3, y) of crop C (reference
+// resize.cuh:70-82,178-189, interpolation.cuh:57-92).  Values outside the aspect-ratio band are
+// the background.  The op chain is NOT applied here.
+__device__ __forceinline__ void gather_quad(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
+                                            float (&v)[4][3]) {
+    fill_background(P, v);
+    const bool row_in = !P.band_test || (y >= C.by1 && y <= C.by2);
+    if (!row_in) return;
+    const AxisTap ty_ = axis_tap(y - C.by1, C.fy);
+    const int y2r = min(ty_.i1 + 1, C.h - 1);
+    const uint8_t* r0 = C.data + (size_t)ty_.i1 * (size_t)C.pitch;
+    const uint8_t* r1 = C.data + (size_t)y2r * (size_t)C.pitch;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int x = x0 + p;
+        if (p < nvalid && x >= C.bx1 && x <= C.bx2) {
+            const AxisTap tx_ = axis_tap(x - C.bx1, C.fx);
+            const bool edge = tx_.i1 + 1 > C.w - 1;  // x2_read == x1
+            const int nb = edge ? 3 : 6;
+            const Window a = load_window(r0 + 3 * tx_.i1, nb);
+            const Window b = load_window(r1 + 3 * tx_.i1, nb);
+            const float w00 = __fmul_rn(tx_.w0, ty_.w0), w10 = __fmul_rn(tx_.w1, ty_.w0);
+            const float w01 = __fmul_rn(tx_.w0, ty_.w1), w11 = __fmul_rn(tx_.w1, ty_.w1);
+            // right taps: bytes 3,4,5 of the window, or the left pixel again at the edge
+            const uint32_t a1 = edge ? a.lo : __funnelshift_r(a.lo, a.hi, 24);
+            const uint32_t b1 = edge ? b.lo : __funnelshift_r(b.lo, b.hi, 24);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                v[p][c] = bilerp(u8_to_f32(a.lo, c), u8_to_f32(a1, c), u8_to_f32(b.lo, c), u8_to_f32(b1, c), w00,
+                                 w10, w01, w11);
+        }
+    }
+}
+
+}  // namespace cvgs

@@ -1,0 +1,165 @@
+// preproc_host.hpp -- host-side logic of the fused batch pipeline: argument validation,
+// resize geometry, op-chain normalisation.  Pure C++ (no CUDA calls) so it is shared by the
+// batch path and the CircularTensor path.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+
+#include "../../include/cvgs_b200.h"
+#include "cvgs_device.cuh"
+#include "cvgs_runtime.hpp"
+
+namespace cvgs {
+
+
+// Host half of fk::Resize::build: scale factors and, for the aspect-ratio preserving modes, the
+// band of the destination that receives the image (reference resize.cuh:100-161,191-216;
+// rounding helper cxp::round, constexpr_cmath.cuh:37-48).
+inline float round_half_away(float x) {
+    if (x != x || std::isinf(x)) return x;
+    return x > 0.f ? static_cast<float>(static_cast<int>(x + 0.5f)) : static_cast<float>(static_cast<int>(x - 0.5f));
+}
+
+inline void resize_geometry(int sw, int sh, int dw, int dh, int aspect, DevCrop& d) {
+    int tw = dw, th = dh;
+    if (aspect != CVGS_IGNORE_AR) {
+        const float sf = dh / static_cast<float>(sh);
+        int w_try = static_cast<int>(round_half_away(sf * sw));
+        const bool even = aspect == CVGS_PRESERVE_AR_RN_EVEN;
+        if (even) w_try -= w_try % 2;
+        if (w_try > dw) {
+            const float sf2 = dw / static_cast<float>(sw);
+            int h_try = static_cast<int>(round_half_away(sf2 * sh));
+            if (even) h_try -= h_try % 2;
+            tw = dw;
+            th = h_try;
+        } else {
+            tw = w_try;
+            th = dh;
+        }
+    }
+    const double cfx = static_cast<double>(tw) / static_cast<double>(sw);
+    const double cfy = static_cast<double>(th) / static_cast<double>(sh);
+    d.fx = static_cast<float>(1.0 / cfx);
+    d.fy = static_cast<float>(1.0 / cfy);
+    if (aspect == CVGS_IGNORE_AR) {
+        d.bx1 = 0; d.by1 = 0; d.bx2 = dw - 1; d.by2 = dh - 1;
+    } else {
+        d.bx1 = aspect == CVGS_PRESERVE_AR_LEFT ? 0 : (dw - tw) / 2;
+        d.by1 = (dh - th) / 2;
+        d.bx2 = d.bx1 + tw - 1;
+        d.by2 = d.by1 + th - 1;
+    }
+}
+
+// Normalise the user's op list (header: enum cvgs_op_kind) into a DevProgram.
+inline int build_program(const cvgs_pipeline_t& p, DevProgram& prog) {
+    std::memset(&prog, 0, sizeof prog);
+    if (p.n_ops < 0 || p.n_ops > CVGS_MAX_OPS) return fail(CVGS_ERR_INVALID_VALUE, "n_ops out of range");
+    prog.round_u8 = p.interp_mode == CVGS_INTERP_ROUND_U8;
+    int cur[3] = {0, 1, 2};  // position c currently holds source channel cur[c]
+    const bool fuse = p.fp_contract == CVGS_FP_REFERENCE_FUSED;
+    int n = 0;
+    for (int i = 0; i < p.n_ops; ++i) {
+        const cvgs_op_t& op = p.ops[i];
+        if (op.kind == CVGS_OP_REORDER) {
+            int nc[3];
+            bool seen[3] = {false, false, false};
+            for (int c = 0; c < 3; ++c) {
+                if (op.perm[c] < 0 || op.perm[c] > 2 || seen[op.perm[c]])
+                    return fail(CVGS_ERR_INVALID_VALUE, "REORDER perm must be a permutation of {0,1,2}");
+                seen[op.perm[c]] = true;
+                nc[c] = cur[op.perm[c]];
+            }
+            std::memcpy(cur, nc, sizeof cur);
+            continue;
+        }
+        DevOp d{};
+        switch (op.kind) {
+            case CVGS_OP_MUL: d.kind = DOP_MUL; break;
+            case CVGS_OP_DIV: d.kind = DOP_DIV; break;
+            case CVGS_OP_ADD:
+            case CVGS_OP_SUB: d.kind = DOP_ADD; break;
+            default: return fail(CVGS_ERR_INVALID_VALUE, "unknown op kind");
+        }
+        for (int c = 0; c < 3; ++c) d.a[cur[c]] = op.kind == CVGS_OP_SUB ? -op.v[c] : op.v[c];
+        // nvcc contracts (x*m) +/- s into one FMA in the reference's inlined chain
+        if (fuse && d.kind == DOP_ADD && n > 0 && prog.ops[n - 1].kind == DOP_MUL) {
+            DevOp& m = prog.ops[n - 1];
+            m.kind = DOP_FMA;
+            for (int c = 0; c < 3; ++c) m.b[c] = d.a[c];
+            continue;
+        }
+        prog.ops[n++] = d;
+    }
+    prog.n_ops = n;
+    for (int c = 0; c < 3; ++c) prog.dst_chan[cur[c]] = c;
+    return CVGS_OK;
+}
+
+inline int validate_pipeline(const cvgs_pipeline_t* p) {
+    if (!p) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
+    if (p->src_type != CVGS_8UC3)
+        return fail(CVGS_ERR_NOT_SUPPORTED, "only CV_8UC3 sources are supported by this build");
+    if (p->dst_width <= 0 || p->dst_height <= 0 || p->dst_width > (1 << 20) || p->dst_height > (1 << 20))
+        return fail(CVGS_ERR_INVALID_VALUE, "destination size out of range");
+    if (p->aspect_mode < 0 || p->aspect_mode > 3) return fail(CVGS_ERR_INVALID_VALUE, "bad aspect_mode");
+    if (p->interp_mode < 0 || p->interp_mode > 1) return fail(CVGS_ERR_INVALID_VALUE, "bad interp_mode");
+    if (p->fp_contract < 0 || p->fp_contract > 1) return fail(CVGS_ERR_INVALID_VALUE, "bad fp_contract");
+    if (p->out_layout < 0 || p->out_layout > 2) return fail(CVGS_ERR_INVALID_VALUE, "bad out_layout");
+    if (p->out_plane_stride < 0) return fail(CVGS_ERR_INVALID_VALUE, "negative out_plane_stride");
+    return CVGS_OK;
+}
+
+// Fill the launch parameters that do not depend on the crops.
+inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float* out, PreprocParams& P) {
+    std::memset(&P, 0, sizeof P);
+    P.n_planes = n_planes;
+    P.used = used;
+    P.W = p.dst_width;
+    P.H = p.dst_height;
+    P.band_test = p.aspect_mode != CVGS_IGNORE_AR;
+    for (int c = 0; c < 3; ++c) P.bg[c] = p.background[c];
+    if (int rc = build_program(p, P.prog)) return rc;
+    const long long plane = static_cast<long long>(p.dst_width) * p.dst_height;
+    OutDesc& o = P.out;
+    o.base = out;
+    switch (p.out_layout) {
+        case CVGS_OUT_NCHW:
+            o.z_stride = p.out_plane_stride ? p.out_plane_stride : 3 * plane;
+            o.c_stride = plane;
+            o.px_stride = 1;
+            break;
+        case CVGS_OUT_CNHW:
+            o.z_stride = p.out_plane_stride ? p.out_plane_stride : plane;
+            o.c_stride = o.z_stride * n_planes;
+            o.px_stride = 1;
+            break;
+        default:
+            o.z_stride = p.out_plane_stride ? p.out_plane_stride : 3 * plane;
+            o.c_stride = 1;
+            o.px_stride = 3;
+    }
+    o.vec4 = o.px_stride == 1 && (p.dst_width % 4) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0 &&
+             (o.z_stride % 4) == 0 && (o.c_stride % 4) == 0;
+    return CVGS_OK;
+}
+
+inline int fill_crop(const cvgs_crop_t& c, const cvgs_pipeline_t& p, int idx, DevCrop& d) {
+    if (!c.data) return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": data is NULL");
+    if (c.width <= 0 || c.height <= 0 || c.width > (1 << 22) || c.height > (1 << 22))
+        return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": size out of range");
+    if (c.pitch < 3 * c.width && c.height > 1)
+        return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": pitch smaller than a row");
+    d.data = static_cast<const uint8_t*>(c.data);
+    d.w = c.width;
+    d.h = c.height;
+    d.pitch = c.pitch;
+    d.pad = 0;
+    resize_geometry(c.width, c.height, p.dst_width, p.dst_height, p.aspect_mode, d);
+    return CVGS_OK;
+}
+
+}  // namespace cvgs

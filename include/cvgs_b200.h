@@ -1,0 +1,195 @@
+/*
+ * cvgs_b200.h -- C-ABI of the B200-native fused image-preprocessing path.
+ *
+ * This is the drop-in boundary for ONE hot path of cvGPUSpeedup / FusedKernelLibrary:
+ *
+ *   batched crop -> bilinear resize -> convertTo/scale -> per-channel mul/sub/div/add
+ *                -> channel reorder (cvtColor) -> planar split           (one kernel launch)
+ *   CircularTensor shift + process                                       (one kernel launch)
+ *
+ * The reference has no FFI: its public surface is header-only C++ templates
+ * (reference include/cvGPUSpeedup.cuh:74-627) whose operation structs are PODs with public
+ * `params` fields.  Every entry point below states which reference interface it replaces;
+ * the header shim in cvgpuspeedup_b200/include/cvGPUSpeedup.cuh maps the reference's
+ * operation-struct chains onto these calls.
+ *
+ * Conventions (same as the reference):
+ *   - caller's thread, caller's stream; launches are asynchronous, nothing is synchronised
+ *     or allocated on the hot call (descriptor staging buffers are created lazily once);
+ *   - all image memory is caller-owned device memory (except CircularTensor, which owns
+ *     its tensors like fk::CircularTensor does);
+ *   - every function returns 0 on success or a non-zero cudaError_t-compatible code; the
+ *     message is available from cvgs_b200_last_error() (thread-local).  The reference
+ *     throws std::runtime_error from gpuErrchk (fkl/.../core/utils/utils.h:42-60); the
+ *     header shim rethrows to keep that behaviour.
+ *
+ * No torch / OpenCV / CUDA types appear in any signature: streams are `void*`
+ * (a cudaStream_t), device pointers are plain pointers.
+ */
+#ifndef CVGS_B200_H_
+#define CVGS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVGS_B200_VERSION 100 /* 0.1.0 */
+
+/* ---- error codes (subset of cudaError_t values so they can be passed through) ---- */
+#define CVGS_OK 0
+#define CVGS_ERR_INVALID_VALUE 1   /* cudaErrorInvalidValue: bad argument / unsupported chain */
+#define CVGS_ERR_NO_DEVICE 100     /* cudaErrorNoDevice */
+#define CVGS_ERR_NOT_SUPPORTED 801 /* cudaErrorNotSupported */
+
+/* ---- pixel types: same numeric values as OpenCV's CV_MAKETYPE(depth, cn) ---- */
+#define CVGS_8UC3 16  /* CV_8UC3  */
+#define CVGS_32FC3 21 /* CV_32FC3 */
+
+/* Aspect-ratio policy of the resize; same numbering as cvGS::AspectRatio
+ * (reference include/cvGPUSpeedup.cuh:32, fkl/.../image_processing/resize.cuh:41). */
+enum cvgs_aspect_ratio {
+    CVGS_PRESERVE_AR = 0,
+    CVGS_IGNORE_AR = 1,
+    CVGS_PRESERVE_AR_RN_EVEN = 2,
+    CVGS_PRESERVE_AR_LEFT = 3
+};
+
+/* Post-resize per-pixel operations, applied in list order (reference
+ * fkl/.../basic_ops/arithmetic.cuh:43-68, cuda_vector.cuh:45-54, cvGPUSpeedup.cuh:131-161). */
+enum cvgs_op_kind {
+    CVGS_OP_MUL = 1,     /* x * v[c]   cvGS::multiply / convertTo(alpha)          */
+    CVGS_OP_SUB = 2,     /* x - v[c]   cvGS::subtract                            */
+    CVGS_OP_DIV = 3,     /* x / v[c]   cvGS::divide   (IEEE-754 correctly rounded) */
+    CVGS_OP_ADD = 4,     /* x + v[c]   cvGS::add / convertTo(alpha, beta)         */
+    CVGS_OP_REORDER = 5  /* out[c] = in[perm[c]]   cvGS::cvtColor<RGB2BGR/BGR2RGB> = {2,1,0} */
+};
+
+/* Floating-point contract:
+ *   CVGS_FP_REFERENCE_FUSED  bit-identical to the reference's fused kernel as nvcc compiles
+ *                            it: a MUL directly followed by ADD/SUB is one FMA.
+ *   CVGS_FP_SEPARATE         every op rounded on its own, i.e. the result of running the
+ *                            OpenCV-CUDA multiply/subtract/divide kernels one after another.
+ * The bilinear interpolation itself is the same in both (1 FMUL + 3 FFMA, see oracle/). */
+enum cvgs_fp_contract { CVGS_FP_REFERENCE_FUSED = 0, CVGS_FP_SEPARATE = 1 };
+
+/* Resize output handed to the op chain:
+ *   CVGS_INTERP_FLOAT     interpolated value stays float (what fk::Interpolate returns).
+ *   CVGS_INTERP_ROUND_U8  value is rounded (RN-even) and saturated to [0,255] first, i.e.
+ *                         cv::cuda::resize on CV_8UC3 followed by convertTo(CV_32F). */
+enum cvgs_interp_mode { CVGS_INTERP_FLOAT = 0, CVGS_INTERP_ROUND_U8 = 1 };
+
+/* Output layouts (reference fkl/.../memory_operations.cuh:168-220, ptr_nd.cuh:53-77). */
+enum cvgs_out_layout {
+    CVGS_OUT_NCHW = 0, /* fk::TensorSplit  : out[z][c][y][x]; cvGS::split(GpuMat, Size)   */
+    CVGS_OUT_CNHW = 1, /* fk::TensorTSplit : out[c][z][y][x]; cvGS::splitT(RawPtr<T3D>)   */
+    CVGS_OUT_NHWC = 2  /* fk::PerThreadWrite<_3D,float3>: packed; cvGS::write(GpuMat,Size) */
+};
+
+/* One source crop = fk::RawPtr<fk::_2D, T> {data, {width, height, pitch}}
+ * (reference fkl/.../core/data/ptr_nd.h:24-60; built by cvGS::gpuMat2RawPtr2D,
+ * include/cvGPUSpeedup.cuh:40-44 from GpuMat::data/cols/rows/step). */
+typedef struct cvgs_crop {
+    const void* data; /* device pointer to the first pixel of the ROI            */
+    int32_t width;    /* pixels                                                   */
+    int32_t height;   /* pixels                                                   */
+    int32_t pitch;    /* bytes between consecutive rows (GpuMat::step)            */
+    int32_t reserved; /* must be 0                                                */
+} cvgs_crop_t;
+
+typedef struct cvgs_op {
+    int32_t kind;    /* enum cvgs_op_kind                                         */
+    int32_t perm[4]; /* CVGS_OP_REORDER only                                      */
+    float v[4];      /* per-channel constant (cv::Scalar cast to float per channel,
+                        reference include/cvGPUSpeedupHelpers.cuh:38-54)          */
+} cvgs_op_t;
+
+#define CVGS_MAX_OPS 8
+
+/* Everything cvGS::executeOperations(stream, resize(...), ops..., split(...)) carries besides
+ * the crops (reference include/cvGPUSpeedup.cuh:218-245 resize, :131-161 ops, :185-202 split). */
+typedef struct cvgs_pipeline {
+    int32_t src_type;    /* CVGS_8UC3                                              */
+    int32_t dst_width;   /* cv::Size dsize of cvGS::resize                         */
+    int32_t dst_height;
+    int32_t aspect_mode; /* enum cvgs_aspect_ratio                                 */
+    int32_t interp_mode; /* enum cvgs_interp_mode                                  */
+    int32_t fp_contract; /* enum cvgs_fp_contract                                  */
+    float background[4]; /* backgroundValue of cvGS::resize: value of inactive planes
+                            (z >= used) and of the bands outside the AR-preserved image;
+                            it still flows through the op chain     */
+    int32_t n_ops;
+    cvgs_op_t ops[CVGS_MAX_OPS];
+    int32_t out_layout; /* enum cvgs_out_layout                                    */
+    int32_t reserved;
+    void* out;                 /* device pointer, float                             */
+    int64_t out_plane_stride;  /* floats between consecutive batch planes z; 0 = tight
+                                  (3*dst_width*dst_height for NCHW/NHWC, dst_width*dst_height
+                                  for CNHW).  The reference ignores GpuMat::step. */
+} cvgs_pipeline_t;
+
+/* ------------------------------------------------------------------------------------------
+ * Library
+ * ------------------------------------------------------------------------------------------ */
+int cvgs_b200_version(void);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* cvgs_b200_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused batch pipeline.  Replaces
+ *   cvGS::executeOperations(stream, cvGS::resize<CV_8UC3, INTER_LINEAR, N, AR>(crops, dsize,
+ *       used, bg), [cvtColor], [multiply], [subtract], [divide], [add], cvGS::split<CV_32FC3>(...))
+ * (reference include/cvGPUSpeedup.cuh:464-473 -> fkl/.../fused_kernel.cuh:22-38 ->
+ *  executors.cuh:123-158 -> data_parallel_patterns.cuh:157-197,256-260).
+ *
+ *   crops       host array of n_planes descriptors (only the first `used` are read)
+ *   n_planes    batch size N of the BatchRead = number of output planes written
+ *   used        usedPlanes: planes z >= used are filled with chain(background)
+ *   stream      cudaStream_t (NULL = legacy default stream)
+ * ------------------------------------------------------------------------------------------ */
+int cvgs_b200_preproc_launch(const cvgs_crop_t* crops, int32_t n_planes, int32_t used,
+                             const cvgs_pipeline_t* pipeline, void* stream);
+
+/* Same pipeline with HOST buffers, for callers that hold frames in (pinned) host memory:
+ * copies the source image to the device, launches, copies the tensor back, all on `stream`
+ * and without synchronising.  Crops are rectangles {x, y, w, h} of the one host image.
+ * `pipeline->out` is ignored; the result goes to host_out (tight layout).
+ * Device staging buffers are owned by the library and reused across calls. */
+typedef struct cvgs_rect { int32_t x, y, width, height; } cvgs_rect_t;
+int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t image_height,
+                           int32_t image_pitch, const cvgs_rect_t* rects, int32_t n_planes,
+                           int32_t used, const cvgs_pipeline_t* pipeline, float* host_out,
+                           void* stream);
+
+/* Kernel-selection override, for tests and profiling: 0 = automatic, 1 = direct-gather kernel,
+ * 2 = TMA-staged kernel.  Returns the previous value. */
+int cvgs_b200_set_kernel_variant(int variant);
+/* Number of kernel launches issued by this library on the calling thread so far. */
+int64_t cvgs_b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * CircularTensor.  Replaces cvGS::CircularTensor<I, O, COLOR_PLANES, BATCH, ORDER, MODE>
+ * (reference include/cvGPUSpeedup.cuh:600-627 over fkl/.../core/data/circular_tensor.cuh:84-151).
+ * data() is a dense, time-ordered float tensor [BATCH][COLOR_PLANES][H][W] (Standard) or
+ * [COLOR_PLANES][BATCH][H][W] (Transposed) that is valid after every update.
+ * ------------------------------------------------------------------------------------------ */
+enum cvgs_ct_order { CVGS_CT_NEWEST_FIRST = 0, CVGS_CT_OLDEST_FIRST = 1 }; /* fk::CircularTensorOrder */
+enum cvgs_ct_planes { CVGS_CT_STANDARD = 0, CVGS_CT_TRANSPOSED = 1 };      /* fk::ColorPlanes        */
+
+/* ctor / Alloc(width, height, deviceID) */
+int cvgs_b200_ct_create(void** handle, int32_t width, int32_t height, int32_t color_planes,
+                        int32_t batch, int32_t order, int32_t plane_mode, int32_t device);
+/* update(stream, frame, ops..., write): runs `pipeline` (its out/out_layout/out_plane_stride
+ * fields are ignored, dst size must equal the tensor plane size) on the new frame, stores it
+ * as the newest plane and shifts the other BATCH-1 planes by one position. */
+int cvgs_b200_ct_update(void* handle, const cvgs_crop_t* frame, const cvgs_pipeline_t* pipeline,
+                        void* stream);
+/* data(): device pointer of the dense tensor (stable for the lifetime of the handle). */
+void* cvgs_b200_ct_data(void* handle);
+int cvgs_b200_ct_destroy(void* handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVGS_B200_H_ */

@@ -1,0 +1,306 @@
+/*
+ * oracle/oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement of the reference's algorithm for the hot path.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library, and only as the checker / CPU baseline -- never as a fallback of
+ * the product path (cvgpuspeedup_b200 fails loudly when its CUDA library is missing).
+ *
+ * Pinning: the arithmetic below was derived from the reference sources cited on each
+ * function AND from the SASS nvcc 12.9 emits for the reference's own fused kernel
+ * (oracle/ref_harness.cu compiled for sm_100a): interpolation = FMUL(p10*w10) then
+ * FFMA(p00,w00), FFMA(p01,w01), FFMA(p11,w11); Mul->Sub contracted to one FFMA; IEEE division.
+ * tests/test_ref_parity.py compares this file bit-for-bit with the reference kernel itself
+ * (oracle/_ref/libfkref_*.so) on a B200, and tests/test_oracle_golden.py checks it against the
+ * known answers the reference's tests hold for this path.
+ *
+ * Build: gcc -O2 -ffp-contract=off -mfma -fopenmp -shared -fPIC (see oracle/Makefile).
+ * -ffp-contract=off + explicit fmaf(): every rounding below is written out.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/cvgs_b200.h"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Geometry of one crop's resize, as stored in fk::ResizeReadParams
+ * (reference fkl/.../image_processing/resize.cuh:43-58). */
+typedef struct oracle_geom {
+    float fx, fy;          /* src_conv_factors                                  */
+    int x1, y1, x2, y2;    /* band that receives the resized image (AR modes)   */
+} oracle_geom_t;
+
+/* cxp::round, reference fkl/.../constexpr_libs/constexpr_cmath.cuh:37-48 (float instance). */
+static float cxp_roundf(float x) {
+    if (x != x || (x == x && x != 0.0f && x + x == x)) return x;
+    return (x > 0.0f) ? (float)(int)(x + 0.5f) : (float)(int)(x - 0.5f);
+}
+
+/* Resize::build (IGNORE_AR) resize.cuh:100-114; AR variants :116-161; compute_target_size :191-216. */
+void oracle_resize_geometry(int src_w, int src_h, int dst_w, int dst_h, int aspect_mode,
+                            oracle_geom_t* g) {
+    if (aspect_mode == CVGS_IGNORE_AR) {
+        const double cfx = (double)dst_w / (double)src_w;
+        const double cfy = (double)dst_h / (double)src_h;
+        g->fx = (float)(1.0 / cfx);
+        g->fy = (float)(1.0 / cfy);
+        g->x1 = 0; g->y1 = 0; g->x2 = dst_w - 1; g->y2 = dst_h - 1;
+        return;
+    }
+    /* compute_target_size */
+    int tw, th;
+    {
+        const float scaleFactor = dst_h / (float)src_h;
+        const int targetHeight = dst_h;
+        const int targetWidth = (int)cxp_roundf(scaleFactor * src_w);
+        if (aspect_mode == CVGS_PRESERVE_AR_RN_EVEN) {
+            const int targetWidthTemp = targetWidth - (targetWidth % 2);
+            if (targetWidthTemp > dst_w) {
+                const float scaleFactorTemp = dst_w / (float)src_w;
+                const int targetHeightTemp = (int)cxp_roundf(scaleFactorTemp * src_h);
+                tw = dst_w; th = targetHeightTemp - (targetHeightTemp % 2);
+            } else {
+                tw = targetWidthTemp; th = targetHeight;
+            }
+        } else {
+            if (targetWidth > dst_w) {
+                const float scaleFactorTemp = dst_w / (float)src_w;
+                tw = dst_w; th = (int)cxp_roundf(scaleFactorTemp * src_h);
+            } else {
+                tw = targetWidth; th = targetHeight;
+            }
+        }
+    }
+    const double cfx = (double)tw / src_w;
+    const double cfy = (double)th / src_h;
+    g->fx = (float)(1.0 / cfx);
+    g->fy = (float)(1.0 / cfy);
+    g->x1 = (aspect_mode == CVGS_PRESERVE_AR_LEFT) ? 0 : (int)((dst_w - tw) / 2);
+    g->y1 = (int)((dst_h - th) / 2);
+    g->x2 = g->x1 + tw - 1;
+    g->y2 = g->y1 + th - 1;
+}
+
+/* SaturateCast<float, uchar> device path: __float2uint_rn then clamp, saturate.cuh:127-147. */
+static float round_sat_u8(float v) {
+    if (!(v > 0.0f)) return 0.0f;          /* negative and NaN -> 0, as cvt.rni.u32.f32 */
+    const float r = nearbyintf(v);         /* default rounding mode = RN-even           */
+    return r > 255.0f ? 255.0f : r;
+}
+
+/* One output pixel of Resize::exec + Interpolate<INTER_LINEAR>::exec
+ * (resize.cuh:70-82,178-189; interpolation.cuh:57-92; PerThreadRead ptr_nd.cuh:41-45).
+ * Rounding sequence = what nvcc emits for the reference kernel (see file header). */
+static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspect_mode,
+                         int x, int y, const float* bg, float out[3]) {
+    if (aspect_mode != CVGS_IGNORE_AR) {
+        if (!(x >= g->x1 && x <= g->x2 && y >= g->y1 && y <= g->y2)) {
+            out[0] = bg[0]; out[1] = bg[1]; out[2] = bg[2];
+            return;
+        }
+        x -= g->x1; y -= g->y1;
+    }
+    const float src_x = (float)x * g->fx;
+    const float src_y = (float)y * g->fy;
+    const int x1 = (int)floorf(src_x);
+    const int y1 = (int)floorf(src_y);
+    const int x2 = x1 + 1, y2 = y1 + 1;
+    const int x2r = x2 < c->width - 1 ? x2 : c->width - 1;
+    const int y2r = y2 < c->height - 1 ? y2 : c->height - 1;
+    const float wx1 = src_x - (float)x1, wx0 = (float)x2 - src_x;
+    const float wy1 = src_y - (float)y1, wy0 = (float)y2 - src_y;
+    const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+    const uint8_t* base = (const uint8_t*)c->data;
+    const uint8_t* r0 = base + (size_t)y1 * (size_t)c->pitch;
+    const uint8_t* r1 = base + (size_t)y2r * (size_t)c->pitch;
+    for (int ch = 0; ch < 3; ++ch) {
+        const float p00 = (float)r0[3 * x1 + ch], p10 = (float)r0[3 * x2r + ch];
+        const float p01 = (float)r1[3 * x1 + ch], p11 = (float)r1[3 * x2r + ch];
+        float t = p10 * w10;
+        t = fmaf(p00, w00, t);
+        t = fmaf(p01, w01, t);
+        t = fmaf(p11, w11, t);
+        out[ch] = t;
+    }
+}
+
+/* Unary/Binary op chain, TransformDPP::operate (data_parallel_patterns.cuh:66-79);
+ * Mul/Sub/Div/Add arithmetic.cuh:43-68; VectorReorder cuda_vector.cuh:45-54. */
+static void apply_chain(const cvgs_pipeline_t* p, float v[3]) {
+    if (p->interp_mode == CVGS_INTERP_ROUND_U8)
+        for (int c = 0; c < 3; ++c) v[c] = round_sat_u8(v[c]);
+    for (int i = 0; i < p->n_ops; ++i) {
+        const cvgs_op_t* op = &p->ops[i];
+        /* nvcc contracts (x*m) -/+ s of the inlined chain into one FMA; a channel reorder in
+         * between is only register renaming and does not prevent it. */
+        if (op->kind == CVGS_OP_MUL && p->fp_contract == CVGS_FP_REFERENCE_FUSED) {
+            int j = i + 1;
+            int perm[3] = {0, 1, 2};
+            while (j < p->n_ops && p->ops[j].kind == CVGS_OP_REORDER) {
+                int np[3];
+                for (int c = 0; c < 3; ++c) np[c] = perm[p->ops[j].perm[c]];
+                memcpy(perm, np, sizeof perm);
+                ++j;
+            }
+            if (j < p->n_ops && (p->ops[j].kind == CVGS_OP_SUB || p->ops[j].kind == CVGS_OP_ADD)) {
+                float t[3];
+                for (int c = 0; c < 3; ++c) {
+                    const int s = perm[c];
+                    const float a = p->ops[j].kind == CVGS_OP_SUB ? -p->ops[j].v[c] : p->ops[j].v[c];
+                    t[c] = fmaf(v[s], op->v[s], a);
+                }
+                memcpy(v, t, sizeof t);
+                i = j;
+                continue;
+            }
+        }
+        switch (op->kind) {
+            case CVGS_OP_MUL: for (int c = 0; c < 3; ++c) v[c] = v[c] * op->v[c]; break;
+            case CVGS_OP_SUB: for (int c = 0; c < 3; ++c) v[c] = v[c] - op->v[c]; break;
+            case CVGS_OP_DIV: for (int c = 0; c < 3; ++c) v[c] = v[c] / op->v[c]; break;
+            case CVGS_OP_ADD: for (int c = 0; c < 3; ++c) v[c] = v[c] + op->v[c]; break;
+            case CVGS_OP_REORDER: {
+                const float t[3] = {v[op->perm[0]], v[op->perm[1]], v[op->perm[2]]};
+                memcpy(v, t, sizeof t);
+                break;
+            }
+            default: break;
+        }
+    }
+}
+
+/* Output addressing: TensorSplit memory_operations.cuh:168-188 + PtrAccessor<_3D> ptr_nd.cuh:53-63;
+ * TensorTSplit :197-220 + PtrAccessor<T3D> ptr_nd.cuh:65-77; PerThreadWrite<_3D>. */
+static void store_pixel(const cvgs_pipeline_t* p, int n_planes, int z, int y, int x, const float v[3]) {
+    float* out = (float*)p->out;
+    const int64_t W = p->dst_width, H = p->dst_height;
+    switch (p->out_layout) {
+        case CVGS_OUT_NCHW: {
+            const int64_t ps = p->out_plane_stride ? p->out_plane_stride : 3 * W * H;
+            float* b = out + z * ps + y * W + x;
+            b[0] = v[0]; b[W * H] = v[1]; b[2 * W * H] = v[2];
+            break;
+        }
+        case CVGS_OUT_CNHW: {
+            const int64_t ps = p->out_plane_stride ? p->out_plane_stride : W * H;
+            float* b = out + z * ps + y * W + x;
+            b[0] = v[0]; b[ps * n_planes] = v[1]; b[2 * ps * n_planes] = v[2];
+            break;
+        }
+        default: {
+            const int64_t ps = p->out_plane_stride ? p->out_plane_stride : 3 * W * H;
+            float* b = out + z * ps + (y * W + x) * 3;
+            b[0] = v[0]; b[1] = v[1]; b[2] = v[2];
+        }
+    }
+}
+
+/* The whole fused call: BatchRead<N, CONDITIONAL_WITH_DEFAULT>::exec (batch_operations.cuh:222-229)
+ * -> chain -> write, for every (x, y, z) of ActiveThreads{dst_w, dst_h, N}.
+ * All pointers are HOST pointers here.  nthreads <= 0 -> all cores. Returns 0 / 1 (bad args). */
+int oracle_preproc(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_pipeline_t* p,
+                   int nthreads) {
+    if (!crops || !p || !p->out || n_planes <= 0 || used < 0 || p->src_type != CVGS_8UC3 ||
+        p->dst_width <= 0 || p->dst_height <= 0 || p->n_ops < 0 || p->n_ops > CVGS_MAX_OPS)
+        return 1;
+    if (used > n_planes) used = n_planes;
+    oracle_geom_t* geoms = (oracle_geom_t*)calloc((size_t)n_planes, sizeof(oracle_geom_t));
+    for (int z = 0; z < used; ++z)
+        oracle_resize_geometry(crops[z].width, crops[z].height, p->dst_width, p->dst_height,
+                               p->aspect_mode, &geoms[z]);
+    const int H = p->dst_height, W = p->dst_width;
+    const long total_rows = (long)n_planes * H;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 8) num_threads(nthreads)
+#endif
+    for (long row = 0; row < total_rows; ++row) {
+        const int z = (int)(row / H), y = (int)(row % H);
+        for (int x = 0; x < W; ++x) {
+            float v[3];
+            if (z >= used) {
+                v[0] = p->background[0]; v[1] = p->background[1]; v[2] = p->background[2];
+            } else {
+                resize_pixel(&crops[z], &geoms[z], p->aspect_mode, x, y, p->background, v);
+            }
+            apply_chain(p, v);
+            store_pixel(p, n_planes, z, y, x, v);
+        }
+    }
+    free(geoms);
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * CircularTensor state machine: fk::CircularTensor::update (circular_tensor.cuh:111-146),
+ * SequenceSelectorType (:26-35), computeCircularThreadIdx (memory_operations.cuh:388-399).
+ * Host memory; planes are [batch][color][H][W] (Standard) or [color][batch][H][W] (Transposed).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct oracle_ct {
+    int w, h, cp, batch, order, mode, next;
+    float* pub;  /* `this` tensor  */
+    float* tmp;  /* m_tempTensor   */
+} oracle_ct_t;
+
+oracle_ct_t* oracle_ct_create(int w, int h, int cp, int batch, int order, int mode) {
+    oracle_ct_t* t = (oracle_ct_t*)calloc(1, sizeof *t);
+    t->w = w; t->h = h; t->cp = cp; t->batch = batch; t->order = order; t->mode = mode;
+    const size_t n = (size_t)w * h * cp * batch;
+    t->pub = (float*)calloc(n, sizeof(float));
+    t->tmp = (float*)calloc(n, sizeof(float));
+    return t;
+}
+void oracle_ct_destroy(oracle_ct_t* t) { if (t) { free(t->pub); free(t->tmp); free(t); } }
+float* oracle_ct_data(oracle_ct_t* t) { return t->pub; }
+/* Lets a test preload the public tensor like the reference tests do (setTo(10.0f), :188-195). */
+float* oracle_ct_temp(oracle_ct_t* t) { return t->tmp; }
+
+static float* ct_plane(const oracle_ct_t* t, float* base, int z, int c) {
+    const size_t px = (size_t)t->w * t->h;
+    return t->mode == CVGS_CT_STANDARD ? base + ((size_t)z * t->cp + c) * px
+                                       : base + ((size_t)c * t->batch + z) * px;
+}
+
+int oracle_ct_update(oracle_ct_t* t, const cvgs_crop_t* frame, const cvgs_pipeline_t* p_in, int nthreads) {
+    if (!t || !frame || !p_in || p_in->dst_width != t->w || p_in->dst_height != t->h || t->cp != 3) return 1;
+    const size_t px = (size_t)t->w * t->h;
+    float* fresh = (float*)malloc(px * 3 * sizeof(float));
+    cvgs_pipeline_t p = *p_in;
+    p.out = fresh; p.out_layout = CVGS_OUT_NCHW; p.out_plane_stride = 0;
+    const int rc = oracle_preproc(frame, 1, 1, &p, nthreads);
+    if (rc) { free(fresh); return rc; }
+    const int B = t->batch, first = t->next;
+    const int upd = t->order == CVGS_CT_NEWEST_FIRST ? 0 : B - 1;
+    for (int c = 0; c < 3; ++c) {
+        /* update sequence: MidWrite CircularTensorWrite<Ascendent> -> temp[(upd + first) mod B],
+         * then the user's write -> this[upd]. */
+        int zt = upd + first; if (zt >= B) zt -= B;
+        memcpy(ct_plane(t, t->tmp, zt, c), fresh + c * px, px * sizeof(float));
+        memcpy(ct_plane(t, t->pub, upd, c), fresh + c * px, px * sizeof(float));
+        /* copy sequence for every other plane z. */
+        for (int z = 0; z < B; ++z) {
+            if (z == upd) continue;
+            int zs;
+            if (t->order == CVGS_CT_NEWEST_FIRST) { zs = first - z; if (zs < 0) zs += B; }
+            else { zs = z + first; if (zs >= B) zs -= B; }
+            memcpy(ct_plane(t, t->pub, z, c), ct_plane(t, t->tmp, zs, c), px * sizeof(float));
+        }
+    }
+    t->next = (first + 1) % B;
+    free(fresh);
+    return 0;
+}
+
+int oracle_has_fma(void) { return __builtin_cpu_supports("fma") ? 1 : 0; }
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

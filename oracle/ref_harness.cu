@@ -1,0 +1,125 @@
+// oracle/ref_harness.cu -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// A thin extern "C" driver that CALLS the unmodified reference library
+// (FusedKernelLibrary headers under /root/reference/fkl/include, found through
+// -I at build time; nothing is copied into this repo) so that
+//   * tests can compare the B200 kernels bit-for-bit with the reference's own
+//     fused kernel on the same inputs (oracle/_ref/libfkref.so), and
+//   * bench.py can time "the kernel to beat" on the same box.
+//
+// The call sequence mirrors benchmarks/benchmark_CPUandGPU_cvGS_vs_fk.cu:124-139
+// (PerThreadRead::build_batch -> Resize::build_batch -> BatchRead::build ->
+// fk::executeOperations(..., ColorConversion, Mul, Sub, Div, TensorSplit)) and
+// tests/batchread/test_circularbatchread_x_write3D.cu:185-203 (CircularTensor).
+//
+// The reference fixes batch size, aspect-ratio mode and the op chain at compile
+// time, so only the few instantiations listed at the bottom exist.
+#include <array>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include <fused_kernel/fused_kernel.cuh>
+#include <fused_kernel/core/data/circular_tensor.cuh>
+#include <fused_kernel/algorithms/image_processing/resize.cuh>
+#include <fused_kernel/algorithms/image_processing/color_conversion.cuh>
+#include <fused_kernel/algorithms/image_processing/saturate.cuh>
+#include <fused_kernel/algorithms/basic_ops/arithmetic.cuh>
+
+#ifndef FKREF_BATCH
+#define FKREF_BATCH 16
+#endif
+
+namespace {
+
+thread_local std::string g_err;
+
+struct CropIn { const void* data; int w, h, pitch; };
+
+template <int BATCH, fk::AspectRatio AR, bool SWAP>
+int run_chain(const void* const* ptrs, const int* ws, const int* hs, const int* pitches,
+              int used, int dst_w, int dst_h, const float* bg,
+              const float* mul, const float* sub, const float* div,
+              float* out, cudaStream_t stream) {
+    using PixelReadOp = fk::PerThreadRead<fk::_2D, uchar3>;
+    std::array<fk::RawPtr<fk::_2D, uchar3>, BATCH> crops{};
+    for (int i = 0; i < BATCH; ++i) {
+        const int j = i < used ? i : 0;  // unused slots still need a valid descriptor
+        crops[i] = fk::RawPtr<fk::_2D, uchar3>{ (uchar3*)ptrs[j],
+            { (uint)ws[j], (uint)hs[j], (uint)pitches[j] } };
+    }
+    const fk::Size dsize{ dst_w, dst_h };
+    const float3 bgv{ bg[0], bg[1], bg[2] };
+    const auto readOP = PixelReadOp::build_batch(crops);
+    const auto sizeArr = fk::make_set_std_array<BATCH>(dsize);
+    using Resize = fk::Resize<fk::INTER_LINEAR, AR, fk::Read<PixelReadOp>>;
+    const fk::Tensor<float> t_out(out, dst_w, dst_h, BATCH, 3);
+    const auto mulOp = fk::Binary<fk::Mul<float3>>{ float3{mul[0], mul[1], mul[2]} };
+    const auto subOp = fk::Binary<fk::Sub<float3>>{ float3{sub[0], sub[1], sub[2]} };
+    const auto divOp = fk::Binary<fk::Div<float3>>{ float3{div[0], div[1], div[2]} };
+    const auto wrOp = fk::Write<fk::TensorSplit<float3>>{ t_out.ptr() };
+    auto launch = [&](const auto& resizeOp) {
+        if constexpr (SWAP) {
+            fk::executeOperations(stream, resizeOp,
+                fk::Unary<fk::ColorConversion<fk::COLOR_RGB2BGR, float3, float3>>{},
+                mulOp, subOp, divOp, wrOp);
+        } else {
+            fk::executeOperations(stream, resizeOp, mulOp, subOp, divOp, wrOp);
+        }
+    };
+    if constexpr (AR == fk::IGNORE_AR) {
+        const auto resizeDFs = Resize::build_batch(readOP, sizeArr);
+        launch(fk::BatchRead<BATCH, fk::CONDITIONAL_WITH_DEFAULT>::build(resizeDFs, used, bgv));
+    } else {
+        const auto bgArr = fk::make_set_std_array<BATCH>(bgv);
+        const auto resizeDFs = Resize::build_batch(readOP, sizeArr, bgArr);
+        launch(fk::BatchRead<BATCH, fk::CONDITIONAL_WITH_DEFAULT>::build(resizeDFs, used, bgv));
+    }
+    return 0;
+}
+
+template <int BATCH>
+int dispatch(const void* const* ptrs, const int* ws, const int* hs, const int* pitches,
+             int used, int dst_w, int dst_h, int ar, const float* bg, int swap,
+             const float* mul, const float* sub, const float* div, float* out, cudaStream_t s) {
+#define FKREF_CASE(ARV, SW) \
+    if (ar == (int)ARV && swap == SW) \
+        return run_chain<BATCH, ARV, SW != 0>(ptrs, ws, hs, pitches, used, dst_w, dst_h, bg, mul, sub, div, out, s);
+    FKREF_CASE(fk::IGNORE_AR, 0) FKREF_CASE(fk::IGNORE_AR, 1)
+#ifdef FKREF_ALL_AR
+    FKREF_CASE(fk::PRESERVE_AR, 0) FKREF_CASE(fk::PRESERVE_AR, 1)
+    FKREF_CASE(fk::PRESERVE_AR_RN_EVEN, 0) FKREF_CASE(fk::PRESERVE_AR_RN_EVEN, 1)
+    FKREF_CASE(fk::PRESERVE_AR_LEFT, 0) FKREF_CASE(fk::PRESERVE_AR_LEFT, 1)
+#endif
+#undef FKREF_CASE
+    g_err = "fkref: unsupported (aspect mode, swap) combination in this build";
+    return -1;
+}
+
+}  // namespace
+
+#define FKREF_CAT_(a, b) a##b
+#define FKREF_CAT(a, b) FKREF_CAT_(a, b)
+
+extern "C" {
+
+// Batch size this translation unit was compiled for (a template parameter in the reference).
+int FKREF_CAT(fkref_batch_, FKREF_BATCH)(void) { return FKREF_BATCH; }
+
+// resize(bilinear) -> [RGB2BGR] -> Mul -> Sub -> Div -> TensorSplit; `out` must hold FKREF_BATCH planes.
+// Asynchronous on `stream`, like the reference. Returns 0, or -1 with fkref_last_error set.
+int FKREF_CAT(fkref_preproc_, FKREF_BATCH)(const void* const* ptrs, const int* ws, const int* hs, const int* pitches,
+                  int used, int dst_w, int dst_h, int aspect_mode, const float* bg, int swap_rb,
+                  const float* mul, const float* sub, const float* div, float* out, void* stream) {
+    try {
+        return dispatch<FKREF_BATCH>(ptrs, ws, hs, pitches, used, dst_w, dst_h, aspect_mode, bg, swap_rb,
+                                     mul, sub, div, out, (cudaStream_t)stream);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+const char* FKREF_CAT(fkref_last_error_, FKREF_BATCH)(void) { return g_err.c_str(); }
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+"""GPU-side test helpers: run the product through its C-ABI, and run the reference's real kernel
+(oracle/_ref/libfkref_N.so, built from /root/reference by oracle/Makefile) for bit-exact comparison."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from cvgpuspeedup_b200 import _abi
+from tests import util
+
+ROOT = util.ROOT
+
+
+def device_image(image: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(image).cuda()
+
+
+def run_cvgs(image, rects, dsize, ops, n_planes=None, used=None, variant=0, fill=float("nan"), d_image=None,
+             **pipe_kw) -> np.ndarray:
+    """One cvgs_b200_preproc_launch on cuda:0; returns the output tensor as numpy."""
+    lib = _abi.load()
+    n_planes = len(rects) if n_planes is None else n_planes
+    used = len(rects) if used is None else used
+    layout = pipe_kw.get("layout", _abi.OUT_NCHW)
+    d_img = device_image(image) if d_image is None else d_image
+    shape = util.out_shape(n_planes, dsize, layout, pipe_kw.get("plane_stride", 0))
+    d_out = torch.full(shape, fill, dtype=torch.float32, device="cuda")
+    p = util.make_pipeline(dsize, ops, out_ptr=d_out.data_ptr(), **pipe_kw)
+    crops = util.host_crops(image, rects[:used], base_ptr=d_img.data_ptr())
+    prev = lib.cvgs_b200_set_kernel_variant(variant)
+    try:
+        _abi.check(lib.cvgs_b200_preproc_launch(crops, n_planes, used, C.byref(p),
+                                                torch.cuda.current_stream().cuda_stream))
+    finally:
+        lib.cvgs_b200_set_kernel_variant(prev)
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()
+
+
+_FKREF = {}
+
+
+def fkref_lib(batch: int):
+    if batch not in _FKREF:
+        path = os.path.join(ROOT, "oracle", "_ref", f"libfkref_{batch}.so")
+        if not os.path.exists(path):
+            return None
+        lib = C.CDLL(path)
+        fn = getattr(lib, f"fkref_preproc_{batch}")
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                       C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float),
+                       C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+        err = getattr(lib, f"fkref_last_error_{batch}")
+        err.restype = C.c_char_p
+        _FKREF[batch] = (fn, err)
+    return _FKREF[batch]
+
+
+def fkref_args(d_img_ptr, pitch, rects, used):
+    n = max(1, used)
+    ptrs = (C.c_void_p * n)(*[d_img_ptr + y * pitch + 3 * x for (x, y, w, h) in rects[:used]])
+    ws = (C.c_int * n)(*[r[2] for r in rects[:used]])
+    hs = (C.c_int * n)(*[r[3] for r in rects[:used]])
+    ps = (C.c_int * n)(*[pitch] * used)
+    return ptrs, ws, hs, ps
+
+
+def run_fkref(image, rects, dsize, swap, mul, sub, div, aspect=_abi.IGNORE_AR, bg=(0, 0, 0), batch=16, used=None,
+              d_image=None) -> np.ndarray:
+    """The reference's own fused kernel: resize -> [RGB2BGR] -> Mul -> Sub -> Div -> TensorSplit, BATCH = batch
+    (a template parameter there).  Returns [batch, 3, H, W]."""
+    lib = fkref_lib(batch)
+    assert lib is not None, "oracle/_ref not built"
+    fn, err = lib
+    used = len(rects) if used is None else used
+    assert used <= batch
+    d_img = device_image(image) if d_image is None else d_image
+    d_out = torch.full((batch, 3, dsize[1], dsize[0]), float("nan"), dtype=torch.float32, device="cuda")
+    ptrs, ws, hs, ps = fkref_args(d_img.data_ptr(), image.shape[1], rects, used)
+    f3 = lambda v: (C.c_float * 3)(*v)  # noqa: E731
+    rc = fn(ptrs, ws, hs, ps, used, dsize[0], dsize[1], aspect, f3(bg), int(swap), f3(mul), f3(sub), f3(div),
+            d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, err().decode()
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()

@@ -1,0 +1,71 @@
+"""CircularTensor update kernel vs the oracle state machine and the reference's known answers."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from cvgpuspeedup_b200 import _abi
+import cvgpuspeedup_b200 as cvgs
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("order,expect", [(_abi.CT_NEWEST_FIRST, lambda z: 100 - z),
+                                          (_abi.CT_OLDEST_FIRST, lambda z: 100 - (15 - z - 1))])
+@pytest.mark.parametrize("mode", [_abi.CT_STANDARD, _abi.CT_TRANSPOSED])
+def test_known_answer_after_100_updates(order, expect, mode):
+    """tests/batchread/test_circularbatchread_x_write3D.cu:176-270,333-460: 128x128, BATCH 15, 100 updates with
+    frame value i+1; plane z == 100-z (NewestFirst) / 100-(15-z-1) (OldestFirst)."""
+    ct = cvgs.CircularTensor(128, 128, 15, order, mode)
+    frame = torch.empty((128, 128, 3), dtype=torch.uint8, device="cuda")
+    for i in range(100):
+        frame.fill_(i + 1)
+        ct.update(None, cvgs.GpuMat.from_tensor(frame))
+    torch.cuda.synchronize()
+    data = ct.data().cpu().numpy()
+    if mode == _abi.CT_TRANSPOSED:
+        data = data.swapaxes(0, 1)
+    for z in range(15):
+        assert np.all(data[z] == expect(z)), z
+    ct.close()
+
+
+@pytest.mark.parametrize("order", [_abi.CT_NEWEST_FIRST, _abi.CT_OLDEST_FIRST])
+@pytest.mark.parametrize("mode", [_abi.CT_STANDARD, _abi.CT_TRANSPOSED])
+@pytest.mark.parametrize("shape", [((96, 64), (200, 120)), ((33, 17), (33, 17)), ((64, 36), (192, 108))])
+def test_matches_oracle_with_resize_chain(order, mode, shape):
+    """BASELINE config 4 in miniature: random frames, resize + normalise on the new frame, depth 5."""
+    (W, H), (fw, fh) = shape
+    B = 5
+    lib = util.oracle_lib()
+    o = lib.oracle_ct_create(W, H, 3, B, order, mode)
+    ct = cvgs.CircularTensor(W, H, B, order, mode)
+    rng = np.random.default_rng(4)
+    p = util.make_pipeline((W, H), util.OPS_C3)
+    ops = [cvgs.cvtColor(), cvgs.multiply((1 / 255.0,) * 3), cvgs.subtract(util._MEAN), cvgs.divide(util._STD)]
+    for i in range(2 * B + 3):
+        img = util.make_image(rng, fw, fh)
+        assert lib.oracle_ct_update(o, util.host_crops(img, [(0, 0, fw, fh)]), C.byref(p), 0) == 0
+        d = torch.from_numpy(img).cuda().view(fh, fw, 3)
+        ct.update(None, cvgs.GpuMat.from_tensor(d), *ops)
+        torch.cuda.synchronize()
+        want = np.ctypeslib.as_array(lib.oracle_ct_data(o), shape=(B * 3 * H * W,))
+        got = ct.data().cpu().numpy().reshape(-1)
+        util.assert_bit_equal(got, want, f"update {i}")
+    lib.oracle_ct_destroy(o)
+    ct.close()
+
+
+def test_errors():
+    lib = _abi.load()
+    h = C.c_void_p()
+    assert lib.cvgs_b200_ct_create(C.byref(h), 0, 10, 3, 4, 0, 0, 0) == 1
+    assert lib.cvgs_b200_ct_create(C.byref(h), 16, 16, 4, 4, 0, 0, 0) == 801
+    ct = cvgs.CircularTensor(16, 16, 3)
+    frame = torch.zeros((16, 16, 3), dtype=torch.uint8, device="cuda")
+    p = util.make_pipeline((8, 8), [])
+    crop = util.host_crops(np.zeros((16, 48), np.uint8), [(0, 0, 16, 16)], base_ptr=frame.data_ptr())
+    assert lib.cvgs_b200_ct_update(ct._h, crop, C.byref(p), None) == 1  # wrong destination size
+    ct.close()

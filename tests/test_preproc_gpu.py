@@ -1,0 +1,182 @@
+"""GPU parity tests: the sm_100a kernels (through the C-ABI) against the CPU oracle, bit for bit.
+
+Float results are compared bit-exactly (0 ULP): BASELINE.json asks for <= 1 ULP against the
+OpenCV-CUDA chain; the kernels reproduce the stated rounding sequence exactly, so the tests demand 0.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from cvgpuspeedup_b200 import _abi
+from tests import gpu_util, util
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [1, 0]  # 1 = direct-gather kernel, 0 = automatic (TMA-staged when the input allows)
+
+
+def _check(w: util.Workload, variant, n_planes=None, used=None, **kw):
+    got = gpu_util.run_cvgs(w.image, w.rects, w.dsize, w.ops, n_planes=n_planes, used=used, variant=variant,
+                            aspect=w.aspect, background=w.background, **kw)
+    want = util.run_oracle(w.image, w.rects, w.dsize, w.ops, n_planes=n_planes, used=used, aspect=w.aspect,
+                           background=w.background, **kw)
+    util.assert_bit_equal(got, want, f"{w.name} variant={variant} {kw}")
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("smooth", [False, True])
+def test_c1_single_crop(variant, smooth):
+    _check(util.workload_c1(smooth=smooth), variant)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("pitch", [6144, 5760])
+@pytest.mark.parametrize("ref_shape", [False, True])
+def test_c2_fifty_crops(variant, pitch, ref_shape):
+    _check(util.workload_c2(pitch=pitch, ref_shape=ref_shape), variant)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_c3_imagenet_batch(variant):
+    # 96 of the 256 crops keep the oracle's runtime at a few seconds; the full batch is covered by
+    # test_full_size_properties
+    _check(util.workload_c3(n=96), variant)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("fp", [_abi.FP_REFERENCE_FUSED, _abi.FP_SEPARATE])
+@pytest.mark.parametrize("interp", [_abi.INTERP_FLOAT, _abi.INTERP_ROUND_U8])
+def test_fp_and_interp_modes(variant, fp, interp):
+    _check(util.workload_c2(n=12, frame=(640, 480), pitch=2048), variant, fp_contract=fp, interp_mode=interp)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("aspect", [_abi.PRESERVE_AR, _abi.PRESERVE_AR_RN_EVEN, _abi.PRESERVE_AR_LEFT])
+def test_aspect_ratio_modes(variant, aspect):
+    rng = np.random.default_rng(5)
+    img = util.make_image(rng, 400, 300, pitch=1280)
+    rects = [(i, i, 30, 120) for i in range(8)] + [(0, 0, 400, 300), (10, 10, 17, 200), (3, 3, 300, 9)]
+    w = util.Workload("ar", img, 400, 300, rects, (64, 128), util.OPS_C2, aspect=aspect,
+                      background=(128.0, 128.0, 128.0))
+    _check(w, variant)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("layout", [_abi.OUT_NCHW, _abi.OUT_CNHW, _abi.OUT_NHWC])
+def test_output_layouts(variant, layout):
+    _check(util.workload_c2(n=9, frame=(640, 480), pitch=1920), variant, layout=layout)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_padded_plane_stride(variant):
+    """explicit batch stride (the reference silently assumes tight)."""
+    w = util.workload_c2(n=5, frame=(320, 240), pitch=960)
+    _check(w, variant, plane_stride=3 * 64 * 128 + 20)
+    _check(w, variant, plane_stride=64 * 128 + 8, layout=_abi.OUT_CNHW)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_unused_planes_get_chain_of_background(variant):
+    """planes z >= usedPlanes are written with chain(background), not skipped."""
+    w = util.workload_c2(n=6, frame=(320, 240), pitch=960)
+    w.background = (3.0, 200.0, 77.5)
+    _check(w, variant, n_planes=10, used=4)
+    _check(w, variant, n_planes=3, used=0)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("dsize", [(63, 17), (1, 1), (5, 300), (130, 2), (224, 224), (66, 66)])
+def test_ragged_destination_sizes(variant, dsize):
+    rng = np.random.default_rng(7)
+    img = util.make_image(rng, 333, 211, pitch=1003)  # odd pitch: rows at every byte alignment
+    rects = [(0, 0, 333, 211), (1, 1, 1, 1), (332, 210, 1, 1), (0, 0, 2, 2), (7, 9, 100, 3), (300, 5, 33, 200),
+             (10, 10, 64, 128), (11, 12, 65, 129)]
+    w = util.Workload("ragged", img, 333, 211, rects, dsize, util.OPS_C1)
+    _check(w, variant)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_right_and_bottom_edge_clamp(variant):
+    """x2_read/y2_read clamping (interpolation.cuh:72-74) on crops that end at the last byte of the
+    allocation: up-scaling makes the last columns/rows tap beyond the crop."""
+    rng = np.random.default_rng(8)
+    img = util.make_image(rng, 48, 40)
+    rects = [(0, 0, 48, 40), (40, 30, 8, 10), (47, 39, 1, 1), (45, 0, 3, 40), (0, 37, 48, 3)]
+    w = util.Workload("edge", img, 48, 40, rects, (96, 100), util.OPS_C1)
+    _check(w, variant)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_chain_shapes(variant):
+    w = util.workload_c2(n=4, frame=(320, 240), pitch=960)
+    chains = [[], [("div", (255.0,) * 3)], [("add", (1.5, 2.5, 3.5)), ("mul", (2.0, 3.0, 4.0))],
+              [("mul", (0.5,) * 3), ("reorder", (2, 1, 0)), ("sub", (1.0, 2.0, 3.0))],
+              [("reorder", (1, 2, 0)), ("mul", (0.25, 0.5, 2.0)), ("add", (1.0, 2.0, 3.0)), ("add", (0.1, 0.2, 0.3)),
+               ("div", (3.0, 7.0, 0.1)), ("reorder", (2, 0, 1)), ("sub", (5.0, 6.0, 7.0)), ("mul", (1.1, 1.2, 1.3))]]
+    for ops in chains:
+        w.ops = ops
+        _check(w, variant)
+        _check(w, variant, fp_contract=_abi.FP_SEPARATE)
+
+
+def test_large_batch_uses_descriptor_ring():
+    """More crops than fit the kernel parameters (64): descriptors go through the pinned staging ring."""
+    w = util.workload_c2(n=300, frame=(640, 480), pitch=1920)
+    w.dsize = (32, 48)
+    for variant in VARIANTS:
+        for _ in range(3):  # reuse of ring slots
+            _check(w, variant)
+
+
+def test_full_size_properties():
+    """BASELINE configs 2/3 at full size through size-independent properties: (1) both kernels agree bit for
+    bit, (2) the result does not depend on how the batch is split into launches (planes are independent),
+    (3) linearity of the chain: doubling mul/sub doubles the output exactly (power-of-two scaling)."""
+    w = util.workload_c3(n=256)
+    d_img = gpu_util.device_image(w.image)
+    a = gpu_util.run_cvgs(w.image, w.rects, w.dsize, w.ops, variant=1, d_image=d_img)
+    b = gpu_util.run_cvgs(w.image, w.rects, w.dsize, w.ops, variant=0, d_image=d_img)
+    util.assert_bit_equal(a, b, "direct vs auto kernel, 256 crops")
+    parts = [gpu_util.run_cvgs(w.image, w.rects[i:i + 50], w.dsize, w.ops, d_image=d_img) for i in range(0, 256, 50)]
+    util.assert_bit_equal(np.concatenate(parts), b, "batch split invariance")
+    ops2 = [("reorder", (2, 1, 0)), ("mul", tuple(2 * v for v in (1 / 255.0,) * 3)),
+            ("sub", tuple(2 * v for v in util._MEAN)), ("div", util._STD)]
+    c = gpu_util.run_cvgs(w.image, w.rects, w.dsize, ops2, d_image=d_img)
+    util.assert_bit_equal(c, 2 * b, "exact scaling by 2")
+    # spot-check 8 planes of the full batch against the oracle
+    idx = [0, 1, 37, 100, 128, 200, 254, 255]
+    want = util.run_oracle(w.image, [w.rects[i] for i in idx], w.dsize, w.ops)
+    util.assert_bit_equal(b[idx], want, "oracle spot check")
+
+
+def test_error_behaviour():
+    """Bad arguments come back as error codes + message (the shim rethrows, like gpuErrchk)."""
+    lib = _abi.load()
+    p = util.make_pipeline((64, 128), [], out_ptr=0)
+    crops = (_abi.Crop * 1)()
+    assert lib.cvgs_b200_preproc_launch(crops, 1, 1, C.byref(p), None) == 1
+    assert b"output" in lib.cvgs_b200_last_error()
+    d_out = torch.zeros(3 * 64 * 128, device="cuda")
+    p = util.make_pipeline((64, 128), [], out_ptr=d_out.data_ptr())
+    assert lib.cvgs_b200_preproc_launch(crops, 1, 1, C.byref(p), None) == 1  # crop.data == NULL
+    assert b"crop 0" in lib.cvgs_b200_last_error()
+    p.src_type = 0
+    assert lib.cvgs_b200_preproc_launch(crops, 1, 1, C.byref(p), None) == 801
+
+
+def test_host_buffer_entry_point():
+    """cvgs_b200_preproc_host: pinned host frame in, host tensor out, copies on the caller's stream."""
+    lib = _abi.load()
+    w = util.workload_c2(n=20, frame=(640, 480), pitch=1920)
+    h_img = torch.from_numpy(w.image).pin_memory()
+    h_out = torch.empty((20, 3, 128, 64), dtype=torch.float32).pin_memory()
+    rects = (_abi.Rect * 20)(*[_abi.Rect(*r) for r in w.rects])
+    p = util.make_pipeline(w.dsize, w.ops)
+    for _ in range(2):
+        h_out.fill_(float("nan"))
+        _abi.check(lib.cvgs_b200_preproc_host(h_img.data_ptr(), 640, 480, 1920, rects, 20, 20, C.byref(p),
+                                              h_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        util.assert_bit_equal(h_out.numpy(), util.run_oracle(w.image, w.rects, w.dsize, w.ops), "host entry point")
