@@ -53,6 +53,13 @@ SYMBOLS = {
     "cvgs_b200_preproc_launch": (C.c_int, [C.POINTER(Crop), C.c_int32, C.c_int32, C.POINTER(Pipeline), C.c_void_p]),
     "cvgs_b200_preproc_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Rect), C.c_int32,
                                          C.c_int32, C.POINTER(Pipeline), C.c_void_p, C.c_void_p]),
+    "cvgs_b200_preproc_launch_sequence": (C.c_int, [C.POINTER(C.POINTER(Crop)), C.POINTER(C.c_int32),
+                                                    C.POINTER(C.c_int32), C.POINTER(C.POINTER(Pipeline)), C.c_int32,
+                                                    C.c_int32, C.c_void_p]),
+    "cvgs_b200_preproc_host_sequence": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32,
+                                                  C.POINTER(C.POINTER(Rect)), C.POINTER(C.c_int32),
+                                                  C.POINTER(C.c_int32), C.POINTER(C.POINTER(Pipeline)),
+                                                  C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p]),
     "cvgs_b200_set_kernel_variant": (C.c_int, [C.c_int]),
     "cvgs_b200_launch_count": (C.c_int64, []),
     "cvgs_b200_ct_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

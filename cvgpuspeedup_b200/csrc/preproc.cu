@@ -316,4 +316,31 @@ int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t 
     return CVGS_OK;
 }
 
+int cvgs_b200_preproc_launch_sequence(const cvgs_crop_t* const* crops, const int32_t* n_planes, const int32_t* used,
+                                      const cvgs_pipeline_t* const* pipelines, int32_t n_sets, int32_t steps,
+                                      void* stream) {
+    if (!crops || !n_planes || !used || !pipelines || n_sets <= 0 || steps < 0)
+        return fail(CVGS_ERR_INVALID_VALUE, "bad sequence arguments");
+    for (int i = 0; i < steps; ++i) {
+        const int s = i % n_sets;
+        if (int rc = cvgs_b200_preproc_launch(crops[s], n_planes[s], used[s], pipelines[s], stream)) return rc;
+    }
+    return CVGS_OK;
+}
+
+int cvgs_b200_preproc_host_sequence(const void* const* host_images, int32_t image_width, int32_t image_height,
+                                    int32_t image_pitch, const cvgs_rect_t* const* rects, const int32_t* n_planes,
+                                    const int32_t* used, const cvgs_pipeline_t* const* pipelines,
+                                    float* const* host_outs, int32_t n_sets, int32_t steps, void* stream) {
+    if (!host_images || !rects || !n_planes || !used || !pipelines || !host_outs || n_sets <= 0 || steps < 0)
+        return fail(CVGS_ERR_INVALID_VALUE, "bad sequence arguments");
+    for (int i = 0; i < steps; ++i) {
+        const int s = i % n_sets;
+        if (int rc = cvgs_b200_preproc_host(host_images[s], image_width, image_height, image_pitch, rects[s],
+                                            n_planes[s], used[s], pipelines[s], host_outs[s], stream))
+            return rc;
+    }
+    return CVGS_OK;
+}
+
 }  // extern "C"

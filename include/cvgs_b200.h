@@ -162,6 +162,22 @@ int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t 
                            int32_t used, const cvgs_pipeline_t* pipeline, float* host_out,
                            void* stream);
 
+/* Frame loops in native code: `steps` consecutive calls of cvgs_b200_preproc_launch /
+ * cvgs_b200_preproc_host, call i using argument set (i % n_sets).  This is what a C++ caller's
+ * per-frame loop does (the reference's benchmarks time exactly such loops,
+ * tests/testsCommon.cuh:260-308); it exists so that language bindings with a slow call path
+ * (ctypes, JNI) can drive and time many frames without their per-call overhead.
+ * Stops at the first error and returns it. */
+int cvgs_b200_preproc_launch_sequence(const cvgs_crop_t* const* crops, const int32_t* n_planes,
+                                      const int32_t* used, const cvgs_pipeline_t* const* pipelines,
+                                      int32_t n_sets, int32_t steps, void* stream);
+int cvgs_b200_preproc_host_sequence(const void* const* host_images, int32_t image_width,
+                                    int32_t image_height, int32_t image_pitch,
+                                    const cvgs_rect_t* const* rects, const int32_t* n_planes,
+                                    const int32_t* used, const cvgs_pipeline_t* const* pipelines,
+                                    float* const* host_outs, int32_t n_sets, int32_t steps,
+                                    void* stream);
+
 /* Kernel-selection override, for tests and profiling: 0 = automatic, 1 = direct-gather kernel,
  * 2 = TMA-staged kernel.  Returns the previous value. */
 int cvgs_b200_set_kernel_variant(int variant);
