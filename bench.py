@@ -1,0 +1,489 @@
+#!/usr/bin/env python
+"""bench.py -- crops/s of the fused crop -> resize -> normalise -> split path on B200.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]`
+prints ONE JSON line on rank 0.
+
+Workload (BASELINE.json configs[1], "c2"): camera frames of 1920x1080 CV_8UC3 (row pitch 6144 B), 50 crops of
+mixed size per frame (w ~ U{24..256}, h = 2w) -> 64x128 bilinear resize -> RGB2BGR -> *0.3 -> -sub -> /div ->
+planar NCHW float.  One cvGS::executeOperations-equivalent call (= ONE kernel launch) per frame.
+A *step* is one pass over `--frames` (default 32) distinct frames, each with its own source image, rect list and
+output tensor, so that the working set (32 x 11.5 MB = 369 MB) is larger than the 126 MB L2 and every launch
+reads its source from HBM and writes its tensor to HBM ("inputs larger than L2" rule).
+
+  value      device-resident inputs: the C-ABI frame loop cvgs_b200_preproc_launch_sequence, timed with CUDA
+             events on the launching stream; crops / s over all ranks (max time over ranks).
+  e2e        the same loop through cvgs_b200_preproc_host_sequence: pinned HOST frames in, pinned HOST tensors
+             out, H2D + kernel + D2H inside the timed region.
+  roofline   algorithmic bytes of one launch (unique tapped source pixels x 3 B + 4 B x 3 x 64 x 128 x 50) /
+             average launch duration inside the timed region, against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline / --impl reference
+             the oracle port (oracle/liboracle.so, OpenMP on all host cores) on a bounded sample of the
+             same frames.  The reference is a CUDA-only header library with no CPU implementation of this
+             path (FKL's __host__ Interpolate has a typo, F10), so kind = "port".
+  baselines  (rank 0, N=1) the reference's own fused GPU kernel instantiated from its headers
+             (oracle/_ref/libfkref_50.so), a restated multi-kernel "OpenCV-CUDA-equivalent" chain
+             (oracle/_ref-free, oracle/libchain.so) and OpenCV-CPU (cv2), same frames, same box.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")  # the CPU port's idle OpenMP threads must not spin
+
+import numpy as np  # noqa: E402
+
+DST = (64, 128)
+CROPS_PER_FRAME = 50
+FRAME = (1920, 1080)
+PITCH = 6144
+MUL, SUB, DIV = (0.3, 0.3, 0.3), (1.0, 4.0, 3.2), (3.2, 0.6, 11.8)
+OPS = [("reorder", (2, 1, 0)), ("mul", MUL), ("sub", SUB), ("div", DIV)]
+
+
+# --------------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------------
+def make_frames(n_frames: int, seed: int, crops=CROPS_PER_FRAME):
+    """n_frames x (image[H, pitch] uint8, rects[crops] (x, y, w, h)); SURVEY.md 8(d) C2 recipe."""
+    rng = np.random.default_rng(seed)
+    fw, fh = FRAME
+    frames = []
+    for _ in range(n_frames):
+        img = rng.integers(0, 256, size=(fh, PITCH), dtype=np.uint8)
+        rects = []
+        for _ in range(crops):
+            w = int(rng.integers(24, 257))
+            h = min(2 * w, fh)
+            rects.append((int(rng.integers(0, fw - w + 1)), int(rng.integers(0, fh - h + 1)), w, h))
+        frames.append((img, rects))
+    return frames
+
+
+def algorithmic_bytes(rects, dst=DST, frame=FRAME) -> tuple[int, int]:
+    """(bytes_in, bytes_out) of one launch, SURVEY.md 8(d): bytes_in = 3 x number of distinct source pixels
+    that are a bilinear tap of at least one output pixel (index math of interpolation.cuh:57-92 with the
+    scale of resize.cuh:100-114), shared between overlapping crops; bytes_out = 4 x 3 x W x H x planes."""
+    fw, fh = frame
+    dw, dh = dst
+    mask = np.zeros((fh, fw), dtype=bool)
+    for (x0, y0, w, h) in rects:
+        fx = np.float32(1.0 / (float(dw) / float(w)))
+        fy = np.float32(1.0 / (float(dh) / float(h)))
+        sx = np.arange(dw, dtype=np.float32) * fx
+        sy = np.arange(dh, dtype=np.float32) * fy
+        x1 = np.floor(sx).astype(np.int64)
+        y1 = np.floor(sy).astype(np.int64)
+        cols = np.unique(np.concatenate([x1, np.minimum(x1 + 1, w - 1)])) + x0
+        rows = np.unique(np.concatenate([y1, np.minimum(y1 + 1, h - 1)])) + y0
+        mask[np.ix_(rows, cols)] = True
+    return 3 * int(mask.sum()), 4 * 3 * dw * dh * len(rects)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks (sampled DURING the timed regions)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    _REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, device_index: int):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.active, self._stop_evt = [], set(), False, threading.Event()
+        self.sm_max = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            import torch
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                if not uuid.startswith("GPU-"):
+                    uuid = "GPU-" + uuid
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            if self.active:
+                try:
+                    self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    try:
+                        bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    for b, name in self._REASONS.items():
+                        if bits & b:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.001)
+            else:
+                time.sleep(0.0005)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (cpu_baseline leg and --impl reference)
+# --------------------------------------------------------------------------------------------------
+_THREADS = None
+
+
+def _best_thread_count(lib, crops, p) -> int:
+    """Thread count that is actually fastest on this host (a cgroup CPU quota can make the full
+    core count slower than a few threads); calibrated once on one frame."""
+    global _THREADS
+    if _THREADS is None:
+        most = max(1, int(lib.oracle_max_threads()))
+        cands = sorted({1, most} | {n for n in (2, 4, 8, 16, 32, 64, 128) if n < most})
+        best = (float("inf"), 1)
+        for n in cands:
+            lib.oracle_preproc(crops, CROPS_PER_FRAME, CROPS_PER_FRAME, C.byref(p), n)  # spin up the pool
+            t = time.perf_counter()
+            lib.oracle_preproc(crops, CROPS_PER_FRAME, CROPS_PER_FRAME, C.byref(p), n)
+            best = min(best, (time.perf_counter() - t, n))
+        _THREADS = best[1]
+    return _THREADS
+
+
+def cpu_port_crops_per_s(frames, min_seconds: float, max_frames: int):
+    """Times oracle_preproc (OpenMP, all cores) frame by frame; returns (crops/s, cores, frames done, seconds)."""
+    from tests import util  # oracle loader: checker / CPU baseline only
+    lib = util.oracle_lib()
+    out = np.empty((CROPS_PER_FRAME, 3, DST[1], DST[0]), dtype=np.float32)
+    p = util.make_pipeline(DST, OPS, out_ptr=out.ctypes.data)
+    crop_sets = [util.host_crops(img, rects) for img, rects in frames]
+    cores = _best_thread_count(lib, crop_sets[0], p)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        lib.oracle_preproc(crop_sets[done % len(frames)], CROPS_PER_FRAME, CROPS_PER_FRAME, C.byref(p), cores)
+        done += 1
+        dt = time.perf_counter() - t0
+        if (dt >= min_seconds and done >= 4) or done >= max_frames:
+            break
+    return done * CROPS_PER_FRAME / dt, cores, done, dt
+
+
+def opencv_cpu_crops_per_s(frames, min_seconds: float):
+    """OpenCV-CPU chain (BASELINE.md baseline C).  Different resize semantics: throughput only."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    cv2.setNumThreads(os.cpu_count() or 1)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        img, rects = frames[done % len(frames)]
+        view = img[:, :3 * FRAME[0]].reshape(FRAME[1], FRAME[0], 3)
+        for (x, y, w, h) in rects:
+            r = cv2.resize(view[y:y + h, x:x + w], DST, interpolation=cv2.INTER_LINEAR)
+            f = r.astype(np.float32) * np.float32(0.3)
+            f = cv2.subtract(f, SUB + (0.0,))
+            f = cv2.divide(f, DIV + (1.0,))
+            cv2.split(f)
+        done += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds and done >= 2:
+            break
+    return {"value": done * CROPS_PER_FRAME / dt, "unit": "crops/s", "cores": os.cpu_count(),
+            "threads": cv2.getNumThreads(), "sample": f"{done} frames x 50 crops", "version": cv2.__version__,
+            "note": "cv2.resize uses half-pixel centres: throughput baseline, not a parity oracle"}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm
+# --------------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank: int, world: int):
+    if rank != 0:
+        return
+    frames = make_frames(min(args.frames, 8), seed=2)
+    per_step_frames = 4  # bounded sample of the step: 4 frames x 50 crops
+    for _ in range(args.warmup):
+        cpu_port_crops_per_s(frames, 0.0, per_step_frames)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        _, cores, done, _ = cpu_port_crops_per_s(frames, 0.0, per_step_frames)
+        total += done
+    dt = time.perf_counter() - t0
+    value = total * CROPS_PER_FRAME / dt
+    line = {
+        "impl": "reference", "metric": "crops_per_second", "value": value, "unit": "crops/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.frames),
+        "cpu_baseline": {"value": value, "unit": "crops/s", "cores": cores, "kind": "port",
+                         "sample": f"each step = {per_step_frames} frames x 50 crops of the workload "
+                                   f"(the GPU arm's step is {args.frames} frames)"},
+        "e2e": {"value": value, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference is a CUDA-only header library without a CPU implementation of this path; this arm "
+                "times the CPU port of its algorithm (oracle/oracle.c, OpenMP, all host cores)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_frames: int):
+    return {"workload": "c2: 50 crops/frame (mixed sizes, w~U{24..256}, h=2w) from 1920x1080 CV_8UC3 -> 64x128 "
+                        "bilinear resize + RGB2BGR + mul/sub/div + NCHW split; one launch per frame",
+            "frames_per_step": n_frames, "crops_per_step": n_frames * CROPS_PER_FRAME,
+            "l2_policy": f"inputs larger than L2: {n_frames} rotating frame/tensor sets = "
+                         f"{n_frames * (FRAME[1] * PITCH + CROPS_PER_FRAME * 3 * DST[0] * DST[1] * 4) / 1e6:.0f} MB",
+            "fp_contract": "reference_fused", "interp_mode": "float", "sharding": "frames per GPU, no collective"}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def gpu_baselines(frames, d_imgs, torch, min_seconds=0.5):
+    """Reference fused kernel (its own headers, BATCH=50 instantiation) on the same device frames."""
+    out = {}
+    path = os.path.join(ROOT, "oracle", "_ref", "libfkref_50.so")
+    if os.path.exists(path):
+        lib = C.CDLL(path)
+        fn = lib.fkref_preproc_50
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                       C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float),
+                       C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+        f3 = lambda v: (C.c_float * 3)(*v)  # noqa: E731
+        n = CROPS_PER_FRAME
+        argsets = []
+        outs = [torch.empty((n, 3, DST[1], DST[0]), dtype=torch.float32, device="cuda") for _ in frames]
+        for (img, rects), d in zip(frames, d_imgs):
+            base = d.data_ptr()
+            ptrs = (C.c_void_p * n)(*[base + y * PITCH + 3 * x for (x, y, w, h) in rects])
+            argsets.append((ptrs, (C.c_int * n)(*[r[2] for r in rects]), (C.c_int * n)(*[r[3] for r in rects]),
+                            (C.c_int * n)(*[PITCH] * n)))
+        bg, mul, sub, div = f3((0, 0, 0)), f3(MUL), f3(SUB), f3(DIV)
+        s = torch.cuda.current_stream()
+
+        def one_pass():
+            for (ptrs, ws, hs, ps), o in zip(argsets, outs):
+                rc = fn(ptrs, ws, hs, ps, n, DST[0], DST[1], 1, bg, 1, mul, sub, div, o.data_ptr(), s.cuda_stream)
+                assert rc == 0
+        for _ in range(3):
+            one_pass()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record(s)
+        for _ in range(reps):
+            one_pass()
+        e1.record(s)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = reps * len(frames)
+        out["reference_fused_kernel_gpu"] = {
+            "value": launches * n / (ms * 1e-3), "unit": "crops/s", "us_per_launch": ms * 1e3 / launches,
+            "what": "fk::executeOperations(BatchRead<50>(Resize<INTER_LINEAR>), ColorConversion, Mul, Sub, Div, "
+                    "TensorSplit) from /root/reference/fkl/include compiled for sm_100a (oracle/_ref/libfkref_50.so), "
+                    "same device frames, launched from a ctypes loop"}
+    return out
+
+
+def run_gpu_arm(args, rank: int, world: int, local_rank: int):
+    import torch
+    from cvgpuspeedup_b200 import _abi
+    from tests import util
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _abi.load()
+    F, K, W = args.frames, args.steps, args.warmup
+
+    frames = make_frames(F, seed=2 + 1000 * rank)
+    alg = [algorithmic_bytes(r) for _, r in frames]
+    bytes_in = sum(a for a, _ in alg) / F
+    bytes_out = sum(b for _, b in alg) / F
+
+    h_imgs = [torch.from_numpy(img).pin_memory() for img, _ in frames]
+    d_imgs = [h.cuda() for h in h_imgs]
+    d_outs = [torch.empty((CROPS_PER_FRAME, 3, DST[1], DST[0]), dtype=torch.float32, device="cuda") for _ in frames]
+    h_outs = [torch.empty((CROPS_PER_FRAME, 3, DST[1], DST[0]), dtype=torch.float32).pin_memory() for _ in frames]
+
+    # argument sets of the C-ABI frame loops
+    crop_sets = [util.host_crops(img, rects, base_ptr=d.data_ptr()) for (img, rects), d in zip(frames, d_imgs)]
+    pipes = [util.make_pipeline(DST, OPS, out_ptr=o.data_ptr()) for o in d_outs]
+    crops_pp = (C.POINTER(_abi.Crop) * F)(*[C.cast(c, C.POINTER(_abi.Crop)) for c in crop_sets])
+    pipes_pp = (C.POINTER(_abi.Pipeline) * F)(*[C.pointer(p) for p in pipes])
+    n_arr = (C.c_int32 * F)(*[CROPS_PER_FRAME] * F)
+    rect_sets = [(_abi.Rect * CROPS_PER_FRAME)(*[_abi.Rect(*r) for r in rects]) for _, rects in frames]
+    rects_pp = (C.POINTER(_abi.Rect) * F)(*[C.cast(r, C.POINTER(_abi.Rect)) for r in rect_sets])
+    himg_pp = (C.c_void_p * F)(*[h.data_ptr() for h in h_imgs])
+    hout_pp = (C.c_void_p * F)(*[h.data_ptr() for h in h_outs])
+    host_pipe = util.make_pipeline(DST, OPS)
+    hpipes_pp = (C.POINTER(_abi.Pipeline) * F)(*[C.pointer(host_pipe)] * F)
+
+    stream = torch.cuda.Stream()
+    sp = stream.cuda_stream
+
+    def device_steps(n):
+        _abi.check(lib.cvgs_b200_preproc_launch_sequence(crops_pp, n_arr, n_arr, pipes_pp, F, F * n, sp))
+
+    def host_steps(n):
+        _abi.check(lib.cvgs_b200_preproc_host_sequence(himg_pp, FRAME[0], FRAME[1], PITCH, rects_pp, n_arr, n_arr,
+                                                       hpipes_pp, hout_pp, F, F * n, sp))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        sampler.active = True
+        l0 = lib.cvgs_b200_launch_count()
+        e0.record(stream)
+        fn(n)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        sampler.active = False
+        launches = lib.cvgs_b200_launch_count() - l0
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, launches
+
+    # ---- device-resident arm ----
+    device_steps(max(W, 3))
+    ms_dev, launches = timed(device_steps, K)
+    # parity spot check of what was just timed (frame 0 against the oracle) -- checker only
+    want = util.run_oracle(frames[0][0], frames[0][1], DST, OPS)
+    util.assert_bit_equal(d_outs[0].cpu().numpy(), want, "bench: frame 0 vs oracle")
+
+    # ---- end-to-end arm (host buffers) ----
+    host_steps(max(W, 3))
+    ms_e2e, launches_e2e = timed(host_steps, K)
+    util.assert_bit_equal(h_outs[F - 1].numpy(), util.run_oracle(frames[F - 1][0], frames[F - 1][1], DST, OPS),
+                          "bench: e2e last frame vs oracle")
+    sampler.stop()
+
+    crops_total = world * F * K * CROPS_PER_FRAME
+    value = crops_total / (ms_dev * 1e-3)
+    e2e_value = crops_total / (ms_e2e * 1e-3)
+    us_per_launch = ms_dev * 1e3 / (F * K)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = (bytes_in + bytes_out) / (us_per_launch * 1e-6) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("c2_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": "crops_per_second", "value": value, "unit": "crops/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(F),
+        "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": int(h2d_bytes(frames)),
+                "d2h_bytes_per_step": int(bytes_out * F), "ms_per_step": ms_e2e / K,
+                "api": "cvgs_b200_preproc_host_sequence (pinned host frames -> pinned host tensors)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "preproc kernel (one launch per frame)", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bytes_in + bytes_out, "bytes_in": bytes_in, "bytes_out": bytes_out,
+                     "us_per_launch": us_per_launch,
+                     "note": "50 crops = 6 MB per launch: launch-latency-bound (SURVEY F6); see c3 in 'extra'"},
+        "clocks": sampler.summary(),
+    }
+    if world == 1:
+        cps, cores, done, dt = cpu_port_crops_per_s(frames, args.cpu_seconds, 10 ** 9)
+        line["cpu_baseline"] = {"value": cps, "unit": "crops/s", "cores": cores, "kind": "port",
+                                "sample": f"{done} frames x 50 crops of the same workload in {dt:.1f} s "
+                                          "(oracle/oracle.c, OpenMP)"}
+        if not args.no_baselines:
+            b = gpu_baselines(frames, d_imgs, torch)
+            ocv = opencv_cpu_crops_per_s(frames, min(args.cpu_seconds, 3.0))
+            if ocv:
+                b["opencv_cpu"] = ocv
+            line["baselines"] = b
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def h2d_bytes(frames) -> int:
+    """Bytes cvgs_b200_preproc_host uploads per step: the rows [min y, max y+h) of each frame, 3*W bytes each."""
+    total = 0
+    for _, rects in frames:
+        lo = min(r[1] for r in rects)
+        hi = max(r[1] + r[3] for r in rects)
+        total += (hi - lo) * 3 * FRAME[0]
+    return total
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=32, help="distinct frame/tensor sets per step (> L2 in total)")
+    ap.add_argument("--cpu-seconds", type=float, default=5.0, help="wall-clock budget of the CPU baseline sample")
+    ap.add_argument("--no-baselines", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    run_gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
