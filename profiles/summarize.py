@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Turn an ncu report / launch list brought back in gpurun_out/ into the small text summaries committed here.
+
+  python profiles/summarize.py rep  gpurun_out/x/prof.ncu-rep  > profiles/rNN_name.txt     (ncu --set full capture)
+  python profiles/summarize.py list gpurun_out/x/launches.csv  > profiles/rNN_launches.txt  (gpu__time_duration list)
+"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+KEEP = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg",
+    "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum", "sm__inst_executed_pipe_alu.sum",
+    "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_lsu.sum", "sm__inst_executed_pipe_xu.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__cycles_elapsed.max", "sm__cycles_active.avg", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+]
+
+
+def rep(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    print(f"# ncu --set full --clock-control none, report {path}; one column per captured launch")
+    name = hdr.index("Kernel Name")
+    for i, r in enumerate(data):
+        print(f"# launch {i}: {r[name]}  grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}")
+    for k in KEEP:
+        if k in hdr:
+            j = hdr.index(k)
+            print(f"{k:84s} [{units[j]}] " + "  ".join(r[j] for r in data))
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
+    d = collections.OrderedDict()
+    for r in rows[1:]:
+        try:
+            d.setdefault((r[ki], r[gi]), []).append(float(r[vi].replace(",", "")))
+        except ValueError:
+            pass
+    tot = sum(sum(v) for v in d.values())
+    print(f"# ncu --metrics gpu__time_duration.sum --clock-control none ({path}); cold-cache, serialised launches")
+    print(f"# {'kernel':70s} {'grid':>14s} {'n':>5s} {'avg_ns':>9s} {'min_ns':>9s} {'max_ns':>9s} {'share':>6s}")
+    for (k, g), v in d.items():
+        print(f"  {k[:70]:70s} {g:>14s} {len(v):5d} {sum(v)/len(v):9.0f} {min(v):9.0f} {max(v):9.0f} {sum(v)/tot:6.1%}")
+
+
+if __name__ == "__main__":
+    {"rep": rep, "list": launches}[sys.argv[1]](sys.argv[2])
