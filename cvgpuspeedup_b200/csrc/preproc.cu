@@ -91,13 +91,19 @@ preproc_direct_kernel(const __grid_constant__ PreprocParams P, const __grid_cons
 // ------------------------------------------------------------------------------------------------
 struct Ring {
     static constexpr int kSlots = 8;
-    DevCrop* h[kSlots] = {};
-    DevCrop* d[kSlots] = {};
+    // one slot = [cap tensor maps][cap crop descriptors], pinned host copy + device copy
+    uint8_t* h[kSlots] = {};
+    uint8_t* d[kSlots] = {};
     cudaEvent_t ev[kSlots] = {};
     bool pending[kSlots] = {};
     size_t cap = 0;  // crops per slot
     int next = 0;
     int device = -1;
+    static size_t slot_bytes(size_t cap) { return cap * (sizeof(CUtensorMap) + sizeof(DevCrop)); }
+    CUtensorMap* maps_h(int s) const { return reinterpret_cast<CUtensorMap*>(h[s]); }
+    CUtensorMap* maps_d(int s) const { return reinterpret_cast<CUtensorMap*>(d[s]); }
+    DevCrop* crops_h(int s) const { return reinterpret_cast<DevCrop*>(h[s] + cap * sizeof(CUtensorMap)); }
+    DevCrop* crops_d(int s) const { return reinterpret_cast<DevCrop*>(d[s] + cap * sizeof(CUtensorMap)); }
 };
 struct HostPath {
     void* d_img = nullptr;
@@ -135,8 +141,8 @@ static int ring_reserve(Ring& r, size_t n, int device) {
     size_t cap = 256;
     while (cap < n) cap *= 2;
     for (int i = 0; i < Ring::kSlots; ++i) {
-        CVGS_CUDA(cudaMallocHost(&r.h[i], cap * sizeof(DevCrop)));
-        CVGS_CUDA(cudaMalloc(&r.d[i], cap * sizeof(DevCrop)));
+        CVGS_CUDA(cudaMallocHost(reinterpret_cast<void**>(&r.h[i]), Ring::slot_bytes(cap)));
+        CVGS_CUDA(cudaMalloc(reinterpret_cast<void**>(&r.d[i]), Ring::slot_bytes(cap)));
     }
     r.cap = cap;
     r.device = device;
@@ -197,15 +203,27 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used,
     int device = 0;
     CVGS_CUDA(cudaGetDevice(&device));
     const int variant = g_variant.load(std::memory_order_relaxed);
+    const int sms = sm_count_of(device);
 
-    if (used <= kParamCrops) {
-        // small batch: descriptors ride in the kernel parameters (no staging copy, graph-capturable)
-        ParamCropTable table;
-        std::memset(&table, 0, sizeof table);
+    if (used <= kTmaParamCrops) {
+        // small batch: descriptors (and tensor maps) ride in the kernel parameters -- no staging copy,
+        // graph-capturable
+        alignas(64) TmaParamTable tt;
         for (int i = 0; i < used; ++i)
-            if (int rc = fill_crop(crops[i], *pipe, i, table.c[i])) return rc;
-        if (variant != 1 && tma_supported(P, table.c, used)) return launch_tma(P, &table, table.c, used, device, stream);
+            if (int rc = fill_crop(crops[i], *pipe, i, tt.c[i])) return rc;
+        TmaParams K;
+        K.P = P;
+        K.maps = nullptr;
+        if (variant != 1 && tma_plan(P, tt.c, used, n_planes, sms, K.G)) {
+            scaled_program(P, K);
+            bool ok = true;
+            for (int i = 0; i < used && ok; ++i) ok = tma_prepare_crop(tt.c[i], K.G, P.W, &tt.m[i]) == CVGS_OK;
+            if (ok) return tma_launch_kernel<TmaParamTable>(K, tt, device, sms, stream);
+            // the driver refused a tensor map (exotic geometry): the direct-gather kernel takes anything
+        }
         if (variant == 2) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
+        ParamCropTable table;
+        std::memcpy(table.c, tt.c, static_cast<size_t>(used) * sizeof(DevCrop));
         return launch_direct(P, &table, stream);
     }
 
@@ -214,17 +232,35 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used,
     const int slot = r.next;
     r.next = (r.next + 1) % Ring::kSlots;
     if (r.pending[slot]) { CVGS_CUDA(cudaEventSynchronize(r.ev[slot])); r.pending[slot] = false; }
+    DevCrop* hc = r.crops_h(slot);
     for (int i = 0; i < used; ++i)
-        if (int rc = fill_crop(crops[i], *pipe, i, r.h[slot][i])) return rc;
-    CVGS_CUDA(cudaMemcpyAsync(r.d[slot], r.h[slot], static_cast<size_t>(used) * sizeof(DevCrop),
-                              cudaMemcpyHostToDevice, stream));
-    P.crops = r.d[slot];
+        if (int rc = fill_crop(crops[i], *pipe, i, hc[i])) return rc;
+    TmaParams K;
+    K.P = P;
+    bool use_tma = variant != 1 && tma_plan(P, hc, used, n_planes, sms, K.G);
+    if (use_tma) {
+        scaled_program(P, K);
+        CUtensorMap* hm = r.maps_h(slot);
+        for (int i = 0; i < used && use_tma; ++i) use_tma = tma_prepare_crop(hc[i], K.G, P.W, &hm[i]) == CVGS_OK;
+    }
+    if (!use_tma && variant == 2) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
+    size_t bytes = static_cast<size_t>(used) * sizeof(DevCrop);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(hc);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(r.crops_d(slot));
+    if (use_tma) {
+        // maps and crops are adjacent in the slot: one copy covers both
+        src = reinterpret_cast<const uint8_t*>(r.maps_h(slot));
+        dst = reinterpret_cast<uint8_t*>(r.maps_d(slot));
+        bytes = r.cap * sizeof(CUtensorMap) + static_cast<size_t>(used) * sizeof(DevCrop);
+    }
+    CVGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
     int rc;
-    if (variant != 1 && tma_supported(P, r.h[slot], used)) {
-        rc = launch_tma(P, nullptr, r.h[slot], used, device, stream);
-    } else if (variant == 2) {
-        rc = fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
+    if (use_tma) {
+        K.P.crops = r.crops_d(slot);
+        K.maps = r.maps_d(slot);
+        rc = tma_launch_kernel<TmaNoTable>(K, TmaNoTable{0}, device, sms, stream);
     } else {
+        P.crops = r.crops_d(slot);
         rc = launch_direct(P, nullptr, stream);
     }
     CVGS_CUDA(cudaEventRecord(r.ev[slot], stream));

@@ -1,10 +1,477 @@
-// preproc_tma.cuh -- placeholder until the TMA-staged kernel lands (next commit).
+// preproc_tma.cuh -- persistent, warp-specialised, TMA-staged kernel of the fused batch path (sm_100a).
+//
+// Same function as preproc_direct_kernel (preproc.cu) and as the reference instantiation of
+// fk::launchTransformDPP_Kernel it replaces (reference fkl/include/fused_kernel/core/execution_model/
+// data_parallel_patterns.cuh:157-197; BatchRead batch_operations.cuh:222-229; Resize resize.cuh:70-82,178-189;
+// Interpolate interpolation.cuh:57-92; TensorSplit memory_operations.cuh:168-188), organised around the
+// issue-slot budget of the path:
+//
+//   * a CTA walks a contiguous range of tiles; a tile = TR output rows x TW output columns of one crop;
+//   * the producer warp stages, per output row of the tile, the two source rows it taps with ONE
+//     cp.async.bulk.tensor.2d (box = 2 rows x the tile's source span; byte-exact start coordinate through a
+//     per-crop tensor map of 8-byte elements), completion on a per-stage mbarrier, kStages deep;
+//   * consumer threads own one quad (4 adjacent output columns) for as long as the CTA stays on the same
+//     crop column band, so the horizontal taps are computed once and only the vertical ones per row;
+//   * u8 -> f32 is one PRMT: byte b placed at bits 16..23 of a float word is exactly b * 2^-133 (exponent
+//     field 0 or 1, both scale 2^-149); the vertical weights carry 2^100 and the first op of the chain the
+//     remaining 2^33 (kPreScale).  Scaling by powers of two commutes with every rounding below (no value
+//     leaves the normal range), so results are bit-identical to the unscaled sequence.
 #pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 #include "cvgs_device.cuh"
 #include "cvgs_runtime.hpp"
+
 namespace cvgs {
-inline bool tma_supported(const PreprocParams&, const DevCrop*, int) { return false; }
-inline int launch_tma(const PreprocParams&, const ParamCropTable*, const DevCrop*, int, int, cudaStream_t) {
-    return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel not built");
+
+constexpr int kTmaParamCrops = 64;      // crops (descriptor + tensor map) that ride in the kernel parameters
+constexpr int kConsumerWarps = 4;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kTmaThreads = kConsumerThreads + 32;  // + producer warp (the last one)
+constexpr int kStages = 4;
+constexpr int kStageBytesMax = 26 * 1024;
+constexpr int kStagePad = 128;          // bytes in front of / behind the stage ring (w[-1] / w[+1] over-reads)
+constexpr int kMaxBoxBytes = 2048;      // 256 elements x 8 bytes
+constexpr float kWeightScale = 1.2676506002282294e30f;  // 2^100
+constexpr float kPreScale = 8589934592.0f;              // 2^33  = 2^133 / 2^100
+
+struct TmaGeom {
+    int32_t TW;              // tile width in output pixels (power of two, 8..256)
+    int32_t q_log2;          // log2(quads per tile row)
+    int32_t groups;          // rows processed concurrently by the consumer threads = 128 >> q_log2
+    int32_t TR;              // output rows per tile
+    int32_t tiles_x, tiles_y, tiles_per_crop, total_tiles;
+    int32_t stage_bytes;     // TR * 2 * max row bytes
+    int32_t explicit_prescale;  // 1: consumers multiply by 2^33 themselves (no op to fold it into)
+};
+
+struct TmaParams {
+    PreprocParams P;         // P.prog = unscaled chain (background values), P.crops = device table or nullptr
+    DevProgram prog_img;     // chain for interpolated values (2^33 folded into its first op)
+    TmaGeom G;
+    const CUtensorMap* maps; // device table (nullptr when the maps ride in the kernel parameters)
+};
+
+struct alignas(64) TmaParamTable {
+    CUtensorMap m[kTmaParamCrops];
+    DevCrop c[kTmaParamCrops];
+};
+struct TmaNoTable {
+    int32_t unused;
+};
+
+// DevCrop::pad of a TMA launch: bits 0..15 = smem row bytes of this crop's box, bits 16..19 = data & 15
+__host__ __device__ __forceinline__ int32_t crop_row_bytes(const DevCrop& c) { return c.pad & 0xFFFF; }
+__host__ __device__ __forceinline__ int32_t crop_misalign(const DevCrop& c) { return (c.pad >> 16) & 15; }
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// byte k of w as the float b * 2^-133 (see file header)
+__device__ __forceinline__ float u8_scaled(uint32_t w, uint32_t k) {
+    return __uint_as_float(__byte_perm(w, 0u, 0x4044u | (k << 8)));
+}
+
+template <typename Table>
+__device__ __forceinline__ const DevCrop& tma_crop_of(const TmaParams& K, const Table& T, int z);
+template <>
+__device__ __forceinline__ const DevCrop& tma_crop_of<TmaParamTable>(const TmaParams&, const TmaParamTable& T, int z) {
+    return T.c[z];
+}
+template <>
+__device__ __forceinline__ const DevCrop& tma_crop_of<TmaNoTable>(const TmaParams& K, const TmaNoTable&, int z) {
+    return K.P.crops[z];
+}
+template <typename Table>
+__device__ __forceinline__ const CUtensorMap* tma_map_of(const TmaParams& K, const Table& T, int z);
+template <>
+__device__ __forceinline__ const CUtensorMap* tma_map_of<TmaParamTable>(const TmaParams&, const TmaParamTable& T, int z) {
+    return &T.m[z];
+}
+template <>
+__device__ __forceinline__ const CUtensorMap* tma_map_of<TmaNoTable>(const TmaParams& K, const TmaNoTable&, int z) {
+    return K.maps + z;
+}
+
+// Where the staged span of a (crop, column band) starts: first in-band output column of the band, its left tap,
+// and the 8-byte element coordinate of the box.  Producer and consumers must agree, so both call this.
+struct BandOrigin {
+    int32_t xa;       // first output column of the band that receives image data (may exceed the band: empty)
+    int32_t xe;       // last such column
+    int32_t c0;       // box start coordinate (8-byte elements) in the crop's tensor map
+    int32_t origin;   // crop-row byte that smem byte 0 of a staged row corresponds to (= 8*c0 - misalign)
+};
+__device__ __forceinline__ BandOrigin band_origin(const PreprocParams& P, const TmaGeom& G, const DevCrop& C, int txi) {
+    BandOrigin b;
+    const int tx0 = txi * G.TW;
+    b.xa = max(tx0, C.bx1);
+    b.xe = min(min(tx0 + G.TW, P.W) - 1, C.bx2);
+    const AxisTap t = axis_tap(b.xa - C.bx1, C.fx);
+    const int mis = crop_misalign(C);
+    b.c0 = ((mis + 3 * t.i1) >> 4) << 1;  // the box must start on a 16-byte boundary of global memory
+    b.origin = 8 * b.c0 - mis;
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+template <typename Table>
+__global__ void __launch_bounds__(kTmaThreads, 2)
+preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ Table T) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[kStages];
+    __shared__ uint64_t bar_empty[kStages];
+
+    const PreprocParams& P = K.P;
+    const TmaGeom& G = K.G;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    // stage ring, 128-byte aligned, with kStagePad bytes of slack on both sides
+    const uint32_t ring = ((smem_u32(smem_raw) + 127u) & ~127u) + kStagePad;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_empty[s]), kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // contiguous tile range of this CTA
+    const long long T0 = (long long)G.total_tiles * blockIdx.x / gridDim.x;
+    const long long T1 = (long long)G.total_tiles * (blockIdx.x + 1) / gridDim.x;
+
+    if (warp == kConsumerWarps) {
+        // ===================================== producer warp =====================================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long t = T0; t < T1; ++t) {
+            const int z = (int)(t / G.tiles_per_crop);
+            const int rem = (int)(t - (long long)z * G.tiles_per_crop);
+            const int txi = rem / G.tiles_y;
+            const int tyi = rem - txi * G.tiles_y;
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+            const uint32_t full = smem_u32(&bar_full[stage]);
+            bool issue = false;
+            int i1 = 0, c0 = 0, rb = 0;
+            if (z < P.used) {
+                const DevCrop& C = tma_crop_of<Table>(K, T, z);
+                const BandOrigin b = band_origin(P, G, C, txi);
+                const int y = tyi * G.TR + lane;
+                rb = crop_row_bytes(C);
+                if (lane < G.TR && y < P.H && y >= C.by1 && y <= C.by2 && b.xa <= b.xe) {
+                    issue = true;
+                    i1 = axis_tap(y - C.by1, C.fy).i1;
+                    c0 = b.c0;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, issue);
+            if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(__popc(m) * 2 * rb));
+            __syncwarp();
+            if (issue) {
+                if (K.maps)  // table written by a host copy into reused ring memory: acquire it for the TMA proxy
+                    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(
+                                     reinterpret_cast<uint64_t>(tma_map_of<Table>(K, T, z)))
+                                 : "memory");
+                tma_load_2d(ring + stage * G.stage_bytes + lane * 2 * rb, tma_map_of<Table>(K, T, z), c0, i1, full);
+            }
+            if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+        return;
+    }
+
+    // ========================================= consumers =========================================
+    const int qx = tid & ((1 << G.q_log2) - 1);
+    const int g = tid >> G.q_log2;
+
+    // chain(background): value of planes z >= used and of pixels outside the aspect-ratio band
+    float vb[1][3] = {{P.bg[0], P.bg[1], P.bg[2]}};
+    apply_program<1>(P.prog, vb);
+
+    // per-thread horizontal state, valid while (z, txi) is unchanged
+    int cur_band = -1;
+    int32_t off[4], shl[4], shr[4];
+    float wx0[4], wx1[4];
+    bool inb[4], edge[4];
+    bool band_ok = false;
+    int nvalid = 0;
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = T0; t < T1; ++t) {
+        const int z = (int)(t / G.tiles_per_crop);
+        const int rem = (int)(t - (long long)z * G.tiles_per_crop);
+        const int txi = rem / G.tiles_y;
+        const int tyi = rem - txi * G.tiles_y;
+        const int x0 = txi * G.TW + 4 * qx;
+        const bool active = z < P.used;
+        const DevCrop& C = tma_crop_of<Table>(K, T, active ? z : 0);  // only dereferenced when active
+        const int rb = active ? crop_row_bytes(C) : 0;
+
+        const int band = z * G.tiles_x + txi;
+        if (band != cur_band) {
+            cur_band = band;
+            nvalid = min(4, P.W - x0);  // <= 0: this thread has no column in the tile
+            band_ok = false;
+            if (active) {
+                const BandOrigin b = band_origin(P, G, C, txi);
+                band_ok = b.xa <= b.xe;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int x = x0 + p;
+                    inb[p] = p < nvalid && x >= b.xa && x <= b.xe;
+                    const AxisTap tx_ = axis_tap((inb[p] ? x : b.xa) - C.bx1, C.fx);
+                    wx0[p] = tx_.w0;
+                    wx1[p] = tx_.w1;
+                    edge[p] = tx_.i1 + 1 > C.w - 1;  // x2_read == x1: the right tap is the left pixel again
+                    const int o = 3 * tx_.i1 - b.origin;
+                    const int R = (o + 3) >> 2;
+                    off[p] = 4 * R;
+                    shl[p] = (o & 3) ? (o & 3) * 8 : 32;
+                    shr[p] = ((o + 3) & 3) * 8;
+                }
+            }
+        }
+
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        const uint32_t sbase = ring + stage * G.stage_bytes;
+
+        for (int r = g; r < G.TR; r += G.groups) {
+            const int y = tyi * G.TR + r;
+            if (y >= P.H) break;
+            if (nvalid <= 0) continue;
+            float v[4][3];
+            const bool row_in = band_ok && y >= C.by1 && y <= C.by2;
+            if (row_in) {
+                const AxisTap ty_ = axis_tap(y - C.by1, C.fy);
+                const uint32_t rowA = sbase + r * 2 * rb;
+                const uint32_t rowB = rowA + ((ty_.i1 + 1 > C.h - 1) ? 0 : rb);
+                const float wy0 = __fmul_rn(ty_.w0, kWeightScale);
+                const float wy1 = __fmul_rn(ty_.w1, kWeightScale);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const uint32_t aA = rowA + off[p], aB = rowB + off[p];
+                    const uint32_t am = lds32(aA - 4), a0 = lds32(aA), a1 = lds32(aA + 4);
+                    const uint32_t bm = lds32(aB - 4), b0 = lds32(aB), b1 = lds32(aB + 4);
+                    const uint32_t al = __funnelshift_rc(am, a0, shl[p]);
+                    const uint32_t bl = __funnelshift_rc(bm, b0, shl[p]);
+                    uint32_t ar = __funnelshift_r(a0, a1, shr[p]);
+                    uint32_t br = __funnelshift_r(b0, b1, shr[p]);
+                    if (edge[p]) {
+                        ar = al;
+                        br = bl;
+                    }
+                    const float w00 = __fmul_rn(wx0[p], wy0), w10 = __fmul_rn(wx1[p], wy0);
+                    const float w01 = __fmul_rn(wx0[p], wy1), w11 = __fmul_rn(wx1[p], wy1);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        v[p][c] = bilerp(u8_scaled(al, c), u8_scaled(ar, c), u8_scaled(bl, c), u8_scaled(br, c), w00, w10,
+                                         w01, w11);
+                }
+                if (G.explicit_prescale) {
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) v[p][c] = __fmul_rn(v[p][c], kPreScale);
+                }
+                apply_program<4>(K.prog_img, v);
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    if (!inb[p]) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) v[p][c] = vb[0][c];
+                    }
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[p][c] = vb[0][c];
+            }
+            store_pixels<4>(P, z, y, x0, nvalid, v);
+        }
+
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_empty[stage]));
+        if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// Source bytes a staged row of a TW-wide band can span for scale factor fx (+ alignment slack), rounded to
+// the 64 bytes that keep every 2-row box 128-byte aligned in shared memory.
+inline int band_row_bytes(int TW, float fx) {
+    // taps of TW columns: floor((TW-1)*fx) + 2 pixels, +1 for the float rounding of the two products
+    const double px = std::ceil(static_cast<double>(TW - 1) * static_cast<double>(fx)) + 3.0;
+    const long long bytes = static_cast<long long>(px) * 3 + 15 /*16-byte aligned start*/ + 4 /*w[+1] word*/;
+    return static_cast<int>((bytes + 63) / 64 * 64);
+}
+
+// Can this launch take the TMA kernel, and with which tiling?  crops = host copies of the DevCrops.
+inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int n_planes, int sm_count, TmaGeom& G) {
+    if (!encode_tiled_fn()) return false;
+    float fx_max = 0.f;
+    for (int i = 0; i < used; ++i) {
+        const DevCrop& c = crops[i];
+        if (c.h > 1 && c.pitch % 16 != 0) return false;  // TMA: row stride must be a multiple of 16 bytes
+        if (!(c.fx > 0.f) || !(c.fy > 0.f) || !std::isfinite(c.fx) || !std::isfinite(c.fy)) return false;
+        fx_max = std::max(fx_max, c.fx);
+    }
+    int TW = 256;
+    while (TW > 8 && (TW / 2 >= P.W || band_row_bytes(std::min(TW, P.W), fx_max) > kMaxBoxBytes)) TW /= 2;
+    if (used > 0 && band_row_bytes(std::min(TW, P.W), fx_max) > kMaxBoxBytes) return false;  // extreme down-scale: direct kernel
+    const int rb_max = used > 0 ? band_row_bytes(std::min(TW, P.W), fx_max) : 64;
+    int q_log2 = 0;
+    while ((4 << q_log2) < TW) ++q_log2;
+    const int groups = kConsumerThreads >> q_log2;
+    int TR = 32;
+    while (TR > 1 && TR * 2 * rb_max > kStageBytesMax) TR /= 2;
+    const int tiles_x = (P.W + TW - 1) / TW;
+    const long long grid_max = 2LL * sm_count;
+    // enough tiles to balance the persistent grid, but never fewer rows than the consumers process at once
+    while (TR > groups && TR > 1 && static_cast<long long>(n_planes) * tiles_x * ((P.H + TR - 1) / TR) < 3 * grid_max)
+        TR /= 2;
+    G.TW = TW;
+    G.q_log2 = q_log2;
+    G.groups = groups;
+    G.TR = TR;
+    G.tiles_x = tiles_x;
+    G.tiles_y = (P.H + TR - 1) / TR;
+    G.tiles_per_crop = G.tiles_x * G.tiles_y;
+    const long long total = static_cast<long long>(n_planes) * G.tiles_per_crop;
+    if (total > 0x7fffffffLL) return false;
+    G.total_tiles = static_cast<int32_t>(total);
+    G.stage_bytes = TR * 2 * rb_max;
+    G.explicit_prescale = 0;
+    return true;
+}
+
+// Chain for interpolated values: the 2^33 that undoes the tap/weight scaling is folded into the first op when
+// that is exact for every input (MUL/FMA/DIV by a constant of moderate magnitude), else applied explicitly.
+inline void scaled_program(const PreprocParams& P, TmaParams& K) {
+    K.prog_img = P.prog;
+    K.G.explicit_prescale = 1;
+    if (P.prog.round_u8 || P.prog.n_ops == 0) return;
+    DevOp& op = K.prog_img.ops[0];
+    auto moderate = [](float a) { return a == 0.f || (std::fabs(a) > 1e-20f && std::fabs(a) < 1e20f); };
+    if (op.kind == DOP_MUL || op.kind == DOP_FMA) {
+        for (int c = 0; c < 3; ++c)
+            if (!moderate(op.a[c])) return;
+        for (int c = 0; c < 3; ++c) op.a[c] *= kPreScale;
+        K.G.explicit_prescale = 0;
+    } else if (op.kind == DOP_DIV) {
+        for (int c = 0; c < 3; ++c)
+            if (!moderate(op.a[c]) || op.a[c] == 0.f) return;
+        for (int c = 0; c < 3; ++c) op.a[c] /= kPreScale;
+        K.G.explicit_prescale = 0;
+    }
+}
+
+// Fill the TMA fields of a crop descriptor and encode its tensor map.
+inline int tma_prepare_crop(DevCrop& c, const TmaGeom& G, int W, CUtensorMap* map) {
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(c.data);
+    const int mis = static_cast<int>(addr & 15);
+    const int rb = band_row_bytes(std::min(G.TW, W), c.fx);
+    c.pad = rb | (mis << 16);
+    const cuuint64_t dim[2] = {static_cast<cuuint64_t>((mis + 3LL * c.w + 7) / 8), static_cast<cuuint64_t>(c.h)};
+    const cuuint64_t pitch = c.h > 1 ? static_cast<cuuint64_t>(c.pitch) : (dim[0] * 8 + 15) / 16 * 16;
+    const cuuint64_t stride[1] = {pitch};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(rb / 8), 2};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, reinterpret_cast<void*>(addr - mis), dim,
+                                         stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CVGS_ERR_INVALID_VALUE, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return CVGS_OK;
+}
+
+inline size_t tma_smem_bytes(const TmaGeom& G) {
+    return static_cast<size_t>(kStages) * G.stage_bytes + 2 * kStagePad + 128;
+}
+
+template <typename Table>
+inline int tma_launch_kernel(const TmaParams& K, const Table& T, int device, int sm_count, cudaStream_t stream) {
+    static thread_local size_t attr_set[64] = {};  // per device: dynamic shared memory opt-in already granted
+    const size_t smem = tma_smem_bytes(K.G);
+    const int slot = device & 63;
+    if (smem > attr_set[slot]) {
+        const size_t want = std::max<size_t>(smem, 112 * 1024);
+        CVGS_CUDA(cudaFuncSetAttribute(preproc_tma_kernel<Table>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(want)));
+        attr_set[slot] = want;
+    }
+    const int grid = static_cast<int>(std::min<long long>(K.G.total_tiles, 2LL * sm_count));
+    preproc_tma_kernel<Table><<<grid, kTmaThreads, smem, stream>>>(K, T);
+    count_launch();
+    CVGS_CUDA(cudaGetLastError());
+    return CVGS_OK;
+}
+
 }  // namespace cvgs

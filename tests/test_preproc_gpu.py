@@ -180,3 +180,80 @@ def test_host_buffer_entry_point():
                                               h_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         util.assert_bit_equal(h_out.numpy(), util.run_oracle(w.image, w.rects, w.dsize, w.ops), "host entry point")
+
+
+# ---- the TMA-staged kernel, forced (variant 2 fails loudly instead of falling back) ----
+def test_tma_kernel_c1_c2_c3():
+    _check(util.workload_c1(), 2)                      # 10x / 3.75x down-scale
+    _check(util.workload_c1(smooth=True), 2)
+    _check(util.workload_c2(pitch=6144), 2)            # mixed up- and down-scales, 50 crops
+    _check(util.workload_c2(pitch=5760, ref_shape=True), 2)
+    w = util.workload_c3(n=40)                         # 224x224: two column bands per crop
+    _check(w, 2)
+
+
+@pytest.mark.parametrize("dsize", [(63, 17), (1, 1), (5, 300), (130, 2), (224, 224), (66, 66), (300, 40), (640, 9)])
+def test_tma_kernel_ragged_sizes(dsize):
+    rng = np.random.default_rng(17)
+    img = util.make_image(rng, 333, 211, pitch=1008)
+    rects = [(0, 0, 333, 211), (1, 1, 1, 1), (332, 210, 1, 1), (0, 0, 2, 2), (7, 9, 100, 3), (300, 5, 33, 200),
+             (10, 10, 64, 128), (11, 12, 65, 129), (5, 0, 328, 1)]
+    w = util.Workload("ragged_tma", img, 333, 211, rects, dsize, util.OPS_C1)
+    _check(w, 2)
+    _check(w, 2, fp_contract=_abi.FP_SEPARATE, interp_mode=_abi.INTERP_ROUND_U8)
+
+
+@pytest.mark.parametrize("aspect", [_abi.PRESERVE_AR, _abi.PRESERVE_AR_RN_EVEN, _abi.PRESERVE_AR_LEFT])
+def test_tma_kernel_aspect_modes_and_layouts(aspect):
+    rng = np.random.default_rng(5)
+    img = util.make_image(rng, 400, 300, pitch=1280)
+    rects = [(i, i, 30, 120) for i in range(8)] + [(0, 0, 400, 300), (10, 10, 17, 200), (3, 3, 300, 9)]
+    for dsize in [(64, 128), (300, 100)]:
+        w = util.Workload("ar_tma", img, 400, 300, rects, dsize, util.OPS_C2, aspect=aspect,
+                          background=(128.0, 7.0, 250.5))
+        _check(w, 2)
+        _check(w, 2, layout=_abi.OUT_NHWC, n_planes=14, used=9)
+        _check(w, 2, layout=_abi.OUT_CNHW, plane_stride=dsize[0] * dsize[1] + 4)
+
+
+def test_tma_kernel_unaligned_base_and_chains():
+    """ROI pointers at every 16-byte phase (image base shifted by 0..15 bytes) and every chain shape."""
+    rng = np.random.default_rng(23)
+    back = rng.integers(0, 256, size=240 * 960 + 64, dtype=np.uint8)
+    d_back = torch.from_numpy(back).cuda()
+    rects = [(0, 0, 319, 240), (3, 5, 40, 80), (100, 20, 200, 200), (318, 0, 1, 240), (7, 7, 64, 128)]
+    for shift in [0, 1, 5, 8, 15]:
+        img = back[shift:shift + 240 * 960].reshape(240, 960)
+        d_img = d_back[shift:shift + 240 * 960].view(240, 960)
+        w = util.Workload("shift", img, 319, 240, rects, (64, 128), util.OPS_C2)
+        got = gpu_util.run_cvgs(img, rects, w.dsize, w.ops, variant=2, d_image=d_img)
+        util.assert_bit_equal(got, util.run_oracle(img, rects, w.dsize, w.ops), f"base shift {shift}")
+    w = util.workload_c2(n=4, frame=(320, 240), pitch=960)
+    chains = [[], [("div", (255.0,) * 3)], [("add", (1.5, 2.5, 3.5)), ("mul", (2.0, 3.0, 4.0))],
+              [("mul", (0.5,) * 3), ("reorder", (2, 1, 0)), ("sub", (1.0, 2.0, 3.0))],
+              [("mul", (1e-30,) * 3), ("mul", (1e30,) * 3)],
+              [("reorder", (1, 2, 0)), ("mul", (0.25, 0.5, 2.0)), ("add", (1.0, 2.0, 3.0)), ("add", (0.1, 0.2, 0.3)),
+               ("div", (3.0, 7.0, 0.1)), ("reorder", (2, 0, 1)), ("sub", (5.0, 6.0, 7.0)), ("mul", (1.1, 1.2, 1.3))]]
+    for ops in chains:
+        w.ops = ops
+        _check(w, 2)
+        _check(w, 2, fp_contract=_abi.FP_SEPARATE)
+        _check(w, 2, interp_mode=_abi.INTERP_ROUND_U8)
+
+
+def test_tma_kernel_large_batch_device_tables():
+    """More than 64 crops: tensor maps and descriptors travel through the pinned ring into device memory."""
+    w = util.workload_c2(n=300, frame=(640, 480), pitch=1920)
+    w.dsize = (32, 48)
+    for _ in range(10):  # more launches than ring slots: slot (and tensor-map address) reuse
+        _check(w, 2)
+    w2 = util.workload_c2(seed=9, n=300, frame=(640, 480), pitch=1920)
+    w2.dsize = (32, 48)
+    _check(w2, 2)
+
+
+def test_tma_kernel_refuses_unsupported_pitch():
+    w = util.workload_c2(n=3, frame=(333, 211), pitch=1003)
+    with pytest.raises(_abi.CvgsError):
+        _check(w, 2)
+    _check(w, 0)  # automatic selection falls back to the direct-gather kernel
