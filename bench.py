@@ -398,6 +398,9 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int):
     ms_e2e, launches_e2e = timed(host_steps, K)
     util.assert_bit_equal(h_outs[F - 1].numpy(), util.run_oracle(frames[F - 1][0], frames[F - 1][1], DST, OPS),
                           "bench: e2e last frame vs oracle")
+    extra = None
+    if world == 1 and not args.no_baselines:
+        extra = c3_extra(lib, torch, _abi, util, stream)
     sampler.stop()
 
     crops_total = world * F * K * CROPS_PER_FRAME
@@ -438,6 +441,9 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int):
                      "note": "50 crops = 6 MB per launch: launch-latency-bound (SURVEY F6); see c3 in 'extra'"},
         "clocks": sampler.summary(),
     }
+    if extra:
+        extra["frac_of_peak"] = extra["achieved_gbs"] / peak
+        line["extra"] = {"c3": extra}
     if world == 1:
         cps, cores, done, dt = cpu_port_crops_per_s(frames, args.cpu_seconds, 10 ** 9)
         line["cpu_baseline"] = {"value": cps, "unit": "crops/s", "cores": cores, "kind": "port",
@@ -452,6 +458,42 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def c3_extra(lib, torch, _abi, util, stream, reps=20):
+    """BASELINE configs[2]: 256 crops (224..896 px) of a 3840x2160 frame -> 224x224, BGR2RGB, ImageNet mean/std,
+    NCHW.  154 MB of output per launch, 2 rotating (frame, tensor) sets > L2: the configuration on which the HBM
+    roofline fraction describes the kernel rather than launch latency."""
+    sets = []
+    for k in range(2):
+        w = util.workload_c3(seed=3 + k)
+        d_img = torch.from_numpy(w.image).cuda()
+        d_out = torch.empty((256, 3, 224, 224), dtype=torch.float32, device="cuda")
+        crops = util.host_crops(w.image, w.rects, base_ptr=d_img.data_ptr())
+        pipe = util.make_pipeline(w.dsize, w.ops, out_ptr=d_out.data_ptr())
+        sets.append((w, d_img, d_out, crops, pipe))
+    n = len(sets)
+    crops_pp = (C.POINTER(_abi.Crop) * n)(*[C.cast(s[3], C.POINTER(_abi.Crop)) for s in sets])
+    pipes_pp = (C.POINTER(_abi.Pipeline) * n)(*[C.pointer(s[4]) for s in sets])
+    n_arr = (C.c_int32 * n)(*[256] * n)
+    sp = stream.cuda_stream
+    _abi.check(lib.cvgs_b200_preproc_launch_sequence(crops_pp, n_arr, n_arr, pipes_pp, n, 4, sp))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    _abi.check(lib.cvgs_b200_preproc_launch_sequence(crops_pp, n_arr, n_arr, pipes_pp, n, reps, sp))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    w0 = sets[0][0]
+    idx = [0, 100, 255]
+    want = util.run_oracle(w0.image, [w0.rects[i] for i in idx], w0.dsize, w0.ops)
+    util.assert_bit_equal(sets[0][2][idx].cpu().numpy(), want, "bench c3: spot check vs oracle")
+    b_in, b_out = algorithmic_bytes(w0.rects, dst=(224, 224), frame=(3840, 2160))
+    gbs = (b_in + b_out) / (us * 1e-6) / 1e9
+    return {"workload": "c3: 256 crops (224..896 px) from 3840x2160 -> 224x224 + BGR2RGB + mean/std + NCHW, one launch",
+            "us_per_launch": us, "crops_per_s": 256 / (us * 1e-6), "algorithmic_bytes_per_launch": b_in + b_out,
+            "bytes_in": b_in, "bytes_out": b_out, "achieved_gbs": gbs}
 
 
 def h2d_bytes(frames) -> int:

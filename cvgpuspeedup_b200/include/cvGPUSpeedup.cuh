@@ -1,0 +1,290 @@
+// cvGPUSpeedup.cuh -- source-compatible shim of the reference's cvGS interface for ONE hot path, on top of the
+// C-ABI of libcvgs_b200.so (include/cvgs_b200.h).
+//
+// A pipeline written against the reference (include/cvGPUSpeedup.cuh of cvGPUSpeedup 0.21.0),
+//
+//     cvGS::executeOperations(cv_stream,
+//         cvGS::resize<CV_8UC3, cv::INTER_LINEAR, BATCH>(crops, dsize, usedPlanes[, background]),
+//         cvGS::cvtColor<cv::COLOR_RGB2BGR, CV_32FC3>(), cvGS::multiply<CV_32FC3>(alpha),
+//         cvGS::subtract<CV_32FC3>(sub), cvGS::divide<CV_32FC3>(div), cvGS::split<CV_32FC3>(d_tensor, dsize));
+//
+// compiles unchanged against this header and becomes ONE call of cvgs_b200_preproc_launch (= one sm_100a kernel
+// launch).  Where the reference builds nested operation-struct types and lets templates fuse them, the
+// operation structs here are small runtime descriptors; chains outside the hot path fail to compile with a
+// static_assert naming the unsupported operation.  Plain host C++17: usable from g++ as well as nvcc.
+//
+// Reference lines mirrored: resize :209-245, convertTo :74-129, multiply/subtract/divide/add :131-149,
+// cvtColor :151-161, split :185-202, write :449-457, executeOperations :464-473, CircularTensor :600-627,
+// AspectRatio :32; error convention fkl/include/fused_kernel/core/utils/utils.h:42-60 (std::runtime_error).
+#pragma once
+#include <array>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/cvgs_b200.h"
+#include "cvgs_opencv_compat.hpp"
+
+namespace fk {  // the few fk names that appear in user code of this path
+enum AspectRatio { PRESERVE_AR = 0, IGNORE_AR = 1, PRESERVE_AR_RN_EVEN = 2, PRESERVE_AR_LEFT = 3 };
+enum class CircularTensorOrder { NewestFirst, OldestFirst };
+enum class ColorPlanes { Standard, Transposed };
+enum ND { _1D = 1, _2D = 2, _3D = 3, T3D = 4 };
+struct PtrDims3D {
+    unsigned width = 0, height = 0, planes = 0, color_planes = 0;
+};
+template <ND D, typename T>
+struct RawPtr {
+    T* data = nullptr;
+    PtrDims3D dims;
+};
+}  // namespace fk
+
+namespace cvGS {
+
+enum AspectRatio { PRESERVE_AR = 0, IGNORE_AR = 1, PRESERVE_AR_RN_EVEN = 2, PRESERVE_AR_LEFT = 3 };
+
+namespace detail {
+inline void check(int rc, const char* what) {
+    if (rc != 0)  // same convention as gpuErrchk in the reference: throw with the message
+        throw std::runtime_error(std::string(what) + ": " + cvgs_b200_last_error() + " (code " + std::to_string(rc) + ")");
+}
+struct ReadBatch {  // cvGS::resize(...) result
+    std::vector<cvgs_crop_t> crops;
+    int n_planes = 0, used = 0, dst_w = 0, dst_h = 0, aspect = CVGS_IGNORE_AR, src_type = 0;
+    float bg[4] = {0, 0, 0, 0};
+};
+struct ChainOp {  // multiply / subtract / divide / add / cvtColor / convertTo pieces
+    cvgs_op_t op[2];
+    int n = 0;
+};
+struct WriteOp {  // split / splitT / write
+    void* out = nullptr;
+    int layout = CVGS_OUT_NCHW;
+    long long plane_stride = 0;
+};
+template <typename T>
+struct is_op : std::false_type {};
+template <>
+struct is_op<ChainOp> : std::true_type {};
+
+inline cvgs_op_t scalar_op(int kind, const cv::Scalar& s) {
+    cvgs_op_t o{};
+    o.kind = kind;
+    for (int c = 0; c < 4; ++c) o.v[c] = static_cast<float>(s[c]);  // cvGPUSpeedupHelpers.cuh:38-54: static_cast per channel
+    return o;
+}
+inline void append(cvgs_pipeline_t& p, const ChainOp& c) {
+    for (int i = 0; i < c.n; ++i) {
+        if (p.n_ops >= CVGS_MAX_OPS) throw std::runtime_error("cvGS: more than CVGS_MAX_OPS operations in the chain");
+        p.ops[p.n_ops++] = c.op[i];
+    }
+}
+inline void append(cvgs_pipeline_t& p, const WriteOp& w) {
+    p.out = w.out;
+    p.out_layout = w.layout;
+    p.out_plane_stride = w.plane_stride;
+}
+template <typename T>
+inline void append(cvgs_pipeline_t&, const T&) {
+    static_assert(std::is_same<T, ChainOp>::value || std::is_same<T, WriteOp>::value,
+                  "cvGS (B200 build): this operation is not on the fused resize/normalise/split path "
+                  "(supported: convertTo, multiply, subtract, divide, add, cvtColor<RGB2BGR/BGR2RGB>, split, splitT, write)");
+}
+inline cvgs_crop_t crop_of(const cv::cuda::GpuMat& m) {  // gpuMat2RawPtr2D, reference :40-44
+    cvgs_crop_t c{};
+    c.data = m.data;
+    c.width = m.cols;
+    c.height = m.rows;
+    c.pitch = static_cast<int32_t>(m.step);
+    return c;
+}
+}  // namespace detail
+
+// Floating-point contract and resize-output mode of subsequent executeOperations calls on this thread
+// (DESIGN.md section 2).  Defaults reproduce the reference's fused kernel bit for bit.
+inline int& fpContract() {
+    thread_local int v = CVGS_FP_REFERENCE_FUSED;
+    return v;
+}
+inline int& interpMode() {
+    thread_local int v = CVGS_INTERP_FLOAT;
+    return v;
+}
+
+// ---- resize (reference :209-245) -------------------------------------------------------------------------
+template <int T, int INTER_F, int NPtr, AspectRatio AR_ = IGNORE_AR>
+inline detail::ReadBatch resize(const std::array<cv::cuda::GpuMat, NPtr>& input, const cv::Size& dsize, const int& usedPlanes,
+                                const cv::Scalar& backgroundValue = cv::Scalar()) {
+    static_assert(T == CV_8UC3, "cvGS (B200 build): only CV_8UC3 sources are on the hot path in this build");
+    static_assert(INTER_F == cv::INTER_LINEAR, "cvGS (B200 build): only INTER_LINEAR is implemented (as in the reference)");
+    detail::ReadBatch r;
+    r.n_planes = NPtr;
+    r.used = usedPlanes;
+    r.dst_w = dsize.width;
+    r.dst_h = dsize.height;
+    r.aspect = static_cast<int>(AR_);
+    r.src_type = T;
+    for (int c = 0; c < 4; ++c) r.bg[c] = static_cast<float>(backgroundValue[c]);
+    r.crops.resize(NPtr);
+    for (int i = 0; i < NPtr && i < usedPlanes; ++i) r.crops[i] = detail::crop_of(input[i]);
+    return r;
+}
+template <int T, int INTER_F>
+inline detail::ReadBatch resize(const cv::cuda::GpuMat& input, const cv::Size& dsize, double fx = 0., double fy = 0.) {
+    cv::Size d = dsize;
+    if (d.width == 0 && d.height == 0) {  // reference :209-216 -> Resize::build with fx, fy (resize.cuh:84-98)
+        d.width = static_cast<int>(fx * input.cols + 0.5);  // cxp::round of a positive value
+        d.height = static_cast<int>(fy * input.rows + 0.5);
+    }
+    return resize<T, INTER_F, 1>(std::array<cv::cuda::GpuMat, 1>{input}, d, 1);
+}
+
+// ---- element-wise operations (reference :74-161) ---------------------------------------------------------
+template <int I, int O>
+inline detail::ChainOp convertTo() {  // SaturateCast<u8 -> f32>: the resize already yields float
+    static_assert(CV_MAT_DEPTH(O) == CV_32F, "cvGS (B200 build): the fused path produces CV_32F");
+    return {};
+}
+template <int I, int O>
+inline detail::ChainOp convertTo(float alpha) {
+    static_assert(CV_MAT_DEPTH(O) == CV_32F, "cvGS (B200 build): the fused path produces CV_32F");
+    detail::ChainOp c;
+    c.op[c.n++] = detail::scalar_op(CVGS_OP_MUL, cv::Scalar::all(alpha));
+    return c;
+}
+template <int I, int O>
+inline detail::ChainOp convertTo(float alpha, float beta) {
+    detail::ChainOp c = convertTo<I, O>(alpha);
+    c.op[c.n++] = detail::scalar_op(CVGS_OP_ADD, cv::Scalar::all(beta));
+    return c;
+}
+#define CVGS_SCALAR_OP(NAME, KIND)                              \
+    template <int I>                                            \
+    inline detail::ChainOp NAME(const cv::Scalar& src2) {       \
+        detail::ChainOp c;                                      \
+        c.op[c.n++] = detail::scalar_op(KIND, src2);            \
+        return c;                                               \
+    }
+CVGS_SCALAR_OP(multiply, CVGS_OP_MUL)
+CVGS_SCALAR_OP(subtract, CVGS_OP_SUB)
+CVGS_SCALAR_OP(divide, CVGS_OP_DIV)
+CVGS_SCALAR_OP(add, CVGS_OP_ADD)
+#undef CVGS_SCALAR_OP
+
+template <cv::ColorConversionCodes CODE, int I, int O = I>
+inline detail::ChainOp cvtColor() {
+    static_assert(CODE == cv::COLOR_RGB2BGR || CODE == cv::COLOR_BGR2RGB,
+                  "cvGS (B200 build): only the 3-channel R<->B swap is on the hot path");
+    static_assert(CV_MAT_CN(I) == 3 && CV_MAT_CN(O) == 3, "cvGS (B200 build): 3-channel only");
+    detail::ChainOp c;
+    c.op[0].kind = CVGS_OP_REORDER;
+    c.op[0].perm[0] = 2;
+    c.op[0].perm[1] = 1;
+    c.op[0].perm[2] = 0;
+    c.n = 1;
+    return c;
+}
+
+// ---- writes (reference :185-202, :449-457) ---------------------------------------------------------------
+template <int O>
+inline detail::WriteOp split(const cv::cuda::GpuMat& output, const cv::Size& /*planeDims*/) {
+    static_assert(O == CV_32FC3, "cvGS (B200 build): CV_32FC3 output");
+    return {output.data, CVGS_OUT_NCHW, 0};  // the reference builds a tight Tensor and ignores GpuMat::step (:67-71)
+}
+template <int O>
+inline detail::WriteOp split(const fk::RawPtr<fk::_3D, float>& output) {
+    return {output.data, CVGS_OUT_NCHW, 0};
+}
+template <int O>
+inline detail::WriteOp splitT(const fk::RawPtr<fk::T3D, float>& output) {
+    return {output.data, CVGS_OUT_CNHW, 0};
+}
+template <int O>
+inline detail::WriteOp write(const cv::cuda::GpuMat& output, const cv::Size& /*plane*/) {
+    static_assert(O == CV_32FC3, "cvGS (B200 build): CV_32FC3 output");
+    return {output.data, CVGS_OUT_NHWC, 0};
+}
+
+// ---- executeOperations (reference :464-473) --------------------------------------------------------------
+template <typename... IOpTypes>
+inline void executeOperations(const cv::cuda::Stream& stream, const detail::ReadBatch& read, const IOpTypes&... iops) {
+    cvgs_pipeline_t p{};
+    p.src_type = read.src_type;
+    p.dst_width = read.dst_w;
+    p.dst_height = read.dst_h;
+    p.aspect_mode = read.aspect;
+    p.interp_mode = interpMode();
+    p.fp_contract = fpContract();
+    for (int c = 0; c < 4; ++c) p.background[c] = read.bg[c];
+    (detail::append(p, iops), ...);
+    detail::check(cvgs_b200_preproc_launch(read.crops.data(), read.n_planes, read.used, &p,
+                                           cv::cuda::StreamAccessor::getStream(stream)),
+                  "cvGS::executeOperations");
+}
+template <bool ENABLE_THREAD_FUSION, typename... IOpTypes>
+inline void executeOperations(const cv::cuda::Stream& stream, const detail::ReadBatch& read, const IOpTypes&... iops) {
+    executeOperations(stream, read, iops...);  // thread fusion is a property of the hand-written kernel here
+}
+
+// ---- CircularTensor (reference :600-627 over fkl/.../core/data/circular_tensor.cuh:84-151) ----------------
+template <int I, int O, int COLOR_PLANES, int BATCH, fk::CircularTensorOrder CT_ORDER,
+          fk::ColorPlanes CP_MODE = fk::ColorPlanes::Standard>
+class CircularTensor {
+    static_assert(I == CV_8UC3 && CV_MAT_DEPTH(O) == CV_32F && COLOR_PLANES == 3,
+                  "cvGS (B200 build): CircularTensor<CV_8UC3, CV_32F, 3, ...> is the supported instantiation");
+
+public:
+    CircularTensor() = default;
+    CircularTensor(const uint& width_, const uint& height_, const int& deviceID_ = 0) { Alloc(width_, height_, deviceID_); }
+    CircularTensor(const CircularTensor&) = delete;
+    CircularTensor& operator=(const CircularTensor&) = delete;
+    ~CircularTensor() {
+        if (h_) cvgs_b200_ct_destroy(h_);
+    }
+    void Alloc(const uint& width_, const uint& height_, const int& deviceID_ = 0) {
+        if (h_) detail::check(cvgs_b200_ct_destroy(h_), "CircularTensor::Alloc");
+        h_ = nullptr;
+        w_ = width_;
+        hgt_ = height_;
+        detail::check(cvgs_b200_ct_create(&h_, static_cast<int>(width_), static_cast<int>(height_), COLOR_PLANES, BATCH,
+                                          CT_ORDER == fk::CircularTensorOrder::NewestFirst ? CVGS_CT_NEWEST_FIRST
+                                                                                           : CVGS_CT_OLDEST_FIRST,
+                                          CP_MODE == fk::ColorPlanes::Standard ? CVGS_CT_STANDARD : CVGS_CT_TRANSPOSED,
+                                          deviceID_),
+                      "CircularTensor::Alloc");
+    }
+    // update(stream, frame, ops..., write): the trailing write names this tensor in the reference
+    // (fk::Write<TensorSplit/TensorTSplit>{myTensor.ptr()}); here the destination is implied, a WriteOp is accepted
+    // and ignored.  The frame is resized to the tensor's plane size when its size differs.
+    template <typename... IOpTypes>
+    void update(const cv::cuda::Stream& stream, const cv::cuda::GpuMat& input, const IOpTypes&... iops) {
+        cvgs_pipeline_t p{};
+        p.src_type = I;
+        p.dst_width = static_cast<int>(w_);
+        p.dst_height = static_cast<int>(hgt_);
+        p.aspect_mode = CVGS_IGNORE_AR;
+        p.interp_mode = interpMode();
+        p.fp_contract = fpContract();
+        (detail::append(p, iops), ...);
+        const cvgs_crop_t frame = detail::crop_of(input);
+        detail::check(cvgs_b200_ct_update(h_, &frame, &p, cv::cuda::StreamAccessor::getStream(stream)),
+                      "CircularTensor::update");
+    }
+    float* data() { return static_cast<float*>(cvgs_b200_ct_data(h_)); }
+    using PtrT = fk::RawPtr<CP_MODE == fk::ColorPlanes::Standard ? fk::_3D : fk::T3D, float>;
+    PtrT ptr() {
+        PtrT r;
+        r.data = data();
+        r.dims = {w_, hgt_, BATCH, COLOR_PLANES};
+        return r;
+    }
+    size_t sizeInBytes() const { return sizeof(float) * w_ * hgt_ * BATCH * COLOR_PLANES; }
+
+private:
+    void* h_ = nullptr;
+    uint w_ = 0, hgt_ = 0;
+};
+
+}  // namespace cvGS

@@ -1,0 +1,170 @@
+// tests/cpp/test_shim.cpp -- the reference's own test programs for this path, restated against the header shim
+// (cvgpuspeedup_b200/include/cvGPUSpeedup.cuh): same cvGS calls, same constants, same acceptance rules.
+//   1. tests/batchresize/test_batchresize_x_split3D.cu:58-78,311-314  constant-image batch pipeline, |diff| <= 1e-4
+//   2. tests/batchread/test_circularbatchread_x_write3D.cu:286-335,391,448  CircularTensor after 100 updates
+//   3. tests/unit_tests/test_split.cu:47-62  (1,2,3) -> planes 1,2,3
+//   4. random image vs the CPU oracle, bit for bit (the reference has no such test: SURVEY F2)
+//   5. error convention: std::runtime_error (gpuErrchk, fkl/.../core/utils/utils.h:42-60)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "../../cvgpuspeedup_b200/include/cvGPUSpeedup.cuh"
+
+extern "C" int oracle_preproc(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_pipeline_t* p, int nthreads);
+
+#define REQUIRE(cond)                                                        \
+    do {                                                                     \
+        if (!(cond)) {                                                       \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);    \
+            return 1;                                                        \
+        }                                                                    \
+    } while (0)
+
+static int test_batchresize_x_split3D() {
+    constexpr int BATCH = 50;
+    constexpr int CV_TYPE_I = CV_8UC3, CV_TYPE_O = CV_32FC3;
+    const cv::Scalar val_init(5, 5, 5), val_alpha(0.3, 0.3, 0.3), val_sub(1, 4, 3.2), val_div(3.2, 0.6, 11.8);
+    const cv::Size up(64, 128);
+    cudaStream_t s;
+    cudaStreamCreate(&s);
+    cv::cuda::Stream cv_stream = cv::cuda::StreamAccessor::wrapStream(s);
+    cv::cuda::GpuMat d_input(2160, 3840, CV_TYPE_I, val_init);
+    std::array<cv::cuda::GpuMat, BATCH> crops;
+    for (int i = 0; i < BATCH; ++i) crops[i] = d_input(cv::Rect(i, i, 60, 120));
+    cv::cuda::GpuMat d_tensor_output(BATCH, up.width * up.height * 3, CV_32FC1);
+    d_tensor_output.step = up.width * up.height * 3 * sizeof(float);  // as the reference test does (:86-87)
+
+    cvGS::executeOperations(cv_stream, cvGS::resize<CV_TYPE_I, cv::INTER_LINEAR, BATCH>(crops, up, BATCH),
+                            cvGS::cvtColor<cv::COLOR_RGB2BGR, CV_TYPE_O>(), cvGS::multiply<CV_TYPE_O>(val_alpha),
+                            cvGS::subtract<CV_TYPE_O>(val_sub), cvGS::divide<CV_TYPE_O>(val_div),
+                            cvGS::split<CV_TYPE_O>(d_tensor_output, up));
+    cv_stream.waitForCompletion();
+    std::vector<float> h(static_cast<size_t>(BATCH) * 3 * up.width * up.height);
+    REQUIRE(cudaMemcpy(h.data(), d_tensor_output.data, h.size() * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess);
+    const size_t plane = static_cast<size_t>(up.width) * up.height;
+    for (int z = 0; z < BATCH; ++z)
+        for (int c = 0; c < 3; ++c) {
+            const float want = (5.0f * 0.3f - static_cast<float>(val_sub[c])) / static_cast<float>(val_div[c]);
+            for (size_t i = 0; i < plane; ++i) REQUIRE(std::fabs(h[(z * 3 + c) * plane + i] - want) <= 1e-4f);
+        }
+    cudaStreamDestroy(s);
+    return 0;
+}
+
+template <fk::CircularTensorOrder ORDER, fk::ColorPlanes MODE>
+static int test_circular_tensor() {
+    constexpr int BATCH = 15, WIDTH = 128, HEIGHT = 128, ITERS = 100;
+    cvGS::CircularTensor<CV_8UC3, CV_32F, 3, BATCH, ORDER, MODE> myTensor(WIDTH, HEIGHT);
+    cv::cuda::GpuMat input(HEIGHT, WIDTH, CV_8UC3);
+    cudaStream_t s;
+    cudaStreamCreate(&s);
+    cv::cuda::Stream cv_stream = cv::cuda::StreamAccessor::wrapStream(s);
+    for (int i = 0; i < ITERS; ++i) {
+        input.setTo(cv::Scalar(i + 1, i + 1, i + 1));
+        if constexpr (MODE == fk::ColorPlanes::Standard)
+            myTensor.update(cv_stream, input, cvGS::convertTo<CV_8UC3, CV_32FC3>(), cvGS::split<CV_32FC3>(myTensor.ptr()));
+        else
+            myTensor.update(cv_stream, input, cvGS::convertTo<CV_8UC3, CV_32FC3>(), cvGS::splitT<CV_32FC3>(myTensor.ptr()));
+        cv_stream.waitForCompletion();
+    }
+    std::vector<float> h(myTensor.sizeInBytes() / sizeof(float));
+    REQUIRE(cudaMemcpy(h.data(), myTensor.data(), myTensor.sizeInBytes(), cudaMemcpyDeviceToHost) == cudaSuccess);
+    const size_t px = static_cast<size_t>(WIDTH) * HEIGHT;
+    for (int c = 0; c < 3; ++c)
+        for (int z = 0; z < BATCH; ++z) {
+            const float* plane = MODE == fk::ColorPlanes::Standard ? &h[(static_cast<size_t>(z) * 3 + c) * px]
+                                                                   : &h[(static_cast<size_t>(c) * BATCH + z) * px];
+            const float want = ORDER == fk::CircularTensorOrder::NewestFirst ? ITERS - z : ITERS - (BATCH - z - 1);
+            for (size_t i = 0; i < px; ++i) REQUIRE(plane[i] == want);
+        }
+    cudaStreamDestroy(s);
+    return 0;
+}
+
+static int test_split() {
+    cv::cuda::GpuMat d_input(16, 16, CV_8UC3, cv::Scalar(1, 2, 3));
+    cv::cuda::GpuMat d_out(1, 16 * 16 * 3, CV_32FC1);
+    cv::cuda::Stream st;
+    cvGS::executeOperations(st, cvGS::resize<CV_8UC3, cv::INTER_LINEAR>(d_input, cv::Size(16, 16)),
+                            cvGS::convertTo<CV_8UC3, CV_32FC3>(), cvGS::split<CV_32FC3>(d_out, cv::Size(16, 16)));
+    st.waitForCompletion();
+    std::vector<float> h(16 * 16 * 3);
+    REQUIRE(cudaMemcpy(h.data(), d_out.data, h.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess);
+    for (int c = 0; c < 3; ++c)
+        for (int i = 0; i < 256; ++i) REQUIRE(h[c * 256 + i] == static_cast<float>(c + 1));
+    return 0;
+}
+
+static int test_random_vs_oracle() {
+    constexpr int BATCH = 8, W = 640, H = 480;
+    std::mt19937 rng(7);
+    cv::cuda::GpuMat d_img(H, W, CV_8UC3);
+    std::vector<uchar> h_img(d_img.step * H);
+    for (auto& b : h_img) b = static_cast<uchar>(rng());
+    REQUIRE(cudaMemcpy(d_img.data, h_img.data(), h_img.size(), cudaMemcpyHostToDevice) == cudaSuccess);
+    std::array<cv::cuda::GpuMat, BATCH> crops;
+    std::vector<cvgs_crop_t> h_crops(BATCH);
+    for (int i = 0; i < BATCH; ++i) {
+        const cv::Rect r(3 + 37 * i, 5 + 11 * i, 24 + 40 * i, 48 + 50 * i);
+        crops[i] = d_img(r);
+        h_crops[i] = {h_img.data() + r.y * d_img.step + 3 * r.x, r.width, r.height, static_cast<int32_t>(d_img.step), 0};
+    }
+    const cv::Size up(64, 128);
+    cv::cuda::GpuMat d_out(BATCH, up.width * up.height * 3, CV_32FC1);
+    cv::cuda::Stream st;
+    const cv::Scalar bg(128, 64, 32);
+    cvGS::executeOperations(st, cvGS::resize<CV_8UC3, cv::INTER_LINEAR, BATCH, cvGS::PRESERVE_AR>(crops, up, BATCH - 2, bg),
+                            cvGS::cvtColor<cv::COLOR_RGB2BGR, CV_32FC3>(), cvGS::multiply<CV_32FC3>(cv::Scalar(0.3, 0.3, 0.3)),
+                            cvGS::subtract<CV_32FC3>(cv::Scalar(1, 4, 3.2)), cvGS::divide<CV_32FC3>(cv::Scalar(3.2, 0.6, 11.8)),
+                            cvGS::split<CV_32FC3>(d_out, up));
+    st.waitForCompletion();
+    std::vector<float> got(static_cast<size_t>(BATCH) * 3 * up.width * up.height), want(got.size());
+    REQUIRE(cudaMemcpy(got.data(), d_out.data, got.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess);
+    cvgs_pipeline_t p{};
+    p.src_type = CVGS_8UC3;
+    p.dst_width = up.width;
+    p.dst_height = up.height;
+    p.aspect_mode = CVGS_PRESERVE_AR;
+    p.background[0] = 128; p.background[1] = 64; p.background[2] = 32;
+    p.n_ops = 4;
+    p.ops[0].kind = CVGS_OP_REORDER; p.ops[0].perm[0] = 2; p.ops[0].perm[1] = 1; p.ops[0].perm[2] = 0;
+    const float mul[3] = {0.3f, 0.3f, 0.3f}, sub[3] = {1.f, 4.f, 3.2f}, div[3] = {3.2f, 0.6f, 11.8f};
+    p.ops[1].kind = CVGS_OP_MUL; p.ops[2].kind = CVGS_OP_SUB; p.ops[3].kind = CVGS_OP_DIV;
+    for (int c = 0; c < 3; ++c) { p.ops[1].v[c] = mul[c]; p.ops[2].v[c] = sub[c]; p.ops[3].v[c] = div[c]; }
+    p.out = want.data();
+    REQUIRE(oracle_preproc(h_crops.data(), BATCH, BATCH - 2, &p, 0) == 0);
+    REQUIRE(std::memcmp(got.data(), want.data(), got.size() * 4) == 0);
+    return 0;
+}
+
+static int test_error_convention() {
+    cv::cuda::GpuMat d_input(16, 16, CV_8UC3, cv::Scalar(1, 2, 3));
+    cv::cuda::GpuMat d_null;  // data == nullptr
+    cv::cuda::Stream st;
+    bool thrown = false;
+    try {
+        cvGS::executeOperations(st, cvGS::resize<CV_8UC3, cv::INTER_LINEAR>(d_input, cv::Size(16, 16)),
+                                cvGS::split<CV_32FC3>(d_null, cv::Size(16, 16)));
+    } catch (const std::runtime_error& e) {
+        thrown = std::strstr(e.what(), "output") != nullptr;
+    }
+    REQUIRE(thrown);
+    return 0;
+}
+
+int main() {
+    int failed = 0;
+    failed += test_batchresize_x_split3D();
+    failed += test_circular_tensor<fk::CircularTensorOrder::NewestFirst, fk::ColorPlanes::Standard>();
+    failed += test_circular_tensor<fk::CircularTensorOrder::NewestFirst, fk::ColorPlanes::Transposed>();
+    failed += test_circular_tensor<fk::CircularTensorOrder::OldestFirst, fk::ColorPlanes::Standard>();
+    failed += test_circular_tensor<fk::CircularTensorOrder::OldestFirst, fk::ColorPlanes::Transposed>();
+    failed += test_split();
+    failed += test_random_vs_oracle();
+    failed += test_error_convention();
+    std::printf(failed ? "test_shim: %d FAILED\n" : "test_shim: all passed\n", failed);
+    return failed ? 1 : 0;
+}
