@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <mutex>
 #include <string>
@@ -31,6 +32,15 @@ namespace cvgs {
 // errors
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string t_last_error;
+// host-side cost breakdown of the launch path (diagnostics, cvgs_b200_debug_host_profile)
+struct HostProfile {
+    double fill = 0, plan = 0, encode = 0, launch = 0;
+    long long calls = 0;
+};
+static thread_local HostProfile t_prof;
+static inline double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 static thread_local int64_t t_launch_count = 0;
 static std::atomic<int> g_variant{0};
 
@@ -209,16 +219,26 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used,
         // small batch: descriptors (and tensor maps) ride in the kernel parameters -- no staging copy,
         // graph-capturable
         alignas(64) TmaParamTable tt;
+        const double t0 = now_us();
         for (int i = 0; i < used; ++i)
             if (int rc = fill_crop(crops[i], *pipe, i, tt.c[i])) return rc;
+        const double t1 = now_us();
         TmaParams K;
         K.P = P;
         K.maps = nullptr;
         if (variant != 1 && tma_plan(P, tt.c, used, n_planes, sms, K.G)) {
-            scaled_program(P, K);
+            const int chain = scaled_program(P, K);
+            const double t2 = now_us();
             bool ok = true;
             for (int i = 0; i < used && ok; ++i) ok = tma_prepare_crop(tt.c[i], K.G, P.W, &tt.m[i]) == CVGS_OK;
-            if (ok) return tma_launch_kernel<TmaParamTable>(K, tt, device, sms, stream);
+            const double t3 = now_us();
+            if (ok) {
+                const int rc = tma_launch_kernel<TmaParamTable>(K, tt, chain, device, stream);
+                const double t4 = now_us();
+                t_prof.fill += t1 - t0; t_prof.plan += t2 - t1; t_prof.encode += t3 - t2; t_prof.launch += t4 - t3;
+                ++t_prof.calls;
+                return rc;
+            }
             // the driver refused a tensor map (exotic geometry): the direct-gather kernel takes anything
         }
         if (variant == 2) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
@@ -238,8 +258,9 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used,
     TmaParams K;
     K.P = P;
     bool use_tma = variant != 1 && tma_plan(P, hc, used, n_planes, sms, K.G);
+    int chain = CH_GENERIC;
     if (use_tma) {
-        scaled_program(P, K);
+        chain = scaled_program(P, K);
         CUtensorMap* hm = r.maps_h(slot);
         for (int i = 0; i < used && use_tma; ++i) use_tma = tma_prepare_crop(hc[i], K.G, P.W, &hm[i]) == CVGS_OK;
     }
@@ -258,7 +279,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used,
     if (use_tma) {
         K.P.crops = r.crops_d(slot);
         K.maps = r.maps_d(slot);
-        rc = tma_launch_kernel<TmaNoTable>(K, TmaNoTable{0}, device, sms, stream);
+        rc = tma_launch_kernel<TmaNoTable>(K, TmaNoTable{0}, chain, device, stream);
     } else {
         P.crops = r.crops_d(slot);
         rc = launch_direct(P, nullptr, stream);
@@ -296,6 +317,14 @@ int cvgs_b200_version(void) { return CVGS_B200_VERSION; }
 const char* cvgs_b200_last_error(void) { return t_last_error.c_str(); }
 int cvgs_b200_set_kernel_variant(int variant) { return g_variant.exchange(variant); }
 int64_t cvgs_b200_launch_count(void) { return t_launch_count; }
+int cvgs_b200_debug_host_profile(double* out5, int reset) {
+    if (out5) {
+        out5[0] = static_cast<double>(t_prof.calls);
+        out5[1] = t_prof.fill; out5[2] = t_prof.plan; out5[3] = t_prof.encode; out5[4] = t_prof.launch;
+    }
+    if (reset) t_prof = HostProfile{};
+    return CVGS_OK;
+}
 
 int cvgs_b200_preproc_launch(const cvgs_crop_t* crops, int32_t n_planes, int32_t used,
                              const cvgs_pipeline_t* pipeline, void* stream) {

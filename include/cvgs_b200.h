@@ -183,6 +183,13 @@ int cvgs_b200_preproc_host_sequence(const void* const* host_images, int32_t imag
 int cvgs_b200_set_kernel_variant(int variant);
 /* Number of kernel launches issued by this library on the calling thread so far. */
 int64_t cvgs_b200_launch_count(void);
+/* Diagnostics: host-side cost of the small-batch TMA launch path on the calling thread, accumulated in
+ * microseconds: out5 = {calls, descriptor fill, planning, tensor-map encoding, kernel launch}. */
+int cvgs_b200_debug_host_profile(double* out5, int reset);
+/* Diagnostics: on the current device, compare the kernels' exact division-by-constant fast path with IEEE
+ * division for every float x with 2^-60 <= |x| < 2^61 and the divisor d; *mismatches = differing results. */
+int cvgs_b200_debug_division_sweep(float d, unsigned long long* mismatches, unsigned* first_bad_bits,
+                                   float* reciprocal_used);
 
 /* ------------------------------------------------------------------------------------------
  * CircularTensor.  Replaces cvGS::CircularTensor<I, O, COLOR_PLANES, BATCH, ORDER, MODE>
