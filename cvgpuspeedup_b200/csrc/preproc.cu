@@ -13,7 +13,9 @@
 //                          into shared memory by the TMA engine (cp.async.bulk, mbarrier pipeline).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <chrono>
 #include <cstdio>
 #include <mutex>
@@ -43,6 +45,89 @@ static inline double now_us() {
 }
 static thread_local int64_t t_launch_count = 0;
 static std::atomic<int> g_variant{0};
+static std::atomic<int> g_overlap{[] {
+    const char* e = std::getenv("CVGS_B200_OVERLAP");
+    return e && e[0] == '1' ? 1 : 0;
+}()};
+
+// ------------------------------------------------------------------------------------------------
+// Overlap of consecutive launches (cvgs_b200_set_overlap).  The TMA kernel is launched with programmatic stream
+// serialisation and normally orders itself after the preceding kernel with griddepcontrol.wait before its first
+// global access.  With overlap enabled the library keeps, per stream, the memory ranges of its recent launches
+// and drops that early wait when the new launch neither reads nor writes what they write and does not write what
+// they read; every kernel still waits for its predecessor before it exits, so completion order (what any later
+// stream operation observes) is unchanged.  At most kWindow launches can be in flight this way.
+// ------------------------------------------------------------------------------------------------
+struct MemRange {
+    uintptr_t lo = 0, hi = 0;
+    bool overlaps(const MemRange& o) const { return lo < o.hi && o.lo < hi; }
+};
+struct StreamTrack {
+    cudaStream_t stream = nullptr;
+    bool used = false;
+    static constexpr int kWindow = 8;
+    MemRange out[kWindow], src[kWindow];
+    int n = 0;
+};
+static std::mutex g_track_mu;
+static StreamTrack g_tracks[16];
+
+// true: this launch must wait for the preceding kernel up front.
+static bool overlap_needs_wait(cudaStream_t stream, const MemRange& out, const MemRange& src) {
+    if (!g_overlap.load(std::memory_order_relaxed)) return true;
+    std::lock_guard<std::mutex> lock(g_track_mu);
+    StreamTrack* t = nullptr;
+    for (auto& k : g_tracks)
+        if (k.used && k.stream == stream) { t = &k; break; }
+    if (!t) {
+        for (auto& k : g_tracks)
+            if (!k.used) { t = &k; break; }
+        if (!t) return true;  // more concurrent streams than slots: plain stream order
+        t->used = true;
+        t->stream = stream;
+        t->n = 0;
+        // first launch seen on this stream: whatever precedes it is unknown
+        t->out[0] = out; t->src[0] = src; t->n = 1;
+        return true;
+    }
+    bool hazard = t->n >= StreamTrack::kWindow;
+    for (int i = 0; i < t->n && !hazard; ++i)
+        hazard = out.overlaps(t->out[i]) || src.overlaps(t->out[i]) || out.overlaps(t->src[i]);
+    if (hazard) t->n = 0;  // the wait orders this launch after everything before it
+    t->out[t->n] = out;
+    t->src[t->n] = src;
+    ++t->n;
+    return hazard;
+}
+static void overlap_forget(cudaStream_t stream) {  // a launch of this library that is not PDL-aware went to `stream`
+    if (!g_overlap.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lock(g_track_mu);
+    for (auto& k : g_tracks)
+        if (k.used && k.stream == stream) k.n = 0;
+}
+static MemRange crops_range(const DevCrop* c, int n) {
+    MemRange r;
+    r.lo = ~static_cast<uintptr_t>(0);
+    for (int i = 0; i < n; ++i) {
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(c[i].data);
+        const uintptr_t hi = lo + static_cast<uintptr_t>(c[i].h - 1) * static_cast<uintptr_t>(c[i].pitch) + 3u * c[i].w;
+        r.lo = std::min(r.lo, lo);
+        r.hi = std::max(r.hi, hi);
+    }
+    if (n <= 0) r.lo = r.hi = 0;
+    return r;
+}
+static MemRange out_range(const PreprocParams& P) {
+    // every layout stays inside [base, base + extent): NCHW/NHWC planes z*z_stride + 3*W*H, CNHW c*c_stride + ...
+    const long long plane = static_cast<long long>(P.W) * P.H;
+    long long extent;
+    if (P.out.px_stride == 3) extent = (P.n_planes - 1) * P.out.z_stride + 3 * plane;
+    else extent = 2 * P.out.c_stride + (P.n_planes - 1) * P.out.z_stride + plane;
+    MemRange r;
+    r.lo = reinterpret_cast<uintptr_t>(P.out.base);
+    r.hi = r.lo + static_cast<uintptr_t>(extent) * sizeof(float);
+    return r;
+}
 
 void set_error(const std::string& msg) { t_last_error = msg; }
 int fail(int code, const std::string& msg) {
@@ -233,6 +318,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used,
             for (int i = 0; i < used && ok; ++i) ok = tma_prepare_crop(tt.c[i], K.G, P.W, &tt.m[i]) == CVGS_OK;
             const double t3 = now_us();
             if (ok) {
+                K.G.pdl_wait = overlap_needs_wait(stream, out_range(P), crops_range(tt.c, used)) ? 1 : 0;
                 const int rc = tma_launch_kernel<TmaParamTable>(K, tt, chain, device, stream);
                 const double t4 = now_us();
                 t_prof.fill += t1 - t0; t_prof.plan += t2 - t1; t_prof.encode += t3 - t2; t_prof.launch += t4 - t3;
@@ -244,6 +330,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used,
         if (variant == 2) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
         ParamCropTable table;
         std::memcpy(table.c, tt.c, static_cast<size_t>(used) * sizeof(DevCrop));
+        overlap_forget(stream);
         return launch_direct(P, &table, stream);
     }
 
@@ -279,9 +366,13 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used,
     if (use_tma) {
         K.P.crops = r.crops_d(slot);
         K.maps = r.maps_d(slot);
+        // the descriptor copy sits between this kernel and its predecessor: plain stream order, no overlap
+        K.G.pdl_wait = 1;
+        overlap_forget(stream);
         rc = tma_launch_kernel<TmaNoTable>(K, TmaNoTable{0}, chain, device, stream);
     } else {
         P.crops = r.crops_d(slot);
+        overlap_forget(stream);
         rc = launch_direct(P, nullptr, stream);
     }
     CVGS_CUDA(cudaEventRecord(r.ev[slot], stream));
@@ -316,6 +407,7 @@ extern "C" {
 int cvgs_b200_version(void) { return CVGS_B200_VERSION; }
 const char* cvgs_b200_last_error(void) { return t_last_error.c_str(); }
 int cvgs_b200_set_kernel_variant(int variant) { return g_variant.exchange(variant); }
+int cvgs_b200_set_overlap(int enable) { return g_overlap.exchange(enable ? 1 : 0); }
 int64_t cvgs_b200_launch_count(void) { return t_launch_count; }
 int cvgs_b200_debug_host_profile(double* out5, int reset) {
     if (out5) {

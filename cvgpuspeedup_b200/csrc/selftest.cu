@@ -1,16 +1,18 @@
 // selftest.cu -- device-side self checks exported for the test-suite (diagnostics, not on the hot path).
 //
-// cvgs_b200_debug_division_sweep: compares the exact-division fast path of the fused kernels (div_by_const,
-// preproc_tma.cuh) with the IEEE routine (__fdiv_rn) for EVERY float x with 2^-60 <= |x| < 2^61 (both signs,
-// 2.03e9 values) and one divisor d, on the GPU.  Returns the number of mismatching bit patterns.
+// cvgs_b200_debug_division_sweep: compares the two-operation division by a launch constant of the fused kernels
+// (div_by_const2, preproc_tma.cuh; constants and host-side proof in div_const.cpp) with the IEEE routine
+// (__fdiv_rn) for EVERY float x with 2^-73 <= |x| < 2^48 (both signs, 2.03e9 values) and one divisor d, on the
+// GPU.  Returns the number of mismatching bit patterns; *reciprocal_used = 0 when the host rejects d for the
+// fast path (the kernels then divide with __fdiv_rn and there is nothing to compare).
 #include <cuda_runtime.h>
 
 #include "preproc_tma.cuh"
 
 namespace cvgs {
 
-__global__ void division_sweep_kernel(float d, float r, unsigned long long* mismatches, unsigned* first_bad) {
-    constexpr unsigned kExpLo = 127 - 60, kExps = 121;
+__global__ void division_sweep_kernel(float d, float zh, float zl, unsigned long long* mismatches, unsigned* first_bad) {
+    constexpr unsigned kExpLo = 127 - 73, kExps = 121;
     const unsigned long long total = 2ull * kExps * (1ull << 23);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long bad = 0;
@@ -19,7 +21,7 @@ __global__ void division_sweep_kernel(float d, float r, unsigned long long* mism
         const unsigned k = (unsigned)(i >> 23);
         const unsigned bits = ((k / kExps) << 31) | ((kExpLo + k % kExps) << 23) | mant;
         const float x = __uint_as_float(bits);
-        const float fast = div_by_const(x, r, -d);
+        const float fast = div_by_const2(make_float2(x, x), zh, zl).y;
         const float want = __fdiv_rn(x, d);
         if (__float_as_uint(fast) != __float_as_uint(want)) {
             if (!bad) atomicCAS(first_bad, 0u, bits);
@@ -41,9 +43,16 @@ extern "C" int cvgs_b200_debug_division_sweep(float d, unsigned long long* misma
     CVGS_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_first), sizeof *d_first));
     CVGS_CUDA(cudaMemset(d_cnt, 0, sizeof *d_cnt));
     CVGS_CUDA(cudaMemset(d_first, 0, sizeof *d_first));
-    const float r = correctly_rounded_reciprocal(d);
-    if (reciprocal_used) *reciprocal_used = r;
-    division_sweep_kernel<<<148 * 16, 256>>>(d, r, d_cnt, d_first);
+    const DivConst dc = div_const_prepare(d);
+    if (reciprocal_used) *reciprocal_used = dc.exact ? dc.zh : 0.f;
+    if (!dc.exact) {
+        *mismatches = 0;
+        if (first_bad_bits) *first_bad_bits = 0;
+        cudaFree(d_cnt);
+        cudaFree(d_first);
+        return CVGS_OK;
+    }
+    division_sweep_kernel<<<148 * 16, 256>>>(d, dc.zh, dc.zl, d_cnt, d_first);
     CVGS_CUDA(cudaGetLastError());
     unsigned first = 0;
     CVGS_CUDA(cudaMemcpy(mismatches, d_cnt, sizeof *d_cnt, cudaMemcpyDeviceToHost));

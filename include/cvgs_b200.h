@@ -181,13 +181,25 @@ int cvgs_b200_preproc_host_sequence(const void* const* host_images, int32_t imag
 /* Kernel-selection override, for tests and profiling: 0 = automatic, 1 = direct-gather kernel,
  * 2 = TMA-staged kernel.  Returns the previous value. */
 int cvgs_b200_set_kernel_variant(int variant);
+/* Overlap of consecutive launches on one stream (default 0 = off; the environment variable CVGS_B200_OVERLAP=1
+ * turns it on at load time).  The fused kernel is always launched with programmatic stream serialisation and, by
+ * default, waits for the preceding kernel of the stream before its first global-memory access: plain stream order.
+ * With overlap enabled the library drops that early wait for a launch whose source images and output tensor are
+ * disjoint from the outputs (and whose output is disjoint from the sources) of its own recent launches on that
+ * stream, so that back-to-back frames overlap instead of paying one launch latency each; every kernel still
+ * waits for its predecessor before it completes, so later stream operations observe the usual order.
+ * Requirement on the caller: kernels of other libraries that trigger programmatic launch completion early
+ * (cudaTriggerProgrammaticLaunchCompletion) must not be the direct producers of a source image.  The reference
+ * has no equivalent (it launches plain kernels, executors.cuh:133-156).  Returns the previous value. */
+int cvgs_b200_set_overlap(int enable);
 /* Number of kernel launches issued by this library on the calling thread so far. */
 int64_t cvgs_b200_launch_count(void);
 /* Diagnostics: host-side cost of the small-batch TMA launch path on the calling thread, accumulated in
  * microseconds: out5 = {calls, descriptor fill, planning, tensor-map encoding, kernel launch}. */
 int cvgs_b200_debug_host_profile(double* out5, int reset);
-/* Diagnostics: on the current device, compare the kernels' exact division-by-constant fast path with IEEE
- * division for every float x with 2^-60 <= |x| < 2^61 and the divisor d; *mismatches = differing results. */
+/* Diagnostics: on the current device, compare the kernels' two-operation division by a launch constant with IEEE
+ * division for every float x with 2^-73 <= |x| < 2^48 and the divisor d; *mismatches = differing results,
+ * *reciprocal_used = RN(1/d), or 0 when the host-side proof rejects d (the kernels then use IEEE division). */
 int cvgs_b200_debug_division_sweep(float d, unsigned long long* mismatches, unsigned* first_bad_bits,
                                    float* reciprocal_used);
 

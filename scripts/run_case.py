@@ -1,5 +1,5 @@
 """Run one workload repeatedly through the C-ABI (for ncu captures and quick timing):
-   python scripts/run_case.py c2|c3 [reps] [variant]"""
+   python scripts/run_case.py c2|c3 [reps] [variant] [overlap]"""
 import ctypes as C, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -10,6 +10,8 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 variant = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 lib = _abi.load()
 lib.cvgs_b200_set_kernel_variant(variant)
+overlap = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+lib.cvgs_b200_set_overlap(overlap)
 nsets = 2 if case == "c3" else 32
 sets = []
 for k in range(nsets):
@@ -29,7 +31,7 @@ run(nsets); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0 = time.perf_counter(); e0.record(st); run(reps * nsets); t1 = time.perf_counter(); e1.record(st); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / (reps * nsets)
-print(f"{case} variant {variant}: {us:.2f} us/launch device, host issue {1e6*(t1-t0)/(reps*nsets):.2f} us/launch, {n/us:.3f} Mcrops/s")
+print(f"{case} variant {variant} overlap {overlap}: {us:.2f} us/launch device, host issue {1e6*(t1-t0)/(reps*nsets):.2f} us/launch, {n/us:.3f} Mcrops/s")
 w0 = sets[0][0]
 idx = list(range(0, n, max(1, n // 6)))
 want = util.run_oracle(w0.image, [w0.rects[i] for i in idx], w0.dsize, w0.ops)
