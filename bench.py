@@ -256,7 +256,9 @@ def workload_config(n_frames: int):
             "frames_per_step": n_frames, "crops_per_step": n_frames * CROPS_PER_FRAME,
             "l2_policy": f"inputs larger than L2: {n_frames} rotating frame/tensor sets = "
                          f"{n_frames * (FRAME[1] * PITCH + CROPS_PER_FRAME * 3 * DST[0] * DST[1] * 4) / 1e6:.0f} MB",
-            "fp_contract": "reference_fused", "interp_mode": "float", "sharding": "frames per GPU, no collective"}
+            "fp_contract": "reference_fused", "interp_mode": "float", "sharding": "frames per GPU, no collective",
+            "launch_api": "cvgs_b200_preproc_launch_ex (crops + parent frame), consecutive independent frames may "
+                          "overlap (cvgs_b200_set_overlap(1))"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -338,7 +340,10 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int):
     # argument sets of the C-ABI frame loops
     crop_sets = [util.host_crops(img, rects, base_ptr=d.data_ptr()) for (img, rects), d in zip(frames, d_imgs)]
     pipes = [util.make_pipeline(DST, OPS, out_ptr=o.data_ptr()) for o in d_outs]
+    parent_sets = [util.host_parents(img, FRAME[0], FRAME[1], CROPS_PER_FRAME, base_ptr=d.data_ptr())
+                   for (img, _), d in zip(frames, d_imgs)]
     crops_pp = (C.POINTER(_abi.Crop) * F)(*[C.cast(c, C.POINTER(_abi.Crop)) for c in crop_sets])
+    parents_pp = (C.POINTER(_abi.Parent) * F)(*[C.cast(c, C.POINTER(_abi.Parent)) for c in parent_sets])
     pipes_pp = (C.POINTER(_abi.Pipeline) * F)(*[C.pointer(p) for p in pipes])
     n_arr = (C.c_int32 * F)(*[CROPS_PER_FRAME] * F)
     rect_sets = [(_abi.Rect * CROPS_PER_FRAME)(*[_abi.Rect(*r) for r in rects]) for _, rects in frames]
@@ -351,8 +356,13 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int):
     stream = torch.cuda.Stream()
     sp = stream.cuda_stream
 
+    # What the header shim emits for cvGS::executeOperations on GpuMat ROIs of a frame: the crops plus the frame they
+    # were cut from (GpuMat::datastart / locateROI).  Consecutive frames are independent; the library is allowed to
+    # prove that and overlap them (cvgs_b200_set_overlap, see include/cvgs_b200.h).
+    lib.cvgs_b200_set_overlap(0 if args.no_overlap else 1)
+
     def device_steps(n):
-        _abi.check(lib.cvgs_b200_preproc_launch_sequence(crops_pp, n_arr, n_arr, pipes_pp, F, F * n, sp))
+        _abi.check(lib.cvgs_b200_preproc_launch_sequence_ex(crops_pp, parents_pp, n_arr, n_arr, pipes_pp, F, F * n, sp))
 
     def host_steps(n):
         _abi.check(lib.cvgs_b200_preproc_host_sequence(himg_pp, FRAME[0], FRAME[1], PITCH, rects_pp, n_arr, n_arr,
@@ -432,7 +442,8 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int):
         "data": "synthetic", "config": workload_config(F),
         "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": int(h2d_bytes(frames)),
                 "d2h_bytes_per_step": int(bytes_out * F), "ms_per_step": ms_e2e / K,
-                "api": "cvgs_b200_preproc_host_sequence (pinned host frames -> pinned host tensors)"},
+                "api": "cvgs_b200_preproc_host_sequence (pinned host frames -> pinned host tensors, 3 frames in "
+                       "flight: upload / kernel / download overlap)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "preproc kernel (one launch per frame)", "peak_source": peak_src,
@@ -471,17 +482,19 @@ def c3_extra(lib, torch, _abi, util, stream, reps=20):
         d_out = torch.empty((256, 3, 224, 224), dtype=torch.float32, device="cuda")
         crops = util.host_crops(w.image, w.rects, base_ptr=d_img.data_ptr())
         pipe = util.make_pipeline(w.dsize, w.ops, out_ptr=d_out.data_ptr())
-        sets.append((w, d_img, d_out, crops, pipe))
+        par = util.host_parents(w.image, w.width, w.height, len(w.rects), base_ptr=d_img.data_ptr())
+        sets.append((w, d_img, d_out, crops, pipe, par))
     n = len(sets)
     crops_pp = (C.POINTER(_abi.Crop) * n)(*[C.cast(s[3], C.POINTER(_abi.Crop)) for s in sets])
     pipes_pp = (C.POINTER(_abi.Pipeline) * n)(*[C.pointer(s[4]) for s in sets])
+    par_pp = (C.POINTER(_abi.Parent) * n)(*[C.cast(s[5], C.POINTER(_abi.Parent)) for s in sets])
     n_arr = (C.c_int32 * n)(*[256] * n)
     sp = stream.cuda_stream
-    _abi.check(lib.cvgs_b200_preproc_launch_sequence(crops_pp, n_arr, n_arr, pipes_pp, n, 4, sp))
+    _abi.check(lib.cvgs_b200_preproc_launch_sequence_ex(crops_pp, par_pp, n_arr, n_arr, pipes_pp, n, 4, sp))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record(stream)
-    _abi.check(lib.cvgs_b200_preproc_launch_sequence(crops_pp, n_arr, n_arr, pipes_pp, n, reps, sp))
+    _abi.check(lib.cvgs_b200_preproc_launch_sequence_ex(crops_pp, par_pp, n_arr, n_arr, pipes_pp, n, reps, sp))
     e1.record(stream)
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
@@ -515,6 +528,7 @@ def main():
     ap.add_argument("--frames", type=int, default=32, help="distinct frame/tensor sets per step (> L2 in total)")
     ap.add_argument("--cpu-seconds", type=float, default=5.0, help="wall-clock budget of the CPU baseline sample")
     ap.add_argument("--no-baselines", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="plain stream order between consecutive launches")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -42,6 +42,10 @@ class Pipeline(C.Structure):
                 ("out_plane_stride", C.c_int64)]
 
 
+class Parent(C.Structure):
+    _fields_ = [("datastart", C.c_void_p), ("whole_width", C.c_int32), ("whole_height", C.c_int32)]
+
+
 class Rect(C.Structure):
     _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
 
@@ -51,6 +55,12 @@ SYMBOLS = {
     "cvgs_b200_version": (C.c_int, []),
     "cvgs_b200_last_error": (C.c_char_p, []),
     "cvgs_b200_preproc_launch": (C.c_int, [C.POINTER(Crop), C.c_int32, C.c_int32, C.POINTER(Pipeline), C.c_void_p]),
+    "cvgs_b200_preproc_launch_ex": (C.c_int, [C.POINTER(Crop), C.POINTER(Parent), C.c_int32, C.c_int32,
+                                              C.POINTER(Pipeline), C.c_void_p]),
+    "cvgs_b200_preproc_launch_sequence_ex": (C.c_int, [C.POINTER(C.POINTER(Crop)), C.POINTER(C.POINTER(Parent)),
+                                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                                       C.POINTER(C.POINTER(Pipeline)), C.c_int32, C.c_int32,
+                                                       C.c_void_p]),
     "cvgs_b200_preproc_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Rect), C.c_int32,
                                          C.c_int32, C.POINTER(Pipeline), C.c_void_p, C.c_void_p]),
     "cvgs_b200_preproc_launch_sequence": (C.c_int, [C.POINTER(C.POINTER(Crop)), C.POINTER(C.c_int32),

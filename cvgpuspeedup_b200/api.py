@@ -32,10 +32,14 @@ class GpuMat:
     """Minimal cv::cuda::GpuMat stand-in: the wrapper only ever touches data/cols/rows/step
     (reference include/cvGPUSpeedup.cuh:36,42,69)."""
 
-    __slots__ = ("data", "cols", "rows", "step", "_owner")
+    __slots__ = ("data", "cols", "rows", "step", "_owner", "datastart", "whole")
 
-    def __init__(self, data: int, cols: int, rows: int, step: int, owner=None):
+    def __init__(self, data: int, cols: int, rows: int, step: int, owner=None, datastart: Optional[int] = None,
+                 whole: Optional[Tuple[int, int]] = None):
         self.data, self.cols, self.rows, self.step, self._owner = int(data), int(cols), int(rows), int(step), owner
+        # cv::cuda::GpuMat::datastart / locateROI(wholeSize, ofs): the image this header was cut from
+        self.datastart = int(data) if datastart is None else int(datastart)
+        self.whole = (int(cols), int(rows)) if whole is None else (int(whole[0]), int(whole[1]))
 
     @classmethod
     def from_tensor(cls, t) -> "GpuMat":
@@ -48,7 +52,8 @@ class GpuMat:
         """d_input(cv::Rect(x, y, w, h))"""
         if x < 0 or y < 0 or w <= 0 or h <= 0 or x + w > self.cols or y + h > self.rows:
             raise ValueError("ROI outside the image")
-        return GpuMat(self.data + y * self.step + 3 * x, w, h, self.step, owner=self._owner)
+        return GpuMat(self.data + y * self.step + 3 * x, w, h, self.step, owner=self._owner, datastart=self.datastart,
+                      whole=self.whole)
 
 
 def _scalar3(s) -> Tuple[float, float, float]:
@@ -201,8 +206,11 @@ def executeOperations(stream, *iops, fp_contract: int = FP_REFERENCE_FUSED, inte
     p = build_pipeline(rs.dsize, mid, rs.background, rs.aspect, fp_contract, interp_mode, wr.out_ptr, wr.layout,
                        wr.plane_stride)
     crops = make_crops(rs.crops[:rs.used])
+    parents = (_abi.Parent * max(1, rs.used))()
+    for i, m in enumerate(rs.crops[:rs.used]):
+        parents[i].datastart, parents[i].whole_width, parents[i].whole_height = m.datastart, m.whole[0], m.whole[1]
     lib = _abi.load()
-    _abi.check(lib.cvgs_b200_preproc_launch(crops, len(rs.crops), rs.used, C.byref(p), _stream_ptr(stream)))
+    _abi.check(lib.cvgs_b200_preproc_launch_ex(crops, parents, len(rs.crops), rs.used, C.byref(p), _stream_ptr(stream)))
 
 
 class CircularTensor:

@@ -14,13 +14,19 @@ namespace cvgs {
 // One source crop plus the resize geometry the host derived for it
 // (= fk::RawPtr<_2D,uchar3> + fk::ResizeReadParams, reference resize.cuh:43-58).
 struct __align__(16) DevCrop {
-    const uint8_t* data;  // first pixel of the ROI
+    union {
+        const uint8_t* data;  // first pixel of the ROI (direct-gather and CircularTensor kernels)
+        struct {              // TMA-staged kernel: where the ROI sits inside the tensor map it is staged through
+            int32_t xb;       //   byte offset of the ROI's first pixel within a row of the map
+            int32_t y0;       //   row of the map that holds the ROI's first row
+        } m;
+    };
     int32_t w, h;         // source size in pixels
     int32_t pitch;        // bytes between rows
     float fx, fy;         // src_conv_factors
     int32_t bx1, by1;     // band that receives the image (aspect-ratio modes); whole plane otherwise
     int32_t bx2, by2;
-    int32_t pad;
+    int32_t pad;          // TMA-staged kernel: bits 0..15 staged row bytes, bits 16..31 index of the tensor map
 };
 static_assert(sizeof(DevCrop) == 48, "DevCrop layout");
 

@@ -207,9 +207,18 @@ struct HostPath {
     size_t out_cap = 0;
     int device = -1;
 };
+constexpr int kHostLanes = 3;  // frames in flight in the host-buffer frame loop (copy engines + SMs overlap)
+struct HostLanes {
+    cudaStream_t stream[kHostLanes] = {};
+    cudaEvent_t done[kHostLanes] = {};
+    cudaEvent_t start = nullptr;
+    int device = -1;
+};
 struct Ctx {
     Ring ring;
-    HostPath host;
+    HostPath host;           // cvgs_b200_preproc_host: caller's stream
+    HostPath lane_buf[kHostLanes];  // cvgs_b200_preproc_host_sequence: one staging set per lane
+    HostLanes lanes;
     int sm_count = 0;
     int sm_count_device = -1;
     ~Ctx() {
@@ -221,6 +230,13 @@ struct Ctx {
         }
         if (host.d_img) cudaFree(host.d_img);
         if (host.d_out) cudaFree(host.d_out);
+        for (int i = 0; i < kHostLanes; ++i) {
+            if (lane_buf[i].d_img) cudaFree(lane_buf[i].d_img);
+            if (lane_buf[i].d_out) cudaFree(lane_buf[i].d_out);
+            if (lanes.stream[i]) cudaStreamDestroy(lanes.stream[i]);
+            if (lanes.done[i]) cudaEventDestroy(lanes.done[i]);
+        }
+        if (lanes.start) cudaEventDestroy(lanes.start);
     }
 };
 static thread_local Ctx t_ctx;
@@ -282,9 +298,60 @@ static int launch_direct(const PreprocParams& P, const ParamCropTable* table, cu
     return CVGS_OK;
 }
 
-// Shared by the batch entry point and the host-buffer entry point.
-static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_pipeline_t* pipe,
-                               float* out, cudaStream_t stream) {
+// Image-mode preparation: bind every crop to a cached per-image tensor map.  Returns the number of distinct maps
+// written to `maps` (<= max_maps), or -1 when the launch cannot use image maps (unknown / inconsistent parents,
+// more maps than fit): the caller then falls back to one map per crop.  On failure the crops are left untouched.
+static thread_local ImageMapCache t_image_maps;
+static int prepare_image_maps(DevCrop* dc, const cvgs_parent_t* parents, int used, const TmaGeom& G, int W,
+                              CUtensorMap* maps, int max_maps) {
+    if (!parents || used <= 0) return -1;
+    struct Slot { uintptr_t datastart; int rb; };
+    Slot slots[kTmaImageMaps];
+    int idx_of[kTmaParamCrops];
+    int rb_of[kTmaParamCrops];
+    int n_maps = 0;
+    if (max_maps > kTmaImageMaps) max_maps = kTmaImageMaps;
+    // pass 1: nothing is modified until every crop is known to fit
+    std::vector<int> idx_big, rb_big;
+    int* idx = idx_of;
+    int* rbs = rb_of;
+    if (used > kTmaParamCrops) {
+        idx_big.resize(used);
+        rb_big.resize(used);
+        idx = idx_big.data();
+        rbs = rb_big.data();
+    }
+    for (int i = 0; i < used; ++i) {
+        const cvgs_parent_t& p = parents[i];
+        if (!p.datastart || p.whole_width <= 0 || p.whole_height <= 0) return -1;
+        const int rb = rb_class(band_row_bytes(std::min(32 * G.NPB, W), dc[i].fx));
+        if (rb == 0 || 4 * rb + kSlotHeader > G.slot_bytes) return -1;
+        const uintptr_t ds = reinterpret_cast<uintptr_t>(p.datastart);
+        int k = 0;
+        for (; k < n_maps; ++k)
+            if (slots[k].datastart == ds && slots[k].rb == rb) break;
+        if (k == n_maps) {
+            if (n_maps == max_maps) return -1;
+            const CUtensorMap* m = t_image_maps.get(ds, dc[i].pitch, p.whole_width, p.whole_height, rb);
+            if (!m) return -1;
+            maps[n_maps] = *m;
+            slots[n_maps++] = Slot{ds, rb};
+        }
+        // geometry check without modifying the crop
+        DevCrop probe = dc[i];
+        if (!tma_place_in_image(probe, ds, p.whole_width, p.whole_height, rb, k)) return -1;
+        idx[i] = k;
+        rbs[i] = rb;
+    }
+    for (int i = 0; i < used; ++i)
+        tma_place_in_image(dc[i], reinterpret_cast<uintptr_t>(parents[i].datastart), parents[i].whole_width,
+                           parents[i].whole_height, rbs[i], idx[i]);
+    return n_maps;
+}
+
+// Shared by the batch entry points and the host-buffer entry point.
+static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* parents, int n_planes, int used,
+                               const cvgs_pipeline_t* pipe, float* out, cudaStream_t stream) {
     if (int rc = validate_pipeline(pipe)) return rc;
     if (!out) return fail(CVGS_ERR_INVALID_VALUE, "output pointer is NULL");
     if (n_planes <= 0) return fail(CVGS_ERR_INVALID_VALUE, "n_planes must be positive");
@@ -303,7 +370,8 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used,
     if (used <= kTmaParamCrops) {
         // small batch: descriptors (and tensor maps) ride in the kernel parameters -- no staging copy,
         // graph-capturable
-        alignas(64) TmaParamTable tt;
+        alignas(64) TmaParamTable tt;  // also serves as the image-mode table (its first maps / same crop array offset
+                                       // are copied into a TmaImageTable below)
         const double t0 = now_us();
         for (int i = 0; i < used; ++i)
             if (int rc = fill_crop(crops[i], *pipe, i, tt.c[i])) return rc;
@@ -311,27 +379,65 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used,
         TmaParams K;
         K.P = P;
         K.maps = nullptr;
-        if (variant != 1 && tma_plan(P, tt.c, used, n_planes, sms, K.G)) {
+        if (variant != 1 && tma_plan(P, tt.c, used, n_planes, sms, parents != nullptr, K.G)) {
             const int chain = scaled_program(P, K);
+            const MemRange src = crops_range(tt.c, used);  // before the TMA fields overwrite the pointers
             const double t2 = now_us();
+            // image mode first (cached maps, small parameter block); else one map per crop
+            alignas(64) TmaImageTable it;
+            DevCrop saved[kTmaParamCrops];
+            std::memcpy(saved, tt.c, static_cast<size_t>(used) * sizeof(DevCrop));
+            const int n_img = prepare_image_maps(tt.c, parents, used, K.G, P.W, it.m, kTmaImageMaps);
+            int rc = -1;
+            if (n_img >= 0) {
+                std::memcpy(it.c, tt.c, static_cast<size_t>(used) * sizeof(DevCrop));
+                const double t3 = now_us();
+                K.G.pdl_wait = overlap_needs_wait(stream, out_range(P), src) ? 1 : 0;
+                rc = tma_launch_kernel<TmaImageTable>(K, it, chain, device, stream);
+                const double t4 = now_us();
+                t_prof.fill += t1 - t0; t_prof.plan += t2 - t1; t_prof.encode += t3 - t2; t_prof.launch += t4 - t3;
+                ++t_prof.calls;
+                return rc;
+            }
             bool ok = true;
-            for (int i = 0; i < used && ok; ++i) ok = tma_prepare_crop(tt.c[i], K.G, P.W, &tt.m[i]) == CVGS_OK;
+            for (int i = 0; i < used && ok; ++i) ok = tma_prepare_crop(tt.c[i], K.G, P.W, i, &tt.m[i]) == CVGS_OK;
             const double t3 = now_us();
             if (ok) {
-                K.G.pdl_wait = overlap_needs_wait(stream, out_range(P), crops_range(tt.c, used)) ? 1 : 0;
-                const int rc = tma_launch_kernel<TmaParamTable>(K, tt, chain, device, stream);
+                K.G.pdl_wait = overlap_needs_wait(stream, out_range(P), src) ? 1 : 0;
+                rc = tma_launch_kernel<TmaParamTable>(K, tt, chain, device, stream);
                 const double t4 = now_us();
                 t_prof.fill += t1 - t0; t_prof.plan += t2 - t1; t_prof.encode += t3 - t2; t_prof.launch += t4 - t3;
                 ++t_prof.calls;
                 return rc;
             }
             // the driver refused a tensor map (exotic geometry): the direct-gather kernel takes anything
+            std::memcpy(tt.c, saved, static_cast<size_t>(used) * sizeof(DevCrop));
         }
         if (variant == 2) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
         ParamCropTable table;
         std::memcpy(table.c, tt.c, static_cast<size_t>(used) * sizeof(DevCrop));
         overlap_forget(stream);
         return launch_direct(P, &table, stream);
+    }
+
+    if (used <= kTmaImageCrops && parents && variant != 1) {
+        // medium batch with named parent images: a few cached maps + the descriptors still fit the kernel
+        // parameters (13 KB), so there is no staging copy in front of the kernel
+        alignas(64) TmaImageTableL lt;
+        bool filled = true;
+        for (int i = 0; i < used && filled; ++i) filled = fill_crop(crops[i], *pipe, i, lt.c[i]) == CVGS_OK;
+        if (!filled) return CVGS_ERR_INVALID_VALUE;  // message already recorded by fill_crop
+        TmaParams K;
+        K.P = P;
+        K.maps = nullptr;
+        if (tma_plan(P, lt.c, used, n_planes, sms, true, K.G)) {
+            const int chain = scaled_program(P, K);
+            const MemRange src = crops_range(lt.c, used);
+            if (prepare_image_maps(lt.c, parents, used, K.G, P.W, lt.m, kTmaImageMaps) >= 0) {
+                K.G.pdl_wait = overlap_needs_wait(stream, out_range(P), src) ? 1 : 0;
+                return tma_launch_kernel<TmaImageTableL>(K, lt, chain, device, stream);
+            }
+        }
     }
 
     Ring& r = t_ctx.ring;
@@ -344,24 +450,29 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, int n_planes, int used,
         if (int rc = fill_crop(crops[i], *pipe, i, hc[i])) return rc;
     TmaParams K;
     K.P = P;
-    bool use_tma = variant != 1 && tma_plan(P, hc, used, n_planes, sms, K.G);
+    bool use_tma = variant != 1 && tma_plan(P, hc, used, n_planes, sms, parents != nullptr, K.G);
     int chain = CH_GENERIC;
+    size_t map_bytes = 0;
     if (use_tma) {
         chain = scaled_program(P, K);
         CUtensorMap* hm = r.maps_h(slot);
-        for (int i = 0; i < used && use_tma; ++i) use_tma = tma_prepare_crop(hc[i], K.G, P.W, &hm[i]) == CVGS_OK;
+        // maps sit in front of the crops in the slot; image mode needs only a few of them
+        const int n_img = prepare_image_maps(hc, parents, used, K.G, P.W, hm, kTmaImageMaps);
+        if (n_img >= 0) {
+            map_bytes = static_cast<size_t>(n_img) * sizeof(CUtensorMap);
+        } else {
+            for (int i = 0; i < used && use_tma; ++i) use_tma = tma_prepare_crop(hc[i], K.G, P.W, i, &hm[i]) == CVGS_OK;
+            map_bytes = static_cast<size_t>(used) * sizeof(CUtensorMap);
+            if (!use_tma)  // restore the pointers the failed preparation overwrote
+                for (int i = 0; i < used; ++i)
+                    if (int rc = fill_crop(crops[i], *pipe, i, hc[i])) return rc;
+        }
     }
     if (!use_tma && variant == 2) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
-    size_t bytes = static_cast<size_t>(used) * sizeof(DevCrop);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(hc);
-    uint8_t* dst = reinterpret_cast<uint8_t*>(r.crops_d(slot));
-    if (use_tma) {
-        // maps and crops are adjacent in the slot: one copy covers both
-        src = reinterpret_cast<const uint8_t*>(r.maps_h(slot));
-        dst = reinterpret_cast<uint8_t*>(r.maps_d(slot));
-        bytes = r.cap * sizeof(CUtensorMap) + static_cast<size_t>(used) * sizeof(DevCrop);
-    }
-    CVGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    // one or two copies: the maps actually used, and the crop descriptors
+    if (use_tma)
+        CVGS_CUDA(cudaMemcpyAsync(r.maps_d(slot), r.maps_h(slot), map_bytes, cudaMemcpyHostToDevice, stream));
+    CVGS_CUDA(cudaMemcpyAsync(r.crops_d(slot), hc, static_cast<size_t>(used) * sizeof(DevCrop), cudaMemcpyHostToDevice, stream));
     int rc;
     if (use_tma) {
         K.P.crops = r.crops_d(slot);
@@ -421,13 +532,21 @@ int cvgs_b200_debug_host_profile(double* out5, int reset) {
 int cvgs_b200_preproc_launch(const cvgs_crop_t* crops, int32_t n_planes, int32_t used,
                              const cvgs_pipeline_t* pipeline, void* stream) {
     if (!pipeline) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
-    return preproc_launch_impl(crops, n_planes, used, pipeline, static_cast<float*>(pipeline->out),
+    return preproc_launch_impl(crops, nullptr, n_planes, used, pipeline, static_cast<float*>(pipeline->out),
                                static_cast<cudaStream_t>(stream));
 }
 
-int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t image_height, int32_t image_pitch,
-                           const cvgs_rect_t* rects, int32_t n_planes, int32_t used,
-                           const cvgs_pipeline_t* pipeline, float* host_out, void* stream_) {
+int cvgs_b200_preproc_launch_ex(const cvgs_crop_t* crops, const cvgs_parent_t* parents, int32_t n_planes, int32_t used,
+                                const cvgs_pipeline_t* pipeline, void* stream) {
+    if (!pipeline) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
+    return preproc_launch_impl(crops, parents, n_planes, used, pipeline, static_cast<float*>(pipeline->out),
+                               static_cast<cudaStream_t>(stream));
+}
+
+static int preproc_host_impl(HostPath& h, const void* host_image, int32_t image_width, int32_t image_height,
+                             int32_t image_pitch, const cvgs_rect_t* rects, int32_t n_planes, int32_t used,
+                             const cvgs_pipeline_t* pipeline, float* host_out, void* stream_,
+                             cudaEvent_t download_after = nullptr, cudaEvent_t download_done = nullptr) {
     if (int rc = validate_pipeline(pipeline)) return rc;
     if (!host_image || !host_out || !rects) return fail(CVGS_ERR_INVALID_VALUE, "NULL host buffer");
     if (image_width <= 0 || image_height <= 0 || image_pitch < 3 * image_width)
@@ -441,8 +560,7 @@ int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t 
     const size_t d_pitch = (static_cast<size_t>(3) * image_width + 511) / 512 * 512;
     const size_t img_bytes = d_pitch * image_height;
     const size_t out_floats = static_cast<size_t>(3) * pipeline->dst_width * pipeline->dst_height * n_planes;
-    if (int rc = host_reserve(t_ctx.host, img_bytes, out_floats * sizeof(float), device)) return rc;
-    HostPath& h = t_ctx.host;
+    if (int rc = host_reserve(h, img_bytes, out_floats * sizeof(float), device)) return rc;
 
     // upload only the rows some crop touches
     int y_lo = image_height, y_hi = 0;
@@ -468,9 +586,22 @@ int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t 
     }
     cvgs_pipeline_t p = *pipeline;
     p.out_plane_stride = 0;
-    if (int rc = preproc_launch_impl(crops.data(), n_planes, used, &p, h.d_out, stream)) return rc;
+    // every crop is a rectangle of the staging image: per-image tensor maps
+    std::vector<cvgs_parent_t> parents(static_cast<size_t>(used), cvgs_parent_t{h.d_img, image_width, image_height});
+    if (int rc = preproc_launch_impl(crops.data(), parents.data(), n_planes, used, &p, h.d_out, stream)) return rc;
+    // frame loop: downloads complete in frame order whatever lane they run on (a later frame may write the same
+    // host tensor as an earlier one)
+    if (download_after) CVGS_CUDA(cudaStreamWaitEvent(stream, download_after, 0));
     CVGS_CUDA(cudaMemcpyAsync(host_out, h.d_out, out_floats * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    if (download_done) CVGS_CUDA(cudaEventRecord(download_done, stream));
     return CVGS_OK;
+}
+
+int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t image_height, int32_t image_pitch,
+                           const cvgs_rect_t* rects, int32_t n_planes, int32_t used,
+                           const cvgs_pipeline_t* pipeline, float* host_out, void* stream) {
+    return preproc_host_impl(t_ctx.host, host_image, image_width, image_height, image_pitch, rects, n_planes, used, pipeline,
+                             host_out, stream);
 }
 
 int cvgs_b200_preproc_launch_sequence(const cvgs_crop_t* const* crops, const int32_t* n_planes, const int32_t* used,
@@ -485,19 +616,56 @@ int cvgs_b200_preproc_launch_sequence(const cvgs_crop_t* const* crops, const int
     return CVGS_OK;
 }
 
-int cvgs_b200_preproc_host_sequence(const void* const* host_images, int32_t image_width, int32_t image_height,
-                                    int32_t image_pitch, const cvgs_rect_t* const* rects, const int32_t* n_planes,
-                                    const int32_t* used, const cvgs_pipeline_t* const* pipelines,
-                                    float* const* host_outs, int32_t n_sets, int32_t steps, void* stream) {
-    if (!host_images || !rects || !n_planes || !used || !pipelines || !host_outs || n_sets <= 0 || steps < 0)
+int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const cvgs_parent_t* const* parents,
+                                         const int32_t* n_planes, const int32_t* used,
+                                         const cvgs_pipeline_t* const* pipelines, int32_t n_sets, int32_t steps,
+                                         void* stream) {
+    if (!crops || !parents || !n_planes || !used || !pipelines || n_sets <= 0 || steps < 0)
         return fail(CVGS_ERR_INVALID_VALUE, "bad sequence arguments");
     for (int i = 0; i < steps; ++i) {
         const int s = i % n_sets;
-        if (int rc = cvgs_b200_preproc_host(host_images[s], image_width, image_height, image_pitch, rects[s],
-                                            n_planes[s], used[s], pipelines[s], host_outs[s], stream))
-            return rc;
+        if (int rc = cvgs_b200_preproc_launch_ex(crops[s], parents[s], n_planes[s], used[s], pipelines[s], stream)) return rc;
     }
     return CVGS_OK;
+}
+
+int cvgs_b200_preproc_host_sequence(const void* const* host_images, int32_t image_width, int32_t image_height,
+                                    int32_t image_pitch, const cvgs_rect_t* const* rects, const int32_t* n_planes,
+                                    const int32_t* used, const cvgs_pipeline_t* const* pipelines,
+                                    float* const* host_outs, int32_t n_sets, int32_t steps, void* stream_) {
+    if (!host_images || !rects || !n_planes || !used || !pipelines || !host_outs || n_sets <= 0 || steps < 0)
+        return fail(CVGS_ERR_INVALID_VALUE, "bad sequence arguments");
+    // The frames are independent (each has its own host image and host tensor), so the loop keeps kHostLanes of
+    // them in flight on internal streams: the upload of frame i+1 overlaps the kernel of frame i and the download
+    // of frame i-1 (two copy engines + SMs).  Seen from the caller's stream the loop is one operation: it starts
+    // after everything queued before it and everything queued after it waits for its last frame.
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int device = 0;
+    CVGS_CUDA(cudaGetDevice(&device));
+    HostLanes& L = t_ctx.lanes;
+    if (L.device != device) {
+        for (int i = 0; i < kHostLanes; ++i) {
+            if (L.stream[i]) { cudaStreamDestroy(L.stream[i]); L.stream[i] = nullptr; }
+            if (L.done[i]) { cudaEventDestroy(L.done[i]); L.done[i] = nullptr; }
+            CVGS_CUDA(cudaStreamCreateWithFlags(&L.stream[i], cudaStreamNonBlocking));
+            CVGS_CUDA(cudaEventCreateWithFlags(&L.done[i], cudaEventDisableTiming));
+        }
+        if (L.start) { cudaEventDestroy(L.start); L.start = nullptr; }
+        CVGS_CUDA(cudaEventCreateWithFlags(&L.start, cudaEventDisableTiming));
+        L.device = device;
+    }
+    CVGS_CUDA(cudaEventRecord(L.start, stream));
+    for (int i = 0; i < kHostLanes; ++i) CVGS_CUDA(cudaStreamWaitEvent(L.stream[i], L.start, 0));
+    int rc = CVGS_OK;
+    for (int i = 0; i < steps && rc == CVGS_OK; ++i) {
+        const int s = i % n_sets, lane = i % kHostLanes;
+        rc = preproc_host_impl(t_ctx.lane_buf[lane], host_images[s], image_width, image_height, image_pitch, rects[s],
+                               n_planes[s], used[s], pipelines[s], host_outs[s], L.stream[lane],
+                               i > 0 ? L.done[(i - 1) % kHostLanes] : nullptr, L.done[lane]);
+    }
+    // every lane ends with a recorded download (or was never used): the caller's stream resumes after all of them
+    for (int i = 0; i < kHostLanes && i < steps; ++i) CVGS_CUDA(cudaStreamWaitEvent(stream, L.done[i], 0));
+    return rc;
 }
 
 }  // extern "C"

@@ -1,19 +1,21 @@
-// preproc_tma.cuh -- persistent, warp-specialised, TMA-staged kernel of the fused batch path (sm_100a).
+// preproc_tma.cuh -- persistent, TMA-staged kernel of the fused batch path (sm_100a).
 //
 // Same function as preproc_direct_kernel (preproc.cu) and as the reference instantiation of
 // fk::launchTransformDPP_Kernel it replaces (reference fkl/include/fused_kernel/core/execution_model/
 // data_parallel_patterns.cuh:157-197; BatchRead batch_operations.cuh:222-229; Resize resize.cuh:70-82,178-189;
-// Interpolate interpolation.cuh:57-92; TensorSplit memory_operations.cuh:168-188), organised around the two
-// budgets that bound the path on B200: issue slots and shared-memory wavefronts per output pixel.
+// Interpolate interpolation.cuh:57-92; TensorSplit memory_operations.cuh:168-188), organised around the budgets
+// that bound the path on B200: issue slots and shared-memory wavefronts per output pixel, and the
+// latency of the staging pipeline.
 //
-//   * a CTA walks a contiguous range of tiles; a tile = TR output rows x TW = 32*NP output columns of one crop;
-//   * the producer warp stages, per output row of the tile, the two source rows it taps with ONE
-//     cp.async.bulk.tensor.2d (box = 2 rows x the tile's source span; byte-exact start coordinate through a
-//     per-crop tensor map of 8-byte elements), completion on a per-stage mbarrier, and leaves the vertical taps of
-//     the row (staged-row offsets + weights) next to the data, so consumers never convert or multiply for them;
-//   * a consumer warp owns row PAIRS; lane l owns columns l, l+32, ... of the band (adjacent lanes read adjacent
-//     source bytes: few shared-memory wavefronts; stores are full 128-byte lines).  The horizontal taps are
-//     computed once per (crop, band), and the two rows of a pair ride in the two halves of packed-FP32
+//   * the unit of work is an ITEM = one pair of output rows (2j, 2j+1) x one band of up to 128 output columns of one
+//     crop; every warp owns a contiguous range of items and feeds itself: it stages the four source rows its next
+//     items tap with cp.async.bulk.tensor.2d (one box of 2 source rows per output row, byte-exact start coordinate
+//     through a per-crop tensor map of 8-byte elements) into its private ring of shared-memory slots, completion
+//     on a per-slot mbarrier.  No producer warp, no cross-warp synchronisation: a slot is refilled by the warp
+//     that just finished reading it;
+//   * lane l owns columns l, l+32, ... of the band (adjacent lanes read adjacent source bytes: few shared-memory
+//     wavefronts; stores are full 128-byte lines).  The horizontal taps are computed once per (crop, band), the
+//     vertical ones once per item by two lanes; the two rows of the pair ride in the two halves of packed-FP32
 //     instructions (FMUL2 / FFMA2, sm_100): one issue slot per two roundings, each still IEEE round-to-nearest;
 //   * u8 -> f32 is one PRMT: byte b placed at bits 16..23 of a float word is exactly b * 2^-133 (exponent
 //     field 0 or 1, both scale 2^-149); the vertical weights carry 2^100 and the first op of the chain the
@@ -37,12 +39,12 @@
 namespace cvgs {
 
 constexpr int kTmaParamCrops = 64;      // crops (descriptor + tensor map) that ride in the kernel parameters
-constexpr int kConsumerWarps = 4;
-constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kTmaThreads = kConsumerThreads + 32;  // + producer warp (the last one)
-constexpr int kStages = 4;
+constexpr int kWarps = 4;               // warps per CTA, each with its own slot ring
+constexpr int kTmaThreads = kWarps * 32;
+constexpr int kMaxSlots = 4;            // slots per warp
 constexpr int kMaxNP = 4;               // 32-column groups per band: a band is at most 128 output columns
-constexpr int kStagePad = 128;          // bytes in front of / behind the stage ring (w[-1] / w[+1] over-reads)
+constexpr int kSlotHeader = 128;        // per slot: two RowInfo records (+ room for the w[-1] over-read)
+constexpr int kRingPad = 128;           // bytes behind the last slot (w[+1] over-read)
 constexpr int kMaxBoxBytes = 2048;      // 256 elements x 8 bytes
 constexpr float kWeightScale = 1.2676506002282294e30f;  // 2^100
 constexpr float kPreScale = 8589934592.0f;              // 2^33  = 2^133 / 2^100
@@ -51,15 +53,16 @@ constexpr uint32_t kRowSkip = 0xFFFFFFFFu;  // RowInfo::offA: row is below the p
 
 struct TmaGeom {
     int32_t NPB;             // 32-column groups per band (1..kMaxNP); band width TW = 32 * NPB
-    int32_t TR;              // output rows per tile (even)
-    int32_t tiles_x, tiles_y, tiles_per_crop, total_tiles;
-    int32_t info_bytes;      // per stage: TR RowInfo records, rounded to 128 bytes
-    int32_t stage_bytes;     // info_bytes + TR * 2 * max row bytes
-    int32_t stages;          // depth of the stage ring actually used (1..kStages)
+    int32_t HP;              // row pairs per plane = ceil(H / 2)
+    int32_t tiles_x;         // bands per plane
+    int32_t items_per_crop;  // tiles_x * HP
+    int32_t total_items;
+    int32_t slot_bytes;      // kSlotHeader + 4 * max row bytes
+    int32_t slots;           // ring depth per warp (1..kMaxSlots)
     int32_t resident;        // CTAs per SM the shared-memory footprint allows
-    int32_t grid;            // CTAs; CTA b walks tiles [b*tiles_base + min(b, tiles_rem), ...)
-    int32_t tiles_base, tiles_rem;
-    int32_t explicit_prescale;  // 1: consumers multiply by 2^33 themselves (no op to fold it into)
+    int32_t grid;            // CTAs; warp g = blockIdx.x * kWarps + warp walks items [g*base + min(g, rem), ...)
+    int32_t items_base, items_rem;
+    int32_t explicit_prescale;  // 1: the kernel multiplies by 2^33 itself (no op to fold it into)
     int32_t pdl_wait;        // 1: wait for the preceding kernel before the first global access (stream order);
                              // 0: the host proved independence, wait only before exiting (completion order)
 };
@@ -72,24 +75,33 @@ struct TmaParams {
     const CUtensorMap* maps; // device table (nullptr when the maps ride in the kernel parameters)
 };
 
-struct alignas(64) TmaParamTable {
-    CUtensorMap m[kTmaParamCrops];
-    DevCrop c[kTmaParamCrops];
+// Descriptors that ride in the kernel parameters: NMAPS tensor maps + up to kTmaParamCrops crops.
+// One map per crop (NMAPS = kTmaParamCrops) when nothing is known about the memory around a crop; a handful of
+// per-image maps (NMAPS = kTmaImageMaps) when the caller names the parent images (cvgs_b200_preproc_launch_ex).
+constexpr int kTmaImageMaps = 8;
+constexpr int kTmaImageCrops = 256;     // image mode: batches up to this size still ride in the parameters (13 KB)
+template <int NMAPS, int NCROPS>
+struct alignas(64) TmaParamTableT {
+    CUtensorMap m[NMAPS];
+    DevCrop c[NCROPS];
 };
+using TmaParamTable = TmaParamTableT<kTmaParamCrops, kTmaParamCrops>;
+using TmaImageTable = TmaParamTableT<kTmaImageMaps, kTmaParamCrops>;
+using TmaImageTableL = TmaParamTableT<kTmaImageMaps, kTmaImageCrops>;
 struct TmaNoTable {
     int32_t unused;
 };
 
-// Vertical taps of one output row of a tile, written by the producer next to the staged rows.
+// Vertical taps of one output row of an item, written next to the staged rows when the item is staged.
 struct __align__(16) RowInfo {
-    uint32_t offA;   // byte offset (from the stage's data block) of the staged upper source row, or kRowFill/kRowSkip
+    uint32_t offA;   // byte offset (from the slot's data block) of the staged upper source row, or kRowFill/kRowSkip
     uint32_t offB;   // ... of the lower source row (== offA when y2 is clamped, interpolation.cuh:73)
     float wy0, wy1;  // (y2 - sy) * 2^100, (sy - y1) * 2^100
 };
 
-// DevCrop::pad of a TMA launch: bits 0..15 = smem row bytes of this crop's box, bits 16..19 = data & 15
+// DevCrop::pad of a TMA launch: bits 0..15 = smem row bytes of this crop's box, bits 16..31 = tensor map index
 __host__ __device__ __forceinline__ int32_t crop_row_bytes(const DevCrop& c) { return c.pad & 0xFFFF; }
-__host__ __device__ __forceinline__ int32_t crop_misalign(const DevCrop& c) { return (c.pad >> 16) & 15; }
+__host__ __device__ __forceinline__ int32_t crop_map_index(const DevCrop& c) { return (c.pad >> 16) & 0xFFFF; }
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers
@@ -154,9 +166,7 @@ __device__ __forceinline__ float u8_scaled(uint32_t w, uint32_t k) {
 }
 
 template <typename Table>
-__device__ __forceinline__ const DevCrop& tma_crop_of(const TmaParams& K, const Table& T, int z);
-template <>
-__device__ __forceinline__ const DevCrop& tma_crop_of<TmaParamTable>(const TmaParams&, const TmaParamTable& T, int z) {
+__device__ __forceinline__ const DevCrop& tma_crop_of(const TmaParams&, const Table& T, int z) {
     return T.c[z];
 }
 template <>
@@ -164,14 +174,12 @@ __device__ __forceinline__ const DevCrop& tma_crop_of<TmaNoTable>(const TmaParam
     return K.P.crops[z];
 }
 template <typename Table>
-__device__ __forceinline__ const CUtensorMap* tma_map_of(const TmaParams& K, const Table& T, int z);
-template <>
-__device__ __forceinline__ const CUtensorMap* tma_map_of<TmaParamTable>(const TmaParams&, const TmaParamTable& T, int z) {
-    return &T.m[z];
+__device__ __forceinline__ const CUtensorMap* tma_map_of(const TmaParams&, const Table& T, const DevCrop& C) {
+    return &T.m[crop_map_index(C)];
 }
 template <>
-__device__ __forceinline__ const CUtensorMap* tma_map_of<TmaNoTable>(const TmaParams& K, const TmaNoTable&, int z) {
-    return K.maps + z;
+__device__ __forceinline__ const CUtensorMap* tma_map_of<TmaNoTable>(const TmaParams& K, const TmaNoTable&, const DevCrop& C) {
+    return K.maps + crop_map_index(C);
 }
 
 // Where the staged span of a (crop, column band) starts: first in-band output column of the band, its left tap,
@@ -180,7 +188,7 @@ struct BandOrigin {
     int32_t xa;       // first output column of the band that receives image data (may exceed the band: empty)
     int32_t xe;       // last such column
     int32_t c0;       // box start coordinate (8-byte elements) in the crop's tensor map
-    int32_t origin;   // crop-row byte that smem byte 0 of a staged row corresponds to (= 8*c0 - misalign)
+    int32_t origin;   // crop-row byte that smem byte 0 of a staged row corresponds to (= 8*c0 - xb)
 };
 __device__ __forceinline__ BandOrigin band_origin(const PreprocParams& P, const TmaGeom& G, const DevCrop& C, int txi) {
     BandOrigin b;
@@ -188,9 +196,9 @@ __device__ __forceinline__ BandOrigin band_origin(const PreprocParams& P, const 
     b.xa = max(tx0, C.bx1);
     b.xe = min(min(tx0 + 32 * G.NPB, P.W) - 1, C.bx2);
     const AxisTap t = axis_tap(b.xa - C.bx1, C.fx);
-    const int mis = crop_misalign(C);
-    b.c0 = ((mis + 3 * t.i1) >> 4) << 1;  // the box must start on a 16-byte boundary of global memory
-    b.origin = 8 * b.c0 - mis;
+    const int xb = C.m.xb;
+    b.c0 = ((xb + 3 * t.i1) >> 4) << 1;  // the box must start on a 16-byte boundary of global memory
+    b.origin = 8 * b.c0 - xb;
     return b;
 }
 
@@ -205,34 +213,21 @@ __device__ __forceinline__ float2 div_by_const2(float2 x, float zh, float zl) {
     return __ffma2_rn(x, make_float2(zh, zh), u);
 }
 
-// Tile walk of one CTA: contiguous range, decoded once and then advanced incrementally (no divisions per tile).
-struct TileCursor {
-    int z, txi, tyi, left;
-    __device__ __forceinline__ void init(const TmaGeom& G) {
-        const int b = blockIdx.x;
-        const int t0 = b * G.tiles_base + min(b, G.tiles_rem);
-        left = G.tiles_base + (b < G.tiles_rem ? 1 : 0);
-        z = t0 / G.tiles_per_crop;
-        const int rem = t0 - z * G.tiles_per_crop;
-        txi = rem / G.tiles_y;
-        tyi = rem - txi * G.tiles_y;
-    }
-    // n tiles further down the same band (n <= tiles_y - tyi)
-    __device__ __forceinline__ void skip(const TmaGeom& G, int n) {
-        left -= n;
-        tyi += n;
-        if (tyi == G.tiles_y) {
-            tyi = 0;
-            if (++txi == G.tiles_x) {
-                txi = 0;
-                ++z;
-            }
-        }
+// Item walk of one warp: contiguous range, decoded once and then advanced incrementally.
+struct ItemCursor {
+    int z, txi, jp, left;
+    __device__ __forceinline__ void init(const TmaGeom& G, int g) {
+        const int i0 = g * G.items_base + min(g, G.items_rem);
+        left = G.items_base + (g < G.items_rem ? 1 : 0);
+        z = i0 / G.items_per_crop;
+        const int rem = i0 - z * G.items_per_crop;
+        txi = rem / G.HP;
+        jp = rem - txi * G.HP;
     }
     __device__ __forceinline__ void next(const TmaGeom& G) {
         --left;
-        if (++tyi == G.tiles_y) {
-            tyi = 0;
+        if (++jp == G.HP) {
+            jp = 0;
             if (++txi == G.tiles_x) {
                 txi = 0;
                 ++z;
@@ -304,123 +299,49 @@ __device__ __forceinline__ void apply_program_pair(const DevProgram& prog, float
     }
 }
 
+// What staging an item needs to know about its (crop, band); recomputed only when the band changes.
+struct StageBand {
+    int z, txi;
+    bool ok;               // the band receives image data at all
+    int32_t c0, rb;        // box start coordinate, staged row bytes
+    int32_t by1, by2, hm1; // image rows of the plane, last source row
+    int32_t y0;            // map row of the crop's first row
+    float fy;
+    const CUtensorMap* map;
+};
+
 // GEN = false: the common geometry -- IGNORE_AR, every plane used, planar output.
 // GEN = true : aspect-ratio bands, unused planes, packed outputs.
 template <typename Table, int CHAIN, bool GEN>
 __global__ void __launch_bounds__(kTmaThreads, 4)
 preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ Table T) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[kStages];
-    __shared__ uint64_t bar_empty[kStages];
+    __shared__ uint64_t bar_full[kWarps * kMaxSlots];
 
     const PreprocParams& P = K.P;
     const TmaGeom& G = K.G;
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int lane = tid & 31;
-    const int nstages = G.stages;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nslots = G.slots;
+    const int W = P.W, H = P.H;
+    const int TW = 32 * G.NPB;
 
     pdl_launch_dependents();  // the next kernel of the stream may start its prologue now
 
-    // stage ring, 128-byte aligned, with kStagePad bytes of slack on both sides
-    uint32_t ring = ((smem_u32(smem_raw) + 127u) & ~127u) + kStagePad;
-    asm volatile("" : "+r"(ring));  // keep it in a register (the compiler would re-derive it per use)
-
-    if (tid == 0) {
-        for (int s = 0; s < nstages; ++s) {
-            mbar_init(smem_u32(&bar_full[s]), 1);
-            mbar_init(smem_u32(&bar_empty[s]), kConsumerWarps);
-        }
+    // this warp's slot ring (128-byte aligned) and its barriers
+    const uint32_t slot_bytes = (uint32_t)G.slot_bytes;
+    uint32_t ring = ((smem_u32(smem_raw) + 127u) & ~127u) + (uint32_t)(warp * nslots) * slot_bytes;
+    uint32_t bars = smem_u32(&bar_full[warp * kMaxSlots]);
+    asm volatile("" : "+r"(ring), "+r"(bars));  // keep them in registers (the compiler would re-derive them per use)
+    if (lane == 0) {
+        for (int s = 0; s < nslots; ++s) mbar_init(bars + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncwarp();
 
-    TileCursor tc;
-    tc.init(G);
-
-    if (warp == kConsumerWarps) {
-        // ===================================== producer warp =====================================
-        if (G.pdl_wait) pdl_wait_prior_grid();  // source images may be written by the preceding kernel
-        int stage = 0;
-        uint32_t phase = 0;
-        if (K.maps) {
-            // Tensor maps that reached global memory through a host copy must be acquired for the TMA proxy once
-            // per CTA and map before their first use (not per load: the fence also drops the descriptor cache).
-            const int t_last = blockIdx.x * G.tiles_base + min((int)blockIdx.x, G.tiles_rem) + tc.left - 1;
-            const int z_last = t_last / G.tiles_per_crop;
-            for (int z = tc.z; z <= z_last; ++z)
-                asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(K.maps + z))
-                             : "memory");
-        }
-        // L2 prefetch cursor: the boxes of the tile `nstages` ahead are requested into L2 while their shared-memory
-        // slot is still occupied, so that the real load later pays L2 latency instead of DRAM latency
-        TileCursor pf = tc;
-        for (int i = 0; i < nstages && pf.left > 0; ++i) pf.next(G);
-        for (; tc.left > 0; tc.next(G)) {
-            if (pf.left > 0) {
-                const int y = pf.tyi * G.TR + lane;
-                if (lane < G.TR && y < P.H && (!GEN || pf.z < P.used)) {
-                    const DevCrop& C = tma_crop_of<Table>(K, T, pf.z);
-                    const BandOrigin b = band_origin(P, G, C, pf.txi);
-                    if (y >= C.by1 && y <= C.by2 && b.xa <= b.xe)
-                        tma_prefetch_2d(tma_map_of<Table>(K, T, pf.z), b.c0, axis_tap(y - C.by1, C.fy).i1);
-                }
-                pf.next(G);
-            }
-            // everything that does not touch the stage is computed before waiting for it: once the consumers
-            // release the slot only the RowInfo store, the arrive and the TMA issue remain
-            const uint32_t full = smem_u32(&bar_full[stage]);
-            const uint32_t sinfo = ring + stage * G.stage_bytes;
-            bool issue = false;
-            int i1 = 0, c0 = 0, rb = 0;
-            RowInfo ri;
-            ri.offA = kRowSkip;
-            ri.offB = 0;
-            ri.wy0 = ri.wy1 = 0.f;
-            if (lane < G.TR) {
-                const int y = tc.tyi * G.TR + lane;
-                if (y < P.H) {
-                    ri.offA = kRowFill;
-                    if (!GEN || tc.z < P.used) {
-                        const DevCrop& C = tma_crop_of<Table>(K, T, tc.z);
-                        const BandOrigin b = band_origin(P, G, C, tc.txi);
-                        rb = crop_row_bytes(C);
-                        if (y >= C.by1 && y <= C.by2 && b.xa <= b.xe) {
-                            issue = true;
-                            const AxisTap t = axis_tap(y - C.by1, C.fy);
-                            i1 = t.i1;
-                            c0 = b.c0;
-                            ri.offA = (uint32_t)(lane * 2 * rb);
-                            ri.offB = ri.offA + ((t.i1 + 1 > C.h - 1) ? 0u : (uint32_t)rb);
-                            ri.wy0 = __fmul_rn(t.w0, kWeightScale);
-                            ri.wy1 = __fmul_rn(t.w1, kWeightScale);
-                        }
-                    }
-                }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, issue);
-            const int rb_all = __shfl_sync(0xffffffffu, rb, m ? (__ffs(m) - 1) : 0);
-            const uint32_t tx_bytes = (uint32_t)(__popc(m) * 2 * rb_all);
-            const CUtensorMap* map = tma_map_of<Table>(K, T, tc.z);
-            const uint32_t dst = sinfo + G.info_bytes + lane * 2 * rb;
-
-            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-            if (lane < G.TR) sts_rowinfo(sinfo + lane * (uint32_t)sizeof(RowInfo), ri);
-            __syncwarp();  // the RowInfo stores of all lanes are ordered before lane 0's (releasing) arrive
-            if (lane == 0) mbar_arrive_expect_tx(full, tx_bytes);
-            if (issue) tma_load_2d(dst, map, c0, i1, full);
-            if (++stage == nstages) {
-                stage = 0;
-                phase ^= 1u;
-            }
-        }
-        if (!G.pdl_wait) pdl_wait_prior_grid();  // never complete before the preceding kernel has
-        return;
-    }
-
-    // ========================================= consumers =========================================
-    const int W = P.W;
-    const int TW = 32 * G.NPB;
+    ItemCursor cc;  // item being computed
+    cc.init(G, blockIdx.x * kWarps + warp);
+    ItemCursor ic = cc;  // item being staged (nslots ahead)
 
     // chain constants of the specialised shape v = fma(v, ca, cb) / cd  (source-channel order)
     float ca[3], cb[3], zh[3], zl[3];
@@ -442,21 +363,90 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
     const long long oc1 = (long long)P.prog.dst_chan[1] * P.out.c_stride;
     const long long oc2 = (long long)P.prog.dst_chan[2] * P.out.c_stride;
     const int pxs = GEN ? P.out.px_stride : 1;
-    const int row_step = W * pxs;            // floats between vertically adjacent pixels
-    const int tile_step = G.TR * row_step;   // ... between the first rows of vertically adjacent tiles
-    const uint32_t info_bytes = (uint32_t)G.info_bytes, stage_bytes = (uint32_t)G.stage_bytes;
-    const int half_rows = G.TR >> 1;
+    const int row_step = W * pxs;  // floats between vertically adjacent pixels
 
-    int stage = 0;
-    uint32_t phase = 0;
-    // From here on this thread stores to global memory: order it after the preceding kernel unless the host
-    // proved the two independent (then only completion is ordered, at the end).
+    // Everything below reads source images and writes the output tensor: order it after the preceding kernel
+    // unless the host proved the two independent (then only completion is ordered, at the end).
     if (G.pdl_wait) pdl_wait_prior_grid();
+    if (K.maps && cc.left > 0) {
+        // Tensor maps that reached global memory through a host copy must be acquired for the TMA proxy before
+        // their first use by this thread (once per map: the fence also drops the descriptor cache).
+        const int g = blockIdx.x * kWarps + warp;
+        const int i_last = g * G.items_base + min(g, G.items_rem) + cc.left - 1;
+        const int z_last = i_last / G.items_per_crop;
+        for (int z = cc.z; z <= z_last; ++z) {
+            if (GEN && z >= P.used) break;
+            const CUtensorMap* map = tma_map_of<Table>(K, T, tma_crop_of<Table>(K, T, z));
+            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+        }
+    }
 
-    while (tc.left > 0) {
+    // ---------------- staging: lanes 0 and 1 stage the two output rows of item `ic` into `slot` ----------------
+    StageBand sb;
+    sb.z = sb.txi = -1;
+    sb.ok = false;
+    sb.c0 = sb.rb = sb.by1 = sb.by2 = sb.hm1 = sb.y0 = 0;
+    sb.fy = 1.f;
+    sb.map = nullptr;
+    auto stage_item = [&](int slot) {
+        if (ic.z != sb.z || ic.txi != sb.txi) {
+            sb.z = ic.z;
+            sb.txi = ic.txi;
+            sb.ok = false;
+            if (!GEN || ic.z < P.used) {
+                const DevCrop& C = tma_crop_of<Table>(K, T, ic.z);
+                const BandOrigin b = band_origin(P, G, C, ic.txi);
+                sb.ok = b.xa <= b.xe;
+                sb.c0 = b.c0;
+                sb.rb = crop_row_bytes(C);
+                sb.by1 = C.by1;
+                sb.by2 = C.by2;
+                sb.hm1 = C.h - 1;
+                sb.fy = C.fy;
+                sb.y0 = C.m.y0;
+                sb.map = tma_map_of<Table>(K, T, C);
+            }
+        }
+        const uint32_t sbase = ring + (uint32_t)slot * slot_bytes;
+        const uint32_t full = bars + 8 * slot;
+        bool issue = false;
+        int i1 = 0;
+        if (lane < 2) {
+            RowInfo ri;
+            ri.offA = kRowSkip;
+            ri.offB = 0;
+            ri.wy0 = ri.wy1 = 0.f;
+            const int y = 2 * ic.jp + lane;
+            if (y < H) {
+                ri.offA = kRowFill;
+                if (sb.ok && y >= sb.by1 && y <= sb.by2) {
+                    issue = true;
+                    const AxisTap t = axis_tap(y - sb.by1, sb.fy);
+                    i1 = t.i1;
+                    ri.offA = (uint32_t)(lane * 2 * sb.rb);
+                    ri.offB = ri.offA + ((t.i1 + 1 > sb.hm1) ? 0u : (uint32_t)sb.rb);
+                    ri.wy0 = __fmul_rn(t.w0, kWeightScale);
+                    ri.wy1 = __fmul_rn(t.w1, kWeightScale);
+                }
+            }
+            sts_rowinfo(sbase + lane * (uint32_t)sizeof(RowInfo), ri);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, issue);  // also orders the RowInfo stores before the arrive
+        // the slot's previous contents were read through the generic proxy; the TMA writes through the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(__popc(m) * 2 * sb.rb));
+        if (issue) tma_load_2d(sbase + kSlotHeader + lane * 2 * sb.rb, sb.map, sb.c0, sb.y0 + i1, full);
+        ic.next(G);
+    };
+
+    for (int s = 0; s < nslots && ic.left > 0; ++s) stage_item(s);
+
+    int slot = 0;
+    uint32_t phase = 0;
+    while (cc.left > 0) {
         // ---------------- horizontal state of this lane for the band (z, txi): column p is tx0 + lane + 32 p ------
-        const int z = tc.z;
-        const int tx0 = tc.txi * TW;
+        const int z = cc.z;
+        const int tx0 = cc.txi * TW;
         const int np = (min(TW, W - tx0) + 31) >> 5;
         int32_t off[kMaxNP], shl[kMaxNP], shr[kMaxNP];
         float wxa[kMaxNP], wxb[kMaxNP];
@@ -471,7 +461,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             int bx1 = 0, wm1 = 0;
             if (active) {
                 const DevCrop& C = tma_crop_of<Table>(K, T, z);
-                b = band_origin(P, G, C, tc.txi);
+                b = band_origin(P, G, C, cc.txi);
                 fx = C.fx;
                 bx1 = C.bx1;
                 wm1 = C.w - 1;
@@ -491,100 +481,103 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                 shr[p] = ((o + 3) & 3) * 8;
             }
         }
-        // first pixel of this lane in the three channel planes of plane z
-        float* bp0 = P.out.base + ((long long)z * P.out.z_stride + (long long)(tx0 + lane) * pxs);
-        float* bp1 = bp0 + oc1;
-        float* bp2 = bp0 + oc2;
-        bp0 += oc0;
-        asm volatile("" : "+l"(bp0), "+l"(bp1), "+l"(bp2));
+        // this lane's first column in rows 2*jp of the three channel planes of plane z
+        float* s0 = P.out.base + ((long long)z * P.out.z_stride + (long long)(tx0 + lane) * pxs + (long long)(2 * cc.jp) * row_step);
+        float* s1 = s0 + oc1;
+        float* s2 = s0 + oc2;
+        s0 += oc0;
 
-        const int ntiles = min(tc.left, G.tiles_y - tc.tyi);  // tiles of this band inside the CTA's range
-        int tile_off = tc.tyi * tile_step;                    // in-plane offset (floats) of the tile's first row
-        for (int t = 0; t < ntiles; ++t, tile_off += tile_step) {
-            mbar_wait(smem_u32(&bar_full[stage]), phase);
-            const uint32_t sinfo = ring + stage * stage_bytes;
-            const uint32_t sdata = sinfo + info_bytes;
-
-            for (int j = warp; j < half_rows; j += kConsumerWarps) {
-                const RowInfo r0 = lds_rowinfo(sinfo + 2 * j * (uint32_t)sizeof(RowInfo));
-                const RowInfo r1 = lds_rowinfo(sinfo + (2 * j + 1) * (uint32_t)sizeof(RowInfo));
-                if (r0.offA == kRowSkip) break;  // rows are ascending: nothing below either
-                const bool st1 = r1.offA != kRowSkip;
-                const bool im0 = !GEN || r0.offA < kRowFill, im1 = r1.offA < kRowFill;
-                // a row without image data borrows the other row's taps (its values are replaced / not stored)
-                uint32_t aA0, aB0, aA1, aB1;
-                float2 wy0, wy1;
-                if (GEN) {
-                    aA0 = sdata + (im0 ? r0.offA : r1.offA), aB0 = sdata + (im0 ? r0.offB : r1.offB);
-                    wy0.x = im0 ? r0.wy0 : r1.wy0, wy1.x = im0 ? r0.wy1 : r1.wy1;
-                } else {
-                    aA0 = sdata + r0.offA, aB0 = sdata + r0.offB;
-                    wy0.x = r0.wy0, wy1.x = r0.wy1;
-                }
-                aA1 = sdata + (im1 ? r1.offA : r0.offA), aB1 = sdata + (im1 ? r1.offB : r0.offB);
-                wy0.y = im1 ? r1.wy0 : r0.wy0, wy1.y = im1 ? r1.wy1 : r0.wy1;
-                // row pointers of the pair for the three channels; opaque to the compiler so that they are kept in
-                // registers instead of being re-derived in front of every store
-                const int ro = tile_off + 2 * j * row_step;
-                float* s0 = bp0 + ro;
-                float* s1 = bp1 + ro;
-                float* s2 = bp2 + ro;
-                float* t0 = s0 + row_step;
-                float* t1 = s1 + row_step;
-                float* t2 = s2 + row_step;
-                asm volatile("" : "+l"(s0), "+l"(s1), "+l"(s2), "+l"(t0), "+l"(t1), "+l"(t2));
-                asm volatile("" : "+r"(aA0), "+r"(aB0), "+r"(aA1), "+r"(aB1), "+f"(wy0.x), "+f"(wy0.y), "+f"(wy1.x), "+f"(wy1.y));
+        const int nitems = min(cc.left, G.HP - cc.jp);  // items of this band inside the warp's range
+        for (int it = 0; it < nitems; ++it) {
+            mbar_wait(bars + 8 * slot, phase);
+            const uint32_t sbase = ring + (uint32_t)slot * slot_bytes;
+            const uint32_t sdata = sbase + kSlotHeader;
+            const RowInfo r0 = lds_rowinfo(sbase);
+            const RowInfo r1 = lds_rowinfo(sbase + (uint32_t)sizeof(RowInfo));
+            const bool st1 = r1.offA != kRowSkip;
+            const bool im0 = !GEN || r0.offA < kRowFill, im1 = r1.offA < kRowFill;
+            // a row without image data borrows the other row's taps (its values are replaced / not stored)
+            uint32_t aA0, aB0, aA1, aB1;
+            float2 wy0, wy1;
+            if (GEN) {
+                aA0 = sdata + (im0 ? r0.offA : r1.offA), aB0 = sdata + (im0 ? r0.offB : r1.offB);
+                wy0.x = im0 ? r0.wy0 : r1.wy0, wy1.x = im0 ? r0.wy1 : r1.wy1;
+            } else {
+                aA0 = sdata + r0.offA, aB0 = sdata + r0.offB;
+                wy0.x = r0.wy0, wy1.x = r0.wy1;
+            }
+            aA1 = sdata + (im1 ? r1.offA : r0.offA), aB1 = sdata + (im1 ? r1.offB : r0.offB);
+            wy0.y = im1 ? r1.wy0 : r0.wy0, wy1.y = im1 ? r1.wy1 : r0.wy1;
+            // row pointers of the pair; opaque to the compiler so that they stay in registers instead of being
+            // re-derived in front of every store
+            float* t0 = s0 + row_step;
+            float* t1 = s1 + row_step;
+            float* t2 = s2 + row_step;
+            asm volatile("" : "+l"(s0), "+l"(s1), "+l"(s2), "+l"(t0), "+l"(t1), "+l"(t2));
+            asm volatile("" : "+r"(aA0), "+r"(aB0), "+r"(aA1), "+r"(aB1), "+f"(wy0.x), "+f"(wy0.y), "+f"(wy1.x), "+f"(wy1.y));
 #pragma unroll
-                for (int p = 0; p < kMaxNP; ++p) {
-                    if (p < np) {
-                        float2 v[3];
-                        if (!GEN || im0 || im1) {
-                            gather_pair(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p], edge[p],
-                                        wxa[p], wxb[p], wy0, wy1, v);
-                            if (CHAIN == CH_FMA_DIV) {
-#pragma unroll
-                                for (int c = 0; c < 3; ++c) {
-                                    v[c] = __ffma2_rn(v[c], make_float2(ca[c], ca[c]), make_float2(cb[c], cb[c]));
-                                    v[c] = div_by_const2(v[c], zh[c], zl[c]);
-                                }
-                            } else {
-                                if (G.explicit_prescale) {
-#pragma unroll
-                                    for (int c = 0; c < 3; ++c) v[c] = __fmul2_rn(v[c], make_float2(kPreScale, kPreScale));
-                                }
-                                apply_program_pair(K.prog_img, v);
-                            }
-                        }
-                        if (GEN) {
+            for (int p = 0; p < kMaxNP; ++p) {
+                if (p < np) {
+                    float2 v[3];
+                    if (!GEN || im0 || im1) {
+                        gather_pair(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p], edge[p], wxa[p],
+                                    wxb[p], wy0, wy1, v);
+                        if (CHAIN == CH_FMA_DIV) {
 #pragma unroll
                             for (int c = 0; c < 3; ++c) {
-                                if (!(im0 && img[p])) v[c].x = vb[0][c];
-                                if (!(im1 && img[p])) v[c].y = vb[0][c];
+                                v[c] = __ffma2_rn(v[c], make_float2(ca[c], ca[c]), make_float2(cb[c], cb[c]));
+                                v[c] = div_by_const2(v[c], zh[c], zl[c]);
                             }
+                        } else {
+                            if (G.explicit_prescale) {
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) v[c] = __fmul2_rn(v[c], make_float2(kPreScale, kPreScale));
+                            }
+                            apply_program_pair(K.prog_img, v);
                         }
-                        if (inw[p]) {
-                            const int q = 32 * p * pxs;
-                            st_cs_f32(s0 + q, v[0].x);
-                            st_cs_f32(s1 + q, v[1].x);
-                            st_cs_f32(s2 + q, v[2].x);
-                            if (st1) {
-                                st_cs_f32(t0 + q, v[0].y);
-                                st_cs_f32(t1 + q, v[1].y);
-                                st_cs_f32(t2 + q, v[2].y);
-                            }
+                    }
+                    if (GEN) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            if (!(im0 && img[p])) v[c].x = vb[0][c];
+                            if (!(im1 && img[p])) v[c].y = vb[0][c];
+                        }
+                    }
+                    if (inw[p]) {
+                        const int q = 32 * p * pxs;
+                        st_cs_f32(s0 + q, v[0].x);
+                        st_cs_f32(s1 + q, v[1].x);
+                        st_cs_f32(s2 + q, v[2].x);
+                        if (st1) {
+                            st_cs_f32(t0 + q, v[0].y);
+                            st_cs_f32(t1 + q, v[1].y);
+                            st_cs_f32(t2 + q, v[2].y);
                         }
                     }
                 }
             }
+            s0 += 2 * row_step;
+            s1 += 2 * row_step;
+            s2 += 2 * row_step;
 
+            // every lane has consumed its taps of this slot (their values fed the stores above): refill it
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_empty[stage]));
-            if (++stage == nstages) {
-                stage = 0;
+            if (ic.left > 0) stage_item(slot);
+            if (++slot == nslots) {
+                slot = 0;
                 phase ^= 1u;
             }
         }
-        tc.skip(G, ntiles);
+        // advance the compute cursor past the band's items
+        cc.left -= nitems;
+        cc.jp += nitems;
+        if (cc.jp == G.HP) {
+            cc.jp = 0;
+            if (++cc.txi == G.tiles_x) {
+                cc.txi = 0;
+                ++cc.z;
+            }
+        }
     }
     if (!G.pdl_wait) pdl_wait_prior_grid();  // never complete before the preceding kernel has
 }
@@ -617,8 +610,17 @@ inline int band_row_bytes(int TW, float fx) {
     return static_cast<int>((bytes + 63) / 64 * 64);
 }
 
-// Can this launch take the TMA kernel, and with which tiling?  crops = host copies of the DevCrops.
-inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int n_planes, int sm_count, TmaGeom& G) {
+// Staged row bytes are rounded up to a few classes so that crops of one image share tensor maps.
+inline int rb_class(int rb) {
+    static const int cls[] = {128, 192, 256, 384, 512, 768, 1024, 1536, 2048};
+    for (int c : cls)
+        if (rb <= c) return c;
+    return 0;
+}
+
+// Can this launch take the TMA kernel, and with which geometry?  crops = host copies of the DevCrops.
+inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int n_planes, int sm_count, bool image_mode,
+                     TmaGeom& G) {
     if (!encode_tiled_fn()) return false;
     float fx_max = 0.f;
     for (int i = 0; i < used; ++i) {
@@ -633,65 +635,37 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
     auto need = [&](int npb) { return used > 0 ? band_row_bytes(std::min(32 * npb, P.W), fx_max) : 64; };
     while (NPB > 1 && need(NPB) > kMaxBoxBytes) --NPB;
     if (need(NPB) > kMaxBoxBytes) return false;  // extreme down-scale: direct kernel
-    const int rb_max = need(NPB);
+    // image mode rounds the staged row bytes up to a class (rb_class) so that crops share tensor maps
+    const int rb_max = image_mode ? rb_class(need(NPB)) : need(NPB);
     const int TW = 32 * NPB;
-    const int tiles_x = (P.W + TW - 1) / TW;
-    const int smem_sm = 227 * 1024;
-    auto stage_of = [&](int tr) { return (tr * static_cast<int>(sizeof(RowInfo)) + 127) / 128 * 128 + tr * 2 * rb_max; };
-    auto resident_of = [&](int tr, int stages) {
-        const int per_cta = stages * stage_of(tr) + 2 * kStagePad + 128 + 1024 /*static + reserved*/;
-        return std::min(4, smem_sm / per_cta);
-    };
-    // rows per tile: first keep as many CTAs per SM as the smallest tile allows (occupancy hides the latency of the
-    // dependent FP chain), then take the tallest tile that still gives every CTA slot at least one tile
-    int TR = 8;
-    const int best_resident = resident_of(8, 2);
-    for (int tr : {32, 16}) {
-        if (resident_of(tr, 2) < best_resident) continue;
-        const long long tiles = static_cast<long long>(n_planes) * tiles_x * ((P.H + tr - 1) / tr);
-        if (tiles >= static_cast<long long>(best_resident) * sm_count) {
-            TR = tr;
-            break;
-        }
-    }
-    if (const char* e = std::getenv("CVGS_TMA_TR")) {  // tuning override (tests / profiling)
-        const int v = std::atoi(e);
-        if ((v == 8 || v == 16 || v == 32) && resident_of(v, 1) >= 1) TR = v;
-    }
-    if (resident_of(TR, 1) < 1) return false;
     G.NPB = NPB;
-    G.TR = TR;
-    G.tiles_x = tiles_x;
-    G.tiles_y = (P.H + TR - 1) / TR;
-    G.tiles_per_crop = G.tiles_x * G.tiles_y;
-    const long long total = static_cast<long long>(n_planes) * G.tiles_per_crop;
+    G.HP = (P.H + 1) / 2;
+    G.tiles_x = (P.W + TW - 1) / TW;
+    G.items_per_crop = G.tiles_x * G.HP;
+    const long long total = static_cast<long long>(n_planes) * G.items_per_crop;
     if (total > 0x7fffffffLL) return false;
-    G.total_tiles = static_cast<int32_t>(total);
-    G.info_bytes = (TR * static_cast<int>(sizeof(RowInfo)) + 127) / 128 * 128;
-    G.stage_bytes = stage_of(TR);
+    G.total_items = static_cast<int32_t>(total);
+    G.slot_bytes = kSlotHeader + 4 * rb_max;  // rb_max is a multiple of 64: slots stay 128-byte aligned
     G.explicit_prescale = 0;
     G.pdl_wait = 1;
-    int stages = 2;
-    int resident = resident_of(TR, stages);
-    if (resident < 1) {
-        stages = 1;
-        resident = resident_of(TR, 1);
+    // ring depth: as deep as possible while four CTAs stay resident per SM, but at least two slots
+    const int smem_sm = 227 * 1024;
+    auto cta_bytes = [&](int slots) { return kWarps * slots * G.slot_bytes + kRingPad + 128 + 1024 /*static + reserved*/; };
+    int slots = kMaxSlots;
+    while (slots > 2 && smem_sm / cta_bytes(slots) < 4) --slots;
+    if (const char* e = std::getenv("CVGS_TMA_SLOTS")) {  // tuning override (tests / profiling)
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= kMaxSlots) slots = v;
     }
-    // deeper ring when it costs no residency
-    while (stages < kStages && resident_of(TR, stages + 1) >= resident) ++stages;
-    const long long slots = static_cast<long long>(resident) * sm_count;
-    G.resident = resident;
-    if (total <= slots) {
-        // small launch: one tile per CTA, every CTA resident at once, no ring
-        G.grid = G.total_tiles;
-        G.stages = 1;
-    } else {
-        // persistent: one CTA per slot
-        G.grid = static_cast<int32_t>(slots);
-        G.stages = stages;
-    }
-    G.tiles_base = G.total_tiles / G.grid;
-    G.tiles_rem = G.total_tiles % G.grid;
+    if (cta_bytes(slots) > smem_sm) return false;
+    G.slots = slots;
+    G.resident = std::min(4, smem_sm / cta_bytes(slots));
+    const long long warps_wanted = std::max<long long>(1, total);  // at least one item per warp
+    const long long ctas_wanted = (warps_wanted + kWarps - 1) / kWarps;
+    G.grid = static_cast<int32_t>(std::min<long long>(ctas_wanted, static_cast<long long>(G.resident) * sm_count));
+    const int n_warps = G.grid * kWarps;
+    G.items_base = G.total_items / n_warps;
+    G.items_rem = G.total_items % n_warps;
     return true;
 }
 
@@ -761,26 +735,76 @@ inline int scaled_program(const PreprocParams& P, TmaParams& K) {
     return CH_GENERIC;
 }
 
-// Fill the TMA fields of a crop descriptor and encode its tensor map.
-inline int tma_prepare_crop(DevCrop& c, const TmaGeom& G, int W, CUtensorMap* map) {
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(c.data);
-    const int mis = static_cast<int>(addr & 15);
-    const int rb = band_row_bytes(std::min(32 * G.NPB, W), c.fx);
-    c.pad = rb | (mis << 16);
-    const cuuint64_t dim[2] = {static_cast<cuuint64_t>((mis + 3LL * c.w + 7) / 8), static_cast<cuuint64_t>(c.h)};
-    const cuuint64_t pitch = c.h > 1 ? static_cast<cuuint64_t>(c.pitch) : (dim[0] * 8 + 15) / 16 * 16;
-    const cuuint64_t stride[1] = {pitch};
+inline int tma_encode(CUtensorMap* map, uintptr_t base16, long long row_bytes, int rows, long long pitch, int rb) {
+    const cuuint64_t dim[2] = {static_cast<cuuint64_t>((row_bytes + 7) / 8), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t stride[1] = {rows > 1 ? static_cast<cuuint64_t>(pitch) : (dim[0] * 8 + 15) / 16 * 16};
     const cuuint32_t box[2] = {static_cast<cuuint32_t>(rb / 8), 2};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, reinterpret_cast<void*>(addr - mis), dim,
-                                         stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+    const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, reinterpret_cast<void*>(base16), dim, stride, box,
+                                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CVGS_ERR_INVALID_VALUE, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return CVGS_OK;
 }
 
+// Per-crop map: nothing is known about the memory around the crop, so the map's bounds are the crop's own (reads
+// never leave it by more than the 8-byte element that holds its last pixel; everything else is zero-filled).
+inline int tma_prepare_crop(DevCrop& c, const TmaGeom& G, int W, int map_index, CUtensorMap* map) {
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(c.data);
+    const int mis = static_cast<int>(addr & 15);
+    const int rb = band_row_bytes(std::min(32 * G.NPB, W), c.fx);
+    if (int rc = tma_encode(map, addr - mis, mis + 3LL * c.w, c.h, c.pitch, rb)) return rc;
+    c.m.xb = mis;   // overwrites c.data (union)
+    c.m.y0 = 0;
+    c.pad = rb | (map_index << 16);
+    return CVGS_OK;
+}
+
+// Per-image maps (cvgs_b200_preproc_launch_ex): the caller named the parent image of a crop, i.e. memory that is
+// known to be readable, so one map per (image, row-bytes class) serves every crop of that image and is cached
+// across launches -- camera buffers recur, their crops do not.
+struct ImageMapCache {
+    struct Entry {
+        uintptr_t datastart = 0;
+        int32_t pitch = 0, width = 0, height = 0, rb = 0;
+        CUtensorMap map;
+    };
+    static constexpr int kEntries = 512;
+    Entry e[kEntries];
+    const CUtensorMap* get(uintptr_t datastart, int pitch, int width, int height, int rb) {
+        const size_t hsh = (static_cast<size_t>(datastart >> 8) * 0x9E3779B97F4A7C15ull + static_cast<size_t>(rb) * 0xC2B2AE3D27D4EB4Full) >> 40;
+        Entry& x = e[hsh % kEntries];
+        if (x.datastart == datastart && x.pitch == pitch && x.width == width && x.height == height && x.rb == rb) return &x.map;
+        const int mis = static_cast<int>(datastart & 15);
+        if (tma_encode(&x.map, datastart - mis, mis + 3LL * width, height, pitch, rb) != CVGS_OK) {
+            x.datastart = 0;
+            return nullptr;
+        }
+        x.datastart = datastart;
+        x.pitch = pitch;
+        x.width = width;
+        x.height = height;
+        x.rb = rb;
+        return &x.map;
+    }
+};
+
+// Locate crop c (c.data still valid) inside its parent image and bind it to map `map_index` with row bytes rb.
+inline bool tma_place_in_image(DevCrop& c, uintptr_t datastart, int width, int height, int rb, int map_index) {
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(c.data);
+    if (addr < datastart || c.pitch <= 0) return false;
+    const uintptr_t off = addr - datastart;
+    const long long y0 = static_cast<long long>(off / static_cast<uintptr_t>(c.pitch));
+    const long long xo = static_cast<long long>(off - static_cast<uintptr_t>(y0) * static_cast<uintptr_t>(c.pitch));
+    if (xo + 3LL * c.w > 3LL * width || y0 + c.h > height || (height > 1 && 3LL * width > c.pitch)) return false;
+    c.m.xb = static_cast<int32_t>((datastart & 15) + xo);  // overwrites c.data (union)
+    c.m.y0 = static_cast<int32_t>(y0);
+    c.pad = rb | (map_index << 16);
+    return true;
+}
+
 inline size_t tma_smem_bytes(const TmaGeom& G) {
-    return static_cast<size_t>(G.stages) * G.stage_bytes + 2 * kStagePad + 128;
+    return static_cast<size_t>(kWarps) * G.slots * G.slot_bytes + kRingPad + 128;
 }
 
 template <typename Table, int CHAIN, bool GEN>
@@ -813,6 +837,7 @@ inline int tma_launch_instance(const TmaParams& K, const Table& T, int device, c
 
 template <typename Table>
 inline int tma_launch_kernel(const TmaParams& K, const Table& T, int chain, int device, cudaStream_t stream) {
+    static_assert(sizeof(TmaParams) + sizeof(Table) <= 32 * 1024, "kernel parameters exceed 32 KB");
     const PreprocParams& P = K.P;
     const bool fast = !P.band_test && P.used == P.n_planes && P.out.px_stride == 1;
     if (chain == CH_FMA_DIV)

@@ -19,8 +19,9 @@ def device_image(image: np.ndarray) -> torch.Tensor:
 
 
 def run_cvgs(image, rects, dsize, ops, n_planes=None, used=None, variant=0, fill=float("nan"), d_image=None,
-             **pipe_kw) -> np.ndarray:
-    """One cvgs_b200_preproc_launch on cuda:0; returns the output tensor as numpy."""
+             parents=None, **pipe_kw) -> np.ndarray:
+    """One cvgs_b200_preproc_launch (or _launch_ex when parents = (width, height) of the image the crops were cut
+    from) on cuda:0; returns the output tensor as numpy."""
     lib = _abi.load()
     n_planes = len(rects) if n_planes is None else n_planes
     used = len(rects) if used is None else used
@@ -32,8 +33,13 @@ def run_cvgs(image, rects, dsize, ops, n_planes=None, used=None, variant=0, fill
     crops = util.host_crops(image, rects[:used], base_ptr=d_img.data_ptr())
     prev = lib.cvgs_b200_set_kernel_variant(variant)
     try:
-        _abi.check(lib.cvgs_b200_preproc_launch(crops, n_planes, used, C.byref(p),
-                                                torch.cuda.current_stream().cuda_stream))
+        if parents is None:
+            _abi.check(lib.cvgs_b200_preproc_launch(crops, n_planes, used, C.byref(p),
+                                                    torch.cuda.current_stream().cuda_stream))
+        else:
+            par = util.host_parents(image, parents[0], parents[1], used, base_ptr=d_img.data_ptr())
+            _abi.check(lib.cvgs_b200_preproc_launch_ex(crops, par, n_planes, used, C.byref(p),
+                                                       torch.cuda.current_stream().cuda_stream))
     finally:
         lib.cvgs_b200_set_kernel_variant(prev)
     torch.cuda.synchronize()

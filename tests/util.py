@@ -176,6 +176,15 @@ def host_crops(image: np.ndarray, rects: Sequence[Rect], base_ptr: int | None = 
     return arr
 
 
+def host_parents(image: np.ndarray, width: int, height: int, n: int, base_ptr: int | None = None):
+    """cvgs_parent_t per crop: every crop was cut from the one image (GpuMat::datastart + locateROI)."""
+    base = image.ctypes.data if base_ptr is None else base_ptr
+    arr = (_abi.Parent * max(1, n))()
+    for i in range(n):
+        arr[i].datastart, arr[i].whole_width, arr[i].whole_height = base, width, height
+    return arr
+
+
 def run_oracle(image, rects, dsize, ops, n_planes=None, used=None, nthreads=0, fill=np.nan, **pipe_kw) -> np.ndarray:
     """CPU oracle on host memory; returns the output tensor (shape by layout)."""
     lib = oracle_lib()
