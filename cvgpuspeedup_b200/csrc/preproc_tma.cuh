@@ -60,8 +60,9 @@ struct TmaGeom {
     int32_t slot_bytes;      // kSlotHeader + 4 * max row bytes
     int32_t slots;           // ring depth per warp (1..kMaxSlots)
     int32_t resident;        // CTAs per SM the shared-memory footprint allows
-    int32_t grid;            // CTAs; warp g = blockIdx.x * kWarps + warp walks items [g*base + min(g, rem), ...)
-    int32_t items_base, items_rem;
+    int32_t grid;            // CTAs; warp g = blockIdx.x * kWarps + warp walks a contiguous range of items whose
+                             // total cost (32-column groups) is 1/(grid*kWarps) of the launch (ItemCursor::init)
+    int32_t np_last;         // 32-column groups of the last band of a plane (the others have NPB)
     int32_t explicit_prescale;  // 1: the kernel multiplies by 2^33 itself (no op to fold it into)
     int32_t pdl_wait;        // 1: wait for the preceding kernel before the first global access (stream order);
                              // 0: the host proved independence, wait only before exiting (completion order)
@@ -78,7 +79,7 @@ struct TmaParams {
 // Descriptors that ride in the kernel parameters: NMAPS tensor maps + up to kTmaParamCrops crops.
 // One map per crop (NMAPS = kTmaParamCrops) when nothing is known about the memory around a crop; a handful of
 // per-image maps (NMAPS = kTmaImageMaps) when the caller names the parent images (cvgs_b200_preproc_launch_ex).
-constexpr int kTmaImageMaps = 8;
+constexpr int kTmaImageMaps = 16;
 constexpr int kTmaImageCrops = 256;     // image mode: batches up to this size still ride in the parameters (13 KB)
 template <int NMAPS, int NCROPS>
 struct alignas(64) TmaParamTableT {
@@ -213,14 +214,28 @@ __device__ __forceinline__ float2 div_by_const2(float2 x, float zh, float zl) {
     return __ffma2_rn(x, make_float2(zh, zh), u);
 }
 
-// Item walk of one warp: contiguous range, decoded once and then advanced incrementally.
+// Item walk of one warp: contiguous range, decoded once and then advanced incrementally.  Items are ordered
+// (plane, band, row pair); an item costs as many column groups as its band has, and the ranges are cut so that every
+// warp gets the same cost (a plane of 224 columns has a 4-group and a 3-group band).
 struct ItemCursor {
     int z, txi, jp, left;
+    // first item whose cumulative cost reaches w (cost counted in column groups from the start of the launch)
+    static __device__ __forceinline__ long long item_at(const TmaGeom& G, long long w, long long w_crop, long long w_full) {
+        const long long z = w / w_crop;
+        const long long r = w - z * w_crop;
+        const long long in_crop = r < w_full ? r / G.NPB : (long long)(G.tiles_x - 1) * G.HP + (r - w_full) / G.np_last;
+        return z * G.items_per_crop + in_crop;
+    }
     __device__ __forceinline__ void init(const TmaGeom& G, int g) {
-        const int i0 = g * G.items_base + min(g, G.items_rem);
-        left = G.items_base + (g < G.items_rem ? 1 : 0);
-        z = i0 / G.items_per_crop;
-        const int rem = i0 - z * G.items_per_crop;
+        const long long n_warps = (long long)G.grid * kWarps;
+        const long long w_full = (long long)(G.tiles_x - 1) * G.HP * G.NPB;  // cost of the full-width bands of a plane
+        const long long w_crop = w_full + (long long)G.HP * G.np_last;
+        const long long w_total = w_crop * (G.total_items / G.items_per_crop);
+        const long long i0 = item_at(G, w_total * g / n_warps, w_crop, w_full);
+        const long long i1 = g + 1 == n_warps ? (long long)G.total_items : item_at(G, w_total * (g + 1) / n_warps, w_crop, w_full);
+        left = (int)(i1 - i0);
+        z = (int)(i0 / G.items_per_crop);
+        const int rem = (int)(i0 - (long long)z * G.items_per_crop);
         txi = rem / G.HP;
         jp = rem - txi * G.HP;
     }
@@ -371,8 +386,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
     if (K.maps && cc.left > 0) {
         // Tensor maps that reached global memory through a host copy must be acquired for the TMA proxy before
         // their first use by this thread (once per map: the fence also drops the descriptor cache).
-        const int g = blockIdx.x * kWarps + warp;
-        const int i_last = g * G.items_base + min(g, G.items_rem) + cc.left - 1;
+        const int i_last = (cc.z * G.items_per_crop + cc.txi * G.HP + cc.jp) + cc.left - 1;
         const int z_last = i_last / G.items_per_crop;
         for (int z = cc.z; z <= z_last; ++z) {
             if (GEN && z >= P.used) break;
@@ -612,7 +626,7 @@ inline int band_row_bytes(int TW, float fx) {
 
 // Staged row bytes are rounded up to a few classes so that crops of one image share tensor maps.
 inline int rb_class(int rb) {
-    static const int cls[] = {128, 192, 256, 384, 512, 768, 1024, 1536, 2048};
+    static const int cls[] = {128, 192, 256, 384, 512, 640, 768, 896, 1024, 1280, 1408, 1536, 1664, 1792, 1920, 2048};
     for (int c : cls)
         if (rb <= c) return c;
     return 0;
@@ -663,9 +677,7 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
     const long long warps_wanted = std::max<long long>(1, total);  // at least one item per warp
     const long long ctas_wanted = (warps_wanted + kWarps - 1) / kWarps;
     G.grid = static_cast<int32_t>(std::min<long long>(ctas_wanted, static_cast<long long>(G.resident) * sm_count));
-    const int n_warps = G.grid * kWarps;
-    G.items_base = G.total_items / n_warps;
-    G.items_rem = G.total_items % n_warps;
+    G.np_last = (std::min(TW, P.W - (G.tiles_x - 1) * TW) + 31) / 32;
     return true;
 }
 

@@ -17,7 +17,9 @@
 // cvtColor :151-161, split :185-202, write :449-457, executeOperations :464-473, CircularTensor :600-627,
 // AspectRatio :32; error convention fkl/include/fused_kernel/core/utils/utils.h:42-60 (std::runtime_error).
 #pragma once
+#include <algorithm>
 #include <array>
+#include <cstddef>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -52,6 +54,7 @@ inline void check(int rc, const char* what) {
 }
 struct ReadBatch {  // cvGS::resize(...) result
     std::vector<cvgs_crop_t> crops;
+    std::vector<cvgs_parent_t> parents;  // the image each ROI was cut from (GpuMat::datastart / dataend)
     int n_planes = 0, used = 0, dst_w = 0, dst_h = 0, aspect = CVGS_IGNORE_AR, src_type = 0;
     float bg[4] = {0, 0, 0, 0};
 };
@@ -100,6 +103,24 @@ inline cvgs_crop_t crop_of(const cv::cuda::GpuMat& m) {  // gpuMat2RawPtr2D, ref
     c.pitch = static_cast<int32_t>(m.step);
     return c;
 }
+// The image a GpuMat header was cut from, from the members cv::cuda::GpuMat::locateROI uses (datastart, dataend,
+// step): lets the library stage all crops of a frame through one cached tensor map (include/cvgs_b200.h,
+// cvgs_b200_preproc_launch_ex).  An all-zero parent means "unknown" and is always safe.
+inline cvgs_parent_t parent_of(const cv::cuda::GpuMat& m) {
+    cvgs_parent_t p{};
+    const size_t esz = m.elemSize();
+    if (!m.datastart || !m.dataend || m.step == 0 || esz == 0 || m.data < m.datastart) return p;
+    const ptrdiff_t d1 = m.data - m.datastart, d2 = m.dataend - m.datastart;
+    const ptrdiff_t step = static_cast<ptrdiff_t>(m.step), minstep = static_cast<ptrdiff_t>(m.cols * esz);
+    const ptrdiff_t oy = d1 / step, ox = (d1 - oy * step) / static_cast<ptrdiff_t>(esz);
+    const ptrdiff_t h = std::max<ptrdiff_t>((d2 - minstep) / step + 1, oy + m.rows);
+    const ptrdiff_t w = std::max<ptrdiff_t>((d2 - step * (h - 1)) / static_cast<ptrdiff_t>(esz), ox + m.cols);
+    if (h <= 0 || w <= 0 || h > 0x7fffffff || w > 0x7fffffff) return p;
+    p.datastart = m.datastart;
+    p.whole_width = static_cast<int32_t>(std::min<ptrdiff_t>(w, step / static_cast<ptrdiff_t>(esz)));
+    p.whole_height = static_cast<int32_t>(h);
+    return p;
+}
 }  // namespace detail
 
 // Floating-point contract and resize-output mode of subsequent executeOperations calls on this thread
@@ -128,7 +149,11 @@ inline detail::ReadBatch resize(const std::array<cv::cuda::GpuMat, NPtr>& input,
     r.src_type = T;
     for (int c = 0; c < 4; ++c) r.bg[c] = static_cast<float>(backgroundValue[c]);
     r.crops.resize(NPtr);
-    for (int i = 0; i < NPtr && i < usedPlanes; ++i) r.crops[i] = detail::crop_of(input[i]);
+    r.parents.resize(NPtr);
+    for (int i = 0; i < NPtr && i < usedPlanes; ++i) {
+        r.crops[i] = detail::crop_of(input[i]);
+        r.parents[i] = detail::parent_of(input[i]);
+    }
     return r;
 }
 template <int T, int INTER_F>
@@ -219,8 +244,8 @@ inline void executeOperations(const cv::cuda::Stream& stream, const detail::Read
     p.fp_contract = fpContract();
     for (int c = 0; c < 4; ++c) p.background[c] = read.bg[c];
     (detail::append(p, iops), ...);
-    detail::check(cvgs_b200_preproc_launch(read.crops.data(), read.n_planes, read.used, &p,
-                                           cv::cuda::StreamAccessor::getStream(stream)),
+    detail::check(cvgs_b200_preproc_launch_ex(read.crops.data(), read.parents.empty() ? nullptr : read.parents.data(),
+                                              read.n_planes, read.used, &p, cv::cuda::StreamAccessor::getStream(stream)),
                   "cvGS::executeOperations");
 }
 template <bool ENABLE_THREAD_FUSION, typename... IOpTypes>

@@ -120,6 +120,27 @@ int FKREF_CAT(fkref_preproc_, FKREF_BATCH)(const void* const* ptrs, const int* w
     }
 }
 
+// Frame loop in native code (what the reference's benchmarks time, tests/testsCommon.cuh:260-308): `steps`
+// consecutive calls, call i using argument set i % n_sets -- so that a ctypes caller's per-call overhead is not
+// charged to the reference.
+int FKREF_CAT(fkref_preproc_sequence_, FKREF_BATCH)(const void* const* const* ptrs, const int* const* ws,
+                  const int* const* hs, const int* const* pitches, int used, int dst_w, int dst_h, int aspect_mode,
+                  const float* bg, int swap_rb, const float* mul, const float* sub, const float* div,
+                  float* const* outs, int n_sets, int steps, void* stream) {
+    try {
+        for (int i = 0; i < steps; ++i) {
+            const int s = i % n_sets;
+            if (int rc = dispatch<FKREF_BATCH>(ptrs[s], ws[s], hs[s], pitches[s], used, dst_w, dst_h, aspect_mode, bg,
+                                               swap_rb, mul, sub, div, outs[s], (cudaStream_t)stream))
+                return rc;
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
 const char* FKREF_CAT(fkref_last_error_, FKREF_BATCH)(void) { return g_err.c_str(); }
 
 }  // extern "C"
