@@ -23,7 +23,7 @@ reads its source from HBM and writes its tensor to HBM ("inputs larger than L2" 
              path (FKL's __host__ Interpolate has a typo, F10), so kind = "port".
   baselines  (rank 0, N=1) the reference's own fused GPU kernel instantiated from its headers
              (oracle/_ref/libfkref_50.so), a restated multi-kernel "OpenCV-CUDA-equivalent" chain
-             (oracle/_ref-free, oracle/libchain.so) and OpenCV-CPU (cv2), same frames, same box.
+             (oracle/libchain.so) and OpenCV-CPU (cv2), same frames, same box.
 """
 from __future__ import annotations
 
@@ -334,7 +334,60 @@ def gpu_baselines(frames, d_imgs, torch, min_seconds=0.5):
             "what": "fk::executeOperations(BatchRead<50>(Resize<INTER_LINEAR>), ColorConversion, Mul, Sub, Div, "
                     "TensorSplit) from /root/reference/fkl/include compiled for sm_100a (oracle/_ref/libfkref_50.so), "
                     "same device frames, " + how}
+    out.update(chain_baseline(frames, d_imgs, torch))
     return out
+
+
+def chain_baseline(frames, d_imgs, torch):
+    """Baseline M: the restated multi-kernel OpenCV-CUDA-equivalent chain (oracle/chain_kernels.cu), 300 launches per
+    50-crop frame, same device frames, native frame loop."""
+    path = os.path.join(ROOT, "oracle", "libchain.so")
+    if not os.path.exists(path):
+        return {}
+    lib = C.CDLL(path)
+    P, I = C.POINTER, C.c_int
+    lib.chain_workspace_bytes.restype = C.c_size_t
+    lib.chain_workspace_bytes.argtypes = [I, I]
+    seq = lib.chain_preproc_sequence
+    seq.restype = I
+    seq.argtypes = [P(P(C.c_void_p)), P(P(I)), P(P(I)), P(P(I)), I, I, I, I, P(C.c_float), P(C.c_float), P(C.c_float),
+                    P(C.c_void_p), C.c_void_p, I, I, C.c_void_p]
+    n, nf = CROPS_PER_FRAME, len(frames)
+    keep = []
+    for (img, rects), d in zip(frames, d_imgs):
+        base = d.data_ptr()
+        keep.append(((C.c_void_p * n)(*[base + y * PITCH + 3 * x for (x, y, w, h) in rects]),
+                     (I * n)(*[r[2] for r in rects]), (I * n)(*[r[3] for r in rects]), (I * n)(*[PITCH] * n)))
+    outs = [torch.empty((n, 3, DST[1], DST[0]), dtype=torch.float32, device="cuda") for _ in frames]
+    ws = torch.empty(int(lib.chain_workspace_bytes(DST[0], DST[1])) + 512, dtype=torch.uint8, device="cuda")
+    a_ptrs = (P(C.c_void_p) * nf)(*[C.cast(k[0], P(C.c_void_p)) for k in keep])
+    a_ws = (P(I) * nf)(*[C.cast(k[1], P(I)) for k in keep])
+    a_hs = (P(I) * nf)(*[C.cast(k[2], P(I)) for k in keep])
+    a_ps = (P(I) * nf)(*[C.cast(k[3], P(I)) for k in keep])
+    a_outs = (C.c_void_p * nf)(*[o.data_ptr() for o in outs])
+    f3 = lambda v: (C.c_float * 3)(*v)  # noqa: E731
+    s = torch.cuda.current_stream()
+
+    def passes(k):
+        rc = seq(a_ptrs, a_ws, a_hs, a_ps, n, DST[0], DST[1], 1, f3(MUL), f3(SUB), f3(DIV), a_outs, ws.data_ptr(), nf, nf * k,
+                 s.cuda_stream)
+        assert rc > 0
+        return rc
+    passes(1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record(s)
+    launches = passes(reps)
+    e1.record(s)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"opencv_cuda_equivalent_chain_gpu": {
+        "value": reps * nf * n / (ms * 1e-3), "unit": "crops/s", "us_per_frame": ms * 1e3 / (reps * nf),
+        "launches_per_frame": launches // (reps * nf),
+        "what": "restated multi-kernel chain per crop: resize(8UC3) -> convertTo(32F, alpha) -> cvtColor -> subtract -> "
+                "divide -> split (oracle/chain_kernels.cu; real OpenCV-CUDA is not installable here), same device "
+                "frames, native frame loop; equals the product's (SEPARATE, ROUND_U8) mode bit for bit"}}
 
 
 def run_gpu_arm(args, rank: int, world: int, local_rank: int):
@@ -532,9 +585,50 @@ def c3_extra(lib, torch, _abi, util, stream, reps=20):
     util.assert_bit_equal(sets[0][2][idx].cpu().numpy(), want, "bench c3: spot check vs oracle")
     b_in, b_out = algorithmic_bytes(w0.rects, dst=(224, 224), frame=(3840, 2160))
     gbs = (b_in + b_out) / (us * 1e-6) / 1e9
-    return {"workload": "c3: 256 crops (224..896 px) from 3840x2160 -> 224x224 + BGR2RGB + mean/std + NCHW, one launch",
+    ref_us = c3_reference_us(sets, torch, stream)
+    return {"reference_fused_kernel_us_per_256_crops": ref_us,
+            "reference_note": "fk::executeOperations with BATCH=128 (a template parameter capped at 255, SURVEY F7): two "
+                              "launches per 256 crops, same frames, oracle/_ref/libfkref_128.so",
+            "workload": "c3: 256 crops (224..896 px) from 3840x2160 -> 224x224 + BGR2RGB + mean/std + NCHW, one launch",
             "us_per_launch": us, "crops_per_s": 256 / (us * 1e-6), "algorithmic_bytes_per_launch": b_in + b_out,
             "bytes_in": b_in, "bytes_out": b_out, "achieved_gbs": gbs}
+
+
+def c3_reference_us(sets, torch, stream, reps=10):
+    """The reference's own fused kernel on the c3 sets: 2 launches of 128 crops (its batch is a template parameter)."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libfkref_128.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    fn = lib.fkref_preproc_128
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                   C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float),
+                   C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+    f3 = lambda v: (C.c_float * 3)(*v)  # noqa: E731
+    calls = []
+    for (w, d_img, d_out, _c, _p, _par) in sets:
+        ref_out = torch.empty_like(d_out)
+        for half in range(2):
+            rects = w.rects[128 * half:128 * (half + 1)]
+            ptrs = (C.c_void_p * 128)(*[d_img.data_ptr() + y * w.pitch + 3 * x for (x, y, _, _) in rects])
+            calls.append((ptrs, (C.c_int * 128)(*[r[2] for r in rects]), (C.c_int * 128)(*[r[3] for r in rects]),
+                          (C.c_int * 128)(*[w.pitch] * 128), ref_out[128 * half:].data_ptr(), ref_out))
+    mul, sub, div = (1 / 255.0,) * 3, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+    def one_pass():
+        for ptrs, ws, hs, ps, optr, _keep in calls:
+            rc = fn(ptrs, ws, hs, ps, 128, 224, 224, 1, f3((0, 0, 0)), 1, f3(mul), f3(sub), f3(div), optr, stream.cuda_stream)
+            assert rc == 0
+    one_pass()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        one_pass()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * len(sets))
 
 
 def h2d_bytes(frames) -> int:

@@ -93,3 +93,45 @@ def run_fkref(image, rects, dsize, swap, mul, sub, div, aspect=_abi.IGNORE_AR, b
     assert rc == 0, err().decode()
     torch.cuda.synchronize()
     return d_out.cpu().numpy()
+
+
+_CHAIN = None
+
+
+def chain_lib():
+    """oracle/libchain.so: the restated multi-kernel 'OpenCV-CUDA-equivalent' chain (baseline M)."""
+    global _CHAIN
+    if _CHAIN is None:
+        path = os.path.join(ROOT, "oracle", "libchain.so")
+        if not os.path.exists(path):
+            return None
+        lib = C.CDLL(path)
+        P, I = C.POINTER, C.c_int
+        lib.chain_workspace_bytes.restype = C.c_size_t
+        lib.chain_workspace_bytes.argtypes = [I, I]
+        lib.chain_preproc.restype = I
+        lib.chain_preproc.argtypes = [P(C.c_void_p), P(I), P(I), P(I), I, I, I, I, P(C.c_float), P(C.c_float), P(C.c_float),
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.chain_preproc_sequence.restype = I
+        lib.chain_preproc_sequence.argtypes = [P(P(C.c_void_p)), P(P(I)), P(P(I)), P(P(I)), I, I, I, I, P(C.c_float),
+                                               P(C.c_float), P(C.c_float), P(C.c_void_p), C.c_void_p, I, I, C.c_void_p]
+        _CHAIN = lib
+    return _CHAIN
+
+
+def run_chain(image, rects, dsize, swap, mul, sub, div, d_image=None):
+    """resize(8U) -> convertTo(alpha) -> [swap] -> subtract -> divide -> split, one launch per step and crop.
+    Returns ([n, 3, H, W] numpy, number of kernel launches)."""
+    lib = chain_lib()
+    assert lib is not None, "oracle/libchain.so not built"
+    d_img = device_image(image) if d_image is None else d_image
+    n = len(rects)
+    out = torch.full((n, 3, dsize[1], dsize[0]), float("nan"), dtype=torch.float32, device="cuda")
+    ws = torch.empty(int(lib.chain_workspace_bytes(dsize[0], dsize[1])) + 512, dtype=torch.uint8, device="cuda")
+    ptrs, w_, h_, p_ = fkref_args(d_img.data_ptr(), image.shape[1], rects, n)
+    f3 = lambda v: (C.c_float * 3)(*v)  # noqa: E731
+    launches = lib.chain_preproc(ptrs, w_, h_, p_, n, dsize[0], dsize[1], int(swap), f3(mul), f3(sub), f3(div),
+                                 out.data_ptr(), ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert launches > 0
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), launches
