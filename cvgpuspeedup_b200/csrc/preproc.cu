@@ -307,45 +307,49 @@ static int prepare_image_maps(DevCrop* dc, const cvgs_parent_t* parents, int use
     if (!parents || used <= 0) return -1;
     struct Slot { uintptr_t datastart; int rb; };
     Slot slots[kTmaImageMaps];
-    int idx_of[kTmaParamCrops];
-    int rb_of[kTmaParamCrops];
     int n_maps = 0;
     if (max_maps > kTmaImageMaps) max_maps = kTmaImageMaps;
-    // pass 1: nothing is modified until every crop is known to fit
-    std::vector<int> idx_big, rb_big;
-    int* idx = idx_of;
-    int* rbs = rb_of;
+    // nothing is modified until every crop is known to fit
+    struct Place { int32_t xb, y0, pad; };
+    Place place_small[kTmaParamCrops];
+    std::vector<Place> place_big;
+    Place* place = place_small;
     if (used > kTmaParamCrops) {
-        idx_big.resize(used);
-        rb_big.resize(used);
-        idx = idx_big.data();
-        rbs = rb_big.data();
+        place_big.resize(used);
+        place = place_big.data();
     }
+    uintptr_t last_ds = 0;
+    int last_rb = -1, last_k = -1;
     for (int i = 0; i < used; ++i) {
         const cvgs_parent_t& p = parents[i];
         if (!p.datastart || p.whole_width <= 0 || p.whole_height <= 0) return -1;
         const int rb = rb_class(band_row_bytes(std::min(32 * G.NPB, W), dc[i].fx));
         if (rb == 0 || 4 * rb + kSlotHeader > G.slot_bytes) return -1;
         const uintptr_t ds = reinterpret_cast<uintptr_t>(p.datastart);
-        int k = 0;
-        for (; k < n_maps; ++k)
-            if (slots[k].datastart == ds && slots[k].rb == rb) break;
-        if (k == n_maps) {
-            if (n_maps == max_maps) return -1;
-            const CUtensorMap* m = t_image_maps.get(ds, dc[i].pitch, p.whole_width, p.whole_height, rb);
-            if (!m) return -1;
-            maps[n_maps] = *m;
-            slots[n_maps++] = Slot{ds, rb};
+        int k = last_k;
+        if (ds != last_ds || rb != last_rb) {
+            for (k = 0; k < n_maps; ++k)
+                if (slots[k].datastart == ds && slots[k].rb == rb) break;
+            if (k == n_maps) {
+                if (n_maps == max_maps) return -1;
+                const CUtensorMap* m = t_image_maps.get(ds, dc[i].pitch, p.whole_width, p.whole_height, rb);
+                if (!m) return -1;
+                maps[n_maps] = *m;
+                slots[n_maps++] = Slot{ds, rb};
+            }
+            last_ds = ds;
+            last_rb = rb;
+            last_k = k;
         }
-        // geometry check without modifying the crop
-        DevCrop probe = dc[i];
+        DevCrop probe = dc[i];  // placement overwrites the pointer (union): keep the crops intact until all fit
         if (!tma_place_in_image(probe, ds, p.whole_width, p.whole_height, rb, k)) return -1;
-        idx[i] = k;
-        rbs[i] = rb;
+        place[i] = Place{probe.m.xb, probe.m.y0, probe.pad};
     }
-    for (int i = 0; i < used; ++i)
-        tma_place_in_image(dc[i], reinterpret_cast<uintptr_t>(parents[i].datastart), parents[i].whole_width,
-                           parents[i].whole_height, rbs[i], idx[i]);
+    for (int i = 0; i < used; ++i) {
+        dc[i].m.xb = place[i].xb;
+        dc[i].m.y0 = place[i].y0;
+        dc[i].pad = place[i].pad;
+    }
     return n_maps;
 }
 
@@ -359,8 +363,34 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
     if (used > n_planes) used = n_planes;
     if (used > 0 && !crops) return fail(CVGS_ERR_INVALID_VALUE, "crops is NULL");
 
+    // Frame loops repeat the same pipeline with a new output pointer: the normalised parameters are memoised
+    // (thread-local, keyed by the bytes of the pipeline struct without `out`, and the batch size).
+    struct ParamMemo {
+        bool valid = false;
+        cvgs_pipeline_t key;
+        int n_planes = 0, used = 0;
+        PreprocParams P;
+    };
+    static thread_local ParamMemo memo;
     PreprocParams P;
-    if (int rc = build_params(*pipe, n_planes, used, out, P)) return rc;
+    {
+        cvgs_pipeline_t key = *pipe;
+        key.out = nullptr;
+        if (memo.valid && memo.n_planes == n_planes && memo.used == used && std::memcmp(&memo.key, &key, sizeof key) == 0) {
+            P = memo.P;
+            P.out.base = out;
+            P.out.vec4 = P.out.px_stride == 1 && (P.W % 4) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0 &&
+                         (P.out.z_stride % 4) == 0 && (P.out.c_stride % 4) == 0;
+        } else {
+            if (int rc = build_params(*pipe, n_planes, used, out, P)) return rc;
+            std::memset(&memo.key, 0, sizeof memo.key);
+            memo.key = key;
+            memo.n_planes = n_planes;
+            memo.used = used;
+            memo.P = P;
+            memo.valid = true;
+        }
+    }
 
     int device = 0;
     CVGS_CUDA(cudaGetDevice(&device));

@@ -42,14 +42,15 @@ constexpr int kTmaParamCrops = 64;      // crops (descriptor + tensor map) that 
 constexpr int kWarps = 4;               // warps per CTA, each with its own slot ring
 constexpr int kTmaThreads = kWarps * 32;
 constexpr int kMaxSlots = 4;            // slots per warp
+constexpr int kMaxResident = 5;         // CTAs per SM the kernel is compiled for (<= 102 registers per thread)
 constexpr int kMaxNP = 4;               // 32-column groups per band: a band is at most 128 output columns
-constexpr int kSlotHeader = 128;        // per slot: two RowInfo records (+ room for the w[-1] over-read)
+constexpr int kSlotHeader = 128;        // per slot: room for the w[-1] over-read in front of the staged rows
 constexpr int kRingPad = 128;           // bytes behind the last slot (w[+1] over-read)
 constexpr int kMaxBoxBytes = 2048;      // 256 elements x 8 bytes
 constexpr float kWeightScale = 1.2676506002282294e30f;  // 2^100
 constexpr float kPreScale = 8589934592.0f;              // 2^33  = 2^133 / 2^100
-constexpr uint32_t kRowFill = 0xFFFFFFF0u;  // RowInfo::offA: row lies outside the image band -> background
-constexpr uint32_t kRowSkip = 0xFFFFFFFFu;  // RowInfo::offA: row is below the plane -> nothing to do
+constexpr uint32_t kRowFill = 0xFFFFFFF0u;  // RowTap::a: row lies outside the image band -> background
+constexpr uint32_t kRowSkip = 0xFFFFFFFFu;  // RowTap::a: row is below the plane (or past the warp's range) -> nothing to do
 
 struct TmaGeom {
     int32_t NPB;             // 32-column groups per band (1..kMaxNP); band width TW = 32 * NPB
@@ -63,6 +64,8 @@ struct TmaGeom {
     int32_t grid;            // CTAs; warp g = blockIdx.x * kWarps + warp walks a contiguous range of items whose
                              // total cost (32-column groups) is 1/(grid*kWarps) of the launch (ItemCursor::init)
     int32_t np_last;         // 32-column groups of the last band of a plane (the others have NPB)
+    int32_t w_full, w_crop;  // cost (column groups) of the full-width bands of a plane / of a whole plane
+    int32_t share_q, share_r;  // total cost = share_q * (grid * kWarps) + share_r
     int32_t explicit_prescale;  // 1: the kernel multiplies by 2^33 itself (no op to fold it into)
     int32_t pdl_wait;        // 1: wait for the preceding kernel before the first global access (stream order);
                              // 0: the host proved independence, wait only before exiting (completion order)
@@ -93,12 +96,15 @@ struct TmaNoTable {
     int32_t unused;
 };
 
-// Vertical taps of one output row of an item, written next to the staged rows when the item is staged.
-struct __align__(16) RowInfo {
-    uint32_t offA;   // byte offset (from the slot's data block) of the staged upper source row, or kRowFill/kRowSkip
-    uint32_t offB;   // ... of the lower source row (== offA when y2 is clamped, interpolation.cuh:73)
+// Vertical taps of one output row, computed 16 rows (8 items) at a time by 16 lanes of the warp that owns the
+// items and kept in a per-warp table; both the staging of an item and its computation read them from there.
+struct __align__(16) RowTap {
+    uint32_t a;      // kRowSkip / kRowFill, or y1 (first source row, relative to the crop) | kTapClamp when y2 == y1
     float wy0, wy1;  // (y2 - sy) * 2^100, (sy - y1) * 2^100
+    uint32_t pad;
 };
+constexpr uint32_t kTapClamp = 1u << 30;   // interpolation.cuh:73: y2_read == y1, both taps read the same source row
+constexpr int kTapBlock = 8;               // items per table block; the table holds two blocks (consumers lag <= kMaxSlots)
 
 // DevCrop::pad of a TMA launch: bits 0..15 = smem row bytes of this crop's box, bits 16..31 = tensor map index
 __host__ __device__ __forceinline__ int32_t crop_row_bytes(const DevCrop& c) { return c.pad & 0xFFFF; }
@@ -146,17 +152,23 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ RowInfo lds_rowinfo(uint32_t addr) {
-    RowInfo r;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.offA), "=r"(r.offB), "=f"(r.wy0), "=f"(r.wy1)
-                 : "r"(addr));
+__device__ __forceinline__ RowTap lds_rowtap(uint32_t addr) {
+    RowTap r;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.a), "=f"(r.wy0), "=f"(r.wy1), "=r"(r.pad) : "r"(addr));
     return r;
 }
-__device__ __forceinline__ void sts_rowinfo(uint32_t addr, const RowInfo& r) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r.offA), "r"(r.offB), "f"(r.wy0), "f"(r.wy1)
-                 : "memory");
+__device__ __forceinline__ void sts_rowtap(uint32_t addr, const RowTap& r) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r.a), "f"(r.wy0), "f"(r.wy1), "r"(r.pad) : "memory");
 }
+// One lane of the (converged) warp; lets the compiler issue warp-uniform work (TMA, mbarrier) without a per-lane loop.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+// Value of lane 0, known to the compiler to be warp-uniform (eligible for the uniform datapath).
+__device__ __forceinline__ int uniform_i(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint32_t uniform_u(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 // Programmatic dependent launch (no-ops when the kernel was launched without the attribute).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -220,22 +232,22 @@ __device__ __forceinline__ float2 div_by_const2(float2 x, float zh, float zl) {
 struct ItemCursor {
     int z, txi, jp, left;
     // first item whose cumulative cost reaches w (cost counted in column groups from the start of the launch)
-    static __device__ __forceinline__ long long item_at(const TmaGeom& G, long long w, long long w_crop, long long w_full) {
-        const long long z = w / w_crop;
-        const long long r = w - z * w_crop;
-        const long long in_crop = r < w_full ? r / G.NPB : (long long)(G.tiles_x - 1) * G.HP + (r - w_full) / G.np_last;
-        return z * G.items_per_crop + in_crop;
+    static __device__ __forceinline__ int item_at(const TmaGeom& G, uint32_t w) {
+        const uint32_t z = w / (uint32_t)G.w_crop;
+        const uint32_t r = w - z * (uint32_t)G.w_crop;
+        const uint32_t in_crop = r < (uint32_t)G.w_full ? r / (uint32_t)G.NPB
+                                                          : (uint32_t)((G.tiles_x - 1) * G.HP) + (r - (uint32_t)G.w_full) / (uint32_t)G.np_last;
+        return (int)(z * (uint32_t)G.items_per_crop + in_crop);
     }
     __device__ __forceinline__ void init(const TmaGeom& G, int g) {
-        const long long n_warps = (long long)G.grid * kWarps;
-        const long long w_full = (long long)(G.tiles_x - 1) * G.HP * G.NPB;  // cost of the full-width bands of a plane
-        const long long w_crop = w_full + (long long)G.HP * G.np_last;
-        const long long w_total = w_crop * (G.total_items / G.items_per_crop);
-        const long long i0 = item_at(G, w_total * g / n_warps, w_crop, w_full);
-        const long long i1 = g + 1 == n_warps ? (long long)G.total_items : item_at(G, w_total * (g + 1) / n_warps, w_crop, w_full);
-        left = (int)(i1 - i0);
-        z = (int)(i0 / G.items_per_crop);
-        const int rem = (int)(i0 - (long long)z * G.items_per_crop);
+        // warp g owns the cost range [g*q + min(g, r), ... + q + (g < r)) of the launch total q * n_warps + r (< 2^31)
+        const uint32_t w0 = (uint32_t)g * (uint32_t)G.share_q + (uint32_t)min(g, G.share_r);
+        const uint32_t w1 = w0 + (uint32_t)G.share_q + (g < G.share_r ? 1u : 0u);
+        const int i0 = item_at(G, w0);
+        const int i1 = g + 1 == G.grid * kWarps ? G.total_items : item_at(G, w1);
+        left = i1 - i0;
+        z = i0 / G.items_per_crop;
+        const int rem = i0 - z * G.items_per_crop;
         txi = rem / G.HP;
         jp = rem - txi * G.HP;
     }
@@ -319,23 +331,22 @@ struct StageBand {
     int z, txi;
     bool ok;               // the band receives image data at all
     int32_t c0, rb;        // box start coordinate, staged row bytes
-    int32_t by1, by2, hm1; // image rows of the plane, last source row
     int32_t y0;            // map row of the crop's first row
-    float fy;
     const CUtensorMap* map;
 };
 
 // GEN = false: the common geometry -- IGNORE_AR, every plane used, planar output.
 // GEN = true : aspect-ratio bands, unused planes, packed outputs.
 template <typename Table, int CHAIN, bool GEN>
-__global__ void __launch_bounds__(kTmaThreads, 4)
+__global__ void __launch_bounds__(kTmaThreads, kMaxResident)
 preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ Table T) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[kWarps * kMaxSlots];
+    __shared__ RowTap tap_table[kWarps][2 * 2 * kTapBlock];
 
     const PreprocParams& P = K.P;
     const TmaGeom& G = K.G;
-    const int warp = threadIdx.x >> 5;
+    const int warp = uniform_i(threadIdx.x >> 5);  // warp-uniform: cursors, slot and barrier addresses derive from it
     const int lane = threadIdx.x & 31;
     const int nslots = G.slots;
     const int W = P.W, H = P.H;
@@ -357,6 +368,10 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
     ItemCursor cc;  // item being computed
     cc.init(G, blockIdx.x * kWarps + warp);
     ItemCursor ic = cc;  // item being staged (nslots ahead)
+    const int first_item = cc.z * G.items_per_crop + cc.txi * G.HP + cc.jp;  // launch-wide index of this warp's first item
+    const int n_items = cc.left;
+    uint32_t taps = smem_u32(&tap_table[warp][0]);
+    asm volatile("" : "+r"(taps));
 
     // chain constants of the specialised shape v = fma(v, ca, cb) / cd  (source-channel order)
     float ca[3], cb[3], zh[3], zl[3];
@@ -395,14 +410,49 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         }
     }
 
-    // ---------------- staging: lanes 0 and 1 stage the two output rows of item `ic` into `slot` ----------------
+    // ---------------- vertical taps: lane l < 16 computes row (l & 1) of the warp's item blk * 8 + (l >> 1) ----------
+    auto compute_taps = [&](int blk) {
+        const int k = blk * kTapBlock + (lane >> 1);
+        RowTap t;
+        t.a = kRowSkip;
+        t.wy0 = t.wy1 = 0.f;
+        t.pad = 0;
+        if (lane < 2 * kTapBlock && k < n_items) {
+            const int idx = first_item + k;
+            const int z = idx / G.items_per_crop;
+            const int rem = idx - z * G.items_per_crop;
+            const int txi = rem / G.HP;
+            const int y = 2 * (rem - txi * G.HP) + (lane & 1);
+            if (y < H) {
+                t.a = kRowFill;
+                if (!GEN || z < P.used) {
+                    const DevCrop& C = tma_crop_of<Table>(K, T, z);
+                    const int tx0 = txi * TW;
+                    const bool band_ok = max(tx0, C.bx1) <= min(min(tx0 + TW, W) - 1, C.bx2);
+                    if (band_ok && y >= C.by1 && y <= C.by2) {
+                        const AxisTap v = axis_tap(y - C.by1, C.fy);
+                        t.a = (uint32_t)v.i1 | ((v.i1 + 1 > C.h - 1) ? kTapClamp : 0u);
+                        t.wy0 = __fmul_rn(v.w0, kWeightScale);
+                        t.wy1 = __fmul_rn(v.w1, kWeightScale);
+                    }
+                }
+            }
+        }
+        if (lane < 2 * kTapBlock) sts_rowtap(taps + (uint32_t)(((blk & 1) * 2 * kTapBlock + lane) * sizeof(RowTap)), t);
+        __syncwarp();
+    };
+    // table address of row 0 of the warp's k-th item (row 1 follows)
+    auto tap_addr = [&](int k) { return taps + (uint32_t)((k & (2 * kTapBlock - 1)) * 2 * sizeof(RowTap)); };
+
+    // ---------------- staging: lane 0 stages the (up to) two 2-row boxes of the warp's item number ks ----------------
     StageBand sb;
     sb.z = sb.txi = -1;
     sb.ok = false;
-    sb.c0 = sb.rb = sb.by1 = sb.by2 = sb.hm1 = sb.y0 = 0;
-    sb.fy = 1.f;
+    sb.c0 = sb.rb = sb.y0 = 0;
     sb.map = nullptr;
+    int ks = 0;  // number of items staged so far
     auto stage_item = [&](int slot) {
+        if ((ks & (kTapBlock - 1)) == 0) compute_taps(ks / kTapBlock);
         if (ic.z != sb.z || ic.txi != sb.txi) {
             sb.z = ic.z;
             sb.txi = ic.txi;
@@ -410,52 +460,36 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             if (!GEN || ic.z < P.used) {
                 const DevCrop& C = tma_crop_of<Table>(K, T, ic.z);
                 const BandOrigin b = band_origin(P, G, C, ic.txi);
-                sb.ok = b.xa <= b.xe;
-                sb.c0 = b.c0;
-                sb.rb = crop_row_bytes(C);
-                sb.by1 = C.by1;
-                sb.by2 = C.by2;
-                sb.hm1 = C.h - 1;
-                sb.fy = C.fy;
-                sb.y0 = C.m.y0;
+                // all lanes computed the same values; telling the compiler so keeps the TMA issue below loop-free
+                sb.ok = uniform_i(b.xa <= b.xe) != 0;
+                sb.c0 = uniform_i(b.c0);
+                sb.rb = uniform_i(crop_row_bytes(C));
+                sb.y0 = uniform_i(C.m.y0);
                 sb.map = tma_map_of<Table>(K, T, C);
+                const unsigned long long mp = reinterpret_cast<unsigned long long>(sb.map);
+                sb.map = reinterpret_cast<const CUtensorMap*>(
+                    ((unsigned long long)uniform_u((uint32_t)(mp >> 32)) << 32) | uniform_u((uint32_t)mp));
             }
         }
-        const uint32_t sbase = ring + (uint32_t)slot * slot_bytes;
-        const uint32_t full = bars + 8 * slot;
-        bool issue = false;
-        int i1 = 0;
-        if (lane < 2) {
-            RowInfo ri;
-            ri.offA = kRowSkip;
-            ri.offB = 0;
-            ri.wy0 = ri.wy1 = 0.f;
-            const int y = 2 * ic.jp + lane;
-            if (y < H) {
-                ri.offA = kRowFill;
-                if (sb.ok && y >= sb.by1 && y <= sb.by2) {
-                    issue = true;
-                    const AxisTap t = axis_tap(y - sb.by1, sb.fy);
-                    i1 = t.i1;
-                    ri.offA = (uint32_t)(lane * 2 * sb.rb);
-                    ri.offB = ri.offA + ((t.i1 + 1 > sb.hm1) ? 0u : (uint32_t)sb.rb);
-                    ri.wy0 = __fmul_rn(t.w0, kWeightScale);
-                    ri.wy1 = __fmul_rn(t.w1, kWeightScale);
-                }
-            }
-            sts_rowinfo(sbase + lane * (uint32_t)sizeof(RowInfo), ri);
+        const uint32_t ta = tap_addr(ks);
+        const uint32_t a0 = uniform_u(lds32(ta)), a1 = uniform_u(lds32(ta + (uint32_t)sizeof(RowTap)));
+        if (elect_one_sync()) {
+            const uint32_t sdst = ring + (uint32_t)slot * slot_bytes + kSlotHeader;
+            const uint32_t full = bars + 8 * slot;
+            const bool i0 = a0 < kRowFill, i1 = a1 < kRowFill;
+            // the slot's previous contents were read through the generic proxy; the TMA writes through the async proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(full, (uint32_t)(((int)i0 + (int)i1) * 2 * sb.rb));
+            if (i0) tma_load_2d(sdst, sb.map, sb.c0, sb.y0 + (int)(a0 & (kTapClamp - 1)), full);
+            if (i1) tma_load_2d(sdst + 2 * sb.rb, sb.map, sb.c0, sb.y0 + (int)(a1 & (kTapClamp - 1)), full);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, issue);  // also orders the RowInfo stores before the arrive
-        // the slot's previous contents were read through the generic proxy; the TMA writes through the async proxy
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(__popc(m) * 2 * sb.rb));
-        if (issue) tma_load_2d(sbase + kSlotHeader + lane * 2 * sb.rb, sb.map, sb.c0, sb.y0 + i1, full);
+        ++ks;
         ic.next(G);
     };
 
     for (int s = 0; s < nslots && ic.left > 0; ++s) stage_item(s);
 
-    int slot = 0;
+    int slot = 0, kc = 0;  // kc = number of items computed so far
     uint32_t phase = 0;
     while (cc.left > 0) {
         // ---------------- horizontal state of this lane for the band (z, txi): column p is tx0 + lane + 32 p ------
@@ -465,6 +499,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         int32_t off[kMaxNP], shl[kMaxNP], shr[kMaxNP];
         float wxa[kMaxNP], wxb[kMaxNP];
         bool edge[kMaxNP], img[kMaxNP], inw[kMaxNP];  // right tap clamped / column receives image data / column < W
+        uint32_t rb = 0;                              // staged row bytes of this crop
         {
             const bool active = !GEN || z < P.used;
             BandOrigin b;
@@ -479,6 +514,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                 fx = C.fx;
                 bx1 = C.bx1;
                 wm1 = C.w - 1;
+                rb = (uint32_t)crop_row_bytes(C);
             }
 #pragma unroll
             for (int p = 0; p < kMaxNP; ++p) {
@@ -504,24 +540,31 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         const int nitems = min(cc.left, G.HP - cc.jp);  // items of this band inside the warp's range
         for (int it = 0; it < nitems; ++it) {
             mbar_wait(bars + 8 * slot, phase);
-            const uint32_t sbase = ring + (uint32_t)slot * slot_bytes;
-            const uint32_t sdata = sbase + kSlotHeader;
-            const RowInfo r0 = lds_rowinfo(sbase);
-            const RowInfo r1 = lds_rowinfo(sbase + (uint32_t)sizeof(RowInfo));
-            const bool st1 = r1.offA != kRowSkip;
-            const bool im0 = !GEN || r0.offA < kRowFill, im1 = r1.offA < kRowFill;
-            // a row without image data borrows the other row's taps (its values are replaced / not stored)
+            const uint32_t sdata = ring + (uint32_t)slot * slot_bytes + kSlotHeader;
+            const uint32_t ta = tap_addr(kc);
+            const RowTap r0 = lds_rowtap(ta);
+            const RowTap r1 = lds_rowtap(ta + (uint32_t)sizeof(RowTap));
+            const bool st1 = r1.a != kRowSkip;
+            const bool im0 = !GEN || r0.a < kRowFill, im1 = r1.a < kRowFill;
+            // staged rows of the slot: [row 0: y1, y1+1][row 1: y1, y1+1], rb bytes each; a clamped y2 re-reads y1.
+            // A row without image data borrows the other row's taps (its values are replaced / not stored).
+            const uint32_t b0 = (r0.a & kTapClamp) ? 0u : rb, b1 = (r1.a & kTapClamp) ? 0u : rb;
             uint32_t aA0, aB0, aA1, aB1;
             float2 wy0, wy1;
-            if (GEN) {
-                aA0 = sdata + (im0 ? r0.offA : r1.offA), aB0 = sdata + (im0 ? r0.offB : r1.offB);
-                wy0.x = im0 ? r0.wy0 : r1.wy0, wy1.x = im0 ? r0.wy1 : r1.wy1;
-            } else {
-                aA0 = sdata + r0.offA, aB0 = sdata + r0.offB;
+            if (!GEN || im0) {
+                aA0 = sdata, aB0 = sdata + b0;
                 wy0.x = r0.wy0, wy1.x = r0.wy1;
+            } else {
+                aA0 = sdata + 2 * rb, aB0 = aA0 + b1;
+                wy0.x = r1.wy0, wy1.x = r1.wy1;
             }
-            aA1 = sdata + (im1 ? r1.offA : r0.offA), aB1 = sdata + (im1 ? r1.offB : r0.offB);
-            wy0.y = im1 ? r1.wy0 : r0.wy0, wy1.y = im1 ? r1.wy1 : r0.wy1;
+            if (im1) {
+                aA1 = sdata + 2 * rb, aB1 = aA1 + b1;
+                wy0.y = r1.wy0, wy1.y = r1.wy1;
+            } else {
+                aA1 = sdata, aB1 = sdata + b0;
+                wy0.y = r0.wy0, wy1.y = r0.wy1;
+            }
             // row pointers of the pair; opaque to the compiler so that they stay in registers instead of being
             // re-derived in front of every store
             float* t0 = s0 + row_step;
@@ -577,6 +620,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             // every lane has consumed its taps of this slot (their values fed the stores above): refill it
             __syncwarp();
             if (ic.left > 0) stage_item(slot);
+            ++kc;
             if (++slot == nslots) {
                 slot = 0;
                 phase ^= 1u;
@@ -662,22 +706,34 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
     G.slot_bytes = kSlotHeader + 4 * rb_max;  // rb_max is a multiple of 64: slots stay 128-byte aligned
     G.explicit_prescale = 0;
     G.pdl_wait = 1;
-    // ring depth: as deep as possible while four CTAs stay resident per SM, but at least two slots
+    // ring depth: as deep as possible while kMaxResident CTAs stay resident per SM, but at least two slots
     const int smem_sm = 227 * 1024;
-    auto cta_bytes = [&](int slots) { return kWarps * slots * G.slot_bytes + kRingPad + 128 + 1024 /*static + reserved*/; };
+    // dynamic ring + static (tap tables, barriers) + the 1 KB the driver reserves per CTA
+    auto cta_bytes = [&](int slots) {
+        return kWarps * slots * G.slot_bytes + kRingPad + 128 + kWarps * 4 * kTapBlock * static_cast<int>(sizeof(RowTap)) + 256 + 1024;
+    };
     int slots = kMaxSlots;
-    while (slots > 2 && smem_sm / cta_bytes(slots) < 4) --slots;
+    while (slots > 2 && smem_sm / cta_bytes(slots) < kMaxResident) --slots;
     if (const char* e = std::getenv("CVGS_TMA_SLOTS")) {  // tuning override (tests / profiling)
         const int v = std::atoi(e);
         if (v >= 1 && v <= kMaxSlots) slots = v;
     }
     if (cta_bytes(slots) > smem_sm) return false;
     G.slots = slots;
-    G.resident = std::min(4, smem_sm / cta_bytes(slots));
+    G.resident = std::min(kMaxResident, smem_sm / cta_bytes(slots));
     const long long warps_wanted = std::max<long long>(1, total);  // at least one item per warp
     const long long ctas_wanted = (warps_wanted + kWarps - 1) / kWarps;
     G.grid = static_cast<int32_t>(std::min<long long>(ctas_wanted, static_cast<long long>(G.resident) * sm_count));
     G.np_last = (std::min(TW, P.W - (G.tiles_x - 1) * TW) + 31) / 32;
+    const long long w_full = static_cast<long long>(G.tiles_x - 1) * G.HP * NPB;
+    const long long w_crop = w_full + static_cast<long long>(G.HP) * G.np_last;
+    const long long w_total = w_crop * n_planes;
+    if (w_total > 0x7fffffffLL) return false;
+    G.w_full = static_cast<int32_t>(w_full);
+    G.w_crop = static_cast<int32_t>(w_crop);
+    const long long n_warps = static_cast<long long>(G.grid) * kWarps;
+    G.share_q = static_cast<int32_t>(w_total / n_warps);
+    G.share_r = static_cast<int32_t>(w_total % n_warps);
     return true;
 }
 
