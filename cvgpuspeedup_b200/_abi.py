@@ -20,7 +20,7 @@ PRESERVE_AR, IGNORE_AR, PRESERVE_AR_RN_EVEN, PRESERVE_AR_LEFT = 0, 1, 2, 3
 OP_MUL, OP_SUB, OP_DIV, OP_ADD, OP_REORDER = 1, 2, 3, 4, 5
 FP_REFERENCE_FUSED, FP_SEPARATE = 0, 1
 INTERP_FLOAT, INTERP_ROUND_U8 = 0, 1
-OUT_NCHW, OUT_CNHW, OUT_NHWC = 0, 1, 2
+OUT_NCHW, OUT_CNHW, OUT_NHWC, OUT_PLANES = 0, 1, 2, 3
 CT_NEWEST_FIRST, CT_OLDEST_FIRST = 0, 1
 CT_STANDARD, CT_TRANSPOSED = 0, 1
 
@@ -44,6 +44,10 @@ class Pipeline(C.Structure):
 
 class Parent(C.Structure):
     _fields_ = [("datastart", C.c_void_p), ("whole_width", C.c_int32), ("whole_height", C.c_int32)]
+
+
+class Plane(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("pitch_bytes", C.c_int64)]
 
 
 class Rect(C.Structure):

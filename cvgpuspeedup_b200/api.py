@@ -18,7 +18,7 @@ from typing import List, Optional, Sequence, Tuple
 from . import _abi
 from ._abi import (CT_NEWEST_FIRST, CT_OLDEST_FIRST, CT_STANDARD, CT_TRANSPOSED, FP_REFERENCE_FUSED,
                    FP_SEPARATE, IGNORE_AR, INTERP_FLOAT, INTERP_ROUND_U8, OUT_CNHW, OUT_NCHW, OUT_NHWC,
-                   PRESERVE_AR, PRESERVE_AR_LEFT, PRESERVE_AR_RN_EVEN, CvgsError)
+                   OUT_PLANES, PRESERVE_AR, PRESERVE_AR_LEFT, PRESERVE_AR_RN_EVEN, CvgsError)
 
 # cv::ColorConversionCodes values used by the reference tests (cv2cuda_types.cuh:77-86)
 COLOR_BGR2RGB = 4
@@ -87,6 +87,7 @@ class _Write:
     layout: int
     plane_stride: int = 0
     owner: object = None
+    planes: object = None  # OUT_PLANES: ctypes array of _abi.Plane kept alive with the op
 
 
 def resize(crops: Sequence[GpuMat], dsize: Tuple[int, int], usedPlanes: Optional[int] = None,
@@ -135,6 +136,22 @@ def cvtColor(code: int = COLOR_RGB2BGR) -> _Op:
 def split(out, planeDims: Optional[Tuple[int, int]] = None, plane_stride: int = 0) -> _Write:
     """cvGS::split<CV_32FC3>(GpuMat out, Size plane) :185-192 -> fk::TensorSplit (NCHW)."""
     return _Write(out.data_ptr(), OUT_NCHW, plane_stride, out)
+
+
+def split_planes(planes) -> _Write:
+    """cvGS::split<CV_32FC3>(vector<GpuMat>) / split<CV_32FC3, N>(array<vector<GpuMat>, N>) :163-183 -> fk::SplitWrite:
+    `planes` = per crop three 2-D float32 CUDA tensors (rows contiguous, any row pitch), or one such triple."""
+    if len(planes) == 3 and not isinstance(planes[0], (list, tuple)):
+        planes = [planes]
+    flat = [t for crop in planes for t in crop]
+    if any(len(crop) != 3 for crop in planes):
+        raise CvgsError("three destination images per crop are required")
+    arr = (_abi.Plane * max(1, len(flat)))()
+    for i, t in enumerate(flat):
+        if t.dim() != 2 or t.stride(1) != 1:
+            raise CvgsError("destination images must be 2-D with contiguous rows")
+        arr[i].data, arr[i].pitch_bytes = t.data_ptr(), t.stride(0) * 4
+    return _Write(C.addressof(arr), _abi.OUT_PLANES, 0, flat, arr)
 
 
 def splitT(out, plane_stride: int = 0) -> _Write:

@@ -46,7 +46,12 @@ struct DevProgram {
     DevOp ops[8];
 };
 
+struct DevPlane {       // one destination image of the per-plane output form (fk::SplitWrite)
+    float* data;
+    long long pitch;    // floats between rows
+};
 struct OutDesc {
+    const DevPlane* planes;  // device table [z][source channel], or nullptr for the tensor layouts below
     float* base;
     long long z_stride;  // floats between batch planes
     long long c_stride;  // floats between colour planes
@@ -170,6 +175,10 @@ __device__ __forceinline__ void store_pixels(const PreprocParams& P, int z, int 
     for (int r = 0; r < 3; ++r) {
         // the channel reorder costs nothing: it only changes which plane register r goes to
         float* dst = row + (long long)P.prog.dst_chan[r] * o.c_stride;
+        if (o.planes) {  // table is indexed by SOURCE channel (the host applied dst_chan when it built it)
+            const DevPlane pl = o.planes[z * 3 + r];
+            dst = pl.data + (long long)y * pl.pitch + x;
+        }
         if (NPIX == 4 && o.vec4 && nvalid == 4) {
             st_cs_f32x4(dst, v[0][r], v[1][r], v[2][r], v[3][r]);
         } else {

@@ -186,7 +186,7 @@ preproc_direct_kernel(const __grid_constant__ PreprocParams P, const __grid_cons
 // ------------------------------------------------------------------------------------------------
 struct Ring {
     static constexpr int kSlots = 8;
-    // one slot = [cap tensor maps][cap crop descriptors], pinned host copy + device copy
+    // one slot = [cap tensor maps][cap crop descriptors][3 * cap destination planes], pinned host copy + device copy
     uint8_t* h[kSlots] = {};
     uint8_t* d[kSlots] = {};
     cudaEvent_t ev[kSlots] = {};
@@ -194,7 +194,9 @@ struct Ring {
     size_t cap = 0;  // crops per slot
     int next = 0;
     int device = -1;
-    static size_t slot_bytes(size_t cap) { return cap * (sizeof(CUtensorMap) + sizeof(DevCrop)); }
+    static size_t slot_bytes(size_t cap) { return cap * (sizeof(CUtensorMap) + sizeof(DevCrop) + 3 * sizeof(DevPlane)); }
+    DevPlane* planes_h(int s) const { return reinterpret_cast<DevPlane*>(h[s] + cap * (sizeof(CUtensorMap) + sizeof(DevCrop))); }
+    DevPlane* planes_d(int s) const { return reinterpret_cast<DevPlane*>(d[s] + cap * (sizeof(CUtensorMap) + sizeof(DevCrop))); }
     CUtensorMap* maps_h(int s) const { return reinterpret_cast<CUtensorMap*>(h[s]); }
     CUtensorMap* maps_d(int s) const { return reinterpret_cast<CUtensorMap*>(d[s]); }
     DevCrop* crops_h(int s) const { return reinterpret_cast<DevCrop*>(h[s] + cap * sizeof(CUtensorMap)); }
@@ -397,7 +399,8 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
     const int variant = g_variant.load(std::memory_order_relaxed);
     const int sms = sm_count_of(device);
 
-    if (used <= kTmaParamCrops) {
+    const bool planes_out = pipe->out_layout == CVGS_OUT_PLANES;  // needs a device table of destinations: ring path
+    if (used <= kTmaParamCrops && !planes_out) {
         // small batch: descriptors (and tensor maps) ride in the kernel parameters -- no staging copy,
         // graph-capturable
         alignas(64) TmaParamTable tt;  // also serves as the image-mode table (its first maps / same crop array offset
@@ -450,7 +453,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         return launch_direct(P, &table, stream);
     }
 
-    if (used <= kTmaImageCrops && parents && variant != 1) {
+    if (used <= kTmaImageCrops && parents && variant != 1 && !planes_out) {
         // medium batch with named parent images: a few cached maps + the descriptors still fit the kernel
         // parameters (13 KB), so there is no staging copy in front of the kernel
         alignas(64) TmaImageTableL lt;
@@ -471,7 +474,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
     }
 
     Ring& r = t_ctx.ring;
-    if (int rc = ring_reserve(r, static_cast<size_t>(used), device)) return rc;
+    if (int rc = ring_reserve(r, static_cast<size_t>(std::max(used, n_planes)), device)) return rc;
     const int slot = r.next;
     r.next = (r.next + 1) % Ring::kSlots;
     if (r.pending[slot]) { CVGS_CUDA(cudaEventSynchronize(r.ev[slot])); r.pending[slot] = false; }
@@ -499,6 +502,23 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         }
     }
     if (!use_tma && variant == 2) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
+    if (planes_out) {
+        // destination images, indexed [z][source channel] on the device (the channel reorder is applied here)
+        const cvgs_plane_t* hp = static_cast<const cvgs_plane_t*>(pipe->out);
+        DevPlane* dp = r.planes_h(slot);
+        for (int z = 0; z < n_planes; ++z)
+            for (int c = 0; c < 3; ++c) {
+                const cvgs_plane_t& q = hp[z * 3 + P.prog.dst_chan[c]];
+                if (!q.data || q.pitch_bytes < 4LL * P.W || (q.pitch_bytes & 3))
+                    return fail(CVGS_ERR_INVALID_VALUE, "plane " + std::to_string(z) + ": bad destination image");
+                dp[z * 3 + c].data = static_cast<float*>(q.data);
+                dp[z * 3 + c].pitch = q.pitch_bytes / 4;
+            }
+        CVGS_CUDA(cudaMemcpyAsync(r.planes_d(slot), dp, static_cast<size_t>(n_planes) * 3 * sizeof(DevPlane),
+                                  cudaMemcpyHostToDevice, stream));
+        P.out.planes = r.planes_d(slot);
+        K.P.out.planes = r.planes_d(slot);
+    }
     // one or two copies: the maps actually used, and the crop descriptors
     if (use_tma)
         CVGS_CUDA(cudaMemcpyAsync(r.maps_d(slot), r.maps_h(slot), map_bytes, cudaMemcpyHostToDevice, stream));

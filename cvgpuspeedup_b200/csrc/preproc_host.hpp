@@ -108,7 +108,7 @@ inline int validate_pipeline(const cvgs_pipeline_t* p) {
     if (p->aspect_mode < 0 || p->aspect_mode > 3) return fail(CVGS_ERR_INVALID_VALUE, "bad aspect_mode");
     if (p->interp_mode < 0 || p->interp_mode > 1) return fail(CVGS_ERR_INVALID_VALUE, "bad interp_mode");
     if (p->fp_contract < 0 || p->fp_contract > 1) return fail(CVGS_ERR_INVALID_VALUE, "bad fp_contract");
-    if (p->out_layout < 0 || p->out_layout > 2) return fail(CVGS_ERR_INVALID_VALUE, "bad out_layout");
+    if (p->out_layout < 0 || p->out_layout > 3) return fail(CVGS_ERR_INVALID_VALUE, "bad out_layout");
     if (p->out_plane_stride < 0) return fail(CVGS_ERR_INVALID_VALUE, "negative out_plane_stride");
     return CVGS_OK;
 }
@@ -126,7 +126,14 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
     const long long plane = static_cast<long long>(p.dst_width) * p.dst_height;
     OutDesc& o = P.out;
     o.base = out;
+    o.planes = nullptr;
     switch (p.out_layout) {
+        case CVGS_OUT_PLANES:  // the launch path uploads the plane table and sets o.planes
+            o.base = nullptr;
+            o.z_stride = 0;
+            o.c_stride = 0;
+            o.px_stride = 1;
+            break;
         case CVGS_OUT_NCHW:
             o.z_stride = p.out_plane_stride ? p.out_plane_stride : 3 * plane;
             o.c_stride = plane;
@@ -142,8 +149,8 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
             o.c_stride = 1;
             o.px_stride = 3;
     }
-    o.vec4 = o.px_stride == 1 && (p.dst_width % 4) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0 &&
-             (o.z_stride % 4) == 0 && (o.c_stride % 4) == 0;
+    o.vec4 = p.out_layout != CVGS_OUT_PLANES && o.px_stride == 1 && (p.dst_width % 4) == 0 &&
+             (reinterpret_cast<uintptr_t>(out) % 16) == 0 && (o.z_stride % 4) == 0 && (o.c_stride % 4) == 0;
     return CVGS_OK;
 }
 

@@ -536,6 +536,14 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         float* s1 = s0 + oc1;
         float* s2 = s0 + oc2;
         s0 += oc0;
+        long long rs0 = row_step, rs1 = row_step, rs2 = row_step;  // floats between vertically adjacent pixels
+        if (GEN && P.out.planes) {  // per-plane destinations (fk::SplitWrite): own pointer and pitch per channel
+            const DevPlane p0 = P.out.planes[z * 3], p1 = P.out.planes[z * 3 + 1], p2 = P.out.planes[z * 3 + 2];
+            rs0 = p0.pitch, rs1 = p1.pitch, rs2 = p2.pitch;
+            s0 = p0.data + (tx0 + lane) + (long long)(2 * cc.jp) * rs0;
+            s1 = p1.data + (tx0 + lane) + (long long)(2 * cc.jp) * rs1;
+            s2 = p2.data + (tx0 + lane) + (long long)(2 * cc.jp) * rs2;
+        }
 
         const int nitems = min(cc.left, G.HP - cc.jp);  // items of this band inside the warp's range
         for (int it = 0; it < nitems; ++it) {
@@ -567,9 +575,9 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             }
             // row pointers of the pair; opaque to the compiler so that they stay in registers instead of being
             // re-derived in front of every store
-            float* t0 = s0 + row_step;
-            float* t1 = s1 + row_step;
-            float* t2 = s2 + row_step;
+            float* t0 = s0 + (GEN ? rs0 : (long long)row_step);
+            float* t1 = s1 + (GEN ? rs1 : (long long)row_step);
+            float* t2 = s2 + (GEN ? rs2 : (long long)row_step);
             asm volatile("" : "+l"(s0), "+l"(s1), "+l"(s2), "+l"(t0), "+l"(t1), "+l"(t2));
             asm volatile("" : "+r"(aA0), "+r"(aB0), "+r"(aA1), "+r"(aB1), "+f"(wy0.x), "+f"(wy0.y), "+f"(wy1.x), "+f"(wy1.y));
 #pragma unroll
@@ -613,9 +621,9 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                     }
                 }
             }
-            s0 += 2 * row_step;
-            s1 += 2 * row_step;
-            s2 += 2 * row_step;
+            s0 += 2 * (GEN ? rs0 : (long long)row_step);
+            s1 += 2 * (GEN ? rs1 : (long long)row_step);
+            s2 += 2 * (GEN ? rs2 : (long long)row_step);
 
             // every lane has consumed its taps of this slot (their values fed the stores above): refill it
             __syncwarp();
@@ -907,7 +915,7 @@ template <typename Table>
 inline int tma_launch_kernel(const TmaParams& K, const Table& T, int chain, int device, cudaStream_t stream) {
     static_assert(sizeof(TmaParams) + sizeof(Table) <= 32 * 1024, "kernel parameters exceed 32 KB");
     const PreprocParams& P = K.P;
-    const bool fast = !P.band_test && P.used == P.n_planes && P.out.px_stride == 1;
+    const bool fast = !P.band_test && P.used == P.n_planes && P.out.px_stride == 1 && !P.out.planes;
     if (chain == CH_FMA_DIV)
         return fast ? tma_launch_instance<Table, CH_FMA_DIV, false>(K, T, device, stream)
                     : tma_launch_instance<Table, CH_FMA_DIV, true>(K, T, device, stream);

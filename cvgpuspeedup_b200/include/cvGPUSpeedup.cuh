@@ -66,6 +66,7 @@ struct WriteOp {  // split / splitT / write
     void* out = nullptr;
     int layout = CVGS_OUT_NCHW;
     long long plane_stride = 0;
+    std::vector<cvgs_plane_t> planes;  // split(vector<GpuMat>): one destination image per (crop, channel)
 };
 template <typename T>
 struct is_op : std::false_type {};
@@ -85,9 +86,15 @@ inline void append(cvgs_pipeline_t& p, const ChainOp& c) {
     }
 }
 inline void append(cvgs_pipeline_t& p, const WriteOp& w) {
-    p.out = w.out;
+    p.out = w.layout == CVGS_OUT_PLANES ? const_cast<cvgs_plane_t*>(w.planes.data()) : w.out;
     p.out_layout = w.layout;
     p.out_plane_stride = w.plane_stride;
+}
+inline cvgs_plane_t plane_of(const cv::cuda::GpuMat& m) {  // gpuMat2RawPtr2D<float>, reference :40-44
+    cvgs_plane_t q{};
+    q.data = m.data;
+    q.pitch_bytes = static_cast<int64_t>(m.step);
+    return q;
 }
 template <typename T>
 inline void append(cvgs_pipeline_t&, const T&) {
@@ -216,20 +223,41 @@ inline detail::ChainOp cvtColor() {
 template <int O>
 inline detail::WriteOp split(const cv::cuda::GpuMat& output, const cv::Size& /*planeDims*/) {
     static_assert(O == CV_32FC3, "cvGS (B200 build): CV_32FC3 output");
-    return {output.data, CVGS_OUT_NCHW, 0};  // the reference builds a tight Tensor and ignores GpuMat::step (:67-71)
+    return {output.data, CVGS_OUT_NCHW, 0, {}};  // the reference builds a tight Tensor and ignores GpuMat::step (:67-71)
+}
+// fk::SplitWrite: the channels of a crop go to separate CV_32FC1 images (reference :163-183)
+template <int O>
+inline detail::WriteOp split(const std::vector<cv::cuda::GpuMat>& output) {
+    static_assert(O == CV_32FC3, "cvGS (B200 build): CV_32FC3 output");
+    if (output.size() != 3) throw std::runtime_error("cvGS::split: three destination images are required");
+    detail::WriteOp w;
+    w.layout = CVGS_OUT_PLANES;
+    for (const auto& m : output) w.planes.push_back(detail::plane_of(m));
+    return w;
+}
+template <int O, int N>
+inline detail::WriteOp split(const std::array<std::vector<cv::cuda::GpuMat>, N>& output) {
+    static_assert(O == CV_32FC3, "cvGS (B200 build): CV_32FC3 output");
+    detail::WriteOp w;
+    w.layout = CVGS_OUT_PLANES;
+    for (const auto& crop : output) {
+        if (crop.size() != 3) throw std::runtime_error("cvGS::split: three destination images per crop are required");
+        for (const auto& m : crop) w.planes.push_back(detail::plane_of(m));
+    }
+    return w;
 }
 template <int O>
 inline detail::WriteOp split(const fk::RawPtr<fk::_3D, float>& output) {
-    return {output.data, CVGS_OUT_NCHW, 0};
+    return {output.data, CVGS_OUT_NCHW, 0, {}};
 }
 template <int O>
 inline detail::WriteOp splitT(const fk::RawPtr<fk::T3D, float>& output) {
-    return {output.data, CVGS_OUT_CNHW, 0};
+    return {output.data, CVGS_OUT_CNHW, 0, {}};
 }
 template <int O>
 inline detail::WriteOp write(const cv::cuda::GpuMat& output, const cv::Size& /*plane*/) {
     static_assert(O == CV_32FC3, "cvGS (B200 build): CV_32FC3 output");
-    return {output.data, CVGS_OUT_NHWC, 0};
+    return {output.data, CVGS_OUT_NHWC, 0, {}};
 }
 
 // ---- executeOperations (reference :464-473) --------------------------------------------------------------

@@ -84,8 +84,18 @@ enum cvgs_interp_mode { CVGS_INTERP_FLOAT = 0, CVGS_INTERP_ROUND_U8 = 1 };
 enum cvgs_out_layout {
     CVGS_OUT_NCHW = 0, /* fk::TensorSplit  : out[z][c][y][x]; cvGS::split(GpuMat, Size)   */
     CVGS_OUT_CNHW = 1, /* fk::TensorTSplit : out[c][z][y][x]; cvGS::splitT(RawPtr<T3D>)   */
-    CVGS_OUT_NHWC = 2  /* fk::PerThreadWrite<_3D,float3>: packed; cvGS::write(GpuMat,Size) */
+    CVGS_OUT_NHWC = 2, /* fk::PerThreadWrite<_3D,float3>: packed; cvGS::write(GpuMat,Size) */
+    CVGS_OUT_PLANES = 3 /* fk::SplitWrite: one 2-D float image per (crop, channel), each with its own pointer and
+                           pitch; cvGS::split(vector<GpuMat>) / split(array<vector<GpuMat>,N>)
+                           (reference memory_operations.cuh:331-360, cvGPUSpeedup.cuh:163-183).  `out` is then a
+                           HOST pointer to n_planes * 3 cvgs_plane_t, crop-major: [z][c]. */
 };
+
+/* One destination image of CVGS_OUT_PLANES = fk::RawPtr<fk::_2D, float> built from a CV_32FC1 GpuMat. */
+typedef struct cvgs_plane {
+    void* data;          /* device pointer, float                                  */
+    int64_t pitch_bytes; /* bytes between rows (GpuMat::step), a multiple of 4     */
+} cvgs_plane_t;
 
 /* One source crop = fk::RawPtr<fk::_2D, T> {data, {width, height, pitch}}
  * (reference fkl/.../core/data/ptr_nd.h:24-60; built by cvGS::gpuMat2RawPtr2D,
@@ -123,7 +133,7 @@ typedef struct cvgs_pipeline {
     cvgs_op_t ops[CVGS_MAX_OPS];
     int32_t out_layout; /* enum cvgs_out_layout                                    */
     int32_t reserved;
-    void* out;                 /* device pointer, float                             */
+    void* out;                 /* device pointer, float (CVGS_OUT_PLANES: host array of cvgs_plane_t) */
     int64_t out_plane_stride;  /* floats between consecutive batch planes z; 0 = tight
                                   (3*dst_width*dst_height for NCHW/NHWC, dst_width*dst_height
                                   for CNHW).  The reference ignores GpuMat::step. */

@@ -192,6 +192,12 @@ static void store_pixel(const cvgs_pipeline_t* p, int n_planes, int z, int y, in
             b[0] = v[0]; b[ps * n_planes] = v[1]; b[2 * ps * n_planes] = v[2];
             break;
         }
+        case CVGS_OUT_PLANES: { /* SplitWrite memory_operations.cuh:331-360: one RawPtr<_2D,float> per channel */
+            const cvgs_plane_t* pl = (const cvgs_plane_t*)p->out + (int64_t)z * 3;
+            for (int c = 0; c < 3; ++c)
+                *(float*)((char*)pl[c].data + (int64_t)y * pl[c].pitch_bytes + (int64_t)x * 4) = v[c];
+            break;
+        }
         default: {
             const int64_t ps = p->out_plane_stride ? p->out_plane_stride : 3 * W * H;
             float* b = out + z * ps + (y * W + x) * 3;

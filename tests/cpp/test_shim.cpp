@@ -98,6 +98,46 @@ static int test_split() {
     return 0;
 }
 
+// tests/resize/test_resize_x_split.cu:51,72-84: one crop -> resize -> alpha -> sub -> div -> split(vector<GpuMat>)
+// (fk::SplitWrite), and the batch form split(array<vector<GpuMat>, N>); constant image so the answer is known.
+static int test_resize_x_split_write() {
+    cv::cuda::GpuMat d_input(480, 640, CV_8UC3, cv::Scalar(5, 5, 5));
+    const cv::Size up(64, 128);
+    const cv::Scalar sub(1, 4, 6), div(2, 8, 1);
+    const double alpha = 0.5;
+    cv::cuda::Stream st;
+    std::vector<cv::cuda::GpuMat> planes(3);
+    for (auto& m : planes) m = cv::cuda::GpuMat(up.height, up.width, CV_32FC1);
+    cvGS::executeOperations(st, cvGS::resize<CV_8UC3, cv::INTER_LINEAR>(d_input(cv::Rect(200, 200, 60, 120)), up),
+                            cvGS::multiply<CV_32FC3>(cv::Scalar(alpha, alpha, alpha)), cvGS::subtract<CV_32FC3>(sub),
+                            cvGS::divide<CV_32FC3>(div), cvGS::split<CV_32FC3>(planes));
+    constexpr int N = 3;
+    std::array<cv::cuda::GpuMat, N> crops;
+    std::array<std::vector<cv::cuda::GpuMat>, N> outs;
+    for (int i = 0; i < N; ++i) {
+        crops[i] = d_input(cv::Rect(i, i, 60, 120));
+        outs[i].resize(3);
+        for (auto& m : outs[i]) m = cv::cuda::GpuMat(up.height, up.width, CV_32FC1);
+    }
+    cvGS::executeOperations(st, cvGS::resize<CV_8UC3, cv::INTER_LINEAR, N, cvGS::IGNORE_AR>(crops, up, N),
+                            cvGS::multiply<CV_32FC3>(cv::Scalar(alpha, alpha, alpha)), cvGS::subtract<CV_32FC3>(sub),
+                            cvGS::divide<CV_32FC3>(div), cvGS::split<CV_32FC3, N>(outs));
+    st.waitForCompletion();
+    auto check = [&](const std::vector<cv::cuda::GpuMat>& v) {
+        for (int c = 0; c < 3; ++c) {
+            std::vector<float> h(static_cast<size_t>(up.width) * up.height);
+            v[c].download(h.data(), up.width * sizeof(float));
+            const float want = static_cast<float>((5.0 * alpha - sub[c]) / div[c]);
+            for (float x : h)
+                if (std::fabs(x - want) > 1e-4f) return 1;
+        }
+        return 0;
+    };
+    REQUIRE(check(planes) == 0);
+    for (int i = 0; i < N; ++i) REQUIRE(check(outs[i]) == 0);
+    return 0;
+}
+
 static int test_random_vs_oracle() {
     constexpr int BATCH = 8, W = 640, H = 480;
     std::mt19937 rng(7);
@@ -163,6 +203,7 @@ int main() {
     failed += test_circular_tensor<fk::CircularTensorOrder::OldestFirst, fk::ColorPlanes::Standard>();
     failed += test_circular_tensor<fk::CircularTensorOrder::OldestFirst, fk::ColorPlanes::Transposed>();
     failed += test_split();
+    failed += test_resize_x_split_write();
     failed += test_random_vs_oracle();
     failed += test_error_convention();
     std::printf(failed ? "test_shim: %d FAILED\n" : "test_shim: all passed\n", failed);

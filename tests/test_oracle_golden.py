@@ -143,6 +143,25 @@ def test_oracle_round_u8_and_layouts():
     util.assert_bit_equal(nhwc, np.moveaxis(want, 1, -1), "NHWC")
 
 
+def test_oracle_split_write_equals_tensor_split():
+    """fk::SplitWrite (one image per crop and channel, own pitch) holds the same values as TensorSplit."""
+    import ctypes as C
+    w = util.workload_c2(seed=8, n=4, frame=(640, 600), pitch=1920)
+    W, H = w.dsize
+    ref = util.run_oracle(w.image, w.rects, w.dsize, w.ops)
+    bufs = [[np.full((H, W + 5 * c), np.nan, dtype=np.float32) for c in range(3)] for _ in w.rects]
+    arr = (_abi.Plane * 12)()
+    for z in range(4):
+        for c in range(3):
+            arr[3 * z + c].data, arr[3 * z + c].pitch_bytes = bufs[z][c].ctypes.data, bufs[z][c].strides[0]
+    p = util.make_pipeline(w.dsize, w.ops, layout=_abi.OUT_PLANES, out_ptr=C.addressof(arr))
+    assert util.oracle_lib().oracle_preproc(util.host_crops(w.image, w.rects), 4, 4, C.byref(p), 0) == 0
+    for z in range(4):
+        for c in range(3):
+            util.assert_bit_equal(bufs[z][c][:, :W], ref[z, c], f"plane {z} channel {c}")
+            assert np.isnan(bufs[z][c][:, W:]).all()
+
+
 def test_post_resize_stages_match_opencv_cpu():
     """BASELINE config 1, read per SURVEY F3: OpenCV-CPU is an exact oracle for convertTo / subtract /
     divide / split, not for the resize stage.  Identity-size 'resize' isolates those stages."""
