@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libcvgs_b200.so")
 MAX_OPS = 8
 
 # enums (include/cvgs_b200.h)
-CVGS_8UC3, CVGS_32FC3 = 16, 21
+CVGS_8UC3, CVGS_16UC3, CVGS_16SC3, CVGS_32FC3 = 16, 18, 19, 21
 PRESERVE_AR, IGNORE_AR, PRESERVE_AR_RN_EVEN, PRESERVE_AR_LEFT = 0, 1, 2, 3
 OP_MUL, OP_SUB, OP_DIV, OP_ADD, OP_REORDER = 1, 2, 3, 4, 5
 FP_REFERENCE_FUSED, FP_SEPARATE = 0, 1

@@ -25,6 +25,8 @@ COLOR_BGR2RGB = 4
 COLOR_RGB2BGR = 4
 INTER_LINEAR = 1
 CV_8UC3 = _abi.CVGS_8UC3
+CV_16UC3 = _abi.CVGS_16UC3
+CV_16SC3 = _abi.CVGS_16SC3
 CV_32FC3 = _abi.CVGS_32FC3
 
 
@@ -72,6 +74,7 @@ class _Resize:
     used: int
     background: Tuple[float, float, float]
     aspect: int
+    src_type: int = _abi.CVGS_8UC3
 
 
 @dataclass
@@ -91,12 +94,12 @@ class _Write:
 
 
 def resize(crops: Sequence[GpuMat], dsize: Tuple[int, int], usedPlanes: Optional[int] = None,
-           backgroundValue=(0.0, 0.0, 0.0), aspect: int = IGNORE_AR) -> _Resize:
+           backgroundValue=(0.0, 0.0, 0.0), aspect: int = IGNORE_AR, src_type: int = _abi.CVGS_8UC3) -> _Resize:
     """cvGS::resize<CV_8UC3, INTER_LINEAR, N, AR>(array<GpuMat,N>, Size, usedPlanes, bg)
     (reference include/cvGPUSpeedup.cuh:218-245)."""
     crops = list(crops)
     return _Resize(crops, (int(dsize[0]), int(dsize[1])), len(crops) if usedPlanes is None else int(usedPlanes),
-                   _scalar3(backgroundValue), int(aspect))
+                   _scalar3(backgroundValue), int(aspect), int(src_type))
 
 
 def multiply(s) -> _Op:   # cvGS::multiply<CV_32FC3>(Scalar) :131
@@ -183,9 +186,9 @@ def _flatten(ops):
 
 def build_pipeline(dsize, ops: Sequence[_Op], background=(0, 0, 0), aspect=IGNORE_AR,
                    fp_contract=FP_REFERENCE_FUSED, interp_mode=INTERP_FLOAT, out_ptr=0, layout=OUT_NCHW,
-                   plane_stride=0) -> _abi.Pipeline:
+                   plane_stride=0, src_type=_abi.CVGS_8UC3) -> _abi.Pipeline:
     p = _abi.Pipeline()
-    p.src_type = _abi.CVGS_8UC3
+    p.src_type = int(src_type)
     p.dst_width, p.dst_height = int(dsize[0]), int(dsize[1])
     p.aspect_mode, p.interp_mode, p.fp_contract = int(aspect), int(interp_mode), int(fp_contract)
     bg = _scalar3(background)
@@ -221,7 +224,7 @@ def executeOperations(stream, *iops, fp_contract: int = FP_REFERENCE_FUSED, inte
     if any(not isinstance(o, _Op) for o in mid):
         raise CvgsError("only multiply/subtract/divide/add/convertTo/cvtColor may sit between read and write")
     p = build_pipeline(rs.dsize, mid, rs.background, rs.aspect, fp_contract, interp_mode, wr.out_ptr, wr.layout,
-                       wr.plane_stride)
+                       wr.plane_stride, rs.src_type)
     crops = make_crops(rs.crops[:rs.used])
     parents = (_abi.Parent * max(1, rs.used))()
     for i, m in enumerate(rs.crops[:rs.used]):

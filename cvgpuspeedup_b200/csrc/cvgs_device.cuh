@@ -41,7 +41,7 @@ struct DevOp {
 };
 struct DevProgram {
     int32_t n_ops;
-    int32_t round_u8;     // CVGS_INTERP_ROUND_U8
+    int32_t round_u8;     // RoundKind: CVGS_INTERP_ROUND_U8 for the source depth of the launch
     int32_t dst_chan[3];  // source channel r is written to output channel dst_chan[r]
     DevOp ops[8];
 };
@@ -64,6 +64,7 @@ struct PreprocParams {
     int32_t n_planes, used;
     int32_t W, H;          // destination size
     int32_t band_test;     // 1 for the aspect-ratio preserving modes
+    int32_t src_type;      // CVGS_8UC3 / CVGS_16UC3 / CVGS_16SC3
     float bg[3];           // background / default value (source channel order)
     DevProgram prog;
     OutDesc out;
@@ -114,6 +115,20 @@ __device__ __forceinline__ float round_sat_u8(float v) {
     const unsigned u = __float2uint_rn(v);
     return (float)(u > 255u ? 255u : u);
 }
+// DevProgram::round_u8 codes: the interpolated value is rounded and saturated to the range of the source depth
+enum RoundKind : int32_t { ROUND_NONE = 0, ROUND_U8 = 1, ROUND_U16 = 2, ROUND_S16 = 3 };
+// SaturateCast<float, ushort> (saturate.cuh:267-298) / <float, short> (:358-378) then back to float.
+__device__ __forceinline__ float round_sat_kind(float v, int kind) {
+    if (kind == ROUND_U16) {
+        const unsigned u = __float2uint_rn(v);
+        return (float)(u > 65535u ? 65535u : u);
+    }
+    if (kind == ROUND_S16) {
+        const int i = __float2int_rn(v);
+        return (float)(i > 32767 ? 32767 : (i < -32768 ? -32768 : i));
+    }
+    return round_sat_u8(v);
+}
 
 // Apply the normalised chain to N values laid out as v[pixel][channel].
 template <int NPIX>
@@ -122,7 +137,7 @@ __device__ __forceinline__ void apply_program(const DevProgram& prog, float (&v)
 #pragma unroll
         for (int p = 0; p < NPIX; ++p)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[p][c] = round_sat_u8(v[p][c]);
+            for (int c = 0; c < 3; ++c) v[p][c] = round_sat_kind(v[p][c], prog.round_u8);
     }
     for (int i = 0; i < prog.n_ops; ++i) {
         const DevOp& op = prog.ops[i];

@@ -2,6 +2,7 @@
 // bilinear taps are fetched straight from global memory with aligned 32-bit loads.
 // Used by preproc_direct_kernel and by the CircularTensor update kernel.
 #pragma once
+#include "../../include/cvgs_b200.h"
 #include "cvgs_device.cuh"
 
 namespace cvgs {
@@ -34,11 +35,41 @@ __device__ __forceinline__ void fill_background(const PreprocParams& P, float (&
 // Resize::exec + Interpolate::exec for output pixels (x0..x0+3, y) of crop C (reference
 // resize.cuh:70-82,178-189, interpolation.cuh:57-92).  Values outside the aspect-ratio band are
 // the background.  The op chain is NOT applied here.
+// 16-bit sources (CV_16UC3 / CV_16SC3): the same arithmetic on ushort3 / short3 taps (the reference promotes them to
+// float exactly, core/utils/cuda_vector_utils.h), one 16-bit load per tap channel.
+template <typename T16>
+__device__ __forceinline__ void gather_quad16(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
+                                              float (&v)[4][3]) {
+    const AxisTap ty_ = axis_tap(y - C.by1, C.fy);
+    const int y2r = min(ty_.i1 + 1, C.h - 1);
+    const T16* r0 = reinterpret_cast<const T16*>(C.data + (size_t)ty_.i1 * (size_t)C.pitch);
+    const T16* r1 = reinterpret_cast<const T16*>(C.data + (size_t)y2r * (size_t)C.pitch);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int x = x0 + p;
+        if (p < nvalid && x >= C.bx1 && x <= C.bx2) {
+            const AxisTap tx_ = axis_tap(x - C.bx1, C.fx);
+            const int x1 = tx_.i1, x2r = min(tx_.i1 + 1, C.w - 1);
+            const float w00 = __fmul_rn(tx_.w0, ty_.w0), w10 = __fmul_rn(tx_.w1, ty_.w0);
+            const float w01 = __fmul_rn(tx_.w0, ty_.w1), w11 = __fmul_rn(tx_.w1, ty_.w1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                v[p][c] = bilerp((float)__ldg(r0 + 3 * x1 + c), (float)__ldg(r0 + 3 * x2r + c), (float)__ldg(r1 + 3 * x1 + c),
+                                 (float)__ldg(r1 + 3 * x2r + c), w00, w10, w01, w11);
+        }
+    }
+}
+
 __device__ __forceinline__ void gather_quad(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
                                             float (&v)[4][3]) {
     fill_background(P, v);
     const bool row_in = !P.band_test || (y >= C.by1 && y <= C.by2);
     if (!row_in) return;
+    if (P.src_type != CVGS_8UC3) {
+        if (P.src_type == CVGS_16UC3) gather_quad16<unsigned short>(P, C, y, x0, nvalid, v);
+        else gather_quad16<short>(P, C, y, x0, nvalid, v);
+        return;
+    }
     const AxisTap ty_ = axis_tap(y - C.by1, C.fy);
     const int y2r = min(ty_.i1 + 1, C.h - 1);
     const uint8_t* r0 = C.data + (size_t)ty_.i1 * (size_t)C.pitch;

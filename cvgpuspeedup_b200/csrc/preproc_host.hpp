@@ -58,7 +58,10 @@ inline void resize_geometry(int sw, int sh, int dw, int dh, int aspect, DevCrop&
 inline int build_program(const cvgs_pipeline_t& p, DevProgram& prog) {
     std::memset(&prog, 0, sizeof prog);
     if (p.n_ops < 0 || p.n_ops > CVGS_MAX_OPS) return fail(CVGS_ERR_INVALID_VALUE, "n_ops out of range");
-    prog.round_u8 = p.interp_mode == CVGS_INTERP_ROUND_U8;
+    prog.round_u8 = p.interp_mode != CVGS_INTERP_ROUND_U8 ? ROUND_NONE
+                    : p.src_type == CVGS_16UC3            ? ROUND_U16
+                    : p.src_type == CVGS_16SC3            ? ROUND_S16
+                                                          : ROUND_U8;
     int cur[3] = {0, 1, 2};  // position c currently holds source channel cur[c]
     const bool fuse = p.fp_contract == CVGS_FP_REFERENCE_FUSED;
     int n = 0;
@@ -101,8 +104,8 @@ inline int build_program(const cvgs_pipeline_t& p, DevProgram& prog) {
 
 inline int validate_pipeline(const cvgs_pipeline_t* p) {
     if (!p) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
-    if (p->src_type != CVGS_8UC3)
-        return fail(CVGS_ERR_NOT_SUPPORTED, "only CV_8UC3 sources are supported by this build");
+    if (p->src_type != CVGS_8UC3 && p->src_type != CVGS_16UC3 && p->src_type != CVGS_16SC3)
+        return fail(CVGS_ERR_NOT_SUPPORTED, "only CV_8UC3, CV_16UC3 and CV_16SC3 sources are supported by this build");
     if (p->dst_width <= 0 || p->dst_height <= 0 || p->dst_width > (1 << 20) || p->dst_height > (1 << 20))
         return fail(CVGS_ERR_INVALID_VALUE, "destination size out of range");
     if (p->aspect_mode < 0 || p->aspect_mode > 3) return fail(CVGS_ERR_INVALID_VALUE, "bad aspect_mode");
@@ -121,6 +124,7 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
     P.W = p.dst_width;
     P.H = p.dst_height;
     P.band_test = p.aspect_mode != CVGS_IGNORE_AR;
+    P.src_type = p.src_type;
     for (int c = 0; c < 3; ++c) P.bg[c] = p.background[c];
     if (int rc = build_program(p, P.prog)) return rc;
     const long long plane = static_cast<long long>(p.dst_width) * p.dst_height;
@@ -158,8 +162,11 @@ inline int fill_crop(const cvgs_crop_t& c, const cvgs_pipeline_t& p, int idx, De
     if (!c.data) return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": data is NULL");
     if (c.width <= 0 || c.height <= 0 || c.width > (1 << 22) || c.height > (1 << 22))
         return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": size out of range");
-    if (c.pitch < 3 * c.width && c.height > 1)
+    const int px_bytes = p.src_type == CVGS_8UC3 ? 3 : 6;
+    if (c.pitch < px_bytes * c.width && c.height > 1)
         return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": pitch smaller than a row");
+    if (px_bytes == 6 && ((reinterpret_cast<uintptr_t>(c.data) | static_cast<uintptr_t>(c.pitch)) & 1))
+        return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": 16-bit pixels must be 2-byte aligned");
     d.data = static_cast<const uint8_t*>(c.data);
     d.w = c.width;
     d.h = c.height;

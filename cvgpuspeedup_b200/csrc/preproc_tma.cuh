@@ -688,6 +688,7 @@ inline int rb_class(int rb) {
 inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int n_planes, int sm_count, bool image_mode,
                      TmaGeom& G) {
     if (!encode_tiled_fn()) return false;
+    if (P.src_type != CVGS_8UC3) return false;  // the byte-level tap extraction is written for 3-byte pixels
     float fx_max = 0.f;
     for (int i = 0; i < used; ++i) {
         const DevCrop& c = crops[i];

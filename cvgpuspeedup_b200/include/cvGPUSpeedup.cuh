@@ -145,7 +145,8 @@ inline int& interpMode() {
 template <int T, int INTER_F, int NPtr, AspectRatio AR_ = IGNORE_AR>
 inline detail::ReadBatch resize(const std::array<cv::cuda::GpuMat, NPtr>& input, const cv::Size& dsize, const int& usedPlanes,
                                 const cv::Scalar& backgroundValue = cv::Scalar()) {
-    static_assert(T == CV_8UC3, "cvGS (B200 build): only CV_8UC3 sources are on the hot path in this build");
+    static_assert(T == CV_8UC3 || T == CV_16UC3 || T == CV_16SC3,
+                  "cvGS (B200 build): CV_8UC3, CV_16UC3 and CV_16SC3 sources are on the hot path in this build");
     static_assert(INTER_F == cv::INTER_LINEAR, "cvGS (B200 build): only INTER_LINEAR is implemented (as in the reference)");
     detail::ReadBatch r;
     r.n_planes = NPtr;
@@ -285,8 +286,8 @@ inline void executeOperations(const cv::cuda::Stream& stream, const detail::Read
 template <int I, int O, int COLOR_PLANES, int BATCH, fk::CircularTensorOrder CT_ORDER,
           fk::ColorPlanes CP_MODE = fk::ColorPlanes::Standard>
 class CircularTensor {
-    static_assert(I == CV_8UC3 && CV_MAT_DEPTH(O) == CV_32F && COLOR_PLANES == 3,
-                  "cvGS (B200 build): CircularTensor<CV_8UC3, CV_32F, 3, ...> is the supported instantiation");
+    static_assert((I == CV_8UC3 || I == CV_16UC3 || I == CV_16SC3) && CV_MAT_DEPTH(O) == CV_32F && COLOR_PLANES == 3,
+                  "cvGS (B200 build): CircularTensor<CV_8UC3 | CV_16UC3 | CV_16SC3, CV_32F, 3, ...> are the supported instantiations");
 
 public:
     CircularTensor() = default;

@@ -45,6 +45,8 @@ typedef unsigned int uint;
 #define CV_MAT_CN(flags) ((((flags) >> CV_CN_SHIFT) & 511) + 1)
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_16UC3 CV_MAKETYPE(CV_16U, 3)
+#define CV_16SC3 CV_MAKETYPE(CV_16S, 3)
 #define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_32FC3 CV_MAKETYPE(CV_32F, 3)

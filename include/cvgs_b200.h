@@ -45,6 +45,8 @@ extern "C" {
 
 /* ---- pixel types: same numeric values as OpenCV's CV_MAKETYPE(depth, cn) ---- */
 #define CVGS_8UC3 16  /* CV_8UC3  */
+#define CVGS_16UC3 18 /* CV_16UC3: source only; taken by the direct-gather kernel (SaturateCast saturate.cuh:267-298) */
+#define CVGS_16SC3 19 /* CV_16SC3: source only; taken by the direct-gather kernel (saturate.cuh:358-378)             */
 #define CVGS_32FC3 21 /* CV_32FC3 */
 
 /* Aspect-ratio policy of the resize; same numbering as cvGS::AspectRatio
@@ -76,8 +78,9 @@ enum cvgs_fp_contract { CVGS_FP_REFERENCE_FUSED = 0, CVGS_FP_SEPARATE = 1 };
 
 /* Resize output handed to the op chain:
  *   CVGS_INTERP_FLOAT     interpolated value stays float (what fk::Interpolate returns).
- *   CVGS_INTERP_ROUND_U8  value is rounded (RN-even) and saturated to [0,255] first, i.e.
- *                         cv::cuda::resize on CV_8UC3 followed by convertTo(CV_32F). */
+ *   CVGS_INTERP_ROUND_U8  value is rounded (RN-even) and saturated to the range of the SOURCE depth first
+ *                         ([0,255], [0,65535] or [-32768,32767]), i.e. cv::cuda::resize on the integer image
+ *                         followed by convertTo(CV_32F). */
 enum cvgs_interp_mode { CVGS_INTERP_FLOAT = 0, CVGS_INTERP_ROUND_U8 = 1 };
 
 /* Output layouts (reference fkl/.../memory_operations.cuh:168-220, ptr_nd.cuh:53-77). */
@@ -120,7 +123,7 @@ typedef struct cvgs_op {
 /* Everything cvGS::executeOperations(stream, resize(...), ops..., split(...)) carries besides
  * the crops (reference include/cvGPUSpeedup.cuh:218-245 resize, :131-161 ops, :185-202 split). */
 typedef struct cvgs_pipeline {
-    int32_t src_type;    /* CVGS_8UC3                                              */
+    int32_t src_type;    /* CVGS_8UC3, CVGS_16UC3 or CVGS_16SC3                    */
     int32_t dst_width;   /* cv::Size dsize of cvGS::resize                         */
     int32_t dst_height;
     int32_t aspect_mode; /* enum cvgs_aspect_ratio                                 */

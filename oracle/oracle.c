@@ -92,11 +92,31 @@ static float round_sat_u8(float v) {
     const float r = nearbyintf(v);         /* default rounding mode = RN-even           */
     return r > 255.0f ? 255.0f : r;
 }
+/* SaturateCast<float, ushort> (saturate.cuh:267-298) and <float, short> (:358-378): round to nearest even, clamp. */
+static float round_sat_u16(float v) {
+    if (!(v > 0.0f)) return 0.0f;
+    const float r = nearbyintf(v);
+    return r > 65535.0f ? 65535.0f : r;
+}
+static float round_sat_s16(float v) {
+    if (v != v) return 0.0f;               /* cvt.rni.s32.f32 of NaN is 0 */
+    const float r = nearbyintf(v);
+    return r > 32767.0f ? 32767.0f : (r < -32768.0f ? -32768.0f : r);
+}
+static float round_sat_src(float v, int src_type) {
+    return src_type == CVGS_16UC3 ? round_sat_u16(v) : src_type == CVGS_16SC3 ? round_sat_s16(v) : round_sat_u8(v);
+}
+/* channel ch of pixel x of a source row, as the float the reference's uchar3/ushort3/short3 * float promotes it to */
+static float src_px(const uint8_t* row, int x, int ch, int src_type) {
+    if (src_type == CVGS_16UC3) return (float)((const uint16_t*)row)[3 * x + ch];
+    if (src_type == CVGS_16SC3) return (float)((const int16_t*)row)[3 * x + ch];
+    return (float)row[3 * x + ch];
+}
 
 /* One output pixel of Resize::exec + Interpolate<INTER_LINEAR>::exec
  * (resize.cuh:70-82,178-189; interpolation.cuh:57-92; PerThreadRead ptr_nd.cuh:41-45).
  * Rounding sequence = what nvcc emits for the reference kernel (see file header). */
-static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspect_mode,
+static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspect_mode, int src_type,
                          int x, int y, const float* bg, float out[3]) {
     if (aspect_mode != CVGS_IGNORE_AR) {
         if (!(x >= g->x1 && x <= g->x2 && y >= g->y1 && y <= g->y2)) {
@@ -119,8 +139,8 @@ static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspec
     const uint8_t* r0 = base + (size_t)y1 * (size_t)c->pitch;
     const uint8_t* r1 = base + (size_t)y2r * (size_t)c->pitch;
     for (int ch = 0; ch < 3; ++ch) {
-        const float p00 = (float)r0[3 * x1 + ch], p10 = (float)r0[3 * x2r + ch];
-        const float p01 = (float)r1[3 * x1 + ch], p11 = (float)r1[3 * x2r + ch];
+        const float p00 = src_px(r0, x1, ch, src_type), p10 = src_px(r0, x2r, ch, src_type);
+        const float p01 = src_px(r1, x1, ch, src_type), p11 = src_px(r1, x2r, ch, src_type);
         float t = p10 * w10;
         t = fmaf(p00, w00, t);
         t = fmaf(p01, w01, t);
@@ -133,7 +153,7 @@ static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspec
  * Mul/Sub/Div/Add arithmetic.cuh:43-68; VectorReorder cuda_vector.cuh:45-54. */
 static void apply_chain(const cvgs_pipeline_t* p, float v[3]) {
     if (p->interp_mode == CVGS_INTERP_ROUND_U8)
-        for (int c = 0; c < 3; ++c) v[c] = round_sat_u8(v[c]);
+        for (int c = 0; c < 3; ++c) v[c] = round_sat_src(v[c], p->src_type);
     for (int i = 0; i < p->n_ops; ++i) {
         const cvgs_op_t* op = &p->ops[i];
         /* nvcc contracts (x*m) -/+ s of the inlined chain into one FMA; a channel reorder in
@@ -211,7 +231,8 @@ static void store_pixel(const cvgs_pipeline_t* p, int n_planes, int z, int y, in
  * All pointers are HOST pointers here.  nthreads <= 0 -> all cores. Returns 0 / 1 (bad args). */
 int oracle_preproc(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_pipeline_t* p,
                    int nthreads) {
-    if (!crops || !p || !p->out || n_planes <= 0 || used < 0 || p->src_type != CVGS_8UC3 ||
+    if (!crops || !p || !p->out || n_planes <= 0 || used < 0 ||
+        (p->src_type != CVGS_8UC3 && p->src_type != CVGS_16UC3 && p->src_type != CVGS_16SC3) ||
         p->dst_width <= 0 || p->dst_height <= 0 || p->n_ops < 0 || p->n_ops > CVGS_MAX_OPS)
         return 1;
     if (used > n_planes) used = n_planes;
@@ -232,7 +253,7 @@ int oracle_preproc(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_
             if (z >= used) {
                 v[0] = p->background[0]; v[1] = p->background[1]; v[2] = p->background[2];
             } else {
-                resize_pixel(&crops[z], &geoms[z], p->aspect_mode, x, y, p->background, v);
+                resize_pixel(&crops[z], &geoms[z], p->aspect_mode, p->src_type, x, y, p->background, v);
             }
             apply_chain(p, v);
             store_pixel(p, n_planes, z, y, x, v);

@@ -36,16 +36,16 @@ thread_local std::string g_err;
 
 struct CropIn { const void* data; int w, h, pitch; };
 
-template <int BATCH, fk::AspectRatio AR, bool SWAP>
+template <typename PixelT, int BATCH, fk::AspectRatio AR, bool SWAP>
 int run_chain(const void* const* ptrs, const int* ws, const int* hs, const int* pitches,
               int used, int dst_w, int dst_h, const float* bg,
               const float* mul, const float* sub, const float* div,
               float* out, cudaStream_t stream) {
-    using PixelReadOp = fk::PerThreadRead<fk::_2D, uchar3>;
-    std::array<fk::RawPtr<fk::_2D, uchar3>, BATCH> crops{};
+    using PixelReadOp = fk::PerThreadRead<fk::_2D, PixelT>;
+    std::array<fk::RawPtr<fk::_2D, PixelT>, BATCH> crops{};
     for (int i = 0; i < BATCH; ++i) {
         const int j = i < used ? i : 0;  // unused slots still need a valid descriptor
-        crops[i] = fk::RawPtr<fk::_2D, uchar3>{ (uchar3*)ptrs[j],
+        crops[i] = fk::RawPtr<fk::_2D, PixelT>{ (PixelT*)ptrs[j],
             { (uint)ws[j], (uint)hs[j], (uint)pitches[j] } };
     }
     const fk::Size dsize{ dst_w, dst_h };
@@ -78,13 +78,13 @@ int run_chain(const void* const* ptrs, const int* ws, const int* hs, const int* 
     return 0;
 }
 
-template <int BATCH>
+template <typename PixelT, int BATCH>
 int dispatch(const void* const* ptrs, const int* ws, const int* hs, const int* pitches,
              int used, int dst_w, int dst_h, int ar, const float* bg, int swap,
              const float* mul, const float* sub, const float* div, float* out, cudaStream_t s) {
 #define FKREF_CASE(ARV, SW) \
     if (ar == (int)ARV && swap == SW) \
-        return run_chain<BATCH, ARV, SW != 0>(ptrs, ws, hs, pitches, used, dst_w, dst_h, bg, mul, sub, div, out, s);
+        return run_chain<PixelT, BATCH, ARV, SW != 0>(ptrs, ws, hs, pitches, used, dst_w, dst_h, bg, mul, sub, div, out, s);
     FKREF_CASE(fk::IGNORE_AR, 0) FKREF_CASE(fk::IGNORE_AR, 1)
 #ifdef FKREF_ALL_AR
     FKREF_CASE(fk::PRESERVE_AR, 0) FKREF_CASE(fk::PRESERVE_AR, 1)
@@ -112,8 +112,8 @@ int FKREF_CAT(fkref_preproc_, FKREF_BATCH)(const void* const* ptrs, const int* w
                   int used, int dst_w, int dst_h, int aspect_mode, const float* bg, int swap_rb,
                   const float* mul, const float* sub, const float* div, float* out, void* stream) {
     try {
-        return dispatch<FKREF_BATCH>(ptrs, ws, hs, pitches, used, dst_w, dst_h, aspect_mode, bg, swap_rb,
-                                     mul, sub, div, out, (cudaStream_t)stream);
+        return dispatch<uchar3, FKREF_BATCH>(ptrs, ws, hs, pitches, used, dst_w, dst_h, aspect_mode, bg, swap_rb,
+                                             mul, sub, div, out, (cudaStream_t)stream);
     } catch (const std::exception& e) {
         g_err = e.what();
         return -1;
@@ -130,7 +130,7 @@ int FKREF_CAT(fkref_preproc_sequence_, FKREF_BATCH)(const void* const* const* pt
     try {
         for (int i = 0; i < steps; ++i) {
             const int s = i % n_sets;
-            if (int rc = dispatch<FKREF_BATCH>(ptrs[s], ws[s], hs[s], pitches[s], used, dst_w, dst_h, aspect_mode, bg,
+            if (int rc = dispatch<uchar3, FKREF_BATCH>(ptrs[s], ws[s], hs[s], pitches[s], used, dst_w, dst_h, aspect_mode, bg,
                                                swap_rb, mul, sub, div, outs[s], (cudaStream_t)stream))
                 return rc;
         }
@@ -140,6 +140,27 @@ int FKREF_CAT(fkref_preproc_sequence_, FKREF_BATCH)(const void* const* const* pt
         return -1;
     }
 }
+
+#ifdef FKREF_16BIT
+// The same chain on CV_16UC3 (pixel_type 18, ushort3) and CV_16SC3 (19, short3) sources.
+int FKREF_CAT(fkref_preproc16_, FKREF_BATCH)(int pixel_type, const void* const* ptrs, const int* ws, const int* hs,
+                  const int* pitches, int used, int dst_w, int dst_h, int aspect_mode, const float* bg, int swap_rb,
+                  const float* mul, const float* sub, const float* div, float* out, void* stream) {
+    try {
+        if (pixel_type == 18)
+            return dispatch<ushort3, FKREF_BATCH>(ptrs, ws, hs, pitches, used, dst_w, dst_h, aspect_mode, bg, swap_rb,
+                                                  mul, sub, div, out, (cudaStream_t)stream);
+        if (pixel_type == 19)
+            return dispatch<short3, FKREF_BATCH>(ptrs, ws, hs, pitches, used, dst_w, dst_h, aspect_mode, bg, swap_rb,
+                                                 mul, sub, div, out, (cudaStream_t)stream);
+        g_err = "fkref: pixel type must be 18 (CV_16UC3) or 19 (CV_16SC3)";
+        return -1;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+#endif
 
 const char* FKREF_CAT(fkref_last_error_, FKREF_BATCH)(void) { return g_err.c_str(); }
 

@@ -162,6 +162,35 @@ def test_oracle_split_write_equals_tensor_split():
             assert np.isnan(bufs[z][c][:, W:]).all()
 
 
+@pytest.mark.parametrize("src_type,dtype", [(_abi.CVGS_16UC3, np.uint16), (_abi.CVGS_16SC3, np.int16)])
+def test_oracle_16bit_sources_equal_numpy(src_type, dtype):
+    """ushort3 / short3 sources: same index math and rounding order on exactly converted taps (independent numpy
+    restatement of interpolation.cuh:57-92 with float32 arithmetic and explicit fma emulation in float64)."""
+    rng = np.random.default_rng(12)
+    w, h, W, H = 37, 29, 16, 24
+    img = rng.integers(0, 256, size=(h, 6 * w + 10), dtype=np.uint8)
+    px = img[:, :6 * w].copy().view(dtype).reshape(h, w, 3).astype(np.float32)
+    out = util.run_oracle(img, [(0, 0, w, h)], (W, H), [], src_type=src_type)[0]
+    fx, fy = np.float32(1.0 / (W / w)), np.float32(1.0 / (H / h))
+
+    def fma(a, b, c):  # float32 fma through float64: exact product (24x24 bits), one rounding of the sum
+        return np.float32(np.float64(a) * np.float64(b) + np.float64(c))
+    for y in range(H):
+        for x in range(W):
+            sx, sy = np.float32(x) * fx, np.float32(y) * fy
+            x1, y1 = int(np.floor(sx)), int(np.floor(sy))
+            x2r, y2r = min(x1 + 1, w - 1), min(y1 + 1, h - 1)
+            wx1, wx0 = sx - np.float32(x1), np.float32(x1 + 1) - sx
+            wy1, wy0 = sy - np.float32(y1), np.float32(y1 + 1) - sy
+            w00, w10, w01, w11 = wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1
+            for c in range(3):
+                t = px[y1, x2r, c] * w10
+                t = fma(px[y1, x1, c], w00, t)
+                t = fma(px[y2r, x1, c], w01, t)
+                t = fma(px[y2r, x2r, c], w11, t)
+                assert out[c, y, x] == t, (x, y, c)
+
+
 def test_post_resize_stages_match_opencv_cpu():
     """BASELINE config 1, read per SURVEY F3: OpenCV-CPU is an exact oracle for convertTo / subtract /
     divide / split, not for the resize stage.  Identity-size 'resize' isolates those stages."""

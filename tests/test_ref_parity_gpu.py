@@ -42,6 +42,26 @@ def test_reference_kernel_equals_ours_and_oracle(swap, aspect):
     util.assert_bit_equal(orc, ref, "oracle vs reference kernel")
 
 
+@pytest.mark.parametrize("src_type", [_abi.CVGS_16UC3, _abi.CVGS_16SC3])
+@pytest.mark.parametrize("aspect", [_abi.IGNORE_AR, _abi.PRESERVE_AR])
+def test_reference_kernel_16bit_sources(src_type, aspect):
+    """ushort3 / short3 instantiations of the reference's Resize (its test matrix, test_batchresize_x_split3D.cu:427-432)."""
+    _need(16)
+    rng = np.random.default_rng(7 + src_type)
+    img = rng.integers(0, 256, size=(240, 1936), dtype=np.uint8)  # 320 x 240 16-bit pixels, full value range
+    rects = [(0, 0, 320, 240), (5, 7, 24, 48), (100, 3, 199, 33), (17, 150, 7, 5), (300, 0, 20, 240), (1, 1, 64, 128),
+             (319, 239, 1, 1), (20, 20, 60, 120)]
+    bg = (128.0, 3.5, 250.0)
+    mul = (1 / 257.0,) * 3
+    ref = gpu_util.run_fkref(img, rects, (64, 128), 1, mul, SUB, DIV, aspect=aspect, bg=bg, batch=16, used=8, src_type=src_type)
+    ours = gpu_util.run_cvgs(img, rects, (64, 128), _ops(1, mul=mul), n_planes=16, used=8, aspect=aspect, background=bg,
+                             src_type=src_type)
+    util.assert_bit_equal(ours, ref, "16-bit source: ours vs reference kernel")
+    orc = util.run_oracle(img, rects, (64, 128), _ops(1, mul=mul), n_planes=16, used=8, aspect=aspect, background=bg,
+                          src_type=src_type)
+    util.assert_bit_equal(orc, ref, "16-bit source: oracle vs reference kernel")
+
+
 def test_reference_kernel_c2_fifty_crops():
     """BASELINE config 2 against the reference instantiated with BATCH=50."""
     _need(50)

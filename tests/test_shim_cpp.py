@@ -35,7 +35,7 @@ def test_shim_rejects_chains_outside_the_hot_path(tmp_path):
         }}"""))
     res = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-DCVGS_FORCE_OPENCV_DOUBLE", "-I/usr/local/cuda/include",
                           "-x", "c++", str(src)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    assert res.returncode != 0 and "only CV_8UC3 sources" in res.stdout
+    assert res.returncode != 0 and "CV_8UC3, CV_16UC3 and CV_16SC3 sources" in res.stdout
 
 
 @pytest.mark.gpu

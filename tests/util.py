@@ -134,9 +134,10 @@ _KIND = {"mul": _abi.OP_MUL, "sub": _abi.OP_SUB, "div": _abi.OP_DIV, "add": _abi
 
 
 def make_pipeline(dsize, ops, aspect=_abi.IGNORE_AR, background=(0, 0, 0), fp_contract=_abi.FP_REFERENCE_FUSED,
-                  interp_mode=_abi.INTERP_FLOAT, layout=_abi.OUT_NCHW, out_ptr=0, plane_stride=0) -> _abi.Pipeline:
+                  interp_mode=_abi.INTERP_FLOAT, layout=_abi.OUT_NCHW, out_ptr=0, plane_stride=0,
+                  src_type=_abi.CVGS_8UC3) -> _abi.Pipeline:
     p = _abi.Pipeline()
-    p.src_type = _abi.CVGS_8UC3
+    p.src_type = src_type
     p.dst_width, p.dst_height = dsize
     p.aspect_mode, p.interp_mode, p.fp_contract = aspect, interp_mode, fp_contract
     for c in range(3):
@@ -166,13 +167,14 @@ def out_shape(n_planes, dsize, layout, plane_stride=0):
     return (n_planes, H, W, 3)
 
 
-def host_crops(image: np.ndarray, rects: Sequence[Rect], base_ptr: int | None = None):
-    """Crop descriptors pointing into `image` (host) or into a device copy at base_ptr with the same pitch."""
+def host_crops(image: np.ndarray, rects: Sequence[Rect], base_ptr: int | None = None, px_bytes: int = 3):
+    """Crop descriptors pointing into `image` (host) or into a device copy at base_ptr with the same pitch.
+    px_bytes = 3 for CV_8UC3, 6 for the 16-bit sources."""
     pitch = image.shape[1]
     base = image.ctypes.data if base_ptr is None else base_ptr
     arr = (_abi.Crop * max(1, len(rects)))()
     for i, (x, y, w, h) in enumerate(rects):
-        arr[i].data, arr[i].width, arr[i].height, arr[i].pitch, arr[i].reserved = base + y * pitch + 3 * x, w, h, pitch, 0
+        arr[i].data, arr[i].width, arr[i].height, arr[i].pitch, arr[i].reserved = base + y * pitch + px_bytes * x, w, h, pitch, 0
     return arr
 
 
@@ -193,7 +195,7 @@ def run_oracle(image, rects, dsize, ops, n_planes=None, used=None, nthreads=0, f
     layout = pipe_kw.get("layout", _abi.OUT_NCHW)
     out = np.full(out_shape(n_planes, dsize, layout, pipe_kw.get("plane_stride", 0)), fill, dtype=np.float32)
     p = make_pipeline(dsize, ops, out_ptr=out.ctypes.data, **pipe_kw)
-    crops = host_crops(image, rects[:used])
+    crops = host_crops(image, rects[:used], px_bytes=3 if pipe_kw.get("src_type", _abi.CVGS_8UC3) == _abi.CVGS_8UC3 else 6)
     rc = lib.oracle_preproc(crops, n_planes, used, C.byref(p), nthreads)
     assert rc == 0, "oracle rejected the arguments"
     return out
