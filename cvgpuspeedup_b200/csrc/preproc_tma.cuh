@@ -498,7 +498,9 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         const int np = (min(TW, W - tx0) + 31) >> 5;
         int32_t off[kMaxNP], shl[kMaxNP], shr[kMaxNP];
         float wxa[kMaxNP], wxb[kMaxNP];
-        bool edge[kMaxNP], img[kMaxNP], inw[kMaxNP];  // right tap clamped / column receives image data / column < W
+        // bit p: right tap of column p clamped / column p receives image data / column p < W.  One register each,
+        // tested with one LOP3 per column (separate flags were re-derived from scratch in front of every column)
+        uint32_t m_edge = 0, m_img = 0, m_in = 0;
         uint32_t rb = 0;                              // staged row bytes of this crop
         {
             const bool active = !GEN || z < P.used;
@@ -519,12 +521,13 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
 #pragma unroll
             for (int p = 0; p < kMaxNP; ++p) {
                 const int x = tx0 + lane + 32 * p;
-                inw[p] = x < W;
-                img[p] = inw[p] && x >= b.xa && x <= b.xe;
-                const AxisTap t = axis_tap((img[p] ? x : b.xa) - bx1, fx);
+                const bool in_p = x < W, img_p = in_p && x >= b.xa && x <= b.xe;
+                const AxisTap t = axis_tap((img_p ? x : b.xa) - bx1, fx);
                 wxa[p] = t.w0;
                 wxb[p] = t.w1;
-                edge[p] = t.i1 + 1 > wm1;
+                m_in |= (in_p ? 1u : 0u) << p;
+                m_img |= (img_p ? 1u : 0u) << p;
+                m_edge |= (t.i1 + 1 > wm1 ? 1u : 0u) << p;
                 const int o = 3 * t.i1 - b.origin;
                 off[p] = ((o + 3) >> 2) * 4;
                 shl[p] = (o & 3) ? (o & 3) * 8 : 32;
@@ -532,6 +535,8 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             }
         }
         // this lane's first column in rows 2*jp of the three channel planes of plane z
+        asm volatile("" : "+r"(m_edge), "+r"(m_img), "+r"(m_in));
+        (void)np;
         float* s0 = P.out.base + ((long long)z * P.out.z_stride + (long long)(tx0 + lane) * pxs + (long long)(2 * cc.jp) * row_step);
         float* s1 = s0 + oc1;
         float* s2 = s0 + oc2;
@@ -582,11 +587,11 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             asm volatile("" : "+r"(aA0), "+r"(aB0), "+r"(aA1), "+r"(aB1), "+f"(wy0.x), "+f"(wy0.y), "+f"(wy1.x), "+f"(wy1.y));
 #pragma unroll
             for (int p = 0; p < kMaxNP; ++p) {
-                if (p < np) {
+                if (m_in & (1u << p)) {  // lanes past the right border of the plane (and whole groups past the band) skip
                     float2 v[3];
                     if (!GEN || im0 || im1) {
-                        gather_pair(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p], edge[p], wxa[p],
-                                    wxb[p], wy0, wy1, v);
+                        gather_pair(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p],
+                                    (m_edge & (1u << p)) != 0, wxa[p], wxb[p], wy0, wy1, v);
                         if (CHAIN == CH_FMA_DIV) {
 #pragma unroll
                             for (int c = 0; c < 3; ++c) {
@@ -604,11 +609,11 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                     if (GEN) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            if (!(im0 && img[p])) v[c].x = vb[0][c];
-                            if (!(im1 && img[p])) v[c].y = vb[0][c];
+                            if (!(im0 && (m_img & (1u << p)))) v[c].x = vb[0][c];
+                            if (!(im1 && (m_img & (1u << p)))) v[c].y = vb[0][c];
                         }
                     }
-                    if (inw[p]) {
+                    {
                         const int q = 32 * p * pxs;
                         st_cs_f32(s0 + q, v[0].x);
                         st_cs_f32(s1 + q, v[1].x);
