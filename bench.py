@@ -536,6 +536,12 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int):
     if extra:
         extra["frac_of_peak"] = extra["achieved_gbs"] / peak
         line["extra"] = {"c3": extra}
+        try:
+            c4 = c4_extra(torch, util, stream)
+            c4["frac_of_peak"] = c4["achieved_gbs"] / peak
+            line["extra"]["c4"] = c4
+        except Exception as e:  # the extra lines never take the headline down with them
+            line["extra"]["c4"] = {"error": str(e)[:200]}
     if world == 1:
         cps, cores, done, dt = cpu_port_crops_per_s(frames, args.cpu_seconds, 10 ** 9)
         line["cpu_baseline"] = {"value": cps, "unit": "crops/s", "cores": cores, "kind": "port",
@@ -592,6 +598,37 @@ def c3_extra(lib, torch, _abi, util, stream, reps=20):
             "workload": "c3: 256 crops (224..896 px) from 3840x2160 -> 224x224 + BGR2RGB + mean/std + NCHW, one launch",
             "us_per_launch": us, "crops_per_s": 256 / (us * 1e-6), "algorithmic_bytes_per_launch": b_in + b_out,
             "bytes_in": b_in, "bytes_out": b_out, "achieved_gbs": gbs}
+
+
+def c4_extra(torch, util, stream, depth=16, reps=20):
+    """BASELINE configs[3]: CircularTensor depth 16 of 1920x1080 planes, 1080p CV_8UC3 frames (no resize), BGR2RGB +
+    mean/std on the new frame; one kernel per update shifts the other 15 planes and processes the new one."""
+    import cvgpuspeedup_b200 as cvGS
+    W, H = 1920, 1080
+    rng = np.random.default_rng(4)
+    frames = [torch.from_numpy(util.make_image(rng, W, H, pitch=6144)).cuda() for _ in range(4)]
+    mats = [cvGS.GpuMat(f.data_ptr(), W, H, 6144, owner=f) for f in frames]
+    ops = [cvGS.cvtColor(cvGS.COLOR_BGR2RGB), cvGS.multiply((1 / 255.0,) * 3), cvGS.subtract((0.485, 0.456, 0.406)),
+           cvGS.divide((0.229, 0.224, 0.225))]
+    ct = cvGS.CircularTensor(W, H, depth, cvGS.CT_NEWEST_FIRST, cvGS.CT_STANDARD)
+    try:
+        for i in range(depth + 2):
+            ct.update(stream, mats[i % 4], *ops)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(reps):
+            ct.update(stream, mats[i % 4], *ops)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+    finally:
+        ct.close()
+    plane = 12 * W * H
+    alg = 3 * W * H + (depth - 1) * plane + depth * plane
+    return {"workload": f"c4: CircularTensor depth {depth}, {W}x{H} planes, 1080p frames, one kernel per update",
+            "us_per_update": us, "updates_per_s": 1e6 / us, "algorithmic_bytes_per_update": alg,
+            "achieved_gbs": alg / (us * 1e-6) / 1e9}
 
 
 def c3_reference_us(sets, torch, stream, reps=10):

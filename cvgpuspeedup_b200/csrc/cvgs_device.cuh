@@ -176,6 +176,10 @@ __device__ __forceinline__ void st_cs_f32x4(float* p, float a, float b, float c,
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
                  : "memory");
 }
+// predicated store (no branch: keeps the surrounding code in one basic block)
+__device__ __forceinline__ void st_cs_f32_if(bool pred, float* p, float a) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.global.cs.f32 [%1], %2;\n}" ::"r"((unsigned)pred), "l"(p), "f"(a) : "memory");
+}
 __device__ __forceinline__ void st_cs_f32(float* p, float a) {
     asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }

@@ -30,6 +30,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "../../include/cvgs_b200.h"
 #include "cvgs_device.cuh"
@@ -152,6 +153,15 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+// Tap load of the compute loop: NOT volatile, so that the compiler may hoist the loads of the next column above the
+// (volatile) stores of the previous one.  Ordering against the staging pipeline is carried by data dependences: the
+// address derives from a value laundered through a volatile asm after the slot's mbarrier wait, and the loaded
+// value feeds a volatile store that precedes the refill of the slot.
+__device__ __forceinline__ uint32_t lds32_tap(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ RowTap lds_rowtap(uint32_t addr) {
     RowTap r;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.a), "=f"(r.wy0), "=f"(r.wy1), "=r"(r.pad) : "r"(addr));
@@ -268,10 +278,10 @@ struct ItemCursor {
 // order nvcc emits for the reference: FMUL(p10*w10), FFMA(p00,w00), FFMA(p01,w01), FFMA(p11,w11).
 __device__ __forceinline__ void gather_pair(uint32_t A0, uint32_t B0, uint32_t A1, uint32_t B1, int shl, int shr, bool edge,
                                             float wx0, float wx1, float2 wy0, float2 wy1, float2 (&v)[3]) {
-    const uint32_t am0 = lds32(A0 - 4), a00 = lds32(A0), a01 = lds32(A0 + 4);
-    const uint32_t bm0 = lds32(B0 - 4), b00 = lds32(B0), b01 = lds32(B0 + 4);
-    const uint32_t am1 = lds32(A1 - 4), a10 = lds32(A1), a11 = lds32(A1 + 4);
-    const uint32_t bm1 = lds32(B1 - 4), b10 = lds32(B1), b11 = lds32(B1 + 4);
+    const uint32_t am0 = lds32_tap(A0 - 4), a00 = lds32_tap(A0), a01 = lds32_tap(A0 + 4);
+    const uint32_t bm0 = lds32_tap(B0 - 4), b00 = lds32_tap(B0), b01 = lds32_tap(B0 + 4);
+    const uint32_t am1 = lds32_tap(A1 - 4), a10 = lds32_tap(A1), a11 = lds32_tap(A1 + 4);
+    const uint32_t bm1 = lds32_tap(B1 - 4), b10 = lds32_tap(B1), b11 = lds32_tap(B1 + 4);
     // left pixel in bytes 0..2 (clamped shift: 32 = the word itself), right pixel in bytes 0..2
     const uint32_t al0 = __funnelshift_rc(am0, a00, shl), bl0 = __funnelshift_rc(bm0, b00, shl);
     const uint32_t al1 = __funnelshift_rc(am1, a10, shl), bl1 = __funnelshift_rc(bm1, b10, shl);
@@ -536,7 +546,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         }
         // this lane's first column in rows 2*jp of the three channel planes of plane z
         asm volatile("" : "+r"(m_edge), "+r"(m_img), "+r"(m_in));
-        (void)np;
+        const bool full_band = tx0 + 32 * np <= W;  // every lane owns a column in each of the band's np groups
         float* s0 = P.out.base + ((long long)z * P.out.z_stride + (long long)(tx0 + lane) * pxs + (long long)(2 * cc.jp) * row_step);
         float* s1 = s0 + oc1;
         float* s2 = s0 + oc2;
@@ -585,46 +595,58 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             float* t2 = s2 + (GEN ? rs2 : (long long)row_step);
             asm volatile("" : "+l"(s0), "+l"(s1), "+l"(s2), "+l"(t0), "+l"(t1), "+l"(t2));
             asm volatile("" : "+r"(aA0), "+r"(aB0), "+r"(aA1), "+r"(aB1), "+f"(wy0.x), "+f"(wy0.y), "+f"(wy1.x), "+f"(wy1.y));
+            // Columns of the pair.  Bands whose 32-column groups are all inside the plane (the common case) run a
+            // branch-free body: one basic block, so the loads of the next column are scheduled above the arithmetic
+            // and the stores of the previous one.  Ragged bands test the lane's column mask per column.
+            auto columns = [&](auto npc_tag, auto check_tag) {
+                constexpr int NPC = decltype(npc_tag)::value;
+                constexpr bool CHECK = decltype(check_tag)::value;
 #pragma unroll
-            for (int p = 0; p < kMaxNP; ++p) {
-                if (m_in & (1u << p)) {  // lanes past the right border of the plane (and whole groups past the band) skip
-                    float2 v[3];
-                    if (!GEN || im0 || im1) {
-                        gather_pair(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p],
-                                    (m_edge & (1u << p)) != 0, wxa[p], wxb[p], wy0, wy1, v);
-                        if (CHAIN == CH_FMA_DIV) {
+                for (int p = 0; p < NPC; ++p) {
+                    if (!CHECK || (m_in & (1u << p))) {  // lanes past the right border of the plane skip
+                        float2 v[3];
+                        if (!GEN || im0 || im1) {
+                            gather_pair(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p],
+                                        (m_edge & (1u << p)) != 0, wxa[p], wxb[p], wy0, wy1, v);
+                            if (CHAIN == CH_FMA_DIV) {
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) {
+                                    v[c] = __ffma2_rn(v[c], make_float2(ca[c], ca[c]), make_float2(cb[c], cb[c]));
+                                    v[c] = div_by_const2(v[c], zh[c], zl[c]);
+                                }
+                            } else {
+                                if (G.explicit_prescale) {
+#pragma unroll
+                                    for (int c = 0; c < 3; ++c) v[c] = __fmul2_rn(v[c], make_float2(kPreScale, kPreScale));
+                                }
+                                apply_program_pair(K.prog_img, v);
+                            }
+                        }
+                        if (GEN) {
 #pragma unroll
                             for (int c = 0; c < 3; ++c) {
-                                v[c] = __ffma2_rn(v[c], make_float2(ca[c], ca[c]), make_float2(cb[c], cb[c]));
-                                v[c] = div_by_const2(v[c], zh[c], zl[c]);
+                                if (!(im0 && (m_img & (1u << p)))) v[c].x = vb[0][c];
+                                if (!(im1 && (m_img & (1u << p)))) v[c].y = vb[0][c];
                             }
-                        } else {
-                            if (G.explicit_prescale) {
-#pragma unroll
-                                for (int c = 0; c < 3; ++c) v[c] = __fmul2_rn(v[c], make_float2(kPreScale, kPreScale));
-                            }
-                            apply_program_pair(K.prog_img, v);
                         }
-                    }
-                    if (GEN) {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            if (!(im0 && (m_img & (1u << p)))) v[c].x = vb[0][c];
-                            if (!(im1 && (m_img & (1u << p)))) v[c].y = vb[0][c];
-                        }
-                    }
-                    {
                         const int q = 32 * p * pxs;
                         st_cs_f32(s0 + q, v[0].x);
                         st_cs_f32(s1 + q, v[1].x);
                         st_cs_f32(s2 + q, v[2].x);
-                        if (st1) {
-                            st_cs_f32(t0 + q, v[0].y);
-                            st_cs_f32(t1 + q, v[1].y);
-                            st_cs_f32(t2 + q, v[2].y);
-                        }
+                        st_cs_f32_if(st1, t0 + q, v[0].y);
+                        st_cs_f32_if(st1, t1 + q, v[1].y);
+                        st_cs_f32_if(st1, t2 + q, v[2].y);
                     }
                 }
+            };
+            using std::integral_constant;
+            if (full_band) {
+                if (np == 4) columns(integral_constant<int, 4>{}, integral_constant<bool, false>{});
+                else if (np == 3) columns(integral_constant<int, 3>{}, integral_constant<bool, false>{});
+                else if (np == 2) columns(integral_constant<int, 2>{}, integral_constant<bool, false>{});
+                else columns(integral_constant<int, 1>{}, integral_constant<bool, false>{});
+            } else {
+                columns(integral_constant<int, kMaxNP>{}, integral_constant<bool, true>{});
             }
             s0 += 2 * (GEN ? rs0 : (long long)row_step);
             s1 += 2 * (GEN ? rs1 : (long long)row_step);
