@@ -37,7 +37,10 @@ struct CtParams {
     int32_t tiles_x;
     long long plane_px;      // W*H
     int32_t copy_vec4;       // planes are 16-byte aligned multiples of 4 floats
+    int32_t copy_chunks;     // copy CTAs per (plane, colour) unit when copy_vec4
 };
+
+constexpr int kCtChunk = 8192;  // float4 per copy CTA (128 KB): 256 threads x 4 accesses x 8 rounds
 
 __device__ __forceinline__ int ring_source(const CtParams& K, int z) {
     // computeCircularThreadIdx, reference memory_operations.cuh:388-399
@@ -77,31 +80,26 @@ __global__ void __launch_bounds__(256) circular_update_kernel(const __grid_const
     const OutDesc& o = P.out;
     const int units = (K.batch - 1) * 3;  // (plane, colour) pairs
     if (K.copy_vec4) {
-        const long long n4 = K.plane_px / 4;
-        const long long total = n4 * units;
-        const long long stride = (long long)ncopy * 256 * 4;
-        for (long long i = ((long long)cta * 256 + threadIdx.x) * 4; i < total; i += stride) {
+        // CTA -> (unit, chunk): one division per CTA, then 16-byte accesses at a fixed stride, 4 in flight per thread
+        const int n4 = (int)(K.plane_px / 4);
+        const int u = cta / K.copy_chunks;
+        const int chunk = cta - u * K.copy_chunks;
+        if (u >= units) return;
+        int z = u / 3;
+        const int c = u - z * 3;
+        if (z >= K.upd) ++z;  // skip the plane the compute CTAs write
+        const int zs = ring_source(K, z);
+        const float4* src = reinterpret_cast<const float4*>(K.ring_ro + zs * o.z_stride + c * o.c_stride);
+        float4* dst = reinterpret_cast<float4*>(o.base + z * o.z_stride + c * o.c_stride);
+        const int lo = chunk * kCtChunk, hi = min(n4, lo + kCtChunk);
+        for (int i = lo + threadIdx.x; i < hi; i += 4 * 256) {
             float4 r[4];
-            float4* dst[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const long long j = i + k;
-                dst[k] = nullptr;
-                if (j < total) {
-                    const int u = (int)(j / n4);
-                    const long long e = j - (long long)u * n4;
-                    int z = u / 3;
-                    const int c = u - z * 3;
-                    if (z >= K.upd) ++z;  // skip the plane the compute CTAs write
-                    const int zs = ring_source(K, z);
-                    const float4* src = reinterpret_cast<const float4*>(K.ring_ro + zs * o.z_stride + c * o.c_stride) + e;
-                    dst[k] = reinterpret_cast<float4*>(o.base + z * o.z_stride + c * o.c_stride) + e;
-                    r[k] = __ldcs(src);
-                }
-            }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (dst[k]) __stcs(dst[k], r[k]);
+                if (i + k * 256 < hi) r[k] = __ldcs(src + i + k * 256);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i + k * 256 < hi) __stcs(dst + i + k * 256, r[k]);
         }
     } else {
         const long long total = K.plane_px * units;
@@ -200,7 +198,10 @@ int cvgs_b200_ct_update(void* handle, const cvgs_crop_t* frame, const cvgs_pipel
     if (compute > (1ll << 30)) return fail(CVGS_ERR_INVALID_VALUE, "plane too large");
     K.compute_ctas = (int)compute;
     int copy_ctas = 0;
-    if (t->batch > 1) {
+    if (t->batch > 1 && K.copy_vec4) {
+        K.copy_chunks = (int)((K.plane_px / 4 + kCtChunk - 1) / kCtChunk);
+        copy_ctas = K.copy_chunks * 3 * (t->batch - 1);
+    } else if (t->batch > 1) {
         const long long work = K.plane_px * 3 * (t->batch - 1) / (K.copy_vec4 ? 16 : 1);  // thread-iterations
         const long long want = (work + 255) / 256;
         const long long cap = (long long)sm_count_of(t->device) * 8;
