@@ -1,0 +1,109 @@
+"""cvgs_b200_set_overlap(1): consecutive launches may overlap when the library proves them independent.  Stream
+semantics must be unchanged: hazards between launches (same output, output used as a source) are ordered, and
+whatever follows on the stream sees every earlier launch complete."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from cvgpuspeedup_b200 import _abi
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def overlap_on():
+    lib = _abi.load()
+    prev = lib.cvgs_b200_set_overlap(1)
+    yield lib
+    lib.cvgs_b200_set_overlap(prev)
+
+
+def _launch(lib, w, d_img, out, stream, parents=True, rects=None):
+    rects = w.rects if rects is None else rects
+    crops = util.host_crops(w.image, rects, base_ptr=d_img.data_ptr())
+    p = util.make_pipeline(w.dsize, w.ops, out_ptr=out.data_ptr())
+    par = util.host_parents(w.image, w.width, w.height, len(rects), base_ptr=d_img.data_ptr()) if parents else None
+    _abi.check(lib.cvgs_b200_preproc_launch_ex(crops, par, len(rects), len(rects), C.byref(p), stream.cuda_stream))
+    return crops, p, par  # keep alive until the caller synchronises
+
+
+def test_many_independent_launches(overlap_on):
+    lib = overlap_on
+    st = torch.cuda.Stream()
+    ws = [util.workload_c2(seed=300 + k, n=20, frame=(640, 480), pitch=1920) for k in range(6)]
+    d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
+    outs = [torch.full((20, 3, 128, 64), float("nan"), device="cuda") for _ in range(40)]
+    keep = [_launch(lib, ws[i % 6], d_imgs[i % 6], outs[i], st) for i in range(40)]  # > the 8-launch window
+    st.synchronize()
+    want = [util.run_oracle(w.image, w.rects, w.dsize, w.ops) for w in ws]
+    for i, o in enumerate(outs):
+        util.assert_bit_equal(o.cpu().numpy(), want[i % 6], f"launch {i}")
+    del keep
+
+
+def test_same_output_is_written_in_launch_order(overlap_on):
+    lib = overlap_on
+    st = torch.cuda.Stream()
+    ws = [util.workload_c2(seed=310 + k, n=50, pitch=6144) for k in range(2)]
+    d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
+    out = torch.full((50, 3, 128, 64), float("nan"), device="cuda")
+    keep = []
+    for rep in range(25):
+        for k in range(2):
+            keep.append(_launch(lib, ws[k], d_imgs[k], out, st))
+    st.synchronize()
+    util.assert_bit_equal(out.cpu().numpy(), util.run_oracle(ws[1].image, ws[1].rects, ws[1].dsize, ws[1].ops), "last writer wins")
+
+
+def test_output_of_one_launch_as_source_of_the_next(overlap_on):
+    """Launch B reads (as CV_8UC3 bytes) the float tensor launch A writes: a read-after-write hazard through memory."""
+    lib = overlap_on
+    st = torch.cuda.Stream()
+    wa = util.workload_c3(seed=320, n=64, frame=(1920, 1080), dsize=(224, 224), lo=200, hi=800)
+    d_img = torch.from_numpy(wa.image).cuda()
+    t = torch.zeros((64, 3, 224, 224), dtype=torch.float32, device="cuda")      # A's output = B's "image"
+    pitch = 3 * 224 * 4                                                          # one float row triple = 896 pixels
+    rows = t.numel() * 4 // pitch
+    rects = [(5 * i, 3 * i, 200 + i, 100 + 2 * i) for i in range(30)]
+    out_b = torch.full((30, 3, 128, 64), float("nan"), device="cuda")
+    keep = []
+    for rep in range(3):
+        keep.append(_launch(lib, wa, d_img, t, st))
+        crops = (_abi.Crop * 30)()
+        for i, (x, y, w, h) in enumerate(rects):
+            crops[i].data, crops[i].width, crops[i].height, crops[i].pitch = t.data_ptr() + y * pitch + 3 * x, w, h, pitch
+        p = util.make_pipeline((64, 128), util.OPS_C2, out_ptr=out_b.data_ptr())
+        _abi.check(lib.cvgs_b200_preproc_launch_ex(crops, None, 30, 30, C.byref(p), st.cuda_stream))
+        keep.append((crops, p))
+    st.synchronize()
+    host_t = t.cpu().numpy().view(np.uint8).reshape(rows, pitch)
+    util.assert_bit_equal(t.cpu().numpy(), util.run_oracle(wa.image, wa.rects, wa.dsize, wa.ops), "launch A")
+    util.assert_bit_equal(out_b.cpu().numpy(), util.run_oracle(host_t, rects, (64, 128), util.OPS_C2), "launch B sees A's output")
+
+
+def test_later_stream_work_sees_every_launch_complete(overlap_on):
+    """A long launch followed by a short independent one, then a device-to-host copy of the FIRST launch's output on
+    the same stream: the copy must see it complete (each kernel waits for its predecessor before it exits)."""
+    lib = overlap_on
+    st = torch.cuda.Stream()
+    big = util.workload_c3(seed=330, n=256)
+    small = util.workload_c2(seed=331, n=2, frame=(320, 240), pitch=960)
+    d_big, d_small = torch.from_numpy(big.image).cuda(), torch.from_numpy(small.image).cuda()
+    out_big = torch.full((256, 3, 224, 224), float("nan"), device="cuda")
+    out_small = torch.full((2, 3, 128, 64), float("nan"), device="cuda")
+    host = torch.empty(out_big.shape, dtype=torch.float32).pin_memory()
+    want = util.run_oracle(big.image, big.rects[:8], big.dsize, big.ops)
+    for rep in range(5):
+        out_big.fill_(float("nan"))
+        torch.cuda.synchronize()
+        k1 = _launch(lib, big, d_big, out_big, st)
+        k2 = _launch(lib, small, d_small, out_small, st)
+        with torch.cuda.stream(st):
+            host.copy_(out_big, non_blocking=True)
+        st.synchronize()
+        assert not np.isnan(host.numpy()).any(), "copy overtook the first launch"
+        util.assert_bit_equal(host.numpy()[:8], want, "first launch output")
+        del k1, k2
