@@ -72,6 +72,16 @@ struct StreamTrack {
 static std::mutex g_track_mu;
 static StreamTrack g_tracks[16];
 
+// Items per warp small launches aim for: 1 in plain stream order (latency), more when launches overlap (throughput).
+static int items_per_warp() {
+    static const int forced = [] {
+        const char* e = std::getenv("CVGS_TMA_ITEMS_PER_WARP");
+        return e ? std::max(1, std::atoi(e)) : 0;
+    }();
+    if (forced) return forced;
+    return g_overlap.load(std::memory_order_relaxed) ? 4 : 1;
+}
+
 // true: this launch must wait for the preceding kernel up front.
 static bool overlap_needs_wait(cudaStream_t stream, const MemRange& out, const MemRange& src) {
     if (!g_overlap.load(std::memory_order_relaxed)) return true;
@@ -343,9 +353,8 @@ static int prepare_image_maps(DevCrop* dc, const cvgs_parent_t* parents, int use
             last_rb = rb;
             last_k = k;
         }
-        DevCrop probe = dc[i];  // placement overwrites the pointer (union): keep the crops intact until all fit
-        if (!tma_place_in_image(probe, ds, p.whole_width, p.whole_height, rb, k)) return -1;
-        place[i] = Place{probe.m.xb, probe.m.y0, probe.pad};
+        if (!tma_place_in_image(dc[i], ds, p.whole_width, p.whole_height, rb, k, place[i].xb, place[i].y0, place[i].pad))
+            return -1;
     }
     for (int i = 0; i < used; ++i) {
         dc[i].m.xb = place[i].xb;
@@ -412,7 +421,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         TmaParams K;
         K.P = P;
         K.maps = nullptr;
-        if (variant != 1 && tma_plan(P, tt.c, used, n_planes, sms, parents != nullptr, K.G)) {
+        if (variant != 1 && tma_plan(P, tt.c, used, n_planes, sms, parents != nullptr, items_per_warp(), K.G)) {
             const int chain = scaled_program(P, K);
             const MemRange src = crops_range(tt.c, used);  // before the TMA fields overwrite the pointers
             const double t2 = now_us();
@@ -463,7 +472,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         TmaParams K;
         K.P = P;
         K.maps = nullptr;
-        if (tma_plan(P, lt.c, used, n_planes, sms, true, K.G)) {
+        if (tma_plan(P, lt.c, used, n_planes, sms, true, items_per_warp(), K.G)) {
             const int chain = scaled_program(P, K);
             const MemRange src = crops_range(lt.c, used);
             if (prepare_image_maps(lt.c, parents, used, K.G, P.W, lt.m, kTmaImageMaps) >= 0) {
@@ -483,7 +492,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         if (int rc = fill_crop(crops[i], *pipe, i, hc[i])) return rc;
     TmaParams K;
     K.P = P;
-    bool use_tma = variant != 1 && tma_plan(P, hc, used, n_planes, sms, parents != nullptr, K.G);
+    bool use_tma = variant != 1 && tma_plan(P, hc, used, n_planes, sms, parents != nullptr, 1, K.G);
     int chain = CH_GENERIC;
     size_t map_bytes = 0;
     if (use_tma) {

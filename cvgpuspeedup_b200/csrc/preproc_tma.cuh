@@ -713,7 +713,7 @@ inline int rb_class(int rb) {
 
 // Can this launch take the TMA kernel, and with which geometry?  crops = host copies of the DevCrops.
 inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int n_planes, int sm_count, bool image_mode,
-                     TmaGeom& G) {
+                     int items_per_warp, TmaGeom& G) {
     if (!encode_tiled_fn()) return false;
     if (P.src_type != CVGS_8UC3) return false;  // the byte-level tap extraction is written for 3-byte pixels
     float fx_max = 0.f;
@@ -757,7 +757,10 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
     if (cta_bytes(slots) > smem_sm) return false;
     G.slots = slots;
     G.resident = std::min(kMaxResident, smem_sm / cta_bytes(slots));
-    const long long warps_wanted = std::max<long long>(1, total);  // at least one item per warp
+    // Small launches: one item per warp spreads the work over the most SMs (shortest isolated launch); when
+    // consecutive launches overlap, several items per warp amortise the staging latency and leave CTA slots free
+    // for the next launch, which raises back-to-back throughput (items_per_warp > 1, cvgs_b200_set_overlap).
+    const long long warps_wanted = std::max<long long>(1, (total + items_per_warp - 1) / items_per_warp);
     const long long ctas_wanted = (warps_wanted + kWarps - 1) / kWarps;
     G.grid = static_cast<int32_t>(std::min<long long>(ctas_wanted, static_cast<long long>(G.resident) * sm_count));
     G.np_last = (std::min(TW, P.W - (G.tiles_x - 1) * TW) + 31) / 32;
@@ -775,7 +778,36 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
 
 // Chain for interpolated values: the 2^33 that undoes the tap/weight scaling is folded into the first op when
 // that is exact for every input (MUL/FMA/DIV by a constant of moderate magnitude), else applied explicitly.
+inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K);
+// Frame loops repeat one chain: the derived program (and the division proofs it looks up) is memoised per thread.
 inline int scaled_program(const PreprocParams& P, TmaParams& K) {
+    struct Memo {
+        bool valid = false;
+        DevProgram key;
+        DevProgram prog_img;
+        float zh[3], zl[3];
+        int explicit_prescale, chain;
+    };
+    static thread_local Memo m;
+    if (m.valid && std::memcmp(&m.key, &P.prog, sizeof(DevProgram)) == 0) {
+        K.prog_img = m.prog_img;
+        std::memcpy(K.zh, m.zh, sizeof m.zh);
+        std::memcpy(K.zl, m.zl, sizeof m.zl);
+        K.G.explicit_prescale = m.explicit_prescale;
+        return m.chain;
+    }
+    for (int c = 0; c < 3; ++c) K.zh[c] = K.zl[c] = 0.f;
+    const int chain = scaled_program_uncached(P, K);
+    m.key = P.prog;
+    m.prog_img = K.prog_img;
+    std::memcpy(m.zh, K.zh, sizeof m.zh);
+    std::memcpy(m.zl, K.zl, sizeof m.zl);
+    m.explicit_prescale = K.G.explicit_prescale;
+    m.chain = chain;
+    m.valid = true;
+    return chain;
+}
+inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
     K.prog_img = P.prog;
     K.G.explicit_prescale = 1;
     if (P.prog.round_u8 || P.prog.n_ops == 0) return CH_GENERIC;
@@ -893,17 +925,22 @@ struct ImageMapCache {
     }
 };
 
-// Locate crop c (c.data still valid) inside its parent image and bind it to map `map_index` with row bytes rb.
-inline bool tma_place_in_image(DevCrop& c, uintptr_t datastart, int width, int height, int rb, int map_index) {
+// Locate crop c (c.data valid) inside its parent image: byte offset within a map row, map row, and the pad word that
+// binds it to map `map_index` with row bytes rb.  The crop itself is not modified.
+inline bool tma_place_in_image(const DevCrop& c, uintptr_t datastart, int width, int height, int rb, int map_index,
+                               int32_t& xb, int32_t& y0_out, int32_t& pad) {
     const uintptr_t addr = reinterpret_cast<uintptr_t>(c.data);
     if (addr < datastart || c.pitch <= 0) return false;
     const uintptr_t off = addr - datastart;
-    const long long y0 = static_cast<long long>(off / static_cast<uintptr_t>(c.pitch));
-    const long long xo = static_cast<long long>(off - static_cast<uintptr_t>(y0) * static_cast<uintptr_t>(c.pitch));
-    if (xo + 3LL * c.w > 3LL * width || y0 + c.h > height || (height > 1 && 3LL * width > c.pitch)) return false;
-    c.m.xb = static_cast<int32_t>((datastart & 15) + xo);  // overwrites c.data (union)
-    c.m.y0 = static_cast<int32_t>(y0);
-    c.pad = rb | (map_index << 16);
+    // crops lie within 2^32 bytes of their parent in practice: 32-bit division is several times cheaper
+    const unsigned long long y0 = off <= 0xffffffffull ? static_cast<uint32_t>(off) / static_cast<uint32_t>(c.pitch)
+                                                       : off / static_cast<uintptr_t>(c.pitch);
+    const long long xo = static_cast<long long>(off - y0 * static_cast<uintptr_t>(c.pitch));
+    if (xo + 3LL * c.w > 3LL * width || static_cast<long long>(y0) + c.h > height || (height > 1 && 3LL * width > c.pitch))
+        return false;
+    xb = static_cast<int32_t>((datastart & 15) + xo);
+    y0_out = static_cast<int32_t>(y0);
+    pad = rb | (map_index << 16);
     return true;
 }
 

@@ -107,3 +107,30 @@ def test_later_stream_work_sees_every_launch_complete(overlap_on):
         assert not np.isnan(host.numpy()).any(), "copy overtook the first launch"
         util.assert_bit_equal(host.numpy()[:8], want, "first launch output")
         del k1, k2
+
+
+@pytest.mark.parametrize("overlap", [0, 1])
+def test_launches_are_graph_capturable(overlap):
+    """Batches whose descriptors ride in the kernel parameters involve no copy and no allocation on the hot call, so a
+    frame loop can be captured into a CUDA graph and replayed (graph replay figure for config 2)."""
+    lib = _abi.load()
+    prev = lib.cvgs_b200_set_overlap(overlap)
+    try:
+        ws = [util.workload_c2(seed=340 + k, n=50, pitch=6144) for k in range(3)]
+        d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
+        outs = [torch.full((50, 3, 128, 64), float("nan"), device="cuda") for _ in ws]
+        st = torch.cuda.Stream()
+        keep = [_launch(lib, w, d, o, st) for w, d, o in zip(ws, d_imgs, outs)]  # warm-up: attributes, proofs, map cache
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            keep += [_launch(lib, w, d, o, torch.cuda.current_stream()) for w, d, o in zip(ws, d_imgs, outs)]
+        for rep in range(3):
+            for o in outs:
+                o.fill_(float("nan"))
+            g.replay()
+            torch.cuda.synchronize()
+            for w, o in zip(ws, outs):
+                util.assert_bit_equal(o.cpu().numpy(), util.run_oracle(w.image, w.rects, w.dsize, w.ops), f"replay {rep}")
+    finally:
+        lib.cvgs_b200_set_overlap(prev)
