@@ -282,6 +282,69 @@ inline void executeOperations(const cv::cuda::Stream& stream, const detail::Read
     executeOperations(stream, read, iops...);  // thread fusion is a property of the hand-written kernel here
 }
 
+// ---- batch reads without a resize (reference :504-584; tests/batchread/test_batchread_x_write3D.cu) -----------
+// fk::BatchRead<PerThreadRead> of N equally sized images.  The same kernel serves it: with destination size ==
+// source size the scale factors are exactly 1, every tap weight is exactly 0 or 1 and the interpolated value is the
+// source pixel bit for bit.
+namespace detail {
+template <size_t Batch>
+inline ReadBatch read_batch(const std::array<cv::cuda::GpuMat, Batch>& input, size_t activeBatch, const cv::Scalar& def) {
+    static_assert(Batch > 0, "empty batch");
+    const int t = input[0].type();
+    if (t != CV_8UC3 && t != CV_16UC3 && t != CV_16SC3)
+        throw std::runtime_error("cvGS (B200 build): batch reads take CV_8UC3, CV_16UC3 or CV_16SC3 images");
+    ReadBatch r;
+    r.n_planes = static_cast<int>(Batch);
+    r.used = static_cast<int>(activeBatch < Batch ? activeBatch : Batch);
+    r.dst_w = input[0].cols;
+    r.dst_h = input[0].rows;
+    r.aspect = CVGS_IGNORE_AR;
+    r.src_type = t;
+    for (int c = 0; c < 4; ++c) r.bg[c] = static_cast<float>(def[c]);
+    r.crops.resize(Batch);
+    r.parents.resize(Batch);
+    for (int i = 0; i < r.used; ++i) {
+        if (input[i].cols != r.dst_w || input[i].rows != r.dst_h || input[i].type() != t)
+            throw std::runtime_error("cvGS::executeOperations: the images of a batch read must have one size and type");
+        r.crops[i] = crop_of(input[i]);
+        r.parents[i] = parent_of(input[i]);
+    }
+    return r;
+}
+}  // namespace detail
+template <size_t Batch, typename... IOpTypes>
+inline void executeOperations(const std::array<cv::cuda::GpuMat, Batch>& input, const size_t& activeBatch,
+                              const cv::Scalar& defaultValue, const cv::cuda::Stream& stream, const IOpTypes&... iops) {
+    executeOperations(stream, detail::read_batch(input, activeBatch, defaultValue), iops...);
+}
+template <size_t Batch, typename... IOpTypes>
+inline void executeOperations(const std::array<cv::cuda::GpuMat, Batch>& input, const cv::cuda::Stream& stream,
+                              const IOpTypes&... iops) {
+    executeOperations(stream, detail::read_batch(input, Batch, cv::Scalar()), iops...);
+}
+// ... with the destination given as (GpuMat, plane size): the implicit final write is PerThreadWrite<_3D> (packed)
+template <size_t Batch, typename... IOpTypes>
+inline void executeOperations(const std::array<cv::cuda::GpuMat, Batch>& input, const size_t& activeBatch,
+                              const cv::Scalar& defaultValue, const cv::cuda::GpuMat& output, const cv::Size& outputPlane,
+                              const cv::cuda::Stream& stream, const IOpTypes&... iops) {
+    executeOperations(stream, detail::read_batch(input, activeBatch, defaultValue), iops..., write<CV_32FC3>(output, outputPlane));
+}
+template <size_t Batch, typename... IOpTypes>
+inline void executeOperations(const std::array<cv::cuda::GpuMat, Batch>& input, const cv::cuda::GpuMat& output,
+                              const cv::Size& outputPlane, const cv::cuda::Stream& stream, const IOpTypes&... iops) {
+    executeOperations(stream, detail::read_batch(input, Batch, cv::Scalar()), iops..., write<CV_32FC3>(output, outputPlane));
+}
+template <bool ENABLE_THREAD_FUSION, size_t Batch, typename... IOpTypes>
+inline void executeOperations(const std::array<cv::cuda::GpuMat, Batch>& input, const cv::cuda::Stream& stream,
+                              const IOpTypes&... iops) {
+    executeOperations(input, stream, iops...);
+}
+// single image (reference :475-487)
+template <typename... IOpTypes>
+inline void executeOperations(const cv::cuda::GpuMat& input, const cv::cuda::Stream& stream, const IOpTypes&... iops) {
+    executeOperations(std::array<cv::cuda::GpuMat, 1>{input}, stream, iops...);
+}
+
 // ---- CircularTensor (reference :600-627 over fkl/.../core/data/circular_tensor.cuh:84-151) ----------------
 template <int I, int O, int COLOR_PLANES, int BATCH, fk::CircularTensorOrder CT_ORDER,
           fk::ColorPlanes CP_MODE = fk::ColorPlanes::Standard>

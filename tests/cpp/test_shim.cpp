@@ -138,6 +138,40 @@ static int test_resize_x_split_write() {
     return 0;
 }
 
+// tests/batchread/test_batchread_x_write3D.cu:83-97: batch read (no resize) -> convertTo(alpha) -> subtract -> divide
+// -> write(tensor); images filled with a constant, so out = (v * alpha - sub) / div.  Also the (output, plane)
+// overload with an active batch smaller than the batch and a default value.
+static int test_batchread_x_write3D() {
+    constexpr int BATCH = 6, W = 40, H = 24;
+    const double alpha = 0.3;
+    const cv::Scalar sub(1, 4, 3.2), div(3.2, 0.6, 11.8), def(7, 8, 9);
+    cv::cuda::GpuMat d_big(H * 2, W * 3, CV_8UC3, cv::Scalar(5, 6, 7));
+    std::array<cv::cuda::GpuMat, BATCH> crops;
+    for (int i = 0; i < BATCH; ++i) crops[i] = d_big(cv::Rect(i, i, W, H));
+    cv::cuda::GpuMat d_out(BATCH, W * H * 3, CV_32FC1);
+    cv::cuda::Stream st;
+    cvGS::executeOperations(crops, st, cvGS::convertTo<CV_8UC3, CV_32FC3>(alpha), cvGS::subtract<CV_32FC3>(sub),
+                            cvGS::divide<CV_32FC3>(div), cvGS::write<CV_32FC3>(d_out, cv::Size(W, H)));
+    st.waitForCompletion();
+    std::vector<float> h(static_cast<size_t>(BATCH) * W * H * 3);
+    REQUIRE(cudaMemcpy(h.data(), d_out.data, h.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess);
+    const double src[3] = {5, 6, 7};
+    for (size_t i = 0; i < h.size(); ++i) {
+        const int c = static_cast<int>(i % 3);
+        REQUIRE(std::fabs(h[i] - static_cast<float>((src[c] * alpha - sub[c]) / div[c])) <= 1e-4f);
+    }
+    cvGS::executeOperations(crops, static_cast<size_t>(BATCH - 2), def, d_out, cv::Size(W, H), st,
+                            cvGS::convertTo<CV_8UC3, CV_32FC3>(alpha), cvGS::subtract<CV_32FC3>(sub), cvGS::divide<CV_32FC3>(div));
+    st.waitForCompletion();
+    REQUIRE(cudaMemcpy(h.data(), d_out.data, h.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess);
+    for (size_t i = 0; i < h.size(); ++i) {
+        const int c = static_cast<int>(i % 3), z = static_cast<int>(i / (static_cast<size_t>(W) * H * 3));
+        const double v = z < BATCH - 2 ? src[c] : def[c];  // inactive planes: chain(default value), SURVEY F9
+        REQUIRE(std::fabs(h[i] - static_cast<float>((v * alpha - sub[c]) / div[c])) <= 1e-4f);
+    }
+    return 0;
+}
+
 static int test_random_vs_oracle() {
     constexpr int BATCH = 8, W = 640, H = 480;
     std::mt19937 rng(7);
@@ -204,6 +238,7 @@ int main() {
     failed += test_circular_tensor<fk::CircularTensorOrder::OldestFirst, fk::ColorPlanes::Transposed>();
     failed += test_split();
     failed += test_resize_x_split_write();
+    failed += test_batchread_x_write3D();
     failed += test_random_vs_oracle();
     failed += test_error_convention();
     std::printf(failed ? "test_shim: %d FAILED\n" : "test_shim: all passed\n", failed);

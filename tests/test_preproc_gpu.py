@@ -257,3 +257,16 @@ def test_tma_kernel_refuses_unsupported_pitch():
     with pytest.raises(_abi.CvgsError):
         _check(w, 2)
     _check(w, 0)  # automatic selection falls back to the direct-gather kernel
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_identity_scale_is_a_plain_batch_read(variant):
+    """Destination size == source size (fk::BatchRead<PerThreadRead>, the reference's batch reads without a resize,
+    tests/batchread/test_batchread_x_write3D.cu): scale factors are exactly 1, so the output is the source pixel."""
+    rng = np.random.default_rng(77)
+    img = util.make_image(rng, 200, 120, pitch=640)
+    rects = [(3 * i, 2 * i, 96, 64) for i in range(10)]
+    got = gpu_util.run_cvgs(img, rects, (96, 64), [], variant=variant, layout=_abi.OUT_NHWC)
+    px = img[:, :600].reshape(120, 200, 3).astype(np.float32)
+    for i, (x, y, w, h) in enumerate(rects):
+        util.assert_bit_equal(got[i], px[y:y + h, x:x + w], f"crop {i}")
