@@ -38,8 +38,8 @@ class Pipeline(C.Structure):
     _fields_ = [("src_type", C.c_int32), ("dst_width", C.c_int32), ("dst_height", C.c_int32),
                 ("aspect_mode", C.c_int32), ("interp_mode", C.c_int32), ("fp_contract", C.c_int32),
                 ("background", C.c_float * 4), ("n_ops", C.c_int32), ("ops", Op * MAX_OPS),
-                ("out_layout", C.c_int32), ("reserved", C.c_int32), ("out", C.c_void_p),
-                ("out_plane_stride", C.c_int64)]
+                ("out_layout", C.c_int32), ("dst_type", C.c_int32), ("out", C.c_void_p),
+                ("out_plane_stride", C.c_int64), ("out_row_pitch", C.c_int64)]
 
 
 class Parent(C.Structure):

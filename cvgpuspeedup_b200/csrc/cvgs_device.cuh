@@ -57,6 +57,8 @@ struct OutDesc {
     long long c_stride;  // floats between colour planes
     int32_t px_stride;   // floats between x-adjacent pixels (1 planar, 3 packed)
     int32_t vec4;        // 1: planar rows are 16-byte aligned and W % 4 == 0
+    int32_t u8;          // 1: packed 8-bit output (SaturateCast<float, uchar> after the chain); strides below in bytes
+    long long row_pitch; // u8 output: bytes between rows
 };
 
 struct PreprocParams {
@@ -189,6 +191,16 @@ template <int NPIX>
 __device__ __forceinline__ void store_pixels(const PreprocParams& P, int z, int y, int x, int nvalid,
                                              const float (&v)[NPIX][3]) {
     const OutDesc& o = P.out;
+    if (o.u8) {  // convertTo<CV_32FC3, CV_8UC3> + packed write: byte dst_chan[r] of pixel p is register r
+        uint8_t* px = reinterpret_cast<uint8_t*>(o.base) + (long long)z * o.z_stride + (long long)y * o.row_pitch + 3LL * x;
+#pragma unroll
+        for (int p = 0; p < NPIX; ++p)
+            if (p < nvalid) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) px[3 * p + P.prog.dst_chan[r]] = (uint8_t)round_sat_u8(v[p][r]);
+            }
+        return;
+    }
     float* row = o.base + (long long)z * o.z_stride + ((long long)y * P.W + x) * o.px_stride;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {

@@ -609,6 +609,8 @@ static int preproc_host_impl(HostPath& h, const void* host_image, int32_t image_
     if (int rc = validate_pipeline(pipeline)) return rc;
     if (!host_image || !host_out || !rects) return fail(CVGS_ERR_INVALID_VALUE, "NULL host buffer");
     if (pipeline->src_type != CVGS_8UC3) return fail(CVGS_ERR_NOT_SUPPORTED, "the host-buffer entry point takes CV_8UC3 frames");
+    if (pipeline->dst_type == CVGS_8UC3 || pipeline->out_layout == CVGS_OUT_PLANES)
+        return fail(CVGS_ERR_NOT_SUPPORTED, "the host-buffer entry point writes one float tensor");
     if (image_width <= 0 || image_height <= 0 || image_pitch < 3 * image_width)
         return fail(CVGS_ERR_INVALID_VALUE, "bad host image geometry");
     if (n_planes <= 0 || used < 0) return fail(CVGS_ERR_INVALID_VALUE, "bad batch size");

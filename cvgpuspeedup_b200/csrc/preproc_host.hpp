@@ -113,6 +113,12 @@ inline int validate_pipeline(const cvgs_pipeline_t* p) {
     if (p->fp_contract < 0 || p->fp_contract > 1) return fail(CVGS_ERR_INVALID_VALUE, "bad fp_contract");
     if (p->out_layout < 0 || p->out_layout > 3) return fail(CVGS_ERR_INVALID_VALUE, "bad out_layout");
     if (p->out_plane_stride < 0) return fail(CVGS_ERR_INVALID_VALUE, "negative out_plane_stride");
+    if (p->dst_type != 0 && p->dst_type != CVGS_32FC3 && p->dst_type != CVGS_8UC3)
+        return fail(CVGS_ERR_NOT_SUPPORTED, "dst_type must be CV_32FC3 (or 0) or CV_8UC3");
+    if (p->dst_type == CVGS_8UC3 && p->out_layout != CVGS_OUT_NHWC)
+        return fail(CVGS_ERR_INVALID_VALUE, "CV_8UC3 output is packed: out_layout must be CVGS_OUT_NHWC");
+    if (p->dst_type == CVGS_8UC3 && p->out_row_pitch != 0 && p->out_row_pitch < 3LL * p->dst_width)
+        return fail(CVGS_ERR_INVALID_VALUE, "out_row_pitch smaller than a row");
     return CVGS_OK;
 }
 
@@ -153,7 +159,13 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
             o.c_stride = 1;
             o.px_stride = 3;
     }
-    o.vec4 = p.out_layout != CVGS_OUT_PLANES && o.px_stride == 1 && (p.dst_width % 4) == 0 &&
+    o.u8 = p.dst_type == CVGS_8UC3;
+    o.row_pitch = 0;
+    if (o.u8) {  // strides in bytes
+        o.row_pitch = p.out_row_pitch ? p.out_row_pitch : 3LL * p.dst_width;
+        o.z_stride = p.out_plane_stride ? p.out_plane_stride : o.row_pitch * p.dst_height;
+    }
+    o.vec4 = !o.u8 && p.out_layout != CVGS_OUT_PLANES && o.px_stride == 1 && (p.dst_width % 4) == 0 &&
              (reinterpret_cast<uintptr_t>(out) % 16) == 0 && (o.z_stride % 4) == 0 && (o.c_stride % 4) == 0;
     return CVGS_OK;
 }

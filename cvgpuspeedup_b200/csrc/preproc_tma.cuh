@@ -716,6 +716,7 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
                      int items_per_warp, TmaGeom& G) {
     if (!encode_tiled_fn()) return false;
     if (P.src_type != CVGS_8UC3) return false;  // the byte-level tap extraction is written for 3-byte pixels
+    if (P.out.u8) return false;                 // 8-bit destinations are written by the direct-gather kernel
     float fx_max = 0.f;
     for (int i = 0; i < used; ++i) {
         const DevCrop& c = crops[i];

@@ -61,12 +61,15 @@ struct ReadBatch {  // cvGS::resize(...) result
 struct ChainOp {  // multiply / subtract / divide / add / cvtColor / convertTo pieces
     cvgs_op_t op[2];
     int n = 0;
+    bool to_u8 = false;  // convertTo<CV_32FC3, CV_8UC3>(): must be the last operation, followed by write<CV_8UC3>
 };
 struct WriteOp {  // split / splitT / write
     void* out = nullptr;
     int layout = CVGS_OUT_NCHW;
     long long plane_stride = 0;
     std::vector<cvgs_plane_t> planes;  // split(vector<GpuMat>): one destination image per (crop, channel)
+    int dst_type = CVGS_32FC3;         // CV_8UC3: write<CV_8UC3>(...) after convertTo<CV_32FC3, CV_8UC3>()
+    long long row_pitch = 0;           // 8-bit destination: GpuMat::step
 };
 template <typename T>
 struct is_op : std::false_type {};
@@ -80,6 +83,8 @@ inline cvgs_op_t scalar_op(int kind, const cv::Scalar& s) {
     return o;
 }
 inline void append(cvgs_pipeline_t& p, const ChainOp& c) {
+    if (p.dst_type == CVGS_8UC3) throw std::runtime_error("cvGS: convertTo<CV_32FC3, CV_8UC3>() must be the last operation before the write");
+    if (c.to_u8) p.dst_type = CVGS_8UC3;
     for (int i = 0; i < c.n; ++i) {
         if (p.n_ops >= CVGS_MAX_OPS) throw std::runtime_error("cvGS: more than CVGS_MAX_OPS operations in the chain");
         p.ops[p.n_ops++] = c.op[i];
@@ -89,6 +94,10 @@ inline void append(cvgs_pipeline_t& p, const WriteOp& w) {
     p.out = w.layout == CVGS_OUT_PLANES ? const_cast<cvgs_plane_t*>(w.planes.data()) : w.out;
     p.out_layout = w.layout;
     p.out_plane_stride = w.plane_stride;
+    if ((w.dst_type == CVGS_8UC3) != (p.dst_type == CVGS_8UC3))
+        throw std::runtime_error("cvGS: write<CV_8UC3> and convertTo<CV_32FC3, CV_8UC3>() go together");
+    p.dst_type = w.dst_type;
+    p.out_row_pitch = w.row_pitch;
 }
 inline cvgs_plane_t plane_of(const cv::cuda::GpuMat& m) {  // gpuMat2RawPtr2D<float>, reference :40-44
     cvgs_plane_t q{};
@@ -177,8 +186,11 @@ inline detail::ReadBatch resize(const cv::cuda::GpuMat& input, const cv::Size& d
 // ---- element-wise operations (reference :74-161) ---------------------------------------------------------
 template <int I, int O>
 inline detail::ChainOp convertTo() {  // SaturateCast<u8 -> f32>: the resize already yields float
-    static_assert(CV_MAT_DEPTH(O) == CV_32F, "cvGS (B200 build): the fused path produces CV_32F");
-    return {};
+    static_assert(CV_MAT_DEPTH(O) == CV_32F || (I == CV_32FC3 && O == CV_8UC3),
+                  "cvGS (B200 build): convertTo produces CV_32F, or CV_8UC3 from CV_32FC3 as the last operation before write<CV_8UC3>");
+    detail::ChainOp c;
+    c.to_u8 = (O == CV_8UC3);  // SaturateCast<float, uchar>: applied by the kernel when it writes the 8-bit pixels
+    return c;
 }
 template <int I, int O>
 inline detail::ChainOp convertTo(float alpha) {
@@ -256,9 +268,27 @@ inline detail::WriteOp splitT(const fk::RawPtr<fk::T3D, float>& output) {
     return {output.data, CVGS_OUT_CNHW, 0, {}};
 }
 template <int O>
-inline detail::WriteOp write(const cv::cuda::GpuMat& output, const cv::Size& /*plane*/) {
-    static_assert(O == CV_32FC3, "cvGS (B200 build): CV_32FC3 output");
-    return {output.data, CVGS_OUT_NHWC, 0, {}};
+inline detail::WriteOp write(const cv::cuda::GpuMat& output, const cv::Size& plane) {
+    static_assert(O == CV_32FC3 || O == CV_8UC3, "cvGS (B200 build): CV_32FC3 or CV_8UC3 output");
+    detail::WriteOp w{output.data, CVGS_OUT_NHWC, 0, {}};
+    if (O == CV_8UC3) {  // gpuMat2Tensor builds a tight tensor of `plane`-sized images (reference :67-71)
+        w.dst_type = CVGS_8UC3;
+        w.row_pitch = 3LL * plane.width;
+    }
+    return w;
+}
+// PerThreadWrite<_2D, O>: one image with the GpuMat's own pitch (reference :449-452; tests/resize/test_resize_write.cu)
+template <int O>
+inline detail::WriteOp write(const cv::cuda::GpuMat& output) {
+    static_assert(O == CV_32FC3 || O == CV_8UC3, "cvGS (B200 build): CV_32FC3 or CV_8UC3 output");
+    detail::WriteOp w{output.data, CVGS_OUT_NHWC, 0, {}};
+    if (O == CV_8UC3) {
+        w.dst_type = CVGS_8UC3;
+        w.row_pitch = static_cast<long long>(output.step);
+    } else if (output.step != static_cast<size_t>(output.cols) * 12) {
+        throw std::runtime_error("cvGS::write<CV_32FC3>(GpuMat): a padded float destination is not supported by this build");
+    }
+    return w;
 }
 
 // ---- executeOperations (reference :464-473) --------------------------------------------------------------

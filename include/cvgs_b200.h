@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CVGS_B200_VERSION 100 /* 0.1.0 */
+#define CVGS_B200_VERSION 101 /* 0.1.1 */
 
 /* ---- error codes (subset of cudaError_t values so they can be passed through) ---- */
 #define CVGS_OK 0
@@ -135,11 +135,17 @@ typedef struct cvgs_pipeline {
     int32_t n_ops;
     cvgs_op_t ops[CVGS_MAX_OPS];
     int32_t out_layout; /* enum cvgs_out_layout                                    */
-    int32_t reserved;
+    int32_t dst_type;   /* 0 or CVGS_32FC3: float output.  CVGS_8UC3: the chain ends with convertTo<CV_32FC3, CV_8UC3>
+                           (SaturateCast<float, uchar>: round to nearest even, clamp to [0, 255], reference
+                           saturate.cuh:127-147) and packed 8-bit pixels are written -- cvGS::write<CV_8UC3>(GpuMat),
+                           the form of the reference's tests/resize/test_resize_write.cu; needs CVGS_OUT_NHWC. */
     void* out;                 /* device pointer, float (CVGS_OUT_PLANES: host array of cvgs_plane_t) */
     int64_t out_plane_stride;  /* floats between consecutive batch planes z; 0 = tight
                                   (3*dst_width*dst_height for NCHW/NHWC, dst_width*dst_height
-                                  for CNHW).  The reference ignores GpuMat::step. */
+                                  for CNHW).  The reference ignores GpuMat::step.
+                                  For CVGS_8UC3 output the unit is bytes. */
+    int64_t out_row_pitch;     /* CVGS_8UC3 output only: bytes between rows of a destination image (GpuMat::step of
+                                  cvGS::write<CV_8UC3>(GpuMat)); 0 = tight (3 * dst_width) */
 } cvgs_pipeline_t;
 
 /* ------------------------------------------------------------------------------------------

@@ -199,6 +199,13 @@ static void apply_chain(const cvgs_pipeline_t* p, float v[3]) {
 static void store_pixel(const cvgs_pipeline_t* p, int n_planes, int z, int y, int x, const float v[3]) {
     float* out = (float*)p->out;
     const int64_t W = p->dst_width, H = p->dst_height;
+    if (p->dst_type == CVGS_8UC3) { /* convertTo<CV_32FC3, CV_8UC3> + PerThreadWrite: SaturateCast saturate.cuh:127-147 */
+        const int64_t rp = p->out_row_pitch ? p->out_row_pitch : 3 * W;
+        const int64_t ps = p->out_plane_stride ? p->out_plane_stride : rp * H;
+        uint8_t* b = (uint8_t*)p->out + z * ps + y * rp + 3 * x;
+        for (int c = 0; c < 3; ++c) b[c] = (uint8_t)round_sat_u8(v[c]);
+        return;
+    }
     switch (p->out_layout) {
         case CVGS_OUT_NCHW: {
             const int64_t ps = p->out_plane_stride ? p->out_plane_stride : 3 * W * H;

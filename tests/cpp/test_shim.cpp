@@ -172,6 +172,29 @@ static int test_batchread_x_write3D() {
     return 0;
 }
 
+// tests/resize/test_resize_write.cu:55-56: resize -> convertTo<CV_32FC3, CV_8UC3>() -> write<CV_8UC3>(GpuMat), up and
+// down, on a constant image (the 8-bit value survives the round trip) and into a pitched destination.
+static int test_resize_write_8u() {
+    cv::cuda::GpuMat d_input(120, 160, CV_8UC3, cv::Scalar(11, 129, 250));
+    cv::cuda::Stream st;
+    for (const cv::Size sz : {cv::Size(320, 200), cv::Size(50, 37)}) {
+        cv::cuda::GpuMat d_out(sz.height, sz.width, CV_8UC3);
+        cvGS::executeOperations(st, cvGS::resize<CV_8UC3, cv::INTER_LINEAR>(d_input, sz, 0., 0.),
+                                cvGS::convertTo<CV_32FC3, CV_8UC3>(), cvGS::write<CV_8UC3>(d_out));
+        st.waitForCompletion();
+        std::vector<uchar> h(static_cast<size_t>(sz.width) * sz.height * 3);
+        d_out.download(h.data(), sz.width * 3);
+        for (size_t i = 0; i < h.size(); ++i) REQUIRE(h[i] == (i % 3 == 0 ? 11 : i % 3 == 1 ? 129 : 250));
+    }
+    bool threw = false;
+    try {
+        cv::cuda::GpuMat d_out(8, 8, CV_8UC3);
+        cvGS::executeOperations(st, cvGS::resize<CV_8UC3, cv::INTER_LINEAR>(d_input, cv::Size(8, 8), 0., 0.), cvGS::write<CV_8UC3>(d_out));
+    } catch (const std::runtime_error&) { threw = true; }
+    REQUIRE(threw);  // an 8-bit write without the cast is a type error in the reference; here it throws
+    return 0;
+}
+
 static int test_random_vs_oracle() {
     constexpr int BATCH = 8, W = 640, H = 480;
     std::mt19937 rng(7);
@@ -239,6 +262,7 @@ int main() {
     failed += test_split();
     failed += test_resize_x_split_write();
     failed += test_batchread_x_write3D();
+    failed += test_resize_write_8u();
     failed += test_random_vs_oracle();
     failed += test_error_convention();
     std::printf(failed ? "test_shim: %d FAILED\n" : "test_shim: all passed\n", failed);

@@ -1,0 +1,52 @@
+"""8-bit output: the chain ends with convertTo<CV_32FC3, CV_8UC3> (SaturateCast<float, uchar>, reference
+saturate.cuh:127-147) and packed pixels are written with the destination's own row pitch
+(cvGS::write<CV_8UC3>(GpuMat); reference tests/resize/test_resize_write.cu:55-56)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from cvgpuspeedup_b200 import _abi
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("src_type,px", [(_abi.CVGS_8UC3, 3), (_abi.CVGS_16UC3, 6)])
+@pytest.mark.parametrize("aspect", [_abi.IGNORE_AR, _abi.PRESERVE_AR_LEFT])
+def test_u8_output_matches_oracle(src_type, px, aspect):
+    rng = np.random.default_rng(61)
+    img = rng.integers(0, 256, size=(240, 2048), dtype=np.uint8)
+    rects = [(0, 0, 320, 240), (3, 5, 40, 80), (100, 20, 200, 200), (319, 0, 1, 240), (7, 7, 64, 128)]
+    lib = _abi.load()
+    d_img = torch.from_numpy(img).cuda()
+    for (W, H), pitch in [((64, 128), 0), ((33, 7), 128), ((200, 150), 608)]:
+        # chain chosen so that values leave [0, 255] on both sides: the saturation is exercised
+        ops = [("reorder", (2, 1, 0)), ("mul", (1.7, 0.004 if px == 6 else 1.0, -0.5)), ("sub", (40.0, -3.0, 0.25))]
+        rp = pitch or 3 * W
+        n = len(rects) + 1  # one unused plane: saturate(chain(background))
+        want = np.full((n, H, rp), 7, dtype=np.uint8)
+        got = torch.full((n, H, rp), 7, dtype=torch.uint8, device="cuda")
+        kw = dict(aspect=aspect, background=(300.0, 12.6, -4.0), layout=_abi.OUT_NHWC, src_type=src_type,
+                  dst_type=_abi.CVGS_8UC3, row_pitch=pitch)
+        p = util.make_pipeline((W, H), ops, out_ptr=want.ctypes.data, **kw)
+        assert util.oracle_lib().oracle_preproc(util.host_crops(img, rects, px_bytes=px), n, len(rects), C.byref(p), 0) == 0
+        p = util.make_pipeline((W, H), ops, out_ptr=got.data_ptr(), **kw)
+        _abi.check(lib.cvgs_b200_preproc_launch(util.host_crops(img, rects, base_ptr=d_img.data_ptr(), px_bytes=px), n,
+                                                len(rects), C.byref(p), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy(), want), f"{(W, H)} pitch {pitch}"
+        assert (want[:, :, :3 * W] == 255).any() and (want[:, :, :3 * W] == 0).any()
+
+
+def test_u8_output_argument_checks():
+    lib = _abi.load()
+    w = util.workload_c2(seed=62, n=2, frame=(320, 240), pitch=960)
+    d_img = torch.from_numpy(w.image).cuda()
+    out = torch.zeros(2 * 128 * 64 * 3, dtype=torch.uint8, device="cuda")
+    crops = util.host_crops(w.image, w.rects, base_ptr=d_img.data_ptr())
+    for kw in [dict(layout=_abi.OUT_NCHW), dict(layout=_abi.OUT_NHWC, row_pitch=100)]:
+        p = util.make_pipeline(w.dsize, w.ops, out_ptr=out.data_ptr(), dst_type=_abi.CVGS_8UC3, **kw)
+        with pytest.raises(_abi.CvgsError):
+            _abi.check(lib.cvgs_b200_preproc_launch(crops, 2, 2, C.byref(p), None))

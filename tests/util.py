@@ -135,7 +135,7 @@ _KIND = {"mul": _abi.OP_MUL, "sub": _abi.OP_SUB, "div": _abi.OP_DIV, "add": _abi
 
 def make_pipeline(dsize, ops, aspect=_abi.IGNORE_AR, background=(0, 0, 0), fp_contract=_abi.FP_REFERENCE_FUSED,
                   interp_mode=_abi.INTERP_FLOAT, layout=_abi.OUT_NCHW, out_ptr=0, plane_stride=0,
-                  src_type=_abi.CVGS_8UC3) -> _abi.Pipeline:
+                  src_type=_abi.CVGS_8UC3, dst_type=0, row_pitch=0) -> _abi.Pipeline:
     p = _abi.Pipeline()
     p.src_type = src_type
     p.dst_width, p.dst_height = dsize
@@ -151,6 +151,7 @@ def make_pipeline(dsize, ops, aspect=_abi.IGNORE_AR, background=(0, 0, 0), fp_co
             else:
                 p.ops[i].v[c] = v[c]
     p.out_layout, p.out, p.out_plane_stride = layout, out_ptr, plane_stride
+    p.dst_type, p.out_row_pitch = dst_type, row_pitch
     return p
 
 
