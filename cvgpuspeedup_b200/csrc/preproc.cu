@@ -7,10 +7,14 @@
 // here (they are template parameters in the reference, capped at 255 planes -- SURVEY.md F7).
 //
 // Two kernels:
-//   preproc_direct_kernel  gathers the bilinear taps straight from global memory with aligned word
-//                          loads; works for any pitch / alignment / size.  Fallback + small batches.
-//   preproc_tma_kernel     (preproc_tma.cuh) persistent, warp-specialised; source rows are staged
-//                          into shared memory by the TMA engine (cp.async.bulk, mbarrier pipeline).
+//   preproc_tma_kernel     (preproc_tma.cuh) the product path: persistent, every warp stages the source rows of its
+//                          own work items into shared memory with the TMA engine (cp.async.bulk.tensor, mbarrier
+//                          per slot) and computes row pairs in packed FP32.
+//   preproc_direct_kernel  gathers the bilinear taps straight from global memory; takes anything the TMA kernel
+//                          declines: pitches that are not multiples of 16 bytes, extreme down-scales, 16-bit
+//                          sources, 8-bit destinations.
+// This file: the direct kernel, the host launch path (descriptor tables in kernel parameters or through a pinned
+// ring, per-image tensor-map cache, overlap bookkeeping) and the C-ABI entry points of the batch pipeline.
 #include <cuda_runtime.h>
 
 #include <algorithm>
