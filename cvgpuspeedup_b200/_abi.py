@@ -16,6 +16,7 @@ MAX_OPS = 8
 
 # enums (include/cvgs_b200.h)
 CVGS_8UC3, CVGS_16UC3, CVGS_16SC3, CVGS_32FC3 = 16, 18, 19, 21
+CVGS_8UC4, CVGS_16UC4, CVGS_16SC4, CVGS_32FC4 = 24, 26, 27, 29
 PRESERVE_AR, IGNORE_AR, PRESERVE_AR_RN_EVEN, PRESERVE_AR_LEFT = 0, 1, 2, 3
 OP_MUL, OP_SUB, OP_DIV, OP_ADD, OP_REORDER = 1, 2, 3, 4, 5
 FP_REFERENCE_FUSED, FP_SEPARATE = 0, 1

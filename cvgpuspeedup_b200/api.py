@@ -27,6 +27,8 @@ INTER_LINEAR = 1
 CV_8UC3 = _abi.CVGS_8UC3
 CV_16UC3 = _abi.CVGS_16UC3
 CV_16SC3 = _abi.CVGS_16SC3
+CV_8UC4, CV_16UC4, CV_16SC4, CV_32FC4 = _abi.CVGS_8UC4, _abi.CVGS_16UC4, _abi.CVGS_16SC4, _abi.CVGS_32FC4
+COLOR_RGBA2BGRA = COLOR_BGRA2RGBA = 5
 CV_32FC3 = _abi.CVGS_32FC3
 
 
@@ -58,13 +60,14 @@ class GpuMat:
                       whole=self.whole)
 
 
-def _scalar3(s) -> Tuple[float, float, float]:
+def _scalar3(s) -> Tuple[float, ...]:
+    """cv::Scalar: up to four values (the fourth is used by 4-channel pipelines only)."""
     if isinstance(s, (int, float)):
-        return (float(s),) * 3
+        return (float(s),) * 4
     s = tuple(float(v) for v in s)
     if len(s) < 3:
-        raise ValueError("a 3-channel cv::Scalar is required")
-    return s[:3]
+        raise ValueError("a cv::Scalar with at least 3 values is required")
+    return (s + (0.0,))[:4]
 
 
 @dataclass
@@ -80,8 +83,8 @@ class _Resize:
 @dataclass
 class _Op:
     kind: int
-    v: Tuple[float, float, float] = (0.0, 0.0, 0.0)
-    perm: Tuple[int, int, int] = (0, 1, 2)
+    v: Tuple[float, ...] = (0.0, 0.0, 0.0, 0.0)
+    perm: Tuple[int, ...] = (0, 1, 2, 3)
 
 
 @dataclass
@@ -131,9 +134,9 @@ def convertTo(alpha: Optional[float] = None, beta: Optional[float] = None) -> Li
 
 def cvtColor(code: int = COLOR_RGB2BGR) -> _Op:
     """cvGS::cvtColor<COLOR_RGB2BGR / COLOR_BGR2RGB, CV_32FC3>() :151-161 = VectorReorder<2,1,0>."""
-    if code != COLOR_RGB2BGR:
-        raise CvgsError("only the 3-channel R<->B swap is on this path")
-    return _Op(_abi.OP_REORDER, perm=(2, 1, 0))
+    if code not in (COLOR_RGB2BGR, COLOR_RGBA2BGRA):
+        raise CvgsError("only the R<->B swaps (3 or 4 channels) are on this path")
+    return _Op(_abi.OP_REORDER, perm=(2, 1, 0, 3))
 
 
 def split(out, planeDims: Optional[Tuple[int, int]] = None, plane_stride: int = 0) -> _Write:
@@ -192,7 +195,7 @@ def build_pipeline(dsize, ops: Sequence[_Op], background=(0, 0, 0), aspect=IGNOR
     p.dst_width, p.dst_height = int(dsize[0]), int(dsize[1])
     p.aspect_mode, p.interp_mode, p.fp_contract = int(aspect), int(interp_mode), int(fp_contract)
     bg = _scalar3(background)
-    for c in range(3):
+    for c in range(4):
         p.background[c] = bg[c]
     ops = list(_flatten(ops))
     if len(ops) > _abi.MAX_OPS:
@@ -200,9 +203,9 @@ def build_pipeline(dsize, ops: Sequence[_Op], background=(0, 0, 0), aspect=IGNOR
     p.n_ops = len(ops)
     for i, o in enumerate(ops):
         p.ops[i].kind = o.kind
-        for c in range(3):
-            p.ops[i].v[c] = o.v[c]
-            p.ops[i].perm[c] = o.perm[c]
+        for c in range(4):
+            p.ops[i].v[c] = (tuple(o.v) + (0.0,) * 4)[c]
+            p.ops[i].perm[c] = (tuple(o.perm) + (3,))[c] if c < len(o.perm) + 1 else c
     p.out_layout, p.out, p.out_plane_stride = int(layout), out_ptr, int(plane_stride)
     return p
 

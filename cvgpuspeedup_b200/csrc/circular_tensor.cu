@@ -164,6 +164,7 @@ int cvgs_b200_ct_update(void* handle, const cvgs_crop_t* frame, const cvgs_pipel
     if (!frame) return fail(CVGS_ERR_INVALID_VALUE, "frame is NULL");
     if (int rc = validate_pipeline(pipeline)) return rc;
     if (pipeline->dst_type == CVGS_8UC3) return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor planes are float");
+    if (channels_of(pipeline->src_type) != 3) return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor takes 3-channel frames");
     if (pipeline->dst_width != t->w || pipeline->dst_height != t->h)
         return fail(CVGS_ERR_INVALID_VALUE, "pipeline destination size must equal the tensor plane size");
     cvgs_pipeline_t p = *pipeline;

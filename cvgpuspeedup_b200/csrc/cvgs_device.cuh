@@ -36,13 +36,13 @@ static_assert(sizeof(DevCrop) == 48, "DevCrop layout");
 enum DevOpKind : int32_t { DOP_MUL = 1, DOP_ADD = 2, DOP_DIV = 3, DOP_FMA = 4 };
 struct DevOp {
     int32_t kind;
-    float a[3];
-    float b[3];
+    float a[4];   // 3-channel launches use [0..2]
+    float b[4];
 };
 struct DevProgram {
     int32_t n_ops;
     int32_t round_u8;     // RoundKind: CVGS_INTERP_ROUND_U8 for the source depth of the launch
-    int32_t dst_chan[3];  // source channel r is written to output channel dst_chan[r]
+    int32_t dst_chan[4];  // source channel r is written to output channel dst_chan[r]
     DevOp ops[8];
 };
 
@@ -66,8 +66,9 @@ struct PreprocParams {
     int32_t n_planes, used;
     int32_t W, H;          // destination size
     int32_t band_test;     // 1 for the aspect-ratio preserving modes
-    int32_t src_type;      // CVGS_8UC3 / CVGS_16UC3 / CVGS_16SC3
-    float bg[3];           // background / default value (source channel order)
+    int32_t src_type;      // CVGS_8UC3 / CVGS_16UC3 / CVGS_16SC3 / CVGS_8UC4 / CVGS_16UC4 / CVGS_16SC4
+    int32_t nc;            // channels: 3 or 4
+    float bg[4];           // background / default value (source channel order)
     DevProgram prog;
     OutDesc out;
 };
@@ -133,13 +134,13 @@ __device__ __forceinline__ float round_sat_kind(float v, int kind) {
 }
 
 // Apply the normalised chain to N values laid out as v[pixel][channel].
-template <int NPIX>
-__device__ __forceinline__ void apply_program(const DevProgram& prog, float (&v)[NPIX][3]) {
+template <int NPIX, int NC = 3>
+__device__ __forceinline__ void apply_program(const DevProgram& prog, float (&v)[NPIX][NC]) {
     if (prog.round_u8) {
 #pragma unroll
         for (int p = 0; p < NPIX; ++p)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[p][c] = round_sat_kind(v[p][c], prog.round_u8);
+            for (int c = 0; c < NC; ++c) v[p][c] = round_sat_kind(v[p][c], prog.round_u8);
     }
     for (int i = 0; i < prog.n_ops; ++i) {
         const DevOp& op = prog.ops[i];
@@ -148,25 +149,25 @@ __device__ __forceinline__ void apply_program(const DevProgram& prog, float (&v)
 #pragma unroll
                 for (int p = 0; p < NPIX; ++p)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) v[p][c] = __fmaf_rn(v[p][c], op.a[c], op.b[c]);
+                    for (int c = 0; c < NC; ++c) v[p][c] = __fmaf_rn(v[p][c], op.a[c], op.b[c]);
                 break;
             case DOP_MUL:
 #pragma unroll
                 for (int p = 0; p < NPIX; ++p)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) v[p][c] = __fmul_rn(v[p][c], op.a[c]);
+                    for (int c = 0; c < NC; ++c) v[p][c] = __fmul_rn(v[p][c], op.a[c]);
                 break;
             case DOP_ADD:
 #pragma unroll
                 for (int p = 0; p < NPIX; ++p)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) v[p][c] = __fadd_rn(v[p][c], op.a[c]);
+                    for (int c = 0; c < NC; ++c) v[p][c] = __fadd_rn(v[p][c], op.a[c]);
                 break;
             case DOP_DIV:
 #pragma unroll
                 for (int p = 0; p < NPIX; ++p)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) v[p][c] = __fdiv_rn(v[p][c], op.a[c]);
+                    for (int c = 0; c < NC; ++c) v[p][c] = __fdiv_rn(v[p][c], op.a[c]);
                 break;
             default:
                 break;
@@ -187,27 +188,27 @@ __device__ __forceinline__ void st_cs_f32(float* p, float a) {
 }
 
 // Store NPIX x-adjacent pixels (first one at column x) of row y, plane z.
-template <int NPIX>
+template <int NPIX, int NC = 3>
 __device__ __forceinline__ void store_pixels(const PreprocParams& P, int z, int y, int x, int nvalid,
-                                             const float (&v)[NPIX][3]) {
+                                             const float (&v)[NPIX][NC]) {
     const OutDesc& o = P.out;
     if (o.u8) {  // convertTo<CV_32FC3, CV_8UC3> + packed write: byte dst_chan[r] of pixel p is register r
-        uint8_t* px = reinterpret_cast<uint8_t*>(o.base) + (long long)z * o.z_stride + (long long)y * o.row_pitch + 3LL * x;
+        uint8_t* px = reinterpret_cast<uint8_t*>(o.base) + (long long)z * o.z_stride + (long long)y * o.row_pitch + (long long)NC * x;
 #pragma unroll
         for (int p = 0; p < NPIX; ++p)
             if (p < nvalid) {
 #pragma unroll
-                for (int r = 0; r < 3; ++r) px[3 * p + P.prog.dst_chan[r]] = (uint8_t)round_sat_u8(v[p][r]);
+                for (int r = 0; r < NC; ++r) px[NC * p + P.prog.dst_chan[r]] = (uint8_t)round_sat_u8(v[p][r]);
             }
         return;
     }
     float* row = o.base + (long long)z * o.z_stride + ((long long)y * P.W + x) * o.px_stride;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
+    for (int r = 0; r < NC; ++r) {
         // the channel reorder costs nothing: it only changes which plane register r goes to
         float* dst = row + (long long)P.prog.dst_chan[r] * o.c_stride;
         if (o.planes) {  // table is indexed by SOURCE channel (the host applied dst_chan when it built it)
-            const DevPlane pl = o.planes[z * 3 + r];
+            const DevPlane pl = o.planes[z * NC + r];
             dst = pl.data + (long long)y * pl.pitch + x;
         }
         if (NPIX == 4 && o.vec4 && nvalid == 4) {

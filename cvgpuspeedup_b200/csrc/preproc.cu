@@ -172,7 +172,7 @@ __device__ __forceinline__ const DevCrop& crop_of<ParamCropTable>(const PreprocP
 }
 
 // block = 256 threads = (1 << bw_log2) quads in x  X  (256 >> bw_log2) rows; a quad = 4 output pixels.
-template <typename Table>
+template <typename Table, int NC>
 __global__ void __launch_bounds__(256)
 preproc_direct_kernel(const __grid_constant__ PreprocParams P, const __grid_constant__ Table T, int bw_log2) {
     const int tid = threadIdx.x;
@@ -184,14 +184,14 @@ preproc_direct_kernel(const __grid_constant__ PreprocParams P, const __grid_cons
     if (x0 >= P.W || y >= P.H) return;
     const int nvalid = min(4, P.W - x0);
 
-    float v[4][3];
+    float v[4][NC];
     if (z < P.used) {
         gather_quad(P, crop_of<Table>(P, T, z), y, x0, nvalid, v);
     } else {
-        fill_background(P, v);
+        fill_background<NC>(P, v);
     }
-    apply_program<4>(P.prog, v);
-    store_pixels<4>(P, z, y, x0, nvalid, v);
+    apply_program<4, NC>(P.prog, v);
+    store_pixels<4, NC>(P, z, y, x0, nvalid, v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -208,7 +208,7 @@ struct Ring {
     size_t cap = 0;  // crops per slot
     int next = 0;
     int device = -1;
-    static size_t slot_bytes(size_t cap) { return cap * (sizeof(CUtensorMap) + sizeof(DevCrop) + 3 * sizeof(DevPlane)); }
+    static size_t slot_bytes(size_t cap) { return cap * (sizeof(CUtensorMap) + sizeof(DevCrop) + 4 * sizeof(DevPlane)); }
     DevPlane* planes_h(int s) const { return reinterpret_cast<DevPlane*>(h[s] + cap * (sizeof(CUtensorMap) + sizeof(DevCrop))); }
     DevPlane* planes_d(int s) const { return reinterpret_cast<DevPlane*>(d[s] + cap * (sizeof(CUtensorMap) + sizeof(DevCrop))); }
     CUtensorMap* maps_h(int s) const { return reinterpret_cast<CUtensorMap*>(h[s]); }
@@ -304,10 +304,13 @@ static int launch_direct(const PreprocParams& P, const ParamCropTable* table, cu
     const int rows = 256 >> l;
     const dim3 grid((qw + (1 << l) - 1) >> l, (P.H + rows - 1) / rows, P.n_planes);
     if (grid.y > 65535u || grid.z > 65535u) return fail(CVGS_ERR_INVALID_VALUE, "batch or height too large for one launch");
-    if (table) {
-        preproc_direct_kernel<ParamCropTable><<<grid, 256, 0, stream>>>(P, *table, l);
+    if (P.nc == 4) {
+        if (table) preproc_direct_kernel<ParamCropTable, 4><<<grid, 256, 0, stream>>>(P, *table, l);
+        else preproc_direct_kernel<NoTable, 4><<<grid, 256, 0, stream>>>(P, NoTable{}, l);
+    } else if (table) {
+        preproc_direct_kernel<ParamCropTable, 3><<<grid, 256, 0, stream>>>(P, *table, l);
     } else {
-        preproc_direct_kernel<NoTable><<<grid, 256, 0, stream>>>(P, NoTable{}, l);
+        preproc_direct_kernel<NoTable, 3><<<grid, 256, 0, stream>>>(P, NoTable{}, l);
     }
     count_launch();
     CVGS_CUDA(cudaGetLastError());
@@ -519,15 +522,16 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         // destination images, indexed [z][source channel] on the device (the channel reorder is applied here)
         const cvgs_plane_t* hp = static_cast<const cvgs_plane_t*>(pipe->out);
         DevPlane* dp = r.planes_h(slot);
+        const int nc = P.nc;
         for (int z = 0; z < n_planes; ++z)
-            for (int c = 0; c < 3; ++c) {
-                const cvgs_plane_t& q = hp[z * 3 + P.prog.dst_chan[c]];
+            for (int c = 0; c < nc; ++c) {
+                const cvgs_plane_t& q = hp[z * nc + P.prog.dst_chan[c]];
                 if (!q.data || q.pitch_bytes < 4LL * P.W || (q.pitch_bytes & 3))
                     return fail(CVGS_ERR_INVALID_VALUE, "plane " + std::to_string(z) + ": bad destination image");
-                dp[z * 3 + c].data = static_cast<float*>(q.data);
-                dp[z * 3 + c].pitch = q.pitch_bytes / 4;
+                dp[z * nc + c].data = static_cast<float*>(q.data);
+                dp[z * nc + c].pitch = q.pitch_bytes / 4;
             }
-        CVGS_CUDA(cudaMemcpyAsync(r.planes_d(slot), dp, static_cast<size_t>(n_planes) * 3 * sizeof(DevPlane),
+        CVGS_CUDA(cudaMemcpyAsync(r.planes_d(slot), dp, static_cast<size_t>(n_planes) * nc * sizeof(DevPlane),
                                   cudaMemcpyHostToDevice, stream));
         P.out.planes = r.planes_d(slot);
         K.P.out.planes = r.planes_d(slot);

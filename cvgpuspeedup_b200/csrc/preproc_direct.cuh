@@ -25,11 +25,12 @@ __device__ __forceinline__ Window load_window(const uint8_t* p, int nbytes) {
     return w;
 }
 
-__device__ __forceinline__ void fill_background(const PreprocParams& P, float (&v)[4][3]) {
+template <int NC>
+__device__ __forceinline__ void fill_background(const PreprocParams& P, float (&v)[4][NC]) {
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[p][c] = P.bg[c];
+        for (int c = 0; c < NC; ++c) v[p][c] = P.bg[c];
 }
 
 // Resize::exec + Interpolate::exec for output pixels (x0..x0+3, y) of crop C (reference
@@ -37,9 +38,10 @@ __device__ __forceinline__ void fill_background(const PreprocParams& P, float (&
 // the background.  The op chain is NOT applied here.
 // 16-bit sources (CV_16UC3 / CV_16SC3): the same arithmetic on ushort3 / short3 taps (the reference promotes them to
 // float exactly, core/utils/cuda_vector_utils.h), one 16-bit load per tap channel.
-template <typename T16>
+// Also the 4-channel sources (T = unsigned char / unsigned short / short, NC = 4).
+template <typename T16, int NC>
 __device__ __forceinline__ void gather_quad16(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
-                                              float (&v)[4][3]) {
+                                              float (&v)[4][NC]) {
     const AxisTap ty_ = axis_tap(y - C.by1, C.fy);
     const int y2r = min(ty_.i1 + 1, C.h - 1);
     const T16* r0 = reinterpret_cast<const T16*>(C.data + (size_t)ty_.i1 * (size_t)C.pitch);
@@ -53,21 +55,32 @@ __device__ __forceinline__ void gather_quad16(const PreprocParams& P, const DevC
             const float w00 = __fmul_rn(tx_.w0, ty_.w0), w10 = __fmul_rn(tx_.w1, ty_.w0);
             const float w01 = __fmul_rn(tx_.w0, ty_.w1), w11 = __fmul_rn(tx_.w1, ty_.w1);
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                v[p][c] = bilerp((float)__ldg(r0 + 3 * x1 + c), (float)__ldg(r0 + 3 * x2r + c), (float)__ldg(r1 + 3 * x1 + c),
-                                 (float)__ldg(r1 + 3 * x2r + c), w00, w10, w01, w11);
+            for (int c = 0; c < NC; ++c)
+                v[p][c] = bilerp((float)__ldg(r0 + NC * x1 + c), (float)__ldg(r0 + NC * x2r + c), (float)__ldg(r1 + NC * x1 + c),
+                                 (float)__ldg(r1 + NC * x2r + c), w00, w10, w01, w11);
         }
     }
 }
 
+// 4-channel sources (CV_8UC4 / CV_16UC4 / CV_16SC4): same arithmetic on four channels.
+__device__ __forceinline__ void gather_quad(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
+                                            float (&v)[4][4]) {
+    fill_background<4>(P, v);
+    const bool row_in = !P.band_test || (y >= C.by1 && y <= C.by2);
+    if (!row_in) return;
+    if (P.src_type == CVGS_8UC4) gather_quad16<unsigned char, 4>(P, C, y, x0, nvalid, v);
+    else if (P.src_type == CVGS_16UC4) gather_quad16<unsigned short, 4>(P, C, y, x0, nvalid, v);
+    else gather_quad16<short, 4>(P, C, y, x0, nvalid, v);
+}
+
 __device__ __forceinline__ void gather_quad(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
                                             float (&v)[4][3]) {
-    fill_background(P, v);
+    fill_background<3>(P, v);
     const bool row_in = !P.band_test || (y >= C.by1 && y <= C.by2);
     if (!row_in) return;
     if (P.src_type != CVGS_8UC3) {
-        if (P.src_type == CVGS_16UC3) gather_quad16<unsigned short>(P, C, y, x0, nvalid, v);
-        else gather_quad16<short>(P, C, y, x0, nvalid, v);
+        if (P.src_type == CVGS_16UC3) gather_quad16<unsigned short, 3>(P, C, y, x0, nvalid, v);
+        else gather_quad16<short, 3>(P, C, y, x0, nvalid, v);
         return;
     }
     const AxisTap ty_ = axis_tap(y - C.by1, C.fy);

@@ -54,25 +54,36 @@ inline void resize_geometry(int sw, int sh, int dw, int dh, int aspect, DevCrop&
     }
 }
 
+inline int channels_of(int src_type) { return (src_type == CVGS_8UC4 || src_type == CVGS_16UC4 || src_type == CVGS_16SC4) ? 4 : 3; }
+inline int pixel_bytes_of(int src_type) {
+    switch (src_type) {
+        case CVGS_8UC3: return 3;
+        case CVGS_8UC4: return 4;
+        case CVGS_16UC3: case CVGS_16SC3: return 6;
+        default: return 8;
+    }
+}
+
 // Normalise the user's op list (header: enum cvgs_op_kind) into a DevProgram.
 inline int build_program(const cvgs_pipeline_t& p, DevProgram& prog) {
+    const int NC = channels_of(p.src_type);
     std::memset(&prog, 0, sizeof prog);
     if (p.n_ops < 0 || p.n_ops > CVGS_MAX_OPS) return fail(CVGS_ERR_INVALID_VALUE, "n_ops out of range");
-    prog.round_u8 = p.interp_mode != CVGS_INTERP_ROUND_U8 ? ROUND_NONE
-                    : p.src_type == CVGS_16UC3            ? ROUND_U16
-                    : p.src_type == CVGS_16SC3            ? ROUND_S16
-                                                          : ROUND_U8;
-    int cur[3] = {0, 1, 2};  // position c currently holds source channel cur[c]
+    prog.round_u8 = p.interp_mode != CVGS_INTERP_ROUND_U8                        ? ROUND_NONE
+                    : (p.src_type == CVGS_16UC3 || p.src_type == CVGS_16UC4)   ? ROUND_U16
+                    : (p.src_type == CVGS_16SC3 || p.src_type == CVGS_16SC4)   ? ROUND_S16
+                                                                               : ROUND_U8;
+    int cur[4] = {0, 1, 2, 3};  // position c currently holds source channel cur[c]
     const bool fuse = p.fp_contract == CVGS_FP_REFERENCE_FUSED;
     int n = 0;
     for (int i = 0; i < p.n_ops; ++i) {
         const cvgs_op_t& op = p.ops[i];
         if (op.kind == CVGS_OP_REORDER) {
-            int nc[3];
-            bool seen[3] = {false, false, false};
-            for (int c = 0; c < 3; ++c) {
-                if (op.perm[c] < 0 || op.perm[c] > 2 || seen[op.perm[c]])
-                    return fail(CVGS_ERR_INVALID_VALUE, "REORDER perm must be a permutation of {0,1,2}");
+            int nc[4];
+            bool seen[4] = {false, false, false, false};
+            for (int c = 0; c < NC; ++c) {
+                if (op.perm[c] < 0 || op.perm[c] >= NC || seen[op.perm[c]])
+                    return fail(CVGS_ERR_INVALID_VALUE, "REORDER perm must be a permutation of the channels");
                 seen[op.perm[c]] = true;
                 nc[c] = cur[op.perm[c]];
             }
@@ -87,25 +98,26 @@ inline int build_program(const cvgs_pipeline_t& p, DevProgram& prog) {
             case CVGS_OP_SUB: d.kind = DOP_ADD; break;
             default: return fail(CVGS_ERR_INVALID_VALUE, "unknown op kind");
         }
-        for (int c = 0; c < 3; ++c) d.a[cur[c]] = op.kind == CVGS_OP_SUB ? -op.v[c] : op.v[c];
+        for (int c = 0; c < NC; ++c) d.a[cur[c]] = op.kind == CVGS_OP_SUB ? -op.v[c] : op.v[c];
         // nvcc contracts (x*m) +/- s into one FMA in the reference's inlined chain
         if (fuse && d.kind == DOP_ADD && n > 0 && prog.ops[n - 1].kind == DOP_MUL) {
             DevOp& m = prog.ops[n - 1];
             m.kind = DOP_FMA;
-            for (int c = 0; c < 3; ++c) m.b[c] = d.a[c];
+            for (int c = 0; c < NC; ++c) m.b[c] = d.a[c];
             continue;
         }
         prog.ops[n++] = d;
     }
     prog.n_ops = n;
-    for (int c = 0; c < 3; ++c) prog.dst_chan[cur[c]] = c;
+    for (int c = 0; c < NC; ++c) prog.dst_chan[cur[c]] = c;
     return CVGS_OK;
 }
 
 inline int validate_pipeline(const cvgs_pipeline_t* p) {
     if (!p) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
-    if (p->src_type != CVGS_8UC3 && p->src_type != CVGS_16UC3 && p->src_type != CVGS_16SC3)
-        return fail(CVGS_ERR_NOT_SUPPORTED, "only CV_8UC3, CV_16UC3 and CV_16SC3 sources are supported by this build");
+    if (p->src_type != CVGS_8UC3 && p->src_type != CVGS_16UC3 && p->src_type != CVGS_16SC3 && p->src_type != CVGS_8UC4 &&
+        p->src_type != CVGS_16UC4 && p->src_type != CVGS_16SC4)
+        return fail(CVGS_ERR_NOT_SUPPORTED, "sources must be CV_8U / CV_16U / CV_16S with 3 or 4 channels");
     if (p->dst_width <= 0 || p->dst_height <= 0 || p->dst_width > (1 << 20) || p->dst_height > (1 << 20))
         return fail(CVGS_ERR_INVALID_VALUE, "destination size out of range");
     if (p->aspect_mode < 0 || p->aspect_mode > 3) return fail(CVGS_ERR_INVALID_VALUE, "bad aspect_mode");
@@ -113,8 +125,10 @@ inline int validate_pipeline(const cvgs_pipeline_t* p) {
     if (p->fp_contract < 0 || p->fp_contract > 1) return fail(CVGS_ERR_INVALID_VALUE, "bad fp_contract");
     if (p->out_layout < 0 || p->out_layout > 3) return fail(CVGS_ERR_INVALID_VALUE, "bad out_layout");
     if (p->out_plane_stride < 0) return fail(CVGS_ERR_INVALID_VALUE, "negative out_plane_stride");
-    if (p->dst_type != 0 && p->dst_type != CVGS_32FC3 && p->dst_type != CVGS_8UC3)
-        return fail(CVGS_ERR_NOT_SUPPORTED, "dst_type must be CV_32FC3 (or 0) or CV_8UC3");
+    if (p->dst_type != 0 && p->dst_type != CVGS_32FC3 && p->dst_type != CVGS_32FC4 && p->dst_type != CVGS_8UC3)
+        return fail(CVGS_ERR_NOT_SUPPORTED, "dst_type must be CV_32FC3 / CV_32FC4 (or 0) or CV_8UC3");
+    if (p->dst_type == CVGS_8UC3 && channels_of(p->src_type) != 3)
+        return fail(CVGS_ERR_NOT_SUPPORTED, "8-bit output is implemented for 3-channel pipelines");
     if (p->dst_type == CVGS_8UC3 && p->out_layout != CVGS_OUT_NHWC)
         return fail(CVGS_ERR_INVALID_VALUE, "CV_8UC3 output is packed: out_layout must be CVGS_OUT_NHWC");
     if (p->dst_type == CVGS_8UC3 && p->out_row_pitch != 0 && p->out_row_pitch < 3LL * p->dst_width)
@@ -131,7 +145,9 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
     P.H = p.dst_height;
     P.band_test = p.aspect_mode != CVGS_IGNORE_AR;
     P.src_type = p.src_type;
-    for (int c = 0; c < 3; ++c) P.bg[c] = p.background[c];
+    P.nc = channels_of(p.src_type);
+    const int NC = P.nc;
+    for (int c = 0; c < NC; ++c) P.bg[c] = p.background[c];
     if (int rc = build_program(p, P.prog)) return rc;
     const long long plane = static_cast<long long>(p.dst_width) * p.dst_height;
     OutDesc& o = P.out;
@@ -145,7 +161,7 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
             o.px_stride = 1;
             break;
         case CVGS_OUT_NCHW:
-            o.z_stride = p.out_plane_stride ? p.out_plane_stride : 3 * plane;
+            o.z_stride = p.out_plane_stride ? p.out_plane_stride : NC * plane;
             o.c_stride = plane;
             o.px_stride = 1;
             break;
@@ -155,9 +171,9 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
             o.px_stride = 1;
             break;
         default:
-            o.z_stride = p.out_plane_stride ? p.out_plane_stride : 3 * plane;
+            o.z_stride = p.out_plane_stride ? p.out_plane_stride : NC * plane;
             o.c_stride = 1;
-            o.px_stride = 3;
+            o.px_stride = NC;
     }
     o.u8 = p.dst_type == CVGS_8UC3;
     o.row_pitch = 0;
@@ -174,10 +190,10 @@ inline int fill_crop(const cvgs_crop_t& c, const cvgs_pipeline_t& p, int idx, De
     if (!c.data) return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": data is NULL");
     if (c.width <= 0 || c.height <= 0 || c.width > (1 << 22) || c.height > (1 << 22))
         return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": size out of range");
-    const int px_bytes = p.src_type == CVGS_8UC3 ? 3 : 6;
+    const int px_bytes = pixel_bytes_of(p.src_type);
     if (c.pitch < px_bytes * c.width && c.height > 1)
         return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": pitch smaller than a row");
-    if (px_bytes == 6 && ((reinterpret_cast<uintptr_t>(c.data) | static_cast<uintptr_t>(c.pitch)) & 1))
+    if (px_bytes >= 6 && ((reinterpret_cast<uintptr_t>(c.data) | static_cast<uintptr_t>(c.pitch)) & 1))
         return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": 16-bit pixels must be 2-byte aligned");
     d.data = static_cast<const uint8_t*>(c.data);
     d.w = c.width;

@@ -154,8 +154,8 @@ inline int& interpMode() {
 template <int T, int INTER_F, int NPtr, AspectRatio AR_ = IGNORE_AR>
 inline detail::ReadBatch resize(const std::array<cv::cuda::GpuMat, NPtr>& input, const cv::Size& dsize, const int& usedPlanes,
                                 const cv::Scalar& backgroundValue = cv::Scalar()) {
-    static_assert(T == CV_8UC3 || T == CV_16UC3 || T == CV_16SC3,
-                  "cvGS (B200 build): CV_8UC3, CV_16UC3 and CV_16SC3 sources are on the hot path in this build");
+    static_assert(T == CV_8UC3 || T == CV_16UC3 || T == CV_16SC3 || T == CV_8UC4 || T == CV_16UC4 || T == CV_16SC4,
+                  "cvGS (B200 build): CV_8U / CV_16U / CV_16S sources with 3 or 4 channels are on the hot path in this build");
     static_assert(INTER_F == cv::INTER_LINEAR, "cvGS (B200 build): only INTER_LINEAR is implemented (as in the reference)");
     detail::ReadBatch r;
     r.n_planes = NPtr;
@@ -220,14 +220,18 @@ CVGS_SCALAR_OP(add, CVGS_OP_ADD)
 
 template <cv::ColorConversionCodes CODE, int I, int O = I>
 inline detail::ChainOp cvtColor() {
-    static_assert(CODE == cv::COLOR_RGB2BGR || CODE == cv::COLOR_BGR2RGB,
-                  "cvGS (B200 build): only the 3-channel R<->B swap is on the hot path");
-    static_assert(CV_MAT_CN(I) == 3 && CV_MAT_CN(O) == 3, "cvGS (B200 build): 3-channel only");
+    static_assert(CODE == cv::COLOR_RGB2BGR || CODE == cv::COLOR_BGR2RGB || CODE == cv::COLOR_RGBA2BGRA ||
+                      CODE == cv::COLOR_BGRA2RGBA,
+                  "cvGS (B200 build): the R<->B swaps (3 or 4 channels) are on the hot path");
+    static_assert(CV_MAT_CN(I) == CV_MAT_CN(O) && (CV_MAT_CN(I) == 3 || CV_MAT_CN(I) == 4),
+                  "cvGS (B200 build): colour conversions that change the channel count are not on the hot path");
+    static_assert((CV_MAT_CN(I) == 4) == (CODE == cv::COLOR_RGBA2BGRA), "cvGS: colour code and channel count disagree");
     detail::ChainOp c;
     c.op[0].kind = CVGS_OP_REORDER;
     c.op[0].perm[0] = 2;
     c.op[0].perm[1] = 1;
     c.op[0].perm[2] = 0;
+    c.op[0].perm[3] = 3;
     c.n = 1;
     return c;
 }
@@ -235,14 +239,14 @@ inline detail::ChainOp cvtColor() {
 // ---- writes (reference :185-202, :449-457) ---------------------------------------------------------------
 template <int O>
 inline detail::WriteOp split(const cv::cuda::GpuMat& output, const cv::Size& /*planeDims*/) {
-    static_assert(O == CV_32FC3, "cvGS (B200 build): CV_32FC3 output");
+    static_assert(O == CV_32FC3 || O == CV_32FC4, "cvGS (B200 build): CV_32FC3 / CV_32FC4 output");
     return {output.data, CVGS_OUT_NCHW, 0, {}};  // the reference builds a tight Tensor and ignores GpuMat::step (:67-71)
 }
 // fk::SplitWrite: the channels of a crop go to separate CV_32FC1 images (reference :163-183)
 template <int O>
 inline detail::WriteOp split(const std::vector<cv::cuda::GpuMat>& output) {
-    static_assert(O == CV_32FC3, "cvGS (B200 build): CV_32FC3 output");
-    if (output.size() != 3) throw std::runtime_error("cvGS::split: three destination images are required");
+    static_assert(O == CV_32FC3 || O == CV_32FC4, "cvGS (B200 build): CV_32FC3 / CV_32FC4 output");
+    if (output.size() != static_cast<size_t>(CV_MAT_CN(O))) throw std::runtime_error("cvGS::split: one destination image per channel is required");
     detail::WriteOp w;
     w.layout = CVGS_OUT_PLANES;
     for (const auto& m : output) w.planes.push_back(detail::plane_of(m));
@@ -250,11 +254,11 @@ inline detail::WriteOp split(const std::vector<cv::cuda::GpuMat>& output) {
 }
 template <int O, int N>
 inline detail::WriteOp split(const std::array<std::vector<cv::cuda::GpuMat>, N>& output) {
-    static_assert(O == CV_32FC3, "cvGS (B200 build): CV_32FC3 output");
+    static_assert(O == CV_32FC3 || O == CV_32FC4, "cvGS (B200 build): CV_32FC3 / CV_32FC4 output");
     detail::WriteOp w;
     w.layout = CVGS_OUT_PLANES;
     for (const auto& crop : output) {
-        if (crop.size() != 3) throw std::runtime_error("cvGS::split: three destination images per crop are required");
+        if (crop.size() != static_cast<size_t>(CV_MAT_CN(O))) throw std::runtime_error("cvGS::split: one destination image per channel and crop is required");
         for (const auto& m : crop) w.planes.push_back(detail::plane_of(m));
     }
     return w;
@@ -321,8 +325,8 @@ template <size_t Batch>
 inline ReadBatch read_batch(const std::array<cv::cuda::GpuMat, Batch>& input, size_t activeBatch, const cv::Scalar& def) {
     static_assert(Batch > 0, "empty batch");
     const int t = input[0].type();
-    if (t != CV_8UC3 && t != CV_16UC3 && t != CV_16SC3)
-        throw std::runtime_error("cvGS (B200 build): batch reads take CV_8UC3, CV_16UC3 or CV_16SC3 images");
+    if (t != CV_8UC3 && t != CV_16UC3 && t != CV_16SC3 && t != CV_8UC4 && t != CV_16UC4 && t != CV_16SC4)
+        throw std::runtime_error("cvGS (B200 build): batch reads take 8U / 16U / 16S images with 3 or 4 channels");
     ReadBatch r;
     r.n_planes = static_cast<int>(Batch);
     r.used = static_cast<int>(activeBatch < Batch ? activeBatch : Batch);

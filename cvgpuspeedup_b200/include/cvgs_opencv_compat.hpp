@@ -47,6 +47,11 @@ typedef unsigned int uint;
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
 #define CV_16UC3 CV_MAKETYPE(CV_16U, 3)
 #define CV_16SC3 CV_MAKETYPE(CV_16S, 3)
+#ifndef CV_8UC4
+#define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
+#endif
+#define CV_16UC4 CV_MAKETYPE(CV_16U, 4)
+#define CV_16SC4 CV_MAKETYPE(CV_16S, 4)
 #define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_32FC3 CV_MAKETYPE(CV_32F, 3)
@@ -56,7 +61,8 @@ namespace cv {
 
 enum InterpolationFlags { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2 };
 enum ColorConversionCodes { COLOR_BGR2BGRA = 0, COLOR_BGRA2BGR = 1, COLOR_BGR2RGBA = 2, COLOR_RGBA2BGR = 3,
-                            COLOR_BGR2RGB = 4, COLOR_RGB2BGR = COLOR_BGR2RGB, COLOR_BGRA2RGBA = 5 };
+                            COLOR_BGR2RGB = 4, COLOR_RGB2BGR = COLOR_BGR2RGB, COLOR_BGRA2RGBA = 5,
+                            COLOR_RGBA2BGRA = COLOR_BGRA2RGBA };
 
 struct Size {
     int width = 0, height = 0;

@@ -48,6 +48,10 @@ extern "C" {
 #define CVGS_16UC3 18 /* CV_16UC3: source only; taken by the direct-gather kernel (SaturateCast saturate.cuh:267-298) */
 #define CVGS_16SC3 19 /* CV_16SC3: source only; taken by the direct-gather kernel (saturate.cuh:358-378)             */
 #define CVGS_32FC3 21 /* CV_32FC3 */
+#define CVGS_8UC4 24  /* CV_8UC4, CV_16UC4, CV_16SC4: 4-channel sources (the reference's test matrix,            */
+#define CVGS_16UC4 26 /* tests/batchresize/test_batchresize_x_split3D.cu:427-432): four output channels, four      */
+#define CVGS_16SC4 27 /* constants per operation, REORDER over four channels; taken by the direct-gather kernel    */
+#define CVGS_32FC4 29 /* CV_32FC4 */
 
 /* Aspect-ratio policy of the resize; same numbering as cvGS::AspectRatio
  * (reference include/cvGPUSpeedup.cuh:32, fkl/.../image_processing/resize.cuh:41). */
@@ -123,7 +127,7 @@ typedef struct cvgs_op {
 /* Everything cvGS::executeOperations(stream, resize(...), ops..., split(...)) carries besides
  * the crops (reference include/cvGPUSpeedup.cuh:218-245 resize, :131-161 ops, :185-202 split). */
 typedef struct cvgs_pipeline {
-    int32_t src_type;    /* CVGS_8UC3, CVGS_16UC3 or CVGS_16SC3                    */
+    int32_t src_type;    /* CVGS_8UC3, CVGS_16UC3, CVGS_16SC3 or their 4-channel forms */
     int32_t dst_width;   /* cv::Size dsize of cvGS::resize                         */
     int32_t dst_height;
     int32_t aspect_mode; /* enum cvgs_aspect_ratio                                 */

@@ -104,23 +104,30 @@ static float round_sat_s16(float v) {
     return r > 32767.0f ? 32767.0f : (r < -32768.0f ? -32768.0f : r);
 }
 static float round_sat_src(float v, int src_type) {
-    return src_type == CVGS_16UC3 ? round_sat_u16(v) : src_type == CVGS_16SC3 ? round_sat_s16(v) : round_sat_u8(v);
+    return (src_type == CVGS_16UC3 || src_type == CVGS_16UC4)   ? round_sat_u16(v)
+           : (src_type == CVGS_16SC3 || src_type == CVGS_16SC4) ? round_sat_s16(v)
+                                                                : round_sat_u8(v);
 }
 /* channel ch of pixel x of a source row, as the float the reference's uchar3/ushort3/short3 * float promotes it to */
+static int n_channels(int src_type) {
+    return (src_type == CVGS_8UC4 || src_type == CVGS_16UC4 || src_type == CVGS_16SC4) ? 4 : 3;
+}
 static float src_px(const uint8_t* row, int x, int ch, int src_type) {
-    if (src_type == CVGS_16UC3) return (float)((const uint16_t*)row)[3 * x + ch];
-    if (src_type == CVGS_16SC3) return (float)((const int16_t*)row)[3 * x + ch];
-    return (float)row[3 * x + ch];
+    const int nc = n_channels(src_type);
+    if (src_type == CVGS_16UC3 || src_type == CVGS_16UC4) return (float)((const uint16_t*)row)[nc * x + ch];
+    if (src_type == CVGS_16SC3 || src_type == CVGS_16SC4) return (float)((const int16_t*)row)[nc * x + ch];
+    return (float)row[nc * x + ch];
 }
 
 /* One output pixel of Resize::exec + Interpolate<INTER_LINEAR>::exec
  * (resize.cuh:70-82,178-189; interpolation.cuh:57-92; PerThreadRead ptr_nd.cuh:41-45).
  * Rounding sequence = what nvcc emits for the reference kernel (see file header). */
 static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspect_mode, int src_type,
-                         int x, int y, const float* bg, float out[3]) {
+                         int x, int y, const float* bg, float out[4]) {
+    const int nc = n_channels(src_type);
     if (aspect_mode != CVGS_IGNORE_AR) {
         if (!(x >= g->x1 && x <= g->x2 && y >= g->y1 && y <= g->y2)) {
-            out[0] = bg[0]; out[1] = bg[1]; out[2] = bg[2];
+            for (int ch = 0; ch < nc; ++ch) out[ch] = bg[ch];
             return;
         }
         x -= g->x1; y -= g->y1;
@@ -138,7 +145,7 @@ static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspec
     const uint8_t* base = (const uint8_t*)c->data;
     const uint8_t* r0 = base + (size_t)y1 * (size_t)c->pitch;
     const uint8_t* r1 = base + (size_t)y2r * (size_t)c->pitch;
-    for (int ch = 0; ch < 3; ++ch) {
+    for (int ch = 0; ch < nc; ++ch) {
         const float p00 = src_px(r0, x1, ch, src_type), p10 = src_px(r0, x2r, ch, src_type);
         const float p01 = src_px(r1, x1, ch, src_type), p11 = src_px(r1, x2r, ch, src_type);
         float t = p10 * w10;
@@ -151,42 +158,44 @@ static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspec
 
 /* Unary/Binary op chain, TransformDPP::operate (data_parallel_patterns.cuh:66-79);
  * Mul/Sub/Div/Add arithmetic.cuh:43-68; VectorReorder cuda_vector.cuh:45-54. */
-static void apply_chain(const cvgs_pipeline_t* p, float v[3]) {
+static void apply_chain(const cvgs_pipeline_t* p, float v[4]) {
+    const int nc = n_channels(p->src_type);
     if (p->interp_mode == CVGS_INTERP_ROUND_U8)
-        for (int c = 0; c < 3; ++c) v[c] = round_sat_src(v[c], p->src_type);
+        for (int c = 0; c < nc; ++c) v[c] = round_sat_src(v[c], p->src_type);
     for (int i = 0; i < p->n_ops; ++i) {
         const cvgs_op_t* op = &p->ops[i];
         /* nvcc contracts (x*m) -/+ s of the inlined chain into one FMA; a channel reorder in
          * between is only register renaming and does not prevent it. */
         if (op->kind == CVGS_OP_MUL && p->fp_contract == CVGS_FP_REFERENCE_FUSED) {
             int j = i + 1;
-            int perm[3] = {0, 1, 2};
+            int perm[4] = {0, 1, 2, 3};
             while (j < p->n_ops && p->ops[j].kind == CVGS_OP_REORDER) {
-                int np[3];
-                for (int c = 0; c < 3; ++c) np[c] = perm[p->ops[j].perm[c]];
+                int np[4];
+                for (int c = 0; c < nc; ++c) np[c] = perm[p->ops[j].perm[c]];
                 memcpy(perm, np, sizeof perm);
                 ++j;
             }
             if (j < p->n_ops && (p->ops[j].kind == CVGS_OP_SUB || p->ops[j].kind == CVGS_OP_ADD)) {
-                float t[3];
-                for (int c = 0; c < 3; ++c) {
+                float t[4];
+                for (int c = 0; c < nc; ++c) {
                     const int s = perm[c];
                     const float a = p->ops[j].kind == CVGS_OP_SUB ? -p->ops[j].v[c] : p->ops[j].v[c];
                     t[c] = fmaf(v[s], op->v[s], a);
                 }
-                memcpy(v, t, sizeof t);
+                memcpy(v, t, (size_t)nc * sizeof(float));
                 i = j;
                 continue;
             }
         }
         switch (op->kind) {
-            case CVGS_OP_MUL: for (int c = 0; c < 3; ++c) v[c] = v[c] * op->v[c]; break;
-            case CVGS_OP_SUB: for (int c = 0; c < 3; ++c) v[c] = v[c] - op->v[c]; break;
-            case CVGS_OP_DIV: for (int c = 0; c < 3; ++c) v[c] = v[c] / op->v[c]; break;
-            case CVGS_OP_ADD: for (int c = 0; c < 3; ++c) v[c] = v[c] + op->v[c]; break;
+            case CVGS_OP_MUL: for (int c = 0; c < nc; ++c) v[c] = v[c] * op->v[c]; break;
+            case CVGS_OP_SUB: for (int c = 0; c < nc; ++c) v[c] = v[c] - op->v[c]; break;
+            case CVGS_OP_DIV: for (int c = 0; c < nc; ++c) v[c] = v[c] / op->v[c]; break;
+            case CVGS_OP_ADD: for (int c = 0; c < nc; ++c) v[c] = v[c] + op->v[c]; break;
             case CVGS_OP_REORDER: {
-                const float t[3] = {v[op->perm[0]], v[op->perm[1]], v[op->perm[2]]};
-                memcpy(v, t, sizeof t);
+                float t[4];
+                for (int c = 0; c < nc; ++c) t[c] = v[op->perm[c]];
+                memcpy(v, t, (size_t)nc * sizeof(float));
                 break;
             }
             default: break;
@@ -196,8 +205,9 @@ static void apply_chain(const cvgs_pipeline_t* p, float v[3]) {
 
 /* Output addressing: TensorSplit memory_operations.cuh:168-188 + PtrAccessor<_3D> ptr_nd.cuh:53-63;
  * TensorTSplit :197-220 + PtrAccessor<T3D> ptr_nd.cuh:65-77; PerThreadWrite<_3D>. */
-static void store_pixel(const cvgs_pipeline_t* p, int n_planes, int z, int y, int x, const float v[3]) {
+static void store_pixel(const cvgs_pipeline_t* p, int n_planes, int z, int y, int x, const float v[4]) {
     float* out = (float*)p->out;
+    const int nc = n_channels(p->src_type);
     const int64_t W = p->dst_width, H = p->dst_height;
     if (p->dst_type == CVGS_8UC3) { /* convertTo<CV_32FC3, CV_8UC3> + PerThreadWrite: SaturateCast saturate.cuh:127-147 */
         const int64_t rp = p->out_row_pitch ? p->out_row_pitch : 3 * W;
@@ -208,27 +218,27 @@ static void store_pixel(const cvgs_pipeline_t* p, int n_planes, int z, int y, in
     }
     switch (p->out_layout) {
         case CVGS_OUT_NCHW: {
-            const int64_t ps = p->out_plane_stride ? p->out_plane_stride : 3 * W * H;
+            const int64_t ps = p->out_plane_stride ? p->out_plane_stride : nc * W * H;
             float* b = out + z * ps + y * W + x;
-            b[0] = v[0]; b[W * H] = v[1]; b[2 * W * H] = v[2];
+            for (int c = 0; c < nc; ++c) b[c * W * H] = v[c];
             break;
         }
         case CVGS_OUT_CNHW: {
             const int64_t ps = p->out_plane_stride ? p->out_plane_stride : W * H;
             float* b = out + z * ps + y * W + x;
-            b[0] = v[0]; b[ps * n_planes] = v[1]; b[2 * ps * n_planes] = v[2];
+            for (int c = 0; c < nc; ++c) b[c * ps * n_planes] = v[c];
             break;
         }
         case CVGS_OUT_PLANES: { /* SplitWrite memory_operations.cuh:331-360: one RawPtr<_2D,float> per channel */
-            const cvgs_plane_t* pl = (const cvgs_plane_t*)p->out + (int64_t)z * 3;
-            for (int c = 0; c < 3; ++c)
+            const cvgs_plane_t* pl = (const cvgs_plane_t*)p->out + (int64_t)z * nc;
+            for (int c = 0; c < nc; ++c)
                 *(float*)((char*)pl[c].data + (int64_t)y * pl[c].pitch_bytes + (int64_t)x * 4) = v[c];
             break;
         }
         default: {
-            const int64_t ps = p->out_plane_stride ? p->out_plane_stride : 3 * W * H;
-            float* b = out + z * ps + (y * W + x) * 3;
-            b[0] = v[0]; b[1] = v[1]; b[2] = v[2];
+            const int64_t ps = p->out_plane_stride ? p->out_plane_stride : nc * W * H;
+            float* b = out + z * ps + (y * W + x) * nc;
+            for (int c = 0; c < nc; ++c) b[c] = v[c];
         }
     }
 }
@@ -239,7 +249,8 @@ static void store_pixel(const cvgs_pipeline_t* p, int n_planes, int z, int y, in
 int oracle_preproc(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_pipeline_t* p,
                    int nthreads) {
     if (!crops || !p || !p->out || n_planes <= 0 || used < 0 ||
-        (p->src_type != CVGS_8UC3 && p->src_type != CVGS_16UC3 && p->src_type != CVGS_16SC3) ||
+        (p->src_type != CVGS_8UC3 && p->src_type != CVGS_16UC3 && p->src_type != CVGS_16SC3 &&
+         p->src_type != CVGS_8UC4 && p->src_type != CVGS_16UC4 && p->src_type != CVGS_16SC4) ||
         p->dst_width <= 0 || p->dst_height <= 0 || p->n_ops < 0 || p->n_ops > CVGS_MAX_OPS)
         return 1;
     if (used > n_planes) used = n_planes;
@@ -256,9 +267,9 @@ int oracle_preproc(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_
     for (long row = 0; row < total_rows; ++row) {
         const int z = (int)(row / H), y = (int)(row % H);
         for (int x = 0; x < W; ++x) {
-            float v[3];
+            float v[4];
             if (z >= used) {
-                v[0] = p->background[0]; v[1] = p->background[1]; v[2] = p->background[2];
+                v[0] = p->background[0]; v[1] = p->background[1]; v[2] = p->background[2]; v[3] = p->background[3];
             } else {
                 resize_pixel(&crops[z], &geoms[z], p->aspect_mode, p->src_type, x, y, p->background, v);
             }

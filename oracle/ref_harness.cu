@@ -48,21 +48,34 @@ int run_chain(const void* const* ptrs, const int* ws, const int* hs, const int* 
         crops[i] = fk::RawPtr<fk::_2D, PixelT>{ (PixelT*)ptrs[j],
             { (uint)ws[j], (uint)hs[j], (uint)pitches[j] } };
     }
+    constexpr int CN = fk::cn<PixelT>;
+    using FloatT = fk::VectorType_t<float, CN>;
     const fk::Size dsize{ dst_w, dst_h };
-    const float3 bgv{ bg[0], bg[1], bg[2] };
+    FloatT bgv, mulv, subv, divv;
+    bgv.x = bg[0]; bgv.y = bg[1]; bgv.z = bg[2];
+    mulv.x = mul[0]; mulv.y = mul[1]; mulv.z = mul[2];
+    subv.x = sub[0]; subv.y = sub[1]; subv.z = sub[2];
+    divv.x = div[0]; divv.y = div[1]; divv.z = div[2];
+    if constexpr (CN == 4) { bgv.w = bg[3]; mulv.w = mul[3]; subv.w = sub[3]; divv.w = div[3]; }
     const auto readOP = PixelReadOp::build_batch(crops);
     const auto sizeArr = fk::make_set_std_array<BATCH>(dsize);
     using Resize = fk::Resize<fk::INTER_LINEAR, AR, fk::Read<PixelReadOp>>;
-    const fk::Tensor<float> t_out(out, dst_w, dst_h, BATCH, 3);
-    const auto mulOp = fk::Binary<fk::Mul<float3>>{ float3{mul[0], mul[1], mul[2]} };
-    const auto subOp = fk::Binary<fk::Sub<float3>>{ float3{sub[0], sub[1], sub[2]} };
-    const auto divOp = fk::Binary<fk::Div<float3>>{ float3{div[0], div[1], div[2]} };
-    const auto wrOp = fk::Write<fk::TensorSplit<float3>>{ t_out.ptr() };
+    const fk::Tensor<float> t_out(out, dst_w, dst_h, BATCH, CN);
+    const auto mulOp = fk::Binary<fk::Mul<FloatT>>{ mulv };
+    const auto subOp = fk::Binary<fk::Sub<FloatT>>{ subv };
+    const auto divOp = fk::Binary<fk::Div<FloatT>>{ divv };
+    const auto wrOp = fk::Write<fk::TensorSplit<FloatT>>{ t_out.ptr() };
     auto launch = [&](const auto& resizeOp) {
         if constexpr (SWAP) {
-            fk::executeOperations(stream, resizeOp,
-                fk::Unary<fk::ColorConversion<fk::COLOR_RGB2BGR, float3, float3>>{},
-                mulOp, subOp, divOp, wrOp);
+            if constexpr (CN == 4) {
+                fk::executeOperations(stream, resizeOp,
+                    fk::Unary<fk::ColorConversion<fk::COLOR_RGBA2BGRA, float4, float4>>{},
+                    mulOp, subOp, divOp, wrOp);
+            } else {
+                fk::executeOperations(stream, resizeOp,
+                    fk::Unary<fk::ColorConversion<fk::COLOR_RGB2BGR, float3, float3>>{},
+                    mulOp, subOp, divOp, wrOp);
+            }
         } else {
             fk::executeOperations(stream, resizeOp, mulOp, subOp, divOp, wrOp);
         }
@@ -153,7 +166,17 @@ int FKREF_CAT(fkref_preproc16_, FKREF_BATCH)(int pixel_type, const void* const* 
         if (pixel_type == 19)
             return dispatch<short3, FKREF_BATCH>(ptrs, ws, hs, pitches, used, dst_w, dst_h, aspect_mode, bg, swap_rb,
                                                  mul, sub, div, out, (cudaStream_t)stream);
-        g_err = "fkref: pixel type must be 18 (CV_16UC3) or 19 (CV_16SC3)";
+        // 4-channel sources: bg / mul / sub / div hold four values, `out` holds FKREF_BATCH x 4 planes
+        if (pixel_type == 24)
+            return dispatch<uchar4, FKREF_BATCH>(ptrs, ws, hs, pitches, used, dst_w, dst_h, aspect_mode, bg, swap_rb,
+                                                 mul, sub, div, out, (cudaStream_t)stream);
+        if (pixel_type == 26)
+            return dispatch<ushort4, FKREF_BATCH>(ptrs, ws, hs, pitches, used, dst_w, dst_h, aspect_mode, bg, swap_rb,
+                                                  mul, sub, div, out, (cudaStream_t)stream);
+        if (pixel_type == 27)
+            return dispatch<short4, FKREF_BATCH>(ptrs, ws, hs, pitches, used, dst_w, dst_h, aspect_mode, bg, swap_rb,
+                                                 mul, sub, div, out, (cudaStream_t)stream);
+        g_err = "fkref: pixel type must be a 16-bit 3-channel or any 4-channel OpenCV type code";
         return -1;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -27,11 +27,11 @@ def run_cvgs(image, rects, dsize, ops, n_planes=None, used=None, variant=0, fill
     used = len(rects) if used is None else used
     layout = pipe_kw.get("layout", _abi.OUT_NCHW)
     d_img = device_image(image) if d_image is None else d_image
-    shape = util.out_shape(n_planes, dsize, layout, pipe_kw.get("plane_stride", 0))
+    st = pipe_kw.get("src_type", _abi.CVGS_8UC3)
+    shape = util.out_shape(n_planes, dsize, layout, pipe_kw.get("plane_stride", 0), util.channels_of(st))
     d_out = torch.full(shape, fill, dtype=torch.float32, device="cuda")
     p = util.make_pipeline(dsize, ops, out_ptr=d_out.data_ptr(), **pipe_kw)
-    crops = util.host_crops(image, rects[:used], base_ptr=d_img.data_ptr(),
-                            px_bytes=3 if pipe_kw.get("src_type", _abi.CVGS_8UC3) == _abi.CVGS_8UC3 else 6)
+    crops = util.host_crops(image, rects[:used], base_ptr=d_img.data_ptr(), px_bytes=util.px_bytes_of(st))
     prev = lib.cvgs_b200_set_kernel_variant(variant)
     try:
         if parents is None:
@@ -86,15 +86,17 @@ def run_fkref(image, rects, dsize, swap, mul, sub, div, aspect=_abi.IGNORE_AR, b
     used = len(rects) if used is None else used
     assert used <= batch
     d_img = device_image(image) if d_image is None else d_image
-    d_out = torch.full((batch, 3, dsize[1], dsize[0]), float("nan"), dtype=torch.float32, device="cuda")
-    f3 = lambda v: (C.c_float * 3)(*v)  # noqa: E731
-    if src_type != _abi.CVGS_8UC3:  # 16-bit instantiations exist in the BATCH=16 library only
+    d_out = torch.full((batch, util.channels_of(src_type), dsize[1], dsize[0]), float("nan"), dtype=torch.float32,
+                       device="cuda")
+    f3 = lambda v: (C.c_float * 4)(*(tuple(v) + (0.0,) * (4 - len(v))))  # noqa: E731
+    if src_type != _abi.CVGS_8UC3:  # 16-bit and 4-channel instantiations exist in the BATCH=16 library only
         fn16 = getattr(C.CDLL(os.path.join(ROOT, "oracle", "_ref", f"libfkref_{batch}.so")), f"fkref_preproc16_{batch}")
         fn16.restype = C.c_int
         fn16.argtypes = [C.c_int] + fn.argtypes
         pitch = image.shape[1]
         n = max(1, used)
-        ptrs = (C.c_void_p * n)(*[d_img.data_ptr() + y * pitch + 6 * x for (x, y, w, h) in rects[:used]])
+        pb = util.px_bytes_of(src_type)
+        ptrs = (C.c_void_p * n)(*[d_img.data_ptr() + y * pitch + pb * x for (x, y, w, h) in rects[:used]])
         _, ws, hs, ps = fkref_args(d_img.data_ptr(), pitch, rects, used)
         rc = fn16(src_type, ptrs, ws, hs, ps, used, dsize[0], dsize[1], aspect, f3(bg), int(swap), f3(mul), f3(sub), f3(div),
                   d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)

@@ -162,14 +162,17 @@ def test_oracle_split_write_equals_tensor_split():
             assert np.isnan(bufs[z][c][:, W:]).all()
 
 
-@pytest.mark.parametrize("src_type,dtype", [(_abi.CVGS_16UC3, np.uint16), (_abi.CVGS_16SC3, np.int16)])
-def test_oracle_16bit_sources_equal_numpy(src_type, dtype):
+@pytest.mark.parametrize("src_type,dtype,nc", [(_abi.CVGS_16UC3, np.uint16, 3), (_abi.CVGS_16SC3, np.int16, 3),
+                                               (_abi.CVGS_8UC4, np.uint8, 4), (_abi.CVGS_16UC4, np.uint16, 4),
+                                               (_abi.CVGS_16SC4, np.int16, 4)])
+def test_oracle_16bit_sources_equal_numpy(src_type, dtype, nc):
     """ushort3 / short3 sources: same index math and rounding order on exactly converted taps (independent numpy
     restatement of interpolation.cuh:57-92 with float32 arithmetic and explicit fma emulation in float64)."""
     rng = np.random.default_rng(12)
     w, h, W, H = 37, 29, 16, 24
-    img = rng.integers(0, 256, size=(h, 6 * w + 10), dtype=np.uint8)
-    px = img[:, :6 * w].copy().view(dtype).reshape(h, w, 3).astype(np.float32)
+    pb = nc * np.dtype(dtype).itemsize
+    img = rng.integers(0, 256, size=(h, pb * w + 10), dtype=np.uint8)
+    px = img[:, :pb * w].copy().view(dtype).reshape(h, w, nc).astype(np.float32)
     out = util.run_oracle(img, [(0, 0, w, h)], (W, H), [], src_type=src_type)[0]
     fx, fy = np.float32(1.0 / (W / w)), np.float32(1.0 / (H / h))
 
@@ -183,7 +186,7 @@ def test_oracle_16bit_sources_equal_numpy(src_type, dtype):
             wx1, wx0 = sx - np.float32(x1), np.float32(x1 + 1) - sx
             wy1, wy0 = sy - np.float32(y1), np.float32(y1 + 1) - sy
             w00, w10, w01, w11 = wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1
-            for c in range(3):
+            for c in range(nc):
                 t = px[y1, x2r, c] * w10
                 t = fma(px[y1, x1, c], w00, t)
                 t = fma(px[y2r, x1, c], w01, t)

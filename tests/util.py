@@ -140,12 +140,12 @@ def make_pipeline(dsize, ops, aspect=_abi.IGNORE_AR, background=(0, 0, 0), fp_co
     p.src_type = src_type
     p.dst_width, p.dst_height = dsize
     p.aspect_mode, p.interp_mode, p.fp_contract = aspect, interp_mode, fp_contract
-    for c in range(3):
+    for c in range(len(background)):
         p.background[c] = background[c]
     p.n_ops = len(ops)
     for i, (k, v) in enumerate(ops):
         p.ops[i].kind = _KIND[k]
-        for c in range(3):
+        for c in range(len(v)):
             if k == "reorder":
                 p.ops[i].perm[c] = v[c]
             else:
@@ -155,17 +155,25 @@ def make_pipeline(dsize, ops, aspect=_abi.IGNORE_AR, background=(0, 0, 0), fp_co
     return p
 
 
-def out_shape(n_planes, dsize, layout, plane_stride=0):
+def px_bytes_of(src_type) -> int:
+    return {_abi.CVGS_8UC3: 3, _abi.CVGS_8UC4: 4, _abi.CVGS_16UC3: 6, _abi.CVGS_16SC3: 6}.get(src_type, 8)
+
+
+def channels_of(src_type) -> int:
+    return 4 if src_type in (_abi.CVGS_8UC4, _abi.CVGS_16UC4, _abi.CVGS_16SC4) else 3
+
+
+def out_shape(n_planes, dsize, layout, plane_stride=0, nc=3):
     W, H = dsize
     if plane_stride:
         if layout == _abi.OUT_CNHW:
-            return (3, n_planes, plane_stride)
+            return (nc, n_planes, plane_stride)
         return (n_planes, plane_stride)
     if layout == _abi.OUT_NCHW:
-        return (n_planes, 3, H, W)
+        return (n_planes, nc, H, W)
     if layout == _abi.OUT_CNHW:
-        return (3, n_planes, H, W)
-    return (n_planes, H, W, 3)
+        return (nc, n_planes, H, W)
+    return (n_planes, H, W, nc)
 
 
 def host_crops(image: np.ndarray, rects: Sequence[Rect], base_ptr: int | None = None, px_bytes: int = 3):
@@ -194,9 +202,10 @@ def run_oracle(image, rects, dsize, ops, n_planes=None, used=None, nthreads=0, f
     n_planes = len(rects) if n_planes is None else n_planes
     used = len(rects) if used is None else used
     layout = pipe_kw.get("layout", _abi.OUT_NCHW)
-    out = np.full(out_shape(n_planes, dsize, layout, pipe_kw.get("plane_stride", 0)), fill, dtype=np.float32)
+    st = pipe_kw.get("src_type", _abi.CVGS_8UC3)
+    out = np.full(out_shape(n_planes, dsize, layout, pipe_kw.get("plane_stride", 0), channels_of(st)), fill, dtype=np.float32)
     p = make_pipeline(dsize, ops, out_ptr=out.ctypes.data, **pipe_kw)
-    crops = host_crops(image, rects[:used], px_bytes=3 if pipe_kw.get("src_type", _abi.CVGS_8UC3) == _abi.CVGS_8UC3 else 6)
+    crops = host_crops(image, rects[:used], px_bytes=px_bytes_of(st))
     rc = lib.oracle_preproc(crops, n_planes, used, C.byref(p), nthreads)
     assert rc == 0, "oracle rejected the arguments"
     return out
