@@ -79,6 +79,9 @@ SYMBOLS = {
     "cvgs_b200_set_overlap": (C.c_int, [C.c_int]),
     "cvgs_b200_launch_count": (C.c_int64, []),
     "cvgs_b200_debug_host_profile": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
+    "cvgs_b200_debug_plan": (C.c_int, [C.POINTER(Crop), C.c_int32, C.c_int32, C.POINTER(Pipeline), C.c_int32, C.c_int32,
+                                       C.c_int32, C.POINTER(C.c_int64)]),
+    "cvgs_b200_debug_overlap_query": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "cvgs_b200_debug_division_sweep": (C.c_int, [C.c_float, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint),
                                                  C.POINTER(C.c_float)]),
     "cvgs_b200_ct_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

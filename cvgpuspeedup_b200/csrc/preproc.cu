@@ -587,6 +587,52 @@ const char* cvgs_b200_last_error(void) { return t_last_error.c_str(); }
 int cvgs_b200_set_kernel_variant(int variant) { return g_variant.exchange(variant); }
 int cvgs_b200_set_overlap(int enable) { return g_overlap.exchange(enable ? 1 : 0); }
 int64_t cvgs_b200_launch_count(void) { return t_launch_count; }
+// Diagnostics for the CPU test-suite: the launch plan of the TMA kernel for a batch geometry (no device needed).
+// out[0..11] = {ok, NPB, HP, tiles_x, total_items, slot_bytes, slots, resident, grid, max row bytes needed,
+//               items covered by the per-warp ranges, 1 if the ranges tile [0, total_items) in order without gaps}
+int cvgs_b200_debug_plan(const cvgs_crop_t* crops, int32_t n_planes, int32_t used, const cvgs_pipeline_t* pipeline,
+                         int32_t sm_count, int32_t image_mode, int32_t items_per_warp_, int64_t* out12) {
+    if (!pipeline || !out12) return fail(CVGS_ERR_INVALID_VALUE, "NULL argument");
+    if (int rc = validate_pipeline(pipeline)) return rc;
+    for (int i = 0; i < 12; ++i) out12[i] = 0;
+    PreprocParams P;
+    static float dummy_out;
+    if (int rc = build_params(*pipeline, n_planes, used, &dummy_out, P)) return rc;
+    std::vector<DevCrop> dc(static_cast<size_t>(std::max(used, 1)));
+    int rb_need = 0;
+    for (int i = 0; i < used; ++i)
+        if (int rc = fill_crop(crops[i], *pipeline, i, dc[i])) return rc;
+    TmaGeom G{};
+    if (!tma_plan(P, dc.data(), used, n_planes, sm_count, image_mode != 0, std::max(1, items_per_warp_), G, false)) return CVGS_OK;
+    for (int i = 0; i < used; ++i) {
+        int rb = band_row_bytes(std::min(32 * G.NPB, P.W), dc[i].fx);
+        if (image_mode) rb = rb_class(rb);
+        rb_need = std::max(rb_need, rb);
+    }
+    long long covered = 0, expect_first = 0;
+    bool tiled = true;
+    for (int g = 0; g < G.grid * kWarps; ++g) {
+        long long first, count;
+        host_item_range(G, g, first, count);
+        if (first != expect_first || count < 0) tiled = false;
+        expect_first = first + count;
+        covered += count;
+    }
+    const int64_t vals[12] = {1, G.NPB, G.HP, G.tiles_x, G.total_items, G.slot_bytes, G.slots, G.resident, G.grid, rb_need,
+                              covered, tiled && expect_first == G.total_items ? 1 : 0};
+    for (int i = 0; i < 12; ++i) out12[i] = vals[i];
+    return CVGS_OK;
+}
+
+// Diagnostics for the CPU test-suite: the overlap bookkeeping (pure host logic).  Returns 1 when a launch with these
+// output / source byte ranges on `stream_key` would have to wait for its predecessor, 0 when it may overlap.
+int cvgs_b200_debug_overlap_query(void* stream_key, uint64_t out_lo, uint64_t out_hi, uint64_t src_lo, uint64_t src_hi) {
+    MemRange o, s;
+    o.lo = static_cast<uintptr_t>(out_lo); o.hi = static_cast<uintptr_t>(out_hi);
+    s.lo = static_cast<uintptr_t>(src_lo); s.hi = static_cast<uintptr_t>(src_hi);
+    return overlap_needs_wait(static_cast<cudaStream_t>(stream_key), o, s) ? 1 : 0;
+}
+
 int cvgs_b200_debug_host_profile(double* out5, int reset) {
     if (out5) {
         out5[0] = static_cast<double>(t_prof.calls);

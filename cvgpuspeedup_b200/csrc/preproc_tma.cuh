@@ -698,6 +698,23 @@ inline int band_row_bytes(int TW, float fx) {
     return static_cast<int>((bytes + 63) / 64 * 64);
 }
 
+// Host mirror of ItemCursor::init (same integer arithmetic): first item and item count of warp g.
+inline void host_item_range(const TmaGeom& G, int g, long long& first, long long& count) {
+    auto item_at = [&](uint32_t w) -> long long {
+        const uint32_t z = w / static_cast<uint32_t>(G.w_crop);
+        const uint32_t r = w - z * static_cast<uint32_t>(G.w_crop);
+        const uint32_t in_crop = r < static_cast<uint32_t>(G.w_full)
+                                     ? r / static_cast<uint32_t>(G.NPB)
+                                     : static_cast<uint32_t>((G.tiles_x - 1) * G.HP) + (r - static_cast<uint32_t>(G.w_full)) / static_cast<uint32_t>(G.np_last);
+        return static_cast<long long>(z) * G.items_per_crop + in_crop;
+    };
+    const uint32_t w0 = static_cast<uint32_t>(g) * static_cast<uint32_t>(G.share_q) + static_cast<uint32_t>(std::min(g, G.share_r));
+    const uint32_t w1 = w0 + static_cast<uint32_t>(G.share_q) + (g < G.share_r ? 1u : 0u);
+    first = item_at(w0);
+    const long long last = g + 1 == G.grid * kWarps ? static_cast<long long>(G.total_items) : item_at(w1);
+    count = last - first;
+}
+
 // Staged row bytes are rounded up to a few classes so that crops of one image share tensor maps.
 inline int rb_class(int rb) {
     static const int cls[] = {128, 192, 256, 384, 512, 640, 768, 896, 1024, 1280, 1408, 1536, 1664, 1792, 1920, 2048};
@@ -708,8 +725,8 @@ inline int rb_class(int rb) {
 
 // Can this launch take the TMA kernel, and with which geometry?  crops = host copies of the DevCrops.
 inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int n_planes, int sm_count, bool image_mode,
-                     int items_per_warp, TmaGeom& G) {
-    if (!encode_tiled_fn()) return false;
+                     int items_per_warp, TmaGeom& G, bool need_driver = true) {
+    if (need_driver && !encode_tiled_fn()) return false;
     if (P.src_type != CVGS_8UC3) return false;  // the byte-level tap extraction is written for 3-byte pixels
     if (P.out.u8) return false;                 // 8-bit destinations are written by the direct-gather kernel
     float fx_max = 0.f;

@@ -239,6 +239,15 @@ int64_t cvgs_b200_launch_count(void);
 /* Diagnostics: host-side cost of the small-batch TMA launch path on the calling thread, accumulated in
  * microseconds: out5 = {calls, descriptor fill, planning, tensor-map encoding, kernel launch}. */
 int cvgs_b200_debug_host_profile(double* out5, int reset);
+/* Diagnostics (no device needed): the launch plan the TMA-staged kernel would get for this batch geometry on a GPU
+ * with sm_count SMs.  out12 = {plan exists, 32-column groups per band, row pairs per plane, bands per plane, work
+ * items, bytes per staging slot, slots per warp, CTAs per SM, grid, staged row bytes needed, items covered by the
+ * per-warp ranges, 1 if those ranges tile [0, items) in order}.  crops need valid sizes and pitches only. */
+int cvgs_b200_debug_plan(const cvgs_crop_t* crops, int32_t n_planes, int32_t used, const cvgs_pipeline_t* pipeline,
+                         int32_t sm_count, int32_t image_mode, int32_t items_per_warp, int64_t* out12);
+/* Diagnostics (no device needed): would a launch with these output / source byte ranges on the stream identified by
+ * stream_key have to wait for its predecessor (1) or may it overlap (0)?  Updates the bookkeeping like a launch. */
+int cvgs_b200_debug_overlap_query(void* stream_key, uint64_t out_lo, uint64_t out_hi, uint64_t src_lo, uint64_t src_hi);
 /* Diagnostics: on the current device, compare the kernels' two-operation division by a launch constant with IEEE
  * division for every float x with 2^-73 <= |x| < 2^48 and the divisor d; *mismatches = differing results,
  * *reciprocal_used = RN(1/d), or 0 when the host-side proof rejects d (the kernels then use IEEE division). */
