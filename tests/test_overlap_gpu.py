@@ -134,3 +134,43 @@ def test_launches_are_graph_capturable(overlap):
                 util.assert_bit_equal(o.cpu().numpy(), util.run_oracle(w.image, w.rects, w.dsize, w.ops), f"replay {rep}")
     finally:
         lib.cvgs_b200_set_overlap(prev)
+
+
+def test_concurrent_host_threads():
+    """Four host threads launching on their own streams at the same time (ctypes releases the GIL): per-thread
+    contexts (descriptor ring, tensor-map cache, memos) and the shared bookkeeping must not interfere."""
+    import threading
+    lib = _abi.load()
+    prev = lib.cvgs_b200_set_overlap(1)
+    errors = []
+
+    def worker(k):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream()
+            small = util.workload_c2(seed=400 + k, n=30, frame=(640, 480), pitch=1920)
+            big = util.workload_c2(seed=500 + k, n=100, frame=(640, 480), pitch=1920)   # > 64 crops: 256-crop table
+            ring = util.workload_c2(seed=600 + k, n=300, frame=(640, 480), pitch=1920)  # > 256 crops: descriptor ring
+            for w in (small, big, ring):
+                w.dsize = (32, 48)
+            ds = [torch.from_numpy(w.image).cuda() for w in (small, big, ring)]
+            wants = [util.run_oracle(w.image, w.rects, w.dsize, w.ops) for w in (small, big, ring)]
+            for rep in range(15):
+                outs, keep = [], []
+                for w, d in zip((small, big, ring), ds):
+                    o = torch.full((len(w.rects), 3, 48, 32), float("nan"), device="cuda")
+                    keep.append(_launch(lib, w, d, o, st))
+                    outs.append(o)
+                st.synchronize()
+                for o, want in zip(outs, wants):
+                    util.assert_bit_equal(o.cpu().numpy(), want, f"thread {k} rep {rep}")
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"thread {k}: {e}")
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    lib.cvgs_b200_set_overlap(prev)
+    assert not errors, errors
