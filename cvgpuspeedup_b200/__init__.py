@@ -6,4 +6,5 @@ this package is the thin host-side mirror of ``namespace cvGS`` used by the test
 from . import _abi  # noqa: F401
 from .api import *  # noqa: F401,F403
 from .api import (CircularTensor, GpuMat, add, build_pipeline, convertTo, cvtColor, divide,  # noqa: F401
-                  executeOperations, make_crops, multiply, resize, split, split_planes, splitT, subtract, write)
+                  executeOperations, make_crops, multiply, resize, resize_nv12, split, split_planes, splitT, subtract,
+                  write)

@@ -17,6 +17,8 @@ MAX_OPS = 8
 # enums (include/cvgs_b200.h)
 CVGS_8UC3, CVGS_16UC3, CVGS_16SC3, CVGS_32FC3 = 16, 18, 19, 21
 CVGS_8UC4, CVGS_16UC4, CVGS_16SC4, CVGS_32FC4 = 24, 26, 27, 29
+CVGS_NV12 = 0x1001
+YUV_BT601_FULL, YUV_BT709_FULL, YUV_BT709_LIMITED, YUV_BT2020_FULL = 0, 1, 2, 3
 PRESERVE_AR, IGNORE_AR, PRESERVE_AR_RN_EVEN, PRESERVE_AR_LEFT = 0, 1, 2, 3
 OP_MUL, OP_SUB, OP_DIV, OP_ADD, OP_REORDER = 1, 2, 3, 4, 5
 FP_REFERENCE_FUSED, FP_SEPARATE = 0, 1
@@ -40,7 +42,8 @@ class Pipeline(C.Structure):
                 ("aspect_mode", C.c_int32), ("interp_mode", C.c_int32), ("fp_contract", C.c_int32),
                 ("background", C.c_float * 4), ("n_ops", C.c_int32), ("ops", Op * MAX_OPS),
                 ("out_layout", C.c_int32), ("dst_type", C.c_int32), ("out", C.c_void_p),
-                ("out_plane_stride", C.c_int64), ("out_row_pitch", C.c_int64)]
+                ("out_plane_stride", C.c_int64), ("out_row_pitch", C.c_int64), ("yuv_standard", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Parent(C.Structure):

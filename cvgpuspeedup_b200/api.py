@@ -78,6 +78,7 @@ class _Resize:
     background: Tuple[float, float, float]
     aspect: int
     src_type: int = _abi.CVGS_8UC3
+    yuv_standard: int = 0
 
 
 @dataclass
@@ -103,6 +104,17 @@ def resize(crops: Sequence[GpuMat], dsize: Tuple[int, int], usedPlanes: Optional
     crops = list(crops)
     return _Resize(crops, (int(dsize[0]), int(dsize[1])), len(crops) if usedPlanes is None else int(usedPlanes),
                    _scalar3(backgroundValue), int(aspect), int(src_type))
+
+
+def resize_nv12(frames: Sequence[GpuMat], dsize: Tuple[int, int], standard: int = _abi.YUV_BT709_FULL,
+                usedPlanes: Optional[int] = None, backgroundValue=(0.0, 0.0, 0.0), aspect: int = IGNORE_AR) -> _Resize:
+    """fk::Resize<INTER_LINEAR>::build(fk::fuse(Read<ReadYUV<NV12>>, Unary<ConvertYUVToRGB<NV12, range, primaries, false,
+    float3>>), dsize) for a batch of NV12 frames (reference color_conversion.cuh:235-362, tests/resize/
+    test_fused_resize.cu:73-76).  Each GpuMat describes the luma plane (cols x rows, step); the interleaved UV plane
+    follows it at data + step * rows.  The chain after it sees float RGB."""
+    r = resize(frames, dsize, usedPlanes, backgroundValue, aspect, _abi.CVGS_NV12)
+    r.yuv_standard = int(standard)
+    return r
 
 
 def multiply(s) -> _Op:   # cvGS::multiply<CV_32FC3>(Scalar) :131
@@ -189,9 +201,10 @@ def _flatten(ops):
 
 def build_pipeline(dsize, ops: Sequence[_Op], background=(0, 0, 0), aspect=IGNORE_AR,
                    fp_contract=FP_REFERENCE_FUSED, interp_mode=INTERP_FLOAT, out_ptr=0, layout=OUT_NCHW,
-                   plane_stride=0, src_type=_abi.CVGS_8UC3) -> _abi.Pipeline:
+                   plane_stride=0, src_type=_abi.CVGS_8UC3, yuv_standard=0) -> _abi.Pipeline:
     p = _abi.Pipeline()
     p.src_type = int(src_type)
+    p.yuv_standard = int(yuv_standard)
     p.dst_width, p.dst_height = int(dsize[0]), int(dsize[1])
     p.aspect_mode, p.interp_mode, p.fp_contract = int(aspect), int(interp_mode), int(fp_contract)
     bg = _scalar3(background)
@@ -227,12 +240,15 @@ def executeOperations(stream, *iops, fp_contract: int = FP_REFERENCE_FUSED, inte
     if any(not isinstance(o, _Op) for o in mid):
         raise CvgsError("only multiply/subtract/divide/add/convertTo/cvtColor may sit between read and write")
     p = build_pipeline(rs.dsize, mid, rs.background, rs.aspect, fp_contract, interp_mode, wr.out_ptr, wr.layout,
-                       wr.plane_stride, rs.src_type)
+                       wr.plane_stride, rs.src_type, rs.yuv_standard)
     crops = make_crops(rs.crops[:rs.used])
     parents = (_abi.Parent * max(1, rs.used))()
     for i, m in enumerate(rs.crops[:rs.used]):
         parents[i].datastart, parents[i].whole_width, parents[i].whole_height = m.datastart, m.whole[0], m.whole[1]
     lib = _abi.load()
+    if rs.src_type == _abi.CVGS_NV12:  # whole frames: nothing to say about parents
+        _abi.check(lib.cvgs_b200_preproc_launch(crops, len(rs.crops), rs.used, C.byref(p), _stream_ptr(stream)))
+        return
     _abi.check(lib.cvgs_b200_preproc_launch_ex(crops, parents, len(rs.crops), rs.used, C.byref(p), _stream_ptr(stream)))
 
 

@@ -62,6 +62,43 @@ __device__ __forceinline__ void gather_quad16(const PreprocParams& P, const DevC
     }
 }
 
+// One source pixel of an NV12 frame as float RGB: fk::ReadYUV<NV12> + fk::ConvertYUVToRGB<NV12, ., ., false, float3>
+// (reference color_conversion.cuh:235-291,296-316).  Rounding sequence of the reference's SASS: per channel
+// FMUL(y * m0), FFMA(u, m1, .), FFMA(v, m2, .) -- zero coefficients included -- after y - 16 (bt601 only), u - 128, v - 128.
+__device__ __forceinline__ void nv12_px(const PreprocParams& P, const DevCrop& C, int x, int y, float (&rgb)[3]) {
+    const uint8_t* uvp = C.data + (size_t)C.pitch * (size_t)C.h + (size_t)(y >> 1) * (size_t)C.pitch + 2 * (size_t)(x >> 1);
+    const float yy = __fsub_rn((float)__ldg(C.data + (size_t)y * (size_t)C.pitch + x), P.yuv[9]);
+    const float u = __fsub_rn((float)__ldg(uvp), 128.0f), v = __fsub_rn((float)__ldg(uvp + 1), 128.0f);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float t = __fmul_rn(yy, P.yuv[3 * r]);
+        t = __fmaf_rn(u, P.yuv[3 * r + 1], t);
+        rgb[r] = __fmaf_rn(v, P.yuv[3 * r + 2], t);
+    }
+}
+__device__ __forceinline__ void gather_quad_nv12(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
+                                                 float (&v)[4][3]) {
+    const AxisTap ty_ = axis_tap(y - C.by1, C.fy);
+    const int y1 = ty_.i1, y2r = min(ty_.i1 + 1, C.h - 1);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int x = x0 + p;
+        if (p < nvalid && x >= C.bx1 && x <= C.bx2) {
+            const AxisTap tx_ = axis_tap(x - C.bx1, C.fx);
+            const int x1 = tx_.i1, x2r = min(tx_.i1 + 1, C.w - 1);
+            const float w00 = __fmul_rn(tx_.w0, ty_.w0), w10 = __fmul_rn(tx_.w1, ty_.w0);
+            const float w01 = __fmul_rn(tx_.w0, ty_.w1), w11 = __fmul_rn(tx_.w1, ty_.w1);
+            float p00[3], p10[3], p01[3], p11[3];
+            nv12_px(P, C, x1, y1, p00);
+            nv12_px(P, C, x2r, y1, p10);
+            nv12_px(P, C, x1, y2r, p01);
+            nv12_px(P, C, x2r, y2r, p11);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[p][c] = bilerp(p00[c], p10[c], p01[c], p11[c], w00, w10, w01, w11);
+        }
+    }
+}
+
 // 4-channel sources (CV_8UC4 / CV_16UC4 / CV_16SC4): same arithmetic on four channels.
 __device__ __forceinline__ void gather_quad(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
                                             float (&v)[4][4]) {
@@ -80,7 +117,8 @@ __device__ __forceinline__ void gather_quad(const PreprocParams& P, const DevCro
     if (!row_in) return;
     if (P.src_type != CVGS_8UC3) {
         if (P.src_type == CVGS_16UC3) gather_quad16<unsigned short, 3>(P, C, y, x0, nvalid, v);
-        else gather_quad16<short, 3>(P, C, y, x0, nvalid, v);
+        else if (P.src_type == CVGS_16SC3) gather_quad16<short, 3>(P, C, y, x0, nvalid, v);
+        else gather_quad_nv12(P, C, y, x0, nvalid, v);
         return;
     }
     const AxisTap ty_ = axis_tap(y - C.by1, C.fy);

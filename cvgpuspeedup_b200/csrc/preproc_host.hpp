@@ -55,8 +55,18 @@ inline void resize_geometry(int sw, int sh, int dw, int dh, int aspect, DevCrop&
 }
 
 inline int channels_of(int src_type) { return (src_type == CVGS_8UC4 || src_type == CVGS_16UC4 || src_type == CVGS_16SC4) ? 4 : 3; }
+// YCbCr -> RGB matrices of the reference (color_conversion.cuh:171-214), row-major, + luma offset
+inline void yuv_constants(int standard, float (&m)[10]) {
+    static const float k[4][10] = {
+        {1.164383562f, 0.f, 1.596026786f, 1.164383562f, -0.39176229f, -0.812967647f, 1.164383562f, 2.017232143f, 0.f, 16.f},
+        {1.f, 0.f, 1.5748f, 1.f, -0.1873f, -0.4681f, 1.f, 1.8556f, 0.f, 0.f},
+        {1.f, 0.f, 1.402f, 1.f, -0.34414f, -0.71414f, 1.f, 1.772f, 0.f, 0.f},
+        {1.f, 0.f, 1.4746f, 1.f, -0.16455312684366f, -0.57135312684366f, 1.f, 1.8814f, 0.f, 0.f}};
+    for (int i = 0; i < 10; ++i) m[i] = k[standard][i];
+}
 inline int pixel_bytes_of(int src_type) {
     switch (src_type) {
+        case CVGS_NV12: return 1;  // luma plane
         case CVGS_8UC3: return 3;
         case CVGS_8UC4: return 4;
         case CVGS_16UC3: case CVGS_16SC3: return 6;
@@ -116,8 +126,10 @@ inline int build_program(const cvgs_pipeline_t& p, DevProgram& prog) {
 inline int validate_pipeline(const cvgs_pipeline_t* p) {
     if (!p) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
     if (p->src_type != CVGS_8UC3 && p->src_type != CVGS_16UC3 && p->src_type != CVGS_16SC3 && p->src_type != CVGS_8UC4 &&
-        p->src_type != CVGS_16UC4 && p->src_type != CVGS_16SC4)
-        return fail(CVGS_ERR_NOT_SUPPORTED, "sources must be CV_8U / CV_16U / CV_16S with 3 or 4 channels");
+        p->src_type != CVGS_16UC4 && p->src_type != CVGS_16SC4 && p->src_type != CVGS_NV12)
+        return fail(CVGS_ERR_NOT_SUPPORTED, "sources must be CV_8U / CV_16U / CV_16S with 3 or 4 channels, or NV12 frames");
+    if (p->src_type == CVGS_NV12 && (p->yuv_standard < 0 || p->yuv_standard > 3))
+        return fail(CVGS_ERR_INVALID_VALUE, "bad yuv_standard");
     if (p->dst_width <= 0 || p->dst_height <= 0 || p->dst_width > (1 << 20) || p->dst_height > (1 << 20))
         return fail(CVGS_ERR_INVALID_VALUE, "destination size out of range");
     if (p->aspect_mode < 0 || p->aspect_mode > 3) return fail(CVGS_ERR_INVALID_VALUE, "bad aspect_mode");
@@ -145,6 +157,7 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
     P.H = p.dst_height;
     P.band_test = p.aspect_mode != CVGS_IGNORE_AR;
     P.src_type = p.src_type;
+    if (p.src_type == CVGS_NV12) yuv_constants(p.yuv_standard, P.yuv);
     P.nc = channels_of(p.src_type);
     const int NC = P.nc;
     for (int c = 0; c < NC; ++c) P.bg[c] = p.background[c];

@@ -53,6 +53,7 @@ inline void check(int rc, const char* what) {
         throw std::runtime_error(std::string(what) + ": " + cvgs_b200_last_error() + " (code " + std::to_string(rc) + ")");
 }
 struct ReadBatch {  // cvGS::resize(...) result
+    int yuv_standard = 0;  // CVGS_NV12 sources
     std::vector<cvgs_crop_t> crops;
     std::vector<cvgs_parent_t> parents;  // the image each ROI was cut from (GpuMat::datastart / dataend)
     int n_planes = 0, used = 0, dst_w = 0, dst_h = 0, aspect = CVGS_IGNORE_AR, src_type = 0;
@@ -183,6 +184,28 @@ inline detail::ReadBatch resize(const cv::cuda::GpuMat& input, const cv::Size& d
     return resize<T, INTER_F, 1>(std::array<cv::cuda::GpuMat, 1>{input}, d, 1);
 }
 
+// NV12 frames (decoder output) as sources.  The reference reaches this through its fk:: layer only
+// (fk::Resize<INTER_LINEAR>::build(fk::fuse(fk::Read<fk::ReadYUV<fk::NV12>>{frame}, fk::Unary<fk::ConvertYUVToRGB<
+// fk::NV12, range, primaries, false, float3>>{}), dsize), tests/resize/test_fused_resize.cu:73-76); here it is one
+// more read of the same pipeline.  Each GpuMat is the CV_8UC1 luma plane; the interleaved UV plane follows it at
+// data + step * rows.  standard: enum cvgs_yuv_standard.
+template <int NPtr>
+inline detail::ReadBatch resizeNV12(const std::array<cv::cuda::GpuMat, NPtr>& frames, const cv::Size& dsize, int standard,
+                                    int usedPlanes = NPtr, const cv::Scalar& backgroundValue = cv::Scalar()) {
+    detail::ReadBatch r;
+    r.n_planes = NPtr;
+    r.used = usedPlanes;
+    r.dst_w = dsize.width;
+    r.dst_h = dsize.height;
+    r.aspect = CVGS_IGNORE_AR;
+    r.src_type = CVGS_NV12;
+    r.yuv_standard = standard;
+    for (int c = 0; c < 4; ++c) r.bg[c] = static_cast<float>(backgroundValue[c]);
+    r.crops.resize(NPtr);
+    for (int i = 0; i < NPtr && i < usedPlanes; ++i) r.crops[i] = detail::crop_of(frames[i]);
+    return r;
+}
+
 // ---- element-wise operations (reference :74-161) ---------------------------------------------------------
 template <int I, int O>
 inline detail::ChainOp convertTo() {  // SaturateCast<u8 -> f32>: the resize already yields float
@@ -305,6 +328,7 @@ inline void executeOperations(const cv::cuda::Stream& stream, const detail::Read
     p.aspect_mode = read.aspect;
     p.interp_mode = interpMode();
     p.fp_contract = fpContract();
+    p.yuv_standard = read.yuv_standard;
     for (int c = 0; c < 4; ++c) p.background[c] = read.bg[c];
     (detail::append(p, iops), ...);
     detail::check(cvgs_b200_preproc_launch_ex(read.crops.data(), read.parents.empty() ? nullptr : read.parents.data(),

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CVGS_B200_VERSION 101 /* 0.1.1 */
+#define CVGS_B200_VERSION 102 /* 0.1.2 */
 
 /* ---- error codes (subset of cudaError_t values so they can be passed through) ---- */
 #define CVGS_OK 0
@@ -52,6 +52,20 @@ extern "C" {
 #define CVGS_16UC4 26 /* tests/batchresize/test_batchresize_x_split3D.cu:427-432): four output channels, four      */
 #define CVGS_16SC4 27 /* constants per operation, REORDER over four channels; taken by the direct-gather kernel    */
 #define CVGS_32FC4 29 /* CV_32FC4 */
+/* Decoder output (not an OpenCV type code): 8-bit 4:2:0, a Y plane of `height` rows followed by an interleaved UV plane
+ * of height/2 rows at data + pitch * height, read as fk::ReadYUV<fk::NV12> and converted per tap by
+ * fk::ConvertYUVToRGB<NV12, range, primaries, false, float3> in front of the resize (reference
+ * fkl/.../image_processing/color_conversion.cuh:235-362; tests/resize/test_fused_resize.cu:73-76,141-143).  A crop
+ * of this type is a whole frame {Y plane, width, height, pitch}; the pipeline sees float RGB.  Direct-gather kernel. */
+#define CVGS_NV12 0x1001
+
+/* YCbCr -> RGB matrices of the reference (color_conversion.cuh:171-214): ccMatrix<range, primaries, YCbCr2RGB>. */
+enum cvgs_yuv_standard {
+    CVGS_YUV_BT601_FULL = 0,   /* luma offset 16, 1.164 / 1.596 / -0.392 / -0.813 / 2.017 */
+    CVGS_YUV_BT709_FULL = 1,
+    CVGS_YUV_BT709_LIMITED = 2,
+    CVGS_YUV_BT2020_FULL = 3
+};
 
 /* Aspect-ratio policy of the resize; same numbering as cvGS::AspectRatio
  * (reference include/cvGPUSpeedup.cuh:32, fkl/.../image_processing/resize.cuh:41). */
@@ -150,6 +164,8 @@ typedef struct cvgs_pipeline {
                                   For CVGS_8UC3 output the unit is bytes. */
     int64_t out_row_pitch;     /* CVGS_8UC3 output only: bytes between rows of a destination image (GpuMat::step of
                                   cvGS::write<CV_8UC3>(GpuMat)); 0 = tight (3 * dst_width) */
+    int32_t yuv_standard;      /* CVGS_NV12 sources only: enum cvgs_yuv_standard */
+    int32_t reserved;          /* must be 0 */
 } cvgs_pipeline_t;
 
 /* ------------------------------------------------------------------------------------------

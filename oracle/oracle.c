@@ -109,6 +109,30 @@ static float round_sat_src(float v, int src_type) {
                                                                 : round_sat_u8(v);
 }
 /* channel ch of pixel x of a source row, as the float the reference's uchar3/ushort3/short3 * float promotes it to */
+/* fk::ReadYUV<NV12> + fk::ConvertYUVToRGB<NV12, range, primaries, false, float3> for one source pixel
+ * (color_conversion.cuh:235-291, matrices :171-214).  Rounding sequence as nvcc compiles MxVFloat3 + VectorReduce for
+ * the reference (SASS): per output channel FMUL(y * m0), FFMA(u, m1, .), FFMA(v, m2, .), zero coefficients included;
+ * bt601 subtracts 16 from the luma first, every standard subtracts 128 from the chroma. */
+static const float kYuvMatrix[4][9] = {
+    {1.164383562f, 0.f, 1.596026786f, 1.164383562f, -0.39176229f, -0.812967647f, 1.164383562f, 2.017232143f, 0.f},
+    {1.f, 0.f, 1.5748f, 1.f, -0.1873f, -0.4681f, 1.f, 1.8556f, 0.f},
+    {1.f, 0.f, 1.402f, 1.f, -0.34414f, -0.71414f, 1.f, 1.772f, 0.f},
+    {1.f, 0.f, 1.4746f, 1.f, -0.16455312684366f, -0.57135312684366f, 1.f, 1.8814f, 0.f}};
+static void nv12_px(const cvgs_crop_t* c, int x, int y, int standard, float rgb[3]) {
+    const uint8_t* base = (const uint8_t*)c->data;
+    const uint8_t* uv = base + (size_t)c->pitch * (size_t)c->height + (size_t)(y >> 1) * (size_t)c->pitch + 2 * (size_t)(x >> 1);
+    float yy = (float)base[(size_t)y * (size_t)c->pitch + x];
+    if (standard == CVGS_YUV_BT601_FULL) yy = yy - 16.0f;
+    const float u = (float)uv[0] - 128.0f, v = (float)uv[1] - 128.0f;
+    const float* m = kYuvMatrix[standard];
+    for (int r = 0; r < 3; ++r) {
+        float t = yy * m[3 * r];
+        t = fmaf(u, m[3 * r + 1], t);
+        t = fmaf(v, m[3 * r + 2], t);
+        rgb[r] = t;
+    }
+}
+
 static int n_channels(int src_type) {
     return (src_type == CVGS_8UC4 || src_type == CVGS_16UC4 || src_type == CVGS_16SC4) ? 4 : 3;
 }
@@ -122,7 +146,7 @@ static float src_px(const uint8_t* row, int x, int ch, int src_type) {
 /* One output pixel of Resize::exec + Interpolate<INTER_LINEAR>::exec
  * (resize.cuh:70-82,178-189; interpolation.cuh:57-92; PerThreadRead ptr_nd.cuh:41-45).
  * Rounding sequence = what nvcc emits for the reference kernel (see file header). */
-static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspect_mode, int src_type,
+static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspect_mode, int src_type, int yuv_standard,
                          int x, int y, const float* bg, float out[4]) {
     const int nc = n_channels(src_type);
     if (aspect_mode != CVGS_IGNORE_AR) {
@@ -145,6 +169,21 @@ static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspec
     const uint8_t* base = (const uint8_t*)c->data;
     const uint8_t* r0 = base + (size_t)y1 * (size_t)c->pitch;
     const uint8_t* r1 = base + (size_t)y2r * (size_t)c->pitch;
+    if (src_type == CVGS_NV12) { /* the back-function of the resize is read + colour conversion: taps are float RGB */
+        float p00[3], p10[3], p01[3], p11[3];
+        nv12_px(c, x1, y1, yuv_standard, p00);
+        nv12_px(c, x2r, y1, yuv_standard, p10);
+        nv12_px(c, x1, y2r, yuv_standard, p01);
+        nv12_px(c, x2r, y2r, yuv_standard, p11);
+        for (int ch = 0; ch < 3; ++ch) {
+            float t = p10[ch] * w10;
+            t = fmaf(p00[ch], w00, t);
+            t = fmaf(p01[ch], w01, t);
+            t = fmaf(p11[ch], w11, t);
+            out[ch] = t;
+        }
+        return;
+    }
     for (int ch = 0; ch < nc; ++ch) {
         const float p00 = src_px(r0, x1, ch, src_type), p10 = src_px(r0, x2r, ch, src_type);
         const float p01 = src_px(r1, x1, ch, src_type), p11 = src_px(r1, x2r, ch, src_type);
@@ -250,7 +289,8 @@ int oracle_preproc(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_
                    int nthreads) {
     if (!crops || !p || !p->out || n_planes <= 0 || used < 0 ||
         (p->src_type != CVGS_8UC3 && p->src_type != CVGS_16UC3 && p->src_type != CVGS_16SC3 &&
-         p->src_type != CVGS_8UC4 && p->src_type != CVGS_16UC4 && p->src_type != CVGS_16SC4) ||
+         p->src_type != CVGS_8UC4 && p->src_type != CVGS_16UC4 && p->src_type != CVGS_16SC4 && p->src_type != CVGS_NV12) ||
+        (p->src_type == CVGS_NV12 && (p->yuv_standard < 0 || p->yuv_standard > 3)) ||
         p->dst_width <= 0 || p->dst_height <= 0 || p->n_ops < 0 || p->n_ops > CVGS_MAX_OPS)
         return 1;
     if (used > n_planes) used = n_planes;
@@ -271,7 +311,7 @@ int oracle_preproc(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_
             if (z >= used) {
                 v[0] = p->background[0]; v[1] = p->background[1]; v[2] = p->background[2]; v[3] = p->background[3];
             } else {
-                resize_pixel(&crops[z], &geoms[z], p->aspect_mode, p->src_type, x, y, p->background, v);
+                resize_pixel(&crops[z], &geoms[z], p->aspect_mode, p->src_type, p->yuv_standard, x, y, p->background, v);
             }
             apply_chain(p, v);
             store_pixel(p, n_planes, z, y, x, v);

@@ -185,6 +185,46 @@ int FKREF_CAT(fkref_preproc16_, FKREF_BATCH)(int pixel_type, const void* const* 
 }
 #endif
 
+#ifdef FKREF_NV12
+// One NV12 frame: Read<ReadYUV<NV12>> fused with ConvertYUVToRGB<NV12, range, primaries, false, float3> as the
+// back-function of Resize<INTER_LINEAR> (tests/resize/test_fused_resize.cu:73-76,141-143), then Mul, Sub, Div and
+// TensorSplit into out[3][dst_h][dst_w].  standard: 0 bt601 full, 1 bt709 full, 2 bt709 limited, 3 bt2020 full.
+}  // extern "C"
+namespace {
+template <fk::ColorRange CR, fk::ColorPrimitives CP>
+int run_nv12(const void* data, int w, int h, int pitch, int dst_w, int dst_h, const float* mul, const float* sub,
+             const float* div, float* out, cudaStream_t stream) {
+    const fk::RawPtr<fk::_2D, uchar> img{ (uchar*)data, { (uint)w, (uint)h, (uint)pitch } };
+    const auto readBackOp = fk::fuse(fk::Read<fk::ReadYUV<fk::NV12>>{ img },
+                                     fk::Unary<fk::ConvertYUVToRGB<fk::NV12, CR, CP, false, float3>>{});
+    const auto readOp = fk::Resize<fk::INTER_LINEAR>::build(readBackOp, fk::Size(dst_w, dst_h));
+    const fk::Tensor<float> t_out(out, dst_w, dst_h, 1, 3);
+    fk::executeOperations(stream, readOp, fk::Binary<fk::Mul<float3>>{ float3{mul[0], mul[1], mul[2]} },
+                          fk::Binary<fk::Sub<float3>>{ float3{sub[0], sub[1], sub[2]} },
+                          fk::Binary<fk::Div<float3>>{ float3{div[0], div[1], div[2]} },
+                          fk::Write<fk::TensorSplit<float3>>{ t_out.ptr() });
+    return 0;
+}
+}  // namespace
+extern "C" {
+int FKREF_CAT(fkref_nv12_, FKREF_BATCH)(int standard, const void* data, int w, int h, int pitch, int dst_w, int dst_h,
+                  const float* mul, const float* sub, const float* div, float* out, void* stream) {
+    try {
+        cudaStream_t s = (cudaStream_t)stream;
+        switch (standard) {
+            case 0: return run_nv12<fk::Full, fk::bt601>(data, w, h, pitch, dst_w, dst_h, mul, sub, div, out, s);
+            case 1: return run_nv12<fk::Full, fk::bt709>(data, w, h, pitch, dst_w, dst_h, mul, sub, div, out, s);
+            case 2: return run_nv12<fk::Limited, fk::bt709>(data, w, h, pitch, dst_w, dst_h, mul, sub, div, out, s);
+            case 3: return run_nv12<fk::Full, fk::bt2020>(data, w, h, pitch, dst_w, dst_h, mul, sub, div, out, s);
+            default: g_err = "fkref: bad yuv standard"; return -1;
+        }
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+#endif
+
 const char* FKREF_CAT(fkref_last_error_, FKREF_BATCH)(void) { return g_err.c_str(); }
 
 }  // extern "C"

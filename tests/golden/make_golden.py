@@ -39,6 +39,32 @@ def main(out_dir):
                             div=np.array(DIV, dtype=np.float32), out=out)
         print(name, out.shape, float(np.nanmean(out)))
 
+    # other source types of the same chain: 16-bit and 4-channel pixels (the reference's ushort3 / short3 / uchar4 /
+    # ushort4 / short4 instantiations) and NV12 frames (ReadYUV + ConvertYUVToRGB in front of the resize)
+    from cvgpuspeedup_b200 import _abi
+    mul4, sub4, div4, bg4 = (0.3, 0.3, 0.3, 0.25), (1.0, 4.0, 3.2, 0.5), (3.2, 0.6, 11.8, 2.0), (128.0, 3.5, 250.0, 7.0)
+    rects = [(0, 0, 96, 72), (5, 7, 24, 48), (40, 3, 50, 33), (17, 50, 7, 5), (95, 71, 1, 1)]
+    for tname, st in [("16uc3", _abi.CVGS_16UC3), ("16sc3", _abi.CVGS_16SC3), ("8uc4", _abi.CVGS_8UC4),
+                      ("16uc4", _abi.CVGS_16UC4), ("16sc4", _abi.CVGS_16SC4)]:
+        nc = util.channels_of(st)
+        image = rng.integers(0, 256, size=(72, 96 * util.px_bytes_of(st) + 32), dtype=np.uint8)
+        out = gpu_util.run_fkref(image, rects, (40, 56), 1, mul4[:nc], sub4[:nc], div4[:nc], aspect=0, bg=bg4[:nc], batch=16,
+                                 used=5, src_type=st)
+        np.savez_compressed(os.path.join(out_dir, f"type_{tname}.npz"), image=image, rects=np.array(rects, dtype=np.int32),
+                            dsize=np.array((40, 56), dtype=np.int32), aspect=0, swap=1, bg=np.array(bg4[:nc], dtype=np.float32),
+                            used=5, n_planes=16, mul=np.array(mul4[:nc], dtype=np.float32),
+                            sub=np.array(sub4[:nc], dtype=np.float32), div=np.array(div4[:nc], dtype=np.float32),
+                            src_type=st, out=out)
+        print("type", tname, out.shape, float(np.nanmean(out)))
+    for standard in range(4):
+        w, h, pitch = 98, 66, 128
+        frame = rng.integers(0, 256, size=(h + (h + 1) // 2, pitch), dtype=np.uint8)
+        out = gpu_util.run_fkref_nv12(frame, w, h, (40, 56), standard, MUL, SUB, DIV)
+        np.savez_compressed(os.path.join(out_dir, f"nv12_std{standard}.npz"), image=frame, width=w, height=h,
+                            dsize=np.array((40, 56), dtype=np.int32), standard=standard, mul=np.array(MUL, dtype=np.float32),
+                            sub=np.array(SUB, dtype=np.float32), div=np.array(DIV, dtype=np.float32), out=out)
+        print("nv12", standard, out.shape, float(np.nanmean(out)))
+
 
 if __name__ == "__main__":
     main(sys.argv[1] if len(sys.argv) > 1 else os.path.dirname(os.path.abspath(__file__)))

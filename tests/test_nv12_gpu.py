@@ -1,0 +1,74 @@
+"""NV12 frames (decoder output) as the source of the fused path: fk::ReadYUV<NV12> + fk::ConvertYUVToRGB in front of
+the resize (reference color_conversion.cuh:235-362; tests/resize/test_fused_resize.cu:73-76,141-143 -- a test without
+assertions there).  Bit-exact against the reference's own kernel and the oracle, for the four matrices it defines."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from cvgpuspeedup_b200 import _abi
+from tests import gpu_util, util
+
+pytestmark = pytest.mark.gpu
+
+MUL, SUB, DIV = (1 / 255.0,) * 3, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+OPS = [("mul", MUL), ("sub", SUB), ("div", DIV)]
+
+
+def _frame(seed, w, h, pitch):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, size=(h + (h + 1) // 2, pitch), dtype=np.uint8)
+
+
+def _ours(frames, sizes, pitch, dsize, standard, ops, **kw):
+    """One launch for all frames (each frame is one 'crop' = a whole NV12 image)."""
+    lib = _abi.load()
+    d = [torch.from_numpy(f).cuda() for f in frames]
+    n = len(frames)
+    crops = (_abi.Crop * n)()
+    for i, (t, (w, h)) in enumerate(zip(d, sizes)):
+        crops[i].data, crops[i].width, crops[i].height, crops[i].pitch = t.data_ptr(), w, h, pitch
+    out = torch.full((n, 3, dsize[1], dsize[0]), float("nan"), device="cuda")
+    p = util.make_pipeline(dsize, ops, out_ptr=out.data_ptr(), src_type=_abi.CVGS_NV12, yuv_standard=standard, **kw)
+    _abi.check(lib.cvgs_b200_preproc_launch(crops, n, n, C.byref(p), None))
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _oracle(frames, sizes, pitch, dsize, standard, ops, **kw):
+    n = len(frames)
+    crops = (_abi.Crop * n)()
+    for i, (f, (w, h)) in enumerate(zip(frames, sizes)):
+        crops[i].data, crops[i].width, crops[i].height, crops[i].pitch = f.ctypes.data, w, h, pitch
+    out = np.full((n, 3, dsize[1], dsize[0]), np.nan, dtype=np.float32)
+    p = util.make_pipeline(dsize, ops, out_ptr=out.ctypes.data, src_type=_abi.CVGS_NV12, yuv_standard=standard, **kw)
+    assert util.oracle_lib().oracle_preproc(crops, n, n, C.byref(p), 0) == 0
+    return out
+
+
+@pytest.mark.parametrize("standard", [0, 1, 2, 3])
+def test_nv12_matches_reference_kernel_and_oracle(standard):
+    if gpu_util.fkref_lib(16) is None:
+        pytest.skip("oracle/_ref not built")
+    pitch = 512
+    sizes = [(320, 240), (322, 242), (161, 121), (64, 36), (2, 2)]
+    frames = [_frame(10 * standard + i, w, h, pitch) for i, (w, h) in enumerate(sizes)]
+    for dsize in [(64, 128), (400, 300), (33, 7)]:
+        ours = _ours(frames, sizes, pitch, dsize, standard, OPS)
+        orc = _oracle(frames, sizes, pitch, dsize, standard, OPS)
+        util.assert_bit_equal(ours, orc, f"standard {standard} dsize {dsize}: ours vs oracle")
+        for i, (f, (w, h)) in enumerate(zip(frames, sizes)):
+            ref = gpu_util.run_fkref_nv12(f, w, h, dsize, standard, MUL, SUB, DIV)
+            util.assert_bit_equal(ours[i], ref, f"standard {standard} dsize {dsize} frame {i}: ours vs reference kernel")
+
+
+def test_nv12_modes_and_layouts():
+    pitch = 384
+    sizes = [(300, 200), (128, 128)]
+    frames = [_frame(77 + i, w, h, pitch) for i, (w, h) in enumerate(sizes)]
+    ops = [("reorder", (2, 1, 0)), ("mul", (0.5, 0.25, 2.0)), ("add", (1.0, 2.0, 3.0))]
+    for kw in [dict(aspect=_abi.PRESERVE_AR, background=(1.0, 2.0, 3.0)), dict(interp_mode=_abi.INTERP_ROUND_U8),
+               dict(fp_contract=_abi.FP_SEPARATE)]:
+        util.assert_bit_equal(_ours(frames, sizes, pitch, (96, 64), 1, ops, **kw), _oracle(frames, sizes, pitch, (96, 64), 1, ops, **kw),
+                              f"nv12 {kw}")

@@ -218,12 +218,26 @@ def test_golden_vectors_from_reference_kernel():
         pytest.skip("golden vectors not generated yet (tests/golden/make_golden.py on a GPU box)")
     for f in files:
         g = np.load(f)
+        if "standard" in g:  # NV12 frame: ReadYUV + ConvertYUVToRGB + resize + mul/sub/div of the reference
+            import ctypes as C
+            img = np.ascontiguousarray(g["image"])
+            crop = (_abi.Crop * 1)()
+            crop[0].data, crop[0].width, crop[0].height, crop[0].pitch = img.ctypes.data, int(g["width"]), int(g["height"]), img.shape[1]
+            dsize = tuple(int(v) for v in g["dsize"])
+            got = np.full((1, 3, dsize[1], dsize[0]), np.nan, dtype=np.float32)
+            p = util.make_pipeline(dsize, [("mul", tuple(g["mul"])), ("sub", tuple(g["sub"])), ("div", tuple(g["div"]))],
+                                   out_ptr=got.ctypes.data, src_type=_abi.CVGS_NV12, yuv_standard=int(g["standard"]))
+            assert util.oracle_lib().oracle_preproc(crop, 1, 1, C.byref(p), 0) == 0
+            util.assert_bit_equal(got[0], g["out"], os.path.basename(f))
+            continue
+        src_type = int(g["src_type"]) if "src_type" in g else _abi.CVGS_8UC3
+        nc = util.channels_of(src_type)
         rects = [tuple(int(v) for v in r) for r in g["rects"]]
         ops = []
         if int(g["swap"]):
-            ops.append(("reorder", (2, 1, 0)))
+            ops.append(("reorder", (2, 1, 0) if nc == 3 else (2, 1, 0, 3)))
         ops += [("mul", tuple(g["mul"])), ("sub", tuple(g["sub"])), ("div", tuple(g["div"]))]
         got = util.run_oracle(g["image"], rects, tuple(int(v) for v in g["dsize"]), ops, aspect=int(g["aspect"]),
                               background=tuple(float(v) for v in g["bg"]), n_planes=int(g["n_planes"]),
-                              used=int(g["used"]))
+                              used=int(g["used"]), src_type=src_type)
         util.assert_bit_equal(got, g["out"], os.path.basename(f))

@@ -135,7 +135,7 @@ _KIND = {"mul": _abi.OP_MUL, "sub": _abi.OP_SUB, "div": _abi.OP_DIV, "add": _abi
 
 def make_pipeline(dsize, ops, aspect=_abi.IGNORE_AR, background=(0, 0, 0), fp_contract=_abi.FP_REFERENCE_FUSED,
                   interp_mode=_abi.INTERP_FLOAT, layout=_abi.OUT_NCHW, out_ptr=0, plane_stride=0,
-                  src_type=_abi.CVGS_8UC3, dst_type=0, row_pitch=0) -> _abi.Pipeline:
+                  src_type=_abi.CVGS_8UC3, dst_type=0, row_pitch=0, yuv_standard=0) -> _abi.Pipeline:
     p = _abi.Pipeline()
     p.src_type = src_type
     p.dst_width, p.dst_height = dsize
@@ -152,11 +152,12 @@ def make_pipeline(dsize, ops, aspect=_abi.IGNORE_AR, background=(0, 0, 0), fp_co
                 p.ops[i].v[c] = v[c]
     p.out_layout, p.out, p.out_plane_stride = layout, out_ptr, plane_stride
     p.dst_type, p.out_row_pitch = dst_type, row_pitch
+    p.yuv_standard = yuv_standard
     return p
 
 
 def px_bytes_of(src_type) -> int:
-    return {_abi.CVGS_8UC3: 3, _abi.CVGS_8UC4: 4, _abi.CVGS_16UC3: 6, _abi.CVGS_16SC3: 6}.get(src_type, 8)
+    return {_abi.CVGS_8UC3: 3, _abi.CVGS_8UC4: 4, _abi.CVGS_16UC3: 6, _abi.CVGS_16SC3: 6, _abi.CVGS_NV12: 1}.get(src_type, 8)
 
 
 def channels_of(src_type) -> int:
