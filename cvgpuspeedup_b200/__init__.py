@@ -7,4 +7,4 @@ from . import _abi  # noqa: F401
 from .api import *  # noqa: F401,F403
 from .api import (CircularTensor, GpuMat, add, build_pipeline, convertTo, cvtColor, divide,  # noqa: F401
                   executeOperations, make_crops, multiply, resize, resize_nv12, split, split_planes, splitT, subtract,
-                  write)
+                  warp, write, write_u8)

@@ -19,6 +19,7 @@ CVGS_8UC3, CVGS_16UC3, CVGS_16SC3, CVGS_32FC3 = 16, 18, 19, 21
 CVGS_8UC4, CVGS_16UC4, CVGS_16SC4, CVGS_32FC4 = 24, 26, 27, 29
 CVGS_NV12 = 0x1001
 YUV_BT601_FULL, YUV_BT709_FULL, YUV_BT709_LIMITED, YUV_BT2020_FULL = 0, 1, 2, 3
+WARP_AFFINE, WARP_PERSPECTIVE = 0, 1
 PRESERVE_AR, IGNORE_AR, PRESERVE_AR_RN_EVEN, PRESERVE_AR_LEFT = 0, 1, 2, 3
 OP_MUL, OP_SUB, OP_DIV, OP_ADD, OP_REORDER = 1, 2, 3, 4, 5
 FP_REFERENCE_FUSED, FP_SEPARATE = 0, 1
@@ -43,7 +44,7 @@ class Pipeline(C.Structure):
                 ("background", C.c_float * 4), ("n_ops", C.c_int32), ("ops", Op * MAX_OPS),
                 ("out_layout", C.c_int32), ("dst_type", C.c_int32), ("out", C.c_void_p),
                 ("out_plane_stride", C.c_int64), ("out_row_pitch", C.c_int64), ("yuv_standard", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("u8_cast", C.c_int32)]
 
 
 class Parent(C.Structure):
@@ -52,6 +53,10 @@ class Parent(C.Structure):
 
 class Plane(C.Structure):
     _fields_ = [("data", C.c_void_p), ("pitch_bytes", C.c_int64)]
+
+
+class Warp(C.Structure):
+    _fields_ = [("type", C.c_int32), ("m", C.c_float * 9)]
 
 
 class Rect(C.Structure):
@@ -69,6 +74,8 @@ SYMBOLS = {
                                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                                        C.POINTER(C.POINTER(Pipeline)), C.c_int32, C.c_int32,
                                                        C.c_void_p]),
+    "cvgs_b200_warp_launch": (C.c_int, [C.POINTER(Crop), C.POINTER(Warp), C.c_int32, C.c_int32, C.POINTER(Pipeline),
+                                        C.c_void_p]),
     "cvgs_b200_preproc_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Rect), C.c_int32,
                                          C.c_int32, C.POINTER(Pipeline), C.c_void_p, C.c_void_p]),
     "cvgs_b200_preproc_launch_sequence": (C.c_int, [C.POINTER(C.POINTER(Crop)), C.POINTER(C.c_int32),

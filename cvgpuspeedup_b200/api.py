@@ -95,6 +95,18 @@ class _Write:
     plane_stride: int = 0
     owner: object = None
     planes: object = None  # OUT_PLANES: ctypes array of _abi.Plane kept alive with the op
+    dst_type: int = 0      # _abi.CVGS_8UC3: packed 8-bit image
+    row_pitch: int = 0
+    u8_cast: int = 0
+
+
+@dataclass
+class _Warp:
+    images: List[GpuMat]
+    inverse: list          # per image (type, nine float32) -- destination -> source
+    dsize: Tuple[int, int]
+    used: int
+    background: Tuple[float, float, float]
 
 
 def resize(crops: Sequence[GpuMat], dsize: Tuple[int, int], usedPlanes: Optional[int] = None,
@@ -115,6 +127,50 @@ def resize_nv12(frames: Sequence[GpuMat], dsize: Tuple[int, int], standard: int 
     r = resize(frames, dsize, usedPlanes, backgroundValue, aspect, _abi.CVGS_NV12)
     r.yuv_standard = int(standard)
     return r
+
+
+WARP_AFFINE, WARP_PERSPECTIVE = _abi.WARP_AFFINE, _abi.WARP_PERSPECTIVE
+
+
+def invert_warp_matrix(m, warp_type: int):
+    """What cvGS::warp does to the user's matrix on the host (reference include/cvGPUSpeedup.cuh:266-283): affine 2x3
+    through cv::invertAffineTransform, perspective 3x3 through Mat::inv(), both in double, then cast to float.
+    Returns nine float32 (row-major; the third row of an affine matrix is unused)."""
+    import numpy as np
+    m = np.asarray(m, dtype=np.float64)
+    out = np.zeros(9, dtype=np.float32)
+    if warp_type == WARP_AFFINE:
+        if m.shape != (2, 3):
+            raise CvgsError("an affine warp takes a 2x3 matrix")
+        # cv::invertAffineTransform (imgproc/src/imgwarp.cpp): closed form, D = 0 gives a zero matrix
+        d = m[0, 0] * m[1, 1] - m[0, 1] * m[1, 0]
+        d = 1.0 / d if d != 0 else 0.0
+        a11, a22, a12, a21 = m[1, 1] * d, m[0, 0] * d, -m[0, 1] * d, -m[1, 0] * d
+        b1 = -a11 * m[0, 2] - a12 * m[1, 2]
+        b2 = -a21 * m[0, 2] - a22 * m[1, 2]
+        out[:6] = np.array([a11, a12, b1, a21, a22, b2], dtype=np.float64).astype(np.float32)
+    elif warp_type == WARP_PERSPECTIVE:
+        if m.shape != (3, 3):
+            raise CvgsError("a perspective warp takes a 3x3 matrix")
+        out[:] = np.linalg.inv(m).astype(np.float32).ravel()
+    else:
+        raise CvgsError("warp type must be WARP_AFFINE or WARP_PERSPECTIVE")
+    return out
+
+
+def warp(images, matrices, dsize: Tuple[int, int], warp_type: int = WARP_AFFINE, usedPlanes: Optional[int] = None,
+         backgroundValue=(0.0, 0.0, 0.0)) -> _Warp:
+    """cvGS::warp<WT, CV_8UC3[, N]>(GpuMat / array<GpuMat, N>, Mat / array<Mat, N>, Size[, usedPlanes, default])
+    (reference include/cvGPUSpeedup.cuh:285-442): `matrices` are the forward transforms cv::warpAffine /
+    cv::warpPerspective take; they are inverted here like the wrapper does."""
+    if isinstance(images, GpuMat):
+        images, matrices = [images], [matrices]
+    images = list(images)
+    inv = [invert_warp_matrix(m, warp_type) for m in matrices]
+    if len(inv) != len(images):
+        raise CvgsError("one matrix per image is required")
+    return _Warp(images, [(int(warp_type), v) for v in inv], (int(dsize[0]), int(dsize[1])),
+                 len(images) if usedPlanes is None else int(usedPlanes), _scalar3(backgroundValue))
 
 
 def multiply(s) -> _Op:   # cvGS::multiply<CV_32FC3>(Scalar) :131
@@ -182,6 +238,12 @@ def write(out, plane_stride: int = 0) -> _Write:
     return _Write(out.data_ptr(), OUT_NHWC, plane_stride, out)
 
 
+def write_u8(out, row_pitch: int = 0, plane_stride: int = 0, cast: bool = False) -> _Write:
+    """cvGS::write<CV_8UC3>(GpuMat) behind convertTo<CV_32FC3, CV_8UC3> (cast=False: SaturateCast, rounding) or behind
+    fk::Cast<float3, uchar3> (cast=True: truncation, reference tests/warping/test_warping_opencv.cu:63)."""
+    return _Write(out.data_ptr(), OUT_NHWC, plane_stride, out, None, _abi.CVGS_8UC3, int(row_pitch), 1 if cast else 0)
+
+
 def _stream_ptr(stream) -> int:
     if stream is None:
         import torch
@@ -234,18 +296,31 @@ def executeOperations(stream, *iops, fp_contract: int = FP_REFERENCE_FUSED, inte
     """cvGS::executeOperations(stream, resize(...), ops..., split(...)) :464-473: ONE kernel launch,
     asynchronous on `stream`.  Raises CvgsError (the reference throws std::runtime_error)."""
     iops = list(_flatten(iops))
-    if len(iops) < 2 or not isinstance(iops[0], _Resize) or not isinstance(iops[-1], _Write):
-        raise CvgsError("chain must start with resize(...) and end with split/splitT/write(...)")
+    if len(iops) < 2 or not isinstance(iops[0], (_Resize, _Warp)) or not isinstance(iops[-1], _Write):
+        raise CvgsError("chain must start with resize(...) / warp(...) and end with split/splitT/write(...)")
     rs, wr, mid = iops[0], iops[-1], iops[1:-1]
     if any(not isinstance(o, _Op) for o in mid):
         raise CvgsError("only multiply/subtract/divide/add/convertTo/cvtColor may sit between read and write")
+    lib = _abi.load()
+    if isinstance(rs, _Warp):
+        p = build_pipeline(rs.dsize, mid, rs.background, IGNORE_AR, fp_contract, INTERP_FLOAT, wr.out_ptr, wr.layout,
+                           wr.plane_stride)
+        p.dst_type, p.out_row_pitch, p.u8_cast = wr.dst_type, wr.row_pitch, wr.u8_cast
+        images = make_crops(rs.images[:rs.used])
+        warps = (_abi.Warp * max(1, rs.used))()
+        for i, (t, v) in enumerate(rs.inverse[:rs.used]):
+            warps[i].type = t
+            for k in range(9):
+                warps[i].m[k] = float(v[k])
+        _abi.check(lib.cvgs_b200_warp_launch(images, warps, len(rs.images), rs.used, C.byref(p), _stream_ptr(stream)))
+        return
     p = build_pipeline(rs.dsize, mid, rs.background, rs.aspect, fp_contract, interp_mode, wr.out_ptr, wr.layout,
                        wr.plane_stride, rs.src_type, rs.yuv_standard)
+    p.dst_type, p.out_row_pitch, p.u8_cast = wr.dst_type, wr.row_pitch, wr.u8_cast
     crops = make_crops(rs.crops[:rs.used])
     parents = (_abi.Parent * max(1, rs.used))()
     for i, m in enumerate(rs.crops[:rs.used]):
         parents[i].datastart, parents[i].whole_width, parents[i].whole_height = m.datastart, m.whole[0], m.whole[1]
-    lib = _abi.load()
     if rs.src_type == _abi.CVGS_NV12:  # whole frames: nothing to say about parents
         _abi.check(lib.cvgs_b200_preproc_launch(crops, len(rs.crops), rs.used, C.byref(p), _stream_ptr(stream)))
         return

@@ -57,7 +57,8 @@ struct OutDesc {
     long long c_stride;  // floats between colour planes
     int32_t px_stride;   // floats between x-adjacent pixels (1 planar, 3 packed)
     int32_t vec4;        // 1: planar rows are 16-byte aligned and W % 4 == 0
-    int32_t u8;          // 1: packed 8-bit output (SaturateCast<float, uchar> after the chain); strides below in bytes
+    int32_t u8;          // packed 8-bit output after the chain, strides below in bytes: 1 SaturateCast<float, uchar>,
+                         // 2 fk::Cast (static_cast: truncation, low byte)
     long long row_pitch; // u8 output: bytes between rows
 };
 
@@ -199,7 +200,9 @@ __device__ __forceinline__ void store_pixels(const PreprocParams& P, int z, int 
         for (int p = 0; p < NPIX; ++p)
             if (p < nvalid) {
 #pragma unroll
-                for (int r = 0; r < NC; ++r) px[NC * p + P.prog.dst_chan[r]] = (uint8_t)round_sat_u8(v[p][r]);
+                for (int r = 0; r < NC; ++r)
+                    px[NC * p + P.prog.dst_chan[r]] =
+                        o.u8 == 2 ? (uint8_t)__float2uint_rz(v[p][r]) : (uint8_t)round_sat_u8(v[p][r]);
             }
         return;
     }

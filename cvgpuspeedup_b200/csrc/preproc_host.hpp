@@ -139,6 +139,8 @@ inline int validate_pipeline(const cvgs_pipeline_t* p) {
     if (p->out_plane_stride < 0) return fail(CVGS_ERR_INVALID_VALUE, "negative out_plane_stride");
     if (p->dst_type != 0 && p->dst_type != CVGS_32FC3 && p->dst_type != CVGS_32FC4 && p->dst_type != CVGS_8UC3)
         return fail(CVGS_ERR_NOT_SUPPORTED, "dst_type must be CV_32FC3 / CV_32FC4 (or 0) or CV_8UC3");
+    if (p->u8_cast != 0 && (p->u8_cast != 1 || p->dst_type != CVGS_8UC3))
+        return fail(CVGS_ERR_INVALID_VALUE, "u8_cast is 0 or 1 and applies to CV_8UC3 output");
     if (p->dst_type == CVGS_8UC3 && channels_of(p->src_type) != 3)
         return fail(CVGS_ERR_NOT_SUPPORTED, "8-bit output is implemented for 3-channel pipelines");
     if (p->dst_type == CVGS_8UC3 && p->out_layout != CVGS_OUT_NHWC)
@@ -188,7 +190,7 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
             o.c_stride = 1;
             o.px_stride = NC;
     }
-    o.u8 = p.dst_type == CVGS_8UC3;
+    o.u8 = p.dst_type == CVGS_8UC3 ? (p.u8_cast ? 2 : 1) : 0;
     o.row_pitch = 0;
     if (o.u8) {  // strides in bytes
         o.row_pitch = p.out_row_pitch ? p.out_row_pitch : 3LL * p.dst_width;

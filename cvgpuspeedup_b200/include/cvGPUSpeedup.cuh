@@ -41,6 +41,7 @@ struct RawPtr {
     T* data = nullptr;
     PtrDims3D dims;
 };
+enum WarpType { Affine = 0, Perspective = 1 };  // warping.cuh:25
 }  // namespace fk
 
 namespace cvGS {
@@ -63,6 +64,13 @@ struct ChainOp {  // multiply / subtract / divide / add / cvtColor / convertTo p
     cvgs_op_t op[2];
     int n = 0;
     bool to_u8 = false;  // convertTo<CV_32FC3, CV_8UC3>(): must be the last operation, followed by write<CV_8UC3>
+    bool cast = false;   // fk::Cast<float3, uchar3>::build(): to_u8 with static_cast (truncation) instead of SaturateCast
+};
+struct WarpBatch {  // cvGS::warp(...) result
+    std::vector<cvgs_crop_t> images;
+    std::vector<cvgs_warp_t> warps;
+    int n_planes = 0, used = 0, dst_w = 0, dst_h = 0;
+    float bg[4] = {0, 0, 0, 0};
 };
 struct WriteOp {  // split / splitT / write
     void* out = nullptr;
@@ -86,6 +94,7 @@ inline cvgs_op_t scalar_op(int kind, const cv::Scalar& s) {
 inline void append(cvgs_pipeline_t& p, const ChainOp& c) {
     if (p.dst_type == CVGS_8UC3) throw std::runtime_error("cvGS: convertTo<CV_32FC3, CV_8UC3>() must be the last operation before the write");
     if (c.to_u8) p.dst_type = CVGS_8UC3;
+    if (c.cast) p.u8_cast = 1;
     for (int i = 0; i < c.n; ++i) {
         if (p.n_ops >= CVGS_MAX_OPS) throw std::runtime_error("cvGS: more than CVGS_MAX_OPS operations in the chain");
         p.ops[p.n_ops++] = c.op[i];
@@ -340,6 +349,92 @@ inline void executeOperations(const cv::cuda::Stream& stream, const detail::Read
     executeOperations(stream, read, iops...);  // thread fusion is a property of the hand-written kernel here
 }
 
+// ---- warp (reference :266-442 -> fk::Warping, warping.cuh:43-91) ------------------------------------------------------
+// The wrapper inverts the user's matrix on the host (cv::invertAffineTransform / Mat::inv(), double) and hands the
+// kernel its float cast; so does this one.
+namespace detail {
+template <fk::WarpType WT>
+inline cvgs_warp_t inverse_of(const cv::Mat& m) {
+    if (m.type() != CV_64FC1) throw std::runtime_error("Transform matrix type should be CV_64FC1.");
+    cvgs_warp_t w{};
+    cv::Mat inv;
+    if (WT == fk::WarpType::Affine) {
+        cv::invertAffineTransform(m, inv);
+        w.type = CVGS_WARP_AFFINE;
+    } else {
+        inv = m.inv();
+        w.type = CVGS_WARP_PERSPECTIVE;
+    }
+    const double* t = inv.ptr<double>();
+    for (int k = 0; k < (WT == fk::WarpType::Affine ? 6 : 9); ++k) w.m[k] = static_cast<float>(t[k]);
+    return w;
+}
+}  // namespace detail
+template <fk::WarpType WT, int InputType = CV_8UC3>
+inline detail::WarpBatch warp(const cv::cuda::GpuMat& input, const cv::Mat& transform_matrix, const cv::Size& dstSize) {
+    static_assert(InputType == CV_8UC3, "cvGS (B200 build): warp takes CV_8UC3 images");
+    if (InputType != input.type()) throw std::runtime_error("Input type does not match the input type of the operation.");
+    detail::WarpBatch b;
+    b.images.push_back(detail::crop_of(input));
+    b.warps.push_back(detail::inverse_of<WT>(transform_matrix));
+    b.n_planes = b.used = 1;
+    b.dst_w = dstSize.width;
+    b.dst_h = dstSize.height;
+    return b;
+}
+template <fk::WarpType WT, int InputType, size_t BATCH>
+inline detail::WarpBatch warp(const std::array<cv::cuda::GpuMat, BATCH>& inputs, const std::array<cv::Mat, BATCH>& transform_matrices,
+                              const std::array<cv::Size, BATCH>& dstSize, const int& usedPlanes, const cv::Scalar& defaultValue) {
+    static_assert(InputType == CV_8UC3, "cvGS (B200 build): warp takes CV_8UC3 images");
+    detail::WarpBatch b;
+    b.n_planes = static_cast<int>(BATCH);
+    b.used = usedPlanes;
+    for (int i = 0; i < usedPlanes && i < static_cast<int>(BATCH); ++i) {
+        if (InputType != inputs[i].type()) throw std::runtime_error("Input type does not match the input type of the operation.");
+        if (dstSize[i].width != dstSize[0].width || dstSize[i].height != dstSize[0].height)
+            throw std::runtime_error("cvGS (B200 build): the warps of a batch share one destination size");
+        b.images.push_back(detail::crop_of(inputs[i]));
+        b.warps.push_back(detail::inverse_of<WT>(transform_matrices[i]));
+    }
+    b.dst_w = dstSize[0].width;
+    b.dst_h = dstSize[0].height;
+    for (int c = 0; c < 4; ++c) b.bg[c] = static_cast<float>(defaultValue[c]);
+    return b;
+}
+template <fk::WarpType WT, int InputType, size_t BATCH>
+inline detail::WarpBatch warp(const std::array<cv::cuda::GpuMat, BATCH>& inputs, const std::array<cv::Mat, BATCH>& transform_matrices,
+                              const std::array<cv::Size, BATCH>& dstSize) {
+    return warp<WT, InputType, BATCH>(inputs, transform_matrices, dstSize, static_cast<int>(BATCH), cv::Scalar());
+}
+template <fk::WarpType WT, int InputType, size_t BATCH>
+inline detail::WarpBatch warp(const std::array<cv::cuda::GpuMat, BATCH>& inputs, const std::array<cv::Mat, BATCH>& transform_matrices,
+                              const cv::Size& dstSize) {
+    std::array<cv::Size, BATCH> sizes;
+    sizes.fill(dstSize);
+    return warp<WT, InputType, BATCH>(inputs, transform_matrices, sizes, static_cast<int>(BATCH), cv::Scalar());
+}
+template <fk::WarpType WT, int InputType, size_t BATCH>
+inline detail::WarpBatch warp(const std::array<cv::cuda::GpuMat, BATCH>& inputs, const std::array<cv::Mat, BATCH>& transform_matrices,
+                              const cv::Size& dstSize, const int& usedPlanes, const cv::Scalar& defaultValue) {
+    std::array<cv::Size, BATCH> sizes;
+    sizes.fill(dstSize);
+    return warp<WT, InputType, BATCH>(inputs, transform_matrices, sizes, usedPlanes, defaultValue);
+}
+template <typename... IOpTypes>
+inline void executeOperations(const cv::cuda::Stream& stream, const detail::WarpBatch& read, const IOpTypes&... iops) {
+    cvgs_pipeline_t p{};
+    p.src_type = CVGS_8UC3;
+    p.dst_width = read.dst_w;
+    p.dst_height = read.dst_h;
+    p.aspect_mode = CVGS_IGNORE_AR;
+    p.fp_contract = fpContract();
+    for (int c = 0; c < 4; ++c) p.background[c] = read.bg[c];
+    (detail::append(p, iops), ...);
+    detail::check(cvgs_b200_warp_launch(read.images.data(), read.warps.data(), read.n_planes, read.used, &p,
+                                        cv::cuda::StreamAccessor::getStream(stream)),
+                  "cvGS::executeOperations");
+}
+
 // ---- batch reads without a resize (reference :504-584; tests/batchread/test_batchread_x_write3D.cu) -----------
 // fk::BatchRead<PerThreadRead> of N equally sized images.  The same kernel serves it: with destination size ==
 // source size the scale factors are exactly 1, every tap weight is exactly 0 or 1 and the interpolated value is the
@@ -463,3 +558,19 @@ private:
 };
 
 }  // namespace cvGS
+
+namespace fk {
+// fk::Cast<float3, uchar3>::build() in front of cvGS::write<CV_8UC3> (reference basic_ops/cast.cuh:22-29; chain of
+// tests/warping/test_warping_opencv.cu:63): static_cast per channel, i.e. truncation.
+template <typename I, typename O>
+struct Cast {
+    static_assert(std::is_same<I, float3>::value && std::is_same<O, uchar3>::value,
+                  "cvGS (B200 build): fk::Cast<float3, uchar3> is the cast on this path");
+    static cvGS::detail::ChainOp build() {
+        cvGS::detail::ChainOp c{};
+        c.to_u8 = true;
+        c.cast = true;
+        return c;
+    }
+};
+}  // namespace fk

@@ -23,9 +23,11 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <cmath>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 typedef unsigned char uchar;
 typedef unsigned int uint;
@@ -54,6 +56,7 @@ typedef unsigned int uint;
 #define CV_16SC4 CV_MAKETYPE(CV_16S, 4)
 #define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
 #define CV_32FC3 CV_MAKETYPE(CV_32F, 3)
 #define CV_32FC4 CV_MAKETYPE(CV_32F, 4)
 
@@ -81,6 +84,119 @@ struct Scalar {
     double operator[](int i) const { return val[i]; }
     static Scalar all(double v) { return Scalar(v, v, v, v); }
 };
+
+struct Point2f {
+    float x = 0, y = 0;
+    Point2f() = default;
+    Point2f(float x_, float y_) : x(x_), y(y_) {}
+};
+
+// The transform matrices of cvGS::warp: small CV_64FC1 host matrices (cv::Mat_<double>(2, 3) << ..., Mat::inv(),
+// ptr<double>()).  Nothing else of cv::Mat is provided.
+class Mat {
+public:
+    int rows = 0, cols = 0;
+    Mat() = default;
+    Mat(int r, int c, int type = CV_64FC1) : rows(r), cols(c), v_(static_cast<size_t>(r) * c, 0.0) {
+        if (type != CV_64FC1) throw std::runtime_error("cv::Mat stand-in: CV_64FC1 only");
+    }
+    int type() const { return CV_64FC1; }
+    bool empty() const { return v_.empty(); }
+    template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(v_.data() + static_cast<size_t>(r) * cols); }
+    template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(v_.data() + static_cast<size_t>(r) * cols); }
+    template <typename T> T& at(int r, int c) { return ptr<T>(r)[c]; }
+    template <typename T> const T& at(int r, int c) const { return ptr<T>(r)[c]; }
+    // 3x3 closed form (what cv::invert does for 3x3 CV_64F with DECOMP_LU); a singular matrix gives zeros
+    Mat inv() const {
+        if (rows != 3 || cols != 3) throw std::runtime_error("cv::Mat stand-in: inv() of 3x3 matrices only");
+        const double* s = v_.data();
+        Mat r(3, 3);
+        double d = s[0] * (s[4] * s[8] - s[5] * s[7]) - s[1] * (s[3] * s[8] - s[5] * s[6]) + s[2] * (s[3] * s[7] - s[4] * s[6]);
+        if (d == 0.) return r;
+        d = 1. / d;
+        double* t = r.v_.data();
+        t[0] = (s[4] * s[8] - s[5] * s[7]) * d;
+        t[1] = (s[2] * s[7] - s[1] * s[8]) * d;
+        t[2] = (s[1] * s[5] - s[2] * s[4]) * d;
+        t[3] = (s[5] * s[6] - s[3] * s[8]) * d;
+        t[4] = (s[0] * s[8] - s[2] * s[6]) * d;
+        t[5] = (s[2] * s[3] - s[0] * s[5]) * d;
+        t[6] = (s[3] * s[7] - s[4] * s[6]) * d;
+        t[7] = (s[1] * s[6] - s[0] * s[7]) * d;
+        t[8] = (s[0] * s[4] - s[1] * s[3]) * d;
+        return r;
+    }
+
+protected:
+    std::vector<double> v_;
+};
+template <typename T>
+class Mat_ : public Mat {
+    static_assert(sizeof(T) == sizeof(double), "cv::Mat_ stand-in: double only");
+    struct Filler {  // cv::MatCommaInitializer_
+        Mat_* m;
+        int i;
+        Filler& operator,(double v) {
+            if (i < m->rows * m->cols) m->template ptr<double>()[i++] = v;
+            return *this;
+        }
+        operator Mat() const { return *m; }
+    };
+
+public:
+    Mat_(int r, int c) : Mat(r, c) {}
+    Filler operator<<(double v) {
+        this->template ptr<double>()[0] = v;
+        return Filler{this, 1};
+    }
+};
+
+// cv::invertAffineTransform (imgproc/src/imgwarp.cpp): closed form in double; D == 0 gives a zero matrix
+inline void invertAffineTransform(const Mat& m, Mat& im) {
+    if (m.rows != 2 || m.cols != 3) throw std::runtime_error("invertAffineTransform: 2x3 matrix required");
+    const double* M = m.ptr<double>();
+    im = Mat(2, 3);
+    double* iM = im.ptr<double>();
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = M[4] * D, A22 = M[0] * D, A12 = -M[1] * D, A21 = -M[3] * D;
+    const double b1 = -A11 * M[2] - A12 * M[5];
+    const double b2 = -A21 * M[2] - A22 * M[5];
+    iM[0] = A11; iM[1] = A12; iM[2] = b1;
+    iM[3] = A21; iM[4] = A22; iM[5] = b2;
+}
+
+// cv::getPerspectiveTransform: the 8x8 system of the four point pairs, solved in double (partial pivoting)
+inline Mat getPerspectiveTransform(const Point2f src[], const Point2f dst[]) {
+    double a[8][9];
+    for (int i = 0; i < 4; ++i) {
+        const double x = src[i].x, y = src[i].y, u = dst[i].x, v = dst[i].y;
+        const double r0[9] = {x, y, 1, 0, 0, 0, -x * u, -y * u, u};
+        const double r1[9] = {0, 0, 0, x, y, 1, -x * v, -y * v, v};
+        for (int k = 0; k < 9; ++k) { a[i][k] = r0[k]; a[i + 4][k] = r1[k]; }
+    }
+    for (int c = 0; c < 8; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 8; ++r)
+            if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+        if (a[piv][c] == 0.) throw std::runtime_error("getPerspectiveTransform: degenerate points");
+        for (int k = 0; k < 9; ++k) std::swap(a[c][k], a[piv][k]);
+        for (int r = c + 1; r < 8; ++r) {
+            const double f = a[r][c] / a[c][c];
+            for (int k = c; k < 9; ++k) a[r][k] -= f * a[c][k];
+        }
+    }
+    double h[9];
+    for (int r = 7; r >= 0; --r) {
+        double acc = a[r][8];
+        for (int k = r + 1; k < 8; ++k) acc -= a[r][k] * h[k];
+        h[r] = acc / a[r][r];
+    }
+    h[8] = 1.;
+    Mat m(3, 3);
+    for (int k = 0; k < 9; ++k) m.ptr<double>()[k] = h[k];
+    return m;
+}
 
 namespace cuda {
 

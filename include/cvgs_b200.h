@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CVGS_B200_VERSION 102 /* 0.1.2 */
+#define CVGS_B200_VERSION 103 /* 0.1.3 */
 
 /* ---- error codes (subset of cudaError_t values so they can be passed through) ---- */
 #define CVGS_OK 0
@@ -165,7 +165,9 @@ typedef struct cvgs_pipeline {
     int64_t out_row_pitch;     /* CVGS_8UC3 output only: bytes between rows of a destination image (GpuMat::step of
                                   cvGS::write<CV_8UC3>(GpuMat)); 0 = tight (3 * dst_width) */
     int32_t yuv_standard;      /* CVGS_NV12 sources only: enum cvgs_yuv_standard */
-    int32_t reserved;          /* must be 0 */
+    int32_t u8_cast;           /* CVGS_8UC3 output only: 0 = SaturateCast (round to nearest even, clamp; convertTo),
+                                  1 = fk::Cast<float3, uchar3> (C++ static_cast: truncation; values must lie in [0, 256),
+                                  reference basic_ops/cast.cuh:22-29, as in tests/warping/test_warping_opencv.cu:63) */
 } cvgs_pipeline_t;
 
 /* ------------------------------------------------------------------------------------------
@@ -204,6 +206,26 @@ typedef struct cvgs_parent {
 } cvgs_parent_t;
 int cvgs_b200_preproc_launch_ex(const cvgs_crop_t* crops, const cvgs_parent_t* parents, int32_t n_planes,
                                 int32_t used, const cvgs_pipeline_t* pipeline, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched affine / perspective warp in front of the same chain.  Replaces
+ *   cvGS::executeOperations(stream, cvGS::warp<WT, CV_8UC3[, N]>(images, matrices, dstSize[, used, default]), ops..., write)
+ * (reference include/cvGPUSpeedup.cuh:285-442 -> fk::Warping<WT, PerThreadRead> fkl/.../image_processing/warping.cuh:
+ * 43-91, which shares fk::Interpolate<INTER_LINEAR> with the resize).  For plane z and destination pixel (x, y):
+ *   affine       sx = (m00*x + m01*y) + m02,  sy = (m10*x + m11*y) + m12
+ *   perspective  c = 1 / ((m20*x + m21*y) + m22),  sx = c * ((m00*x + m01*y) + m02),  sy = c * (...)
+ * with m the INVERSE transform (destination -> source; the cvGS wrapper inverts the user's matrix on the host and
+ * casts it to float); inside [0, w) x [0, h) the pixel is the bilinear interpolation at (sx, sy), outside it is 0;
+ * the op chain and the output forms are those of the resize pipeline (pipeline->aspect_mode is ignored).
+ * CV_8UC3 sources, direct-gather kernel.
+ * ------------------------------------------------------------------------------------------ */
+enum cvgs_warp_type { CVGS_WARP_AFFINE = 0, CVGS_WARP_PERSPECTIVE = 1 };
+typedef struct cvgs_warp {
+    int32_t type; /* enum cvgs_warp_type                                              */
+    float m[9];   /* inverse transform, row-major; affine uses m[0..5]                */
+} cvgs_warp_t;
+int cvgs_b200_warp_launch(const cvgs_crop_t* images, const cvgs_warp_t* warps, int32_t n_planes, int32_t used,
+                          const cvgs_pipeline_t* pipeline, void* stream);
 
 /* Same pipeline with HOST buffers, for callers that hold frames in (pinned) host memory:
  * copies the source image to the device, launches, copies the tensor back, all on `stream`

@@ -195,6 +195,42 @@ static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspec
     }
 }
 
+/* One output pixel of fk::Warping<WT, PerThreadRead<_2D, uchar3>> (warping.cuh:43-91): WarpingCoords (:43-63), the
+ * bounds test (:78-82) and Interpolate<INTER_LINEAR> at the warped coordinate (interpolation.cuh:57-92).  Rounding
+ * sequence of the reference's SASS: FMUL(m01*y), FFMA(m00, x, .), FADD(m02) per row; perspective multiplies by the
+ * correctly rounded reciprocal of the third row. */
+static void warp_pixel(const cvgs_crop_t* c, const cvgs_warp_t* wp, int x, int y, float out[3]) {
+    const float fx = (float)x, fy = (float)y;
+    const float* m = wp->m;
+    float sx = fmaf(m[0], fx, m[1] * fy) + m[2];
+    float sy = fmaf(m[3], fx, m[4] * fy) + m[5];
+    if (wp->type == CVGS_WARP_PERSPECTIVE) {
+        const float coeff = 1.0f / (fmaf(m[6], fx, m[7] * fy) + m[8]);
+        sx = coeff * sx;
+        sy = coeff * sy;
+    }
+    if (!(sx >= 0.f && sx < (float)c->width && sy >= 0.f && sy < (float)c->height)) {
+        out[0] = out[1] = out[2] = 0.f;
+        return;
+    }
+    const int x1 = (int)floorf(sx), y1 = (int)floorf(sy);
+    const int x2 = x1 + 1, y2 = y1 + 1;
+    const int x2r = x2 < c->width - 1 ? x2 : c->width - 1;
+    const int y2r = y2 < c->height - 1 ? y2 : c->height - 1;
+    const float wx1 = sx - (float)x1, wx0 = (float)x2 - sx;
+    const float wy1 = sy - (float)y1, wy0 = (float)y2 - sy;
+    const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+    const uint8_t* r0 = (const uint8_t*)c->data + (size_t)y1 * (size_t)c->pitch;
+    const uint8_t* r1 = (const uint8_t*)c->data + (size_t)y2r * (size_t)c->pitch;
+    for (int ch = 0; ch < 3; ++ch) {
+        float t = (float)r0[3 * x2r + ch] * w10;
+        t = fmaf((float)r0[3 * x1 + ch], w00, t);
+        t = fmaf((float)r1[3 * x1 + ch], w01, t);
+        t = fmaf((float)r1[3 * x2r + ch], w11, t);
+        out[ch] = t;
+    }
+}
+
 /* Unary/Binary op chain, TransformDPP::operate (data_parallel_patterns.cuh:66-79);
  * Mul/Sub/Div/Add arithmetic.cuh:43-68; VectorReorder cuda_vector.cuh:45-54. */
 static void apply_chain(const cvgs_pipeline_t* p, float v[4]) {
@@ -252,7 +288,8 @@ static void store_pixel(const cvgs_pipeline_t* p, int n_planes, int z, int y, in
         const int64_t rp = p->out_row_pitch ? p->out_row_pitch : 3 * W;
         const int64_t ps = p->out_plane_stride ? p->out_plane_stride : rp * H;
         uint8_t* b = (uint8_t*)p->out + z * ps + y * rp + 3 * x;
-        for (int c = 0; c < 3; ++c) b[c] = (uint8_t)round_sat_u8(v[c]);
+        for (int c = 0; c < 3; ++c)  /* u8_cast: fk::Cast = static_cast (truncation, cast.cuh:22-29) */
+            b[c] = p->u8_cast ? (uint8_t)(unsigned)v[c] : (uint8_t)round_sat_u8(v[c]);
         return;
     }
     switch (p->out_layout) {
@@ -318,6 +355,35 @@ int oracle_preproc(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_
         }
     }
     free(geoms);
+    return 0;
+}
+
+/* Batched warp + chain + write: BatchRead<N, CONDITIONAL_WITH_DEFAULT> of Warping ops (cvGPUSpeedup.cuh:285-442). */
+int oracle_warp(const cvgs_crop_t* images, const cvgs_warp_t* warps, int n_planes, int used, const cvgs_pipeline_t* p,
+                int nthreads) {
+    if (!images || !warps || !p || !p->out || n_planes <= 0 || used < 0 || p->src_type != CVGS_8UC3 || p->dst_width <= 0 ||
+        p->dst_height <= 0 || p->n_ops < 0 || p->n_ops > CVGS_MAX_OPS)
+        return 1;
+    if (used > n_planes) used = n_planes;
+    const int H = p->dst_height, W = p->dst_width;
+    const long total_rows = (long)n_planes * H;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 8) num_threads(nthreads)
+#endif
+    for (long row = 0; row < total_rows; ++row) {
+        const int z = (int)(row / H), y = (int)(row % H);
+        for (int x = 0; x < W; ++x) {
+            float v[4];
+            if (z >= used) {
+                v[0] = p->background[0]; v[1] = p->background[1]; v[2] = p->background[2]; v[3] = 0.f;
+            } else {
+                warp_pixel(&images[z], &warps[z], x, y, v);
+            }
+            apply_chain(p, v);
+            store_pixel(p, n_planes, z, y, x, v);
+        }
+    }
     return 0;
 }
 

@@ -225,6 +225,51 @@ int FKREF_CAT(fkref_nv12_, FKREF_BATCH)(int standard, const void* data, int w, i
 }
 #endif
 
+#ifdef FKREF_WARP
+// One image through fk::Warping<WT, PerThreadRead<_2D, uchar3>> (tests/warping/test_warping_opencv.cu:60-64):
+//   mode 0:  warp -> Mul(mul) -> TensorSplit into float out[3][dst_h][dst_w]
+//   mode 1:  warp -> Cast<float3, uchar3> -> PerThreadWrite into packed uchar3 out (row pitch out_pitch bytes)
+// m is the inverse transform the wrapper hands to the kernel (cvGPUSpeedup.cuh:266-283), row-major.
+}  // extern "C"
+#include <fused_kernel/algorithms/image_processing/warping.cuh>
+#include <fused_kernel/algorithms/basic_ops/cast.cuh>
+namespace {
+template <fk::WarpType WT>
+int run_warp(int mode, const void* data, int w, int h, int pitch, const float* m, int dst_w, int dst_h, const float* mul,
+             void* out, int out_pitch, cudaStream_t stream) {
+    const auto read = fk::PerThreadRead<fk::_2D, uchar3>::build(
+        fk::RawPtr<fk::_2D, uchar3>{ (uchar3*)data, { (uint)w, (uint)h, (uint)pitch } });
+    fk::WarpingParameters<WT> params{};
+    for (int r = 0; r < (WT == fk::Affine ? 2 : 3); ++r)
+        for (int c = 0; c < 3; ++c) params.transformMatrix.data[r][c] = m[3 * r + c];
+    params.dstSize = fk::Size(dst_w, dst_h);
+    const auto warp = fk::Warping<WT, std::decay_t<decltype(read)>>::build({ params, read });
+    if (mode == 0) {
+        const fk::Tensor<float> t_out((float*)out, dst_w, dst_h, 1, 3);
+        fk::executeOperations(stream, warp, fk::Binary<fk::Mul<float3>>{ float3{mul[0], mul[1], mul[2]} },
+                              fk::Write<fk::TensorSplit<float3>>{ t_out.ptr() });
+    } else {
+        const fk::RawPtr<fk::_2D, uchar3> o{ (uchar3*)out, { (uint)dst_w, (uint)dst_h, (uint)out_pitch } };
+        fk::executeOperations(stream, warp, fk::Unary<fk::Cast<float3, uchar3>>{},
+                              fk::Write<fk::PerThreadWrite<fk::_2D, uchar3>>{ o });
+    }
+    return 0;
+}
+}  // namespace
+extern "C" {
+int FKREF_CAT(fkref_warp_, FKREF_BATCH)(int type, int mode, const void* data, int w, int h, int pitch, const float* m,
+                                        int dst_w, int dst_h, const float* mul, void* out, int out_pitch, void* stream) {
+    try {
+        cudaStream_t s = (cudaStream_t)stream;
+        if (type == 0) return run_warp<fk::Affine>(mode, data, w, h, pitch, m, dst_w, dst_h, mul, out, out_pitch, s);
+        return run_warp<fk::Perspective>(mode, data, w, h, pitch, m, dst_w, dst_h, mul, out, out_pitch, s);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+#endif
+
 const char* FKREF_CAT(fkref_last_error_, FKREF_BATCH)(void) { return g_err.c_str(); }
 
 }  // extern "C"

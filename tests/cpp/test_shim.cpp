@@ -4,6 +4,8 @@
 //   2. tests/batchread/test_circularbatchread_x_write3D.cu:286-335,391,448  CircularTensor after 100 updates
 //   3. tests/unit_tests/test_split.cu:47-62  (1,2,3) -> planes 1,2,3
 //   4. random image vs the CPU oracle, bit for bit (the reference has no such test: SURVEY F2)
+//   6. tests/warping/test_warping_opencv.cu:34-197  affine / perspective / batched perspective warp + fk::Cast + write,
+//      against the oracle (cv::cuda::warpAffine is not in this image), plus exact checks of the translation case
 //   5. error convention: std::runtime_error (gpuErrchk, fkl/.../core/utils/utils.h:42-60)
 #include <cmath>
 #include <cstdio>
@@ -13,6 +15,8 @@
 
 #include "../../cvgpuspeedup_b200/include/cvGPUSpeedup.cuh"
 
+extern "C" int oracle_warp(const cvgs_crop_t* images, const cvgs_warp_t* warps, int n_planes, int used, const cvgs_pipeline_t* p,
+                           int nthreads);
 extern "C" int oracle_preproc(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_pipeline_t* p, int nthreads);
 
 #define REQUIRE(cond)                                                        \
@@ -237,6 +241,102 @@ static int test_random_vs_oracle() {
     return 0;
 }
 
+static int test_warping() {
+    constexpr int W = 420, H = 410;
+    std::mt19937 rng(11);
+    cv::cuda::GpuMat d_img(H, W, CV_8UC3);
+    std::vector<uchar> h_img(d_img.step * H);
+    for (auto& b : h_img) b = static_cast<uchar>(rng());
+    REQUIRE(cudaMemcpy(d_img.data, h_img.data(), h_img.size(), cudaMemcpyHostToDevice) == cudaSuccess);
+    const cvgs_crop_t h_image{h_img.data(), W, H, static_cast<int32_t>(d_img.step), 0};
+    cv::cuda::Stream stream;
+    const cv::Size size(W, H);
+    auto oracle_u8 = [&](const std::vector<cvgs_warp_t>& warps, std::vector<uchar>& out) {
+        std::vector<cvgs_crop_t> images(warps.size(), h_image);
+        cvgs_pipeline_t p{};
+        p.src_type = CVGS_8UC3;
+        p.dst_width = W;
+        p.dst_height = H;
+        p.aspect_mode = CVGS_IGNORE_AR;
+        p.out_layout = CVGS_OUT_NHWC;
+        p.dst_type = CVGS_8UC3;
+        p.u8_cast = 1;
+        out.assign(warps.size() * 3 * W * H, 0);
+        p.out = out.data();
+        return oracle_warp(images.data(), warps.data(), static_cast<int>(warps.size()), static_cast<int>(warps.size()), &p, 0);
+    };
+    auto download = [&](const cv::cuda::GpuMat& m, std::vector<uchar>& out) {
+        out.resize(static_cast<size_t>(3) * m.cols * m.rows);
+        return cudaMemcpy2D(out.data(), 3 * m.cols, m.data, m.step, 3 * m.cols, m.rows, cudaMemcpyDeviceToHost) == cudaSuccess;
+    };
+
+    // testAffine (:84-123): translation by (50, 100)
+    {
+        const double tx = 50, ty = 100;
+        cv::Mat affine_matrix = (cv::Mat_<double>(2, 3) << 1, 0, tx, 0, 1, ty);
+        cv::cuda::GpuMat d_result(H, W, CV_8UC3);
+        const auto warpFunc = cvGS::warp<fk::WarpType::Affine, CV_8UC3>(d_img, affine_matrix, size);
+        cvGS::executeOperations(stream, warpFunc, fk::Cast<float3, uchar3>::build(), cvGS::write<CV_8UC3>(d_result));
+        stream.waitForCompletion();
+        std::vector<uchar> got, want;
+        REQUIRE(download(d_result, got));
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x)
+                for (int c = 0; c < 3; ++c) {
+                    const uchar expect = (x >= 50 && y >= 100) ? h_img[(y - 100) * d_img.step + 3 * (x - 50) + c] : 0;
+                    REQUIRE(got[(static_cast<size_t>(y) * W + x) * 3 + c] == expect);
+                }
+        cvgs_warp_t w{};
+        w.type = CVGS_WARP_AFFINE;
+        const float inv[6] = {1, 0, -50, 0, 1, -100};
+        std::memcpy(w.m, inv, sizeof inv);
+        REQUIRE(oracle_u8({w}, want) == 0);
+        REQUIRE(got == want);
+    }
+    // testPerspective (:34-82) and testPerspectiveBatch (:125-197)
+    {
+        cv::Point2f src_points[4] = {cv::Point2f(56, 65), cv::Point2f(368, 52), cv::Point2f(28, 387), cv::Point2f(389, 390)};
+        cv::Point2f dst1[4] = {cv::Point2f(0, 0), cv::Point2f(300, 0), cv::Point2f(0, 300), cv::Point2f(300, 300)};
+        cv::Point2f dst2[4] = {cv::Point2f(0, 0), cv::Point2f(200, 0), cv::Point2f(0, 200), cv::Point2f(200, 200)};
+        const cv::Mat m1 = cv::getPerspectiveTransform(src_points, dst1);
+        const cv::Mat m2 = cv::getPerspectiveTransform(src_points, dst2);
+        // the forward matrix maps the source points onto the destination points
+        for (int i = 0; i < 4; ++i) {
+            const double* h = m1.ptr<double>();
+            const double d = h[6] * src_points[i].x + h[7] * src_points[i].y + h[8];
+            REQUIRE(std::fabs((h[0] * src_points[i].x + h[1] * src_points[i].y + h[2]) / d - dst1[i].x) < 1e-6);
+            REQUIRE(std::fabs((h[3] * src_points[i].x + h[4] * src_points[i].y + h[5]) / d - dst1[i].y) < 1e-6);
+        }
+        cv::cuda::GpuMat d_result(H, W, CV_8UC3);
+        cvGS::executeOperations(stream, cvGS::warp<fk::WarpType::Perspective, CV_8UC3>(d_img, m1, size),
+                                fk::Cast<float3, uchar3>::build(), cvGS::write<CV_8UC3>(d_result));
+        stream.waitForCompletion();
+        std::vector<uchar> got, want;
+        REQUIRE(download(d_result, got));
+        const cvgs_warp_t w1 = cvGS::detail::inverse_of<fk::WarpType::Perspective>(m1);
+        const cvgs_warp_t w2 = cvGS::detail::inverse_of<fk::WarpType::Perspective>(m2);
+        REQUIRE(oracle_u8({w1}, want) == 0);
+        REQUIRE(got == want);
+        size_t nonzero = 0;
+        for (uchar b : got) nonzero += b != 0;
+        REQUIRE(nonzero > got.size() / 4);
+
+        constexpr size_t NUM_IMGS = 5;
+        const std::array<cv::cuda::GpuMat, NUM_IMGS> d_imgs = {d_img, d_img, d_img, d_img, d_img};
+        const std::array<cv::Mat, NUM_IMGS> mats = {m1, m2, m1, m2, m1};
+        cv::cuda::GpuMat d_batch(static_cast<int>(NUM_IMGS) * H, W, CV_8UC3);
+        d_batch.step = 3 * W;  // a tight tensor of five images, as write<CV_8UC3>(GpuMat, Size) defines it
+        cvGS::executeOperations(stream, cvGS::warp<fk::WarpType::Perspective, CV_8UC3, NUM_IMGS>(d_imgs, mats, size),
+                                fk::Cast<float3, uchar3>::build(), cvGS::write<CV_8UC3>(d_batch, size));
+        stream.waitForCompletion();
+        std::vector<uchar> gotb(NUM_IMGS * 3 * W * H), wantb;
+        REQUIRE(cudaMemcpy(gotb.data(), d_batch.data, gotb.size(), cudaMemcpyDeviceToHost) == cudaSuccess);
+        REQUIRE(oracle_u8({w1, w2, w1, w2, w1}, wantb) == 0);
+        REQUIRE(gotb == wantb);
+    }
+    return 0;
+}
+
 static int test_error_convention() {
     cv::cuda::GpuMat d_input(16, 16, CV_8UC3, cv::Scalar(1, 2, 3));
     cv::cuda::GpuMat d_null;  // data == nullptr
@@ -264,6 +364,7 @@ int main() {
     failed += test_batchread_x_write3D();
     failed += test_resize_write_8u();
     failed += test_random_vs_oracle();
+    failed += test_warping();
     failed += test_error_convention();
     std::printf(failed ? "test_shim: %d FAILED\n" : "test_shim: all passed\n", failed);
     return failed ? 1 : 0;

@@ -170,3 +170,28 @@ def run_fkref_nv12(frame, width, height, dsize, standard, mul, sub, div, d_frame
     assert rc == 0
     torch.cuda.synchronize()
     return out.cpu().numpy()
+
+
+def run_fkref_warp(image, width, height, warp_type, inverse, dsize, mul=None, d_image=None):
+    """The reference's fk::Warping<WT, PerThreadRead<_2D, uchar3>> on one image (oracle/_ref/libfkref_16.so, built with
+    -DFKREF_WARP): mul given -> Mul + TensorSplit, float [3, H, W]; mul None -> fk::Cast<float3, uchar3> + packed write,
+    uint8 [H, W, 3].  `inverse`: nine floats, destination -> source."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libfkref_16.so")
+    lib = C.CDLL(path)
+    fn = lib.fkref_warp_16
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int,
+                   C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_void_p]
+    d = device_image(image) if d_image is None else d_image
+    m = (C.c_float * 9)(*[float(v) for v in inverse])
+    if mul is not None:
+        out = torch.full((3, dsize[1], dsize[0]), float("nan"), dtype=torch.float32, device="cuda")
+        rc = fn(warp_type, 0, d.data_ptr(), width, height, image.shape[1], m, dsize[0], dsize[1], (C.c_float * 3)(*mul),
+                out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    else:
+        out = torch.full((dsize[1], dsize[0], 3), 77, dtype=torch.uint8, device="cuda")
+        rc = fn(warp_type, 1, d.data_ptr(), width, height, image.shape[1], m, dsize[0], dsize[1], None,
+                out.data_ptr(), 3 * dsize[0], torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return out.cpu().numpy()

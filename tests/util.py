@@ -46,6 +46,9 @@ def oracle_lib() -> C.CDLL:
         lib.oracle_ct_temp.argtypes = [C.c_void_p]
         lib.oracle_ct_update.restype = C.c_int
         lib.oracle_ct_update.argtypes = [C.c_void_p, C.POINTER(_abi.Crop), C.POINTER(_abi.Pipeline), C.c_int]
+        lib.oracle_warp.restype = C.c_int
+        lib.oracle_warp.argtypes = [C.POINTER(_abi.Crop), C.POINTER(_abi.Warp), C.c_int, C.c_int,
+                                    C.POINTER(_abi.Pipeline), C.c_int]
         lib.oracle_has_fma.restype = C.c_int
         lib.oracle_max_threads.restype = C.c_int
         assert lib.oracle_has_fma() == 1, "host CPU lacks FMA: the oracle would not be exact"
@@ -135,7 +138,7 @@ _KIND = {"mul": _abi.OP_MUL, "sub": _abi.OP_SUB, "div": _abi.OP_DIV, "add": _abi
 
 def make_pipeline(dsize, ops, aspect=_abi.IGNORE_AR, background=(0, 0, 0), fp_contract=_abi.FP_REFERENCE_FUSED,
                   interp_mode=_abi.INTERP_FLOAT, layout=_abi.OUT_NCHW, out_ptr=0, plane_stride=0,
-                  src_type=_abi.CVGS_8UC3, dst_type=0, row_pitch=0, yuv_standard=0) -> _abi.Pipeline:
+                  src_type=_abi.CVGS_8UC3, dst_type=0, row_pitch=0, yuv_standard=0, u8_cast=0) -> _abi.Pipeline:
     p = _abi.Pipeline()
     p.src_type = src_type
     p.dst_width, p.dst_height = dsize
@@ -153,6 +156,7 @@ def make_pipeline(dsize, ops, aspect=_abi.IGNORE_AR, background=(0, 0, 0), fp_co
     p.out_layout, p.out, p.out_plane_stride = layout, out_ptr, plane_stride
     p.dst_type, p.out_row_pitch = dst_type, row_pitch
     p.yuv_standard = yuv_standard
+    p.u8_cast = u8_cast
     return p
 
 
