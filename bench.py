@@ -265,8 +265,10 @@ def workload_config(n_frames: int):
             "l2_policy": f"inputs larger than L2: {n_frames} rotating frame/tensor sets = "
                          f"{n_frames * (FRAME[1] * PITCH + CROPS_PER_FRAME * 3 * DST[0] * DST[1] * 4) / 1e6:.0f} MB",
             "fp_contract": "reference_fused", "interp_mode": "float", "sharding": "frames per GPU, no collective",
-            "launch_api": "cvgs_b200_preproc_launch_ex (crops + parent frame), consecutive independent frames may "
-                          "overlap (cvgs_b200_set_overlap(1))"}
+            "launch_api": "cvgs_b200_preproc_launch_sequence_ex -> one cvgs_b200_preproc_launch_ex (crops + parent frame) "
+                          "per frame; consecutive independent frames may overlap (cvgs_b200_set_overlap(1)) and the "
+                          "frame loop is driven by several host threads, one stream each",
+            "host_threads": int(os.environ.get("CVGS_B200_SEQ_THREADS", "3"))}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -554,7 +556,10 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int):
                      "traffic": traffic, "kernel": "preproc kernel (one launch per frame)", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_in + bytes_out, "bytes_in": bytes_in, "bytes_out": bytes_out,
                      "us_per_launch": us_per_launch,
-                     "note": "50 crops = 6 MB per launch: launch-latency-bound (SURVEY F6); see c3 in 'extra'"},
+                     "note": "us_per_launch = timed region / launches (frames of different host threads overlap on the "
+                             "GPU, so this is the effective per-launch time); 50 crops = 7.5 MB per launch, one host "
+                             "thread alone is launch-bound at ~3.9 us (SURVEY F6); see c3 in 'extra' for the same "
+                             "kernel on a 256-crop batch"},
         "clocks": sampler.summary(),
     }
     if extra:

@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cvgs_device.cuh"
@@ -77,6 +78,9 @@ struct StreamTrack {
 static std::mutex g_track_mu;
 static StreamTrack g_tracks[16];
 
+// set by the multi-threaded frame loop: several launches are resident at once, so fewer, longer-lived CTAs per launch
+// measured best there (8 items per warp: 2.13 us per 50-crop frame; 4: 2.32; 16: 2.20)
+static thread_local int t_items_hint = 0;
 // Items per warp small launches aim for: 1 in plain stream order (latency), more when launches overlap (throughput).
 static int items_per_warp() {
     static const int forced = [] {
@@ -84,6 +88,7 @@ static int items_per_warp() {
         return e ? std::max(1, std::atoi(e)) : 0;
     }();
     if (forced) return forced;
+    if (t_items_hint) return t_items_hint;
     return g_overlap.load(std::memory_order_relaxed) ? 4 : 1;
 }
 
@@ -814,17 +819,167 @@ int cvgs_b200_preproc_launch_sequence(const cvgs_crop_t* const* crops, const int
     return CVGS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Frame loop over several host threads.  One launch costs the host 3-4 us (descriptor fill, plan, tensor-map lookup,
+// cudaLaunchKernelEx) and the GPU about as long for a 50-crop frame, so a loop driven by one thread is host-bound.
+// When the argument sets of a sequence are provably independent (outputs pairwise disjoint, no output overlaps a
+// source) the loop is split by argument set over the calling thread and a few helper threads, each launching into
+// its own stream: set s always goes to worker s % T, so repeated uses of one set stay in stream order, and the
+// caller's stream is forked into / joined from the helper streams with events -- seen from that stream the loop is
+// still one operation.  Only with cvgs_b200_set_overlap(1) (the caller allowed the library to reorder independent
+// launches) and outside stream capture.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSeqMaxWorkers = 4;
+struct SeqStreams {
+    cudaStream_t stream[kSeqMaxWorkers] = {};
+    cudaEvent_t done[kSeqMaxWorkers] = {};
+    cudaEvent_t start = nullptr;
+    int device = -1;
+};
+static std::mutex g_seq_mu;  // one multi-threaded sequence at a time per process (they would share the helper streams)
+static SeqStreams g_seq;
+
+static int seq_workers() {
+    static const int n = [] {
+        const char* e = std::getenv("CVGS_B200_SEQ_THREADS");
+        return e ? std::max(1, std::min(kSeqMaxWorkers, std::atoi(e))) : 3;  // measured: 1: 3.85, 2: 2.73, 3: 2.32, 4: 2.29 us per frame
+    }();
+    return n;
+}
+
+// Conservative independence proof over the argument sets of a sequence.
+static bool sequence_sets_independent(const cvgs_crop_t* const* crops, const int32_t* n_planes, const int32_t* used,
+                                      const cvgs_pipeline_t* const* pipelines, int n_sets) {
+    if (n_sets > 256) return false;
+    std::vector<MemRange> outs(n_sets), srcs(n_sets);
+    for (int s = 0; s < n_sets; ++s) {
+        const cvgs_pipeline_t* p = pipelines[s];
+        if (!p || !p->out || !crops[s] || n_planes[s] <= 0 || used[s] < 0) return false;
+        if (validate_pipeline(p) != CVGS_OK) return false;
+        if (p->out_layout == CVGS_OUT_PLANES || p->dst_type == CVGS_8UC3 || p->src_type == CVGS_NV12) return false;
+        PreprocParams P;
+        if (build_params(*p, n_planes[s], std::min(used[s], n_planes[s]), static_cast<float*>(p->out), P) != CVGS_OK) return false;
+        const long long plane = static_cast<long long>(P.W) * P.H;
+        const int nc = P.nc;
+        const long long extent = P.out.px_stride == 1 ? (nc - 1) * P.out.c_stride + (P.n_planes - 1) * P.out.z_stride + plane
+                                                      : (P.n_planes - 1) * P.out.z_stride + nc * plane;
+        outs[s].lo = reinterpret_cast<uintptr_t>(p->out);
+        outs[s].hi = outs[s].lo + static_cast<uintptr_t>(extent) * sizeof(float);
+        const int px = pixel_bytes_of(p->src_type);
+        MemRange r;
+        r.lo = ~static_cast<uintptr_t>(0);
+        for (int i = 0; i < std::min(used[s], n_planes[s]); ++i) {
+            const cvgs_crop_t& c = crops[s][i];
+            if (!c.data || c.width <= 0 || c.height <= 0 || c.pitch <= 0) return false;
+            const uintptr_t lo = reinterpret_cast<uintptr_t>(c.data);
+            r.lo = std::min(r.lo, lo);
+            r.hi = std::max(r.hi, lo + static_cast<uintptr_t>(c.height - 1) * c.pitch + static_cast<uintptr_t>(px) * c.width);
+        }
+        if (r.lo > r.hi) r.lo = r.hi = 0;
+        srcs[s] = r;
+    }
+    for (int a = 0; a < n_sets; ++a)
+        for (int b = 0; b < n_sets; ++b) {
+            if (outs[a].overlaps(srcs[b])) return false;
+            if (a < b && outs[a].overlaps(outs[b])) return false;
+        }
+    return true;
+}
+
 int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const cvgs_parent_t* const* parents,
                                          const int32_t* n_planes, const int32_t* used,
                                          const cvgs_pipeline_t* const* pipelines, int32_t n_sets, int32_t steps,
-                                         void* stream) {
+                                         void* stream_) {
     if (!crops || !parents || !n_planes || !used || !pipelines || n_sets <= 0 || steps < 0)
         return fail(CVGS_ERR_INVALID_VALUE, "bad sequence arguments");
-    for (int i = 0; i < steps; ++i) {
-        const int s = i % n_sets;
-        if (int rc = cvgs_b200_preproc_launch_ex(crops[s], parents[s], n_planes[s], used[s], pipelines[s], stream)) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int workers = std::min(seq_workers(), static_cast<int>(n_sets));
+    if (workers > 1 && (steps < 128 || !g_overlap.load(std::memory_order_relaxed))) workers = 1;
+    if (workers > 1) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) workers = 1;
     }
-    return CVGS_OK;
+    if (workers > 1 && !sequence_sets_independent(crops, n_planes, used, pipelines, n_sets)) workers = 1;
+    std::unique_lock<std::mutex> seq_lock(g_seq_mu, std::defer_lock);
+    if (workers > 1 && !seq_lock.try_lock()) workers = 1;
+    if (workers <= 1) {
+        for (int i = 0; i < steps; ++i) {
+            const int s = i % n_sets;
+            if (int rc = cvgs_b200_preproc_launch_ex(crops[s], parents[s], n_planes[s], used[s], pipelines[s], stream)) return rc;
+        }
+        return CVGS_OK;
+    }
+
+    int device = 0;
+    CVGS_CUDA(cudaGetDevice(&device));
+    SeqStreams& Q = g_seq;
+    if (Q.device != device) {
+        for (int i = 1; i < kSeqMaxWorkers; ++i) {
+            if (Q.stream[i]) { cudaStreamDestroy(Q.stream[i]); Q.stream[i] = nullptr; }
+            if (Q.done[i]) { cudaEventDestroy(Q.done[i]); Q.done[i] = nullptr; }
+            CVGS_CUDA(cudaStreamCreateWithFlags(&Q.stream[i], cudaStreamNonBlocking));
+            CVGS_CUDA(cudaEventCreateWithFlags(&Q.done[i], cudaEventDisableTiming));
+        }
+        if (Q.start) { cudaEventDestroy(Q.start); Q.start = nullptr; }
+        CVGS_CUDA(cudaEventCreateWithFlags(&Q.start, cudaEventDisableTiming));
+        Q.device = device;
+    }
+    CVGS_CUDA(cudaEventRecord(Q.start, stream));
+    struct Result {
+        int rc = CVGS_OK;
+        std::string err;
+        int64_t launches = 0;
+    };
+    Result res[kSeqMaxWorkers];
+    auto run = [&](int w, cudaStream_t st) {
+        t_items_hint = 8;
+        int rc = CVGS_OK;
+        for (int i = 0; i < steps && rc == CVGS_OK; ++i) {
+            const int s = i % n_sets;
+            if (s % workers != w) continue;
+            rc = cvgs_b200_preproc_launch_ex(crops[s], parents[s], n_planes[s], used[s], pipelines[s], st);
+        }
+        t_items_hint = 0;
+        return rc;
+    };
+    std::thread helpers[kSeqMaxWorkers];
+    for (int w = 1; w < workers; ++w) {
+        helpers[w] = std::thread([&, w] {
+            Result& r = res[w];
+            if (cudaSetDevice(device) != cudaSuccess || cudaStreamWaitEvent(Q.stream[w], Q.start, 0) != cudaSuccess) {
+                r.rc = CVGS_ERR_INVALID_VALUE;
+                r.err = "sequence helper: cannot attach to the device";
+                return;
+            }
+            const int64_t before = t_launch_count;
+            r.rc = run(w, Q.stream[w]);
+            if (r.rc != CVGS_OK) r.err = t_last_error;
+            r.launches = t_launch_count - before;
+            if (cudaEventRecord(Q.done[w], Q.stream[w]) != cudaSuccess && r.rc == CVGS_OK) {
+                r.rc = CVGS_ERR_INVALID_VALUE;
+                r.err = "sequence helper: cudaEventRecord failed";
+            }
+        });
+    }
+    res[0].rc = run(0, stream);
+    if (res[0].rc != CVGS_OK) res[0].err = t_last_error;
+    int rc = res[0].rc;
+    for (int w = 1; w < workers; ++w) {
+        helpers[w].join();
+        // join the helper stream even after an error: whatever it launched must finish before the caller's stream goes on
+        const cudaError_t e = cudaStreamWaitEvent(stream, Q.done[w], 0);
+        t_launch_count += res[w].launches;
+        if (rc == CVGS_OK && res[w].rc != CVGS_OK) {
+            rc = res[w].rc;
+            res[0].err = res[w].err;
+        }
+        if (rc == CVGS_OK && e != cudaSuccess) {
+            rc = static_cast<int>(e);
+            res[0].err = std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(e);
+        }
+    }
+    if (rc != CVGS_OK) t_last_error = res[0].err;
+    return rc;
 }
 
 int cvgs_b200_preproc_host_sequence(const void* const* host_images, int32_t image_width, int32_t image_height,

@@ -174,3 +174,80 @@ def test_concurrent_host_threads():
         t.join()
     lib.cvgs_b200_set_overlap(prev)
     assert not errors, errors
+
+
+def _sequence(lib, ws, d_imgs, outs, steps, stream):
+    n = len(ws)
+    keep = []
+    for w, d, o in zip(ws, d_imgs, outs):
+        crops = util.host_crops(w.image, w.rects, base_ptr=d.data_ptr())
+        par = util.host_parents(w.image, w.width, w.height, len(w.rects), base_ptr=d.data_ptr())
+        p = util.make_pipeline(w.dsize, w.ops, out_ptr=o.data_ptr())
+        keep.append((crops, par, p))
+    crops_pp = (C.POINTER(_abi.Crop) * n)(*[C.cast(k[0], C.POINTER(_abi.Crop)) for k in keep])
+    par_pp = (C.POINTER(_abi.Parent) * n)(*[C.cast(k[1], C.POINTER(_abi.Parent)) for k in keep])
+    pipes_pp = (C.POINTER(_abi.Pipeline) * n)(*[C.pointer(k[2]) for k in keep])
+    n_arr = (C.c_int32 * n)(*[len(w.rects) for w in ws])
+    before = lib.cvgs_b200_launch_count()
+    _abi.check(lib.cvgs_b200_preproc_launch_sequence_ex(crops_pp, par_pp, n_arr, n_arr, pipes_pp, n, steps,
+                                                        stream.cuda_stream))
+    return lib.cvgs_b200_launch_count() - before, keep
+
+
+def test_frame_loop_over_several_host_threads(overlap_on):
+    """steps >= 128 with independent argument sets: the loop is split over helper threads and streams
+    (include/cvgs_b200.h); every frame's result, the launch count and the ordering on the caller's stream hold."""
+    lib = overlap_on
+    st = torch.cuda.Stream()
+    ws = [util.workload_c2(seed=700 + k, n=50, pitch=6144) for k in range(7)]
+    d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
+    outs = [torch.full((50, 3, 128, 64), float("nan"), device="cuda") for _ in ws]
+    want = [util.run_oracle(w.image, w.rects, w.dsize, w.ops) for w in ws]
+    with torch.cuda.stream(st):
+        launches, keep = _sequence(lib, ws, d_imgs, outs, 7 * 30, st)
+        # work queued behind the loop on the caller's stream must see every frame complete, whichever stream ran it
+        copies = [o.clone() for o in outs]
+    st.synchronize()
+    assert launches == 7 * 30
+    for k, (o, c) in enumerate(zip(outs, copies)):
+        util.assert_bit_equal(o.cpu().numpy(), want[k], f"set {k}")
+        util.assert_bit_equal(c.cpu().numpy(), want[k], f"set {k}: copy queued after the loop")
+    del keep
+
+
+def test_frame_loop_with_dependent_sets_stays_in_order(overlap_on):
+    """Two argument sets that write the same tensor are not independent: the loop must run in plain order, so the
+    last call (set 1) wins; a set whose source is another set's output likewise."""
+    lib = overlap_on
+    st = torch.cuda.Stream()
+    ws = [util.workload_c2(seed=720 + k, n=50, pitch=6144) for k in range(2)]
+    d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
+    out = torch.full((50, 3, 128, 64), float("nan"), device="cuda")
+    launches, keep = _sequence(lib, ws, d_imgs, [out, out], 2 * 80, st)
+    st.synchronize()
+    assert launches == 160
+    util.assert_bit_equal(out.cpu().numpy(), util.run_oracle(ws[1].image, ws[1].rects, ws[1].dsize, ws[1].ops), "last writer wins")
+    del keep
+
+
+def test_frame_loop_error_is_reported(overlap_on):
+    lib = overlap_on
+    st = torch.cuda.Stream()
+    ws = [util.workload_c2(seed=730 + k, n=10, frame=(640, 480), pitch=1920) for k in range(4)]
+    d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
+    outs = [torch.zeros((10, 3, 128, 64), device="cuda") for _ in ws]
+    n = 4
+    keep = []
+    for i, (w, d, o) in enumerate(zip(ws, d_imgs, outs)):
+        crops = util.host_crops(w.image, w.rects, base_ptr=d.data_ptr())
+        if i == 3:
+            crops[2].pitch = 1  # smaller than a row: rejected when that set is launched (by a helper thread)
+        par = util.host_parents(w.image, w.width, w.height, len(w.rects), base_ptr=d.data_ptr())
+        keep.append((crops, par, util.make_pipeline(w.dsize, w.ops, out_ptr=o.data_ptr())))
+    crops_pp = (C.POINTER(_abi.Crop) * n)(*[C.cast(k[0], C.POINTER(_abi.Crop)) for k in keep])
+    par_pp = (C.POINTER(_abi.Parent) * n)(*[C.cast(k[1], C.POINTER(_abi.Parent)) for k in keep])
+    pipes_pp = (C.POINTER(_abi.Pipeline) * n)(*[C.pointer(k[2]) for k in keep])
+    n_arr = (C.c_int32 * n)(*[10] * n)
+    rc = lib.cvgs_b200_preproc_launch_sequence_ex(crops_pp, par_pp, n_arr, n_arr, pipes_pp, n, 400, st.cuda_stream)
+    st.synchronize()
+    assert rc != 0 and b"pitch" in lib.cvgs_b200_last_error()
