@@ -22,6 +22,8 @@ YUV_BT601_FULL, YUV_BT709_FULL, YUV_BT709_LIMITED, YUV_BT2020_FULL = 0, 1, 2, 3
 WARP_AFFINE, WARP_PERSPECTIVE = 0, 1
 PRESERVE_AR, IGNORE_AR, PRESERVE_AR_RN_EVEN, PRESERVE_AR_LEFT = 0, 1, 2, 3
 OP_MUL, OP_SUB, OP_DIV, OP_ADD, OP_REORDER = 1, 2, 3, 4, 5
+OP_ADD_ALPHA, OP_DROP_ALPHA, OP_GRAY = 6, 7, 8
+CVGS_32FC1 = 5
 FP_REFERENCE_FUSED, FP_SEPARATE = 0, 1
 INTERP_FLOAT, INTERP_ROUND_U8 = 0, 1
 OUT_NCHW, OUT_CNHW, OUT_NHWC, OUT_PLANES = 0, 1, 2, 3

@@ -29,6 +29,11 @@ CV_16UC3 = _abi.CVGS_16UC3
 CV_16SC3 = _abi.CVGS_16SC3
 CV_8UC4, CV_16UC4, CV_16SC4, CV_32FC4 = _abi.CVGS_8UC4, _abi.CVGS_16UC4, _abi.CVGS_16SC4, _abi.CVGS_32FC4
 COLOR_RGBA2BGRA = COLOR_BGRA2RGBA = 5
+COLOR_BGR2BGRA = COLOR_RGB2RGBA = 0
+COLOR_BGRA2BGR = COLOR_RGBA2RGB = 1
+COLOR_BGR2RGBA = COLOR_RGB2BGRA = 2
+COLOR_RGBA2BGR = COLOR_BGRA2RGB = 3
+COLOR_BGR2GRAY, COLOR_RGB2GRAY, COLOR_BGRA2GRAY, COLOR_RGBA2GRAY = 6, 7, 10, 11
 CV_32FC3 = _abi.CVGS_32FC3
 
 
@@ -200,11 +205,21 @@ def convertTo(alpha: Optional[float] = None, beta: Optional[float] = None) -> Li
     return ops
 
 
-def cvtColor(code: int = COLOR_RGB2BGR) -> _Op:
-    """cvGS::cvtColor<COLOR_RGB2BGR / COLOR_BGR2RGB, CV_32FC3>() :151-161 = VectorReorder<2,1,0>."""
-    if code not in (COLOR_RGB2BGR, COLOR_RGBA2BGRA):
-        raise CvgsError("only the R<->B swaps (3 or 4 channels) are on this path")
-    return _Op(_abi.OP_REORDER, perm=(2, 1, 0, 3))
+def cvtColor(code: int = COLOR_RGB2BGR):
+    """cvGS::cvtColor<CODE, I, O>() :151-161 -> fk::ColorConversion<CODE> (color_conversion.cuh:364-461): the R<->B
+    swaps are a VectorReorder; the other supported codes add an opaque alpha (255, AddOpaqueAlpha<float3, p8bit>), drop
+    the alpha or reduce to gray, each optionally behind the swap.  Returns one op or a list of two."""
+    swap3, swap4 = _Op(_abi.OP_REORDER, perm=(2, 1, 0, 3)), _Op(_abi.OP_REORDER, perm=(2, 1, 0, 3))
+    alpha = _Op(_abi.OP_ADD_ALPHA, v=(255.0, 0.0, 0.0, 0.0))
+    drop = _Op(_abi.OP_DROP_ALPHA)
+    # the stand-alone FMUL of the gray formula differs between the instantiations (include/cvgs_b200.h, CVGS_OP_GRAY)
+    gray_x, gray_y = _Op(_abi.OP_GRAY, perm=(0, 0, 0, 0)), _Op(_abi.OP_GRAY, perm=(1, 0, 0, 0))
+    table = {COLOR_RGB2BGR: swap3, COLOR_RGBA2BGRA: swap4, COLOR_BGR2BGRA: alpha, COLOR_BGRA2BGR: drop,
+             COLOR_BGR2RGBA: [swap3, alpha], COLOR_RGBA2BGR: [swap4, drop], COLOR_BGR2GRAY: [swap3, gray_x],
+             COLOR_RGB2GRAY: gray_y, COLOR_BGRA2GRAY: [swap4, gray_x], COLOR_RGBA2GRAY: gray_y}
+    if code not in table:
+        raise CvgsError("colour conversion code not supported (reference cv2cuda_types.cuh:77-86 lists the set)")
+    return table[code]
 
 
 def split(out, planeDims: Optional[Tuple[int, int]] = None, plane_stride: int = 0) -> _Write:

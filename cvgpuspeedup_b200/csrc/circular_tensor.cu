@@ -173,6 +173,7 @@ int cvgs_b200_ct_update(void* handle, const cvgs_crop_t* frame, const cvgs_pipel
     CtParams K;
     std::memset(&K, 0, sizeof K);
     if (int rc = build_params(p, t->batch, 1, t->pub, K.pre)) return rc;
+    if (K.pre.prog.special) return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor planes have 3 channels: no channel-count changing conversion");
     DevCrop dc;
     if (int rc = fill_crop(*frame, p, 0, dc)) return rc;
     K.ring = t->ring;

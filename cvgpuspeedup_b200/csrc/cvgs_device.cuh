@@ -33,7 +33,11 @@ static_assert(sizeof(DevCrop) == 48, "DevCrop layout");
 // Normalised op chain.  Channel reorders are folded into out_perm, SUB is ADD of the negated
 // constant (exact), and under the reference-fused contract MUL followed by ADD/SUB is one FMA.
 // Constants are indexed by SOURCE channel ("register space").
-enum DevOpKind : int32_t { DOP_MUL = 1, DOP_ADD = 2, DOP_DIV = 3, DOP_FMA = 4 };
+// DOP_SET: register c takes a[c] where b[c] != 0 (AddOpaqueAlpha; hoisted to the front of the program by the host).
+// DOP_GRAY: register 0 = float(int_rn(0.299 x + 0.587 y + 0.114 z)) with x, y, z = registers (kind >> 8) & 3, (kind >> 12) & 3,
+// (kind >> 16) & 3; bit 20: every product and sum rounded on its own (CVGS_FP_SEPARATE) instead of FMUL, FFMA, FFMA;
+// bit 21: the stand-alone FMUL is y * 0.587 (else x * 0.299).
+enum DevOpKind : int32_t { DOP_MUL = 1, DOP_ADD = 2, DOP_DIV = 3, DOP_FMA = 4, DOP_SET = 5, DOP_GRAY = 6 };
 struct DevOp {
     int32_t kind;
     float a[4];   // 3-channel launches use [0..2]
@@ -42,7 +46,10 @@ struct DevOp {
 struct DevProgram {
     int32_t n_ops;
     int32_t round_u8;     // RoundKind: CVGS_INTERP_ROUND_U8 for the source depth of the launch
-    int32_t dst_chan[4];  // source channel r is written to output channel dst_chan[r]
+    int32_t dst_chan[4];  // register (= source channel) r is written to output channel dst_chan[r]; < 0: not written
+    int32_t nc_out;       // channels of the output pixel (differs from the source's after ADD_ALPHA / DROP_ALPHA / GRAY)
+    int32_t nregs;        // registers per pixel the chain needs: source channels, or 4 when a 3-channel source gets an alpha
+    int32_t special;      // 1: the program has DOP_SET / DOP_GRAY or nc_out != source channels (direct-gather kernel only)
     DevOp ops[8];
 };
 
@@ -171,7 +178,38 @@ __device__ __forceinline__ void apply_program(const DevProgram& prog, float (&v)
 #pragma unroll
                     for (int c = 0; c < NC; ++c) v[p][c] = __fdiv_rn(v[p][c], op.a[c]);
                 break;
+            case DOP_SET:
+#pragma unroll
+                for (int p = 0; p < NPIX; ++p)
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) v[p][c] = op.b[c] != 0.f ? op.a[c] : v[p][c];
+                break;
             default:
+                if ((op.kind & 0xff) == DOP_GRAY) {
+                    const int rx = (op.kind >> 8) & 3, ry = (op.kind >> 12) & 3, rz = (op.kind >> 16) & 3;
+                    const bool separate = (op.kind >> 20) & 1, y_first = (op.kind >> 21) & 1;
+#pragma unroll
+                    for (int p = 0; p < NPIX; ++p) {
+                        // selects instead of dynamic indexing: v stays in registers
+                        auto pick = [&](int r) {
+                            float t = v[p][0];
+#pragma unroll
+                            for (int c = 1; c < NC; ++c) t = r == c ? v[p][c] : t;
+                            return t;
+                        };
+                        const float x = pick(rx), y = pick(ry), z = pick(rz);
+                        float t;
+                        if (separate) {
+                            t = __fadd_rn(__fadd_rn(__fmul_rn(x, 0.299f), __fmul_rn(y, 0.587f)), __fmul_rn(z, 0.114f));
+                        } else if (y_first) {
+                            t = __fmaf_rn(z, 0.114f, __fmaf_rn(x, 0.299f, __fmul_rn(y, 0.587f)));
+                        } else {
+                            t = __fmaf_rn(z, 0.114f, __fmaf_rn(y, 0.587f, __fmul_rn(x, 0.299f)));
+                        }
+                        // the reference's RGB2Gray<I, float> rounds the luminance to an integer (its is_signed branch)
+                        v[p][0] = static_cast<float>(__float2int_rn(t));
+                    }
+                }
                 break;
         }
     }
@@ -209,6 +247,7 @@ __device__ __forceinline__ void store_pixels(const PreprocParams& P, int z, int 
     float* row = o.base + (long long)z * o.z_stride + ((long long)y * P.W + x) * o.px_stride;
 #pragma unroll
     for (int r = 0; r < NC; ++r) {
+        if (P.prog.dst_chan[r] < 0) continue;  // register dropped by a channel-count changing conversion
         // the channel reorder costs nothing: it only changes which plane register r goes to
         float* dst = row + (long long)P.prog.dst_chan[r] * o.c_stride;
         if (o.planes) {  // table is indexed by SOURCE channel (the host applied dst_chan when it built it)

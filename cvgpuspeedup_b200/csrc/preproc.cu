@@ -141,8 +141,9 @@ static MemRange out_range(const PreprocParams& P) {
     // every layout stays inside [base, base + extent): NCHW/NHWC planes z*z_stride + 3*W*H, CNHW c*c_stride + ...
     const long long plane = static_cast<long long>(P.W) * P.H;
     long long extent;
-    if (P.out.px_stride == 3) extent = (P.n_planes - 1) * P.out.z_stride + 3 * plane;
-    else extent = 2 * P.out.c_stride + (P.n_planes - 1) * P.out.z_stride + plane;
+    const int nco = P.prog.nc_out > 0 ? P.prog.nc_out : 3;
+    if (P.out.px_stride != 1) extent = (P.n_planes - 1) * P.out.z_stride + nco * plane;
+    else extent = (nco - 1) * P.out.c_stride + (P.n_planes - 1) * P.out.z_stride + plane;
     MemRange r;
     r.lo = reinterpret_cast<uintptr_t>(P.out.base);
     r.hi = r.lo + static_cast<uintptr_t>(extent) * sizeof(float);
@@ -178,7 +179,9 @@ __device__ __forceinline__ const DevCrop& crop_of<ParamCropTable>(const PreprocP
 }
 
 // block = 256 threads = (1 << bw_log2) quads in x  X  (256 >> bw_log2) rows; a quad = 4 output pixels.
-template <typename Table, int NC>
+// NC = channels of the source pixel, NR = registers per pixel of the chain (4 for a 3-channel source whose chain
+// adds an alpha channel, else NC).
+template <typename Table, int NC, int NR = NC>
 __global__ void __launch_bounds__(256)
 preproc_direct_kernel(const __grid_constant__ PreprocParams P, const __grid_constant__ Table T, int bw_log2) {
     const int tid = threadIdx.x;
@@ -196,8 +199,18 @@ preproc_direct_kernel(const __grid_constant__ PreprocParams P, const __grid_cons
     } else {
         fill_background<NC>(P, v);
     }
-    apply_program<4, NC>(P.prog, v);
-    store_pixels<4, NC>(P, z, y, x0, nvalid, v);
+    if constexpr (NR == NC) {
+        apply_program<4, NC>(P.prog, v);
+        store_pixels<4, NC>(P, z, y, x0, nvalid, v);
+    } else {
+        float r[4][NR];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int c = 0; c < NR; ++c) r[p][c] = c < NC ? v[p][c] : 0.f;
+        apply_program<4, NR>(P.prog, r);
+        store_pixels<4, NR>(P, z, y, x0, nvalid, r);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -310,7 +323,10 @@ static int launch_direct(const PreprocParams& P, const ParamCropTable* table, cu
     const int rows = 256 >> l;
     const dim3 grid((qw + (1 << l) - 1) >> l, (P.H + rows - 1) / rows, P.n_planes);
     if (grid.y > 65535u || grid.z > 65535u) return fail(CVGS_ERR_INVALID_VALUE, "batch or height too large for one launch");
-    if (P.nc == 4) {
+    if (P.nc == 3 && P.prog.nregs == 4) {  // cvtColor<BGR2BGRA / BGR2RGBA>: a fourth register per pixel
+        if (table) preproc_direct_kernel<ParamCropTable, 3, 4><<<grid, 256, 0, stream>>>(P, *table, l);
+        else preproc_direct_kernel<NoTable, 3, 4><<<grid, 256, 0, stream>>>(P, NoTable{}, l);
+    } else if (P.nc == 4) {
         if (table) preproc_direct_kernel<ParamCropTable, 4><<<grid, 256, 0, stream>>>(P, *table, l);
         else preproc_direct_kernel<NoTable, 4><<<grid, 256, 0, stream>>>(P, NoTable{}, l);
     } else if (table) {
@@ -677,6 +693,7 @@ static int warp_launch_impl(const cvgs_crop_t* images, const cvgs_warp_t* warps,
     q.aspect_mode = CVGS_IGNORE_AR;
     PreprocParams P;
     if (int rc = build_params(q, n_planes, used, static_cast<float*>(pipe->out), P)) return rc;
+    if (P.prog.special) return fail(CVGS_ERR_NOT_SUPPORTED, "warp: conversions that change the channel count are not on this path");
     for (int i = 0; i < used; ++i) {
         DevCrop scratch;
         if (int rc = fill_crop(images[i], q, i, scratch)) return rc;
@@ -860,7 +877,7 @@ static bool sequence_sets_independent(const cvgs_crop_t* const* crops, const int
         PreprocParams P;
         if (build_params(*p, n_planes[s], std::min(used[s], n_planes[s]), static_cast<float*>(p->out), P) != CVGS_OK) return false;
         const long long plane = static_cast<long long>(P.W) * P.H;
-        const int nc = P.nc;
+        const int nc = P.prog.nc_out;
         const long long extent = P.out.px_stride == 1 ? (nc - 1) * P.out.c_stride + (P.n_planes - 1) * P.out.z_stride + plane
                                                       : (P.n_planes - 1) * P.out.z_stride + nc * plane;
         outs[s].lo = reinterpret_cast<uintptr_t>(p->out);

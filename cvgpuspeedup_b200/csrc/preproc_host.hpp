@@ -83,16 +83,20 @@ inline int build_program(const cvgs_pipeline_t& p, DevProgram& prog) {
                     : (p.src_type == CVGS_16UC3 || p.src_type == CVGS_16UC4)   ? ROUND_U16
                     : (p.src_type == CVGS_16SC3 || p.src_type == CVGS_16SC4)   ? ROUND_S16
                                                                                : ROUND_U8;
-    int cur[4] = {0, 1, 2, 3};  // position c currently holds source channel cur[c]
+    int cur[4] = {0, 1, 2, 3};  // logical channel c currently lives in register cur[c] (registers = source channels)
+    int ncur = NC;               // logical channels at this point of the chain
     const bool fuse = p.fp_contract == CVGS_FP_REFERENCE_FUSED;
+    DevOp set{};                 // AddOpaqueAlpha, hoisted to the front (see below)
+    bool have_set = false;
+    DevOp body[CVGS_MAX_OPS];
     int n = 0;
     for (int i = 0; i < p.n_ops; ++i) {
         const cvgs_op_t& op = p.ops[i];
         if (op.kind == CVGS_OP_REORDER) {
-            int nc[4];
+            int nc[4] = {cur[0], cur[1], cur[2], cur[3]};
             bool seen[4] = {false, false, false, false};
-            for (int c = 0; c < NC; ++c) {
-                if (op.perm[c] < 0 || op.perm[c] >= NC || seen[op.perm[c]])
+            for (int c = 0; c < ncur; ++c) {
+                if (op.perm[c] < 0 || op.perm[c] >= ncur || seen[op.perm[c]])
                     return fail(CVGS_ERR_INVALID_VALUE, "REORDER perm must be a permutation of the channels");
                 seen[op.perm[c]] = true;
                 nc[c] = cur[op.perm[c]];
@@ -100,7 +104,42 @@ inline int build_program(const cvgs_pipeline_t& p, DevProgram& prog) {
             std::memcpy(cur, nc, sizeof cur);
             continue;
         }
+        if (op.kind == CVGS_OP_ADD_ALPHA) {
+            if (ncur != 3) return fail(CVGS_ERR_INVALID_VALUE, "ADD_ALPHA needs a 3-channel pixel");
+            if (have_set) return fail(CVGS_ERR_NOT_SUPPORTED, "one ADD_ALPHA per chain");
+            const int r = 6 - cur[0] - cur[1] - cur[2];  // the register no live channel uses
+            // The constant does not depend on anything computed before it, so the assignment is hoisted to the front
+            // of the program and every earlier per-channel op gets the identity on that register (x*1, x+(-0), x/1
+            // are exact): a MUL ... ADD pair around the conversion still contracts like in the reference's kernel.
+            set.kind = DOP_SET;
+            set.a[r] = op.v[0];
+            set.b[r] = 1.f;
+            have_set = true;
+            for (int k = 0; k < n; ++k) {
+                if ((body[k].kind & 0xff) == DOP_GRAY) continue;
+                body[k].a[r] = body[k].kind == DOP_ADD ? -0.0f : 1.0f;
+                body[k].b[r] = -0.0f;
+            }
+            cur[3] = r;
+            ncur = 4;
+            continue;
+        }
+        if (op.kind == CVGS_OP_DROP_ALPHA) {
+            if (ncur != 4) return fail(CVGS_ERR_INVALID_VALUE, "DROP_ALPHA needs a 4-channel pixel");
+            ncur = 3;
+            continue;
+        }
+        if (n >= CVGS_MAX_OPS) return fail(CVGS_ERR_INVALID_VALUE, "too many operations");
         DevOp d{};
+        if (op.kind == CVGS_OP_GRAY) {
+            if (ncur < 3) return fail(CVGS_ERR_INVALID_VALUE, "GRAY needs a 3- or 4-channel pixel");
+            if (op.perm[0] != 0 && op.perm[0] != 1) return fail(CVGS_ERR_INVALID_VALUE, "GRAY: perm[0] is 0 or 1");
+            d.kind = DOP_GRAY | (cur[0] << 8) | (cur[1] << 12) | (cur[2] << 16) | (fuse ? 0 : 1 << 20) | (op.perm[0] << 21);
+            body[n++] = d;
+            cur[0] = 0;  // DOP_GRAY leaves its result in register 0
+            ncur = 1;
+            continue;
+        }
         switch (op.kind) {
             case CVGS_OP_MUL: d.kind = DOP_MUL; break;
             case CVGS_OP_DIV: d.kind = DOP_DIV; break;
@@ -108,18 +147,30 @@ inline int build_program(const cvgs_pipeline_t& p, DevProgram& prog) {
             case CVGS_OP_SUB: d.kind = DOP_ADD; break;
             default: return fail(CVGS_ERR_INVALID_VALUE, "unknown op kind");
         }
-        for (int c = 0; c < NC; ++c) d.a[cur[c]] = op.kind == CVGS_OP_SUB ? -op.v[c] : op.v[c];
+        // registers that hold no live channel get the identity (their lanes are computed but never stored)
+        for (int r = 0; r < 4; ++r) d.a[r] = d.kind == DOP_ADD ? -0.0f : 1.0f;
+        for (int c = 0; c < ncur; ++c) d.a[cur[c]] = op.kind == CVGS_OP_SUB ? -op.v[c] : op.v[c];
         // nvcc contracts (x*m) +/- s into one FMA in the reference's inlined chain
-        if (fuse && d.kind == DOP_ADD && n > 0 && prog.ops[n - 1].kind == DOP_MUL) {
-            DevOp& m = prog.ops[n - 1];
+        if (fuse && d.kind == DOP_ADD && n > 0 && body[n - 1].kind == DOP_MUL) {
+            DevOp& m = body[n - 1];
             m.kind = DOP_FMA;
-            for (int c = 0; c < NC; ++c) m.b[c] = d.a[c];
+            for (int r = 0; r < 4; ++r) m.b[r] = d.a[r];
             continue;
         }
-        prog.ops[n++] = d;
+        body[n++] = d;
     }
-    prog.n_ops = n;
-    for (int c = 0; c < NC; ++c) prog.dst_chan[cur[c]] = c;
+    if (n + (have_set ? 1 : 0) > CVGS_MAX_OPS) return fail(CVGS_ERR_INVALID_VALUE, "too many operations");
+    int k = 0;
+    if (have_set) prog.ops[k++] = set;
+    for (int i = 0; i < n; ++i) prog.ops[k++] = body[i];
+    prog.n_ops = k;
+    for (int r = 0; r < 4; ++r) prog.dst_chan[r] = -1;
+    for (int c = 0; c < ncur; ++c) prog.dst_chan[cur[c]] = c;
+    prog.nc_out = ncur;
+    prog.nregs = (have_set && NC == 3) ? 4 : NC;
+    prog.special = (have_set || ncur != NC) ? 1 : 0;
+    for (int i = 0; i < k; ++i)
+        if ((prog.ops[i].kind & 0xff) == DOP_GRAY) prog.special = 1;
     return CVGS_OK;
 }
 
@@ -137,8 +188,9 @@ inline int validate_pipeline(const cvgs_pipeline_t* p) {
     if (p->fp_contract < 0 || p->fp_contract > 1) return fail(CVGS_ERR_INVALID_VALUE, "bad fp_contract");
     if (p->out_layout < 0 || p->out_layout > 3) return fail(CVGS_ERR_INVALID_VALUE, "bad out_layout");
     if (p->out_plane_stride < 0) return fail(CVGS_ERR_INVALID_VALUE, "negative out_plane_stride");
-    if (p->dst_type != 0 && p->dst_type != CVGS_32FC3 && p->dst_type != CVGS_32FC4 && p->dst_type != CVGS_8UC3)
-        return fail(CVGS_ERR_NOT_SUPPORTED, "dst_type must be CV_32FC3 / CV_32FC4 (or 0) or CV_8UC3");
+    if (p->dst_type != 0 && p->dst_type != CVGS_32FC1 && p->dst_type != CVGS_32FC3 && p->dst_type != CVGS_32FC4 &&
+        p->dst_type != CVGS_8UC3)
+        return fail(CVGS_ERR_NOT_SUPPORTED, "dst_type must be CV_32FC1 / CV_32FC3 / CV_32FC4 (or 0) or CV_8UC3");
     if (p->u8_cast != 0 && (p->u8_cast != 1 || p->dst_type != CVGS_8UC3))
         return fail(CVGS_ERR_INVALID_VALUE, "u8_cast is 0 or 1 and applies to CV_8UC3 output");
     if (p->dst_type == CVGS_8UC3 && channels_of(p->src_type) != 3)
@@ -161,9 +213,15 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
     P.src_type = p.src_type;
     if (p.src_type == CVGS_NV12) yuv_constants(p.yuv_standard, P.yuv);
     P.nc = channels_of(p.src_type);
-    const int NC = P.nc;
-    for (int c = 0; c < NC; ++c) P.bg[c] = p.background[c];
+    for (int c = 0; c < P.nc; ++c) P.bg[c] = p.background[c];
     if (int rc = build_program(p, P.prog)) return rc;
+    const int NC = P.prog.nc_out;  // channels of the OUTPUT pixel
+    if (P.prog.special && (p.dst_type == CVGS_8UC3 || p.out_layout == CVGS_OUT_PLANES))
+        return fail(CVGS_ERR_NOT_SUPPORTED, "conversions that change the channel count write float tensors (NCHW / CNHW / NHWC)");
+    if (p.dst_type == CVGS_32FC1 || p.dst_type == CVGS_32FC3 || p.dst_type == CVGS_32FC4) {
+        const int want = p.dst_type == CVGS_32FC1 ? 1 : (p.dst_type == CVGS_32FC3 ? 3 : 4);
+        if (want != NC) return fail(CVGS_ERR_INVALID_VALUE, "dst_type does not match the channels the chain produces");
+    }
     const long long plane = static_cast<long long>(p.dst_width) * p.dst_height;
     OutDesc& o = P.out;
     o.base = out;

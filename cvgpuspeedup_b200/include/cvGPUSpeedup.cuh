@@ -77,7 +77,7 @@ struct WriteOp {  // split / splitT / write
     int layout = CVGS_OUT_NCHW;
     long long plane_stride = 0;
     std::vector<cvgs_plane_t> planes;  // split(vector<GpuMat>): one destination image per (crop, channel)
-    int dst_type = CVGS_32FC3;         // CV_8UC3: write<CV_8UC3>(...) after convertTo<CV_32FC3, CV_8UC3>()
+    int dst_type = 0;                  // CV_32FC1/3/4 as named by the write op; CV_8UC3: write<CV_8UC3>(...) after convertTo<CV_32FC3, CV_8UC3>()
     long long row_pitch = 0;           // 8-bit destination: GpuMat::step
 };
 template <typename T>
@@ -250,34 +250,61 @@ CVGS_SCALAR_OP(divide, CVGS_OP_DIV)
 CVGS_SCALAR_OP(add, CVGS_OP_ADD)
 #undef CVGS_SCALAR_OP
 
+// fk::ColorConversion<CODE, I, O> (color_conversion.cuh:364-461; supported set cv2cuda_types.cuh:77-86): the R<->B swaps
+// are a channel reorder; the other codes add an opaque alpha (AddOpaqueAlpha<I, p8bit>: 255), drop the alpha or reduce
+// to gray (RGB2Gray), each optionally behind the swap.
 template <cv::ColorConversionCodes CODE, int I, int O = I>
 inline detail::ChainOp cvtColor() {
-    static_assert(CODE == cv::COLOR_RGB2BGR || CODE == cv::COLOR_BGR2RGB || CODE == cv::COLOR_RGBA2BGRA ||
-                      CODE == cv::COLOR_BGRA2RGBA,
-                  "cvGS (B200 build): the R<->B swaps (3 or 4 channels) are on the hot path");
-    static_assert(CV_MAT_CN(I) == CV_MAT_CN(O) && (CV_MAT_CN(I) == 3 || CV_MAT_CN(I) == 4),
-                  "cvGS (B200 build): colour conversions that change the channel count are not on the hot path");
-    static_assert((CV_MAT_CN(I) == 4) == (CODE == cv::COLOR_RGBA2BGRA), "cvGS: colour code and channel count disagree");
+    static_assert(CV_MAT_DEPTH(I) == CV_32F && CV_MAT_DEPTH(O) == CV_32F,
+                  "cvGS (B200 build): colour conversions run on the float pixels behind the resize");
+    constexpr int ci = CV_MAT_CN(I), co = CV_MAT_CN(O);
+    constexpr bool swap = CODE == cv::COLOR_BGR2RGB || CODE == cv::COLOR_BGRA2RGBA || CODE == cv::COLOR_BGR2RGBA ||
+                          CODE == cv::COLOR_RGBA2BGR || CODE == cv::COLOR_BGR2GRAY || CODE == cv::COLOR_BGRA2GRAY;
+    constexpr bool add_alpha = CODE == cv::COLOR_BGR2BGRA || CODE == cv::COLOR_BGR2RGBA;
+    constexpr bool drop_alpha = CODE == cv::COLOR_BGRA2BGR || CODE == cv::COLOR_RGBA2BGR;
+    constexpr bool gray = CODE == cv::COLOR_BGR2GRAY || CODE == cv::COLOR_RGB2GRAY || CODE == cv::COLOR_BGRA2GRAY ||
+                          CODE == cv::COLOR_RGBA2GRAY;
+    static_assert(swap || add_alpha || drop_alpha || gray, "Color conversion type not supported yet.");
+    constexpr int want_ci = (CODE == cv::COLOR_BGRA2RGBA || drop_alpha || CODE == cv::COLOR_BGRA2GRAY || CODE == cv::COLOR_RGBA2GRAY) ? 4 : 3;
+    constexpr int want_co = gray ? 1 : (add_alpha ? 4 : (drop_alpha ? 3 : want_ci));
+    static_assert(ci == want_ci && co == want_co, "cvGS: colour code and channel counts disagree");
     detail::ChainOp c;
-    c.op[0].kind = CVGS_OP_REORDER;
-    c.op[0].perm[0] = 2;
-    c.op[0].perm[1] = 1;
-    c.op[0].perm[2] = 0;
-    c.op[0].perm[3] = 3;
-    c.n = 1;
+    if (swap) {
+        cvgs_op_t& r = c.op[c.n++];
+        r.kind = CVGS_OP_REORDER;
+        r.perm[0] = 2; r.perm[1] = 1; r.perm[2] = 0; r.perm[3] = 3;
+    }
+    if (add_alpha) {
+        cvgs_op_t& a = c.op[c.n++];
+        a.kind = CVGS_OP_ADD_ALPHA;
+        a.v[0] = 255.f;  // maxDepthValue<p8bit>, the ColorDepth cvGS::cvtColor leaves at its default
+    } else if (drop_alpha) {
+        c.op[c.n++].kind = CVGS_OP_DROP_ALPHA;
+    } else if (gray) {
+        cvgs_op_t& g = c.op[c.n++];
+        g.kind = CVGS_OP_GRAY;
+        g.perm[0] = swap ? 0 : 1;  // the stand-alone FMUL of that instantiation (include/cvgs_b200.h, CVGS_OP_GRAY)
+    }
     return c;
 }
 
+namespace detail {
+template <int O>
+inline WriteOp typed(WriteOp w) {  // the write op names the pixel type the chain must end with
+    w.dst_type = O;                // CV_32FC1 / CV_32FC3 / CV_32FC4 / CV_8UC3 have the values of CVGS_32FC1 ... CVGS_8UC3
+    return w;
+}
+}  // namespace detail
 // ---- writes (reference :185-202, :449-457) ---------------------------------------------------------------
 template <int O>
 inline detail::WriteOp split(const cv::cuda::GpuMat& output, const cv::Size& /*planeDims*/) {
-    static_assert(O == CV_32FC3 || O == CV_32FC4, "cvGS (B200 build): CV_32FC3 / CV_32FC4 output");
-    return {output.data, CVGS_OUT_NCHW, 0, {}};  // the reference builds a tight Tensor and ignores GpuMat::step (:67-71)
+    static_assert(O == CV_32FC1 || O == CV_32FC3 || O == CV_32FC4, "cvGS (B200 build): CV_32FC1 / CV_32FC3 / CV_32FC4 output");
+    return detail::typed<O>({output.data, CVGS_OUT_NCHW, 0, {}});  // the reference builds a tight Tensor and ignores GpuMat::step (:67-71)
 }
 // fk::SplitWrite: the channels of a crop go to separate CV_32FC1 images (reference :163-183)
 template <int O>
 inline detail::WriteOp split(const std::vector<cv::cuda::GpuMat>& output) {
-    static_assert(O == CV_32FC3 || O == CV_32FC4, "cvGS (B200 build): CV_32FC3 / CV_32FC4 output");
+    static_assert(O == CV_32FC1 || O == CV_32FC3 || O == CV_32FC4, "cvGS (B200 build): CV_32FC1 / CV_32FC3 / CV_32FC4 output");
     if (output.size() != static_cast<size_t>(CV_MAT_CN(O))) throw std::runtime_error("cvGS::split: one destination image per channel is required");
     detail::WriteOp w;
     w.layout = CVGS_OUT_PLANES;
@@ -286,7 +313,7 @@ inline detail::WriteOp split(const std::vector<cv::cuda::GpuMat>& output) {
 }
 template <int O, int N>
 inline detail::WriteOp split(const std::array<std::vector<cv::cuda::GpuMat>, N>& output) {
-    static_assert(O == CV_32FC3 || O == CV_32FC4, "cvGS (B200 build): CV_32FC3 / CV_32FC4 output");
+    static_assert(O == CV_32FC1 || O == CV_32FC3 || O == CV_32FC4, "cvGS (B200 build): CV_32FC1 / CV_32FC3 / CV_32FC4 output");
     detail::WriteOp w;
     w.layout = CVGS_OUT_PLANES;
     for (const auto& crop : output) {
@@ -297,32 +324,28 @@ inline detail::WriteOp split(const std::array<std::vector<cv::cuda::GpuMat>, N>&
 }
 template <int O>
 inline detail::WriteOp split(const fk::RawPtr<fk::_3D, float>& output) {
-    return {output.data, CVGS_OUT_NCHW, 0, {}};
+    return detail::typed<O>({output.data, CVGS_OUT_NCHW, 0, {}});
 }
 template <int O>
 inline detail::WriteOp splitT(const fk::RawPtr<fk::T3D, float>& output) {
-    return {output.data, CVGS_OUT_CNHW, 0, {}};
+    return detail::typed<O>({output.data, CVGS_OUT_CNHW, 0, {}});
 }
 template <int O>
 inline detail::WriteOp write(const cv::cuda::GpuMat& output, const cv::Size& plane) {
-    static_assert(O == CV_32FC3 || O == CV_8UC3, "cvGS (B200 build): CV_32FC3 or CV_8UC3 output");
-    detail::WriteOp w{output.data, CVGS_OUT_NHWC, 0, {}};
-    if (O == CV_8UC3) {  // gpuMat2Tensor builds a tight tensor of `plane`-sized images (reference :67-71)
-        w.dst_type = CVGS_8UC3;
-        w.row_pitch = 3LL * plane.width;
-    }
+    static_assert(O == CV_32FC1 || O == CV_32FC3 || O == CV_32FC4 || O == CV_8UC3, "cvGS (B200 build): CV_32FC1/3/4 or CV_8UC3 output");
+    detail::WriteOp w = detail::typed<O>({output.data, CVGS_OUT_NHWC, 0, {}});
+    if (O == CV_8UC3) w.row_pitch = 3LL * plane.width;  // gpuMat2Tensor builds a tight tensor of `plane`-sized images (reference :67-71)
     return w;
 }
 // PerThreadWrite<_2D, O>: one image with the GpuMat's own pitch (reference :449-452; tests/resize/test_resize_write.cu)
 template <int O>
 inline detail::WriteOp write(const cv::cuda::GpuMat& output) {
-    static_assert(O == CV_32FC3 || O == CV_8UC3, "cvGS (B200 build): CV_32FC3 or CV_8UC3 output");
-    detail::WriteOp w{output.data, CVGS_OUT_NHWC, 0, {}};
+    static_assert(O == CV_32FC1 || O == CV_32FC3 || O == CV_32FC4 || O == CV_8UC3, "cvGS (B200 build): CV_32FC1/3/4 or CV_8UC3 output");
+    detail::WriteOp w = detail::typed<O>({output.data, CVGS_OUT_NHWC, 0, {}});
     if (O == CV_8UC3) {
-        w.dst_type = CVGS_8UC3;
         w.row_pitch = static_cast<long long>(output.step);
-    } else if (output.step != static_cast<size_t>(output.cols) * 12) {
-        throw std::runtime_error("cvGS::write<CV_32FC3>(GpuMat): a padded float destination is not supported by this build");
+    } else if (output.step != static_cast<size_t>(output.cols) * 4 * CV_MAT_CN(O)) {
+        throw std::runtime_error("cvGS::write<CV_32FCn>(GpuMat): a padded float destination is not supported by this build");
     }
     return w;
 }

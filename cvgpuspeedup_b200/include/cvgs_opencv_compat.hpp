@@ -65,7 +65,9 @@ namespace cv {
 enum InterpolationFlags { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2 };
 enum ColorConversionCodes { COLOR_BGR2BGRA = 0, COLOR_BGRA2BGR = 1, COLOR_BGR2RGBA = 2, COLOR_RGBA2BGR = 3,
                             COLOR_BGR2RGB = 4, COLOR_RGB2BGR = COLOR_BGR2RGB, COLOR_BGRA2RGBA = 5,
-                            COLOR_RGBA2BGRA = COLOR_BGRA2RGBA };
+                            COLOR_RGBA2BGRA = COLOR_BGRA2RGBA, COLOR_RGB2RGBA = COLOR_BGR2BGRA,
+                            COLOR_RGBA2RGB = COLOR_BGRA2BGR, COLOR_RGB2BGRA = COLOR_BGR2RGBA, COLOR_BGRA2RGB = COLOR_RGBA2BGR,
+                            COLOR_BGR2GRAY = 6, COLOR_RGB2GRAY = 7, COLOR_BGRA2GRAY = 10, COLOR_RGBA2GRAY = 11 };
 
 struct Size {
     int width = 0, height = 0;

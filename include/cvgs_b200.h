@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CVGS_B200_VERSION 103 /* 0.1.3 */
+#define CVGS_B200_VERSION 104 /* 0.1.4 */
 
 /* ---- error codes (subset of cudaError_t values so they can be passed through) ---- */
 #define CVGS_OK 0
@@ -47,6 +47,7 @@ extern "C" {
 #define CVGS_8UC3 16  /* CV_8UC3  */
 #define CVGS_16UC3 18 /* CV_16UC3: source only; taken by the direct-gather kernel (SaturateCast saturate.cuh:267-298) */
 #define CVGS_16SC3 19 /* CV_16SC3: source only; taken by the direct-gather kernel (saturate.cuh:358-378)             */
+#define CVGS_32FC1 5  /* CV_32FC1: output of a chain that ends in one channel (CVGS_OP_GRAY) */
 #define CVGS_32FC3 21 /* CV_32FC3 */
 #define CVGS_8UC4 24  /* CV_8UC4, CV_16UC4, CV_16SC4: 4-channel sources (the reference's test matrix,            */
 #define CVGS_16UC4 26 /* tests/batchresize/test_batchresize_x_split3D.cu:427-432): four output channels, four      */
@@ -83,7 +84,20 @@ enum cvgs_op_kind {
     CVGS_OP_SUB = 2,     /* x - v[c]   cvGS::subtract                            */
     CVGS_OP_DIV = 3,     /* x / v[c]   cvGS::divide   (IEEE-754 correctly rounded) */
     CVGS_OP_ADD = 4,     /* x + v[c]   cvGS::add / convertTo(alpha, beta)         */
-    CVGS_OP_REORDER = 5  /* out[c] = in[perm[c]]   cvGS::cvtColor<RGB2BGR/BGR2RGB> = {2,1,0} */
+    CVGS_OP_REORDER = 5, /* out[c] = in[perm[c]]   cvGS::cvtColor<RGB2BGR/BGR2RGB> = {2,1,0} */
+    /* colour conversions that change the channel count (reference color_conversion.cuh:364-461; the codes that also
+     * swap R and B are a REORDER followed by one of these).  Direct-gather kernel; the ops after them take the new
+     * channel count, and the output has it (tensor layouts; dst_type 0 or the matching CVGS_32FCn). */
+    CVGS_OP_ADD_ALPHA = 6,  /* 3 -> 4 channels, alpha = v[0]   cvtColor<BGR2BGRA / BGR2RGBA> (the wrapper passes 255:
+                               AddOpaqueAlpha<float3, p8bit>, color_conversion.cuh:122-130)            */
+    CVGS_OP_DROP_ALPHA = 7, /* 4 -> 3 channels                 cvtColor<BGRA2BGR / RGBA2BGR> (fk::Discard)            */
+    CVGS_OP_GRAY = 8        /* 3 or 4 -> 1 channel, 0.299 R + 0.587 G + 0.114 B of channels (0, 1, 2) in that order
+                               cvtColor<RGB2GRAY / RGBA2GRAY>; BGR2GRAY = REORDER {2,1,0} + GRAY (RGB2Gray<I, float>,
+                               color_conversion.cuh:42-68; as compiled: FMUL, FFMA, FFMA; the reference then rounds
+                               the luminance to the nearest integer even for float output -- std::is_signed_v<float> is
+                               true, :55-60 -- and so does this op).  perm[0] = which product nvcc left as
+                               the stand-alone FMUL in that instantiation: 1 (y * 0.587) for RGB2GRAY / RGBA2GRAY, 0
+                               (x * 0.299) for BGR2GRAY / BGRA2GRAY, whose reorder is fused in front                  */
 };
 
 /* Floating-point contract:

@@ -233,44 +233,97 @@ static void warp_pixel(const cvgs_crop_t* c, const cvgs_warp_t* wp, int x, int y
 
 /* Unary/Binary op chain, TransformDPP::operate (data_parallel_patterns.cuh:66-79);
  * Mul/Sub/Div/Add arithmetic.cuh:43-68; VectorReorder cuda_vector.cuh:45-54. */
+/* Channels of the pixel the chain ends with (ADD_ALPHA 3 -> 4, DROP_ALPHA 4 -> 3, GRAY -> 1:
+ * color_conversion.cuh:364-461). */
+static int chain_out_channels(const cvgs_pipeline_t* p) {
+    int nc = n_channels(p->src_type);
+    for (int i = 0; i < p->n_ops; ++i) {
+        if (p->ops[i].kind == CVGS_OP_ADD_ALPHA) nc = 4;
+        else if (p->ops[i].kind == CVGS_OP_DROP_ALPHA) nc = 3;
+        else if (p->ops[i].kind == CVGS_OP_GRAY) nc = 1;
+    }
+    return nc;
+}
+
 static void apply_chain(const cvgs_pipeline_t* p, float v[4]) {
-    const int nc = n_channels(p->src_type);
+    int nc = n_channels(p->src_type);
     if (p->interp_mode == CVGS_INTERP_ROUND_U8)
         for (int c = 0; c < nc; ++c) v[c] = round_sat_src(v[c], p->src_type);
+    /* nvcc contracts (x*m) -/+ s of the inlined chain into one FMA; channel reorders and the alpha conversions in
+     * between are only register renaming and do not prevent it.  mul_x / mul_m remember, per channel, the factors of
+     * a product that nothing has consumed yet. */
+    const int fused = p->fp_contract == CVGS_FP_REFERENCE_FUSED;
+    float mul_x[4] = {0, 0, 0, 0}, mul_m[4] = {0, 0, 0, 0};
+    int pending[4] = {0, 0, 0, 0};
     for (int i = 0; i < p->n_ops; ++i) {
         const cvgs_op_t* op = &p->ops[i];
-        /* nvcc contracts (x*m) -/+ s of the inlined chain into one FMA; a channel reorder in
-         * between is only register renaming and does not prevent it. */
-        if (op->kind == CVGS_OP_MUL && p->fp_contract == CVGS_FP_REFERENCE_FUSED) {
-            int j = i + 1;
-            int perm[4] = {0, 1, 2, 3};
-            while (j < p->n_ops && p->ops[j].kind == CVGS_OP_REORDER) {
-                int np[4];
-                for (int c = 0; c < nc; ++c) np[c] = perm[p->ops[j].perm[c]];
-                memcpy(perm, np, sizeof perm);
-                ++j;
-            }
-            if (j < p->n_ops && (p->ops[j].kind == CVGS_OP_SUB || p->ops[j].kind == CVGS_OP_ADD)) {
-                float t[4];
-                for (int c = 0; c < nc; ++c) {
-                    const int s = perm[c];
-                    const float a = p->ops[j].kind == CVGS_OP_SUB ? -p->ops[j].v[c] : p->ops[j].v[c];
-                    t[c] = fmaf(v[s], op->v[s], a);
-                }
-                memcpy(v, t, (size_t)nc * sizeof(float));
-                i = j;
-                continue;
-            }
-        }
         switch (op->kind) {
-            case CVGS_OP_MUL: for (int c = 0; c < nc; ++c) v[c] = v[c] * op->v[c]; break;
-            case CVGS_OP_SUB: for (int c = 0; c < nc; ++c) v[c] = v[c] - op->v[c]; break;
-            case CVGS_OP_DIV: for (int c = 0; c < nc; ++c) v[c] = v[c] / op->v[c]; break;
-            case CVGS_OP_ADD: for (int c = 0; c < nc; ++c) v[c] = v[c] + op->v[c]; break;
+            case CVGS_OP_MUL:
+                for (int c = 0; c < nc; ++c) {
+                    mul_x[c] = v[c];
+                    mul_m[c] = op->v[c];
+                    pending[c] = fused;
+                    v[c] = v[c] * op->v[c];
+                }
+                break;
+            case CVGS_OP_SUB:
+            case CVGS_OP_ADD:
+                for (int c = 0; c < nc; ++c) {
+                    const float a = op->kind == CVGS_OP_SUB ? -op->v[c] : op->v[c];
+                    v[c] = pending[c] ? fmaf(mul_x[c], mul_m[c], a) : v[c] + a;
+                    pending[c] = 0;
+                }
+                break;
+            case CVGS_OP_DIV:
+                for (int c = 0; c < nc; ++c) { v[c] = v[c] / op->v[c]; pending[c] = 0; }
+                break;
             case CVGS_OP_REORDER: {
-                float t[4];
-                for (int c = 0; c < nc; ++c) t[c] = v[op->perm[c]];
-                memcpy(v, t, (size_t)nc * sizeof(float));
+                float t[4], tx[4], tm[4];
+                int tp[4];
+                for (int c = 0; c < nc; ++c) {
+                    const int s = op->perm[c];
+                    t[c] = v[s]; tx[c] = mul_x[s]; tm[c] = mul_m[s]; tp[c] = pending[s];
+                }
+                for (int c = 0; c < nc; ++c) { v[c] = t[c]; mul_x[c] = tx[c]; mul_m[c] = tm[c]; pending[c] = tp[c]; }
+                break;
+            }
+            case CVGS_OP_ADD_ALPHA: /* AddOpaqueAlpha: AddLast(input, alpha), color_conversion.cuh:122-130 */
+                v[3] = op->v[0];
+                pending[3] = 0;
+                nc = 4;
+                break;
+            case CVGS_OP_DROP_ALPHA: /* Discard<I, VectorType_t<VBase<I>, 3>> */
+                nc = 3;
+                break;
+            case CVGS_OP_GRAY: { /* RGB2Gray<I, float>::compute_luminance, color_conversion.cuh:64-66; as compiled by
+                                    nvcc: FMUL(x, 0.299), FFMA(y, 0.587, .), FFMA(z, 0.114, .) */
+                /* Which of the first two products stays a stand-alone FMUL is nvcc's choice per instantiation:
+                 * RGB2GRAY / RGBA2GRAY multiply y first (op->perm[0] == 1), the codes with the fused reorder in front
+                 * (BGR2GRAY / BGRA2GRAY) multiply x first (perm[0] == 0) -- read off the reference's SASS. */
+                float t;
+                if (!fused) {
+                    const float a = v[0] * 0.299f, u = v[1] * 0.587f, w = v[2] * 0.114f;
+                    t = (a + u) + w;
+                } else if (op->perm[0] == 1) {
+                    t = v[1] * 0.587f;
+                    t = fmaf(v[0], 0.299f, t);
+                    t = fmaf(v[2], 0.114f, t);
+                } else {
+                    t = v[0] * 0.299f;
+                    t = fmaf(v[1], 0.587f, t);
+                    t = fmaf(v[2], 0.114f, t);
+                }
+                /* RGB2Gray<I, float> takes the `std::is_signed_v<OutputType>` branch (true for float,
+                 * color_conversion.cuh:55-60): the luminance goes through __float2int_rn -- rounded to the nearest even
+                 * integer, saturated to the int range, NaN -> 0 -- and back to float. */
+                if (t != t) t = 0.f;
+                else {
+                    t = nearbyintf(t);
+                    t = t >= 2147483648.f ? 2147483648.f : (t < -2147483648.f ? -2147483648.f : (float)(int)t);
+                }
+                v[0] = t;
+                pending[0] = 0;
+                nc = 1;
                 break;
             }
             default: break;
@@ -282,7 +335,7 @@ static void apply_chain(const cvgs_pipeline_t* p, float v[4]) {
  * TensorTSplit :197-220 + PtrAccessor<T3D> ptr_nd.cuh:65-77; PerThreadWrite<_3D>. */
 static void store_pixel(const cvgs_pipeline_t* p, int n_planes, int z, int y, int x, const float v[4]) {
     float* out = (float*)p->out;
-    const int nc = n_channels(p->src_type);
+    const int nc = chain_out_channels(p);
     const int64_t W = p->dst_width, H = p->dst_height;
     if (p->dst_type == CVGS_8UC3) { /* convertTo<CV_32FC3, CV_8UC3> + PerThreadWrite: SaturateCast saturate.cuh:127-147 */
         const int64_t rp = p->out_row_pitch ? p->out_row_pitch : 3 * W;

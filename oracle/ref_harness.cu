@@ -270,6 +270,61 @@ int FKREF_CAT(fkref_warp_, FKREF_BATCH)(int type, int mode, const void* data, in
 }
 #endif
 
+#ifdef FKREF_CVT
+// Colour conversions that change the channel count (color_conversion.cuh:364-461), fused behind the resize like
+// cvGS::cvtColor<CODE, CV_32FCn, CV_32FCm> puts them (include/cvGPUSpeedup.cuh:151-161):
+//   Resize<INTER_LINEAR>(PerThreadRead<uchar3 | uchar4>) -> ColorConversion<CODE, I, O> -> Mul<O> -> Sub<O> -> write
+// O = float4 / float3: TensorSplit into out[C][dst_h][dst_w]; O = float (gray): PerThreadWrite into out[dst_h][dst_w].
+// code: the cv:: / fk:: ColorConversionCodes value (0 BGR2BGRA, 1 BGRA2BGR, 2 BGR2RGBA, 3 RGBA2BGR, 6 BGR2GRAY,
+// 7 RGB2GRAY, 10 BGRA2GRAY, 11 RGBA2GRAY).
+}  // extern "C"
+namespace {
+template <fk::ColorConversionCodes CODE, typename SrcT, typename O>
+int run_cvt(const void* data, int w, int h, int pitch, int dst_w, int dst_h, const float* mul, const float* sub, float* out,
+            cudaStream_t stream) {
+    using I = fk::VectorType_t<float, fk::cn<SrcT>>;
+    const auto read = fk::PerThreadRead<fk::_2D, SrcT>::build(fk::RawPtr<fk::_2D, SrcT>{ (SrcT*)data, { (uint)w, (uint)h, (uint)pitch } });
+    const auto rs = fk::Resize<fk::INTER_LINEAR>::build(read, fk::Size(dst_w, dst_h));
+    const auto cvt = fk::Unary<fk::ColorConversion<CODE, I, O>>{};
+    if constexpr (std::is_same_v<O, float>) {
+        const fk::RawPtr<fk::_2D, float> o{ out, { (uint)dst_w, (uint)dst_h, (uint)(dst_w * 4) } };
+        fk::executeOperations(stream, rs, cvt, fk::Binary<fk::Mul<float>>{ mul[0] }, fk::Binary<fk::Sub<float>>{ sub[0] },
+                              fk::Write<fk::PerThreadWrite<fk::_2D, float>>{ o });
+    } else {
+        O m, b;
+        m.x = mul[0]; m.y = mul[1]; m.z = mul[2];
+        b.x = sub[0]; b.y = sub[1]; b.z = sub[2];
+        if constexpr (fk::cn<O> == 4) { m.w = mul[3]; b.w = sub[3]; }
+        const fk::Tensor<float> t_out(out, dst_w, dst_h, 1, fk::cn<O>);
+        fk::executeOperations(stream, rs, cvt, fk::Binary<fk::Mul<O>>{ m }, fk::Binary<fk::Sub<O>>{ b },
+                              fk::Write<fk::TensorSplit<O>>{ t_out.ptr() });
+    }
+    return 0;
+}
+}  // namespace
+extern "C" {
+int FKREF_CAT(fkref_cvt_, FKREF_BATCH)(int code, const void* data, int w, int h, int pitch, int dst_w, int dst_h,
+                                       const float* mul, const float* sub, float* out, void* stream) {
+    try {
+        cudaStream_t s = (cudaStream_t)stream;
+        switch (code) {
+            case 0: return run_cvt<fk::COLOR_BGR2BGRA, uchar3, float4>(data, w, h, pitch, dst_w, dst_h, mul, sub, out, s);
+            case 1: return run_cvt<fk::COLOR_BGRA2BGR, uchar4, float3>(data, w, h, pitch, dst_w, dst_h, mul, sub, out, s);
+            case 2: return run_cvt<fk::COLOR_BGR2RGBA, uchar3, float4>(data, w, h, pitch, dst_w, dst_h, mul, sub, out, s);
+            case 3: return run_cvt<fk::COLOR_RGBA2BGR, uchar4, float3>(data, w, h, pitch, dst_w, dst_h, mul, sub, out, s);
+            case 6: return run_cvt<fk::COLOR_BGR2GRAY, uchar3, float>(data, w, h, pitch, dst_w, dst_h, mul, sub, out, s);
+            case 7: return run_cvt<fk::COLOR_RGB2GRAY, uchar3, float>(data, w, h, pitch, dst_w, dst_h, mul, sub, out, s);
+            case 10: return run_cvt<fk::COLOR_BGRA2GRAY, uchar4, float>(data, w, h, pitch, dst_w, dst_h, mul, sub, out, s);
+            case 11: return run_cvt<fk::COLOR_RGBA2GRAY, uchar4, float>(data, w, h, pitch, dst_w, dst_h, mul, sub, out, s);
+            default: g_err = "fkref: colour conversion code not instantiated"; return -1;
+        }
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+#endif
+
 const char* FKREF_CAT(fkref_last_error_, FKREF_BATCH)(void) { return g_err.c_str(); }
 
 }  // extern "C"

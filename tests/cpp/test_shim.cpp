@@ -6,6 +6,7 @@
 //   4. random image vs the CPU oracle, bit for bit (the reference has no such test: SURVEY F2)
 //   6. tests/warping/test_warping_opencv.cu:34-197  affine / perspective / batched perspective warp + fk::Cast + write,
 //      against the oracle (cv::cuda::warpAffine is not in this image), plus exact checks of the translation case
+//   7. cvGS::cvtColor codes that add / drop the alpha channel or reduce to gray, against the oracle
 //   5. error convention: std::runtime_error (gpuErrchk, fkl/.../core/utils/utils.h:42-60)
 #include <cmath>
 #include <cstdio>
@@ -337,6 +338,82 @@ static int test_warping() {
     return 0;
 }
 
+// cvGS::cvtColor with the codes that change the channel count (reference include/cvGPUSpeedup.cuh:151-161,
+// cv2cuda_types.cuh:77-86): against the oracle, plus exact checks of the alpha and gray values.
+static int test_cvtcolor_channel_changes() {
+    constexpr int W = 96, H = 64;
+    std::mt19937 rng(21);
+    cv::cuda::GpuMat d_img(H, W, CV_8UC3);
+    std::vector<uchar> h_img(d_img.step * H);
+    for (auto& b : h_img) b = static_cast<uchar>(rng());
+    REQUIRE(cudaMemcpy(d_img.data, h_img.data(), h_img.size(), cudaMemcpyHostToDevice) == cudaSuccess);
+    const cvgs_crop_t h_crop{h_img.data(), W, H, static_cast<int32_t>(d_img.step), 0};
+    cv::cuda::Stream st;
+    const cv::Size size(W, H);
+    auto oracle = [&](const std::vector<cvgs_op_t>& ops, int nco, std::vector<float>& out) {
+        cvgs_pipeline_t p{};
+        p.src_type = CVGS_8UC3;
+        p.dst_width = W;
+        p.dst_height = H;
+        p.aspect_mode = CVGS_IGNORE_AR;
+        p.n_ops = static_cast<int>(ops.size());
+        for (size_t i = 0; i < ops.size(); ++i) p.ops[i] = ops[i];
+        out.assign(static_cast<size_t>(nco) * W * H, -1.f);
+        p.out = out.data();
+        return oracle_preproc(&h_crop, 1, 1, &p, 0);
+    };
+    auto op = [](int kind, float v0 = 0.f, float v1 = 0.f, float v2 = 0.f, float v3 = 0.f, int p0 = 0, int p1 = 1, int p2 = 2, int p3 = 3) {
+        cvgs_op_t o{};
+        o.kind = kind;
+        o.v[0] = v0; o.v[1] = v1; o.v[2] = v2; o.v[3] = v3;
+        o.perm[0] = p0; o.perm[1] = p1; o.perm[2] = p2; o.perm[3] = p3;
+        return o;
+    };
+    {   // BGR -> RGBA, scaled per channel, planar CV_32FC4 tensor
+        cv::cuda::GpuMat d_out(1, W * H * 4, CV_32FC1);
+        cvGS::executeOperations(st, cvGS::resize<CV_8UC3, cv::INTER_LINEAR>(d_img, size),
+                                cvGS::cvtColor<cv::COLOR_BGR2RGBA, CV_32FC3, CV_32FC4>(),
+                                cvGS::multiply<CV_32FC4>(cv::Scalar(0.5, 0.25, 2.0, 1.0 / 255.0)), cvGS::split<CV_32FC4>(d_out, size));
+        st.waitForCompletion();
+        std::vector<float> got(static_cast<size_t>(4) * W * H), want;
+        REQUIRE(cudaMemcpy(got.data(), d_out.data, got.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess);
+        REQUIRE(oracle({op(CVGS_OP_REORDER, 0, 0, 0, 0, 2, 1, 0, 3), op(CVGS_OP_ADD_ALPHA, 255.f), op(CVGS_OP_MUL, 0.5f, 0.25f, 2.0f, 1.0f / 255.0f)}, 4, want) == 0);
+        REQUIRE(std::memcmp(got.data(), want.data(), got.size() * 4) == 0);
+        for (int i = 0; i < W * H; ++i) {
+            REQUIRE(got[3 * W * H + i] == 255.f * (1.0f / 255.0f));
+            REQUIRE(got[i] == 0.5f * h_img[(i / W) * d_img.step + 3 * (i % W) + 2]);  // R of a BGR pixel
+        }
+    }
+    {   // RGB -> gray, one CV_32FC1 image
+        cv::cuda::GpuMat d_out(H, W, CV_32FC1);
+        d_out.step = W * sizeof(float);
+        cvGS::executeOperations(st, cvGS::resize<CV_8UC3, cv::INTER_LINEAR>(d_img, size), cvGS::cvtColor<cv::COLOR_RGB2GRAY, CV_32FC3, CV_32FC1>(),
+                                cvGS::write<CV_32FC1>(d_out));
+        st.waitForCompletion();
+        std::vector<float> got(static_cast<size_t>(W) * H), want;
+        REQUIRE(cudaMemcpy(got.data(), d_out.data, got.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess);
+        REQUIRE(oracle({op(CVGS_OP_GRAY, 0, 0, 0, 0, 1)}, 1, want) == 0);
+        REQUIRE(std::memcmp(got.data(), want.data(), got.size() * 4) == 0);
+        for (int i = 0; i < W * H; ++i) {
+            const uchar* px = &h_img[(i / W) * d_img.step + 3 * (i % W)];
+            const double lum = 0.299 * px[0] + 0.587 * px[1] + 0.114 * px[2];
+            REQUIRE(got[i] == std::floor(got[i]) && std::fabs(got[i] - lum) <= 0.5 + 1e-3);
+        }
+    }
+    {   // the write op names the pixel type the chain ends with
+        cv::cuda::GpuMat d_out(1, W * H * 3, CV_32FC1);
+        bool thrown = false;
+        try {
+            cvGS::executeOperations(st, cvGS::resize<CV_8UC3, cv::INTER_LINEAR>(d_img, size),
+                                    cvGS::cvtColor<cv::COLOR_BGR2GRAY, CV_32FC3, CV_32FC1>(), cvGS::split<CV_32FC3>(d_out, size));
+        } catch (const std::runtime_error& e) {
+            thrown = std::strstr(e.what(), "dst_type") != nullptr;
+        }
+        REQUIRE(thrown);
+    }
+    return 0;
+}
+
 static int test_error_convention() {
     cv::cuda::GpuMat d_input(16, 16, CV_8UC3, cv::Scalar(1, 2, 3));
     cv::cuda::GpuMat d_null;  // data == nullptr
@@ -365,6 +442,7 @@ int main() {
     failed += test_resize_write_8u();
     failed += test_random_vs_oracle();
     failed += test_warping();
+    failed += test_cvtcolor_channel_changes();
     failed += test_error_convention();
     std::printf(failed ? "test_shim: %d FAILED\n" : "test_shim: all passed\n", failed);
     return failed ? 1 : 0;

@@ -28,7 +28,7 @@ def run_cvgs(image, rects, dsize, ops, n_planes=None, used=None, variant=0, fill
     layout = pipe_kw.get("layout", _abi.OUT_NCHW)
     d_img = device_image(image) if d_image is None else d_image
     st = pipe_kw.get("src_type", _abi.CVGS_8UC3)
-    shape = util.out_shape(n_planes, dsize, layout, pipe_kw.get("plane_stride", 0), util.channels_of(st))
+    shape = util.out_shape(n_planes, dsize, layout, pipe_kw.get("plane_stride", 0), util.out_channels(st, ops))
     d_out = torch.full(shape, fill, dtype=torch.float32, device="cuda")
     p = util.make_pipeline(dsize, ops, out_ptr=d_out.data_ptr(), **pipe_kw)
     crops = util.host_crops(image, rects[:used], base_ptr=d_img.data_ptr(), px_bytes=util.px_bytes_of(st))
@@ -192,6 +192,38 @@ def run_fkref_warp(image, width, height, warp_type, inverse, dsize, mul=None, d_
         out = torch.full((dsize[1], dsize[0], 3), 77, dtype=torch.uint8, device="cuda")
         rc = fn(warp_type, 1, d.data_ptr(), width, height, image.shape[1], m, dsize[0], dsize[1], None,
                 out.data_ptr(), 3 * dsize[0], torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+CVT_CODES = {  # cv:: / fk:: ColorConversionCodes -> (source channels, ops of the C-ABI)
+    0: (3, [("add_alpha", (255.0,))]),                                  # BGR2BGRA / RGB2RGBA
+    1: (4, [("drop_alpha", ())]),                                       # BGRA2BGR / RGBA2RGB
+    2: (3, [("reorder", (2, 1, 0)), ("add_alpha", (255.0,))]),          # BGR2RGBA / RGB2BGRA
+    3: (4, [("reorder", (2, 1, 0, 3)), ("drop_alpha", ())]),            # RGBA2BGR / BGRA2RGB
+    6: (3, [("reorder", (2, 1, 0)), ("gray", ())]),                     # BGR2GRAY
+    7: (3, [("gray", (1,))]),                                           # RGB2GRAY (gray (1,): y * 0.587 first)
+    10: (4, [("reorder", (2, 1, 0, 3)), ("gray", ())]),                 # BGRA2GRAY
+    11: (4, [("gray", (1,))]),                                          # RGBA2GRAY
+}
+
+
+def run_fkref_cvt(code, image, width, height, dsize, mul, sub, d_image=None):
+    """The reference's Resize + ColorConversion<code> + Mul + Sub + write on one image (oracle/_ref/libfkref_16.so,
+    -DFKREF_CVT).  Returns [C, H, W] float32 (C = channels after the conversion)."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libfkref_16.so")
+    lib = C.CDLL(path)
+    fn = lib.fkref_cvt_16
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                   C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+    nc_out = {0: 4, 2: 4, 1: 3, 3: 3}.get(code, 1)
+    d = device_image(image) if d_image is None else d_image
+    out = torch.full((nc_out, dsize[1], dsize[0]), float("nan"), dtype=torch.float32, device="cuda")
+    f4 = lambda v: (C.c_float * 4)(*(tuple(v) + (0.0,) * 4)[:4])  # noqa: E731
+    rc = fn(code, d.data_ptr(), width, height, image.shape[1], dsize[0], dsize[1], f4(mul), f4(sub), out.data_ptr(),
+            torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     torch.cuda.synchronize()
     return out.cpu().numpy()

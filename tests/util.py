@@ -133,7 +133,16 @@ def workload_c3(seed=3, n=256, frame=(3840, 2160), dsize=(224, 224), lo=224, hi=
     return Workload("c3", img, fw, fh, rects, dsize, OPS_C3)
 
 
-_KIND = {"mul": _abi.OP_MUL, "sub": _abi.OP_SUB, "div": _abi.OP_DIV, "add": _abi.OP_ADD, "reorder": _abi.OP_REORDER}
+_KIND = {"mul": _abi.OP_MUL, "sub": _abi.OP_SUB, "div": _abi.OP_DIV, "add": _abi.OP_ADD, "reorder": _abi.OP_REORDER,
+         "add_alpha": _abi.OP_ADD_ALPHA, "drop_alpha": _abi.OP_DROP_ALPHA, "gray": _abi.OP_GRAY}
+
+
+def out_channels(src_type, ops) -> int:
+    """Channels of the pixel a chain ends with (the alpha / gray conversions change the count)."""
+    nc = channels_of(src_type)
+    for k, _ in ops:
+        nc = {"add_alpha": 4, "drop_alpha": 3, "gray": 1}.get(k, nc)
+    return nc
 
 
 def make_pipeline(dsize, ops, aspect=_abi.IGNORE_AR, background=(0, 0, 0), fp_contract=_abi.FP_REFERENCE_FUSED,
@@ -149,7 +158,7 @@ def make_pipeline(dsize, ops, aspect=_abi.IGNORE_AR, background=(0, 0, 0), fp_co
     for i, (k, v) in enumerate(ops):
         p.ops[i].kind = _KIND[k]
         for c in range(len(v)):
-            if k == "reorder":
+            if k in ("reorder", "gray"):
                 p.ops[i].perm[c] = v[c]
             else:
                 p.ops[i].v[c] = v[c]
@@ -208,7 +217,7 @@ def run_oracle(image, rects, dsize, ops, n_planes=None, used=None, nthreads=0, f
     used = len(rects) if used is None else used
     layout = pipe_kw.get("layout", _abi.OUT_NCHW)
     st = pipe_kw.get("src_type", _abi.CVGS_8UC3)
-    out = np.full(out_shape(n_planes, dsize, layout, pipe_kw.get("plane_stride", 0), channels_of(st)), fill, dtype=np.float32)
+    out = np.full(out_shape(n_planes, dsize, layout, pipe_kw.get("plane_stride", 0), out_channels(st, ops)), fill, dtype=np.float32)
     p = make_pipeline(dsize, ops, out_ptr=out.ctypes.data, **pipe_kw)
     crops = host_crops(image, rects[:used], px_bytes=px_bytes_of(st))
     rc = lib.oracle_preproc(crops, n_planes, used, C.byref(p), nthreads)
