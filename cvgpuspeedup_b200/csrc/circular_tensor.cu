@@ -163,7 +163,7 @@ int cvgs_b200_ct_update(void* handle, const cvgs_crop_t* frame, const cvgs_pipel
     if (!t) return fail(CVGS_ERR_INVALID_VALUE, "handle is NULL");
     if (!frame) return fail(CVGS_ERR_INVALID_VALUE, "frame is NULL");
     if (int rc = validate_pipeline(pipeline)) return rc;
-    if (pipeline->dst_type == CVGS_8UC3) return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor planes are float");
+    if (pipeline->dst_type == CVGS_8UC3 || pipeline->dst_type == CVGS_8UC4 || pipeline->out_row_pitch != 0) return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor planes are float");
     if (channels_of(pipeline->src_type) != 3) return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor takes 3-channel frames");
     if (pipeline->dst_width != t->w || pipeline->dst_height != t->h)
         return fail(CVGS_ERR_INVALID_VALUE, "pipeline destination size must equal the tensor plane size");

@@ -67,6 +67,7 @@ struct OutDesc {
     int32_t u8;          // packed 8-bit output after the chain, strides below in bytes: 1 SaturateCast<float, uchar>,
                          // 2 fk::Cast (static_cast: truncation, low byte)
     long long row_pitch; // u8 output: bytes between rows
+    long long row_stride; // float output (tensor layouts): floats between rows (W * px_stride unless the caller set out_row_pitch)
 };
 
 struct PreprocParams {
@@ -244,7 +245,7 @@ __device__ __forceinline__ void store_pixels(const PreprocParams& P, int z, int 
             }
         return;
     }
-    float* row = o.base + (long long)z * o.z_stride + ((long long)y * P.W + x) * o.px_stride;
+    float* row = o.base + (long long)z * o.z_stride + (long long)y * o.row_stride + (long long)x * o.px_stride;
 #pragma unroll
     for (int r = 0; r < NC; ++r) {
         if (P.prog.dst_chan[r] < 0) continue;  // register dropped by a channel-count changing conversion

@@ -142,7 +142,7 @@ static MemRange out_range(const PreprocParams& P) {
     const long long plane = static_cast<long long>(P.W) * P.H;
     long long extent;
     const int nco = P.prog.nc_out > 0 ? P.prog.nc_out : 3;
-    if (P.out.px_stride != 1) extent = (P.n_planes - 1) * P.out.z_stride + nco * plane;
+    if (P.out.px_stride != 1) extent = (P.n_planes - 1) * P.out.z_stride + P.out.row_stride * P.H;
     else extent = (nco - 1) * P.out.c_stride + (P.n_planes - 1) * P.out.z_stride + plane;
     MemRange r;
     r.lo = reinterpret_cast<uintptr_t>(P.out.base);
@@ -767,7 +767,8 @@ static int preproc_host_impl(HostPath& h, const void* host_image, int32_t image_
     if (int rc = validate_pipeline(pipeline)) return rc;
     if (!host_image || !host_out || !rects) return fail(CVGS_ERR_INVALID_VALUE, "NULL host buffer");
     if (pipeline->src_type != CVGS_8UC3) return fail(CVGS_ERR_NOT_SUPPORTED, "the host-buffer entry point takes CV_8UC3 frames");
-    if (pipeline->dst_type == CVGS_8UC3 || pipeline->out_layout == CVGS_OUT_PLANES)
+    if (pipeline->dst_type == CVGS_8UC3 || pipeline->dst_type == CVGS_8UC4 || pipeline->out_row_pitch != 0 ||
+        pipeline->out_layout == CVGS_OUT_PLANES)
         return fail(CVGS_ERR_NOT_SUPPORTED, "the host-buffer entry point writes one float tensor");
     if (image_width <= 0 || image_height <= 0 || image_pitch < 3 * image_width)
         return fail(CVGS_ERR_INVALID_VALUE, "bad host image geometry");
@@ -873,13 +874,13 @@ static bool sequence_sets_independent(const cvgs_crop_t* const* crops, const int
         const cvgs_pipeline_t* p = pipelines[s];
         if (!p || !p->out || !crops[s] || n_planes[s] <= 0 || used[s] < 0) return false;
         if (validate_pipeline(p) != CVGS_OK) return false;
-        if (p->out_layout == CVGS_OUT_PLANES || p->dst_type == CVGS_8UC3 || p->src_type == CVGS_NV12) return false;
+        if (p->out_layout == CVGS_OUT_PLANES || p->dst_type == CVGS_8UC3 || p->dst_type == CVGS_8UC4 || p->src_type == CVGS_NV12) return false;
         PreprocParams P;
         if (build_params(*p, n_planes[s], std::min(used[s], n_planes[s]), static_cast<float*>(p->out), P) != CVGS_OK) return false;
         const long long plane = static_cast<long long>(P.W) * P.H;
         const int nc = P.prog.nc_out;
         const long long extent = P.out.px_stride == 1 ? (nc - 1) * P.out.c_stride + (P.n_planes - 1) * P.out.z_stride + plane
-                                                      : (P.n_planes - 1) * P.out.z_stride + nc * plane;
+                                                      : (P.n_planes - 1) * P.out.z_stride + P.out.row_stride * P.H;
         outs[s].lo = reinterpret_cast<uintptr_t>(p->out);
         outs[s].hi = outs[s].lo + static_cast<uintptr_t>(extent) * sizeof(float);
         const int px = pixel_bytes_of(p->src_type);

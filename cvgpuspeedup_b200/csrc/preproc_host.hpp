@@ -189,16 +189,20 @@ inline int validate_pipeline(const cvgs_pipeline_t* p) {
     if (p->out_layout < 0 || p->out_layout > 3) return fail(CVGS_ERR_INVALID_VALUE, "bad out_layout");
     if (p->out_plane_stride < 0) return fail(CVGS_ERR_INVALID_VALUE, "negative out_plane_stride");
     if (p->dst_type != 0 && p->dst_type != CVGS_32FC1 && p->dst_type != CVGS_32FC3 && p->dst_type != CVGS_32FC4 &&
-        p->dst_type != CVGS_8UC3)
-        return fail(CVGS_ERR_NOT_SUPPORTED, "dst_type must be CV_32FC1 / CV_32FC3 / CV_32FC4 (or 0) or CV_8UC3");
-    if (p->u8_cast != 0 && (p->u8_cast != 1 || p->dst_type != CVGS_8UC3))
-        return fail(CVGS_ERR_INVALID_VALUE, "u8_cast is 0 or 1 and applies to CV_8UC3 output");
-    if (p->dst_type == CVGS_8UC3 && channels_of(p->src_type) != 3)
-        return fail(CVGS_ERR_NOT_SUPPORTED, "8-bit output is implemented for 3-channel pipelines");
-    if (p->dst_type == CVGS_8UC3 && p->out_layout != CVGS_OUT_NHWC)
-        return fail(CVGS_ERR_INVALID_VALUE, "CV_8UC3 output is packed: out_layout must be CVGS_OUT_NHWC");
-    if (p->dst_type == CVGS_8UC3 && p->out_row_pitch != 0 && p->out_row_pitch < 3LL * p->dst_width)
+        p->dst_type != CVGS_8UC3 && p->dst_type != CVGS_8UC4)
+        return fail(CVGS_ERR_NOT_SUPPORTED, "dst_type must be CV_32FC1 / CV_32FC3 / CV_32FC4 (or 0) or CV_8UC3 / CV_8UC4");
+    if (p->u8_cast != 0 && (p->u8_cast != 1 || (p->dst_type != CVGS_8UC3 && p->dst_type != CVGS_8UC4)))
+        return fail(CVGS_ERR_INVALID_VALUE, "u8_cast is 0 or 1 and applies to 8-bit output");
+    const bool u8_out = p->dst_type == CVGS_8UC3 || p->dst_type == CVGS_8UC4;
+    if (u8_out && channels_of(p->src_type) != (p->dst_type == CVGS_8UC3 ? 3 : 4))
+        return fail(CVGS_ERR_NOT_SUPPORTED, "8-bit output has the channel count of the source (CV_8UC3 / CV_8UC4)");
+    if (u8_out && p->out_layout != CVGS_OUT_NHWC)
+        return fail(CVGS_ERR_INVALID_VALUE, "8-bit output is packed: out_layout must be CVGS_OUT_NHWC");
+    if (u8_out && p->out_row_pitch != 0 && p->out_row_pitch < static_cast<long long>(channels_of(p->src_type)) * p->dst_width)
         return fail(CVGS_ERR_INVALID_VALUE, "out_row_pitch smaller than a row");
+    if (!u8_out && p->out_row_pitch != 0 && p->out_layout != CVGS_OUT_NHWC)
+        return fail(CVGS_ERR_INVALID_VALUE, "out_row_pitch applies to packed output (CVGS_OUT_NHWC)");
+    if (p->out_row_pitch < 0) return fail(CVGS_ERR_INVALID_VALUE, "negative out_row_pitch");
     return CVGS_OK;
 }
 
@@ -216,7 +220,8 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
     for (int c = 0; c < P.nc; ++c) P.bg[c] = p.background[c];
     if (int rc = build_program(p, P.prog)) return rc;
     const int NC = P.prog.nc_out;  // channels of the OUTPUT pixel
-    if (P.prog.special && (p.dst_type == CVGS_8UC3 || p.out_layout == CVGS_OUT_PLANES))
+    const bool u8_out = p.dst_type == CVGS_8UC3 || p.dst_type == CVGS_8UC4;
+    if (P.prog.special && (u8_out || p.out_layout == CVGS_OUT_PLANES))
         return fail(CVGS_ERR_NOT_SUPPORTED, "conversions that change the channel count write float tensors (NCHW / CNHW / NHWC)");
     if (p.dst_type == CVGS_32FC1 || p.dst_type == CVGS_32FC3 || p.dst_type == CVGS_32FC4) {
         const int want = p.dst_type == CVGS_32FC1 ? 1 : (p.dst_type == CVGS_32FC3 ? 3 : 4);
@@ -248,11 +253,17 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
             o.c_stride = 1;
             o.px_stride = NC;
     }
-    o.u8 = p.dst_type == CVGS_8UC3 ? (p.u8_cast ? 2 : 1) : 0;
+    o.u8 = u8_out ? (p.u8_cast ? 2 : 1) : 0;
     o.row_pitch = 0;
+    o.row_stride = static_cast<long long>(p.dst_width) * o.px_stride;
     if (o.u8) {  // strides in bytes
-        o.row_pitch = p.out_row_pitch ? p.out_row_pitch : 3LL * p.dst_width;
+        o.row_pitch = p.out_row_pitch ? p.out_row_pitch : static_cast<long long>(NC) * p.dst_width;
         o.z_stride = p.out_plane_stride ? p.out_plane_stride : o.row_pitch * p.dst_height;
+    } else if (p.out_row_pitch) {  // packed float image with padded rows (a GpuMat from cudaMallocPitch)
+        if ((p.out_row_pitch & 3) || p.out_row_pitch < 4LL * NC * p.dst_width)
+            return fail(CVGS_ERR_INVALID_VALUE, "out_row_pitch must be a multiple of 4 and hold a row");
+        o.row_stride = p.out_row_pitch / 4;
+        o.z_stride = p.out_plane_stride ? p.out_plane_stride : o.row_stride * p.dst_height;
     }
     o.vec4 = !o.u8 && p.out_layout != CVGS_OUT_PLANES && o.px_stride == 1 && (p.dst_width % 4) == 0 &&
              (reinterpret_cast<uintptr_t>(out) % 16) == 0 && (o.z_stride % 4) == 0 && (o.c_stride % 4) == 0;

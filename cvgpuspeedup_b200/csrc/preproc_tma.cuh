@@ -730,6 +730,7 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
     if (P.src_type != CVGS_8UC3) return false;  // the byte-level tap extraction is written for 3-byte pixels
     if (P.out.u8) return false;                 // 8-bit destinations are written by the direct-gather kernel
     if (P.prog.special) return false;           // conversions that change the channel count: direct-gather kernel
+    if (P.out.row_stride != static_cast<long long>(P.W) * P.out.px_stride) return false;  // padded packed rows: direct-gather kernel
     float fx_max = 0.f;
     for (int i = 0; i < used; ++i) {
         const DevCrop& c = crops[i];

@@ -63,7 +63,7 @@ struct ReadBatch {  // cvGS::resize(...) result
 struct ChainOp {  // multiply / subtract / divide / add / cvtColor / convertTo pieces
     cvgs_op_t op[2];
     int n = 0;
-    bool to_u8 = false;  // convertTo<CV_32FC3, CV_8UC3>(): must be the last operation, followed by write<CV_8UC3>
+    int to_u8 = 0;       // CVGS_8UC3 / CVGS_8UC4: convertTo<CV_32FCn, CV_8UCn>(), the last operation, followed by write<CV_8UCn>
     bool cast = false;   // fk::Cast<float3, uchar3>::build(): to_u8 with static_cast (truncation) instead of SaturateCast
 };
 struct WarpBatch {  // cvGS::warp(...) result
@@ -92,8 +92,9 @@ inline cvgs_op_t scalar_op(int kind, const cv::Scalar& s) {
     return o;
 }
 inline void append(cvgs_pipeline_t& p, const ChainOp& c) {
-    if (p.dst_type == CVGS_8UC3) throw std::runtime_error("cvGS: convertTo<CV_32FC3, CV_8UC3>() must be the last operation before the write");
-    if (c.to_u8) p.dst_type = CVGS_8UC3;
+    if (p.dst_type == CVGS_8UC3 || p.dst_type == CVGS_8UC4)
+        throw std::runtime_error("cvGS: convertTo<CV_32FCn, CV_8UCn>() must be the last operation before the write");
+    if (c.to_u8) p.dst_type = c.to_u8;
     if (c.cast) p.u8_cast = 1;
     for (int i = 0; i < c.n; ++i) {
         if (p.n_ops >= CVGS_MAX_OPS) throw std::runtime_error("cvGS: more than CVGS_MAX_OPS operations in the chain");
@@ -104,8 +105,10 @@ inline void append(cvgs_pipeline_t& p, const WriteOp& w) {
     p.out = w.layout == CVGS_OUT_PLANES ? const_cast<cvgs_plane_t*>(w.planes.data()) : w.out;
     p.out_layout = w.layout;
     p.out_plane_stride = w.plane_stride;
-    if ((w.dst_type == CVGS_8UC3) != (p.dst_type == CVGS_8UC3))
-        throw std::runtime_error("cvGS: write<CV_8UC3> and convertTo<CV_32FC3, CV_8UC3>() go together");
+    const bool chain_u8 = p.dst_type == CVGS_8UC3 || p.dst_type == CVGS_8UC4;
+    const bool write_u8 = w.dst_type == CVGS_8UC3 || w.dst_type == CVGS_8UC4;
+    if (chain_u8 != write_u8 || (chain_u8 && p.dst_type != w.dst_type))
+        throw std::runtime_error("cvGS: write<CV_8UCn> and convertTo<CV_32FCn, CV_8UCn>() go together");
     p.dst_type = w.dst_type;
     p.out_row_pitch = w.row_pitch;
 }
@@ -218,10 +221,10 @@ inline detail::ReadBatch resizeNV12(const std::array<cv::cuda::GpuMat, NPtr>& fr
 // ---- element-wise operations (reference :74-161) ---------------------------------------------------------
 template <int I, int O>
 inline detail::ChainOp convertTo() {  // SaturateCast<u8 -> f32>: the resize already yields float
-    static_assert(CV_MAT_DEPTH(O) == CV_32F || (I == CV_32FC3 && O == CV_8UC3),
-                  "cvGS (B200 build): convertTo produces CV_32F, or CV_8UC3 from CV_32FC3 as the last operation before write<CV_8UC3>");
+    static_assert(CV_MAT_DEPTH(O) == CV_32F || (I == CV_32FC3 && O == CV_8UC3) || (I == CV_32FC4 && O == CV_8UC4),
+                  "cvGS (B200 build): convertTo produces CV_32F, or CV_8UCn from CV_32FCn as the last operation before write<CV_8UCn>");
     detail::ChainOp c;
-    c.to_u8 = (O == CV_8UC3);  // SaturateCast<float, uchar>: applied by the kernel when it writes the 8-bit pixels
+    c.to_u8 = (O == CV_8UC3 || O == CV_8UC4) ? O : 0;  // SaturateCast<float, uchar>: applied by the kernel when it writes the 8-bit pixels
     return c;
 }
 template <int I, int O>
@@ -332,21 +335,17 @@ inline detail::WriteOp splitT(const fk::RawPtr<fk::T3D, float>& output) {
 }
 template <int O>
 inline detail::WriteOp write(const cv::cuda::GpuMat& output, const cv::Size& plane) {
-    static_assert(O == CV_32FC1 || O == CV_32FC3 || O == CV_32FC4 || O == CV_8UC3, "cvGS (B200 build): CV_32FC1/3/4 or CV_8UC3 output");
+    static_assert(O == CV_32FC1 || O == CV_32FC3 || O == CV_32FC4 || O == CV_8UC3 || O == CV_8UC4, "cvGS (B200 build): CV_32FC1/3/4 or CV_8UC3/4 output");
     detail::WriteOp w = detail::typed<O>({output.data, CVGS_OUT_NHWC, 0, {}});
-    if (O == CV_8UC3) w.row_pitch = 3LL * plane.width;  // gpuMat2Tensor builds a tight tensor of `plane`-sized images (reference :67-71)
+    if (CV_MAT_DEPTH(O) == CV_8U) w.row_pitch = static_cast<long long>(CV_MAT_CN(O)) * plane.width;  // gpuMat2Tensor builds a tight tensor of `plane`-sized images (reference :67-71)
     return w;
 }
 // PerThreadWrite<_2D, O>: one image with the GpuMat's own pitch (reference :449-452; tests/resize/test_resize_write.cu)
 template <int O>
 inline detail::WriteOp write(const cv::cuda::GpuMat& output) {
-    static_assert(O == CV_32FC1 || O == CV_32FC3 || O == CV_32FC4 || O == CV_8UC3, "cvGS (B200 build): CV_32FC1/3/4 or CV_8UC3 output");
+    static_assert(O == CV_32FC1 || O == CV_32FC3 || O == CV_32FC4 || O == CV_8UC3 || O == CV_8UC4, "cvGS (B200 build): CV_32FC1/3/4 or CV_8UC3/4 output");
     detail::WriteOp w = detail::typed<O>({output.data, CVGS_OUT_NHWC, 0, {}});
-    if (O == CV_8UC3) {
-        w.row_pitch = static_cast<long long>(output.step);
-    } else if (output.step != static_cast<size_t>(output.cols) * 4 * CV_MAT_CN(O)) {
-        throw std::runtime_error("cvGS::write<CV_32FCn>(GpuMat): a padded float destination is not supported by this build");
-    }
+    w.row_pitch = static_cast<long long>(output.step);  // the image's own pitch (cudaMallocPitch pads rows)
     return w;
 }
 
@@ -520,6 +519,27 @@ template <typename... IOpTypes>
 inline void executeOperations(const cv::cuda::GpuMat& input, const cv::cuda::Stream& stream, const IOpTypes&... iops) {
     executeOperations(std::array<cv::cuda::GpuMat, 1>{input}, stream, iops...);
 }
+// One image in, one image out (reference :489-503; tests/read/test_read_x_write.cu): PerThreadRead -> ops ->
+// PerThreadWrite<_2D> with the output's own pitch.  The reference takes the pixel type of the write from the last
+// operation; the operations are type-erased here, so it is the GpuMat's type (the library checks it against the chain).
+template <typename... IOpTypes>
+inline void executeOperations(const cv::cuda::GpuMat& input, cv::cuda::GpuMat& output, cv::cuda::Stream& stream,
+                              const IOpTypes&... iops) {
+    const int t = output.type();
+    if (t != CV_32FC1 && t != CV_32FC3 && t != CV_32FC4 && t != CV_8UC3 && t != CV_8UC4)
+        throw std::runtime_error("cvGS::executeOperations: output must be CV_32FC1/3/4 or CV_8UC3/4");
+    if (output.cols != input.cols || output.rows != input.rows)
+        throw std::runtime_error("cvGS::executeOperations: input and output sizes differ");
+    detail::WriteOp w{output.data, CVGS_OUT_NHWC, 0, {}};
+    w.dst_type = t;
+    w.row_pitch = static_cast<long long>(output.step);
+    executeOperations(stream, detail::read_batch(std::array<cv::cuda::GpuMat, 1>{input}, 1, cv::Scalar()), iops..., w);
+}
+template <bool ENABLE_THREAD_FUSION, typename... IOpTypes>
+inline void executeOperations(const cv::cuda::GpuMat& input, cv::cuda::GpuMat& output, cv::cuda::Stream& stream,
+                              const IOpTypes&... iops) {
+    executeOperations(input, output, stream, iops...);
+}
 
 // ---- CircularTensor (reference :600-627 over fkl/.../core/data/circular_tensor.cuh:84-151) ----------------
 template <int I, int O, int COLOR_PLANES, int BATCH, fk::CircularTensorOrder CT_ORDER,
@@ -587,11 +607,12 @@ namespace fk {
 // tests/warping/test_warping_opencv.cu:63): static_cast per channel, i.e. truncation.
 template <typename I, typename O>
 struct Cast {
-    static_assert(std::is_same<I, float3>::value && std::is_same<O, uchar3>::value,
-                  "cvGS (B200 build): fk::Cast<float3, uchar3> is the cast on this path");
+    static_assert((std::is_same<I, float3>::value && std::is_same<O, uchar3>::value) ||
+                      (std::is_same<I, float4>::value && std::is_same<O, uchar4>::value),
+                  "cvGS (B200 build): fk::Cast<float3, uchar3> / <float4, uchar4> are the casts on this path");
     static cvGS::detail::ChainOp build() {
         cvGS::detail::ChainOp c{};
-        c.to_u8 = true;
+        c.to_u8 = std::is_same<O, uchar3>::value ? CVGS_8UC3 : CVGS_8UC4;
         c.cast = true;
         return c;
     }

@@ -167,19 +167,22 @@ typedef struct cvgs_pipeline {
     int32_t n_ops;
     cvgs_op_t ops[CVGS_MAX_OPS];
     int32_t out_layout; /* enum cvgs_out_layout                                    */
-    int32_t dst_type;   /* 0 or CVGS_32FC3: float output.  CVGS_8UC3: the chain ends with convertTo<CV_32FC3, CV_8UC3>
-                           (SaturateCast<float, uchar>: round to nearest even, clamp to [0, 255], reference
-                           saturate.cuh:127-147) and packed 8-bit pixels are written -- cvGS::write<CV_8UC3>(GpuMat),
-                           the form of the reference's tests/resize/test_resize_write.cu; needs CVGS_OUT_NHWC. */
+    int32_t dst_type;   /* 0 (float, channels as the chain leaves them) or the matching CVGS_32FC1 / CVGS_32FC3 /
+                           CVGS_32FC4: float output.  CVGS_8UC3 / CVGS_8UC4 (3- / 4-channel sources): the chain ends with
+                           convertTo<CV_32FCn, CV_8UCn> (SaturateCast<float, uchar>: round to nearest even, clamp to
+                           [0, 255], reference saturate.cuh:127-147) and packed 8-bit pixels are written --
+                           cvGS::write<CV_8UCn>(GpuMat), the form of the reference's tests/resize/test_resize_write.cu
+                           and test_resize_CPUvsGPUresults.cu; needs CVGS_OUT_NHWC. */
     void* out;                 /* device pointer, float (CVGS_OUT_PLANES: host array of cvgs_plane_t) */
     int64_t out_plane_stride;  /* floats between consecutive batch planes z; 0 = tight
                                   (3*dst_width*dst_height for NCHW/NHWC, dst_width*dst_height
                                   for CNHW).  The reference ignores GpuMat::step.
-                                  For CVGS_8UC3 output the unit is bytes. */
-    int64_t out_row_pitch;     /* CVGS_8UC3 output only: bytes between rows of a destination image (GpuMat::step of
-                                  cvGS::write<CV_8UC3>(GpuMat)); 0 = tight (3 * dst_width) */
+                                  For 8-bit output the unit is bytes. */
+    int64_t out_row_pitch;     /* CVGS_OUT_NHWC only: BYTES between rows of a packed destination image (GpuMat::step of
+                                  cvGS::write<O>(GpuMat) / executeOperations(input, output, ...)); 0 = tight.  Float
+                                  images: a multiple of 4; out_plane_stride then defaults to rows * pitch. */
     int32_t yuv_standard;      /* CVGS_NV12 sources only: enum cvgs_yuv_standard */
-    int32_t u8_cast;           /* CVGS_8UC3 output only: 0 = SaturateCast (round to nearest even, clamp; convertTo),
+    int32_t u8_cast;           /* 8-bit output only: 0 = SaturateCast (round to nearest even, clamp; convertTo),
                                   1 = fk::Cast<float3, uchar3> (C++ static_cast: truncation; values must lie in [0, 256),
                                   reference basic_ops/cast.cuh:22-29, as in tests/warping/test_warping_opencv.cu:63) */
 } cvgs_pipeline_t;

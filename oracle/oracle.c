@@ -337,11 +337,11 @@ static void store_pixel(const cvgs_pipeline_t* p, int n_planes, int z, int y, in
     float* out = (float*)p->out;
     const int nc = chain_out_channels(p);
     const int64_t W = p->dst_width, H = p->dst_height;
-    if (p->dst_type == CVGS_8UC3) { /* convertTo<CV_32FC3, CV_8UC3> + PerThreadWrite: SaturateCast saturate.cuh:127-147 */
-        const int64_t rp = p->out_row_pitch ? p->out_row_pitch : 3 * W;
+    if (p->dst_type == CVGS_8UC3 || p->dst_type == CVGS_8UC4) { /* convertTo<CV_32FCn, CV_8UCn> + PerThreadWrite: SaturateCast saturate.cuh:127-147 */
+        const int64_t rp = p->out_row_pitch ? p->out_row_pitch : nc * W;
         const int64_t ps = p->out_plane_stride ? p->out_plane_stride : rp * H;
-        uint8_t* b = (uint8_t*)p->out + z * ps + y * rp + 3 * x;
-        for (int c = 0; c < 3; ++c)  /* u8_cast: fk::Cast = static_cast (truncation, cast.cuh:22-29) */
+        uint8_t* b = (uint8_t*)p->out + z * ps + y * rp + nc * x;
+        for (int c = 0; c < nc; ++c)  /* u8_cast: fk::Cast = static_cast (truncation, cast.cuh:22-29) */
             b[c] = p->u8_cast ? (uint8_t)(unsigned)v[c] : (uint8_t)round_sat_u8(v[c]);
         return;
     }
@@ -364,9 +364,10 @@ static void store_pixel(const cvgs_pipeline_t* p, int n_planes, int z, int y, in
                 *(float*)((char*)pl[c].data + (int64_t)y * pl[c].pitch_bytes + (int64_t)x * 4) = v[c];
             break;
         }
-        default: {
-            const int64_t ps = p->out_plane_stride ? p->out_plane_stride : nc * W * H;
-            float* b = out + z * ps + (y * W + x) * nc;
+        default: { /* packed pixels; rows may be padded (PerThreadWrite<_2D> into a pitched GpuMat) */
+            const int64_t rs = p->out_row_pitch ? p->out_row_pitch / 4 : nc * W;
+            const int64_t ps = p->out_plane_stride ? p->out_plane_stride : rs * H;
+            float* b = out + z * ps + y * rs + x * nc;
             for (int c = 0; c < nc; ++c) b[c] = v[c];
         }
     }

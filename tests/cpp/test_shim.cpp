@@ -7,6 +7,8 @@
 //   6. tests/warping/test_warping_opencv.cu:34-197  affine / perspective / batched perspective warp + fk::Cast + write,
 //      against the oracle (cv::cuda::warpAffine is not in this image), plus exact checks of the translation case
 //   7. cvGS::cvtColor codes that add / drop the alpha channel or reduce to gray, against the oracle
+//   8. one image in / one pitched image out (tests/read/test_read_x_write.cu) and the CV_8UC4 round trip of
+//      tests/resize/test_resize_CPUvsGPUresults.cu
 //   5. error convention: std::runtime_error (gpuErrchk, fkl/.../core/utils/utils.h:42-60)
 #include <cmath>
 #include <cstdio>
@@ -414,6 +416,64 @@ static int test_cvtcolor_channel_changes() {
     return 0;
 }
 
+// tests/read/test_read_x_write.cu:60-75 (one image in, one pitched image out: convertTo, subtract, multiply, divide, add)
+// and tests/resize/test_resize_CPUvsGPUresults.cu:45-47 (resize<CV_8UC4> -> convertTo<CV_32FC4, CV_8UC4> -> write<CV_8UC4>)
+static int test_read_x_write_and_8uc4() {
+    constexpr int W = 150, H = 70;
+    std::mt19937 rng(31);
+    cv::cuda::Stream st;
+    {
+        cv::cuda::GpuMat d_in(H, W, CV_8UC3), d_out(H, W, CV_32FC3);
+        REQUIRE(d_out.step > static_cast<size_t>(W) * 12);  // the stand-in pads rows like cudaMallocPitch
+        std::vector<uchar> h_in(d_in.step * H);
+        for (auto& b : h_in) b = static_cast<uchar>(rng());
+        REQUIRE(cudaMemcpy(d_in.data, h_in.data(), h_in.size(), cudaMemcpyHostToDevice) == cudaSuccess);
+        REQUIRE(cudaMemset(d_out.data, 0xCD, d_out.step * H) == cudaSuccess);
+        const cv::Scalar val_sub(1, 4, 3.2), val_mul(0.3, 0.5, 2.0), val_div(3.2, 0.6, 11.8), val_add(0.5, 1.5, 2.5);
+        cvGS::executeOperations(d_in, d_out, st, cvGS::convertTo<CV_8UC3, CV_32FC3>(), cvGS::subtract<CV_32FC3>(val_sub),
+                                cvGS::multiply<CV_32FC3>(val_mul), cvGS::divide<CV_32FC3>(val_div), cvGS::add<CV_32FC3>(val_add));
+        st.waitForCompletion();
+        std::vector<uchar> raw(d_out.step * H);
+        REQUIRE(cudaMemcpy(raw.data(), d_out.data, raw.size(), cudaMemcpyDeviceToHost) == cudaSuccess);
+        for (int y = 0; y < H; ++y) {
+            const float* row = reinterpret_cast<const float*>(raw.data() + y * d_out.step);
+            for (int x = 0; x < W; ++x)
+                for (int c = 0; c < 3; ++c) {
+                    const float px = h_in[y * d_in.step + 3 * x + c];
+                    // separate roundings: sub, mul, div, add in the order of the chain (no mul directly before the add)
+                    const float want = ((px - static_cast<float>(val_sub[c])) * static_cast<float>(val_mul[c])) / static_cast<float>(val_div[c]) +
+                                       static_cast<float>(val_add[c]);
+                    REQUIRE(row[3 * x + c] == want);
+                }
+            for (size_t b = static_cast<size_t>(W) * 12; b < d_out.step; ++b) REQUIRE(raw[y * d_out.step + b] == 0xCD);
+        }
+    }
+    {
+        cv::cuda::GpuMat d_in(H, W, CV_8UC4), d_out(40, 60, CV_8UC4);
+        std::vector<uchar> h_in(d_in.step * H);
+        for (auto& b : h_in) b = static_cast<uchar>(rng());
+        REQUIRE(cudaMemcpy(d_in.data, h_in.data(), h_in.size(), cudaMemcpyHostToDevice) == cudaSuccess);
+        cvGS::executeOperations(st, cvGS::resize<CV_8UC4, cv::INTER_LINEAR>(d_in, cv::Size(60, 40), 0., 0.),
+                                cvGS::convertTo<CV_32FC4, CV_8UC4>(), cvGS::write<CV_8UC4>(d_out));
+        st.waitForCompletion();
+        std::vector<uchar> got(d_out.step * 40), want(d_out.step * 40, 0);
+        REQUIRE(cudaMemcpy(got.data(), d_out.data, got.size(), cudaMemcpyDeviceToHost) == cudaSuccess);
+        const cvgs_crop_t crop{h_in.data(), W, H, static_cast<int32_t>(d_in.step), 0};
+        cvgs_pipeline_t p{};
+        p.src_type = CVGS_8UC4;
+        p.dst_width = 60;
+        p.dst_height = 40;
+        p.aspect_mode = CVGS_IGNORE_AR;
+        p.out_layout = CVGS_OUT_NHWC;
+        p.dst_type = CVGS_8UC4;
+        p.out_row_pitch = static_cast<int64_t>(d_out.step);
+        p.out = want.data();
+        REQUIRE(oracle_preproc(&crop, 1, 1, &p, 0) == 0);
+        for (int y = 0; y < 40; ++y) REQUIRE(std::memcmp(&got[y * d_out.step], &want[y * d_out.step], 60 * 4) == 0);
+    }
+    return 0;
+}
+
 static int test_error_convention() {
     cv::cuda::GpuMat d_input(16, 16, CV_8UC3, cv::Scalar(1, 2, 3));
     cv::cuda::GpuMat d_null;  // data == nullptr
@@ -443,6 +503,7 @@ int main() {
     failed += test_random_vs_oracle();
     failed += test_warping();
     failed += test_cvtcolor_channel_changes();
+    failed += test_read_x_write_and_8uc4();
     failed += test_error_convention();
     std::printf(failed ? "test_shim: %d FAILED\n" : "test_shim: all passed\n", failed);
     return failed ? 1 : 0;
