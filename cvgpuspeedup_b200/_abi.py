@@ -18,6 +18,7 @@ MAX_OPS = 8
 CVGS_8UC3, CVGS_16UC3, CVGS_16SC3, CVGS_32FC3 = 16, 18, 19, 21
 CVGS_8UC4, CVGS_16UC4, CVGS_16SC4, CVGS_32FC4 = 24, 26, 27, 29
 CVGS_NV12 = 0x1001
+CVGS_NV21, CVGS_P010, CVGS_P210, CVGS_Y210 = 0x1002, 0x1003, 0x1004, 0x1005
 YUV_BT601_FULL, YUV_BT709_FULL, YUV_BT709_LIMITED, YUV_BT2020_FULL = 0, 1, 2, 3
 WARP_AFFINE, WARP_PERSPECTIVE = 0, 1
 PRESERVE_AR, IGNORE_AR, PRESERVE_AR_RN_EVEN, PRESERVE_AR_LEFT = 0, 1, 2, 3

@@ -124,12 +124,14 @@ def resize(crops: Sequence[GpuMat], dsize: Tuple[int, int], usedPlanes: Optional
 
 
 def resize_nv12(frames: Sequence[GpuMat], dsize: Tuple[int, int], standard: int = _abi.YUV_BT709_FULL,
-                usedPlanes: Optional[int] = None, backgroundValue=(0.0, 0.0, 0.0), aspect: int = IGNORE_AR) -> _Resize:
+                usedPlanes: Optional[int] = None, backgroundValue=(0.0, 0.0, 0.0), aspect: int = IGNORE_AR,
+                fmt: int = _abi.CVGS_NV12) -> _Resize:
     """fk::Resize<INTER_LINEAR>::build(fk::fuse(Read<ReadYUV<NV12>>, Unary<ConvertYUVToRGB<NV12, range, primaries, false,
     float3>>), dsize) for a batch of NV12 frames (reference color_conversion.cuh:235-362, tests/resize/
     test_fused_resize.cu:73-76).  Each GpuMat describes the luma plane (cols x rows, step); the interleaved UV plane
-    follows it at data + step * rows.  The chain after it sees float RGB."""
-    r = resize(frames, dsize, usedPlanes, backgroundValue, aspect, _abi.CVGS_NV12)
+    follows it at data + step * rows.  The chain after it sees float RGB.  `fmt`: _abi.CVGS_NV12 / NV21 / P010 / P210 /
+    Y210 (include/cvgs_b200.h)."""
+    r = resize(frames, dsize, usedPlanes, backgroundValue, aspect, int(fmt))
     r.yuv_standard = int(standard)
     return r
 
@@ -336,7 +338,7 @@ def executeOperations(stream, *iops, fp_contract: int = FP_REFERENCE_FUSED, inte
     parents = (_abi.Parent * max(1, rs.used))()
     for i, m in enumerate(rs.crops[:rs.used]):
         parents[i].datastart, parents[i].whole_width, parents[i].whole_height = m.datastart, m.whole[0], m.whole[1]
-    if rs.src_type == _abi.CVGS_NV12:  # whole frames: nothing to say about parents
+    if _abi.CVGS_NV12 <= rs.src_type <= _abi.CVGS_Y210:  # whole frames: nothing to say about parents
         _abi.check(lib.cvgs_b200_preproc_launch(crops, len(rs.crops), rs.used, C.byref(p), _stream_ptr(stream)))
         return
     _abi.check(lib.cvgs_b200_preproc_launch_ex(crops, parents, len(rs.crops), rs.used, C.byref(p), _stream_ptr(stream)))

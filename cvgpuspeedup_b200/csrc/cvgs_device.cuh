@@ -77,7 +77,8 @@ struct PreprocParams {
     int32_t band_test;     // 1 for the aspect-ratio preserving modes
     int32_t src_type;      // CVGS_8UC3 / CVGS_16UC3 / CVGS_16SC3 / CVGS_8UC4 / CVGS_16UC4 / CVGS_16SC4
     int32_t nc;            // channels: 3 or 4
-    float yuv[10];         // CVGS_NV12: YCbCr -> RGB matrix (row-major 3x3) and the luma offset (16 for bt601, else 0)
+    float yuv[12];         // YUV sources: YCbCr -> RGB matrix (row-major 3x3), [9] luma offset (bt601: 16, 10-bit 64; else 0),
+                           // [10] chroma offset (128 / 512), [11] scale back to the stored range (1 / 64)
     float bg[4];           // background / default value (source channel order)
     DevProgram prog;
     OutDesc out;

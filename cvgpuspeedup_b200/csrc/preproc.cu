@@ -874,7 +874,7 @@ static bool sequence_sets_independent(const cvgs_crop_t* const* crops, const int
         const cvgs_pipeline_t* p = pipelines[s];
         if (!p || !p->out || !crops[s] || n_planes[s] <= 0 || used[s] < 0) return false;
         if (validate_pipeline(p) != CVGS_OK) return false;
-        if (p->out_layout == CVGS_OUT_PLANES || p->dst_type == CVGS_8UC3 || p->dst_type == CVGS_8UC4 || p->src_type == CVGS_NV12) return false;
+        if (p->out_layout == CVGS_OUT_PLANES || p->dst_type == CVGS_8UC3 || p->dst_type == CVGS_8UC4 || CVGS_IS_YUV(p->src_type)) return false;
         PreprocParams P;
         if (build_params(*p, n_planes[s], std::min(used[s], n_planes[s]), static_cast<float*>(p->out), P) != CVGS_OK) return false;
         const long long plane = static_cast<long long>(P.W) * P.H;

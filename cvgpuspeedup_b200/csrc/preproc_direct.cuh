@@ -65,15 +65,36 @@ __device__ __forceinline__ void gather_quad16(const PreprocParams& P, const DevC
 // One source pixel of an NV12 frame as float RGB: fk::ReadYUV<NV12> + fk::ConvertYUVToRGB<NV12, ., ., false, float3>
 // (reference color_conversion.cuh:235-291,296-316).  Rounding sequence of the reference's SASS: per channel
 // FMUL(y * m0), FFMA(u, m1, .), FFMA(v, m2, .) -- zero coefficients included -- after y - 16 (bt601 only), u - 128, v - 128.
+// The other readers (ReadYUV<NV21 / P010 / P210 / Y210>, :296-345) differ in where the three samples sit; the 10-bit
+// formats shift them down by 6, convert in the 10-bit range and multiply the float RGB by 64 afterwards (:226-232,270-291).
 __device__ __forceinline__ void nv12_px(const PreprocParams& P, const DevCrop& C, int x, int y, float (&rgb)[3]) {
-    const uint8_t* uvp = C.data + (size_t)C.pitch * (size_t)C.h + (size_t)(y >> 1) * (size_t)C.pitch + 2 * (size_t)(x >> 1);
-    const float yy = __fsub_rn((float)__ldg(C.data + (size_t)y * (size_t)C.pitch + x), P.yuv[9]);
-    const float u = __fsub_rn((float)__ldg(uvp), 128.0f), v = __fsub_rn((float)__ldg(uvp + 1), 128.0f);
+    float fy, fu, fv;
+    const size_t pitch = (size_t)C.pitch;
+    if (P.src_type == CVGS_NV12 || P.src_type == CVGS_NV21) {
+        const uint8_t* uvp = C.data + pitch * (size_t)C.h + (size_t)(y >> 1) * pitch + 2 * (size_t)(x >> 1);
+        fy = (float)__ldg(C.data + (size_t)y * pitch + x);
+        const float a = (float)__ldg(uvp), b = (float)__ldg(uvp + 1);
+        fu = P.src_type == CVGS_NV12 ? a : b;
+        fv = P.src_type == CVGS_NV12 ? b : a;
+    } else if (P.src_type == CVGS_Y210) {
+        const ushort4 q = __ldg(reinterpret_cast<const ushort4*>(C.data + (size_t)y * pitch) + (x >> 1));
+        fy = (float)(((x & 1) ? q.z : q.x) >> 6);
+        fu = (float)(q.y >> 6);
+        fv = (float)(q.w >> 6);
+    } else {  // P010 (4:2:0) / P210 (4:2:2)
+        const int cy = P.src_type == CVGS_P010 ? (y >> 1) : y;
+        const ushort2 uv = __ldg(reinterpret_cast<const ushort2*>(C.data + pitch * (size_t)C.h + (size_t)cy * pitch) + (x >> 1));
+        fy = (float)(__ldg(reinterpret_cast<const unsigned short*>(C.data + (size_t)y * pitch) + x) >> 6);
+        fu = (float)(uv.x >> 6);
+        fv = (float)(uv.y >> 6);
+    }
+    const float yy = __fsub_rn(fy, P.yuv[9]);
+    const float u = __fsub_rn(fu, P.yuv[10]), v = __fsub_rn(fv, P.yuv[10]);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         float t = __fmul_rn(yy, P.yuv[3 * r]);
         t = __fmaf_rn(u, P.yuv[3 * r + 1], t);
-        rgb[r] = __fmaf_rn(v, P.yuv[3 * r + 2], t);
+        rgb[r] = __fmul_rn(__fmaf_rn(v, P.yuv[3 * r + 2], t), P.yuv[11]);
     }
 }
 __device__ __forceinline__ void gather_quad_nv12(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,

@@ -56,17 +56,25 @@ inline void resize_geometry(int sw, int sh, int dw, int dh, int aspect, DevCrop&
 
 inline int channels_of(int src_type) { return (src_type == CVGS_8UC4 || src_type == CVGS_16UC4 || src_type == CVGS_16SC4) ? 4 : 3; }
 // YCbCr -> RGB matrices of the reference (color_conversion.cuh:171-214), row-major, + luma offset
-inline void yuv_constants(int standard, float (&m)[10]) {
+inline bool yuv_is_10bit(int src_type) { return src_type == CVGS_P010 || src_type == CVGS_P210 || src_type == CVGS_Y210; }
+inline void yuv_constants(int standard, int src_type, float (&m)[12]) {
     static const float k[4][10] = {
         {1.164383562f, 0.f, 1.596026786f, 1.164383562f, -0.39176229f, -0.812967647f, 1.164383562f, 2.017232143f, 0.f, 16.f},
         {1.f, 0.f, 1.5748f, 1.f, -0.1873f, -0.4681f, 1.f, 1.8556f, 0.f, 0.f},
         {1.f, 0.f, 1.402f, 1.f, -0.34414f, -0.71414f, 1.f, 1.772f, 0.f, 0.f},
         {1.f, 0.f, 1.4746f, 1.f, -0.16455312684366f, -0.57135312684366f, 1.f, 1.8814f, 0.f, 0.f}};
     for (int i = 0; i < 10; ++i) m[i] = k[standard][i];
+    // subCoefficients<p10bit> {64, 512}, floatShiftFactor<p10bit> 64 (color_conversion.cuh:106-111,189-192)
+    const bool ten = yuv_is_10bit(src_type);
+    if (ten) m[9] *= 4.f;
+    m[10] = ten ? 512.f : 128.f;
+    m[11] = ten ? 64.f : 1.f;
 }
 inline int pixel_bytes_of(int src_type) {
     switch (src_type) {
-        case CVGS_NV12: return 1;  // luma plane
+        case CVGS_NV12: case CVGS_NV21: return 1;  // luma plane
+        case CVGS_P010: case CVGS_P210: return 2;
+        case CVGS_Y210: return 4;                  // {Y0, U, Y1, V} words per pixel pair
         case CVGS_8UC3: return 3;
         case CVGS_8UC4: return 4;
         case CVGS_16UC3: case CVGS_16SC3: return 6;
@@ -177,9 +185,9 @@ inline int build_program(const cvgs_pipeline_t& p, DevProgram& prog) {
 inline int validate_pipeline(const cvgs_pipeline_t* p) {
     if (!p) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
     if (p->src_type != CVGS_8UC3 && p->src_type != CVGS_16UC3 && p->src_type != CVGS_16SC3 && p->src_type != CVGS_8UC4 &&
-        p->src_type != CVGS_16UC4 && p->src_type != CVGS_16SC4 && p->src_type != CVGS_NV12)
-        return fail(CVGS_ERR_NOT_SUPPORTED, "sources must be CV_8U / CV_16U / CV_16S with 3 or 4 channels, or NV12 frames");
-    if (p->src_type == CVGS_NV12 && (p->yuv_standard < 0 || p->yuv_standard > 3))
+        p->src_type != CVGS_16UC4 && p->src_type != CVGS_16SC4 && !CVGS_IS_YUV(p->src_type))
+        return fail(CVGS_ERR_NOT_SUPPORTED, "sources must be CV_8U / CV_16U / CV_16S with 3 or 4 channels, or NV12 / NV21 / P010 / P210 / Y210 frames");
+    if (CVGS_IS_YUV(p->src_type) && (p->yuv_standard < 0 || p->yuv_standard > 3))
         return fail(CVGS_ERR_INVALID_VALUE, "bad yuv_standard");
     if (p->dst_width <= 0 || p->dst_height <= 0 || p->dst_width > (1 << 20) || p->dst_height > (1 << 20))
         return fail(CVGS_ERR_INVALID_VALUE, "destination size out of range");
@@ -215,7 +223,7 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
     P.H = p.dst_height;
     P.band_test = p.aspect_mode != CVGS_IGNORE_AR;
     P.src_type = p.src_type;
-    if (p.src_type == CVGS_NV12) yuv_constants(p.yuv_standard, P.yuv);
+    if (CVGS_IS_YUV(p.src_type)) yuv_constants(p.yuv_standard, p.src_type, P.yuv);
     P.nc = channels_of(p.src_type);
     for (int c = 0; c < P.nc; ++c) P.bg[c] = p.background[c];
     if (int rc = build_program(p, P.prog)) return rc;
@@ -277,8 +285,9 @@ inline int fill_crop(const cvgs_crop_t& c, const cvgs_pipeline_t& p, int idx, De
     const int px_bytes = pixel_bytes_of(p.src_type);
     if (c.pitch < px_bytes * c.width && c.height > 1)
         return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": pitch smaller than a row");
-    if (px_bytes >= 6 && ((reinterpret_cast<uintptr_t>(c.data) | static_cast<uintptr_t>(c.pitch)) & 1))
-        return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": 16-bit pixels must be 2-byte aligned");
+    const int align = p.src_type == CVGS_Y210 ? 8 : ((p.src_type == CVGS_P010 || p.src_type == CVGS_P210) ? 4 : (px_bytes >= 6 ? 2 : 1));
+    if ((reinterpret_cast<uintptr_t>(c.data) | static_cast<uintptr_t>(c.pitch)) & (align - 1))
+        return fail(CVGS_ERR_INVALID_VALUE, "crop " + std::to_string(idx) + ": 16-bit pixels must be aligned to their vector type");
     d.data = static_cast<const uint8_t*>(c.data);
     d.w = c.width;
     d.h = c.height;

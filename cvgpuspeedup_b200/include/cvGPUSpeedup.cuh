@@ -42,6 +42,7 @@ struct RawPtr {
     PtrDims3D dims;
 };
 enum WarpType { Affine = 0, Perspective = 1 };  // warping.cuh:25
+enum PixelFormat { NV12, NV21, YV12, P010, P016, P216, P210, Y216, Y210, Y416 };  // color_conversion.cuh:89
 }  // namespace fk
 
 namespace cvGS {
@@ -201,9 +202,28 @@ inline detail::ReadBatch resize(const cv::cuda::GpuMat& input, const cv::Size& d
 // fk::NV12, range, primaries, false, float3>>{}), dsize), tests/resize/test_fused_resize.cu:73-76); here it is one
 // more read of the same pipeline.  Each GpuMat is the CV_8UC1 luma plane; the interleaved UV plane follows it at
 // data + step * rows.  standard: enum cvgs_yuv_standard.
+// resizeYUV<fk::NV21 / fk::P010 / fk::P210 / fk::Y210, N>: the other fk::ReadYUV formats (color_conversion.cuh:296-345);
+// the GpuMat describes the luma plane in pixels (cols x rows, step in bytes) -- CV_8UC1, CV_16UC1, or for Y210 the
+// packed image with cols = pixel width.
 template <int NPtr>
 inline detail::ReadBatch resizeNV12(const std::array<cv::cuda::GpuMat, NPtr>& frames, const cv::Size& dsize, int standard,
-                                    int usedPlanes = NPtr, const cv::Scalar& backgroundValue = cv::Scalar()) {
+                                    int usedPlanes = NPtr, const cv::Scalar& backgroundValue = cv::Scalar());
+template <fk::PixelFormat PF, int NPtr>
+inline detail::ReadBatch resizeYUV(const std::array<cv::cuda::GpuMat, NPtr>& frames, const cv::Size& dsize, int standard,
+                                   int usedPlanes = NPtr, const cv::Scalar& backgroundValue = cv::Scalar()) {
+    static_assert(PF == fk::NV12 || PF == fk::NV21 || PF == fk::P010 || PF == fk::P210 || PF == fk::Y210,
+                  "cvGS (B200 build): NV12, NV21, P010, P210 and Y210 frames are the YUV sources on this path");
+    detail::ReadBatch r = resizeNV12<NPtr>(frames, dsize, standard, usedPlanes, backgroundValue);
+    r.src_type = PF == fk::NV12 ? CVGS_NV12 : PF == fk::NV21 ? CVGS_NV21 : PF == fk::P010 ? CVGS_P010 : PF == fk::P210 ? CVGS_P210 : CVGS_Y210;
+    for (int i = 0; i < NPtr && i < usedPlanes; ++i) {  // crop_of takes the width in pixels of the GpuMat's own type
+        r.crops[i].width = frames[i].cols;
+        r.crops[i].height = frames[i].rows;
+    }
+    return r;
+}
+template <int NPtr>
+inline detail::ReadBatch resizeNV12(const std::array<cv::cuda::GpuMat, NPtr>& frames, const cv::Size& dsize, int standard,
+                                    int usedPlanes, const cv::Scalar& backgroundValue) {
     detail::ReadBatch r;
     r.n_planes = NPtr;
     r.used = usedPlanes;

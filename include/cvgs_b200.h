@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CVGS_B200_VERSION 104 /* 0.1.4 */
+#define CVGS_B200_VERSION 105 /* 0.1.5 */
 
 /* ---- error codes (subset of cudaError_t values so they can be passed through) ---- */
 #define CVGS_OK 0
@@ -59,6 +59,19 @@ extern "C" {
  * fkl/.../image_processing/color_conversion.cuh:235-362; tests/resize/test_fused_resize.cu:73-76,141-143).  A crop
  * of this type is a whole frame {Y plane, width, height, pitch}; the pipeline sees float RGB.  Direct-gather kernel. */
 #define CVGS_NV12 0x1001
+/* The other fk::PixelFormat readers the reference can instantiate (color_conversion.cuh:89-98,296-345), same contract:
+ *   CVGS_NV21  as NV12 with the chroma bytes in V, U order
+ *   CVGS_P010  16-bit words with the 10-bit sample in the high bits (>> 6): Y plane, then an interleaved UV plane of
+ *              height/2 rows at data + pitch * height (4:2:0)
+ *   CVGS_P210  as P010 with a chroma row per luma row (4:2:2)
+ *   CVGS_Y210  packed 4:2:2: {Y0, U, Y1, V} 16-bit words per pixel pair, 10-bit samples in the high bits
+ * The 10-bit formats are converted in their own range (chroma - 512, bt601 luma - 64) and the float RGB is multiplied by
+ * 64 afterwards (NormalizeColorRangeDepth), i.e. it is 16-bit-scaled like the stored samples. */
+#define CVGS_NV21 0x1002
+#define CVGS_P010 0x1003
+#define CVGS_P210 0x1004
+#define CVGS_Y210 0x1005
+#define CVGS_IS_YUV(t) ((t) >= CVGS_NV12 && (t) <= CVGS_Y210)
 
 /* YCbCr -> RGB matrices of the reference (color_conversion.cuh:171-214): ccMatrix<range, primaries, YCbCr2RGB>. */
 enum cvgs_yuv_standard {
@@ -181,7 +194,7 @@ typedef struct cvgs_pipeline {
     int64_t out_row_pitch;     /* CVGS_OUT_NHWC only: BYTES between rows of a packed destination image (GpuMat::step of
                                   cvGS::write<O>(GpuMat) / executeOperations(input, output, ...)); 0 = tight.  Float
                                   images: a multiple of 4; out_plane_stride then defaults to rows * pitch. */
-    int32_t yuv_standard;      /* CVGS_NV12 sources only: enum cvgs_yuv_standard */
+    int32_t yuv_standard;      /* YUV sources (CVGS_NV12 ... CVGS_Y210) only: enum cvgs_yuv_standard */
     int32_t u8_cast;           /* 8-bit output only: 0 = SaturateCast (round to nearest even, clamp; convertTo),
                                   1 = fk::Cast<float3, uchar3> (C++ static_cast: truncation; values must lie in [0, 256),
                                   reference basic_ops/cast.cuh:22-29, as in tests/warping/test_warping_opencv.cu:63) */

@@ -118,18 +118,41 @@ static const float kYuvMatrix[4][9] = {
     {1.f, 0.f, 1.5748f, 1.f, -0.1873f, -0.4681f, 1.f, 1.8556f, 0.f},
     {1.f, 0.f, 1.402f, 1.f, -0.34414f, -0.71414f, 1.f, 1.772f, 0.f},
     {1.f, 0.f, 1.4746f, 1.f, -0.16455312684366f, -0.57135312684366f, 1.f, 1.8814f, 0.f}};
-static void nv12_px(const cvgs_crop_t* c, int x, int y, int standard, float rgb[3]) {
+/* The other readers (ReadYUV<NV21 / P010 / P210 / Y210>, :296-345): NV21 swaps the chroma bytes; the 10-bit formats keep
+ * the sample in the high bits of 16-bit words (ShiftRight by shiftFactor<p10bit> = 6, :183-186,278), are converted in the
+ * 10-bit range (subCoefficients<p10bit> {64, 512}, :106-111) and the float RGB is scaled back by floatShiftFactor = 64
+ * (NormalizeColorRangeDepth, :226-232). */
+static void nv12_px(const cvgs_crop_t* c, int src_type, int x, int y, int standard, float rgb[3]) {
     const uint8_t* base = (const uint8_t*)c->data;
-    const uint8_t* uv = base + (size_t)c->pitch * (size_t)c->height + (size_t)(y >> 1) * (size_t)c->pitch + 2 * (size_t)(x >> 1);
-    float yy = (float)base[(size_t)y * (size_t)c->pitch + x];
-    if (standard == CVGS_YUV_BT601_FULL) yy = yy - 16.0f;
-    const float u = (float)uv[0] - 128.0f, v = (float)uv[1] - 128.0f;
+    const size_t pitch = (size_t)c->pitch;
+    float yy, u, v;
+    const int ten = src_type == CVGS_P010 || src_type == CVGS_P210 || src_type == CVGS_Y210;
+    if (src_type == CVGS_NV12 || src_type == CVGS_NV21) {
+        const uint8_t* uv = base + pitch * (size_t)c->height + (size_t)(y >> 1) * pitch + 2 * (size_t)(x >> 1);
+        yy = (float)base[(size_t)y * pitch + x];
+        u = (float)uv[src_type == CVGS_NV12 ? 0 : 1];
+        v = (float)uv[src_type == CVGS_NV12 ? 1 : 0];
+    } else if (src_type == CVGS_Y210) {
+        const uint16_t* q = (const uint16_t*)(base + (size_t)y * pitch) + 4 * (size_t)(x >> 1);
+        yy = (float)(q[(x & 1) ? 2 : 0] >> 6);
+        u = (float)(q[1] >> 6);
+        v = (float)(q[3] >> 6);
+    } else {
+        const int cy = src_type == CVGS_P010 ? (y >> 1) : y;
+        const uint16_t* uv = (const uint16_t*)(base + pitch * (size_t)c->height + (size_t)cy * pitch) + 2 * (size_t)(x >> 1);
+        yy = (float)(((const uint16_t*)(base + (size_t)y * pitch))[x] >> 6);
+        u = (float)(uv[0] >> 6);
+        v = (float)(uv[1] >> 6);
+    }
+    if (standard == CVGS_YUV_BT601_FULL) yy = yy - (ten ? 64.0f : 16.0f);
+    u = u - (ten ? 512.0f : 128.0f);
+    v = v - (ten ? 512.0f : 128.0f);
     const float* m = kYuvMatrix[standard];
     for (int r = 0; r < 3; ++r) {
         float t = yy * m[3 * r];
         t = fmaf(u, m[3 * r + 1], t);
         t = fmaf(v, m[3 * r + 2], t);
-        rgb[r] = t;
+        rgb[r] = ten ? t * 64.0f : t;
     }
 }
 
@@ -169,12 +192,12 @@ static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspec
     const uint8_t* base = (const uint8_t*)c->data;
     const uint8_t* r0 = base + (size_t)y1 * (size_t)c->pitch;
     const uint8_t* r1 = base + (size_t)y2r * (size_t)c->pitch;
-    if (src_type == CVGS_NV12) { /* the back-function of the resize is read + colour conversion: taps are float RGB */
+    if (CVGS_IS_YUV(src_type)) { /* the back-function of the resize is read + colour conversion: taps are float RGB */
         float p00[3], p10[3], p01[3], p11[3];
-        nv12_px(c, x1, y1, yuv_standard, p00);
-        nv12_px(c, x2r, y1, yuv_standard, p10);
-        nv12_px(c, x1, y2r, yuv_standard, p01);
-        nv12_px(c, x2r, y2r, yuv_standard, p11);
+        nv12_px(c, src_type, x1, y1, yuv_standard, p00);
+        nv12_px(c, src_type, x2r, y1, yuv_standard, p10);
+        nv12_px(c, src_type, x1, y2r, yuv_standard, p01);
+        nv12_px(c, src_type, x2r, y2r, yuv_standard, p11);
         for (int ch = 0; ch < 3; ++ch) {
             float t = p10[ch] * w10;
             t = fmaf(p00[ch], w00, t);
@@ -380,8 +403,8 @@ int oracle_preproc(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_
                    int nthreads) {
     if (!crops || !p || !p->out || n_planes <= 0 || used < 0 ||
         (p->src_type != CVGS_8UC3 && p->src_type != CVGS_16UC3 && p->src_type != CVGS_16SC3 &&
-         p->src_type != CVGS_8UC4 && p->src_type != CVGS_16UC4 && p->src_type != CVGS_16SC4 && p->src_type != CVGS_NV12) ||
-        (p->src_type == CVGS_NV12 && (p->yuv_standard < 0 || p->yuv_standard > 3)) ||
+         p->src_type != CVGS_8UC4 && p->src_type != CVGS_16UC4 && p->src_type != CVGS_16SC4 && !CVGS_IS_YUV(p->src_type)) ||
+        (CVGS_IS_YUV(p->src_type) && (p->yuv_standard < 0 || p->yuv_standard > 3)) ||
         p->dst_width <= 0 || p->dst_height <= 0 || p->n_ops < 0 || p->n_ops > CVGS_MAX_OPS)
         return 1;
     if (used > n_planes) used = n_planes;

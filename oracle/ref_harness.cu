@@ -225,6 +225,54 @@ int FKREF_CAT(fkref_nv12_, FKREF_BATCH)(int standard, const void* data, int w, i
 }
 #endif
 
+#ifdef FKREF_YUV
+// The other ReadYUV formats (NV21 8-bit; P010, P210, Y210 10-bit in 16-bit words), same chain as fkref_nv12.
+// format: 2 NV21, 3 P010, 4 P210, 5 Y210 (CVGS_NVxx & 0xf).  Instantiated for bt601 full (0) and bt2020 full (3).
+}  // extern "C"
+namespace {
+template <fk::PixelFormat PF, fk::ColorRange CR, fk::ColorPrimitives CP>
+int run_yuv(const void* data, int w, int h, int pitch, int dst_w, int dst_h, const float* mul, const float* sub,
+            const float* div, float* out, cudaStream_t stream) {
+    using Base = typename fk::ReadYUV<PF>::PixelBaseType;
+    const fk::RawPtr<fk::_2D, Base> img{ (Base*)data, { (uint)w, (uint)h, (uint)pitch } };
+    const auto readBackOp = fk::fuse(fk::Read<fk::ReadYUV<PF>>{ img },
+                                     fk::Unary<fk::ConvertYUVToRGB<PF, CR, CP, false, float3>>{});
+    const auto readOp = fk::Resize<fk::INTER_LINEAR>::build(readBackOp, fk::Size(dst_w, dst_h));
+    const fk::Tensor<float> t_out(out, dst_w, dst_h, 1, 3);
+    fk::executeOperations(stream, readOp, fk::Binary<fk::Mul<float3>>{ float3{mul[0], mul[1], mul[2]} },
+                          fk::Binary<fk::Sub<float3>>{ float3{sub[0], sub[1], sub[2]} },
+                          fk::Binary<fk::Div<float3>>{ float3{div[0], div[1], div[2]} },
+                          fk::Write<fk::TensorSplit<float3>>{ t_out.ptr() });
+    return 0;
+}
+template <fk::PixelFormat PF>
+int run_yuv_std(int standard, const void* data, int w, int h, int pitch, int dst_w, int dst_h, const float* mul,
+                const float* sub, const float* div, float* out, cudaStream_t s) {
+    if (standard == 0) return run_yuv<PF, fk::Full, fk::bt601>(data, w, h, pitch, dst_w, dst_h, mul, sub, div, out, s);
+    if (standard == 3) return run_yuv<PF, fk::Full, fk::bt2020>(data, w, h, pitch, dst_w, dst_h, mul, sub, div, out, s);
+    g_err = "fkref: yuv standard not instantiated for this format";
+    return -1;
+}
+}  // namespace
+extern "C" {
+int FKREF_CAT(fkref_yuv_, FKREF_BATCH)(int format, int standard, const void* data, int w, int h, int pitch, int dst_w,
+                                       int dst_h, const float* mul, const float* sub, const float* div, float* out, void* stream) {
+    try {
+        cudaStream_t s = (cudaStream_t)stream;
+        switch (format) {
+            case 2: return run_yuv_std<fk::NV21>(standard, data, w, h, pitch, dst_w, dst_h, mul, sub, div, out, s);
+            case 3: return run_yuv_std<fk::P010>(standard, data, w, h, pitch, dst_w, dst_h, mul, sub, div, out, s);
+            case 4: return run_yuv_std<fk::P210>(standard, data, w, h, pitch, dst_w, dst_h, mul, sub, div, out, s);
+            case 5: return run_yuv_std<fk::Y210>(standard, data, w, h, pitch, dst_w, dst_h, mul, sub, div, out, s);
+            default: g_err = "fkref: bad yuv format"; return -1;
+        }
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+#endif
+
 #ifdef FKREF_WARP
 // One image through fk::Warping<WT, PerThreadRead<_2D, uchar3>> (tests/warping/test_warping_opencv.cu:60-64):
 //   mode 0:  warp -> Mul(mul) -> TensorSplit into float out[3][dst_h][dst_w]

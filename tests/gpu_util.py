@@ -227,3 +227,22 @@ def run_fkref_cvt(code, image, width, height, dsize, mul, sub, d_image=None):
     assert rc == 0
     torch.cuda.synchronize()
     return out.cpu().numpy()
+
+
+def run_fkref_yuv(fmt, frame, width, height, dsize, standard, mul, sub, div, d_frame=None):
+    """The reference's ReadYUV<fmt> + ConvertYUVToRGB + Resize + Mul/Sub/Div + TensorSplit on one frame
+    (oracle/_ref/libfkref_16.so, -DFKREF_YUV; standards 0 and 3).  fmt: _abi.CVGS_NV21 / P010 / P210 / Y210."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libfkref_16.so")
+    lib = C.CDLL(path)
+    fn = lib.fkref_yuv_16
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                   C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+    d = device_image(frame) if d_frame is None else d_frame
+    out = torch.full((3, dsize[1], dsize[0]), float("nan"), dtype=torch.float32, device="cuda")
+    f3 = lambda v: (C.c_float * 3)(*v)  # noqa: E731
+    rc = fn(fmt & 0xF, standard, d.data_ptr(), width, height, frame.shape[1], dsize[0], dsize[1], f3(mul), f3(sub), f3(div),
+            out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return out.cpu().numpy()

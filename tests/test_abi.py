@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_abi.SYMBOLS) == declared, "ctypes table and header disagree"
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.cvgs_b200_version() == 104
+    assert lib.cvgs_b200_version() == 105
 
 
 def test_struct_layouts_match_c(tmp_path):

@@ -21,7 +21,7 @@ def _frame(seed, w, h, pitch):
     return rng.integers(0, 256, size=(h + (h + 1) // 2, pitch), dtype=np.uint8)
 
 
-def _ours(frames, sizes, pitch, dsize, standard, ops, **kw):
+def _ours(frames, sizes, pitch, dsize, standard, ops, src_type=_abi.CVGS_NV12, **kw):
     """One launch for all frames (each frame is one 'crop' = a whole NV12 image)."""
     lib = _abi.load()
     d = [torch.from_numpy(f).cuda() for f in frames]
@@ -30,19 +30,19 @@ def _ours(frames, sizes, pitch, dsize, standard, ops, **kw):
     for i, (t, (w, h)) in enumerate(zip(d, sizes)):
         crops[i].data, crops[i].width, crops[i].height, crops[i].pitch = t.data_ptr(), w, h, pitch
     out = torch.full((n, 3, dsize[1], dsize[0]), float("nan"), device="cuda")
-    p = util.make_pipeline(dsize, ops, out_ptr=out.data_ptr(), src_type=_abi.CVGS_NV12, yuv_standard=standard, **kw)
+    p = util.make_pipeline(dsize, ops, out_ptr=out.data_ptr(), src_type=src_type, yuv_standard=standard, **kw)
     _abi.check(lib.cvgs_b200_preproc_launch(crops, n, n, C.byref(p), None))
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
 
-def _oracle(frames, sizes, pitch, dsize, standard, ops, **kw):
+def _oracle(frames, sizes, pitch, dsize, standard, ops, src_type=_abi.CVGS_NV12, **kw):
     n = len(frames)
     crops = (_abi.Crop * n)()
     for i, (f, (w, h)) in enumerate(zip(frames, sizes)):
         crops[i].data, crops[i].width, crops[i].height, crops[i].pitch = f.ctypes.data, w, h, pitch
     out = np.full((n, 3, dsize[1], dsize[0]), np.nan, dtype=np.float32)
-    p = util.make_pipeline(dsize, ops, out_ptr=out.ctypes.data, src_type=_abi.CVGS_NV12, yuv_standard=standard, **kw)
+    p = util.make_pipeline(dsize, ops, out_ptr=out.ctypes.data, src_type=src_type, yuv_standard=standard, **kw)
     assert util.oracle_lib().oracle_preproc(crops, n, n, C.byref(p), 0) == 0
     return out
 
@@ -72,3 +72,54 @@ def test_nv12_modes_and_layouts():
                dict(fp_contract=_abi.FP_SEPARATE)]:
         util.assert_bit_equal(_ours(frames, sizes, pitch, (96, 64), 1, ops, **kw), _oracle(frames, sizes, pitch, (96, 64), 1, ops, **kw),
                               f"nv12 {kw}")
+
+
+def _yuv_frame(seed, fmt, w, h, pitch):
+    """Random frame of the given format: every byte random, so the low 6 bits of the 10-bit words are noise too."""
+    rng = np.random.default_rng(seed)
+    rows = {_abi.CVGS_NV21: h + (h + 1) // 2, _abi.CVGS_P010: h + (h + 1) // 2, _abi.CVGS_P210: 2 * h, _abi.CVGS_Y210: h}[fmt]
+    return rng.integers(0, 256, size=(rows, pitch), dtype=np.uint8)
+
+
+FORMATS = [_abi.CVGS_NV21, _abi.CVGS_P010, _abi.CVGS_P210, _abi.CVGS_Y210]
+
+
+@pytest.mark.parametrize("standard", [0, 3])
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_other_yuv_formats_match_reference_kernel_and_oracle(fmt, standard):
+    """ReadYUV<NV21 / P010 / P210 / Y210> + ConvertYUVToRGB (reference color_conversion.cuh:296-345,235-291)."""
+    if gpu_util.fkref_lib(16) is None:
+        pytest.skip("oracle/_ref not built")
+    pitch = 2048
+    sizes = [(320, 240), (322, 242), (162, 122), (64, 36), (2, 2)]
+    frames = [_yuv_frame(1000 + 10 * standard + i + fmt, fmt, w, h, pitch) for i, (w, h) in enumerate(sizes)]
+    for dsize in [(64, 128), (400, 300), (33, 7)]:
+        ours = _ours(frames, sizes, pitch, dsize, standard, OPS, src_type=fmt)
+        orc = _oracle(frames, sizes, pitch, dsize, standard, OPS, src_type=fmt)
+        util.assert_bit_equal(ours, orc, f"format {fmt:#x} standard {standard} dsize {dsize}: ours vs oracle")
+        for i, (f, (w, h)) in enumerate(zip(frames, sizes)):
+            ref = gpu_util.run_fkref_yuv(fmt, f, w, h, dsize, standard, MUL, SUB, DIV)
+            util.assert_bit_equal(ours[i], ref, f"format {fmt:#x} standard {standard} dsize {dsize} frame {i}: ours vs reference kernel")
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_other_yuv_formats_modes(fmt):
+    pitch = 1280
+    sizes = [(300, 200), (128, 128)]
+    frames = [_yuv_frame(1100 + i + fmt, fmt, w, h, pitch) for i, (w, h) in enumerate(sizes)]
+    ops = [("reorder", (2, 1, 0)), ("mul", (0.5, 0.25, 2.0)), ("add", (1.0, 2.0, 3.0))]
+    for standard, kw in [(1, dict(aspect=_abi.PRESERVE_AR, background=(1.0, 2.0, 3.0))), (2, dict(fp_contract=_abi.FP_SEPARATE)),
+                         (0, dict(layout=_abi.OUT_NHWC))]:
+        got = _ours(frames, sizes, pitch, (96, 64), standard, ops, src_type=fmt, **kw)
+        want = _oracle(frames, sizes, pitch, (96, 64), standard, ops, src_type=fmt, **kw)
+        util.assert_bit_equal(got.reshape(-1), want.reshape(-1), f"format {fmt:#x} {kw}")
+
+
+def test_yuv_alignment_is_checked():
+    lib = _abi.load()
+    t = torch.zeros(1 << 16, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(3 * 8 * 8, device="cuda")
+    crops = (_abi.Crop * 1)()
+    crops[0].data, crops[0].width, crops[0].height, crops[0].pitch = t.data_ptr() + 2, 16, 16, 128
+    p = util.make_pipeline((8, 8), [], out_ptr=out.data_ptr(), src_type=_abi.CVGS_Y210)
+    assert lib.cvgs_b200_preproc_launch(crops, 1, 1, C.byref(p), None) != 0 and b"aligned" in lib.cvgs_b200_last_error()

@@ -228,7 +228,8 @@ def test_golden_vectors_from_reference_kernel():
             dsize = tuple(int(v) for v in g["dsize"])
             got = np.full((1, 3, dsize[1], dsize[0]), np.nan, dtype=np.float32)
             p = util.make_pipeline(dsize, [("mul", tuple(g["mul"])), ("sub", tuple(g["sub"])), ("div", tuple(g["div"]))],
-                                   out_ptr=got.ctypes.data, src_type=_abi.CVGS_NV12, yuv_standard=int(g["standard"]))
+                                   out_ptr=got.ctypes.data, src_type=int(g["src_type"]) if "src_type" in g else _abi.CVGS_NV12,
+                                   yuv_standard=int(g["standard"]))
             assert util.oracle_lib().oracle_preproc(crop, 1, 1, C.byref(p), 0) == 0
             util.assert_bit_equal(got[0], g["out"], os.path.basename(f))
             continue
