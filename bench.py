@@ -570,6 +570,10 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int):
                 graph_extra["frac_of_peak"] = graph_extra["achieved_gbs"] / peak
             line["extra"]["c2_cuda_graph"] = graph_extra
         try:
+            line["extra"]["c2_single_launch"] = c2_latency_extra(lib, torch, _abi, crops_pp, parents_pp, n_arr, pipes_pp, F, stream)
+        except Exception as e:
+            line["extra"]["c2_single_launch"] = {"error": str(e)[:200]}
+        try:
             c4 = c4_extra(torch, util, stream)
             c4["frac_of_peak"] = c4["achieved_gbs"] / peak
             line["extra"]["c4"] = c4
@@ -662,6 +666,39 @@ def c4_extra(torch, util, stream, depth=16, reps=20):
     return {"workload": f"c4: CircularTensor depth {depth}, {W}x{H} planes, 1080p frames, one kernel per update",
             "us_per_update": us, "updates_per_s": 1e6 / us, "algorithmic_bytes_per_update": alg,
             "achieved_gbs": alg / (us * 1e-6) / 1e9}
+
+
+def c2_latency_extra(lib, torch, _abi, crops_pp, parents_pp, n_arr, pipes_pp, n_sets, stream, reps=200):
+    """the latency of ONE 50-crop launch (stream idle before and after: event, launch, event, synchronise),
+    plain stream order, min / median over `reps` launches on rotating frames; and the back-to-back time of the same
+    launches from one host thread (the frame loop of the headline uses three)."""
+    prev = lib.cvgs_b200_set_overlap(0)
+    try:
+        sp = stream.cuda_stream
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lat = []
+        for i in range(reps + 20):
+            s = i % n_sets
+            torch.cuda.synchronize()
+            e0.record(stream)
+            _abi.check(lib.cvgs_b200_preproc_launch_ex(crops_pp[s], parents_pp[s], n_arr[s], n_arr[s], pipes_pp[s], sp))
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if i >= 20:
+                lat.append(e0.elapsed_time(e1) * 1e3)
+        lat.sort()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        _abi.check(lib.cvgs_b200_preproc_launch_sequence_ex(crops_pp, parents_pp, n_arr, n_arr, pipes_pp, n_sets, 20 * n_sets, sp))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        serial = e0.elapsed_time(e1) * 1e3 / (20 * n_sets)
+    finally:
+        lib.cvgs_b200_set_overlap(prev)
+    return {"what": "one isolated 50-crop launch between two events on an idle stream (includes the event overhead), plain "
+                    "stream order; and the same launches back to back from one host thread without overlap",
+            "latency_us_min": lat[0], "latency_us_median": lat[len(lat) // 2], "launches": len(lat),
+            "one_thread_stream_order_us_per_launch": serial}
 
 
 def c3_reference_us(sets, torch, stream, reps=10):

@@ -57,6 +57,7 @@ struct DevPlane {       // one destination image of the per-plane output form (f
     float* data;
     long long pitch;    // floats between rows
 };
+constexpr long long kNoStore = -0x7fffffffffffffffLL - 1;
 struct OutDesc {
     const DevPlane* planes;  // device table [z][source channel], or nullptr for the tensor layouts below
     float* base;
@@ -67,6 +68,7 @@ struct OutDesc {
     int32_t u8;          // packed 8-bit output after the chain, strides below in bytes: 1 SaturateCast<float, uchar>,
                          // 2 fk::Cast (static_cast: truncation, low byte)
     long long row_pitch; // u8 output: bytes between rows
+    long long c_off[4];   // float tensor layouts: register r goes to row + c_off[r] (= dst_chan[r] * c_stride); kNoStore: dropped
     long long row_stride; // float output (tensor layouts): floats between rows (W * px_stride unless the caller set out_row_pitch)
 };
 
@@ -246,23 +248,32 @@ __device__ __forceinline__ void store_pixels(const PreprocParams& P, int z, int 
             }
         return;
     }
-    float* row = o.base + (long long)z * o.z_stride + (long long)y * o.row_stride + (long long)x * o.px_stride;
+    if (o.planes) {  // fk::SplitWrite: a table of destination images indexed by SOURCE channel (the host applied dst_chan)
 #pragma unroll
-    for (int r = 0; r < NC; ++r) {
-        if (P.prog.dst_chan[r] < 0) continue;  // register dropped by a channel-count changing conversion
-        // the channel reorder costs nothing: it only changes which plane register r goes to
-        float* dst = row + (long long)P.prog.dst_chan[r] * o.c_stride;
-        if (o.planes) {  // table is indexed by SOURCE channel (the host applied dst_chan when it built it)
+        for (int r = 0; r < NC; ++r) {
             const DevPlane pl = o.planes[z * NC + r];
-            dst = pl.data + (long long)y * pl.pitch + x;
-        }
-        if (NPIX == 4 && o.vec4 && nvalid == 4) {
-            st_cs_f32x4(dst, v[0][r], v[1][r], v[2][r], v[3][r]);
-        } else {
+            float* dst = pl.data + (long long)y * pl.pitch + x;
 #pragma unroll
             for (int p = 0; p < NPIX; ++p)
-                if (p < nvalid) st_cs_f32(dst + (long long)p * o.px_stride, v[p][r]);
+                if (p < nvalid) st_cs_f32(dst + p, v[p][r]);
         }
+        return;
+    }
+    // the channel reorder costs nothing: it only changes which plane register r goes to (c_off, computed on the host)
+    float* row = o.base + (long long)z * o.z_stride + (long long)y * o.row_stride + (long long)x * o.px_stride;
+    if (NPIX == 4 && o.vec4 && nvalid == 4) {
+#pragma unroll
+        for (int r = 0; r < NC; ++r)
+            if (o.c_off[r] != kNoStore) st_cs_f32x4(row + o.c_off[r], v[0][r], v[1][r], v[2][r], v[3][r]);
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < NC; ++r) {
+        if (o.c_off[r] == kNoStore) continue;  // register dropped by a channel-count changing conversion
+        float* dst = row + o.c_off[r];
+#pragma unroll
+        for (int p = 0; p < NPIX; ++p)
+            if (p < nvalid) st_cs_f32(dst + (long long)p * o.px_stride, v[p][r]);
     }
 }
 

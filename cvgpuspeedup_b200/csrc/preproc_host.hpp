@@ -273,6 +273,7 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
         o.row_stride = p.out_row_pitch / 4;
         o.z_stride = p.out_plane_stride ? p.out_plane_stride : o.row_stride * p.dst_height;
     }
+    for (int r = 0; r < 4; ++r) o.c_off[r] = P.prog.dst_chan[r] < 0 ? kNoStore : P.prog.dst_chan[r] * o.c_stride;
     o.vec4 = !o.u8 && p.out_layout != CVGS_OUT_PLANES && o.px_stride == 1 && (p.dst_width % 4) == 0 &&
              (reinterpret_cast<uintptr_t>(out) % 16) == 0 && (o.z_stride % 4) == 0 && (o.c_stride % 4) == 0;
     return CVGS_OK;

@@ -741,6 +741,10 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
     if (static_cast<long long>(P.W) * P.H * 3 * std::max<long long>(1, std::abs(P.out.px_stride)) > 0x3fffffffLL)
         return false;  // in-plane offsets are 32-bit in the kernel
     int NPB = std::min(kMaxNP, (P.W + 31) / 32);
+    if (const char* e = std::getenv("CVGS_TMA_NPB")) {  // tuning override (profiling)
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= kMaxNP) NPB = std::min(NPB, v);
+    }
     auto need = [&](int npb) { return used > 0 ? band_row_bytes(std::min(32 * npb, P.W), fx_max) : 64; };
     while (NPB > 1 && need(NPB) > kMaxBoxBytes) --NPB;
     if (need(NPB) > kMaxBoxBytes) return false;  // extreme down-scale: direct kernel
