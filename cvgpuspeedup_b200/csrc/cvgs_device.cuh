@@ -236,15 +236,17 @@ template <int NPIX, int NC = 3>
 __device__ __forceinline__ void store_pixels(const PreprocParams& P, int z, int y, int x, int nvalid,
                                              const float (&v)[NPIX][NC]) {
     const OutDesc& o = P.out;
-    if (o.u8) {  // convertTo<CV_32FC3, CV_8UC3> + packed write: byte dst_chan[r] of pixel p is register r
-        uint8_t* px = reinterpret_cast<uint8_t*>(o.base) + (long long)z * o.z_stride + (long long)y * o.row_pitch + (long long)NC * x;
+    if (o.u8) {  // convertTo<CV_32FCn, CV_8UCn> + packed write: byte dst_chan[r] of pixel p is register r
+        const int nco = P.prog.nc_out;  // channels of the written pixel (the chain may have added / dropped the alpha)
+        uint8_t* px = reinterpret_cast<uint8_t*>(o.base) + (long long)z * o.z_stride + (long long)y * o.row_pitch + (long long)nco * x;
 #pragma unroll
         for (int p = 0; p < NPIX; ++p)
             if (p < nvalid) {
 #pragma unroll
                 for (int r = 0; r < NC; ++r)
-                    px[NC * p + P.prog.dst_chan[r]] =
-                        o.u8 == 2 ? (uint8_t)__float2uint_rz(v[p][r]) : (uint8_t)round_sat_u8(v[p][r]);
+                    if (P.prog.dst_chan[r] >= 0)
+                        px[nco * p + P.prog.dst_chan[r]] =
+                            o.u8 == 2 ? (uint8_t)__float2uint_rz(v[p][r]) : (uint8_t)round_sat_u8(v[p][r]);
             }
         return;
     }

@@ -202,11 +202,9 @@ inline int validate_pipeline(const cvgs_pipeline_t* p) {
     if (p->u8_cast != 0 && (p->u8_cast != 1 || (p->dst_type != CVGS_8UC3 && p->dst_type != CVGS_8UC4)))
         return fail(CVGS_ERR_INVALID_VALUE, "u8_cast is 0 or 1 and applies to 8-bit output");
     const bool u8_out = p->dst_type == CVGS_8UC3 || p->dst_type == CVGS_8UC4;
-    if (u8_out && channels_of(p->src_type) != (p->dst_type == CVGS_8UC3 ? 3 : 4))
-        return fail(CVGS_ERR_NOT_SUPPORTED, "8-bit output has the channel count of the source (CV_8UC3 / CV_8UC4)");
     if (u8_out && p->out_layout != CVGS_OUT_NHWC)
         return fail(CVGS_ERR_INVALID_VALUE, "8-bit output is packed: out_layout must be CVGS_OUT_NHWC");
-    if (u8_out && p->out_row_pitch != 0 && p->out_row_pitch < static_cast<long long>(channels_of(p->src_type)) * p->dst_width)
+    if (u8_out && p->out_row_pitch != 0 && p->out_row_pitch < (p->dst_type == CVGS_8UC3 ? 3LL : 4LL) * p->dst_width)
         return fail(CVGS_ERR_INVALID_VALUE, "out_row_pitch smaller than a row");
     if (!u8_out && p->out_row_pitch != 0 && p->out_layout != CVGS_OUT_NHWC)
         return fail(CVGS_ERR_INVALID_VALUE, "out_row_pitch applies to packed output (CVGS_OUT_NHWC)");
@@ -229,8 +227,10 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
     if (int rc = build_program(p, P.prog)) return rc;
     const int NC = P.prog.nc_out;  // channels of the OUTPUT pixel
     const bool u8_out = p.dst_type == CVGS_8UC3 || p.dst_type == CVGS_8UC4;
-    if (P.prog.special && (u8_out || p.out_layout == CVGS_OUT_PLANES))
-        return fail(CVGS_ERR_NOT_SUPPORTED, "conversions that change the channel count write float tensors (NCHW / CNHW / NHWC)");
+    if (P.prog.special && p.out_layout == CVGS_OUT_PLANES)
+        return fail(CVGS_ERR_NOT_SUPPORTED, "conversions that change the channel count write tensors or packed images, not per-plane images");
+    if (u8_out && NC != (p.dst_type == CVGS_8UC3 ? 3 : 4))
+        return fail(CVGS_ERR_INVALID_VALUE, "dst_type does not match the channels the chain produces");
     if (p.dst_type == CVGS_32FC1 || p.dst_type == CVGS_32FC3 || p.dst_type == CVGS_32FC4) {
         const int want = p.dst_type == CVGS_32FC1 ? 1 : (p.dst_type == CVGS_32FC3 ? 3 : 4);
         if (want != NC) return fail(CVGS_ERR_INVALID_VALUE, "dst_type does not match the channels the chain produces");

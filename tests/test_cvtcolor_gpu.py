@@ -114,6 +114,7 @@ def test_bad_chains_are_rejected():
     assert rc([("gray", ())], dst_type=_abi.CVGS_32FC3) != 0 and b"dst_type" in lib.cvgs_b200_last_error()
     assert rc([("gray", ())], dst_type=_abi.CVGS_32FC1) == 0
     assert rc([("gray", ())], layout=_abi.OUT_PLANES) != 0
+    assert rc([("gray", ())], layout=_abi.OUT_NHWC, dst_type=_abi.CVGS_8UC3) != 0
     assert rc([("add_alpha", (1.0,)), ("reorder", (0, 1, 2, 4))]) != 0
     torch.cuda.synchronize()
 

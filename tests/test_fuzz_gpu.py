@@ -52,3 +52,94 @@ def test_random_geometry(seed):
         got = gpu_util.run_cvgs(img, rects, dsize, ops, variant=variant, d_image=d_img, parents=parents, **kw)
         util.assert_bit_equal(got, want, f"seed {seed} variant {variant} parents {parents} frame {fw}x{fh} pitch {pitch} "
                                          f"shift {shift} n {n} dsize {dsize} aspect {aspect} layout {layout}")
+
+
+def _random_chain(rng, nc):
+    """A random chain over the per-channel ops, reorders and the channel-count changing conversions; returns
+    (ops, channels of the result)."""
+    ops = []
+    for _ in range(int(rng.integers(0, 6))):
+        k = int(rng.integers(0, 8))
+        vals = tuple(float(v) for v in rng.uniform(0.25, 4.0, size=nc) * rng.choice([-1.0, 1.0], size=nc))
+        if k == 0:
+            ops.append(("mul", vals))
+        elif k == 1:
+            ops.append(("sub", vals))
+        elif k == 2:
+            ops.append(("add", vals))
+        elif k == 3:
+            ops.append(("div", vals))
+        elif k == 4 and nc >= 3:
+            ops.append(("reorder", tuple(int(v) for v in rng.permutation(nc))))
+        elif k == 5 and nc == 3 and not any(o[0] == "add_alpha" for o in ops):
+            ops.append(("add_alpha", (float(rng.choice([255.0, 1.0, 0.5])),)))
+            nc = 4
+        elif k == 6 and nc == 4:
+            ops.append(("drop_alpha", ()))
+            nc = 3
+        elif k == 7 and nc >= 3:
+            ops.append(("gray", (int(rng.integers(0, 2)),)))
+            nc = 1
+    return ops, nc
+
+
+SRC_TYPES = [_abi.CVGS_8UC3, _abi.CVGS_16UC3, _abi.CVGS_16SC3, _abi.CVGS_8UC4, _abi.CVGS_16UC4, _abi.CVGS_16SC4]
+
+
+@pytest.mark.parametrize("seed", range(36))
+def test_random_source_types_chains_and_outputs(seed):
+    """The forms outside the TMA kernel: every source depth / channel count, chains with the colour conversions,
+    8-bit output, packed float output with padded rows -- against the oracle."""
+    import ctypes as C
+    rng = np.random.default_rng(5000 + seed)
+    src_type = SRC_TYPES[seed % len(SRC_TYPES)]
+    px, nc = util.px_bytes_of(src_type), util.channels_of(src_type)
+    fw, fh = int(rng.integers(20, 300)), int(rng.integers(20, 200))
+    pitch = (px * fw + 15) // 16 * 16 + 16 * int(rng.integers(0, 3))
+    img = rng.integers(0, 256, size=(fh, pitch), dtype=np.uint8)
+    d_img = torch.from_numpy(img).cuda()
+    n = int(rng.integers(1, 80))
+    rects = []
+    for _ in range(n):
+        w, h = int(rng.integers(1, fw + 1)), int(rng.integers(1, fh + 1))
+        rects.append((int(rng.integers(0, fw - w + 1)), int(rng.integers(0, fh - h + 1)), w, h))
+    W, H = int(rng.integers(1, 150)), int(rng.integers(1, 100))
+    ops, nco = _random_chain(rng, nc)
+    n_planes = n + int(rng.integers(0, 3))
+    kw = dict(aspect=int(rng.integers(0, 4)), background=tuple(float(v) for v in rng.uniform(-5, 260, size=4))[:nc],
+              src_type=src_type)
+    if rng.random() < 0.3:
+        kw.update(fp_contract=_abi.FP_SEPARATE)
+    if rng.random() < 0.3:
+        kw.update(interp_mode=_abi.INTERP_ROUND_U8)
+    form = int(rng.integers(0, 4))
+    lib = _abi.load()
+    crops_h = util.host_crops(img, rects, px_bytes=px)
+    crops_d = util.host_crops(img, rects, base_ptr=d_img.data_ptr(), px_bytes=px)
+    what = f"seed {seed} src {src_type} ops {ops} form {form} dsize {(W, H)} n {n}/{n_planes} {kw}"
+    if form == 0 and nco >= 3:  # 8-bit packed output with its own pitch
+        rp = nco * W + int(rng.integers(0, 9))
+        kw.update(layout=_abi.OUT_NHWC, dst_type=_abi.CVGS_8UC3 if nco == 3 else _abi.CVGS_8UC4, row_pitch=rp,
+                  u8_cast=0)
+        want = np.full((n_planes, H, rp), 7, dtype=np.uint8)
+        got = torch.full((n_planes, H, rp), 7, dtype=torch.uint8, device="cuda")
+    elif form == 1:  # packed float output with padded rows
+        rs = nco * W + int(rng.integers(0, 6))
+        kw.update(layout=_abi.OUT_NHWC, row_pitch=4 * rs)
+        want = np.full((n_planes, H, rs), -3.0, dtype=np.float32)
+        got = torch.full((n_planes, H, rs), -3.0, dtype=torch.float32, device="cuda")
+    else:  # tensor layouts
+        layout = int(rng.integers(0, 3))
+        kw.update(layout=layout)
+        shape = util.out_shape(n_planes, (W, H), layout, 0, nco)
+        want = np.full(shape, np.nan, dtype=np.float32)
+        got = torch.full(shape, float("nan"), dtype=torch.float32, device="cuda")
+    p = util.make_pipeline((W, H), ops, out_ptr=want.ctypes.data, **kw)
+    assert util.oracle_lib().oracle_preproc(crops_h, n_planes, n, C.byref(p), 0) == 0, what
+    p = util.make_pipeline((W, H), ops, out_ptr=got.data_ptr(), **kw)
+    _abi.check(lib.cvgs_b200_preproc_launch(crops_d, n_planes, n, C.byref(p), None))
+    torch.cuda.synchronize()
+    if want.dtype == np.uint8:
+        assert np.array_equal(got.cpu().numpy(), want), what
+    else:
+        util.assert_bit_equal(got.cpu().numpy(), want, what)

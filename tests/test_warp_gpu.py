@@ -227,3 +227,34 @@ def test_warp_rejects_bad_input():
     p16 = util.make_pipeline((8, 8), [], out_ptr=out.data_ptr(), src_type=_abi.CVGS_16UC3)
     assert lib.cvgs_b200_warp_launch(crops, warps, 1, 1, C.byref(p16), None) != 0
     assert lib.cvgs_b200_warp_launch(None, warps, 1, 1, C.byref(p), None) != 0
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_wild_matrices_against_oracle(seed):
+    """Raw inverse matrices straight into the C-ABI: huge and tiny coefficients, denominators that cross zero inside
+    the destination (infinite / NaN coordinates), mirrored and degenerate transforms -- whatever the coordinate is, both
+    sides must agree on inside / outside and on every bit of the interpolation."""
+    rng = np.random.default_rng(8000 + seed)
+    w, h, pitch = int(rng.integers(2, 200)), int(rng.integers(2, 150)), 640
+    img = util.make_image(rng, w, h, pitch)
+    d = gpu_util.device_image(img)
+    warp_type = seed % 2
+    n = 5
+    inverses = []
+    for i in range(n):
+        scale = float(10.0 ** rng.uniform(-3, 2))
+        m = rng.normal(0, scale, size=9).astype(np.float32)
+        m[2], m[5] = rng.uniform(-w, 2 * w), rng.uniform(-h, 2 * h)
+        if warp_type == 1:
+            m[6], m[7] = rng.normal(0, 0.02, size=2)
+            m[8] = rng.choice([1.0, -0.5, 0.0, 1e-30, 3.0])
+        if i == 3:
+            m[:] = 0.0                       # everything maps to (0, 0) (affine) or to NaN (perspective: 0 / 0)
+        if i == 4:
+            m[:6] = [1, 0, 0.5, 0, 1, -0.25]  # near identity with fractional shifts
+        inverses.append(m)
+    dsize = (int(rng.integers(1, 130)), int(rng.integers(1, 90)))
+    ops = util.OPS_C2 if seed % 3 else []
+    ours = _launch([d] * n, [(w, h)] * n, pitch, inverses, warp_type, dsize, ops)
+    orc = _oracle([img] * n, [(w, h)] * n, pitch, inverses, warp_type, dsize, ops)
+    util.assert_bit_equal(ours, orc, f"seed {seed} type {warp_type} image {w}x{h} dsize {dsize}")
