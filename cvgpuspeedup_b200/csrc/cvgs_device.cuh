@@ -239,6 +239,29 @@ __device__ __forceinline__ void store_pixels(const PreprocParams& P, int z, int 
     if (o.u8) {  // convertTo<CV_32FCn, CV_8UCn> + packed write: byte dst_chan[r] of pixel p is register r
         const int nco = P.prog.nc_out;  // channels of the written pixel (the chain may have added / dropped the alpha)
         uint8_t* px = reinterpret_cast<uint8_t*>(o.base) + (long long)z * o.z_stride + (long long)y * o.row_pitch + (long long)nco * x;
+        if (NPIX == 4 && nvalid == 4 && nco == NC && o.vec4) {
+            // the four pixels of the thread are NC * 4 contiguous bytes starting at a multiple of 4 (x % 4 == 0, rows and
+            // base 4-byte aligned: vec4): assemble them in registers and store NC words instead of 4 * NC bytes
+            uint32_t b[4][NC];  // [pixel][output channel]
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    float t = v[p][0];
+#pragma unroll
+                    for (int r = 1; r < NC; ++r) t = P.prog.dst_chan[r] == c ? v[p][r] : t;  // uniform selects
+                    b[p][c] = o.u8 == 2 ? (__float2uint_rz(t) & 0xffu) : (uint32_t)round_sat_u8(t);
+                }
+            uint32_t* wp = reinterpret_cast<uint32_t*>(px);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {  // word k holds bytes 4k .. 4k+3 of the NC * 4
+                uint32_t w = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w |= b[(4 * k + j) / NC][(4 * k + j) % NC] << (8 * j);
+                asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(wp + k), "r"(w) : "memory");
+            }
+            return;
+        }
 #pragma unroll
         for (int p = 0; p < NPIX; ++p)
             if (p < nvalid) {

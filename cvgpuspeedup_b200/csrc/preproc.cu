@@ -419,8 +419,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         if (memo.valid && memo.n_planes == n_planes && memo.used == used && std::memcmp(&memo.key, &key, sizeof key) == 0) {
             P = memo.P;
             P.out.base = out;
-            P.out.vec4 = P.out.px_stride == 1 && (P.W % 4) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0 &&
-                         (P.out.z_stride % 4) == 0 && (P.out.c_stride % 4) == 0;
+            P.out.vec4 = out_vec4(P.out, P.W, pipe->out_layout == CVGS_OUT_PLANES, out);
         } else {
             if (int rc = build_params(*pipe, n_planes, used, out, P)) return rc;
             std::memset(&memo.key, 0, sizeof memo.key);

@@ -120,13 +120,39 @@ __device__ __forceinline__ void gather_quad_nv12(const PreprocParams& P, const D
     }
 }
 
+// CV_8UC4 taps as one aligned 32-bit load each (uchar4 rows are 4-byte aligned whenever base and pitch are).
+__device__ __forceinline__ void gather_quad_u8c4(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
+                                                 float (&v)[4][4]) {
+    const AxisTap ty_ = axis_tap(y - C.by1, C.fy);
+    const int y2r = min(ty_.i1 + 1, C.h - 1);
+    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(C.data + (size_t)ty_.i1 * (size_t)C.pitch);
+    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(C.data + (size_t)y2r * (size_t)C.pitch);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int x = x0 + p;
+        if (p < nvalid && x >= C.bx1 && x <= C.bx2) {
+            const AxisTap tx_ = axis_tap(x - C.bx1, C.fx);
+            const int x1 = tx_.i1, x2r = min(tx_.i1 + 1, C.w - 1);
+            const float w00 = __fmul_rn(tx_.w0, ty_.w0), w10 = __fmul_rn(tx_.w1, ty_.w0);
+            const float w01 = __fmul_rn(tx_.w0, ty_.w1), w11 = __fmul_rn(tx_.w1, ty_.w1);
+            const uint32_t a0 = __ldg(r0 + x1), a1 = __ldg(r0 + x2r), b0 = __ldg(r1 + x1), b1 = __ldg(r1 + x2r);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                v[p][c] = bilerp(u8_to_f32(a0, c), u8_to_f32(a1, c), u8_to_f32(b0, c), u8_to_f32(b1, c), w00, w10, w01, w11);
+        }
+    }
+}
+
 // 4-channel sources (CV_8UC4 / CV_16UC4 / CV_16SC4): same arithmetic on four channels.
 __device__ __forceinline__ void gather_quad(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
                                             float (&v)[4][4]) {
     fill_background<4>(P, v);
     const bool row_in = !P.band_test || (y >= C.by1 && y <= C.by2);
     if (!row_in) return;
-    if (P.src_type == CVGS_8UC4) gather_quad16<unsigned char, 4>(P, C, y, x0, nvalid, v);
+    if (P.src_type == CVGS_8UC4) {
+        if (((reinterpret_cast<uintptr_t>(C.data) | static_cast<uintptr_t>(C.pitch)) & 3) == 0) gather_quad_u8c4(P, C, y, x0, nvalid, v);
+        else gather_quad16<unsigned char, 4>(P, C, y, x0, nvalid, v);
+    }
     else if (P.src_type == CVGS_16UC4) gather_quad16<unsigned short, 4>(P, C, y, x0, nvalid, v);
     else gather_quad16<short, 4>(P, C, y, x0, nvalid, v);
 }

@@ -212,6 +212,13 @@ inline int validate_pipeline(const cvgs_pipeline_t* p) {
     return CVGS_OK;
 }
 
+// Wide stores: planar float rows written 16 bytes at a time, or (8-bit output) quads of pixels as whole 32-bit words.
+inline int out_vec4(const OutDesc& o, int dst_width, bool planes, const void* out) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(out);
+    if (o.u8) return (a % 4) == 0 && (o.row_pitch % 4) == 0 && (o.z_stride % 4) == 0;
+    return !planes && o.px_stride == 1 && (dst_width % 4) == 0 && (a % 16) == 0 && (o.z_stride % 4) == 0 && (o.c_stride % 4) == 0;
+}
+
 // Fill the launch parameters that do not depend on the crops.
 inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float* out, PreprocParams& P) {
     std::memset(&P, 0, sizeof P);
@@ -274,8 +281,7 @@ inline int build_params(const cvgs_pipeline_t& p, int n_planes, int used, float*
         o.z_stride = p.out_plane_stride ? p.out_plane_stride : o.row_stride * p.dst_height;
     }
     for (int r = 0; r < 4; ++r) o.c_off[r] = P.prog.dst_chan[r] < 0 ? kNoStore : P.prog.dst_chan[r] * o.c_stride;
-    o.vec4 = !o.u8 && p.out_layout != CVGS_OUT_PLANES && o.px_stride == 1 && (p.dst_width % 4) == 0 &&
-             (reinterpret_cast<uintptr_t>(out) % 16) == 0 && (o.z_stride % 4) == 0 && (o.c_stride % 4) == 0;
+    o.vec4 = out_vec4(o, p.dst_width, p.out_layout == CVGS_OUT_PLANES, out);
     return CVGS_OK;
 }
 
