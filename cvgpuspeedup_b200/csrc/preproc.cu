@@ -11,8 +11,8 @@
 //                          own work items into shared memory with the TMA engine (cp.async.bulk.tensor, mbarrier
 //                          per slot) and computes row pairs in packed FP32.
 //   preproc_direct_kernel  gathers the bilinear taps straight from global memory; takes anything the TMA kernel
-//                          declines: pitches that are not multiples of 16 bytes, extreme down-scales, 16-bit
-//                          sources, 8-bit destinations.
+//                          declines: pitches that are not multiples of 16 bytes, extreme down-scales, 16-bit and
+//                          4-channel sources, YUV frames, conversions that change the channel count.
 // This file: the direct kernel, the host launch path (descriptor tables in kernel parameters or through a pinned
 // ring, per-image tensor-map cache, overlap bookkeeping) and the C-ABI entry points of the batch pipeline.
 #include <cuda_runtime.h>
@@ -140,12 +140,16 @@ static MemRange crops_range(const DevCrop* c, int n) {
 static MemRange out_range(const PreprocParams& P) {
     // every layout stays inside [base, base + extent): NCHW/NHWC planes z*z_stride + 3*W*H, CNHW c*c_stride + ...
     const long long plane = static_cast<long long>(P.W) * P.H;
+    MemRange r;
+    r.lo = reinterpret_cast<uintptr_t>(P.out.base);
+    if (P.out.u8) {  // strides in bytes
+        r.hi = r.lo + static_cast<uintptr_t>((P.n_planes - 1) * P.out.z_stride + P.out.row_pitch * P.H);
+        return r;
+    }
     long long extent;
     const int nco = P.prog.nc_out > 0 ? P.prog.nc_out : 3;
     if (P.out.px_stride != 1) extent = (P.n_planes - 1) * P.out.z_stride + P.out.row_stride * P.H;
     else extent = (nco - 1) * P.out.c_stride + (P.n_planes - 1) * P.out.z_stride + plane;
-    MemRange r;
-    r.lo = reinterpret_cast<uintptr_t>(P.out.base);
     r.hi = r.lo + static_cast<uintptr_t>(extent) * sizeof(float);
     return r;
 }

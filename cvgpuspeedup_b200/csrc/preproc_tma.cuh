@@ -547,6 +547,11 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         float* s2 = s0 + oc2;
         s0 += oc0;
         long long rs0 = row_step, rs1 = row_step, rs2 = row_step;  // floats between vertically adjacent pixels
+        // 8-bit packed output (general instantiation only): byte address of this lane's first pixel in row 2*jp
+        uint8_t* u8row = nullptr;
+        if (GEN && P.out.u8)
+            u8row = reinterpret_cast<uint8_t*>(P.out.base) + (long long)z * P.out.z_stride + (long long)(2 * cc.jp) * P.out.row_pitch +
+                    3LL * (tx0 + lane);
         if (GEN && P.out.planes) {  // per-plane destinations (fk::SplitWrite): own pointer and pitch per channel
             const DevPlane p0 = P.out.planes[z * 3], p1 = P.out.planes[z * 3 + 1], p2 = P.out.planes[z * 3 + 2];
             rs0 = p0.pitch, rs1 = p1.pitch, rs2 = p2.pitch;
@@ -624,13 +629,26 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                                 if (!(im1 && (m_img & (1u << p)))) v[c].y = vb[0][c];
                             }
                         }
-                        const int q = 32 * p * pxs;
-                        st_cs_f32(s0 + q, v[0].x);
-                        st_cs_f32(s1 + q, v[1].x);
-                        st_cs_f32(s2 + q, v[2].x);
-                        st_cs_f32_if(st1, t0 + q, v[0].y);
-                        st_cs_f32_if(st1, t1 + q, v[1].y);
-                        st_cs_f32_if(st1, t2 + q, v[2].y);
+                        if (GEN && P.out.u8) {  // SaturateCast<float, uchar> (or fk::Cast) + packed pixels, 3 bytes each
+                            uint8_t* ub = u8row + 96 * p;
+                            uint8_t* ub1 = ub + P.out.row_pitch;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const int d = P.prog.dst_chan[c];
+                                const uint32_t a = P.out.u8 == 2 ? __float2uint_rz(v[c].x) : (uint32_t)round_sat_u8(v[c].x);
+                                const uint32_t b = P.out.u8 == 2 ? __float2uint_rz(v[c].y) : (uint32_t)round_sat_u8(v[c].y);
+                                ub[d] = (uint8_t)a;
+                                if (st1) ub1[d] = (uint8_t)b;
+                            }
+                        } else {
+                            const int q = 32 * p * pxs;
+                            st_cs_f32(s0 + q, v[0].x);
+                            st_cs_f32(s1 + q, v[1].x);
+                            st_cs_f32(s2 + q, v[2].x);
+                            st_cs_f32_if(st1, t0 + q, v[0].y);
+                            st_cs_f32_if(st1, t1 + q, v[1].y);
+                            st_cs_f32_if(st1, t2 + q, v[2].y);
+                        }
                     }
                 }
             };
@@ -646,6 +664,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             s0 += 2 * (GEN ? rs0 : (long long)row_step);
             s1 += 2 * (GEN ? rs1 : (long long)row_step);
             s2 += 2 * (GEN ? rs2 : (long long)row_step);
+            if (GEN && P.out.u8) u8row += 2 * P.out.row_pitch;
 
             // every lane has consumed its taps of this slot (their values fed the stores above): refill it
             __syncwarp();
@@ -728,7 +747,7 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
                      int items_per_warp, TmaGeom& G, bool need_driver = true) {
     if (need_driver && !encode_tiled_fn()) return false;
     if (P.src_type != CVGS_8UC3) return false;  // the byte-level tap extraction is written for 3-byte pixels
-    if (P.out.u8) return false;                 // 8-bit destinations are written by the direct-gather kernel
+    if (P.out.u8 && P.prog.nc_out != 3) return false;
     if (P.prog.special) return false;           // conversions that change the channel count: direct-gather kernel
     if (P.out.row_stride != static_cast<long long>(P.W) * P.out.px_stride) return false;  // padded packed rows: direct-gather kernel
     float fx_max = 0.f;
@@ -999,7 +1018,7 @@ template <typename Table>
 inline int tma_launch_kernel(const TmaParams& K, const Table& T, int chain, int device, cudaStream_t stream) {
     static_assert(sizeof(TmaParams) + sizeof(Table) <= 32 * 1024, "kernel parameters exceed 32 KB");
     const PreprocParams& P = K.P;
-    const bool fast = !P.band_test && P.used == P.n_planes && P.out.px_stride == 1 && !P.out.planes;
+    const bool fast = !P.band_test && P.used == P.n_planes && P.out.px_stride == 1 && !P.out.planes && !P.out.u8;
     if (chain == CH_FMA_DIV)
         return fast ? tma_launch_instance<Table, CH_FMA_DIV, false>(K, T, device, stream)
                     : tma_launch_instance<Table, CH_FMA_DIV, true>(K, T, device, stream);

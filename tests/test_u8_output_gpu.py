@@ -105,3 +105,35 @@ def test_packed_float_output_with_padded_rows(src_type, px, nc):
         util.assert_bit_equal(got.cpu().numpy(), want, f"src {src_type} {(W, H)} pitch {pitch_floats}")
         if pitch_floats > W * nc:
             assert (want[:, :, W * nc:] == -7.0).all()
+
+
+def test_u8_output_through_the_tma_kernel():
+    """CV_8UC3 -> CV_8UC3 with 16-byte aligned pitches is taken by the TMA-staged kernel (general instantiation): forced
+    variant 2 must accept it and agree with the oracle, for both casts, with padded rows, unused planes and AR bands."""
+    rng = np.random.default_rng(65)
+    w = util.workload_c2(seed=66, n=40, frame=(640, 480), pitch=1920)
+    lib = _abi.load()
+    d_img = torch.from_numpy(w.image).cuda()
+    prev = lib.cvgs_b200_set_kernel_variant(2)
+    try:
+        for (W, H), pitch, cast, aspect, ops in [((64, 128), 0, 0, _abi.IGNORE_AR, []), ((100, 60), 320, 0, _abi.PRESERVE_AR, util.OPS_C2),
+                                                 ((33, 7), 0, 1, _abi.IGNORE_AR, []), ((224, 224), 700, 0, _abi.PRESERVE_AR_LEFT,
+                                                                                     [("reorder", (2, 1, 0)), ("mul", (1.7, 1.0, -0.5)), ("sub", (40.0, -3.0, 0.25))])]:
+            rp = pitch or 3 * W
+            n = len(w.rects) + 2
+            want = np.full((n, H, rp), 7, dtype=np.uint8)
+            got = torch.full((n, H, rp), 7, dtype=torch.uint8, device="cuda")
+            kw = dict(aspect=aspect, background=(300.0, 12.6, -4.0), layout=_abi.OUT_NHWC, dst_type=_abi.CVGS_8UC3, row_pitch=pitch,
+                      u8_cast=cast)
+            if cast:
+                kw["background"] = (30.0, 12.6, 4.0)  # fk::Cast is defined for values inside [0, 256)
+            p = util.make_pipeline((W, H), ops, out_ptr=want.ctypes.data, **kw)
+            assert util.oracle_lib().oracle_preproc(util.host_crops(w.image, w.rects), n, len(w.rects), C.byref(p), 0) == 0
+            p = util.make_pipeline((W, H), ops, out_ptr=got.data_ptr(), **kw)
+            par = util.host_parents(w.image, w.width, w.height, len(w.rects), base_ptr=d_img.data_ptr())
+            _abi.check(lib.cvgs_b200_preproc_launch_ex(util.host_crops(w.image, w.rects, base_ptr=d_img.data_ptr()), par, n,
+                                                       len(w.rects), C.byref(p), None))
+            torch.cuda.synchronize()
+            assert np.array_equal(got.cpu().numpy(), want), f"{(W, H)} pitch {pitch} cast {cast}"
+    finally:
+        lib.cvgs_b200_set_kernel_variant(prev)
