@@ -101,7 +101,8 @@ static float round_sat_u16(float v) {
 static float round_sat_s16(float v) {
     if (v != v) return 0.0f;               /* cvt.rni.s32.f32 of NaN is 0 */
     const float r = nearbyintf(v);
-    return r > 32767.0f ? 32767.0f : (r < -32768.0f ? -32768.0f : r);
+    /* the value passes through a short: (-0.5, -0] comes back as +0, not as the -0 nearbyintf returns */
+    return (r > 32767.0f ? 32767.0f : (r < -32768.0f ? -32768.0f : r)) + 0.0f;
 }
 static float round_sat_src(float v, int src_type) {
     return (src_type == CVGS_16UC3 || src_type == CVGS_16UC4)   ? round_sat_u16(v)

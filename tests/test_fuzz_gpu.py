@@ -9,6 +9,9 @@ from cvgpuspeedup_b200 import _abi
 from tests import gpu_util, util
 
 pytestmark = pytest.mark.gpu
+# CVGS_FUZZ_EXTRA=n adds n more seeds to every fuzz test (one-off soak runs; the default suite stays short)
+import os
+_EXTRA = int(os.environ.get("CVGS_FUZZ_EXTRA", "0"))
 
 OPS_POOL = [
     [],
@@ -21,7 +24,7 @@ OPS_POOL = [
 ]
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(24 + _EXTRA))
 def test_random_geometry(seed):
     rng = np.random.default_rng(1000 + seed)
     fw, fh = int(rng.integers(40, 700)), int(rng.integers(30, 500))
@@ -86,7 +89,7 @@ def _random_chain(rng, nc):
 SRC_TYPES = [_abi.CVGS_8UC3, _abi.CVGS_16UC3, _abi.CVGS_16SC3, _abi.CVGS_8UC4, _abi.CVGS_16UC4, _abi.CVGS_16SC4]
 
 
-@pytest.mark.parametrize("seed", range(36))
+@pytest.mark.parametrize("seed", range(36 + _EXTRA))
 def test_random_source_types_chains_and_outputs(seed):
     """The forms outside the TMA kernel: every source depth / channel count, chains with the colour conversions,
     8-bit output, packed float output with padded rows -- against the oracle."""

@@ -244,3 +244,14 @@ def test_golden_vectors_from_reference_kernel():
                               background=tuple(float(v) for v in g["bg"]), n_planes=int(g["n_planes"]),
                               used=int(g["used"]), src_type=src_type)
         util.assert_bit_equal(got, g["out"], os.path.basename(f))
+
+
+def test_round_to_source_depth_of_small_negative_values_is_plus_zero():
+    """CVGS_INTERP_ROUND_U8 on CV_16SC3: the interpolated value passes through a short, so (-0.5, -0] comes back as +0
+    (found by the fuzz soak: the oracle used to return the -0 of nearbyintf)."""
+    img = np.zeros((2, 16), dtype=np.int16)
+    img[0, :3] = -1          # pixel (0, 0) = -1, pixel (1, 0) = 0: a 2x up-scale interpolates -0.5 and -0.25... in between
+    crops_img = img.view(np.uint8)
+    out = util.run_oracle(crops_img, [(0, 0, 2, 2)], (8, 8), [], src_type=_abi.CVGS_16SC3, interp_mode=_abi.INTERP_ROUND_U8)
+    assert not np.signbit(out[out == 0]).any()
+    assert (out[0, :, 0, 0] == -1).all() and (out == 0).any()
