@@ -81,6 +81,7 @@ class _Resize:
     dsize: Tuple[int, int]  # (width, height) like cv::Size
     used: int
     background: Tuple[float, float, float]
+    src_type: int = _abi.CVGS_8UC3
     aspect: int
     src_type: int = _abi.CVGS_8UC3
     yuv_standard: int = 0
@@ -112,6 +113,7 @@ class _Warp:
     dsize: Tuple[int, int]
     used: int
     background: Tuple[float, float, float]
+    src_type: int = _abi.CVGS_8UC3
 
 
 def resize(crops: Sequence[GpuMat], dsize: Tuple[int, int], usedPlanes: Optional[int] = None,
@@ -166,7 +168,7 @@ def invert_warp_matrix(m, warp_type: int):
 
 
 def warp(images, matrices, dsize: Tuple[int, int], warp_type: int = WARP_AFFINE, usedPlanes: Optional[int] = None,
-         backgroundValue=(0.0, 0.0, 0.0)) -> _Warp:
+         backgroundValue=(0.0, 0.0, 0.0), src_type: int = _abi.CVGS_8UC3) -> _Warp:
     """cvGS::warp<WT, CV_8UC3[, N]>(GpuMat / array<GpuMat, N>, Mat / array<Mat, N>, Size[, usedPlanes, default])
     (reference include/cvGPUSpeedup.cuh:285-442): `matrices` are the forward transforms cv::warpAffine /
     cv::warpPerspective take; they are inverted here like the wrapper does."""
@@ -177,7 +179,7 @@ def warp(images, matrices, dsize: Tuple[int, int], warp_type: int = WARP_AFFINE,
     if len(inv) != len(images):
         raise CvgsError("one matrix per image is required")
     return _Warp(images, [(int(warp_type), v) for v in inv], (int(dsize[0]), int(dsize[1])),
-                 len(images) if usedPlanes is None else int(usedPlanes), _scalar3(backgroundValue))
+                 len(images) if usedPlanes is None else int(usedPlanes), _scalar3(backgroundValue), int(src_type))
 
 
 def multiply(s) -> _Op:   # cvGS::multiply<CV_32FC3>(Scalar) :131
@@ -321,7 +323,7 @@ def executeOperations(stream, *iops, fp_contract: int = FP_REFERENCE_FUSED, inte
     lib = _abi.load()
     if isinstance(rs, _Warp):
         p = build_pipeline(rs.dsize, mid, rs.background, IGNORE_AR, fp_contract, INTERP_FLOAT, wr.out_ptr, wr.layout,
-                           wr.plane_stride)
+                           wr.plane_stride, rs.src_type)
         p.dst_type, p.out_row_pitch, p.u8_cast = wr.dst_type, wr.row_pitch, wr.u8_cast
         images = make_crops(rs.images[:rs.used])
         warps = (_abi.Warp * max(1, rs.used))()

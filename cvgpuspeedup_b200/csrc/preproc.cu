@@ -685,7 +685,7 @@ int cvgs_b200_preproc_launch_ex(const cvgs_crop_t* crops, const cvgs_parent_t* p
 static int warp_launch_impl(const cvgs_crop_t* images, const cvgs_warp_t* warps, int n_planes, int used,
                             const cvgs_pipeline_t* pipe, cudaStream_t stream) {
     if (int rc = validate_pipeline(pipe)) return rc;
-    if (pipe->src_type != CVGS_8UC3) return fail(CVGS_ERR_NOT_SUPPORTED, "warp takes CV_8UC3 sources");
+    if (CVGS_IS_YUV(pipe->src_type)) return fail(CVGS_ERR_NOT_SUPPORTED, "warp takes CV_8U / CV_16U / CV_16S sources with 3 or 4 channels");
     if (!pipe->out) return fail(CVGS_ERR_INVALID_VALUE, "output pointer is NULL");
     if (n_planes <= 0) return fail(CVGS_ERR_INVALID_VALUE, "n_planes must be positive");
     if (used < 0) return fail(CVGS_ERR_INVALID_VALUE, "used must be non-negative");
@@ -714,15 +714,16 @@ static int warp_launch_impl(const cvgs_crop_t* images, const cvgs_warp_t* warps,
         if (r.pending[slot]) { CVGS_CUDA(cudaEventSynchronize(r.ev[slot])); r.pending[slot] = false; }
         const cvgs_plane_t* hp = static_cast<const cvgs_plane_t*>(pipe->out);
         DevPlane* dp = r.planes_h(slot);
+        const int nc = P.nc;
         for (int z = 0; z < n_planes; ++z)
-            for (int c = 0; c < 3; ++c) {
-                const cvgs_plane_t& pl = hp[z * 3 + P.prog.dst_chan[c]];
+            for (int c = 0; c < nc; ++c) {
+                const cvgs_plane_t& pl = hp[z * nc + P.prog.dst_chan[c]];
                 if (!pl.data || pl.pitch_bytes < 4LL * P.W || (pl.pitch_bytes & 3))
                     return fail(CVGS_ERR_INVALID_VALUE, "plane " + std::to_string(z) + ": bad destination image");
-                dp[z * 3 + c].data = static_cast<float*>(pl.data);
-                dp[z * 3 + c].pitch = pl.pitch_bytes / 4;
+                dp[z * nc + c].data = static_cast<float*>(pl.data);
+                dp[z * nc + c].pitch = pl.pitch_bytes / 4;
             }
-        CVGS_CUDA(cudaMemcpyAsync(r.planes_d(slot), dp, static_cast<size_t>(n_planes) * 3 * sizeof(DevPlane),
+        CVGS_CUDA(cudaMemcpyAsync(r.planes_d(slot), dp, static_cast<size_t>(n_planes) * nc * sizeof(DevPlane),
                                   cudaMemcpyHostToDevice, stream));
         P.out.planes = r.planes_d(slot);
         CVGS_CUDA(cudaEventRecord(r.ev[slot], stream));  // re-recorded after the kernels below
@@ -745,7 +746,14 @@ static int warp_launch_impl(const cvgs_crop_t* images, const cvgs_warp_t* warps,
         }
         // four pixels per thread measured best from 640x640 planes up and within 10% below (1, 2 and 4 tried on B200)
         const dim3 grid((P.W + 127) / 128, (P.H + 7) / 8, nz);
-        preproc_warp_kernel<4><<<grid, block, 0, stream>>>(P, T, z0);
+        switch (pipe->src_type) {
+            case CVGS_8UC3: preproc_warp_kernel<4, unsigned char, 3><<<grid, block, 0, stream>>>(P, T, z0); break;
+            case CVGS_8UC4: preproc_warp_kernel<4, unsigned char, 4><<<grid, block, 0, stream>>>(P, T, z0); break;
+            case CVGS_16UC3: preproc_warp_kernel<4, unsigned short, 3><<<grid, block, 0, stream>>>(P, T, z0); break;
+            case CVGS_16UC4: preproc_warp_kernel<4, unsigned short, 4><<<grid, block, 0, stream>>>(P, T, z0); break;
+            case CVGS_16SC3: preproc_warp_kernel<4, short, 3><<<grid, block, 0, stream>>>(P, T, z0); break;
+            default: preproc_warp_kernel<4, short, 4><<<grid, block, 0, stream>>>(P, T, z0); break;
+        }
         CVGS_CUDA(cudaGetLastError());
         ++t_launch_count;
     }

@@ -29,7 +29,9 @@ struct WarpTable {
     DevWarp w[kWarpParamPlanes];
 };
 
-__device__ __forceinline__ void warp_one_pixel(const DevWarp& d, int x, int y, float (&out)[3]) {
+// T = unsigned char / unsigned short / short, NC = 3 / 4: the pixel types cvGS::warp<WT, InputType> is instantiated with
+template <typename T, int NC>
+__device__ __forceinline__ void warp_one_pixel(const DevWarp& d, int x, int y, float (&out)[NC]) {
     const float fx = static_cast<float>(x), fy = static_cast<float>(y);
     float sx = __fadd_rn(__fmaf_rn(d.m[0], fx, __fmul_rn(d.m[1], fy)), d.m[2]);
     float sy = __fadd_rn(__fmaf_rn(d.m[3], fx, __fmul_rn(d.m[4], fy)), d.m[5]);
@@ -39,7 +41,8 @@ __device__ __forceinline__ void warp_one_pixel(const DevWarp& d, int x, int y, f
         sy = __fmul_rn(coeff, sy);
     }
     if (!(sx >= 0.f && sx < static_cast<float>(d.w) && sy >= 0.f && sy < static_cast<float>(d.h))) {
-        out[0] = out[1] = out[2] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) out[c] = 0.f;
         return;
     }
     const int x1 = __float2int_rd(sx), y1 = __float2int_rd(sy);
@@ -49,14 +52,14 @@ __device__ __forceinline__ void warp_one_pixel(const DevWarp& d, int x, int y, f
     const float wy1 = __fsub_rn(sy, static_cast<float>(y1)), wy0 = __fsub_rn(static_cast<float>(y2), sy);
     const float w00 = __fmul_rn(wx0, wy0), w10 = __fmul_rn(wx1, wy0);
     const float w01 = __fmul_rn(wx0, wy1), w11 = __fmul_rn(wx1, wy1);
-    const uint8_t* r0 = d.data + static_cast<long long>(y1) * d.pitch;
-    const uint8_t* r1 = d.data + static_cast<long long>(y2r) * d.pitch;
-    const uint8_t* p00 = r0 + 3 * x1;
-    const uint8_t* p10 = r0 + 3 * x2r;
-    const uint8_t* p01 = r1 + 3 * x1;
-    const uint8_t* p11 = r1 + 3 * x2r;
+    const T* r0 = reinterpret_cast<const T*>(d.data + static_cast<long long>(y1) * d.pitch);
+    const T* r1 = reinterpret_cast<const T*>(d.data + static_cast<long long>(y2r) * d.pitch);
+    const T* p00 = r0 + NC * x1;
+    const T* p10 = r0 + NC * x2r;
+    const T* p01 = r1 + NC * x1;
+    const T* p11 = r1 + NC * x2r;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < NC; ++c) {
         float t = __fmul_rn(static_cast<float>(__ldg(p10 + c)), w10);
         t = __fmaf_rn(static_cast<float>(__ldg(p00 + c)), w00, t);
         t = __fmaf_rn(static_cast<float>(__ldg(p01 + c)), w01, t);
@@ -67,34 +70,35 @@ __device__ __forceinline__ void warp_one_pixel(const DevWarp& d, int x, int y, f
 
 // grid (ceil(W / (32 * PX)), ceil(H / 8), planes of this chunk); block 256 = 32 lanes x 8 rows; a thread produces PX
 // x-adjacent pixels (PX = 4: 16-byte planar stores; PX = 1: most threads in flight, the stores of a warp still coalesce)
-template <int PX>
+template <int PX, typename T = unsigned char, int NC = 3>
 __global__ void __launch_bounds__(256)
-preproc_warp_kernel(const __grid_constant__ PreprocParams P, const __grid_constant__ WarpTable T, int z0) {
+preproc_warp_kernel(const __grid_constant__ PreprocParams P, const __grid_constant__ WarpTable Tb, int z0) {
     const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * PX;
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int zl = blockIdx.z;
     const int z = z0 + zl;
     if (x0 >= P.W || y >= P.H) return;
     const int nvalid = min(PX, P.W - x0);
-    float v[PX][3];
+    float v[PX][NC];
     if (z < P.used) {
-        const DevWarp& d = T.w[zl];
+        const DevWarp& d = Tb.w[zl];
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
             if (p < nvalid) {
-                warp_one_pixel(d, x0 + p, y, v[p]);
+                warp_one_pixel<T, NC>(d, x0 + p, y, v[p]);
             } else {
-                v[p][0] = v[p][1] = v[p][2] = 0.f;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) v[p][c] = 0.f;
             }
         }
     } else {
 #pragma unroll
         for (int p = 0; p < PX; ++p)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[p][c] = P.bg[c];
+            for (int c = 0; c < NC; ++c) v[p][c] = P.bg[c];
     }
-    apply_program<PX, 3>(P.prog, v);
-    store_pixels<PX, 3>(P, z, y, x0, nvalid, v);
+    apply_program<PX, NC>(P.prog, v);
+    store_pixels<PX, NC>(P, z, y, x0, nvalid, v);
 }
 
 }  // namespace cvgs

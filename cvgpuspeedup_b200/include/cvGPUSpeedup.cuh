@@ -70,7 +70,7 @@ struct ChainOp {  // multiply / subtract / divide / add / cvtColor / convertTo p
 struct WarpBatch {  // cvGS::warp(...) result
     std::vector<cvgs_crop_t> images;
     std::vector<cvgs_warp_t> warps;
-    int n_planes = 0, used = 0, dst_w = 0, dst_h = 0;
+    int n_planes = 0, used = 0, dst_w = 0, dst_h = 0, src_type = CVGS_8UC3;
     float bg[4] = {0, 0, 0, 0};
 };
 struct WriteOp {  // split / splitT / write
@@ -414,12 +414,15 @@ inline cvgs_warp_t inverse_of(const cv::Mat& m) {
 }  // namespace detail
 template <fk::WarpType WT, int InputType = CV_8UC3>
 inline detail::WarpBatch warp(const cv::cuda::GpuMat& input, const cv::Mat& transform_matrix, const cv::Size& dstSize) {
-    static_assert(InputType == CV_8UC3, "cvGS (B200 build): warp takes CV_8UC3 images");
+    static_assert((CV_MAT_DEPTH(InputType) == CV_8U || CV_MAT_DEPTH(InputType) == CV_16U || CV_MAT_DEPTH(InputType) == CV_16S) &&
+                      (CV_MAT_CN(InputType) == 3 || CV_MAT_CN(InputType) == 4),
+                  "cvGS (B200 build): warp takes CV_8U / CV_16U / CV_16S images with 3 or 4 channels");
     if (InputType != input.type()) throw std::runtime_error("Input type does not match the input type of the operation.");
     detail::WarpBatch b;
     b.images.push_back(detail::crop_of(input));
     b.warps.push_back(detail::inverse_of<WT>(transform_matrix));
     b.n_planes = b.used = 1;
+    b.src_type = InputType;  // CV type codes and CVGS_* source codes coincide
     b.dst_w = dstSize.width;
     b.dst_h = dstSize.height;
     return b;
@@ -427,9 +430,12 @@ inline detail::WarpBatch warp(const cv::cuda::GpuMat& input, const cv::Mat& tran
 template <fk::WarpType WT, int InputType, size_t BATCH>
 inline detail::WarpBatch warp(const std::array<cv::cuda::GpuMat, BATCH>& inputs, const std::array<cv::Mat, BATCH>& transform_matrices,
                               const std::array<cv::Size, BATCH>& dstSize, const int& usedPlanes, const cv::Scalar& defaultValue) {
-    static_assert(InputType == CV_8UC3, "cvGS (B200 build): warp takes CV_8UC3 images");
+    static_assert((CV_MAT_DEPTH(InputType) == CV_8U || CV_MAT_DEPTH(InputType) == CV_16U || CV_MAT_DEPTH(InputType) == CV_16S) &&
+                      (CV_MAT_CN(InputType) == 3 || CV_MAT_CN(InputType) == 4),
+                  "cvGS (B200 build): warp takes CV_8U / CV_16U / CV_16S images with 3 or 4 channels");
     detail::WarpBatch b;
     b.n_planes = static_cast<int>(BATCH);
+    b.src_type = InputType;
     b.used = usedPlanes;
     for (int i = 0; i < usedPlanes && i < static_cast<int>(BATCH); ++i) {
         if (InputType != inputs[i].type()) throw std::runtime_error("Input type does not match the input type of the operation.");
@@ -465,7 +471,7 @@ inline detail::WarpBatch warp(const std::array<cv::cuda::GpuMat, BATCH>& inputs,
 template <typename... IOpTypes>
 inline void executeOperations(const cv::cuda::Stream& stream, const detail::WarpBatch& read, const IOpTypes&... iops) {
     cvgs_pipeline_t p{};
-    p.src_type = CVGS_8UC3;
+    p.src_type = read.src_type;
     p.dst_width = read.dst_w;
     p.dst_height = read.dst_h;
     p.aspect_mode = CVGS_IGNORE_AR;

@@ -239,7 +239,7 @@ int cvgs_b200_preproc_launch_ex(const cvgs_crop_t* crops, const cvgs_parent_t* p
 
 /* ------------------------------------------------------------------------------------------
  * Batched affine / perspective warp in front of the same chain.  Replaces
- *   cvGS::executeOperations(stream, cvGS::warp<WT, CV_8UC3[, N]>(images, matrices, dstSize[, used, default]), ops..., write)
+ *   cvGS::executeOperations(stream, cvGS::warp<WT, InputType[, N]>(images, matrices, dstSize[, used, default]), ops..., write)
  * (reference include/cvGPUSpeedup.cuh:285-442 -> fk::Warping<WT, PerThreadRead> fkl/.../image_processing/warping.cuh:
  * 43-91, which shares fk::Interpolate<INTER_LINEAR> with the resize).  For plane z and destination pixel (x, y):
  *   affine       sx = (m00*x + m01*y) + m02,  sy = (m10*x + m11*y) + m12
@@ -247,7 +247,7 @@ int cvgs_b200_preproc_launch_ex(const cvgs_crop_t* crops, const cvgs_parent_t* p
  * with m the INVERSE transform (destination -> source; the cvGS wrapper inverts the user's matrix on the host and
  * casts it to float); inside [0, w) x [0, h) the pixel is the bilinear interpolation at (sx, sy), outside it is 0;
  * the op chain and the output forms are those of the resize pipeline (pipeline->aspect_mode is ignored).
- * CV_8UC3 sources, direct-gather kernel.
+ * Sources: CV_8U / CV_16U / CV_16S with 3 or 4 channels (pipeline->src_type); gather kernel.
  * ------------------------------------------------------------------------------------------ */
 enum cvgs_warp_type { CVGS_WARP_AFFINE = 0, CVGS_WARP_PERSPECTIVE = 1 };
 typedef struct cvgs_warp {

@@ -223,7 +223,8 @@ static void resize_pixel(const cvgs_crop_t* c, const oracle_geom_t* g, int aspec
  * bounds test (:78-82) and Interpolate<INTER_LINEAR> at the warped coordinate (interpolation.cuh:57-92).  Rounding
  * sequence of the reference's SASS: FMUL(m01*y), FFMA(m00, x, .), FADD(m02) per row; perspective multiplies by the
  * correctly rounded reciprocal of the third row. */
-static void warp_pixel(const cvgs_crop_t* c, const cvgs_warp_t* wp, int x, int y, float out[3]) {
+static void warp_pixel(const cvgs_crop_t* c, const cvgs_warp_t* wp, int src_type, int x, int y, float out[4]) {
+    const int nc = n_channels(src_type);
     const float fx = (float)x, fy = (float)y;
     const float* m = wp->m;
     float sx = fmaf(m[0], fx, m[1] * fy) + m[2];
@@ -234,7 +235,7 @@ static void warp_pixel(const cvgs_crop_t* c, const cvgs_warp_t* wp, int x, int y
         sy = coeff * sy;
     }
     if (!(sx >= 0.f && sx < (float)c->width && sy >= 0.f && sy < (float)c->height)) {
-        out[0] = out[1] = out[2] = 0.f;
+        out[0] = out[1] = out[2] = out[3] = 0.f;
         return;
     }
     const int x1 = (int)floorf(sx), y1 = (int)floorf(sy);
@@ -246,11 +247,11 @@ static void warp_pixel(const cvgs_crop_t* c, const cvgs_warp_t* wp, int x, int y
     const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
     const uint8_t* r0 = (const uint8_t*)c->data + (size_t)y1 * (size_t)c->pitch;
     const uint8_t* r1 = (const uint8_t*)c->data + (size_t)y2r * (size_t)c->pitch;
-    for (int ch = 0; ch < 3; ++ch) {
-        float t = (float)r0[3 * x2r + ch] * w10;
-        t = fmaf((float)r0[3 * x1 + ch], w00, t);
-        t = fmaf((float)r1[3 * x1 + ch], w01, t);
-        t = fmaf((float)r1[3 * x2r + ch], w11, t);
+    for (int ch = 0; ch < nc; ++ch) {
+        float t = src_px(r0, x2r, ch, src_type) * w10;
+        t = fmaf(src_px(r0, x1, ch, src_type), w00, t);
+        t = fmaf(src_px(r1, x1, ch, src_type), w01, t);
+        t = fmaf(src_px(r1, x2r, ch, src_type), w11, t);
         out[ch] = t;
     }
 }
@@ -439,7 +440,7 @@ int oracle_preproc(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_
 /* Batched warp + chain + write: BatchRead<N, CONDITIONAL_WITH_DEFAULT> of Warping ops (cvGPUSpeedup.cuh:285-442). */
 int oracle_warp(const cvgs_crop_t* images, const cvgs_warp_t* warps, int n_planes, int used, const cvgs_pipeline_t* p,
                 int nthreads) {
-    if (!images || !warps || !p || !p->out || n_planes <= 0 || used < 0 || p->src_type != CVGS_8UC3 || p->dst_width <= 0 ||
+    if (!images || !warps || !p || !p->out || n_planes <= 0 || used < 0 || CVGS_IS_YUV(p->src_type) || p->dst_width <= 0 ||
         p->dst_height <= 0 || p->n_ops < 0 || p->n_ops > CVGS_MAX_OPS)
         return 1;
     if (used > n_planes) used = n_planes;
@@ -454,9 +455,9 @@ int oracle_warp(const cvgs_crop_t* images, const cvgs_warp_t* warps, int n_plane
         for (int x = 0; x < W; ++x) {
             float v[4];
             if (z >= used) {
-                v[0] = p->background[0]; v[1] = p->background[1]; v[2] = p->background[2]; v[3] = 0.f;
+                v[0] = p->background[0]; v[1] = p->background[1]; v[2] = p->background[2]; v[3] = p->background[3];
             } else {
-                warp_pixel(&images[z], &warps[z], x, y, v);
+                warp_pixel(&images[z], &warps[z], p->src_type, x, y, v);
             }
             apply_chain(p, v);
             store_pixel(p, n_planes, z, y, x, v);

@@ -282,6 +282,26 @@ int FKREF_CAT(fkref_yuv_, FKREF_BATCH)(int format, int standard, const void* dat
 #include <fused_kernel/algorithms/image_processing/warping.cuh>
 #include <fused_kernel/algorithms/basic_ops/cast.cuh>
 namespace {
+// Other pixel types of cvGS::warp<WT, InputType>: warp -> Mul -> TensorSplit into float out[C][dst_h][dst_w].
+template <fk::WarpType WT, typename PixelT>
+int run_warp_typed(const void* data, int w, int h, int pitch, const float* m, int dst_w, int dst_h, const float* mul,
+                   float* out, cudaStream_t stream) {
+    const auto read = fk::PerThreadRead<fk::_2D, PixelT>::build(
+        fk::RawPtr<fk::_2D, PixelT>{ (PixelT*)data, { (uint)w, (uint)h, (uint)pitch } });
+    fk::WarpingParameters<WT> params{};
+    for (int r = 0; r < (WT == fk::Affine ? 2 : 3); ++r)
+        for (int c = 0; c < 3; ++c) params.transformMatrix.data[r][c] = m[3 * r + c];
+    params.dstSize = fk::Size(dst_w, dst_h);
+    const auto warp = fk::Warping<WT, std::decay_t<decltype(read)>>::build({ params, read });
+    constexpr int CN = fk::cn<PixelT>;
+    using F = fk::VectorType_t<float, CN>;
+    F mv;
+    mv.x = mul[0]; mv.y = mul[1]; mv.z = mul[2];
+    if constexpr (CN == 4) mv.w = mul[3];
+    const fk::Tensor<float> t_out(out, dst_w, dst_h, 1, CN);
+    fk::executeOperations(stream, warp, fk::Binary<fk::Mul<F>>{ mv }, fk::Write<fk::TensorSplit<F>>{ t_out.ptr() });
+    return 0;
+}
 template <fk::WarpType WT>
 int run_warp(int mode, const void* data, int w, int h, int pitch, const float* m, int dst_w, int dst_h, const float* mul,
              void* out, int out_pitch, cudaStream_t stream) {
@@ -311,6 +331,27 @@ int FKREF_CAT(fkref_warp_, FKREF_BATCH)(int type, int mode, const void* data, in
         cudaStream_t s = (cudaStream_t)stream;
         if (type == 0) return run_warp<fk::Affine>(mode, data, w, h, pitch, m, dst_w, dst_h, mul, out, out_pitch, s);
         return run_warp<fk::Perspective>(mode, data, w, h, pitch, m, dst_w, dst_h, mul, out, out_pitch, s);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+// src_type: the CV type code (24 CV_8UC4, 18 CV_16UC3, 27 CV_16SC4); perspective (type 1) and affine (type 0)
+int FKREF_CAT(fkref_warp_typed_, FKREF_BATCH)(int type, int src_type, const void* data, int w, int h, int pitch, const float* m,
+                                              int dst_w, int dst_h, const float* mul, float* out, void* stream) {
+    try {
+        cudaStream_t s = (cudaStream_t)stream;
+#define FKREF_WARP_CASE(CODE, PIX)                                                                                          \
+    case CODE:                                                                                                              \
+        return type == 0 ? run_warp_typed<fk::Affine, PIX>(data, w, h, pitch, m, dst_w, dst_h, mul, out, s)                 \
+                         : run_warp_typed<fk::Perspective, PIX>(data, w, h, pitch, m, dst_w, dst_h, mul, out, s);
+        switch (src_type) {
+            FKREF_WARP_CASE(24, uchar4)
+            FKREF_WARP_CASE(18, ushort3)
+            FKREF_WARP_CASE(27, short4)
+            default: g_err = "fkref: warp pixel type not instantiated"; return -1;
+        }
+#undef FKREF_WARP_CASE
     } catch (const std::exception& e) {
         g_err = e.what();
         return -1;

@@ -246,3 +246,22 @@ def run_fkref_yuv(fmt, frame, width, height, dsize, standard, mul, sub, div, d_f
     assert rc == 0
     torch.cuda.synchronize()
     return out.cpu().numpy()
+
+
+def run_fkref_warp_typed(image, width, height, src_type, warp_type, inverse, dsize, mul, d_image=None):
+    """fk::Warping on a CV_8UC4 / CV_16UC3 / CV_16SC4 image -> Mul -> TensorSplit (oracle/_ref/libfkref_16.so)."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libfkref_16.so")
+    lib = C.CDLL(path)
+    fn = lib.fkref_warp_typed_16
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int,
+                   C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+    d = device_image(image) if d_image is None else d_image
+    nc = util.channels_of(src_type)
+    out = torch.full((nc, dsize[1], dsize[0]), float("nan"), dtype=torch.float32, device="cuda")
+    m = (C.c_float * 9)(*[float(v) for v in inverse])
+    rc = fn(warp_type, src_type, d.data_ptr(), width, height, image.shape[1], m, dsize[0], dsize[1],
+            (C.c_float * 4)(*(tuple(mul) + (0.0,) * 4)[:4]), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return out.cpu().numpy()

@@ -48,7 +48,7 @@ def _matrices(rng, n, warp_type, w, h):
 
 
 def _launch(d_imgs, sizes, pitch, inverses, warp_type, dsize, ops, n_planes=None, used=None, background=(0, 0, 0),
-            layout=_abi.OUT_NCHW, u8=None):
+            layout=_abi.OUT_NCHW, u8=None, src_type=_abi.CVGS_8UC3):
     lib = _abi.load()
     n = len(d_imgs)
     n_planes = n if n_planes is None else n_planes
@@ -61,8 +61,8 @@ def _launch(d_imgs, sizes, pitch, inverses, warp_type, dsize, ops, n_planes=None
         for k in range(9):
             warps[i].m[k] = float(inverses[i][k])
     if u8 is None:
-        out = torch.full(util.out_shape(n_planes, dsize, layout), float("nan"), device="cuda")
-        p = util.make_pipeline(dsize, ops, out_ptr=out.data_ptr(), layout=layout, background=background)
+        out = torch.full(util.out_shape(n_planes, dsize, layout, 0, util.channels_of(src_type)), float("nan"), device="cuda")
+        p = util.make_pipeline(dsize, ops, out_ptr=out.data_ptr(), layout=layout, background=background, src_type=src_type)
     else:
         out = torch.full((n_planes, dsize[1], dsize[0], 3), 99, dtype=torch.uint8, device="cuda")
         p = util.make_pipeline(dsize, ops, out_ptr=out.data_ptr(), layout=_abi.OUT_NHWC, background=background,
@@ -73,7 +73,7 @@ def _launch(d_imgs, sizes, pitch, inverses, warp_type, dsize, ops, n_planes=None
 
 
 def _oracle(imgs, sizes, pitch, inverses, warp_type, dsize, ops, n_planes=None, used=None, background=(0, 0, 0),
-            layout=_abi.OUT_NCHW, u8=None):
+            layout=_abi.OUT_NCHW, u8=None, src_type=_abi.CVGS_8UC3):
     n = len(imgs)
     n_planes = n if n_planes is None else n_planes
     used = n if used is None else used
@@ -85,8 +85,8 @@ def _oracle(imgs, sizes, pitch, inverses, warp_type, dsize, ops, n_planes=None, 
         for k in range(9):
             warps[i].m[k] = float(inverses[i][k])
     if u8 is None:
-        out = np.full(util.out_shape(n_planes, dsize, layout), np.nan, dtype=np.float32)
-        p = util.make_pipeline(dsize, ops, out_ptr=out.ctypes.data, layout=layout, background=background)
+        out = np.full(util.out_shape(n_planes, dsize, layout, 0, util.channels_of(src_type)), np.nan, dtype=np.float32)
+        p = util.make_pipeline(dsize, ops, out_ptr=out.ctypes.data, layout=layout, background=background, src_type=src_type)
     else:
         out = np.full((n_planes, dsize[1], dsize[0], 3), 99, dtype=np.uint8)
         p = util.make_pipeline(dsize, ops, out_ptr=out.ctypes.data, layout=_abi.OUT_NHWC, background=background,
@@ -224,8 +224,8 @@ def test_warp_rejects_bad_input():
     assert lib.cvgs_b200_warp_launch(crops, warps, 1, 1, C.byref(p), None) != 0
     assert b"bad type" in lib.cvgs_b200_last_error()
     warps[0].type = 0
-    p16 = util.make_pipeline((8, 8), [], out_ptr=out.data_ptr(), src_type=_abi.CVGS_16UC3)
-    assert lib.cvgs_b200_warp_launch(crops, warps, 1, 1, C.byref(p16), None) != 0
+    pnv = util.make_pipeline((8, 8), [], out_ptr=out.data_ptr(), src_type=_abi.CVGS_NV12)
+    assert lib.cvgs_b200_warp_launch(crops, warps, 1, 1, C.byref(pnv), None) != 0
     assert lib.cvgs_b200_warp_launch(None, warps, 1, 1, C.byref(p), None) != 0
 
 
@@ -258,3 +258,46 @@ def test_wild_matrices_against_oracle(seed):
     ours = _launch([d] * n, [(w, h)] * n, pitch, inverses, warp_type, dsize, ops)
     orc = _oracle([img] * n, [(w, h)] * n, pitch, inverses, warp_type, dsize, ops)
     util.assert_bit_equal(ours, orc, f"seed {seed} type {warp_type} image {w}x{h} dsize {dsize}")
+
+
+TYPED = [_abi.CVGS_8UC4, _abi.CVGS_16UC3, _abi.CVGS_16SC4]
+
+
+@pytest.mark.parametrize("warp_type", [cvgs.WARP_AFFINE, cvgs.WARP_PERSPECTIVE])
+@pytest.mark.parametrize("src_type", TYPED)
+def test_other_pixel_types_match_reference_kernel_and_oracle(src_type, warp_type):
+    """cvGS::warp<WT, InputType> for the other pixel types of the chain (reference include/cvGPUSpeedup.cuh:285-307)."""
+    if gpu_util.fkref_lib(16) is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(40 + src_type + warp_type)
+    w, h = 211, 157
+    px, nc = util.px_bytes_of(src_type), util.channels_of(src_type)
+    pitch = px * w + 24
+    img = rng.integers(0, 256, size=(h, pitch), dtype=np.uint8)
+    d = gpu_util.device_image(img)
+    mul = (0.5, 1.25, 1 / 255.0, 2.0)[:nc]
+    for m in _matrices(rng, 3, warp_type, w, h):
+        inv = cvgs.api.invert_warp_matrix(m, warp_type)
+        dsize = (int(rng.integers(8, 300)), int(rng.integers(8, 200)))
+        ref = gpu_util.run_fkref_warp_typed(img, w, h, src_type, warp_type, inv, dsize, mul, d_image=d)
+        ours = _launch([d], [(w, h)], pitch, [inv], warp_type, dsize, [("mul", mul)], src_type=src_type)[0]
+        orc = _oracle([img], [(w, h)], pitch, [inv], warp_type, dsize, [("mul", mul)], src_type=src_type)[0]
+        util.assert_bit_equal(ours, ref, f"src {src_type} type {warp_type} dsize {dsize}: ours vs reference kernel")
+        util.assert_bit_equal(orc, ref, f"src {src_type} type {warp_type} dsize {dsize}: oracle vs reference kernel")
+
+
+@pytest.mark.parametrize("src_type", [_abi.CVGS_16SC3, _abi.CVGS_16UC4, _abi.CVGS_8UC4])
+def test_other_pixel_types_batches_and_layouts(src_type):
+    rng = np.random.default_rng(60 + src_type)
+    px, nc = util.px_bytes_of(src_type), util.channels_of(src_type)
+    pitch = 1024
+    sizes = [(int(rng.integers(8, 120)), int(rng.integers(8, 100))) for _ in range(50)]
+    imgs = [rng.integers(0, 256, size=(hh, pitch), dtype=np.uint8) for (_, hh) in sizes]
+    d = [gpu_util.device_image(im) for im in imgs]
+    inverses = [cvgs.api.invert_warp_matrix(m, cvgs.WARP_PERSPECTIVE) for (w, h) in sizes for m in _matrices(rng, 1, cvgs.WARP_PERSPECTIVE, w, h)]
+    ops = [("mul", (0.3, 0.5, 2.0, 1.5)[:nc]), ("sub", (1.0, 4.0, 3.2, 0.5)[:nc]), ("div", (3.2, 0.6, 11.8, 2.0)[:nc])]
+    for layout in (_abi.OUT_NCHW, _abi.OUT_NHWC, _abi.OUT_CNHW):
+        kw = dict(n_planes=53, used=50, background=(3.0, 5.0, 7.0, 9.0)[:nc], layout=layout, src_type=src_type)
+        ours = _launch(d, sizes, pitch, inverses, cvgs.WARP_PERSPECTIVE, (45, 31), ops, **kw)
+        orc = _oracle(imgs, sizes, pitch, inverses, cvgs.WARP_PERSPECTIVE, (45, 31), ops, **kw)
+        util.assert_bit_equal(ours, orc, f"src {src_type} layout {layout}")
