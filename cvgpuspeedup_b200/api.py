@@ -81,7 +81,6 @@ class _Resize:
     dsize: Tuple[int, int]  # (width, height) like cv::Size
     used: int
     background: Tuple[float, float, float]
-    src_type: int = _abi.CVGS_8UC3
     aspect: int
     src_type: int = _abi.CVGS_8UC3
     yuv_standard: int = 0
