@@ -615,6 +615,26 @@ int64_t cvgs_b200_launch_count(void) { return t_launch_count; }
 // Diagnostics for the CPU test-suite: the launch plan of the TMA kernel for a batch geometry (no device needed).
 // out[0..11] = {ok, NPB, HP, tiles_x, total_items, slot_bytes, slots, resident, grid, max row bytes needed,
 //               items covered by the per-warp ranges, 1 if the ranges tile [0, total_items) in order without gaps}
+int cvgs_b200_debug_program(const cvgs_pipeline_t* pipeline, float* out80) {
+    if (!pipeline || !out80) return fail(CVGS_ERR_INVALID_VALUE, "NULL argument");
+    if (int rc = validate_pipeline(pipeline)) return rc;
+    DevProgram prog;
+    if (int rc = build_program(*pipeline, prog)) return rc;
+    for (int i = 0; i < 80; ++i) out80[i] = 0.f;
+    out80[0] = static_cast<float>(prog.n_ops);
+    out80[1] = static_cast<float>(prog.nc_out);
+    out80[2] = static_cast<float>(prog.nregs);
+    out80[3] = static_cast<float>(prog.special);
+    for (int r = 0; r < 4; ++r) out80[4 + r] = static_cast<float>(prog.dst_chan[r]);
+    for (int i = 0; i < prog.n_ops && i < 8; ++i) {
+        out80[8 + 9 * i] = static_cast<float>(prog.ops[i].kind);
+        for (int c = 0; c < 4; ++c) {
+            out80[8 + 9 * i + 1 + c] = prog.ops[i].a[c];
+            out80[8 + 9 * i + 5 + c] = prog.ops[i].b[c];
+        }
+    }
+    return CVGS_OK;
+}
 int cvgs_b200_debug_plan(const cvgs_crop_t* crops, int32_t n_planes, int32_t used, const cvgs_pipeline_t* pipeline,
                          int32_t sm_count, int32_t image_mode, int32_t items_per_warp_, int64_t* out12) {
     if (!pipeline || !out12) return fail(CVGS_ERR_INVALID_VALUE, "NULL argument");

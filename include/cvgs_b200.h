@@ -317,6 +317,12 @@ int cvgs_b200_debug_host_profile(double* out5, int reset);
  * with sm_count SMs.  out12 = {plan exists, 32-column groups per band, row pairs per plane, bands per plane, work
  * items, bytes per staging slot, slots per warp, CTAs per SM, grid, staged row bytes needed, items covered by the
  * per-warp ranges, 1 if those ranges tile [0, items) in order}.  crops need valid sizes and pitches only. */
+/* Diagnostics (no device needed): the normalised program the kernels run for pipeline->ops (a MUL
+ * directly followed by ADD / SUB becomes one FMA, reorders become store offsets, AddOpaqueAlpha is hoisted to the front).
+ * out[0..7] = {ops, channels of the output pixel, registers per pixel, 1 if the chain changes the channel count or
+ * uses SET / GRAY, dst_chan[0..3]}; out[8 + 9 * i .. 8 + 9 * i + 8] = {kind, a[0..3], b[0..3]} of op i as floats
+ * (kind: 1 MUL, 2 ADD, 3 DIV, 4 FMA, 5 SET, low byte 6 GRAY). */
+int cvgs_b200_debug_program(const cvgs_pipeline_t* pipeline, float* out80);
 int cvgs_b200_debug_plan(const cvgs_crop_t* crops, int32_t n_planes, int32_t used, const cvgs_pipeline_t* pipeline,
                          int32_t sm_count, int32_t image_mode, int32_t items_per_warp, int64_t* out12);
 /* Diagnostics (no device needed): would a launch with these output / source byte ranges on the stream identified by

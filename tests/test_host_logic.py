@@ -80,3 +80,64 @@ def test_overlap_bookkeeping():
         assert q(0x8880, (30_000, 30_100), (5000, 6000)) == 1            # another stream has its own history
     finally:
         lib.cvgs_b200_set_overlap(prev)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# op-chain normalisation (csrc/preproc_host.hpp build_program) through cvgs_b200_debug_program: no device needed
+# ---------------------------------------------------------------------------------------------------------------
+def _program(ops, **kw):
+    import ctypes as C
+    lib = _abi.load()
+    out = (C.c_float * 80)()
+    p = util.make_pipeline((8, 8), ops, out_ptr=16, **kw)
+    rc = lib.cvgs_b200_debug_program(C.byref(p), out)
+    if rc != 0:
+        raise _abi.CvgsError(lib.cvgs_b200_last_error().decode())
+    v = list(out)
+    n = int(v[0])
+    ops_out = [(int(v[8 + 9 * i]), v[9 + 9 * i:13 + 9 * i], v[13 + 9 * i:17 + 9 * i]) for i in range(n)]
+    return dict(n=n, nc_out=int(v[1]), nregs=int(v[2]), special=int(v[3]), dst_chan=[int(x) for x in v[4:8]], ops=ops_out)
+
+
+MUL, ADD, DIV, FMA, SET, GRAY = 1, 2, 3, 4, 5, 6
+
+
+def test_program_mul_sub_contracts_and_reorder_becomes_store_offsets():
+    g = _program(util.OPS_C2)  # reorder(2,1,0), mul, sub, div
+    assert g["n"] == 2 and [k for k, _, _ in g["ops"]] == [FMA, DIV] and not g["special"]
+    assert g["dst_chan"][:3] == [2, 1, 0]                      # register (source channel) r is stored as channel 2 - r
+    f32 = np.float32
+    # constants follow the registers: logical channel 0 (mul 0.3, sub 1.0, div 3.2) lives in register 2
+    assert g["ops"][0][1][2] == f32(0.3) and g["ops"][0][2][2] == f32(-1.0) and g["ops"][1][1][2] == f32(3.2)
+    assert g["ops"][0][2][0] == f32(-3.2) and g["ops"][1][1][0] == f32(11.8)
+    sep = _program(util.OPS_C2, fp_contract=_abi.FP_SEPARATE)
+    assert [k for k, _, _ in sep["ops"]] == [MUL, ADD, DIV]
+
+
+def test_program_alpha_is_hoisted_and_keeps_the_contraction():
+    g = _program([("mul", (0.5, 0.25, 2.0)), ("add_alpha", (255.0,)), ("sub", (1.0, 2.0, 3.0, 4.0))])
+    assert [k for k, _, _ in g["ops"]] == [SET, FMA] and g["nc_out"] == 4 and g["nregs"] == 4 and g["special"]
+    assert g["ops"][0][1][3] == 255.0 and g["ops"][0][2][3] == 1.0           # SET writes register 3 only
+    assert g["ops"][0][2][:3] == [0.0, 0.0, 0.0]
+    assert g["ops"][1][1][3] == 1.0 and g["ops"][1][2][3] == -4.0            # alpha: 255 * 1 + (-4)
+    assert g["dst_chan"] == [0, 1, 2, 3]
+
+
+def test_program_drop_and_gray():
+    g = _program([("reorder", (2, 1, 0, 3)), ("drop_alpha", ()), ("mul", (2.0, 3.0, 4.0))], src_type=_abi.CVGS_8UC4)
+    assert g["nc_out"] == 3 and g["nregs"] == 4 and g["special"] and g["dst_chan"] == [2, 1, 0, -1]
+    assert g["ops"][0][1] == [4.0, 3.0, 2.0, 1.0]                            # the dropped register gets the identity
+    g = _program([("reorder", (2, 1, 0)), ("gray", (0,)), ("sub", (0.5,))])
+    kind = g["ops"][0][0]
+    assert kind & 0xFF == GRAY and (kind >> 8) & 3 == 2 and (kind >> 12) & 3 == 1 and (kind >> 16) & 3 == 0
+    assert not (kind >> 20) & 1 and not (kind >> 21) & 1
+    assert g["nc_out"] == 1 and g["dst_chan"] == [0, -1, -1, -1] and g["ops"][1][0] == ADD and g["ops"][1][1][0] == -0.5
+    assert (_program([("gray", (1,))], fp_contract=_abi.FP_SEPARATE)["ops"][0][0] >> 20) & 3 == 3
+
+
+def test_program_rejects_inconsistent_chains():
+    for ops, kw in [([("drop_alpha", ())], {}), ([("add_alpha", (1.0,))], dict(src_type=_abi.CVGS_8UC4)),
+                    ([("gray", ()), ("gray", ())], {}), ([("add_alpha", (1.0,)), ("add_alpha", (1.0,))], {}),
+                    ([("gray", (2,))], {}), ([("reorder", (0, 0, 1))], {})]:
+        with pytest.raises(_abi.CvgsError):
+            _program(ops, **kw)
