@@ -136,3 +136,15 @@ def test_python_api_codes():
     want1 = util.run_oracle(img, [(0, 0, 160, 120)], (80, 60), [("gray", (1,))])
     util.assert_bit_equal(out4.cpu().numpy(), want4, "BGR2RGBA")
     util.assert_bit_equal(out1.cpu().numpy(), want1, "RGB2GRAY")
+
+
+def test_unused_planes_take_the_converted_default():
+    """Planes z >= used: the chain -- conversion included -- applied to the default value (BatchRead default + chain)."""
+    img = _img(995, 3)
+    ops = [("mul", (2.0, 3.0, 4.0)), ("reorder", (2, 1, 0)), ("add_alpha", (255.0,)), ("sub", (1.0, 1.0, 1.0, 5.0))]
+    got = gpu_util.run_cvgs(img, [(0, 0, 320, 240)], (16, 12), ops, n_planes=3, used=1, background=(10.0, 20.0, 30.0))
+    want = util.run_oracle(img, [(0, 0, 320, 240)], (16, 12), ops, n_planes=3, used=1, background=(10.0, 20.0, 30.0))
+    util.assert_bit_equal(got, want, "defaults through a conversion")
+    assert got[2, :, 0, 0].tolist() == [119.0, 59.0, 19.0, 250.0]
+    got0 = gpu_util.run_cvgs(img, [], (16, 12), [("gray", (0,))], n_planes=2, used=0, background=(100.0, 100.0, 100.0))
+    assert got0.shape == (2, 1, 12, 16) and (got0 == 100.0).all()

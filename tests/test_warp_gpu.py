@@ -301,3 +301,14 @@ def test_other_pixel_types_batches_and_layouts(src_type):
         ours = _launch(d, sizes, pitch, inverses, cvgs.WARP_PERSPECTIVE, (45, 31), ops, **kw)
         orc = _oracle(imgs, sizes, pitch, inverses, cvgs.WARP_PERSPECTIVE, (45, 31), ops, **kw)
         util.assert_bit_equal(ours, orc, f"src {src_type} layout {layout}")
+
+
+def test_no_used_planes_and_empty_chain():
+    """used = 0: every plane is the chain of the default value; nothing is read (images may be NULL)."""
+    lib = _abi.load()
+    out = torch.full((3, 3, 9, 11), float("nan"), device="cuda")
+    p = util.make_pipeline((11, 9), [("mul", (2.0, 3.0, 4.0))], out_ptr=out.data_ptr(), background=(1.0, 2.0, 3.0))
+    _abi.check(lib.cvgs_b200_warp_launch(None, None, 3, 0, C.byref(p), None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert (got[:, 0] == 2.0).all() and (got[:, 1] == 6.0).all() and (got[:, 2] == 12.0).all()
