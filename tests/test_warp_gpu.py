@@ -312,3 +312,38 @@ def test_no_used_planes_and_empty_chain():
     torch.cuda.synchronize()
     got = out.cpu().numpy()
     assert (got[:, 0] == 2.0).all() and (got[:, 1] == 6.0).all() and (got[:, 2] == 12.0).all()
+
+
+@pytest.mark.parametrize("src_type", [_abi.CVGS_8UC3, _abi.CVGS_8UC4])
+def test_warp_into_per_plane_images(src_type):
+    """fk::SplitWrite behind a warp: one pitched float image per (plane, channel); equal to the NCHW tensor of the same
+    launch, reorder included."""
+    rng = np.random.default_rng(90 + src_type)
+    px, nc = util.px_bytes_of(src_type), util.channels_of(src_type)
+    w, h, pitch = 120, 90, 512
+    n = 60  # more than one launch's descriptor table
+    img = rng.integers(0, 256, size=(h, pitch), dtype=np.uint8)
+    d = gpu_util.device_image(img)
+    inverses = [cvgs.api.invert_warp_matrix(m, cvgs.WARP_AFFINE) for m in _matrices(rng, n, cvgs.WARP_AFFINE, w, h)]
+    perm = (2, 1, 0) if nc == 3 else (2, 1, 0, 3)
+    ops = [("reorder", perm), ("mul", (0.5, 1.5, 2.5, 3.5)[:nc])]
+    W, H = 50, 40
+    want = _launch([d] * n, [(w, h)] * n, pitch, inverses, cvgs.WARP_AFFINE, (W, H), ops, src_type=src_type)
+    lib = _abi.load()
+    planes = [torch.full((H, W + (i % 3) * 4), float("nan"), device="cuda") for i in range(n * nc)]
+    arr = (_abi.Plane * (n * nc))()
+    for i, t in enumerate(planes):
+        arr[i].data, arr[i].pitch_bytes = t.data_ptr(), t.stride(0) * 4
+    crops = (_abi.Crop * n)()
+    warps = (_abi.Warp * n)()
+    for i in range(n):
+        crops[i].data, crops[i].width, crops[i].height, crops[i].pitch = d.data_ptr(), w, h, pitch
+        warps[i].type = cvgs.WARP_AFFINE
+        for k in range(9):
+            warps[i].m[k] = float(inverses[i][k])
+    p = util.make_pipeline((W, H), ops, out_ptr=C.addressof(arr), layout=_abi.OUT_PLANES, src_type=src_type)
+    _abi.check(lib.cvgs_b200_warp_launch(crops, warps, n, n, C.byref(p), None))
+    torch.cuda.synchronize()
+    for z in range(n):
+        for c in range(nc):
+            util.assert_bit_equal(planes[z * nc + c][:, :W].cpu().numpy(), want[z, c], f"plane {z} channel {c}")
