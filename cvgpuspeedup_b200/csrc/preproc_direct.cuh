@@ -25,6 +25,63 @@ __device__ __forceinline__ Window load_window(const uint8_t* p, int nbytes) {
     return w;
 }
 
+// 12-byte window [p(x1) | p(x1+1)] of a row of 16-bit 3-channel pixels (2-byte aligned), same rule.
+struct Window12 {
+    uint32_t w[3];  // {c0, c1} {c2, c0'} {c1', c2'} as 16-bit halves
+};
+__device__ __forceinline__ Window12 load_window12(const uint8_t* p, int nbytes) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t mis = static_cast<uint32_t>(a & 3u);  // 0 or 2
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a - mis);
+    const uint32_t w0 = __ldg(wp);
+    const uint32_t w1 = __ldg(wp + 1);  // nbytes >= 6: always needed
+    const uint32_t w2 = (mis + nbytes > 8) ? __ldg(wp + 2) : 0u;
+    const uint32_t w3 = (mis + nbytes > 12) ? __ldg(wp + 3) : 0u;
+    Window12 r;
+    r.w[0] = __funnelshift_r(w0, w1, mis * 8);
+    r.w[1] = __funnelshift_r(w1, w2, mis * 8);
+    r.w[2] = __funnelshift_r(w2, w3, mis * 8);
+    return r;
+}
+// half h (0 low, 1 high) of a word as float: exact for unsigned (mantissa trick) and signed (I2F.S16) samples
+template <typename T16>
+__device__ __forceinline__ float half_to_f32(uint32_t w, int h) {
+    if (sizeof(T16) == 2 && static_cast<T16>(-1) < 0) return static_cast<float>(static_cast<short>(h ? (w >> 16) : (w & 0xffffu)));
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, h ? 0x7432u : 0x7410u)), 8388608.0f);
+}
+// CV_16UC3 / CV_16SC3 taps through 32-bit windows: 3-4 loads per row instead of six 16-bit loads.
+template <typename T16>
+__device__ __forceinline__ void gather_quad_16c3(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
+                                                 float (&v)[4][3]) {
+    const AxisTap ty_ = axis_tap(y - C.by1, C.fy);
+    const int y2r = min(ty_.i1 + 1, C.h - 1);
+    const uint8_t* r0 = C.data + (size_t)ty_.i1 * (size_t)C.pitch;
+    const uint8_t* r1 = C.data + (size_t)y2r * (size_t)C.pitch;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int x = x0 + p;
+        if (p < nvalid && x >= C.bx1 && x <= C.bx2) {
+            const AxisTap tx_ = axis_tap(x - C.bx1, C.fx);
+            const bool edge = tx_.i1 + 1 > C.w - 1;  // x2_read == x1
+            const int nb = edge ? 6 : 12;
+            const Window12 a = load_window12(r0 + 6 * tx_.i1, nb);
+            const Window12 b = load_window12(r1 + 6 * tx_.i1, nb);
+            const float w00 = __fmul_rn(tx_.w0, ty_.w0), w10 = __fmul_rn(tx_.w1, ty_.w0);
+            const float w01 = __fmul_rn(tx_.w0, ty_.w1), w11 = __fmul_rn(tx_.w1, ty_.w1);
+            // left taps: halves 0, 1, 2 of the window; right taps: halves 3, 4, 5, or the left pixel again at the edge
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int hl = c, hr = edge ? c : c + 3;
+                const float a0 = half_to_f32<T16>(a.w[hl >> 1], hl & 1), b0 = half_to_f32<T16>(b.w[hl >> 1], hl & 1);
+                const float a1 = edge ? a0 : half_to_f32<T16>(a.w[(c + 3) >> 1], (c + 3) & 1);
+                const float b1 = edge ? b0 : half_to_f32<T16>(b.w[(c + 3) >> 1], (c + 3) & 1);
+                (void)hr;
+                v[p][c] = bilerp(a0, a1, b0, b1, w00, w10, w01, w11);
+            }
+        }
+    }
+}
+
 template <int NC>
 __device__ __forceinline__ void fill_background(const PreprocParams& P, float (&v)[4][NC]) {
 #pragma unroll
@@ -143,6 +200,34 @@ __device__ __forceinline__ void gather_quad_u8c4(const PreprocParams& P, const D
     }
 }
 
+// CV_16UC4 / CV_16SC4 taps as one aligned 64-bit load each (ushort4 / short4 rows are 8-byte aligned whenever base and
+// pitch are).
+template <typename T16>
+__device__ __forceinline__ void gather_quad_16c4(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
+                                                 float (&v)[4][4]) {
+    const AxisTap ty_ = axis_tap(y - C.by1, C.fy);
+    const int y2r = min(ty_.i1 + 1, C.h - 1);
+    const uint2* r0 = reinterpret_cast<const uint2*>(C.data + (size_t)ty_.i1 * (size_t)C.pitch);
+    const uint2* r1 = reinterpret_cast<const uint2*>(C.data + (size_t)y2r * (size_t)C.pitch);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int x = x0 + p;
+        if (p < nvalid && x >= C.bx1 && x <= C.bx2) {
+            const AxisTap tx_ = axis_tap(x - C.bx1, C.fx);
+            const int x1 = tx_.i1, x2r = min(tx_.i1 + 1, C.w - 1);
+            const float w00 = __fmul_rn(tx_.w0, ty_.w0), w10 = __fmul_rn(tx_.w1, ty_.w0);
+            const float w01 = __fmul_rn(tx_.w0, ty_.w1), w11 = __fmul_rn(tx_.w1, ty_.w1);
+            const uint2 a0 = __ldg(r0 + x1), a1 = __ldg(r0 + x2r), b0 = __ldg(r1 + x1), b1 = __ldg(r1 + x2r);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int h = c & 1;
+                v[p][c] = bilerp(half_to_f32<T16>(c < 2 ? a0.x : a0.y, h), half_to_f32<T16>(c < 2 ? a1.x : a1.y, h),
+                                 half_to_f32<T16>(c < 2 ? b0.x : b0.y, h), half_to_f32<T16>(c < 2 ? b1.x : b1.y, h), w00, w10, w01, w11);
+            }
+        }
+    }
+}
+
 // 4-channel sources (CV_8UC4 / CV_16UC4 / CV_16SC4): same arithmetic on four channels.
 __device__ __forceinline__ void gather_quad(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
                                             float (&v)[4][4]) {
@@ -153,8 +238,16 @@ __device__ __forceinline__ void gather_quad(const PreprocParams& P, const DevCro
         if (((reinterpret_cast<uintptr_t>(C.data) | static_cast<uintptr_t>(C.pitch)) & 3) == 0) gather_quad_u8c4(P, C, y, x0, nvalid, v);
         else gather_quad16<unsigned char, 4>(P, C, y, x0, nvalid, v);
     }
-    else if (P.src_type == CVGS_16UC4) gather_quad16<unsigned short, 4>(P, C, y, x0, nvalid, v);
-    else gather_quad16<short, 4>(P, C, y, x0, nvalid, v);
+    else {
+        const bool aligned8 = ((reinterpret_cast<uintptr_t>(C.data) | static_cast<uintptr_t>(C.pitch)) & 7) == 0;
+        if (P.src_type == CVGS_16UC4) {
+            if (aligned8) gather_quad_16c4<unsigned short>(P, C, y, x0, nvalid, v);
+            else gather_quad16<unsigned short, 4>(P, C, y, x0, nvalid, v);
+        } else {
+            if (aligned8) gather_quad_16c4<short>(P, C, y, x0, nvalid, v);
+            else gather_quad16<short, 4>(P, C, y, x0, nvalid, v);
+        }
+    }
 }
 
 __device__ __forceinline__ void gather_quad(const PreprocParams& P, const DevCrop& C, int y, int x0, int nvalid,
@@ -163,8 +256,8 @@ __device__ __forceinline__ void gather_quad(const PreprocParams& P, const DevCro
     const bool row_in = !P.band_test || (y >= C.by1 && y <= C.by2);
     if (!row_in) return;
     if (P.src_type != CVGS_8UC3) {
-        if (P.src_type == CVGS_16UC3) gather_quad16<unsigned short, 3>(P, C, y, x0, nvalid, v);
-        else if (P.src_type == CVGS_16SC3) gather_quad16<short, 3>(P, C, y, x0, nvalid, v);
+        if (P.src_type == CVGS_16UC3) gather_quad_16c3<unsigned short>(P, C, y, x0, nvalid, v);
+        else if (P.src_type == CVGS_16SC3) gather_quad_16c3<short>(P, C, y, x0, nvalid, v);
         else gather_quad_nv12(P, C, y, x0, nvalid, v);
         return;
     }

@@ -38,7 +38,7 @@ def tapped_bytes(px_bytes):
     return int(mask.sum()) * px_bytes
 
 
-def run(name, src_type, ops, px_bytes, image, crops_of, out_channels=3, out_bytes_per_value=4, variant=0, **kw):
+def run(name, src_type, ops, px_bytes, image, crops_of, out_channels=3, out_bytes_per_value=4, variant=0, src_bytes=None, **kw):
     d_img = torch.from_numpy(image).cuda()
     n_out = N * out_channels * DST[0] * DST[1]
     if out_bytes_per_value == 1:
@@ -79,7 +79,7 @@ def run(name, src_type, ops, px_bytes, image, crops_of, out_channels=3, out_byte
     assert util.oracle_lib().oracle_preproc(sub, 3, 3, C.byref(po), 0) == 0
     got = out.cpu().numpy().reshape(N, plane)[idx].reshape(-1)
     assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), f"{name}: differs from the oracle"
-    b_in = tapped_bytes(px_bytes) if px_bytes else 0
+    b_in = tapped_bytes(px_bytes) if px_bytes else int(src_bytes or 0)
     b_out = n_out * out_bytes_per_value
     gbs = (b_in + b_out) / us / 1e3
     print(f"{name:<46} {us:8.1f} us  in {b_in / 1e6:6.1f} MB  out {b_out / 1e6:6.1f} MB  {gbs:7.0f} GB/s  {gbs / PEAK:5.2f} of HBM peak", flush=True)
@@ -136,4 +136,4 @@ for name, fmt, rows, bpl, bpp in [("NV12 frames 448x448 -> NCHW float", _abi.CVG
     image, cf = yuv_frames(rows, bpl)
     d_img = None
     # source bytes: every sample of the 8 distinct frames is tapped at a 2x down-scale (both rows and columns of a 2x2 cell)
-    run(name, fmt, NORM, 0, image, cf, yuv_standard=1)
+    run(name, fmt, NORM, 0, image, cf, yuv_standard=1, src_bytes=8 * fw * fh * bpp)

@@ -51,3 +51,33 @@ def test_tma_kernel_declines_4channel_sources():
     img = _img(90, _abi.CVGS_8UC4)
     with pytest.raises(_abi.CvgsError):
         gpu_util.run_cvgs(img, [(0, 0, 64, 64)], (32, 32), [], variant=2, src_type=_abi.CVGS_8UC4)
+
+
+@pytest.mark.parametrize("src_type,shifts", [(_abi.CVGS_8UC4, (0, 1, 2, 3)), (_abi.CVGS_16UC4, (0, 2, 4, 6)), (_abi.CVGS_16SC4, (0, 2))])
+def test_4channel_taps_at_every_base_alignment(src_type, shifts):
+    """Aligned images fetch a tap with one 32-/64-bit load; any other base or pitch must fall back to element loads and
+    give the same bits."""
+    import ctypes as C
+    import torch
+    px = util.px_bytes_of(src_type)
+    rng = np.random.default_rng(85 + src_type)
+    w, h = 100, 60
+    lib = _abi.load()
+    for shift in shifts:
+        for pitch in (px * w + 16, px * w + 2 * (px // 4) + (2 if px == 8 else 1)):
+            if px == 8 and pitch % 2:
+                pitch += 1
+            back = rng.integers(0, 256, size=h * pitch + 16, dtype=np.uint8)
+            img = back[shift:shift + h * pitch].reshape(h, pitch)
+            d_back = torch.from_numpy(back).cuda()
+            rects = [(0, 0, w, h), (3, 5, 40, 30), (99, 0, 1, 60)]
+            ops = [("mul", MUL), ("sub", SUB)]
+            want = util.run_oracle(np.ascontiguousarray(img), rects, (37, 23), ops, src_type=src_type)
+            out = torch.full((3, 4, 23, 37), float("nan"), device="cuda")
+            crops = util.host_crops(np.ascontiguousarray(img), rects, base_ptr=d_back.data_ptr() + shift, px_bytes=px)
+            for i in range(3):
+                crops[i].pitch = pitch
+            p = util.make_pipeline((37, 23), ops, out_ptr=out.data_ptr(), src_type=src_type)
+            _abi.check(lib.cvgs_b200_preproc_launch(crops, 3, 3, C.byref(p), None))
+            torch.cuda.synchronize()
+            util.assert_bit_equal(out.cpu().numpy(), want, f"src {src_type} shift {shift} pitch {pitch}")
