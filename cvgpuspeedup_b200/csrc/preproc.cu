@@ -21,6 +21,8 @@
 #include <atomic>
 #include <cstdlib>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <cstdio>
 #include <mutex>
 #include <string>
@@ -605,6 +607,65 @@ static int host_reserve(HostPath& h, size_t img_bytes, size_t out_bytes, int dev
 // ------------------------------------------------------------------------------------------------
 using namespace cvgs;
 
+// Helper threads of the frame loop live for the rest of the process (their per-thread caches -- tensor maps, memoised
+// programs -- stay warm between sequences, and a sequence does not pay for thread creation).  The pool is allocated
+// once and never destroyed: at process exit the helpers are parked on the condition variable and simply end with the
+// process.
+struct SeqPool {
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::atomic<uint64_t> generation{0};
+    std::function<void(int)> job;  // called with the worker index 1 .. job_workers - 1
+    int job_workers = 0;
+    int pending = 0;
+    int n_threads = 0;             // helpers started so far (worker indices 1 .. n_threads)
+    void helper_main(int w) {
+        uint64_t seen = 0;
+        for (;;) {
+            // a short spin first: frame loops arrive back to back, and a futex wake costs tens of microseconds
+            for (int i = 0; i < 20000 && generation.load(std::memory_order_acquire) == seen; ++i) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            std::unique_lock<std::mutex> lk(mu);
+            cv_job.wait(lk, [&] { return generation.load(std::memory_order_acquire) != seen; });
+            seen = generation.load(std::memory_order_acquire);
+            if (w >= job_workers) continue;
+            std::function<void(int)> f = job;
+            lk.unlock();
+            f(w);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_all();
+        }
+    }
+    // runs f(1) .. f(workers - 1) on the helpers; returns after the caller-supplied `own` ran on this thread and every
+    // helper finished
+    template <typename Own>
+    void run(int workers, std::function<void(int)> f, Own own) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            while (n_threads < workers - 1) {
+                const int w = ++n_threads;
+                std::thread([this, w] { helper_main(w); }).detach();
+            }
+            job = std::move(f);
+            job_workers = workers;
+            pending = workers - 1;
+            generation.fetch_add(1, std::memory_order_release);
+        }
+        cv_job.notify_all();
+        own();
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+        job = nullptr;
+    }
+};
+static SeqPool* seq_pool() {
+    static SeqPool* p = new SeqPool;  // intentionally leaked, see above
+    return p;
+}
+
 extern "C" {
 
 int cvgs_b200_version(void) { return CVGS_B200_VERSION; }
@@ -943,7 +1004,7 @@ int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const 
         return fail(CVGS_ERR_INVALID_VALUE, "bad sequence arguments");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     int workers = std::min(seq_workers(), static_cast<int>(n_sets));
-    if (workers > 1 && (steps < 128 || !g_overlap.load(std::memory_order_relaxed))) workers = 1;
+    if (workers > 1 && (steps < 16 || !g_overlap.load(std::memory_order_relaxed))) workers = 1;
     if (workers > 1) {
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) workers = 1;
@@ -991,9 +1052,9 @@ int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const 
         t_items_hint = 0;
         return rc;
     };
-    std::thread helpers[kSeqMaxWorkers];
-    for (int w = 1; w < workers; ++w) {
-        helpers[w] = std::thread([&, w] {
+    seq_pool()->run(
+        workers,
+        [&](int w) {
             Result& r = res[w];
             if (cudaSetDevice(device) != cudaSuccess || cudaStreamWaitEvent(Q.stream[w], Q.start, 0) != cudaSuccess) {
                 r.rc = CVGS_ERR_INVALID_VALUE;
@@ -1008,13 +1069,13 @@ int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const 
                 r.rc = CVGS_ERR_INVALID_VALUE;
                 r.err = "sequence helper: cudaEventRecord failed";
             }
+        },
+        [&] {
+            res[0].rc = run(0, stream);
+            if (res[0].rc != CVGS_OK) res[0].err = t_last_error;
         });
-    }
-    res[0].rc = run(0, stream);
-    if (res[0].rc != CVGS_OK) res[0].err = t_last_error;
     int rc = res[0].rc;
     for (int w = 1; w < workers; ++w) {
-        helpers[w].join();
         // join the helper stream even after an error: whatever it launched must finish before the caller's stream goes on
         const cudaError_t e = cudaStreamWaitEvent(stream, Q.done[w], 0);
         t_launch_count += res[w].launches;

@@ -275,7 +275,7 @@ int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t 
  * (ctypes, JNI) can drive and time many frames without their per-call overhead.
  * Stops at the first error and returns it.
  * cvgs_b200_preproc_launch_sequence_ex with cvgs_b200_set_overlap(1): when the argument sets are provably
- * independent (outputs pairwise disjoint and disjoint from every source) and steps >= 128, the loop is driven by
+ * independent (outputs pairwise disjoint and disjoint from every source) and steps >= 16, the loop is driven by
  * several host threads (CVGS_B200_SEQ_THREADS, default 3, at most 4), each launching the sets it owns into its own
  * stream; the caller's stream is forked into and joined from those streams, so for the caller the sequence is still
  * one ordered operation and every result is identical.  One host thread sustains ~3.9 us per 50-crop frame, three

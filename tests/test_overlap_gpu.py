@@ -195,7 +195,7 @@ def _sequence(lib, ws, d_imgs, outs, steps, stream):
 
 
 def test_frame_loop_over_several_host_threads(overlap_on):
-    """steps >= 128 with independent argument sets: the loop is split over helper threads and streams
+    """steps >= 16 with independent argument sets: the loop is split over helper threads and streams
     (include/cvgs_b200.h); every frame's result, the launch count and the ordering on the caller's stream hold."""
     lib = overlap_on
     st = torch.cuda.Stream()
