@@ -16,6 +16,7 @@
 // This file: the direct kernel, the host launch path (descriptor tables in kernel parameters or through a pinned
 // ring, per-image tensor-map cache, overlap bookkeeping) and the C-ABI entry points of the batch pipeline.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -662,7 +663,14 @@ struct SeqPool {
     }
 };
 static SeqPool* seq_pool() {
-    static SeqPool* p = new SeqPool;  // intentionally leaked, see above
+    // intentionally leaked, see above.  A forked child inherits the pool's bookkeeping but none of its threads: it gets
+    // a pool of its own (callers hold g_seq_mu, so this is not racy).
+    static SeqPool* p = nullptr;
+    static pid_t owner = 0;
+    if (!p || owner != getpid()) {
+        p = new SeqPool;
+        owner = getpid();
+    }
     return p;
 }
 
