@@ -123,3 +123,41 @@ def test_yuv_alignment_is_checked():
     crops[0].data, crops[0].width, crops[0].height, crops[0].pitch = t.data_ptr() + 2, 16, 16, 128
     p = util.make_pipeline((8, 8), [], out_ptr=out.data_ptr(), src_type=_abi.CVGS_Y210)
     assert lib.cvgs_b200_preproc_launch(crops, 1, 1, C.byref(p), None) != 0 and b"aligned" in lib.cvgs_b200_last_error()
+
+
+@pytest.mark.parametrize("seed", range(20 + int(__import__("os").environ.get("CVGS_FUZZ_EXTRA", "0"))))
+def test_random_yuv_frames_against_oracle(seed):
+    """Every format, odd and even frame sizes (the last column / row shares its chroma sample), random pitches, sizes,
+    standards, aspect modes and chains."""
+    rng = np.random.default_rng(12000 + seed)
+    fmt = [_abi.CVGS_NV12] + FORMATS
+    fmt = fmt[seed % len(fmt)]
+    n = int(rng.integers(1, 6))
+    sizes = [(int(rng.integers(1, 140)), int(rng.integers(1, 100))) for _ in range(n)]
+    wmax = max(w for w, _ in sizes)
+    per_px = {_abi.CVGS_NV12: 1, _abi.CVGS_NV21: 1, _abi.CVGS_P010: 2, _abi.CVGS_P210: 2, _abi.CVGS_Y210: 4}[fmt]
+    pitch = ((wmax + 1) // 2 * 2 * per_px + 7) // 8 * 8 + 8 * int(rng.integers(0, 4))
+    frames = []
+    for (w, h) in sizes:
+        rows = {_abi.CVGS_NV12: h + (h + 1) // 2, _abi.CVGS_NV21: h + (h + 1) // 2, _abi.CVGS_P010: h + (h + 1) // 2,
+                _abi.CVGS_P210: 2 * h, _abi.CVGS_Y210: h}[fmt]
+        frames.append(rng.integers(0, 256, size=(rows, pitch), dtype=np.uint8))
+    dsize = (int(rng.integers(1, 120)), int(rng.integers(1, 90)))
+    ops = [OPS, [], [("reorder", (2, 1, 0)), ("mul", (0.5, 0.25, 2.0))], [("gray", (1,)), ("sub", (3.0,))]][int(rng.integers(0, 4))]
+    kw = dict(aspect=int(rng.integers(0, 4)), background=(1.0, 2.0, 3.0))
+    standard = int(rng.integers(0, 4))
+    lib = _abi.load()
+    d = [torch.from_numpy(f).cuda() for f in frames]
+    crops_d, crops_h = (_abi.Crop * n)(), (_abi.Crop * n)()
+    for i, (t, f, (w, h)) in enumerate(zip(d, frames, sizes)):
+        crops_d[i].data, crops_d[i].width, crops_d[i].height, crops_d[i].pitch = t.data_ptr(), w, h, pitch
+        crops_h[i].data, crops_h[i].width, crops_h[i].height, crops_h[i].pitch = f.ctypes.data, w, h, pitch
+    nco = util.out_channels(_abi.CVGS_8UC3, ops)
+    out = torch.full((n, nco, dsize[1], dsize[0]), float("nan"), device="cuda")
+    want = np.full((n, nco, dsize[1], dsize[0]), np.nan, dtype=np.float32)
+    p = util.make_pipeline(dsize, ops, out_ptr=out.data_ptr(), src_type=fmt, yuv_standard=standard, **kw)
+    _abi.check(lib.cvgs_b200_preproc_launch(crops_d, n, n, C.byref(p), None))
+    torch.cuda.synchronize()
+    p = util.make_pipeline(dsize, ops, out_ptr=want.ctypes.data, src_type=fmt, yuv_standard=standard, **kw)
+    assert util.oracle_lib().oracle_preproc(crops_h, n, n, C.byref(p), 0) == 0
+    util.assert_bit_equal(out.cpu().numpy(), want, f"seed {seed} fmt {fmt:#x} sizes {sizes} pitch {pitch} dsize {dsize} std {standard} ops {ops} {kw}")
