@@ -69,3 +69,30 @@ def test_errors():
     crop = util.host_crops(np.zeros((16, 48), np.uint8), [(0, 0, 16, 16)], base_ptr=frame.data_ptr())
     assert lib.cvgs_b200_ct_update(ct._h, crop, C.byref(p), None) == 1  # wrong destination size
     ct.close()
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_depths_sizes_and_orders(seed):
+    """Depth 1 (nothing to shift) to 9, plane sizes with and without 16-byte multiples, every order / layout, a run of
+    updates longer than the ring."""
+    rng = np.random.default_rng(700 + seed)
+    W, H = int(rng.integers(1, 90)), int(rng.integers(1, 60))
+    fw, fh = int(rng.integers(2, 200)), int(rng.integers(2, 150))
+    B = int(rng.integers(1, 10))
+    order = int(rng.integers(0, 2))
+    mode = int(rng.integers(0, 2))
+    lib = util.oracle_lib()
+    o = lib.oracle_ct_create(W, H, 3, B, order, mode)
+    ct = cvgs.CircularTensor(W, H, B, order, mode)
+    p = util.make_pipeline((W, H), util.OPS_C2)
+    ops = [cvgs.cvtColor(), cvgs.multiply((0.3, 0.3, 0.3)), cvgs.subtract((1.0, 4.0, 3.2)), cvgs.divide((3.2, 0.6, 11.8))]
+    for i in range(B + 4):
+        img = util.make_image(rng, fw, fh)
+        assert lib.oracle_ct_update(o, util.host_crops(img, [(0, 0, fw, fh)]), C.byref(p), 0) == 0
+        d = torch.from_numpy(img).cuda().view(fh, fw, 3)
+        ct.update(None, cvgs.GpuMat.from_tensor(d), *ops)
+    torch.cuda.synchronize()
+    want = np.ctypeslib.as_array(lib.oracle_ct_data(o), shape=(B * 3 * H * W,))
+    util.assert_bit_equal(ct.data().cpu().numpy().reshape(-1), want, f"seed {seed}: {W}x{H} depth {B} order {order} mode {mode}")
+    lib.oracle_ct_destroy(o)
+    ct.close()
