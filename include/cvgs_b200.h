@@ -6,6 +6,8 @@
  *   batched crop -> bilinear resize -> convertTo/scale -> per-channel mul/sub/div/add
  *                -> channel reorder (cvtColor) -> planar split           (one kernel launch)
  *   CircularTensor shift + process                                       (one kernel launch)
+ * and the callers / data formats either side of it that SURVEY.md 8(f) ranks next: YUV frames as sources, batched
+ * affine / perspective warps in front of the same chain, the other source depths, channel counts and output forms.
  *
  * The reference has no FFI: its public surface is header-only C++ templates
  * (reference include/cvGPUSpeedup.cuh:74-627) whose operation structs are PODs with public
