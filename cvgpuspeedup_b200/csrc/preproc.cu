@@ -54,6 +54,10 @@ static inline double now_us() {
 }
 static thread_local int64_t t_launch_count = 0;
 static std::atomic<int> g_variant{0};
+static std::atomic<int> g_coalesce{[] {
+    const char* e = std::getenv("CVGS_B200_SEQ_COALESCE");
+    return e && e[0] == '0' ? 0 : 1;
+}()};
 static std::atomic<int> g_overlap{[] {
     const char* e = std::getenv("CVGS_B200_OVERLAP");
     return e && e[0] == '1' ? 1 : 0;
@@ -77,6 +81,7 @@ struct StreamTrack {
     static constexpr int kWindow = 8;
     MemRange out[kWindow], src[kWindow];
     int n = 0;
+    bool unknown_pred = false;  // something this bookkeeping did not see went to the stream: the next launch waits up front
 };
 static std::mutex g_track_mu;
 static StreamTrack g_tracks[16];
@@ -113,7 +118,8 @@ static bool overlap_needs_wait(cudaStream_t stream, const MemRange& out, const M
         t->out[0] = out; t->src[0] = src; t->n = 1;
         return true;
     }
-    bool hazard = t->n >= StreamTrack::kWindow;
+    bool hazard = t->n >= StreamTrack::kWindow || t->unknown_pred;
+    t->unknown_pred = false;
     for (int i = 0; i < t->n && !hazard; ++i)
         hazard = out.overlaps(t->out[i]) || src.overlaps(t->out[i]) || out.overlaps(t->src[i]);
     if (hazard) t->n = 0;  // the wait orders this launch after everything before it
@@ -126,7 +132,10 @@ static void overlap_forget(cudaStream_t stream) {  // a launch of this library t
     if (!g_overlap.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lock(g_track_mu);
     for (auto& k : g_tracks)
-        if (k.used && k.stream == stream) k.n = 0;
+        if (k.used && k.stream == stream) {
+            k.n = 0;
+            k.unknown_pred = true;
+        }
 }
 static MemRange crops_range(const DevCrop* c, int n) {
     MemRange r;
@@ -586,6 +595,90 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Coalesced frame groups: the crops of several independent argument sets (own parent frame, own output tensor, same
+// pipeline) in ONE launch of the TMA-staged kernel.  A 50-crop frame is 7.5 MB of traffic -- 1.5 us of HBM time, less
+// than a kernel launch costs the host and the GPU front end -- so a frame loop that launches per frame is bound by
+// launch granularity; ten frames per launch are not.  Used by cvgs_b200_preproc_launch_sequence_ex.
+// ------------------------------------------------------------------------------------------------
+static thread_local DevMapCache t_dev_maps;
+struct MultiSet {
+    const cvgs_crop_t* crops;
+    const cvgs_parent_t* parents;
+    int n;
+    float* out;
+};
+constexpr int kMultiDeclined = -2;  // not an error: the caller launches the sets one by one
+
+static int launch_multi(const MultiSet* sets, int G, const cvgs_pipeline_t* pipe, bool early_wait, cudaStream_t stream) {
+    int total = 0;
+    for (int g = 0; g < G; ++g) total += sets[g].n;
+    if (G <= 0 || G > kMultiGroups || total <= 0 || total > kMultiCrops) return kMultiDeclined;
+    PreprocParams P;
+    if (int rc = build_params(*pipe, total, total, sets[0].out, P)) return rc;
+    int device = 0;
+    CVGS_CUDA(cudaGetDevice(&device));
+    const int sms = sm_count_of(device);
+    DevMapCache& mc = t_dev_maps;
+    if (int rc = mc.reserve(device)) return rc;
+    alignas(64) TmaMultiTable mt;
+    TmaParams K;
+    for (int attempt = 0;; ++attempt) {
+        int z = 0;
+        for (int g = 0; g < G; ++g) {
+            mt.out_base[g] = sets[g].out;
+            mt.z_first[g] = z;
+            for (int i = 0; i < sets[g].n; ++i, ++z)
+                if (int rc = fill_crop(sets[g].crops[i], *pipe, z, mt.c[z])) return rc;
+        }
+        K.P = P;
+        K.P.out.base = nullptr;  // every plane goes through out_base[]
+        if (!tma_plan(P, mt.c, total, total, sms, true, 1, K.G)) return kMultiDeclined;
+        const uint32_t gen = mc.generation;
+        const int TWp = std::min(32 * K.G.NPB, P.W);
+        bool restart = false;
+        z = 0;
+        for (int g = 0; g < G && !restart; ++g) {
+            uintptr_t last_ds = 0;
+            int last_rb = -1, last_idx = -1;
+            for (int i = 0; i < sets[g].n; ++i, ++z) {
+                const cvgs_parent_t& p = sets[g].parents[i];
+                DevCrop& c = mt.c[z];
+                if (!p.datastart || p.whole_width <= 0 || p.whole_height <= 0) return kMultiDeclined;
+                const int rb = rb_class(band_row_bytes(TWp, c.fx));
+                if (rb == 0 || 4 * rb + kSlotHeader > K.G.slot_bytes) return kMultiDeclined;
+                const uintptr_t ds = reinterpret_cast<uintptr_t>(p.datastart);
+                int idx = last_idx;
+                if (ds != last_ds || rb != last_rb) {
+                    idx = mc.get(ds, c.pitch, p.whole_width, p.whole_height, rb);
+                    if (idx < 0) return kMultiDeclined;
+                    if (mc.generation != gen) {  // the table started over: indices handed out so far are void
+                        restart = true;
+                        break;
+                    }
+                    last_ds = ds;
+                    last_rb = rb;
+                    last_idx = idx;
+                }
+                int32_t xb, y0, pad;
+                if (!tma_place_in_image(c, ds, p.whole_width, p.whole_height, rb, idx, xb, y0, pad)) return kMultiDeclined;
+                c.m.xb = xb;  // overwrites c.data (union)
+                c.m.y0 = y0;
+                c.pad = pad;
+                c.pitch = g;
+            }
+        }
+        if (!restart) break;
+        if (attempt > 0) return kMultiDeclined;
+    }
+    if (int rc = mc.flush()) return rc;
+    const int chain = scaled_program(P, K);
+    K.P.crops = nullptr;
+    K.maps = mc.d;
+    K.G.pdl_wait = early_wait ? 1 : 0;
+    return tma_launch_multi(K, mt, chain, device, stream);
+}
+
 static int host_reserve(HostPath& h, size_t img_bytes, size_t out_bytes, int device) {
     if (h.device != device) { h.img_cap = h.out_cap = 0; h.d_img = nullptr; h.d_out = nullptr; h.device = device; }
     if (img_bytes > h.img_cap) {
@@ -680,6 +773,7 @@ int cvgs_b200_version(void) { return CVGS_B200_VERSION; }
 const char* cvgs_b200_last_error(void) { return t_last_error.c_str(); }
 int cvgs_b200_set_kernel_variant(int variant) { return g_variant.exchange(variant); }
 int cvgs_b200_set_overlap(int enable) { return g_overlap.exchange(enable ? 1 : 0); }
+int cvgs_b200_set_coalesce(int enable) { return g_coalesce.exchange(enable ? 1 : 0); }
 int64_t cvgs_b200_launch_count(void) { return t_launch_count; }
 // Diagnostics for the CPU test-suite: the launch plan of the TMA kernel for a batch geometry (no device needed).
 // out[0..11] = {ok, NPB, HP, tiles_x, total_items, slot_bytes, slots, resident, grid, max row bytes needed,
@@ -1004,6 +1098,72 @@ static bool sequence_sets_independent(const cvgs_crop_t* const* crops, const int
     return true;
 }
 
+// Can the argument sets ride in shared launches (launch_multi)?  Same pipeline in every set apart from the output
+// pointer, the common geometry (CV_8UC3, IGNORE_AR, every plane used, tight or strided NCHW float), parents named.
+static bool sequence_sets_coalescible(const cvgs_parent_t* const* parents, const int32_t* n_planes, const int32_t* used,
+                                      const cvgs_pipeline_t* const* pipelines, int n_sets) {
+    if (!g_coalesce.load(std::memory_order_relaxed) || n_sets < 2) return false;
+    const cvgs_pipeline_t& p0 = *pipelines[0];
+    if (p0.src_type != CVGS_8UC3 || p0.aspect_mode != CVGS_IGNORE_AR || p0.out_layout != CVGS_OUT_NCHW || p0.out_row_pitch != 0 ||
+        (p0.dst_type != 0 && p0.dst_type != CVGS_32FC3))
+        return false;
+    DevProgram prog;
+    if (build_program(p0, prog) != CVGS_OK || prog.special) return false;
+    cvgs_pipeline_t k0 = p0;
+    k0.out = nullptr;
+    for (int s = 0; s < n_sets; ++s) {
+        if (!parents[s] || n_planes[s] != used[s] || n_planes[s] <= 0 || n_planes[s] > kMultiCrops) return false;
+        cvgs_pipeline_t k = *pipelines[s];
+        k.out = nullptr;
+        if (std::memcmp(&k, &k0, sizeof k) != 0) return false;
+    }
+    return true;
+}
+
+// The coalesced frame loop: consecutive steps (distinct, independent argument sets) share launches of up to
+// kMultiCrops crops.  One host thread, the caller's stream.  Consecutive launches overlap (late griddepcontrol.wait)
+// unless a launch rewrites the tensor of a set that a launch possibly still in flight wrote: everything since the
+// last launch that waited up front may be in flight, and at most StreamTrack::kWindow launches are allowed to be.
+static int sequence_coalesced(const cvgs_crop_t* const* crops, const cvgs_parent_t* const* parents, const int32_t* n_planes,
+                              const cvgs_pipeline_t* const* pipelines, int n_sets, int steps, cudaStream_t stream) {
+    std::vector<int> last_writer(static_cast<size_t>(n_sets), -1);
+    int last_early = 0, L = 0;
+    bool force_early = true;  // whatever precedes the sequence on the stream is unknown
+    MultiSet ms[kMultiGroups];
+    overlap_forget(stream);
+    for (int i = 0; i < steps;) {
+        int G = 0, total = 0;
+        bool hazard = force_early || L - last_early >= StreamTrack::kWindow;
+        while (i + G < steps && G < kMultiGroups && G < n_sets) {
+            const int s = (i + G) % n_sets;
+            if (total + n_planes[s] > kMultiCrops) break;
+            ms[G] = MultiSet{crops[s], parents[s], n_planes[s], static_cast<float*>(pipelines[s]->out)};
+            if (last_writer[static_cast<size_t>(s)] >= last_early) hazard = true;
+            total += n_planes[s];
+            ++G;
+        }
+        int rc = launch_multi(ms, G, pipelines[i % n_sets], hazard, stream);
+        if (rc == kMultiDeclined) {  // a geometry the shared launch does not take: these sets go one by one, in plain order
+            for (int g = 0; g < G; ++g) {
+                const int s = (i + g) % n_sets;
+                if (int r2 = cvgs_b200_preproc_launch_ex(crops[s], parents[s], n_planes[s], n_planes[s], pipelines[s], stream)) return r2;
+            }
+            overlap_forget(stream);
+            force_early = true;
+        } else if (rc != CVGS_OK) {
+            return rc;
+        } else {
+            force_early = false;
+            if (hazard) last_early = L;
+        }
+        for (int g = 0; g < G; ++g) last_writer[static_cast<size_t>((i + g) % n_sets)] = L;
+        ++L;
+        i += G;
+    }
+    overlap_forget(stream);
+    return CVGS_OK;
+}
+
 int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const cvgs_parent_t* const* parents,
                                          const int32_t* n_planes, const int32_t* used,
                                          const cvgs_pipeline_t* const* pipelines, int32_t n_sets, int32_t steps,
@@ -1011,6 +1171,13 @@ int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const 
     if (!crops || !parents || !n_planes || !used || !pipelines || n_sets <= 0 || steps < 0)
         return fail(CVGS_ERR_INVALID_VALUE, "bad sequence arguments");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (steps >= 2 && g_overlap.load(std::memory_order_relaxed) && g_variant.load(std::memory_order_relaxed) != 1) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone &&
+            sequence_sets_independent(crops, n_planes, used, pipelines, n_sets) &&
+            sequence_sets_coalescible(parents, n_planes, used, pipelines, n_sets))
+            return sequence_coalesced(crops, parents, n_planes, pipelines, n_sets, steps, stream);
+    }
     int workers = std::min(seq_workers(), static_cast<int>(n_sets));
     if (workers > 1 && (steps < 16 || !g_overlap.load(std::memory_order_relaxed))) workers = 1;
     if (workers > 1) {

@@ -96,6 +96,16 @@ using TmaImageTableL = TmaParamTableT<kTmaImageMaps, kTmaImageCrops>;
 struct TmaNoTable {
     int32_t unused;
 };
+// Coalesced frame groups (cvgs_b200_preproc_launch_sequence_ex): the crops of up to kMultiGroups independent argument
+// sets -- each with its own parent frame and its own output tensor -- ride in ONE launch.  Descriptors in the kernel
+// parameters, tensor maps in the device-resident cache (TmaParams::maps, DevMapCache below).
+constexpr int kMultiCrops = 512;
+constexpr int kMultiGroups = 32;
+struct alignas(64) TmaMultiTable {
+    DevCrop c[kMultiCrops];          // DevCrop::pitch = index of the crop's group (the TMA kernel never reads the pitch)
+    float* out_base[kMultiGroups];   // output tensor of group g
+    int32_t z_first[kMultiGroups];   // launch-wide plane index of the group's first crop
+};
 
 // Vertical taps of one output row, computed 16 rows (8 items) at a time by 16 lanes of the warp that owns the
 // items and kept in a per-warp table; both the staging of an item and its computation read them from there.
@@ -198,6 +208,20 @@ __device__ __forceinline__ const CUtensorMap* tma_map_of(const TmaParams&, const
 template <>
 __device__ __forceinline__ const CUtensorMap* tma_map_of<TmaNoTable>(const TmaParams& K, const TmaNoTable&, const DevCrop& C) {
     return K.maps + crop_map_index(C);
+}
+template <>
+__device__ __forceinline__ const CUtensorMap* tma_map_of<TmaMultiTable>(const TmaParams& K, const TmaMultiTable&, const DevCrop& C) {
+    return K.maps + crop_map_index(C);
+}
+// First float of output plane z (float layouts).
+template <typename Table>
+__device__ __forceinline__ float* tma_plane_base(const TmaParams& K, const Table&, int z) {
+    return K.P.out.base + (long long)z * K.P.out.z_stride;
+}
+template <>
+__device__ __forceinline__ float* tma_plane_base<TmaMultiTable>(const TmaParams& K, const TmaMultiTable& T, int z) {
+    const int g = T.c[z].pitch;
+    return T.out_base[g] + (long long)(z - T.z_first[g]) * K.P.out.z_stride;
 }
 
 // Where the staged span of a (crop, column band) starts: first in-band output column of the band, its left tap,
@@ -542,7 +566,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         // this lane's first column in rows 2*jp of the three channel planes of plane z
         asm volatile("" : "+r"(m_edge), "+r"(m_img), "+r"(m_in));
         const bool full_band = tx0 + 32 * np <= W;  // every lane owns a column in each of the band's np groups
-        float* s0 = P.out.base + ((long long)z * P.out.z_stride + (long long)(tx0 + lane) * pxs + (long long)(2 * cc.jp) * row_step);
+        float* s0 = tma_plane_base<Table>(K, T, z) + ((long long)(tx0 + lane) * pxs + (long long)(2 * cc.jp) * row_step);
         float* s1 = s0 + oc1;
         float* s2 = s0 + oc2;
         s0 += oc0;
@@ -963,6 +987,85 @@ struct ImageMapCache {
     }
 };
 
+// Device-resident copy of the per-image maps, for launches that coalesce more frames than tensor maps fit in the
+// kernel parameters.  Append-only: an entry is encoded on the host, uploaded once (flush(): one copy on an internal
+// stream, waited for on the host -- a first-sight cost per (camera buffer, row-bytes class), never on a hit) and from
+// then on referenced by index, so a map in use by a kernel in flight is never rewritten.  When the table is full the
+// device is synchronised and the table starts over.  One cache per host thread, like ImageMapCache.
+struct DevMapCache {
+    static constexpr int kCap = 4096;          // entries (16-bit index in DevCrop::pad); 512 KB of device memory
+    static constexpr int kBuckets = 2 * kCap;  // open addressing, power of two
+    struct Key {
+        uintptr_t datastart = 0;
+        int32_t pitch = 0, width = 0, height = 0, rb = 0;
+    };
+    CUtensorMap* d = nullptr;   // device table
+    CUtensorMap* h = nullptr;   // pinned host mirror
+    Key* keys = nullptr;
+    int32_t* bucket = nullptr;  // entry index + 1, 0 = empty
+    int count = 0, uploaded = 0, device = -1;
+    uint32_t generation = 0;    // bumped when the table starts over: indices handed out before are void
+    cudaStream_t up = nullptr;
+    int reserve(int dev) {
+        if (device == dev && d) return CVGS_OK;
+        release();
+        CVGS_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), sizeof(CUtensorMap) * kCap));
+        CVGS_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h), sizeof(CUtensorMap) * kCap));
+        CVGS_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+        keys = new Key[kCap];
+        bucket = new int32_t[kBuckets]();
+        count = uploaded = 0;
+        device = dev;
+        return CVGS_OK;
+    }
+    void release() {  // errors ignored: also runs at thread exit, possibly after the context is gone
+        if (d) cudaFree(d);
+        if (h) cudaFreeHost(h);
+        if (up) cudaStreamDestroy(up);
+        delete[] keys;
+        delete[] bucket;
+        d = h = nullptr;
+        up = nullptr;
+        keys = nullptr;
+        bucket = nullptr;
+        count = uploaded = 0;
+        device = -1;
+    }
+    ~DevMapCache() { release(); }
+    // index of the map of (image, rb), encoding it on a miss; -1 when the driver refuses the geometry
+    int get(uintptr_t datastart, int pitch, int width, int height, int rb) {
+        size_t b = ((static_cast<size_t>(datastart >> 8) * 0x9E3779B97F4A7C15ull + static_cast<size_t>(rb) * 0xC2B2AE3D27D4EB4Full) >> 40) &
+                   (kBuckets - 1);
+        for (;; b = (b + 1) & (kBuckets - 1)) {
+            const int32_t e = bucket[b];
+            if (e == 0) break;
+            const Key& k = keys[e - 1];
+            if (k.datastart == datastart && k.rb == rb && k.pitch == pitch && k.width == width && k.height == height) return e - 1;
+        }
+        if (count == kCap) {  // start over; nothing in flight may still read the old entries
+            if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+            std::memset(bucket, 0, sizeof(int32_t) * kBuckets);
+            count = uploaded = 0;
+            ++generation;
+            return get(datastart, pitch, width, height, rb);
+        }
+        const int mis = static_cast<int>(datastart & 15);
+        if (tma_encode(&h[count], datastart - mis, mis + 3LL * width, height, pitch, rb) != CVGS_OK) return -1;
+        keys[count] = Key{datastart, pitch, width, height, rb};
+        bucket[b] = count + 1;
+        return count++;
+    }
+    // make every entry handed out so far usable by kernels launched from now on (any stream)
+    int flush() {
+        if (uploaded == count) return CVGS_OK;
+        CVGS_CUDA(cudaMemcpyAsync(d + uploaded, h + uploaded, sizeof(CUtensorMap) * static_cast<size_t>(count - uploaded),
+                                  cudaMemcpyHostToDevice, up));
+        CVGS_CUDA(cudaStreamSynchronize(up));
+        uploaded = count;
+        return CVGS_OK;
+    }
+};
+
 // Locate crop c (c.data valid) inside its parent image: byte offset within a map row, map row, and the pad word that
 // binds it to map `map_index` with row bytes rb.  The crop itself is not modified.
 inline bool tma_place_in_image(const DevCrop& c, uintptr_t datastart, int width, int height, int rb, int map_index,
@@ -1012,6 +1115,13 @@ inline int tma_launch_instance(const TmaParams& K, const Table& T, int device, c
     CVGS_CUDA(cudaLaunchKernelEx(&cfg, kernel, K, T));
     count_launch();
     return CVGS_OK;
+}
+
+// Coalesced frame groups: only the common geometry (IGNORE_AR, every plane used, planar float output) is coalesced.
+inline int tma_launch_multi(const TmaParams& K, const TmaMultiTable& T, int chain, int device, cudaStream_t stream) {
+    static_assert(sizeof(TmaParams) + sizeof(TmaMultiTable) <= 32 * 1024 - 256, "kernel parameters exceed 32 KB");
+    if (chain == CH_FMA_DIV) return tma_launch_instance<TmaMultiTable, CH_FMA_DIV, false>(K, T, device, stream);
+    return tma_launch_instance<TmaMultiTable, CH_GENERIC, false>(K, T, device, stream);
 }
 
 template <typename Table>

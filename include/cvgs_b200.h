@@ -310,6 +310,16 @@ int cvgs_b200_set_kernel_variant(int variant);
  * (cudaTriggerProgrammaticLaunchCompletion) must not be the direct producers of a source image.  The reference
  * has no equivalent (it launches plain kernels, executors.cuh:133-156).  Returns the previous value. */
 int cvgs_b200_set_overlap(int enable);
+/* Frame loops (cvgs_b200_preproc_launch_sequence_ex) with overlap enabled: when the argument sets are provably
+ * independent, carry the same pipeline apart from the output pointer, name their parent frames and have the common
+ * geometry (CV_8UC3 sources, IGNORE_AR, every plane used, NCHW float output), consecutive steps SHARE kernel launches:
+ * up to 512 crops of up to 32 argument sets per launch, each crop writing into its own set's tensor, one host thread,
+ * the caller's stream.  A 50-crop frame is 7.5 MB of traffic (~1.5 us of HBM time), less than one kernel launch costs
+ * the host and the GPU front end; ten frames per launch are bound by the GPU instead.  Results are identical.  Default
+ * 1 (on; CVGS_B200_SEQ_COALESCE=0 turns it off at load time); 0 = one launch per step as before, driven by several
+ * host threads.  The reference would express the same thing as one BatchRead over all the crops
+ * (batch_operations.cuh:222-229), which its template batch size caps at 255 planes.  Returns the previous value. */
+int cvgs_b200_set_coalesce(int enable);
 /* Number of kernel launches issued by this library on the calling thread so far. */
 int64_t cvgs_b200_launch_count(void);
 /* Diagnostics: host-side cost of the small-batch TMA launch path on the calling thread, accumulated in

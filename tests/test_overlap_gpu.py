@@ -194,10 +194,81 @@ def _sequence(lib, ws, d_imgs, outs, steps, stream):
     return lib.cvgs_b200_launch_count() - before, keep
 
 
-def test_frame_loop_over_several_host_threads(overlap_on):
+@pytest.fixture()
+def per_step_launches(overlap_on):
+    """cvgs_b200_set_coalesce(0): the frame loop launches once per step (helper threads) instead of sharing launches."""
+    prev = overlap_on.cvgs_b200_set_coalesce(0)
+    yield overlap_on
+    overlap_on.cvgs_b200_set_coalesce(prev)
+
+
+def test_frame_loop_shares_launches(overlap_on):
+    """Independent argument sets with the same pipeline: consecutive steps ride in shared launches (up to 512 crops of
+    up to 32 sets), every crop landing in its own set's tensor; results, ordering on the caller's stream and the
+    reduced launch count hold.  Sets of different sizes, more steps than sets (tensors are rewritten: write-after-
+    write hazards between launches), and a run long enough to wrap the in-flight window."""
+    lib = overlap_on
+    st = torch.cuda.Stream()
+    sizes = [50, 50, 7, 50, 120, 50, 1, 50, 33, 50, 50]
+    ws = [util.workload_c2(seed=740 + k, n=n, pitch=6144) for k, n in enumerate(sizes)]
+    d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
+    outs = [torch.full((len(w.rects), 3, 128, 64), float("nan"), device="cuda") for w in ws]
+    want = [util.run_oracle(w.image, w.rects, w.dsize, w.ops) for w in ws]
+    steps = len(ws) * 9 + 5
+    with torch.cuda.stream(st):
+        launches, keep = _sequence(lib, ws, d_imgs, outs, steps, st)
+        copies = [o.clone() for o in outs]
+    st.synchronize()
+    assert 0 < launches <= steps // 5, launches  # 511 crops per pass over the sets: about one launch per pass
+    for k, (o, c) in enumerate(zip(outs, copies)):
+        util.assert_bit_equal(o.cpu().numpy(), want[k], f"set {k}")
+        util.assert_bit_equal(c.cpu().numpy(), want[k], f"set {k}: copy queued after the loop")
+    # a second sequence on the same stream reuses the cached tensor maps
+    for o in outs:
+        o.fill_(float("nan"))
+    launches2, keep2 = _sequence(lib, ws, d_imgs, outs, len(ws), st)
+    st.synchronize()
+    assert launches2 <= 2
+    for k, o in enumerate(outs):
+        util.assert_bit_equal(o.cpu().numpy(), want[k], f"second sequence, set {k}")
+    del keep, keep2
+
+
+def test_frame_loop_shared_launch_c3_shape(overlap_on):
+    """224x224 planes (two column bands of different width) from three 4K frames in shared launches."""
+    lib = overlap_on
+    st = torch.cuda.Stream()
+    ws = [util.workload_c3(seed=760 + k, n=40) for k in range(3)]
+    d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
+    outs = [torch.full((40, 3, 224, 224), float("nan"), device="cuda") for _ in ws]
+    launches, keep = _sequence(lib, ws, d_imgs, outs, 6, st)
+    st.synchronize()
+    assert launches == 2
+    for k, (w, o) in enumerate(zip(ws, outs)):
+        util.assert_bit_equal(o.cpu().numpy(), util.run_oracle(w.image, w.rects, w.dsize, w.ops), f"set {k}")
+    del keep
+
+
+def test_frame_loop_declines_to_share_what_the_tma_kernel_cannot_take(overlap_on):
+    """A set whose frame pitch is not a multiple of 16 bytes cannot be staged by TMA: the group it falls into is
+    launched set by set (direct-gather kernel for that set), results unchanged."""
+    lib = overlap_on
+    st = torch.cuda.Stream()
+    ws = [util.workload_c2(seed=770 + k, n=20, frame=(640, 480), pitch=1920 if k != 2 else 1923) for k in range(5)]
+    d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
+    outs = [torch.full((20, 3, 128, 64), float("nan"), device="cuda") for _ in ws]
+    launches, keep = _sequence(lib, ws, d_imgs, outs, 10, st)
+    st.synchronize()
+    assert launches == 10
+    for k, (w, o) in enumerate(zip(ws, outs)):
+        util.assert_bit_equal(o.cpu().numpy(), util.run_oracle(w.image, w.rects, w.dsize, w.ops), f"set {k}")
+    del keep
+
+
+def test_frame_loop_over_several_host_threads(per_step_launches):
     """steps >= 16 with independent argument sets: the loop is split over helper threads and streams
     (include/cvgs_b200.h); every frame's result, the launch count and the ordering on the caller's stream hold."""
-    lib = overlap_on
+    lib = per_step_launches
     st = torch.cuda.Stream()
     ws = [util.workload_c2(seed=700 + k, n=50, pitch=6144) for k in range(7)]
     d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
@@ -230,8 +301,10 @@ def test_frame_loop_with_dependent_sets_stays_in_order(overlap_on):
     del keep
 
 
-def test_frame_loop_error_is_reported(overlap_on):
+@pytest.mark.parametrize("coalesce", [0, 1])
+def test_frame_loop_error_is_reported(overlap_on, coalesce):
     lib = overlap_on
+    lib.cvgs_b200_set_coalesce(coalesce)
     st = torch.cuda.Stream()
     ws = [util.workload_c2(seed=730 + k, n=10, frame=(640, 480), pitch=1920) for k in range(4)]
     d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
@@ -250,4 +323,5 @@ def test_frame_loop_error_is_reported(overlap_on):
     n_arr = (C.c_int32 * n)(*[10] * n)
     rc = lib.cvgs_b200_preproc_launch_sequence_ex(crops_pp, par_pp, n_arr, n_arr, pipes_pp, n, 400, st.cuda_stream)
     st.synchronize()
+    lib.cvgs_b200_set_coalesce(1)
     assert rc != 0 and b"pitch" in lib.cvgs_b200_last_error()
