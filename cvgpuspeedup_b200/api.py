@@ -41,11 +41,12 @@ class GpuMat:
     """Minimal cv::cuda::GpuMat stand-in: the wrapper only ever touches data/cols/rows/step
     (reference include/cvGPUSpeedup.cuh:36,42,69)."""
 
-    __slots__ = ("data", "cols", "rows", "step", "_owner", "datastart", "whole")
+    __slots__ = ("data", "cols", "rows", "step", "_owner", "datastart", "whole", "elem_size")
 
     def __init__(self, data: int, cols: int, rows: int, step: int, owner=None, datastart: Optional[int] = None,
-                 whole: Optional[Tuple[int, int]] = None):
+                 whole: Optional[Tuple[int, int]] = None, elem_size: int = 3):
         self.data, self.cols, self.rows, self.step, self._owner = int(data), int(cols), int(rows), int(step), owner
+        self.elem_size = int(elem_size)  # GpuMat::elemSize(): 3 for CV_8UC3, 4 for CV_8UC4, 6 / 8 for the 16-bit types
         # cv::cuda::GpuMat::datastart / locateROI(wholeSize, ofs): the image this header was cut from
         self.datastart = int(data) if datastart is None else int(datastart)
         self.whole = (int(cols), int(rows)) if whole is None else (int(whole[0]), int(whole[1]))
@@ -61,8 +62,8 @@ class GpuMat:
         """d_input(cv::Rect(x, y, w, h))"""
         if x < 0 or y < 0 or w <= 0 or h <= 0 or x + w > self.cols or y + h > self.rows:
             raise ValueError("ROI outside the image")
-        return GpuMat(self.data + y * self.step + 3 * x, w, h, self.step, owner=self._owner, datastart=self.datastart,
-                      whole=self.whole)
+        return GpuMat(self.data + y * self.step + self.elem_size * x, w, h, self.step, owner=self._owner,
+                      datastart=self.datastart, whole=self.whole, elem_size=self.elem_size)
 
 
 def _scalar3(s) -> Tuple[float, ...]:
@@ -310,9 +311,12 @@ def make_crops(mats: Sequence[GpuMat]):
     return arr
 
 
-def executeOperations(stream, *iops, fp_contract: int = FP_REFERENCE_FUSED, interp_mode: int = INTERP_FLOAT) -> None:
+def executeOperations(stream, *iops, fp_contract: int = FP_REFERENCE_FUSED, interp_mode: int = INTERP_FLOAT,
+                      replicas: Sequence[int] = ()) -> None:
     """cvGS::executeOperations(stream, resize(...), ops..., split(...)) :464-473: ONE kernel launch,
-    asynchronous on `stream`.  Raises CvgsError (the reference throws std::runtime_error)."""
+    asynchronous on `stream`.  Raises CvgsError (the reference throws std::runtime_error).
+    replicas: device pointers of further tensors (same layout, e.g. other GPUs' copies mapped into this process) that
+    receive the same planes from the same launch (cvgs_b200_preproc_launch_replicated)."""
     iops = list(_flatten(iops))
     if len(iops) < 2 or not isinstance(iops[0], (_Resize, _Warp)) or not isinstance(iops[-1], _Write):
         raise CvgsError("chain must start with resize(...) / warp(...) and end with split/splitT/write(...)")
@@ -339,10 +343,32 @@ def executeOperations(stream, *iops, fp_contract: int = FP_REFERENCE_FUSED, inte
     parents = (_abi.Parent * max(1, rs.used))()
     for i, m in enumerate(rs.crops[:rs.used]):
         parents[i].datastart, parents[i].whole_width, parents[i].whole_height = m.datastart, m.whole[0], m.whole[1]
+    if rs.src_type != _abi.CVGS_8UC3 and not (_abi.CVGS_NV12 <= rs.src_type <= _abi.CVGS_Y210):
+        # parents describe 3-byte pixels (the TMA-staged kernel's domain): other depths go without
+        _abi.check(lib.cvgs_b200_preproc_launch(crops, len(rs.crops), rs.used, C.byref(p), _stream_ptr(stream)))
+        return
     if _abi.CVGS_NV12 <= rs.src_type <= _abi.CVGS_Y210:  # whole frames: nothing to say about parents
         _abi.check(lib.cvgs_b200_preproc_launch(crops, len(rs.crops), rs.used, C.byref(p), _stream_ptr(stream)))
         return
+    if replicas:
+        reps = (C.c_void_p * len(replicas))(*[int(r) for r in replicas])
+        _abi.check(lib.cvgs_b200_preproc_launch_replicated(crops, parents, len(rs.crops), rs.used, C.byref(p), reps,
+                                                           len(replicas), _stream_ptr(stream)))
+        return
     _abi.check(lib.cvgs_b200_preproc_launch_ex(crops, parents, len(rs.crops), rs.used, C.byref(p), _stream_ptr(stream)))
+
+
+def device_view(ptr: int, shape, dtype_str: str = "<f4"):
+    """torch view (no copy, no ownership) of device memory somebody else allocated."""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": dtype_str, "data": (int(ptr), False),
+                                  "version": 2, "strides": None}
+    return torch.as_tensor(h, device="cuda")
 
 
 class CircularTensor:

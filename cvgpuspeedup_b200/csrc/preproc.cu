@@ -410,8 +410,10 @@ static int prepare_image_maps(DevCrop* dc, const cvgs_parent_t* parents, int use
 }
 
 // Shared by the batch entry points and the host-buffer entry point.
+// replicas / n_replicas: cvgs_b200_preproc_launch_replicated -- the tensor is written at out and at every replicas[d].
 static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* parents, int n_planes, int used,
-                               const cvgs_pipeline_t* pipe, float* out, cudaStream_t stream) {
+                               const cvgs_pipeline_t* pipe, float* out, cudaStream_t stream,
+                               void* const* replicas = nullptr, int n_replicas = 0) {
     if (int rc = validate_pipeline(pipe)) return rc;
     if (!out) return fail(CVGS_ERR_INVALID_VALUE, "output pointer is NULL");
     if (n_planes <= 0) return fail(CVGS_ERR_INVALID_VALUE, "n_planes must be positive");
@@ -453,7 +455,12 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
     const int sms = sm_count_of(device);
 
     const bool planes_out = pipe->out_layout == CVGS_OUT_PLANES;  // needs a device table of destinations: ring path
-    if (used <= kTmaParamCrops && !planes_out) {
+    if (n_replicas > 0) {
+        const bool fast = !P.band_test && P.used == P.n_planes && P.out.px_stride == 1 && !planes_out && !P.out.u8;
+        if (!fast || variant == 1 || n_replicas + 1 > kMaxDest)
+            return fail(CVGS_ERR_NOT_SUPPORTED, "replicated output: IGNORE_AR, every plane used, planar float tensors, at most 7 replicas");
+    }
+    if (used <= kTmaParamCrops && !planes_out && n_replicas == 0) {
         // small batch: descriptors (and tensor maps) ride in the kernel parameters -- no staging copy,
         // graph-capturable
         alignas(64) TmaParamTable tt;  // also serves as the image-mode table (its first maps / same crop array offset
@@ -506,7 +513,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         return launch_direct(P, &table, stream);
     }
 
-    if (used <= kTmaImageCrops && parents && variant != 1 && !planes_out) {
+    if (used <= kTmaImageCrops && parents && variant != 1 && !planes_out && n_replicas == 0) {
         // medium batch with named parent images: a few cached maps + the descriptors still fit the kernel
         // parameters (13 KB), so there is no staging copy in front of the kernel
         alignas(64) TmaImageTableL lt;
@@ -554,7 +561,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
                     if (int rc = fill_crop(crops[i], *pipe, i, hc[i])) return rc;
         }
     }
-    if (!use_tma && variant == 2) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
+    if (!use_tma && (variant == 2 || n_replicas > 0)) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
     if (planes_out) {
         // destination images, indexed [z][source channel] on the device (the channel reorder is applied here)
         const cvgs_plane_t* hp = static_cast<const cvgs_plane_t*>(pipe->out);
@@ -584,7 +591,18 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         // the descriptor copy sits between this kernel and its predecessor: plain stream order, no overlap
         K.G.pdl_wait = 1;
         overlap_forget(stream);
-        rc = tma_launch_kernel<TmaNoTable>(K, TmaNoTable{0}, chain, device, stream);
+        if (n_replicas > 0) {
+            K.n_dest = n_replicas + 1;
+            K.dest_delta[0] = 0;
+            for (int d = 0; d < n_replicas; ++d) {
+                const long long diff = reinterpret_cast<const char*>(replicas[d]) - reinterpret_cast<const char*>(out);
+                if (!replicas[d] || (diff & 3)) return fail(CVGS_ERR_INVALID_VALUE, "replica " + std::to_string(d) + ": NULL or not float-aligned");
+                K.dest_delta[d + 1] = diff / 4;
+            }
+            rc = tma_launch_replicated(K, chain, device, stream);
+        } else {
+            rc = tma_launch_kernel<TmaNoTable>(K, TmaNoTable{0}, chain, device, stream);
+        }
     } else {
         P.crops = r.crops_d(slot);
         overlap_forget(stream);
@@ -862,6 +880,46 @@ int cvgs_b200_preproc_launch_ex(const cvgs_crop_t* crops, const cvgs_parent_t* p
     if (!pipeline) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
     return preproc_launch_impl(crops, parents, n_planes, used, pipeline, static_cast<float*>(pipeline->out),
                                static_cast<cudaStream_t>(stream));
+}
+
+int cvgs_b200_preproc_launch_replicated(const cvgs_crop_t* crops, const cvgs_parent_t* parents, int32_t n_planes, int32_t used,
+                                        const cvgs_pipeline_t* pipeline, void* const* replicas, int32_t n_replicas,
+                                        void* stream) {
+    if (!pipeline) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
+    if (n_replicas < 0 || (n_replicas > 0 && !replicas)) return fail(CVGS_ERR_INVALID_VALUE, "bad replica list");
+    return preproc_launch_impl(crops, parents, n_planes, used, pipeline, static_cast<float*>(pipeline->out),
+                               static_cast<cudaStream_t>(stream), replicas, n_replicas);
+}
+
+// Peer-mapped device memory for the replicated launch: thin wrappers over cudaMalloc / cudaIpc* so that a host language
+// without CUDA bindings (and torch-free callers) can place one tensor per GPU and map the others' into its own process.
+int cvgs_b200_dev_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return fail(CVGS_ERR_INVALID_VALUE, "ptr is NULL");
+    CVGS_CUDA(cudaMalloc(ptr, static_cast<size_t>(bytes)));
+    return CVGS_OK;
+}
+int cvgs_b200_dev_free(void* ptr) {
+    CVGS_CUDA(cudaFree(ptr));
+    return CVGS_OK;
+}
+int cvgs_b200_ipc_export(void* ptr, void* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!ptr || !handle64) return fail(CVGS_ERR_INVALID_VALUE, "NULL argument");
+    cudaIpcMemHandle_t h;
+    CVGS_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    std::memcpy(handle64, &h, sizeof h);
+    return CVGS_OK;
+}
+int cvgs_b200_ipc_open(const void* handle64, void** ptr) {
+    if (!ptr || !handle64) return fail(CVGS_ERR_INVALID_VALUE, "NULL argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof h);
+    CVGS_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CVGS_OK;
+}
+int cvgs_b200_ipc_close(void* ptr) {
+    CVGS_CUDA(cudaIpcCloseMemHandle(ptr));
+    return CVGS_OK;
 }
 
 // Batched warp: descriptors ride in the kernel parameters, kWarpParamPlanes planes per launch.

@@ -72,12 +72,18 @@ struct TmaGeom {
                              // 0: the host proved independence, wait only before exiting (completion order)
 };
 
+constexpr int kMaxDest = 8;  // replicas of the output tensor one launch can write (this GPU's + peer-mapped ones)
 struct TmaParams {
     PreprocParams P;         // P.prog = unscaled chain (background values), P.crops = device table or nullptr
     DevProgram prog_img;     // chain for interpolated values (2^33 folded into its first op)
     float zh[3], zl[3];      // CH_FMA_DIV: 1/d = zh + zl per source channel (div_const.cpp)
     TmaGeom G;
     const CUtensorMap* maps; // device table (nullptr when the maps ride in the kernel parameters)
+    // PEER instantiation (cvgs_b200_preproc_launch_replicated): every value is stored n_dest times, at
+    // P.out.base + dest_delta[d] (floats; dest_delta[0] = 0) -- the same tensor on this GPU and, through peer-mapped
+    // pointers, on the other GPUs of the box, so that the gather of BASELINE config 5 rides on the kernel's own stores
+    int32_t n_dest;
+    long long dest_delta[kMaxDest];
 };
 
 // Descriptors that ride in the kernel parameters: NMAPS tensor maps + up to kTmaParamCrops crops.
@@ -366,7 +372,8 @@ struct StageBand {
 
 // GEN = false: the common geometry -- IGNORE_AR, every plane used, planar output.
 // GEN = true : aspect-ratio bands, unused planes, packed outputs.
-template <typename Table, int CHAIN, bool GEN>
+// PEER = true: every store goes to K.n_dest replicas of the output tensor (fast geometry only).
+template <typename Table, int CHAIN, bool GEN, bool PEER = false>
 __global__ void __launch_bounds__(kTmaThreads, kMaxResident)
 preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ Table T) {
     extern __shared__ uint8_t smem_raw[];
@@ -663,6 +670,18 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                                 const uint32_t b = P.out.u8 == 2 ? __float2uint_rz(v[c].y) : (uint32_t)round_sat_u8(v[c].y);
                                 ub[d] = (uint8_t)a;
                                 if (st1) ub1[d] = (uint8_t)b;
+                            }
+                        } else if (PEER) {
+                            const int q = 32 * p * pxs;
+#pragma unroll 1
+                            for (int d = 0; d < K.n_dest; ++d) {  // this GPU's tensor first, then the peers' over NVLink
+                                const long long dq = K.dest_delta[d] + q;
+                                st_cs_f32(s0 + dq, v[0].x);
+                                st_cs_f32(s1 + dq, v[1].x);
+                                st_cs_f32(s2 + dq, v[2].x);
+                                st_cs_f32_if(st1, t0 + dq, v[0].y);
+                                st_cs_f32_if(st1, t1 + dq, v[1].y);
+                                st_cs_f32_if(st1, t2 + dq, v[2].y);
                             }
                         } else {
                             const int q = 32 * p * pxs;
@@ -1089,12 +1108,12 @@ inline size_t tma_smem_bytes(const TmaGeom& G) {
     return static_cast<size_t>(kWarps) * G.slots * G.slot_bytes + kRingPad + 128;
 }
 
-template <typename Table, int CHAIN, bool GEN>
+template <typename Table, int CHAIN, bool GEN, bool PEER = false>
 inline int tma_launch_instance(const TmaParams& K, const Table& T, int device, cudaStream_t stream) {
     static thread_local size_t attr_set[64] = {};  // per device: dynamic shared memory opt-in already granted
     const size_t smem = tma_smem_bytes(K.G);
     const int slot = device & 63;
-    auto kernel = preproc_tma_kernel<Table, CHAIN, GEN>;
+    auto kernel = preproc_tma_kernel<Table, CHAIN, GEN, PEER>;
     if (smem > attr_set[slot]) {
         const size_t want = std::max<size_t>(smem, 112 * 1024);
         CVGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(want)));
@@ -1122,6 +1141,12 @@ inline int tma_launch_multi(const TmaParams& K, const TmaMultiTable& T, int chai
     static_assert(sizeof(TmaParams) + sizeof(TmaMultiTable) <= 32 * 1024 - 256, "kernel parameters exceed 32 KB");
     if (chain == CH_FMA_DIV) return tma_launch_instance<TmaMultiTable, CH_FMA_DIV, false>(K, T, device, stream);
     return tma_launch_instance<TmaMultiTable, CH_GENERIC, false>(K, T, device, stream);
+}
+
+// Replicated output (K.n_dest tensors): descriptors in global memory, common geometry only.
+inline int tma_launch_replicated(const TmaParams& K, int chain, int device, cudaStream_t stream) {
+    if (chain == CH_FMA_DIV) return tma_launch_instance<TmaNoTable, CH_FMA_DIV, false, true>(K, TmaNoTable{0}, device, stream);
+    return tma_launch_instance<TmaNoTable, CH_GENERIC, false, true>(K, TmaNoTable{0}, device, stream);
 }
 
 template <typename Table>

@@ -239,6 +239,26 @@ typedef struct cvgs_parent {
 int cvgs_b200_preproc_launch_ex(const cvgs_crop_t* crops, const cvgs_parent_t* parents, int32_t n_planes,
                                 int32_t used, const cvgs_pipeline_t* pipeline, void* stream);
 
+/* The same launch writing its tensor more than once: at pipeline->out and at each of replicas[0 .. n_replicas) (at most
+ * 7), all with the layout the pipeline describes.  Meant for BASELINE config 5 -- crops sharded over the GPUs of one box,
+ * every GPU ending with the whole [N][3][H][W] tensor: replicas are the other GPUs' tensors mapped into this process
+ * (cvgs_b200_ipc_open), so the kernel's own stores travel over NVLink while it computes and no gather collective follows.
+ * The reference has no multi-GPU path (fkl/.../execution_model/parallel_architectures.h:20-30 only names architectures);
+ * what makes the split legal is that batch planes are independent (batch_operations.cuh:222-229).
+ * Common geometry only (CV_8UC3, IGNORE_AR, used == n_planes, NCHW / CNHW float); other forms return
+ * CVGS_ERR_NOT_SUPPORTED.  Ordering between GPUs is the caller's (a barrier / stream-ordered collective after the launch). */
+int cvgs_b200_preproc_launch_replicated(const cvgs_crop_t* crops, const cvgs_parent_t* parents, int32_t n_planes,
+                                        int32_t used, const cvgs_pipeline_t* pipeline, void* const* replicas,
+                                        int32_t n_replicas, void* stream);
+/* Device memory that can be mapped into the other processes of the box (one process per GPU): cudaMalloc / cudaFree and
+ * cudaIpcGetMemHandle / cudaIpcOpenMemHandle (lazy peer access) / cudaIpcCloseMemHandle behind plain pointers.
+ * handle64 = 64 bytes, to be exchanged between the processes by any means. */
+int cvgs_b200_dev_alloc(void** ptr, uint64_t bytes);
+int cvgs_b200_dev_free(void* ptr);
+int cvgs_b200_ipc_export(void* ptr, void* handle64);
+int cvgs_b200_ipc_open(const void* handle64, void** ptr);
+int cvgs_b200_ipc_close(void* ptr);
+
 /* ------------------------------------------------------------------------------------------
  * Batched affine / perspective warp in front of the same chain.  Replaces
  *   cvGS::executeOperations(stream, cvGS::warp<WT, InputType[, N]>(images, matrices, dstSize[, used, default]), ops..., write)

@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <thread>
 
 #include <fused_kernel/fused_kernel.cuh>
 #include <fused_kernel/core/data/circular_tensor.cuh>
@@ -153,6 +154,129 @@ int FKREF_CAT(fkref_preproc_sequence_, FKREF_BATCH)(const void* const* const* pt
         return -1;
     }
 }
+
+// The same loop driven by `threads` host threads, one stream each (argument set s belongs to thread s % threads), forked
+// from / joined into `stream` with events: the launch strategy of the product's multi-threaded frame loop, so that
+// bench.py can compare kernels under the same strategy.
+int FKREF_CAT(fkref_preproc_sequence_mt_, FKREF_BATCH)(const void* const* const* ptrs, const int* const* ws,
+                  const int* const* hs, const int* const* pitches, int used, int dst_w, int dst_h, int aspect_mode,
+                  const float* bg, int swap_rb, const float* mul, const float* sub, const float* div,
+                  float* const* outs, int n_sets, int steps, void* stream, int threads) {
+    constexpr int kMax = 8;
+    static cudaStream_t st[kMax] = {};
+    static cudaEvent_t done[kMax] = {}, start = nullptr;
+    if (threads < 1 || threads > kMax) { g_err = "fkref: 1..8 threads"; return -1; }
+    int device = 0;
+    cudaGetDevice(&device);
+    if (!start) {
+        cudaEventCreateWithFlags(&start, cudaEventDisableTiming);
+        for (int i = 0; i < kMax; ++i) {
+            cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+        }
+    }
+    cudaEventRecord(start, (cudaStream_t)stream);
+    int rcs[kMax] = {};
+    std::string errs[kMax];
+    std::thread pool[kMax];
+    for (int w = 0; w < threads; ++w) {
+        pool[w] = std::thread([&, w] {
+            cudaSetDevice(device);
+            cudaStreamWaitEvent(st[w], start, 0);
+            try {
+                for (int i = 0; i < steps && rcs[w] == 0; ++i) {
+                    const int s = i % n_sets;
+                    if (s % threads != w) continue;
+                    rcs[w] = dispatch<uchar3, FKREF_BATCH>(ptrs[s], ws[s], hs[s], pitches[s], used, dst_w, dst_h, aspect_mode, bg,
+                                                           swap_rb, mul, sub, div, outs[s], st[w]);
+                }
+            } catch (const std::exception& e) {
+                errs[w] = e.what();
+                rcs[w] = -1;
+            }
+            cudaEventRecord(done[w], st[w]);
+        });
+    }
+    int rc = 0;
+    for (int w = 0; w < threads; ++w) {
+        pool[w].join();
+        cudaStreamWaitEvent((cudaStream_t)stream, done[w], 0);
+        if (rcs[w] != 0 && rc == 0) { rc = rcs[w]; g_err = errs[w]; }
+    }
+    return rc;
+}
+
+#ifdef FKREF_CT
+// fk::CircularTensor<float, 3, BATCH, ORDER, Standard>::update (circular_tensor.cuh:111-146) with the pipeline of the
+// cvGS wrapper (include/cvGPUSpeedup.cuh:600-627): Read<PerThreadRead<_2D, uchar3>> [-> Resize<INTER_LINEAR> when the
+// frame is not plane-sized] -> SaturateCast<uchar3, float3> / the resize's float3 -> [RGB2BGR] -> Mul -> Sub -> Div ->
+// TensorSplit<float3>.  BATCH is a template parameter: depths 4 and 16 are instantiated.
+}  // extern "C"
+namespace {
+struct CtBase {
+    virtual ~CtBase() {}
+    virtual int update(const void* data, int w, int h, int pitch, int swap, const float* mul, const float* sub, const float* div,
+                       cudaStream_t s) = 0;
+    virtual float* data() = 0;
+    virtual size_t bytes() = 0;
+};
+template <int BATCH, fk::CircularTensorOrder ORDER>
+struct CtImpl : CtBase {
+    fk::CircularTensor<float, 3, BATCH, ORDER, fk::ColorPlanes::Standard> t;
+    int W, H;
+    CtImpl(int w, int h) : t((uint)w, (uint)h), W(w), H(h) {}
+    float* data() override { return t.ptr().data; }
+    size_t bytes() override { return t.sizeInBytes(); }
+    int update(const void* data, int w, int h, int pitch, int swap, const float* mul, const float* sub, const float* div,
+               cudaStream_t s) override {
+        const fk::RawPtr<fk::_2D, uchar3> img{ (uchar3*)data, { (uint)w, (uint)h, (uint)pitch } };
+        const auto mulOp = fk::Binary<fk::Mul<float3>>{ float3{ mul[0], mul[1], mul[2] } };
+        const auto subOp = fk::Binary<fk::Sub<float3>>{ float3{ sub[0], sub[1], sub[2] } };
+        const auto divOp = fk::Binary<fk::Div<float3>>{ float3{ div[0], div[1], div[2] } };
+        const auto wrOp = fk::Write<fk::TensorSplit<float3>>{ t.ptr() };
+        const auto swapOp = fk::Unary<fk::ColorConversion<fk::COLOR_RGB2BGR, float3, float3>>{};
+        if (w == W && h == H) {
+            const auto rd = fk::Read<fk::PerThreadRead<fk::_2D, uchar3>>{ { img } };
+            const auto cast = fk::Unary<fk::SaturateCast<uchar3, float3>>{};
+            if (swap) t.update(s, rd, cast, swapOp, mulOp, subOp, divOp, wrOp);
+            else t.update(s, rd, cast, mulOp, subOp, divOp, wrOp);
+        } else {
+            const auto rd = fk::Resize<fk::INTER_LINEAR>::build(fk::Read<fk::PerThreadRead<fk::_2D, uchar3>>{ { img } }, fk::Size(W, H));
+            if (swap) t.update(s, rd, swapOp, mulOp, subOp, divOp, wrOp);
+            else t.update(s, rd, mulOp, subOp, divOp, wrOp);
+        }
+        return 0;
+    }
+};
+}  // namespace
+extern "C" {
+// order: 0 NewestFirst, 1 OldestFirst.  Returns a handle or NULL (unsupported depth).
+void* fkref_ct_create(int batch, int order, int w, int h) {
+    try {
+        using O = fk::CircularTensorOrder;
+        if (batch == 16 && order == 0) return new CtImpl<16, O::NewestFirst>(w, h);
+        if (batch == 16 && order == 1) return new CtImpl<16, O::OldestFirst>(w, h);
+        if (batch == 4 && order == 0) return new CtImpl<4, O::NewestFirst>(w, h);
+        if (batch == 4 && order == 1) return new CtImpl<4, O::OldestFirst>(w, h);
+        g_err = "fkref_ct: depth 4 or 16";
+    } catch (const std::exception& e) {
+        g_err = e.what();
+    }
+    return nullptr;
+}
+int fkref_ct_update(void* h, const void* data, int w, int hgt, int pitch, int swap_rb, const float* mul, const float* sub,
+                    const float* div, void* stream) {
+    try {
+        return static_cast<CtBase*>(h)->update(data, w, hgt, pitch, swap_rb, mul, sub, div, (cudaStream_t)stream);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+float* fkref_ct_data(void* h) { return static_cast<CtBase*>(h)->data(); }
+unsigned long long fkref_ct_bytes(void* h) { return static_cast<CtBase*>(h)->bytes(); }
+void fkref_ct_destroy(void* h) { delete static_cast<CtBase*>(h); }
+#endif
 
 #ifdef FKREF_16BIT
 // The same chain on CV_16UC3 (pixel_type 18, ushort3) and CV_16SC3 (19, short3) sources.

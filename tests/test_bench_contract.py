@@ -29,7 +29,7 @@ def test_bench_line_has_the_contract_keys():
     c = d["cpu_baseline"]
     assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
-    # value = crops of the timed region / its duration; launches = one per frame
+    # value = crops of the timed region / its duration; launches: at least one, at most one per frame
     crops = d["config"]["crops_per_step"] * d["steps"]
     assert abs(d["value"] - crops / (d["ms_per_step"] * d["steps"] * 1e-3)) / d["value"] < 1e-6
-    assert d["gpu_launches"] == d["config"]["frames_per_step"] * d["steps"]
+    assert 0 < d["gpu_launches"] <= d["config"]["frames_per_step"] * d["steps"]

@@ -96,3 +96,61 @@ def test_random_depths_sizes_and_orders(seed):
     util.assert_bit_equal(ct.data().cpu().numpy().reshape(-1), want, f"seed {seed}: {W}x{H} depth {B} order {order} mode {mode}")
     lib.oracle_ct_destroy(o)
     ct.close()
+
+
+def _fkref_ct():
+    import os
+    path = os.path.join(util.ROOT, "oracle", "_ref", "libfkref_ct.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libfkref_ct.so not built (needs /root/reference at build time)")
+    ref = C.CDLL(path)
+    ref.fkref_ct_create.restype = C.c_void_p
+    ref.fkref_ct_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    ref.fkref_ct_update.restype = C.c_int
+    ref.fkref_ct_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                    C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]
+    ref.fkref_ct_data.restype = C.c_void_p
+    ref.fkref_ct_data.argtypes = [C.c_void_p]
+    ref.fkref_ct_bytes.restype = C.c_ulonglong
+    ref.fkref_ct_bytes.argtypes = [C.c_void_p]
+    ref.fkref_ct_destroy.argtypes = [C.c_void_p]
+    return ref
+
+
+@pytest.mark.parametrize("order", [_abi.CT_NEWEST_FIRST, _abi.CT_OLDEST_FIRST])
+@pytest.mark.parametrize("depth,shape", [(4, ((96, 64), (200, 120))), (4, ((64, 48), (64, 48))), (16, ((160, 90), (640, 360)))])
+def test_three_way_against_the_reference_kernel(order, depth, shape):
+    """fk::CircularTensor<float, 3, BATCH, ORDER, Standard>::update instantiated from the reference's own headers
+    (oracle/_ref/libfkref_ct.so; circular_tensor.cuh:111-146), this library's kernel and the oracle state machine on
+    the same frames: bit-equal tensors after every update (resize + RGB2BGR + mul/sub/div, and the plain
+    SaturateCast read when the frame is plane-sized)."""
+    ref = _fkref_ct()
+    (W, H), (fw, fh) = shape
+    h = ref.fkref_ct_create(depth, order, W, H)
+    assert h
+    assert ref.fkref_ct_bytes(h) == 4 * 3 * depth * W * H
+    lib = util.oracle_lib()
+    o = lib.oracle_ct_create(W, H, 3, depth, order, _abi.CT_STANDARD)
+    ct = cvgs.CircularTensor(W, H, depth, order, _abi.CT_STANDARD)
+    ref_view = cvgs.api.device_view(ref.fkref_ct_data(h), (depth, 3, H, W))
+    ref_view.zero_()  # the reference leaves a new tensor uninitialised; ours and the oracle start from zeros
+    rng = np.random.default_rng(40 + depth)
+    p = util.make_pipeline((W, H), util.OPS_C3)
+    ops = [cvgs.cvtColor(), cvgs.multiply((1 / 255.0,) * 3), cvgs.subtract(util._MEAN), cvgs.divide(util._STD)]
+    f3 = lambda v: (C.c_float * 3)(*v)  # noqa: E731
+    mul, sub, div = f3((1 / 255.0,) * 3), f3(util._MEAN), f3(util._STD)
+    st = torch.cuda.current_stream().cuda_stream
+    for i in range(depth + 3):
+        img = util.make_image(rng, fw, fh)
+        d = torch.from_numpy(img).cuda().view(fh, fw, 3)
+        assert lib.oracle_ct_update(o, util.host_crops(img, [(0, 0, fw, fh)]), C.byref(p), 0) == 0
+        ct.update(None, cvgs.GpuMat.from_tensor(d), *ops)
+        assert ref.fkref_ct_update(h, d.data_ptr(), fw, fh, 3 * fw, 1, mul, sub, div, st) == 0
+        torch.cuda.synchronize()
+        if i >= depth - 1:  # until the ring has wrapped, the reference's temp tensor holds uninitialised planes
+            want = np.ctypeslib.as_array(lib.oracle_ct_data(o), shape=(depth, 3, H, W))
+            util.assert_bit_equal(ct.data().cpu().numpy(), want, f"update {i}: ours vs oracle")
+            util.assert_bit_equal(ref_view.cpu().numpy(), want, f"update {i}: reference kernel vs oracle")
+    lib.oracle_ct_destroy(o)
+    ct.close()
+    ref.fkref_ct_destroy(h)

@@ -15,7 +15,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-from cvgpuspeedup_b200 import _abi  # noqa: E402  (struct layouts are those of include/cvgs_b200.h)
+from cvgpuspeedup_b200 import _abi, marshal  # noqa: E402  (struct layouts are those of include/cvgs_b200.h)
 
 _ORACLE = None
 
@@ -133,8 +133,7 @@ def workload_c3(seed=3, n=256, frame=(3840, 2160), dsize=(224, 224), lo=224, hi=
     return Workload("c3", img, fw, fh, rects, dsize, OPS_C3)
 
 
-_KIND = {"mul": _abi.OP_MUL, "sub": _abi.OP_SUB, "div": _abi.OP_DIV, "add": _abi.OP_ADD, "reorder": _abi.OP_REORDER,
-         "add_alpha": _abi.OP_ADD_ALPHA, "drop_alpha": _abi.OP_DROP_ALPHA, "gray": _abi.OP_GRAY}
+from cvgpuspeedup_b200.marshal import OP_KINDS as _KIND, make_pipeline  # noqa: E402,F401
 
 
 def out_channels(src_type, ops) -> int:
@@ -143,30 +142,6 @@ def out_channels(src_type, ops) -> int:
     for k, _ in ops:
         nc = {"add_alpha": 4, "drop_alpha": 3, "gray": 1}.get(k, nc)
     return nc
-
-
-def make_pipeline(dsize, ops, aspect=_abi.IGNORE_AR, background=(0, 0, 0), fp_contract=_abi.FP_REFERENCE_FUSED,
-                  interp_mode=_abi.INTERP_FLOAT, layout=_abi.OUT_NCHW, out_ptr=0, plane_stride=0,
-                  src_type=_abi.CVGS_8UC3, dst_type=0, row_pitch=0, yuv_standard=0, u8_cast=0) -> _abi.Pipeline:
-    p = _abi.Pipeline()
-    p.src_type = src_type
-    p.dst_width, p.dst_height = dsize
-    p.aspect_mode, p.interp_mode, p.fp_contract = aspect, interp_mode, fp_contract
-    for c in range(len(background)):
-        p.background[c] = background[c]
-    p.n_ops = len(ops)
-    for i, (k, v) in enumerate(ops):
-        p.ops[i].kind = _KIND[k]
-        for c in range(len(v)):
-            if k in ("reorder", "gray"):
-                p.ops[i].perm[c] = v[c]
-            else:
-                p.ops[i].v[c] = v[c]
-    p.out_layout, p.out, p.out_plane_stride = layout, out_ptr, plane_stride
-    p.dst_type, p.out_row_pitch = dst_type, row_pitch
-    p.yuv_standard = yuv_standard
-    p.u8_cast = u8_cast
-    return p
 
 
 def px_bytes_of(src_type) -> int:
@@ -193,21 +168,12 @@ def out_shape(n_planes, dsize, layout, plane_stride=0, nc=3):
 def host_crops(image: np.ndarray, rects: Sequence[Rect], base_ptr: int | None = None, px_bytes: int = 3):
     """Crop descriptors pointing into `image` (host) or into a device copy at base_ptr with the same pitch.
     px_bytes = 3 for CV_8UC3, 6 for the 16-bit sources."""
-    pitch = image.shape[1]
-    base = image.ctypes.data if base_ptr is None else base_ptr
-    arr = (_abi.Crop * max(1, len(rects)))()
-    for i, (x, y, w, h) in enumerate(rects):
-        arr[i].data, arr[i].width, arr[i].height, arr[i].pitch, arr[i].reserved = base + y * pitch + px_bytes * x, w, h, pitch, 0
-    return arr
+    return marshal.crop_array(image.ctypes.data if base_ptr is None else base_ptr, image.shape[1], rects, px_bytes)
 
 
 def host_parents(image: np.ndarray, width: int, height: int, n: int, base_ptr: int | None = None):
     """cvgs_parent_t per crop: every crop was cut from the one image (GpuMat::datastart + locateROI)."""
-    base = image.ctypes.data if base_ptr is None else base_ptr
-    arr = (_abi.Parent * max(1, n))()
-    for i in range(n):
-        arr[i].datastart, arr[i].whole_width, arr[i].whole_height = base, width, height
-    return arr
+    return marshal.parent_array(image.ctypes.data if base_ptr is None else base_ptr, width, height, n)
 
 
 def run_oracle(image, rects, dsize, ops, n_planes=None, used=None, nthreads=0, fill=np.nan, **pipe_kw) -> np.ndarray:
