@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcvgs_b200.so")
+LIB_PATH = os.environ.get("CVGS_B200_LIB") or os.path.join(_HERE, "libcvgs_b200.so")  # override: diagnostic builds
 
 MAX_OPS = 8
 

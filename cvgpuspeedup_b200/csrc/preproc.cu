@@ -651,7 +651,11 @@ static int launch_multi(const MultiSet* sets, int G, const cvgs_pipeline_t* pipe
         }
         K.P = P;
         K.P.out.base = nullptr;  // every plane goes through out_base[]
-        if (!tma_plan(P, mt.c, total, total, sms, true, 1, K.G)) return kMultiDeclined;
+        static const int grid_div = [] {  // tuning override (profiling)
+            const char* e = std::getenv("CVGS_B200_MULTI_GRID_DIV");
+            return e ? std::max(1, std::atoi(e)) : 1;
+        }();
+        if (!tma_plan(P, mt.c, total, total, sms, true, 1, K.G, true, grid_div)) return kMultiDeclined;
         const uint32_t gen = mc.generation;
         const int TWp = std::min(32 * K.G.NPB, P.W);
         bool restart = false;
@@ -663,7 +667,7 @@ static int launch_multi(const MultiSet* sets, int G, const cvgs_pipeline_t* pipe
                 const cvgs_parent_t& p = sets[g].parents[i];
                 DevCrop& c = mt.c[z];
                 if (!p.datastart || p.whole_width <= 0 || p.whole_height <= 0) return kMultiDeclined;
-                const int rb = rb_class(band_row_bytes(TWp, c.fx));
+                const int rb = rb_class(band_row_bytes(TWp, c.fx), true);
                 if (rb == 0 || 4 * rb + kSlotHeader > K.G.slot_bytes) return kMultiDeclined;
                 const uintptr_t ds = reinterpret_cast<uintptr_t>(p.datastart);
                 int idx = last_idx;
@@ -1188,13 +1192,21 @@ static int sequence_coalesced(const cvgs_crop_t* const* crops, const cvgs_parent
     int last_early = 0, L = 0;
     bool force_early = true;  // whatever precedes the sequence on the stream is unknown
     MultiSet ms[kMultiGroups];
+    static const int max_groups = [] {  // tuning overrides (profiling)
+        const char* e = std::getenv("CVGS_B200_MULTI_GROUPS");
+        return e ? std::max(1, std::min(kMultiGroups, std::atoi(e))) : kMultiGroups;
+    }();
+    static const int max_crops = [] {
+        const char* e = std::getenv("CVGS_B200_MULTI_CROPS");
+        return e ? std::max(1, std::min(kMultiCrops, std::atoi(e))) : kMultiCrops;
+    }();
     overlap_forget(stream);
     for (int i = 0; i < steps;) {
         int G = 0, total = 0;
         bool hazard = force_early || L - last_early >= StreamTrack::kWindow;
-        while (i + G < steps && G < kMultiGroups && G < n_sets) {
+        while (i + G < steps && G < max_groups && G < n_sets) {
             const int s = (i + G) % n_sets;
-            if (total + n_planes[s] > kMultiCrops) break;
+            if (G > 0 && total + n_planes[s] > max_crops) break;
             ms[G] = MultiSet{crops[s], parents[s], n_planes[s], static_cast<float*>(pipelines[s]->out)};
             if (last_writer[static_cast<size_t>(s)] >= last_early) hazard = true;
             total += n_planes[s];

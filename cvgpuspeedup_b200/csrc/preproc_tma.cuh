@@ -53,6 +53,31 @@ constexpr float kPreScale = 8589934592.0f;              // 2^33  = 2^133 / 2^100
 constexpr uint32_t kRowFill = 0xFFFFFFF0u;  // RowTap::a: row lies outside the image band -> background
 constexpr uint32_t kRowSkip = 0xFFFFFFFFu;  // RowTap::a: row is below the plane (or past the warp's range) -> nothing to do
 
+// Division of n < 2^31 by a launch constant: q = umulhi(n, mul) >> shr (mul == 0: divisor 1).  Exact on that range
+// (round-up method: p = 31 + ceil(log2 d), mul = ceil(2^p / d)); the warps divide item and cost indices by the plan's
+// constants in their prologues, where a 32-bit hardware-less division costs ~40 instructions each.
+struct FastDiv {
+    uint32_t mul, shr;
+};
+inline FastDiv fast_div_make(uint32_t d) {
+    FastDiv f{0u, 0u};
+    if (d > 1) {
+        uint32_t l = 0;
+        while ((1ull << l) < d) ++l;
+        const uint32_t p = 31 + l;
+        f.mul = static_cast<uint32_t>(((1ull << p) + d - 1) / d);
+        f.shr = p - 32;
+    }
+    return f;
+}
+__host__ __device__ __forceinline__ uint32_t fast_div(uint32_t n, FastDiv f) {
+#ifdef __CUDA_ARCH__
+    return f.mul ? __umulhi(n, f.mul) >> f.shr : n;
+#else
+    return f.mul ? static_cast<uint32_t>((static_cast<unsigned long long>(n) * f.mul) >> 32) >> f.shr : n;
+#endif
+}
+
 struct TmaGeom {
     int32_t NPB;             // 32-column groups per band (1..kMaxNP); band width TW = 32 * NPB
     int32_t HP;              // row pairs per plane = ceil(H / 2)
@@ -70,6 +95,7 @@ struct TmaGeom {
     int32_t explicit_prescale;  // 1: the kernel multiplies by 2^33 itself (no op to fold it into)
     int32_t pdl_wait;        // 1: wait for the preceding kernel before the first global access (stream order);
                              // 0: the host proved independence, wait only before exiting (completion order)
+    FastDiv d_w_crop, d_NPB, d_np_last, d_items_per_crop, d_HP;  // divisions by the fields of those names
 };
 
 constexpr int kMaxDest = 8;  // replicas of the output tensor one launch can write (this GPU's + peer-mapped ones)
@@ -122,6 +148,22 @@ struct __align__(16) RowTap {
 };
 constexpr uint32_t kTapClamp = 1u << 30;   // interpolation.cuh:73: y2_read == y1, both taps read the same source row
 constexpr int kTapBlock = 8;               // items per table block; the table holds two blocks (consumers lag <= kMaxSlots)
+// What the warp's k-th item needs, derived once per kTapBlock items by the lanes in parallel (compute_taps) and read
+// back by the consumer loop (first 32 bytes) and by the staging code (last 16 bytes): nothing about an item's rows
+// is recomputed in the per-item code.
+struct __align__(16) ItemRec {
+    uint32_t a0;     // shared-memory offsets from the slot's data of the two source rows output row 0 taps: lo16 upper, hi16
+                     // lower (multiples of 64: staged row bytes are).  Bits 0..3 of the word are flags (kRec*)
+    uint32_t a1;     // same for output row 1 (a row without image data borrows the other row's: its values are replaced / not stored)
+    int32_t y0, y1;  // tensor-map rows of the boxes of output rows 0 / 1; < 0: nothing to stage
+    float wy0x, wy0y, wy1x, wy1y;  // vertical weights x 2^100: (y2 - sy) of rows 0 / 1, (sy - y1) of rows 0 / 1
+};
+constexpr uint32_t kRecRow1 = 1u;     // output row 1 exists (odd H: the last pair has one row)
+constexpr uint32_t kRecImg0 = 2u;     // output row 0 / 1 receives image data (else background)
+constexpr uint32_t kRecImg1 = 4u;
+constexpr uint32_t kRecNewBand = 8u;  // first item of a (plane, band) in the warp's range: the staging code re-derives its band state
+constexpr uint32_t kRecOffMask = 0xffc0u;
+static_assert(sizeof(ItemRec) == 32, "ItemRec layout");
 
 // DevCrop::pad of a TMA launch: bits 0..15 = smem row bytes of this crop's box, bits 16..31 = tensor map index
 __host__ __device__ __forceinline__ int32_t crop_row_bytes(const DevCrop& c) { return c.pad & 0xFFFF; }
@@ -268,10 +310,10 @@ struct ItemCursor {
     int z, txi, jp, left;
     // first item whose cumulative cost reaches w (cost counted in column groups from the start of the launch)
     static __device__ __forceinline__ int item_at(const TmaGeom& G, uint32_t w) {
-        const uint32_t z = w / (uint32_t)G.w_crop;
+        const uint32_t z = fast_div(w, G.d_w_crop);
         const uint32_t r = w - z * (uint32_t)G.w_crop;
-        const uint32_t in_crop = r < (uint32_t)G.w_full ? r / (uint32_t)G.NPB
-                                                          : (uint32_t)((G.tiles_x - 1) * G.HP) + (r - (uint32_t)G.w_full) / (uint32_t)G.np_last;
+        const uint32_t in_crop = r < (uint32_t)G.w_full ? fast_div(r, G.d_NPB)
+                                                          : (uint32_t)((G.tiles_x - 1) * G.HP) + fast_div(r - (uint32_t)G.w_full, G.d_np_last);
         return (int)(z * (uint32_t)G.items_per_crop + in_crop);
     }
     __device__ __forceinline__ void init(const TmaGeom& G, int g) {
@@ -281,9 +323,9 @@ struct ItemCursor {
         const int i0 = item_at(G, w0);
         const int i1 = g + 1 == G.grid * kWarps ? G.total_items : item_at(G, w1);
         left = i1 - i0;
-        z = i0 / G.items_per_crop;
+        z = (int)fast_div((uint32_t)i0, G.d_items_per_crop);
         const int rem = i0 - z * G.items_per_crop;
-        txi = rem / G.HP;
+        txi = (int)fast_div((uint32_t)rem, G.d_HP);
         jp = rem - txi * G.HP;
     }
     __device__ __forceinline__ void next(const TmaGeom& G) {
@@ -363,22 +405,24 @@ __device__ __forceinline__ void apply_program_pair(const DevProgram& prog, float
 
 // What staging an item needs to know about its (crop, band); recomputed only when the band changes.
 struct StageBand {
-    int z, txi;
-    bool ok;               // the band receives image data at all
     int32_t c0, rb;        // box start coordinate, staged row bytes
-    int32_t y0;            // map row of the crop's first row
     const CUtensorMap* map;
 };
 
 // GEN = false: the common geometry -- IGNORE_AR, every plane used, planar output.
 // GEN = true : aspect-ratio bands, unused planes, packed outputs.
 // PEER = true: every store goes to K.n_dest replicas of the output tensor (fast geometry only).
-template <typename Table, int CHAIN, bool GEN, bool PEER = false>
-__global__ void __launch_bounds__(kTmaThreads, kMaxResident)
+// MAXNP: 32-column groups per band the instantiation is compiled for.  An instantiation for planes of at most 64 columns
+// (two groups: 78 registers, six CTAs per SM instead of five) was measured on the 50-crop frames and gained nothing
+// (1.81 against 1.80 us per frame: that workload is bound by DRAM traffic), so only kMaxNP is built.
+constexpr int kNarrowNP = 2;
+constexpr int kNarrowResident = 6;
+template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP>
+__global__ void __launch_bounds__(kTmaThreads, MAXNP <= kNarrowNP ? kNarrowResident : kMaxResident)
 preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ Table T) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[kWarps * kMaxSlots];
-    __shared__ RowTap tap_table[kWarps][2 * 2 * kTapBlock];
+    __shared__ ItemRec rec_table[kWarps][2 * kTapBlock];
 
     const PreprocParams& P = K.P;
     const TmaGeom& G = K.G;
@@ -403,11 +447,10 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
 
     ItemCursor cc;  // item being computed
     cc.init(G, blockIdx.x * kWarps + warp);
-    ItemCursor ic = cc;  // item being staged (nslots ahead)
     const int first_item = cc.z * G.items_per_crop + cc.txi * G.HP + cc.jp;  // launch-wide index of this warp's first item
     const int n_items = cc.left;
-    uint32_t taps = smem_u32(&tap_table[warp][0]);
-    asm volatile("" : "+r"(taps));
+    uint32_t recs = smem_u32(&rec_table[warp][0]);
+    asm volatile("" : "+r"(recs));
 
     // chain constants of the specialised shape v = fma(v, ca, cb) / cd  (source-channel order)
     float ca[3], cb[3], zh[3], zl[3];
@@ -429,7 +472,8 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
     const long long oc1 = (long long)P.prog.dst_chan[1] * P.out.c_stride;
     const long long oc2 = (long long)P.prog.dst_chan[2] * P.out.c_stride;
     const int pxs = GEN ? P.out.px_stride : 1;
-    const int row_step = W * pxs;  // floats between vertically adjacent pixels
+    int row_step = W * pxs;  // floats between vertically adjacent pixels
+    if (!GEN) asm volatile("" : "+r"(row_step));  // in a register, not re-read from the parameters per item
 
     // Everything below reads source images and writes the output tensor: order it after the preceding kernel
     // unless the host proved the two independent (then only completion is ordered, at the end).
@@ -438,7 +482,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         // Tensor maps that reached global memory through a host copy must be acquired for the TMA proxy before
         // their first use by this thread (once per map: the fence also drops the descriptor cache).
         const int i_last = (cc.z * G.items_per_crop + cc.txi * G.HP + cc.jp) + cc.left - 1;
-        const int z_last = i_last / G.items_per_crop;
+        const int z_last = (int)fast_div((uint32_t)i_last, G.d_items_per_crop);
         for (int z = cc.z; z <= z_last; ++z) {
             if (GEN && z >= P.used) break;
             const CUtensorMap* map = tma_map_of<Table>(K, T, tma_crop_of<Table>(K, T, z));
@@ -446,25 +490,31 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         }
     }
 
-    // ---------------- vertical taps: lane l < 16 computes row (l & 1) of the warp's item blk * 8 + (l >> 1) ----------
+    // ---------------- item records: lane l < 16 computes row (l & 1) of the warp's item blk * 8 + (l >> 1), the even
+    // lane of each pair assembles the record ----------------
     auto compute_taps = [&](int blk) {
         const int k = blk * kTapBlock + (lane >> 1);
         RowTap t;
         t.a = kRowSkip;
         t.wy0 = t.wy1 = 0.f;
         t.pad = 0;
+        int rb = 0, ymap = 0;
+        bool new_band = false;
         if (lane < 2 * kTapBlock && k < n_items) {
             const int idx = first_item + k;
-            const int z = idx / G.items_per_crop;
+            const int z = (int)fast_div((uint32_t)idx, G.d_items_per_crop);
             const int rem = idx - z * G.items_per_crop;
-            const int txi = rem / G.HP;
+            const int txi = (int)fast_div((uint32_t)rem, G.d_HP);
             const int y = 2 * (rem - txi * G.HP) + (lane & 1);
+            new_band = k == 0 || rem == txi * G.HP;
             if (y < H) {
                 t.a = kRowFill;
                 if (!GEN || z < P.used) {
                     const DevCrop& C = tma_crop_of<Table>(K, T, z);
                     const int tx0 = txi * TW;
                     const bool band_ok = max(tx0, C.bx1) <= min(min(tx0 + TW, W) - 1, C.bx2);
+                    rb = crop_row_bytes(C);
+                    ymap = C.m.y0;
                     if (band_ok && y >= C.by1 && y <= C.by2) {
                         const AxisTap v = axis_tap(y - C.by1, C.fy);
                         t.a = (uint32_t)v.i1 | ((v.i1 + 1 > C.h - 1) ? kTapClamp : 0u);
@@ -474,56 +524,81 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                 }
             }
         }
-        if (lane < 2 * kTapBlock) sts_rowtap(taps + (uint32_t)(((blk & 1) * 2 * kTapBlock + lane) * sizeof(RowTap)), t);
+        // the odd lane's row joins the even lane's
+        RowTap u;
+        u.a = __shfl_xor_sync(0xffffffffu, t.a, 1);
+        u.wy0 = __shfl_xor_sync(0xffffffffu, t.wy0, 1);
+        u.wy1 = __shfl_xor_sync(0xffffffffu, t.wy1, 1);
+        if (lane < 2 * kTapBlock && !(lane & 1)) {
+            const bool im0 = t.a < kRowFill, im1 = u.a < kRowFill;
+            // staged rows of a slot: [row 0: y1, y1+1][row 1: y1, y1+1], rb bytes each; a clamped y2 re-reads y1
+            const uint32_t b0 = (t.a & kTapClamp) ? 0u : (uint32_t)rb, b1 = (u.a & kTapClamp) ? 0u : (uint32_t)rb;
+            const uint32_t r0 = b0 << 16, r1 = (uint32_t)(2 * rb) | ((uint32_t)(2 * rb) + b1) << 16;
+            ItemRec r;
+            r.a0 = (im0 ? r0 : r1) | (u.a != kRowSkip ? kRecRow1 : 0u) | (im0 ? kRecImg0 : 0u) | (im1 ? kRecImg1 : 0u) |
+                   (new_band ? kRecNewBand : 0u);
+            r.a1 = im1 ? r1 : r0;
+            r.wy0x = im0 ? t.wy0 : u.wy0;
+            r.wy1x = im0 ? t.wy1 : u.wy1;
+            r.wy0y = im1 ? u.wy0 : t.wy0;
+            r.wy1y = im1 ? u.wy1 : t.wy1;
+            r.y0 = im0 ? ymap + (int)(t.a & (kTapClamp - 1)) : -1;
+            r.y1 = im1 ? ymap + (int)(u.a & (kTapClamp - 1)) : -1;
+            const uint32_t dst = recs + (uint32_t)(((blk & 1) * kTapBlock + (lane >> 1)) * sizeof(ItemRec));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r.a0), "r"(r.a1), "r"(r.y0), "r"(r.y1) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16), "f"(r.wy0x), "f"(r.wy0y), "f"(r.wy1x), "f"(r.wy1y) : "memory");
+        }
         __syncwarp();
     };
-    // table address of row 0 of the warp's k-th item (row 1 follows)
-    auto tap_addr = [&](int k) { return taps + (uint32_t)((k & (2 * kTapBlock - 1)) * 2 * sizeof(RowTap)); };
+    // record of the warp's k-th item
+    auto rec_addr = [&](int k) { return recs + (uint32_t)((k & (2 * kTapBlock - 1)) * sizeof(ItemRec)); };
 
-    // ---------------- staging: lane 0 stages the (up to) two 2-row boxes of the warp's item number ks ----------------
+    // ---------------- staging: one lane stages the (up to) two 2-row boxes of the warp's item number ks ----------------
     StageBand sb;
-    sb.z = sb.txi = -1;
-    sb.ok = false;
-    sb.c0 = sb.rb = sb.y0 = 0;
+    sb.c0 = sb.rb = 0;
     sb.map = nullptr;
     int ks = 0;  // number of items staged so far
     auto stage_item = [&](int slot) {
         if ((ks & (kTapBlock - 1)) == 0) compute_taps(ks / kTapBlock);
-        if (ic.z != sb.z || ic.txi != sb.txi) {
-            sb.z = ic.z;
-            sb.txi = ic.txi;
-            sb.ok = false;
-            if (!GEN || ic.z < P.used) {
-                const DevCrop& C = tma_crop_of<Table>(K, T, ic.z);
-                const BandOrigin b = band_origin(P, G, C, ic.txi);
+        int32_t y0, y1;
+        uint32_t fl, unused;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(fl), "=r"(unused), "=r"(y0), "=r"(y1) : "r"(rec_addr(ks)));
+        if (uniform_u(fl & kRecNewBand)) {
+            const int idx = first_item + ks;
+            const int iz = (int)fast_div((uint32_t)idx, G.d_items_per_crop);
+            const int itx = (int)fast_div((uint32_t)(idx - iz * G.items_per_crop), G.d_HP);
+            if (!GEN || iz < P.used) {
+                const DevCrop& C = tma_crop_of<Table>(K, T, iz);
+                const BandOrigin b = band_origin(P, G, C, itx);
                 // all lanes computed the same values; telling the compiler so keeps the TMA issue below loop-free
-                sb.ok = uniform_i(b.xa <= b.xe) != 0;
                 sb.c0 = uniform_i(b.c0);
                 sb.rb = uniform_i(crop_row_bytes(C));
-                sb.y0 = uniform_i(C.m.y0);
                 sb.map = tma_map_of<Table>(K, T, C);
                 const unsigned long long mp = reinterpret_cast<unsigned long long>(sb.map);
                 sb.map = reinterpret_cast<const CUtensorMap*>(
                     ((unsigned long long)uniform_u((uint32_t)(mp >> 32)) << 32) | uniform_u((uint32_t)mp));
             }
         }
-        const uint32_t ta = tap_addr(ks);
-        const uint32_t a0 = uniform_u(lds32(ta)), a1 = uniform_u(lds32(ta + (uint32_t)sizeof(RowTap)));
+        y0 = uniform_i(y0);
+        y1 = uniform_i(y1);
         if (elect_one_sync()) {
             const uint32_t sdst = ring + (uint32_t)slot * slot_bytes + kSlotHeader;
             const uint32_t full = bars + 8 * slot;
-            const bool i0 = a0 < kRowFill, i1 = a1 < kRowFill;
+            const bool i0 = y0 >= 0, i1 = y1 >= 0;
             // the slot's previous contents were read through the generic proxy; the TMA writes through the async proxy
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#ifdef CVGS_DIAG_SKIP_LOADS  // diagnostic build: nothing is staged (results are garbage), the barrier completes at once
+            mbar_arrive_expect_tx(full, 0u);
+#else
             mbar_arrive_expect_tx(full, (uint32_t)(((int)i0 + (int)i1) * 2 * sb.rb));
-            if (i0) tma_load_2d(sdst, sb.map, sb.c0, sb.y0 + (int)(a0 & (kTapClamp - 1)), full);
-            if (i1) tma_load_2d(sdst + 2 * sb.rb, sb.map, sb.c0, sb.y0 + (int)(a1 & (kTapClamp - 1)), full);
+            if (i0) tma_load_2d(sdst, sb.map, sb.c0, y0, full);
+            if (i1) tma_load_2d(sdst + 2 * sb.rb, sb.map, sb.c0, y1, full);
+#endif
         }
         ++ks;
-        ic.next(G);
     };
 
-    for (int s = 0; s < nslots && ic.left > 0; ++s) stage_item(s);
+    for (int s = 0; s < nslots && s < n_items; ++s) stage_item(s);
 
     int slot = 0, kc = 0;  // kc = number of items computed so far
     uint32_t phase = 0;
@@ -532,8 +607,8 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         const int z = cc.z;
         const int tx0 = cc.txi * TW;
         const int np = (min(TW, W - tx0) + 31) >> 5;
-        int32_t off[kMaxNP], shl[kMaxNP], shr[kMaxNP];
-        float wxa[kMaxNP], wxb[kMaxNP];
+        int32_t off[MAXNP], shl[MAXNP], shr[MAXNP];
+        float wxa[MAXNP], wxb[MAXNP];
         // bit p: right tap of column p clamped / column p receives image data / column p < W.  One register each,
         // tested with one LOP3 per column (separate flags were re-derived from scratch in front of every column)
         uint32_t m_edge = 0, m_img = 0, m_in = 0;
@@ -555,19 +630,23 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                 rb = (uint32_t)crop_row_bytes(C);
             }
 #pragma unroll
-            for (int p = 0; p < kMaxNP; ++p) {
-                const int x = tx0 + lane + 32 * p;
-                const bool in_p = x < W, img_p = in_p && x >= b.xa && x <= b.xe;
-                const AxisTap t = axis_tap((img_p ? x : b.xa) - bx1, fx);
-                wxa[p] = t.w0;
-                wxb[p] = t.w1;
-                m_in |= (in_p ? 1u : 0u) << p;
-                m_img |= (img_p ? 1u : 0u) << p;
-                m_edge |= (t.i1 + 1 > wm1 ? 1u : 0u) << p;
-                const int o = 3 * t.i1 - b.origin;
-                off[p] = ((o + 3) >> 2) * 4;
-                shl[p] = (o & 3) ? (o & 3) * 8 : 32;
-                shr[p] = ((o + 3) & 3) * 8;
+            for (int p = 0; p < MAXNP; ++p) {
+                off[p] = shl[p] = shr[p] = 0;
+                wxa[p] = wxb[p] = 0.f;
+                if (p < np) {  // warp-uniform: narrow planes (64 columns: two groups) skip the unused groups
+                    const int x = tx0 + lane + 32 * p;
+                    const bool in_p = x < W, img_p = in_p && x >= b.xa && x <= b.xe;
+                    const AxisTap t = axis_tap((img_p ? x : b.xa) - bx1, fx);
+                    wxa[p] = t.w0;
+                    wxb[p] = t.w1;
+                    m_in |= (in_p ? 1u : 0u) << p;
+                    m_img |= (img_p ? 1u : 0u) << p;
+                    m_edge |= (t.i1 + 1 > wm1 ? 1u : 0u) << p;
+                    const int o = 3 * t.i1 - b.origin;
+                    off[p] = ((o + 3) >> 2) * 4;
+                    shl[p] = (o & 3) ? (o & 3) * 8 : 32;
+                    shr[p] = ((o + 3) & 3) * 8;
+                }
             }
         }
         // this lane's first column in rows 2*jp of the three channel planes of plane z
@@ -592,33 +671,30 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         }
 
         const int nitems = min(cc.left, G.HP - cc.jp);  // items of this band inside the warp's range
+        if (!GEN) asm volatile("" : "+r"(rb));  // keep the crop's row bytes in a register (else re-read from the parameters per item)
+        // The item loop is instantiated per band shape (number of column groups; ragged or not) and chosen once per
+        // band: inside it the columns of a row pair are straight-line code.  Bands whose 32-column groups are all inside
+        // the plane (the common case) run a branch-free body: one basic block, so the loads of the next column are
+        // scheduled above the arithmetic and the stores of the previous one.  Ragged bands test the lane's column mask
+        // per column.
+        auto run_band = [&](auto npc_tag, auto check_tag) {
+        constexpr int NPC = decltype(npc_tag)::value;
+        constexpr bool CHECK = decltype(check_tag)::value;
+#pragma unroll 1
         for (int it = 0; it < nitems; ++it) {
             mbar_wait(bars + 8 * slot, phase);
             const uint32_t sdata = ring + (uint32_t)slot * slot_bytes + kSlotHeader;
-            const uint32_t ta = tap_addr(kc);
-            const RowTap r0 = lds_rowtap(ta);
-            const RowTap r1 = lds_rowtap(ta + (uint32_t)sizeof(RowTap));
-            const bool st1 = r1.a != kRowSkip;
-            const bool im0 = !GEN || r0.a < kRowFill, im1 = r1.a < kRowFill;
-            // staged rows of the slot: [row 0: y1, y1+1][row 1: y1, y1+1], rb bytes each; a clamped y2 re-reads y1.
-            // A row without image data borrows the other row's taps (its values are replaced / not stored).
-            const uint32_t b0 = (r0.a & kTapClamp) ? 0u : rb, b1 = (r1.a & kTapClamp) ? 0u : rb;
-            uint32_t aA0, aB0, aA1, aB1;
+            uint32_t ra0, ra1;
             float2 wy0, wy1;
-            if (!GEN || im0) {
-                aA0 = sdata, aB0 = sdata + b0;
-                wy0.x = r0.wy0, wy1.x = r0.wy1;
-            } else {
-                aA0 = sdata + 2 * rb, aB0 = aA0 + b1;
-                wy0.x = r1.wy0, wy1.x = r1.wy1;
+            {
+                const uint32_t ra = rec_addr(kc);
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(ra0), "=r"(ra1) : "r"(ra));
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(wy0.x), "=f"(wy0.y), "=f"(wy1.x), "=f"(wy1.y) : "r"(ra + 16));
             }
-            if (im1) {
-                aA1 = sdata + 2 * rb, aB1 = aA1 + b1;
-                wy0.y = r1.wy0, wy1.y = r1.wy1;
-            } else {
-                aA1 = sdata, aB1 = sdata + b0;
-                wy0.y = r0.wy0, wy1.y = r0.wy1;
-            }
+            const bool st1 = (ra0 & kRecRow1) != 0;
+            const bool im0 = !GEN || (ra0 & kRecImg0) != 0, im1 = !GEN || (ra0 & kRecImg1) != 0;
+            uint32_t aA0 = sdata + (ra0 & kRecOffMask), aB0 = sdata + (ra0 >> 16);
+            uint32_t aA1 = sdata + (ra1 & 0xffffu), aB1 = sdata + (ra1 >> 16);
             // row pointers of the pair; opaque to the compiler so that they stay in registers instead of being
             // re-derived in front of every store
             float* t0 = s0 + (GEN ? rs0 : (long long)row_step);
@@ -626,12 +702,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             float* t2 = s2 + (GEN ? rs2 : (long long)row_step);
             asm volatile("" : "+l"(s0), "+l"(s1), "+l"(s2), "+l"(t0), "+l"(t1), "+l"(t2));
             asm volatile("" : "+r"(aA0), "+r"(aB0), "+r"(aA1), "+r"(aB1), "+f"(wy0.x), "+f"(wy0.y), "+f"(wy1.x), "+f"(wy1.y));
-            // Columns of the pair.  Bands whose 32-column groups are all inside the plane (the common case) run a
-            // branch-free body: one basic block, so the loads of the next column are scheduled above the arithmetic
-            // and the stores of the previous one.  Ragged bands test the lane's column mask per column.
-            auto columns = [&](auto npc_tag, auto check_tag) {
-                constexpr int NPC = decltype(npc_tag)::value;
-                constexpr bool CHECK = decltype(check_tag)::value;
+            {
 #pragma unroll
                 for (int p = 0; p < NPC; ++p) {
                     if (!CHECK || (m_in & (1u << p))) {  // lanes past the right border of the plane skip
@@ -685,24 +756,20 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                             }
                         } else {
                             const int q = 32 * p * pxs;
+#ifdef CVGS_DIAG_SKIP_STORES  // diagnostic build (scripts/diag_build.sh): stores only for a value that never occurs
+                            if (v[0].x == 123456.0f)
+#endif
+                            {
                             st_cs_f32(s0 + q, v[0].x);
                             st_cs_f32(s1 + q, v[1].x);
                             st_cs_f32(s2 + q, v[2].x);
                             st_cs_f32_if(st1, t0 + q, v[0].y);
                             st_cs_f32_if(st1, t1 + q, v[1].y);
                             st_cs_f32_if(st1, t2 + q, v[2].y);
+                            }
                         }
                     }
                 }
-            };
-            using std::integral_constant;
-            if (full_band) {
-                if (np == 4) columns(integral_constant<int, 4>{}, integral_constant<bool, false>{});
-                else if (np == 3) columns(integral_constant<int, 3>{}, integral_constant<bool, false>{});
-                else if (np == 2) columns(integral_constant<int, 2>{}, integral_constant<bool, false>{});
-                else columns(integral_constant<int, 1>{}, integral_constant<bool, false>{});
-            } else {
-                columns(integral_constant<int, kMaxNP>{}, integral_constant<bool, true>{});
             }
             s0 += 2 * (GEN ? rs0 : (long long)row_step);
             s1 += 2 * (GEN ? rs1 : (long long)row_step);
@@ -711,12 +778,22 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
 
             // every lane has consumed its taps of this slot (their values fed the stores above): refill it
             __syncwarp();
-            if (ic.left > 0) stage_item(slot);
+            if (ks < n_items) stage_item(slot);
             ++kc;
             if (++slot == nslots) {
                 slot = 0;
                 phase ^= 1u;
             }
+        }
+        };
+        using std::integral_constant;
+        if (full_band) {
+            if (MAXNP >= 4 && np == 4) run_band(integral_constant<int, MAXNP >= 4 ? 4 : 1>{}, integral_constant<bool, false>{});
+            else if (MAXNP >= 3 && np == 3) run_band(integral_constant<int, MAXNP >= 3 ? 3 : 1>{}, integral_constant<bool, false>{});
+            else if (np == 2) run_band(integral_constant<int, 2>{}, integral_constant<bool, false>{});
+            else run_band(integral_constant<int, 1>{}, integral_constant<bool, false>{});
+        } else {
+            run_band(integral_constant<int, MAXNP>{}, integral_constant<bool, true>{});
         }
         // advance the compute cursor past the band's items
         cc.left -= nitems;
@@ -778,7 +855,11 @@ inline void host_item_range(const TmaGeom& G, int g, long long& first, long long
 }
 
 // Staged row bytes are rounded up to a few classes so that crops of one image share tensor maps.
-inline int rb_class(int rb) {
+// fine: classes every 64 bytes (launches whose maps live in the device-resident cache, where their number does not
+// matter): 9 % less source traffic from DRAM on the 50-crop frames than the coarse classes, which exist so that the
+// crops of a launch share the 16 maps that fit its kernel parameters.
+inline int rb_class(int rb, bool fine = false) {
+    if (fine) return rb <= 2048 ? std::max(128, (rb + 63) / 64 * 64) : 0;
     static const int cls[] = {128, 192, 256, 384, 512, 640, 768, 896, 1024, 1280, 1408, 1536, 1664, 1792, 1920, 2048};
     for (int c : cls)
         if (rb <= c) return c;
@@ -786,8 +867,10 @@ inline int rb_class(int rb) {
 }
 
 // Can this launch take the TMA kernel, and with which geometry?  crops = host copies of the DevCrops.
+// grid_div > 1: the launch takes only 1/grid_div of the CTA slots of the device, so that consecutive launches of a
+// stream (chained by programmatic dependent launch) are co-resident and each one's ramp-up and tail overlap its neighbours.
 inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int n_planes, int sm_count, bool image_mode,
-                     int items_per_warp, TmaGeom& G, bool need_driver = true) {
+                     int items_per_warp, TmaGeom& G, bool need_driver = true, int grid_div = 1, int max_resident = kMaxResident) {
     if (need_driver && !encode_tiled_fn()) return false;
     if (P.src_type != CVGS_8UC3) return false;  // the byte-level tap extraction is written for 3-byte pixels
     if (P.out.u8 && P.prog.nc_out != 3) return false;
@@ -830,20 +913,21 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
         return kWarps * slots * G.slot_bytes + kRingPad + 128 + kWarps * 4 * kTapBlock * static_cast<int>(sizeof(RowTap)) + 256 + 1024;
     };
     int slots = kMaxSlots;
-    while (slots > 2 && smem_sm / cta_bytes(slots) < kMaxResident) --slots;
+    while (slots > 2 && smem_sm / cta_bytes(slots) < max_resident) --slots;
     if (const char* e = std::getenv("CVGS_TMA_SLOTS")) {  // tuning override (tests / profiling)
         const int v = std::atoi(e);
         if (v >= 1 && v <= kMaxSlots) slots = v;
     }
     if (cta_bytes(slots) > smem_sm) return false;
     G.slots = slots;
-    G.resident = std::min(kMaxResident, smem_sm / cta_bytes(slots));
+    G.resident = std::min(max_resident, smem_sm / cta_bytes(slots));
     // Small launches: one item per warp spreads the work over the most SMs (shortest isolated launch); when
     // consecutive launches overlap, several items per warp amortise the staging latency and leave CTA slots free
     // for the next launch, which raises back-to-back throughput (items_per_warp > 1, cvgs_b200_set_overlap).
     const long long warps_wanted = std::max<long long>(1, (total + items_per_warp - 1) / items_per_warp);
     const long long ctas_wanted = (warps_wanted + kWarps - 1) / kWarps;
-    G.grid = static_cast<int32_t>(std::min<long long>(ctas_wanted, static_cast<long long>(G.resident) * sm_count));
+    G.grid = static_cast<int32_t>(std::min<long long>(
+        ctas_wanted, std::max<long long>(1, static_cast<long long>(G.resident) * sm_count / std::max(1, grid_div))));
     G.np_last = (std::min(TW, P.W - (G.tiles_x - 1) * TW) + 31) / 32;
     const long long w_full = static_cast<long long>(G.tiles_x - 1) * G.HP * NPB;
     const long long w_crop = w_full + static_cast<long long>(G.HP) * G.np_last;
@@ -854,6 +938,11 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
     const long long n_warps = static_cast<long long>(G.grid) * kWarps;
     G.share_q = static_cast<int32_t>(w_total / n_warps);
     G.share_r = static_cast<int32_t>(w_total % n_warps);
+    G.d_w_crop = fast_div_make(static_cast<uint32_t>(G.w_crop));
+    G.d_NPB = fast_div_make(static_cast<uint32_t>(G.NPB));
+    G.d_np_last = fast_div_make(static_cast<uint32_t>(G.np_last));
+    G.d_items_per_crop = fast_div_make(static_cast<uint32_t>(G.items_per_crop));
+    G.d_HP = fast_div_make(static_cast<uint32_t>(G.HP));
     return true;
 }
 
@@ -957,9 +1046,15 @@ inline int tma_encode(CUtensorMap* map, uintptr_t base16, long long row_bytes, i
     const cuuint64_t stride[1] = {rows > 1 ? static_cast<cuuint64_t>(pitch) : (dim[0] * 8 + 15) / 16 * 16};
     const cuuint32_t box[2] = {static_cast<cuuint32_t>(rb / 8), 2};
     const cuuint32_t estr[2] = {1, 1};
+    static const CUtensorMapL2promotion promo = [] {  // tuning override (profiling): 0 none, 1 64 B, 2 128 B, 3 256 B
+        const char* e = std::getenv("CVGS_TMA_L2PROMO");
+        const int v = e ? std::atoi(e) : 2;
+        return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+               : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }();
     const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, reinterpret_cast<void*>(base16), dim, stride, box,
-                                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CVGS_ERR_INVALID_VALUE, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return CVGS_OK;
 }
@@ -1108,12 +1203,12 @@ inline size_t tma_smem_bytes(const TmaGeom& G) {
     return static_cast<size_t>(kWarps) * G.slots * G.slot_bytes + kRingPad + 128;
 }
 
-template <typename Table, int CHAIN, bool GEN, bool PEER = false>
+template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP>
 inline int tma_launch_instance(const TmaParams& K, const Table& T, int device, cudaStream_t stream) {
     static thread_local size_t attr_set[64] = {};  // per device: dynamic shared memory opt-in already granted
     const size_t smem = tma_smem_bytes(K.G);
     const int slot = device & 63;
-    auto kernel = preproc_tma_kernel<Table, CHAIN, GEN, PEER>;
+    auto kernel = preproc_tma_kernel<Table, CHAIN, GEN, PEER, MAXNP>;
     if (smem > attr_set[slot]) {
         const size_t want = std::max<size_t>(smem, 112 * 1024);
         CVGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(want)));

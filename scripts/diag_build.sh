@@ -1,0 +1,12 @@
+#!/bin/sh
+# Diagnostic builds of the product library (NOT shipped): the TMA-staged kernel without its stores / without its loads,
+# to see which side of the memory system bounds a workload.  Use with CVGS_B200_LIB=<path> (results are garbage).
+set -e
+cd "$(dirname "$0")/../cvgpuspeedup_b200"
+FLAGS="-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared"
+SRCS="csrc/preproc.cu csrc/circular_tensor.cu csrc/selftest.cu csrc/div_const.o"
+mkdir -p ../gpurun_out
+nvcc $FLAGS -DCVGS_DIAG_SKIP_STORES -o /tmp/libcvgs_diag_nostore.so $SRCS &
+nvcc $FLAGS -DCVGS_DIAG_SKIP_LOADS -o /tmp/libcvgs_diag_noload.so $SRCS &
+wait
+mkdir -p diag && cp /tmp/libcvgs_diag_nostore.so /tmp/libcvgs_diag_noload.so diag/
