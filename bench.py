@@ -436,6 +436,10 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int):
 
     # ---- end-to-end arm (host buffers) ----
     host_steps(W)
+    b_h2d, b_d2h = C.c_uint64(), C.c_uint64()
+    lib.cvgs_b200_debug_host_bytes(None, None, 1)
+    host_steps(1)
+    lib.cvgs_b200_debug_host_bytes(C.byref(b_h2d), C.byref(b_d2h), 1)  # what one step actually moves, counted by the library
     times_e2e = timed_repeats(torch, dist, stream, host_steps, K, sampler, min_total_ms=300.0, min_reps=3, max_reps=20)
     ms_e2e = statistics.median(times_e2e)
     util.assert_bit_equal(h_outs[F - 1].numpy(), util.run_oracle(frames[F - 1][0], frames[F - 1][1], DST, OPS),
@@ -495,9 +499,10 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int):
                    "value_best_repetition": crops_step * K / (min(times) * 1e-3), "warmup_requested": args.warmup,
                    "note": "each repetition = K steps between barrier + synchronise, CUDA events on the launching "
                            "stream, max over ranks; value / ms_per_step are the median repetition"},
-        "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": int(h2d_bytes(frames)),
-                "d2h_bytes_per_step": int(bytes_out * F), "ms_per_step": ms_e2e / K, "repetitions": len(times_e2e),
+        "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": int(b_h2d.value),
+                "d2h_bytes_per_step": int(b_d2h.value), "ms_per_step": ms_e2e / K, "repetitions": len(times_e2e),
                 "value_best_repetition": crops_step * K / (min(times_e2e) * 1e-3),
+                "h2d_bytes_whole_rows": int(h2d_bytes(frames)),
                 "api": "cvgs_b200_preproc_host_sequence (pinned host frames -> pinned host tensors, 3 frames in "
                        "flight: upload / kernel / download overlap)"},
         "gpu_launches": int(launches_per_rep),
@@ -933,7 +938,7 @@ def c3_reference_us(sets, torch, stream, reps=10):
 
 
 def h2d_bytes(frames) -> int:
-    """Bytes cvgs_b200_preproc_host uploads per step: the rows [min y, max y+h) of each frame, 3*W bytes each."""
+    """Bytes cvgs_b200_preproc_host would upload per step with plain row copies: rows [min y, max y+h) of each frame."""
     total = 0
     for _, rects in frames:
         lo = min(r[1] for r in rects)

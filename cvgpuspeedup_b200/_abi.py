@@ -91,6 +91,7 @@ SYMBOLS = {
     "cvgs_b200_set_kernel_variant": (C.c_int, [C.c_int]),
     "cvgs_b200_set_overlap": (C.c_int, [C.c_int]),
     "cvgs_b200_set_coalesce": (C.c_int, [C.c_int]),
+    "cvgs_b200_set_host_upload": (C.c_int, [C.c_int]),
     "cvgs_b200_preproc_launch_replicated": (C.c_int, [C.POINTER(Crop), C.POINTER(Parent), C.c_int32, C.c_int32,
                                                       C.POINTER(Pipeline), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "cvgs_b200_dev_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
@@ -100,6 +101,7 @@ SYMBOLS = {
     "cvgs_b200_ipc_close": (C.c_int, [C.c_void_p]),
     "cvgs_b200_launch_count": (C.c_int64, []),
     "cvgs_b200_debug_host_profile": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
+    "cvgs_b200_debug_host_bytes": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]),
     "cvgs_b200_debug_program": (C.c_int, [C.POINTER(Pipeline), C.POINTER(C.c_float)]),
     "cvgs_b200_debug_plan": (C.c_int, [C.POINTER(Crop), C.c_int32, C.c_int32, C.POINTER(Pipeline), C.c_int32, C.c_int32,
                                        C.c_int32, C.POINTER(C.c_int64)]),

@@ -162,6 +162,11 @@ int cvgs_b200_ct_update(void* handle, const cvgs_crop_t* frame, const cvgs_pipel
     CircularTensor* t = static_cast<CircularTensor*>(handle);
     if (!t) return fail(CVGS_ERR_INVALID_VALUE, "handle is NULL");
     if (!frame) return fail(CVGS_ERR_INVALID_VALUE, "frame is NULL");
+    int cur_device = -1;
+    CVGS_CUDA(cudaGetDevice(&cur_device));
+    if (cur_device != t->device)
+        return fail(CVGS_ERR_INVALID_VALUE, "CircularTensor lives on device " + std::to_string(t->device) + ", the current device is " +
+                                                std::to_string(cur_device));
     if (int rc = validate_pipeline(pipeline)) return rc;
     if (pipeline->dst_type == CVGS_8UC3 || pipeline->dst_type == CVGS_8UC4 || pipeline->out_row_pitch != 0) return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor planes are float");
     if (channels_of(pipeline->src_type) != 3) return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor takes 3-channel frames");

@@ -54,6 +54,10 @@ static inline double now_us() {
 }
 static thread_local int64_t t_launch_count = 0;
 static std::atomic<int> g_variant{0};
+static std::atomic<int> g_host_tiles{[] {
+    const char* e = std::getenv("CVGS_B200_HOST_TILES");
+    return e && e[0] == '1' ? 1 : 0;
+}()};
 static std::atomic<int> g_coalesce{[] {
     const char* e = std::getenv("CVGS_B200_SEQ_COALESCE");
     return e && e[0] == '0' ? 0 : 1;
@@ -701,8 +705,75 @@ static int launch_multi(const MultiSet* sets, int G, const cvgs_pipeline_t* pipe
     return tma_launch_multi(K, mt, chain, device, stream);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Host-buffer path: upload of the part of a frame its crops touch.  Default: one cudaMemcpy2DAsync of the rows [min y,
+// max y + h).  Optional (cvgs_b200_set_host_upload(1)), when the caller's frame is pinned host memory that the device can
+// read in place: a small kernel pulls the 128-byte x 16-row tiles that some crop overlaps into the device staging
+// image -- 4.4 MB instead of 6.0 MB on the bench's 1080p frames (the exact union of the rectangles is 3.8 MB).  Measured
+// on the PCIe Gen5 boxes of this pool it LOSES: SM-issued reads of host memory are 128-byte requests and reach 29 GB/s
+// where the copy engine streams 47 GB/s, so 332 K against 386 K crops/s end to end; it is kept for hosts whose GPUs read
+// host memory at link rate (NVLink-C2C).  The tile mask rides in the kernel parameters.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileBytes = 128;        // tile width (one PCIe read request per row of a tile)
+constexpr int kTileMaskWords = 1008;   // 32256 tiles: ~4 KB of kernel parameters
+struct TileMask {
+    uint32_t bits[kTileMaskWords];
+};
+__global__ void __launch_bounds__(256) upload_tiles_kernel(const uint8_t* __restrict__ host_img, long long host_pitch,
+                                                           uint8_t* __restrict__ dev_img, long long dev_pitch, int row_chunks,
+                                                           int height, int tiles_x, int tile_rows, int n_tiles,
+                                                           const __grid_constant__ TileMask mask) {
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);  // one warp per tile
+    if (tile >= n_tiles || !((mask.bits[tile >> 5] >> (tile & 31)) & 1u)) return;
+    const int lane = threadIdx.x & 31;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int chunk = tx * (kTileBytes / 16) + (lane & 7);  // 16-byte chunk of the row
+    if (chunk >= row_chunks) return;
+    const int y0 = ty * tile_rows, y1 = min(height, y0 + tile_rows);
+    // every lane keeps up to four 16-byte reads in flight (rows y, y + 4, y + 8, y + 12): PCIe latency is microseconds
+    for (int y = y0 + (lane >> 3); y < y1; y += 16) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (y + 4 * k < y1) v[k] = *reinterpret_cast<const uint4*>(host_img + (long long)(y + 4 * k) * host_pitch + 16LL * chunk);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (y + 4 * k < y1) *reinterpret_cast<uint4*>(dev_img + (long long)(y + 4 * k) * dev_pitch + 16LL * chunk) = v[k];
+    }
+}
+
+// Device-visible address of a pinned host buffer, or nullptr (pageable memory, or the query failed).  Frame buffers
+// recur: a small per-thread cache keeps cudaPointerGetAttributes off the per-frame path.
+static const uint8_t* pinned_device_view(const void* host_ptr) {
+    struct Entry { const void* host; const uint8_t* dev; };
+    static thread_local Entry cache[64] = {};
+    Entry& e = cache[(reinterpret_cast<uintptr_t>(host_ptr) >> 12) & 63];
+    if (e.host == host_ptr) return e.dev;
+    cudaPointerAttributes a;
+    const uint8_t* dev = nullptr;
+    if (cudaPointerGetAttributes(&a, host_ptr) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer)
+        dev = static_cast<const uint8_t*>(a.devicePointer);
+    else
+        (void)cudaGetLastError();
+    e.host = host_ptr;
+    e.dev = dev;
+    return dev;
+}
+static thread_local uint64_t t_h2d_bytes = 0, t_d2h_bytes = 0;  // cvgs_b200_debug_host_bytes
+
 static int host_reserve(HostPath& h, size_t img_bytes, size_t out_bytes, int device) {
-    if (h.device != device) { h.img_cap = h.out_cap = 0; h.d_img = nullptr; h.d_out = nullptr; h.device = device; }
+    if (h.device != device) {  // the old buffers belong to the old device: free them there
+        if (h.device >= 0 && (h.d_img || h.d_out)) {
+            CVGS_CUDA(cudaSetDevice(h.device));
+            if (h.d_img) cudaFree(h.d_img);
+            if (h.d_out) cudaFree(h.d_out);
+            CVGS_CUDA(cudaSetDevice(device));
+        }
+        h.img_cap = h.out_cap = 0;
+        h.d_img = nullptr;
+        h.d_out = nullptr;
+        h.device = device;
+    }
     if (img_bytes > h.img_cap) {
         if (h.d_img) { CVGS_CUDA(cudaDeviceSynchronize()); CVGS_CUDA(cudaFree(h.d_img)); }
         CVGS_CUDA(cudaMalloc(&h.d_img, img_bytes));
@@ -796,6 +867,7 @@ const char* cvgs_b200_last_error(void) { return t_last_error.c_str(); }
 int cvgs_b200_set_kernel_variant(int variant) { return g_variant.exchange(variant); }
 int cvgs_b200_set_overlap(int enable) { return g_overlap.exchange(enable ? 1 : 0); }
 int cvgs_b200_set_coalesce(int enable) { return g_coalesce.exchange(enable ? 1 : 0); }
+int cvgs_b200_set_host_upload(int mode) { return g_host_tiles.exchange(mode ? 1 : 0); }
 int64_t cvgs_b200_launch_count(void) { return t_launch_count; }
 // Diagnostics for the CPU test-suite: the launch plan of the TMA kernel for a batch geometry (no device needed).
 // out[0..11] = {ok, NPB, HP, tiles_x, total_items, slot_bytes, slots, resident, grid, max row bytes needed,
@@ -861,6 +933,13 @@ int cvgs_b200_debug_overlap_query(void* stream_key, uint64_t out_lo, uint64_t ou
     o.lo = static_cast<uintptr_t>(out_lo); o.hi = static_cast<uintptr_t>(out_hi);
     s.lo = static_cast<uintptr_t>(src_lo); s.hi = static_cast<uintptr_t>(src_hi);
     return overlap_needs_wait(static_cast<cudaStream_t>(stream_key), o, s) ? 1 : 0;
+}
+
+int cvgs_b200_debug_host_bytes(uint64_t* h2d, uint64_t* d2h, int reset) {
+    if (h2d) *h2d = t_h2d_bytes;
+    if (d2h) *d2h = t_d2h_bytes;
+    if (reset) t_h2d_bytes = t_d2h_bytes = 0;
+    return CVGS_OK;
 }
 
 int cvgs_b200_debug_host_profile(double* out5, int reset) {
@@ -1036,7 +1115,10 @@ static int preproc_host_impl(HostPath& h, const void* host_image, int32_t image_
     // device copy keeps rows 512-byte aligned like cudaMallocPitch would
     const size_t d_pitch = (static_cast<size_t>(3) * image_width + 511) / 512 * 512;
     const size_t img_bytes = d_pitch * image_height;
-    const size_t out_floats = static_cast<size_t>(3) * pipeline->dst_width * pipeline->dst_height * n_planes;
+    // the chain may change the channel count (cvtColor to BGRA / gray): the tensor has what it produces
+    DevProgram prog;
+    if (int rc = build_program(*pipeline, prog)) return rc;
+    const size_t out_floats = static_cast<size_t>(prog.nc_out) * pipeline->dst_width * pipeline->dst_height * n_planes;
     if (int rc = host_reserve(h, img_bytes, out_floats * sizeof(float), device)) return rc;
 
     // upload only the rows some crop touches
@@ -1056,10 +1138,44 @@ static int preproc_host_impl(HostPath& h, const void* host_image, int32_t image_
         crops[i].reserved = 0;
     }
     if (used > 0) {
-        CVGS_CUDA(cudaMemcpy2DAsync(static_cast<uint8_t*>(h.d_img) + static_cast<size_t>(y_lo) * d_pitch, d_pitch,
-                                    static_cast<const uint8_t*>(host_image) + static_cast<size_t>(y_lo) * image_pitch,
-                                    static_cast<size_t>(image_pitch), static_cast<size_t>(3) * image_width,
-                                    static_cast<size_t>(y_hi - y_lo), cudaMemcpyHostToDevice, stream));
+        const uint8_t* pinned = g_host_tiles.load(std::memory_order_relaxed) ? pinned_device_view(host_image) : nullptr;
+        const int row_chunks = (3 * image_width + 15) / 16;
+        const int tiles_x = (3 * image_width + kTileBytes - 1) / kTileBytes;
+        int tile_rows = 16;
+        while (static_cast<long long>(tiles_x) * ((image_height + tile_rows - 1) / tile_rows) > 32LL * kTileMaskWords) tile_rows *= 2;
+        const int tiles_y = (image_height + tile_rows - 1) / tile_rows;
+        if (pinned && (reinterpret_cast<uintptr_t>(pinned) & 15) == 0 && (image_pitch & 15) == 0 &&
+            16LL * row_chunks <= image_pitch) {
+            alignas(64) TileMask mask;
+            const int n_tiles = tiles_x * tiles_y;
+            std::memset(mask.bits, 0, static_cast<size_t>((n_tiles + 31) / 32) * 4);
+            long long tiles_set = 0;
+            for (int i = 0; i < used; ++i) {
+                const cvgs_rect_t& r = rects[i];
+                const int tx0 = 3 * r.x / kTileBytes, tx1 = (3 * (r.x + r.width) - 1) / kTileBytes;
+                const int ty0 = r.y / tile_rows, ty1 = (r.y + r.height - 1) / tile_rows;
+                for (int ty = ty0; ty <= ty1; ++ty)
+                    for (int t = ty * tiles_x + tx0; t <= ty * tiles_x + tx1; ++t) {
+                        uint32_t& w = mask.bits[t >> 5];
+                        const uint32_t b = 1u << (t & 31);
+                        tiles_set += !(w & b);
+                        w |= b;
+                    }
+            }
+            upload_tiles_kernel<<<(n_tiles + 7) / 8, 256, 0, stream>>>(pinned, image_pitch, static_cast<uint8_t*>(h.d_img),
+                                                                      static_cast<long long>(d_pitch), row_chunks, image_height,
+                                                                      tiles_x, tile_rows, n_tiles, mask);
+            CVGS_CUDA(cudaGetLastError());
+            count_launch();
+            overlap_forget(stream);
+            t_h2d_bytes += static_cast<uint64_t>(tiles_set) * kTileBytes * tile_rows;  // upper bound: edge tiles are clipped
+        } else {
+            CVGS_CUDA(cudaMemcpy2DAsync(static_cast<uint8_t*>(h.d_img) + static_cast<size_t>(y_lo) * d_pitch, d_pitch,
+                                        static_cast<const uint8_t*>(host_image) + static_cast<size_t>(y_lo) * image_pitch,
+                                        static_cast<size_t>(image_pitch), static_cast<size_t>(3) * image_width,
+                                        static_cast<size_t>(y_hi - y_lo), cudaMemcpyHostToDevice, stream));
+            t_h2d_bytes += static_cast<uint64_t>(3) * image_width * (y_hi - y_lo);
+        }
     }
     cvgs_pipeline_t p = *pipeline;
     p.out_plane_stride = 0;
@@ -1070,6 +1186,7 @@ static int preproc_host_impl(HostPath& h, const void* host_image, int32_t image_
     // host tensor as an earlier one)
     if (download_after) CVGS_CUDA(cudaStreamWaitEvent(stream, download_after, 0));
     CVGS_CUDA(cudaMemcpyAsync(host_out, h.d_out, out_floats * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    t_d2h_bytes += out_floats * sizeof(float);
     if (download_done) CVGS_CUDA(cudaEventRecord(download_done, stream));
     return CVGS_OK;
 }

@@ -280,10 +280,11 @@ int cvgs_b200_warp_launch(const cvgs_crop_t* images, const cvgs_warp_t* warps, i
                           const cvgs_pipeline_t* pipeline, void* stream);
 
 /* Same pipeline with HOST buffers, for callers that hold frames in (pinned) host memory:
- * copies the source image to the device, launches, copies the tensor back, all on `stream`
- * and without synchronising.  Crops are rectangles {x, y, w, h} of the one host image.
- * `pipeline->out` is ignored; the result goes to host_out (tight layout).
- * Device staging buffers are owned by the library and reused across calls. */
+ * brings the part of the source image its crops touch to the device, launches, copies the tensor back, all on
+ * `stream` and without synchronising.  Crops are rectangles {x, y, w, h} of the one host image.
+ * `pipeline->out` is ignored; the result goes to host_out (tight layout; channels as the chain leaves them).
+ * Device staging buffers are owned by the library and reused across calls.  The frame is copied with
+ * cudaMemcpy2DAsync, whole rows from the first to the last row a crop touches (see cvgs_b200_set_host_upload). */
 typedef struct cvgs_rect { int32_t x, y, width, height; } cvgs_rect_t;
 int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t image_height,
                            int32_t image_pitch, const cvgs_rect_t* rects, int32_t n_planes,
@@ -340,8 +341,16 @@ int cvgs_b200_set_overlap(int enable);
  * host threads.  The reference would express the same thing as one BatchRead over all the crops
  * (batch_operations.cuh:222-229), which its template batch size caps at 255 planes.  Returns the previous value. */
 int cvgs_b200_set_coalesce(int enable);
+/* Upload strategy of the host-buffer entry points: 0 (default) = cudaMemcpy2DAsync of the rows the crops span; 1 = for
+ * pinned frames (base and pitch multiples of 16 bytes) a kernel reads the 128-byte x 16-row tiles some crop overlaps
+ * from host memory in place (fewer bytes, but 128-byte PCIe requests: slower than the copy engine on PCIe hosts, see
+ * DESIGN.md 6).  CVGS_B200_HOST_TILES=1 selects 1 at load time.  Returns the previous value. */
+int cvgs_b200_set_host_upload(int mode);
 /* Number of kernel launches issued by this library on the calling thread so far. */
 int64_t cvgs_b200_launch_count(void);
+/* Diagnostics: bytes the host-buffer entry points moved host -> device and device -> host on the calling thread so far
+ * (uploads count whole tiles / rows as issued). */
+int cvgs_b200_debug_host_bytes(uint64_t* h2d, uint64_t* d2h, int reset);
 /* Diagnostics: host-side cost of the small-batch TMA launch path on the calling thread, accumulated in
  * microseconds: out5 = {calls, descriptor fill, planning, tensor-map encoding, kernel launch}. */
 int cvgs_b200_debug_host_profile(double* out5, int reset);

@@ -182,6 +182,62 @@ def test_host_buffer_entry_point():
         util.assert_bit_equal(h_out.numpy(), util.run_oracle(w.image, w.rects, w.dsize, w.ops), "host entry point")
 
 
+@pytest.fixture()
+def tile_upload():
+    lib = _abi.load()
+    prev = lib.cvgs_b200_set_host_upload(1)
+    yield lib
+    lib.cvgs_b200_set_host_upload(prev)
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("frame", [(640, 480, 1920), (333, 211, 1008), (1000, 37, 3008)])
+def test_host_buffer_upload_paths(tile_upload, pinned, frame):
+    """cvgs_b200_set_host_upload(1): pinned frames are pulled tile by tile by the upload kernel (frame widths that are /
+    are not multiples of the 128-byte tile, heights that are not multiples of 16 rows); pageable frames take the row
+    copy.  Same results."""
+    lib = tile_upload
+    fw, fh, pitch = frame
+    w = util.workload_c2(seed=77, n=12, frame=(fw, fh), pitch=pitch)
+    w.rects = [(x, y, max(1, min(ww, fw - x)), max(1, min(hh, fh - y))) for (x, y, ww, hh) in w.rects] + [(0, 0, fw, fh), (fw - 1, fh - 1, 1, 1)]
+    n = len(w.rects)
+    h_img = torch.from_numpy(w.image.copy())
+    if pinned:
+        h_img = h_img.pin_memory()
+    h_out = torch.empty((n, 3, 128, 64), dtype=torch.float32).pin_memory()
+    rects = (_abi.Rect * n)(*[_abi.Rect(*r) for r in w.rects])
+    p = util.make_pipeline(w.dsize, w.ops)
+    lib.cvgs_b200_debug_host_bytes(None, None, 1)
+    h_out.fill_(float("nan"))
+    _abi.check(lib.cvgs_b200_preproc_host(h_img.data_ptr(), fw, fh, pitch, rects, n, n, C.byref(p), h_out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    up, down = C.c_uint64(), C.c_uint64()
+    lib.cvgs_b200_debug_host_bytes(C.byref(up), C.byref(down), 1)
+    assert down.value == h_out.numel() * 4 and up.value >= 3 * fw * fh
+    util.assert_bit_equal(h_out.numpy(), util.run_oracle(w.image, w.rects, w.dsize, w.ops), "host entry point")
+
+
+@pytest.mark.parametrize("ops,nc", [([("reorder", (2, 1, 0)), ("add_alpha", (255.0,)), ("mul", (0.5, 0.25, 2.0, 1.0))], 4),
+                                    ([("gray", (1,)), ("mul", (0.5,))], 1)])
+def test_host_buffer_entry_point_with_channel_changing_chain(ops, nc):
+    """cvtColor<BGR2RGBA> / <RGB2GRAY> in the host-buffer path: the tensor has the channels the chain leaves (4 / 1)."""
+    lib = _abi.load()
+    w = util.workload_c2(seed=78, n=9, frame=(320, 240), pitch=960)
+    h_img = torch.from_numpy(w.image).pin_memory()
+    guard = 1024
+    h_out = torch.full((9 * nc * 128 * 64 + guard,), -7.0, dtype=torch.float32).pin_memory()
+    rects = (_abi.Rect * 9)(*[_abi.Rect(*r) for r in w.rects])
+    p = util.make_pipeline(w.dsize, ops)
+    _abi.check(lib.cvgs_b200_preproc_host(h_img.data_ptr(), 320, 240, 960, rects, 9, 9, C.byref(p), h_out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got = h_out.numpy()
+    assert np.all(got[9 * nc * 128 * 64:] == -7.0), "the download ran past the tensor"
+    util.assert_bit_equal(got[:9 * nc * 128 * 64].reshape(9, nc, 128, 64), util.run_oracle(w.image, w.rects, w.dsize, ops),
+                          "host entry point, channel-changing chain")
+
+
 # ---- the TMA-staged kernel, forced (variant 2 fails loudly instead of falling back) ----
 def test_tma_kernel_c1_c2_c3():
     _check(util.workload_c1(), 2)                      # 10x / 3.75x down-scale
