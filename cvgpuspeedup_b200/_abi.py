@@ -92,6 +92,8 @@ SYMBOLS = {
     "cvgs_b200_set_overlap": (C.c_int, [C.c_int]),
     "cvgs_b200_set_coalesce": (C.c_int, [C.c_int]),
     "cvgs_b200_set_host_upload": (C.c_int, [C.c_int]),
+    "cvgs_b200_preproc_launch_rects": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Rect), C.c_int32,
+                                                 C.c_int32, C.POINTER(Pipeline), C.c_void_p]),
     "cvgs_b200_preproc_launch_replicated": (C.c_int, [C.POINTER(Crop), C.POINTER(Parent), C.c_int32, C.c_int32,
                                                       C.POINTER(Pipeline), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "cvgs_b200_dev_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
@@ -110,6 +112,7 @@ SYMBOLS = {
                                                  C.POINTER(C.c_float)]),
     "cvgs_b200_ct_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32]),
+    "cvgs_b200_ct_create_ex": (C.c_int, [C.POINTER(C.c_void_p)] + [C.c_int32] * 8),
     "cvgs_b200_ct_update": (C.c_int, [C.c_void_p, C.POINTER(Crop), C.POINTER(Pipeline), C.c_void_p]),
     "cvgs_b200_ct_data": (C.c_void_p, [C.c_void_p]),
     "cvgs_b200_ct_destroy": (C.c_int, [C.c_void_p]),

@@ -66,6 +66,15 @@ class GpuMat:
                       datastart=self.datastart, whole=self.whole, elem_size=self.elem_size)
 
 
+def crop(image: "GpuMat", rects) -> List["GpuMat"]:
+    """cvGS::crop(readOfImage, rect) / crop(readOfImage, rects) (reference include/cvGPUSpeedup.cuh:247-265,444 ->
+    fk::Crop, crop.cuh:23-55): the rectangles (x, y, w, h) of one image as the crop list resize() / executeOperations take.
+    Every crop remembers the image it was cut from, so the launch stages them through the image's cached tensor maps."""
+    if rects and isinstance(rects[0], (int, float)):
+        rects = [rects]
+    return [image.roi(int(x), int(y), int(w), int(h)) for (x, y, w, h) in rects]
+
+
 def _scalar3(s) -> Tuple[float, ...]:
     """cv::Scalar: up to four values (the fourth is used by 4-channel pipelines only)."""
     if isinstance(s, (int, float)):
@@ -377,18 +386,22 @@ class CircularTensor:
     the newest plane and shifts the others; ``data()`` is the dense time-ordered tensor."""
 
     def __init__(self, width: int, height: int, batch: int, order: int = CT_NEWEST_FIRST,
-                 mode: int = CT_STANDARD, color_planes: int = 3, device: int = 0):
+                 mode: int = CT_STANDARD, color_planes: int = 3, device: int = 0, elem_channels: int = 1,
+                 src_type: int = _abi.CVGS_8UC3):
+        """color_planes planes of floats (1, 3 or 4), or -- color_planes 1, elem_channels 3 / 4 -- one plane of packed
+        float pixels (cvGS::CircularTensor<CV_8UC4, CV_32FC4, 1, ...>).  src_type: the frames' pixel type."""
         self._lib = _abi.load()
         self._h = C.c_void_p()
         self.width, self.height, self.batch, self.order, self.mode, self.color_planes = (
             width, height, batch, order, mode, color_planes)
-        _abi.check(self._lib.cvgs_b200_ct_create(C.byref(self._h), width, height, color_planes, batch, order, mode,
-                                                 device))
+        self.elem_channels, self.src_type = elem_channels, src_type
+        _abi.check(self._lib.cvgs_b200_ct_create_ex(C.byref(self._h), width, height, color_planes, elem_channels, batch,
+                                                    order, mode, device))
 
     def update(self, stream, frame: GpuMat, *ops, fp_contract: int = FP_REFERENCE_FUSED,
                interp_mode: int = INTERP_FLOAT) -> None:
         p = build_pipeline((self.width, self.height), list(_flatten(ops)), fp_contract=fp_contract,
-                           interp_mode=interp_mode)
+                           interp_mode=interp_mode, src_type=self.src_type)
         crop = make_crops([frame])
         _abi.check(self._lib.cvgs_b200_ct_update(self._h, crop, C.byref(p), _stream_ptr(stream)))
 
@@ -400,6 +413,8 @@ class CircularTensor:
         import torch
         shape = ((self.batch, self.color_planes, self.height, self.width) if self.mode == CT_STANDARD
                  else (self.color_planes, self.batch, self.height, self.width))
+        if self.elem_channels > 1:
+            shape = shape + (self.elem_channels,)
 
         class _Holder:
             pass

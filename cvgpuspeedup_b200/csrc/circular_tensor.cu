@@ -36,8 +36,10 @@ struct CtParams {
     int32_t bw_log2;
     int32_t tiles_x;
     long long plane_px;      // W*H
-    int32_t copy_vec4;       // planes are 16-byte aligned multiples of 4 floats
-    int32_t copy_chunks;     // copy CTAs per (plane, colour) unit when copy_vec4
+    int32_t copy_vec4;       // copy units are 16-byte aligned multiples of 4 floats
+    int32_t copy_chunks;     // copy CTAs per copy unit when copy_vec4
+    int32_t units_per_plane; // copy units per batch plane: the colour planes (split tensors) or 1 (packed elements)
+    long long unit_floats;   // floats per copy unit: W*H (split) or channels * W*H (packed)
 };
 
 constexpr int kCtChunk = 8192;  // float4 per copy CTA (128 KB): 256 threads x 4 accesses x 8 rounds
@@ -52,6 +54,8 @@ __device__ __forceinline__ int ring_source(const CtParams& K, int z) {
     return s >= K.batch ? s - K.batch : s;
 }
 
+// NC = channels of the source pixel, NR = registers per pixel of the chain (4 when a 3-channel source gains an alpha).
+template <int NC, int NR>
 __global__ void __launch_bounds__(256) circular_update_kernel(const __grid_constant__ CtParams K,
                                                               const __grid_constant__ DevCrop frame) {
     const PreprocParams& P = K.pre;
@@ -65,28 +69,34 @@ __global__ void __launch_bounds__(256) circular_update_kernel(const __grid_const
         const int y = by * (256 >> K.bw_log2) + ty;
         if (x0 >= P.W || y >= P.H) return;
         const int nvalid = min(4, P.W - x0);
-        float v[4][3];
+        float v[4][NC];
         gather_quad(P, frame, y, x0, nvalid, v);
-        apply_program<4>(P.prog, v);
-        store_pixels<4>(P, K.upd, y, x0, nvalid, v);  // public tensor, newest position
-        PreprocParams R = P;                          // same strides, ring base
+        float r[4][NR];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int c = 0; c < NR; ++c) r[p][c] = c < NC ? v[p][c] : 0.f;
+        apply_program<4, NR>(P.prog, r);
+        store_pixels<4, NR>(P, K.upd, y, x0, nvalid, r);  // public tensor, newest position
+        PreprocParams R = P;                              // same strides, ring base
         R.out.base = K.ring;
-        store_pixels<4>(R, K.slot, y, x0, nvalid, v);
+        store_pixels<4, NR>(R, K.slot, y, x0, nvalid, r);
         return;
     }
     // ---- copy role: planes z != upd, public[z][c] <- ring[ring_source(z)][c] ----
     const int ncopy = gridDim.x - K.compute_ctas;
     const int cta = blockIdx.x - K.compute_ctas;
     const OutDesc& o = P.out;
-    const int units = (K.batch - 1) * 3;  // (plane, colour) pairs
+    const int upp = K.units_per_plane;
+    const int units = (K.batch - 1) * upp;  // (plane, colour) pairs, or whole planes of packed elements
     if (K.copy_vec4) {
         // CTA -> (unit, chunk): one division per CTA, then 16-byte accesses at a fixed stride, 4 in flight per thread
-        const int n4 = (int)(K.plane_px / 4);
+        const int n4 = (int)(K.unit_floats / 4);
         const int u = cta / K.copy_chunks;
         const int chunk = cta - u * K.copy_chunks;
         if (u >= units) return;
-        int z = u / 3;
-        const int c = u - z * 3;
+        int z = u / upp;
+        const int c = u - z * upp;
         if (z >= K.upd) ++z;  // skip the plane the compute CTAs write
         const int zs = ring_source(K, z);
         const float4* src = reinterpret_cast<const float4*>(K.ring_ro + zs * o.z_stride + c * o.c_stride);
@@ -102,13 +112,13 @@ __global__ void __launch_bounds__(256) circular_update_kernel(const __grid_const
                 if (i + k * 256 < hi) __stcs(dst + i + k * 256, r[k]);
         }
     } else {
-        const long long total = K.plane_px * units;
+        const long long total = K.unit_floats * units;
         const long long stride = (long long)ncopy * 256;
         for (long long j = (long long)cta * 256 + threadIdx.x; j < total; j += stride) {
-            const int u = (int)(j / K.plane_px);
-            const long long e = j - (long long)u * K.plane_px;
-            int z = u / 3;
-            const int c = u - z * 3;
+            const int u = (int)(j / K.unit_floats);
+            const long long e = j - (long long)u * K.unit_floats;
+            int z = u / upp;
+            const int c = u - z * upp;
             if (z >= K.upd) ++z;
             const int zs = ring_source(K, z);
             o.base[z * o.z_stride + c * o.c_stride + e] = K.ring_ro[zs * o.z_stride + c * o.c_stride + e];
@@ -117,7 +127,7 @@ __global__ void __launch_bounds__(256) circular_update_kernel(const __grid_const
 }
 
 struct CircularTensor {
-    int32_t w, h, cp, batch, order, mode, device;
+    int32_t w, h, cp, ec, batch, order, mode, device;  // cp colour planes of ec-channel elements
     float* pub = nullptr;
     float* ring = nullptr;
     int32_t next = 0;
@@ -129,21 +139,25 @@ using namespace cvgs;
 
 extern "C" {
 
-int cvgs_b200_ct_create(void** handle, int32_t width, int32_t height, int32_t color_planes, int32_t batch,
-                        int32_t order, int32_t plane_mode, int32_t device) {
+int cvgs_b200_ct_create_ex(void** handle, int32_t width, int32_t height, int32_t color_planes, int32_t elem_channels,
+                           int32_t batch, int32_t order, int32_t plane_mode, int32_t device) {
     if (!handle) return fail(CVGS_ERR_INVALID_VALUE, "handle is NULL");
     *handle = nullptr;
     if (width <= 0 || height <= 0 || batch <= 0) return fail(CVGS_ERR_INVALID_VALUE, "bad tensor shape");
-    if (color_planes != 3) return fail(CVGS_ERR_NOT_SUPPORTED, "only 3 colour planes are supported by this build");
+    // split tensors: 1, 3 or 4 colour planes of floats; packed tensors: one plane of float3 / float4 elements
+    const bool split = elem_channels == 1 && (color_planes == 1 || color_planes == 3 || color_planes == 4);
+    const bool packed = color_planes == 1 && (elem_channels == 3 || elem_channels == 4);
+    if (!split && !packed)
+        return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor: 1, 3 or 4 colour planes of floats, or one plane of 3- / 4-channel float pixels");
     if (order < 0 || order > 1 || plane_mode < 0 || plane_mode > 1) return fail(CVGS_ERR_INVALID_VALUE, "bad order/mode");
     int prev = 0;
     CVGS_CUDA(cudaGetDevice(&prev));
     CVGS_CUDA(cudaSetDevice(device));
     CircularTensor* t = new (std::nothrow) CircularTensor();
     if (!t) return fail(2 /*cudaErrorMemoryAllocation*/, "out of host memory");
-    t->w = width; t->h = height; t->cp = color_planes; t->batch = batch; t->order = order; t->mode = plane_mode;
+    t->w = width; t->h = height; t->cp = color_planes; t->ec = elem_channels; t->batch = batch; t->order = order; t->mode = plane_mode;
     t->device = device;
-    const size_t bytes = sizeof(float) * (size_t)width * height * color_planes * batch;
+    const size_t bytes = sizeof(float) * (size_t)width * height * color_planes * elem_channels * batch;
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&t->pub), bytes);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->ring), bytes);
     if (e == cudaSuccess) e = cudaMemset(t->pub, 0, bytes);
@@ -158,6 +172,11 @@ int cvgs_b200_ct_create(void** handle, int32_t width, int32_t height, int32_t co
     return CVGS_OK;
 }
 
+int cvgs_b200_ct_create(void** handle, int32_t width, int32_t height, int32_t color_planes, int32_t batch,
+                        int32_t order, int32_t plane_mode, int32_t device) {
+    return cvgs_b200_ct_create_ex(handle, width, height, color_planes, 1, batch, order, plane_mode, device);
+}
+
 int cvgs_b200_ct_update(void* handle, const cvgs_crop_t* frame, const cvgs_pipeline_t* pipeline, void* stream_) {
     CircularTensor* t = static_cast<CircularTensor*>(handle);
     if (!t) return fail(CVGS_ERR_INVALID_VALUE, "handle is NULL");
@@ -169,16 +188,20 @@ int cvgs_b200_ct_update(void* handle, const cvgs_crop_t* frame, const cvgs_pipel
                                                 std::to_string(cur_device));
     if (int rc = validate_pipeline(pipeline)) return rc;
     if (pipeline->dst_type == CVGS_8UC3 || pipeline->dst_type == CVGS_8UC4 || pipeline->out_row_pitch != 0) return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor planes are float");
-    if (channels_of(pipeline->src_type) != 3) return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor takes 3-channel frames");
+    if (CVGS_IS_YUV(pipeline->src_type)) return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor takes CV_8U / CV_16U / CV_16S frames");
     if (pipeline->dst_width != t->w || pipeline->dst_height != t->h)
         return fail(CVGS_ERR_INVALID_VALUE, "pipeline destination size must equal the tensor plane size");
     cvgs_pipeline_t p = *pipeline;
-    p.out_layout = t->mode == CVGS_CT_STANDARD ? CVGS_OUT_NCHW : CVGS_OUT_CNHW;
+    // packed elements: [z][y][x][channel] (TensorWrite); split: one plane per channel, plane-major or colour-major
+    p.out_layout = t->ec > 1 ? CVGS_OUT_NHWC : (t->mode == CVGS_CT_STANDARD ? CVGS_OUT_NCHW : CVGS_OUT_CNHW);
     p.out_plane_stride = 0;
+    p.dst_type = 0;
     CtParams K;
     std::memset(&K, 0, sizeof K);
     if (int rc = build_params(p, t->batch, 1, t->pub, K.pre)) return rc;
-    if (K.pre.prog.special) return fail(CVGS_ERR_NOT_SUPPORTED, "CircularTensor planes have 3 channels: no channel-count changing conversion");
+    if (K.pre.prog.nc_out != t->cp * t->ec)
+        return fail(CVGS_ERR_INVALID_VALUE, "the chain produces " + std::to_string(K.pre.prog.nc_out) + " channels, the tensor stores " +
+                                                std::to_string(t->cp * t->ec));
     DevCrop dc;
     if (int rc = fill_crop(*frame, p, 0, dc)) return rc;
     K.ring = t->ring;
@@ -189,7 +212,9 @@ int cvgs_b200_ct_update(void* handle, const cvgs_crop_t* frame, const cvgs_pipel
     K.upd = t->order == CVGS_CT_NEWEST_FIRST ? 0 : t->batch - 1;
     K.slot = (K.upd + t->next) % t->batch;
     K.plane_px = (long long)t->w * t->h;
-    K.copy_vec4 = (K.plane_px % 4) == 0;  // cudaMalloc bases are 256-byte aligned
+    K.units_per_plane = t->ec > 1 ? 1 : t->cp;
+    K.unit_floats = K.plane_px * (t->ec > 1 ? t->ec : 1);
+    K.copy_vec4 = (K.unit_floats % 4) == 0;  // cudaMalloc bases are 256-byte aligned
 
     // compute tiles: same block shape heuristic as the batch kernel
     const int qw = (t->w + 3) / 4;
@@ -207,16 +232,20 @@ int cvgs_b200_ct_update(void* handle, const cvgs_crop_t* frame, const cvgs_pipel
     K.compute_ctas = (int)compute;
     int copy_ctas = 0;
     if (t->batch > 1 && K.copy_vec4) {
-        K.copy_chunks = (int)((K.plane_px / 4 + kCtChunk - 1) / kCtChunk);
-        copy_ctas = K.copy_chunks * 3 * (t->batch - 1);
+        K.copy_chunks = (int)((K.unit_floats / 4 + kCtChunk - 1) / kCtChunk);
+        copy_ctas = K.copy_chunks * K.units_per_plane * (t->batch - 1);
     } else if (t->batch > 1) {
-        const long long work = K.plane_px * 3 * (t->batch - 1) / (K.copy_vec4 ? 16 : 1);  // thread-iterations
+        const long long work = K.unit_floats * K.units_per_plane * (t->batch - 1);  // thread-iterations
         const long long want = (work + 255) / 256;
         const long long cap = (long long)sm_count_of(t->device) * 8;
         copy_ctas = (int)std::max<long long>(1, std::min(want, cap));
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    circular_update_kernel<<<K.compute_ctas + copy_ctas, 256, 0, stream>>>(K, dc);
+    const int grid = K.compute_ctas + copy_ctas;
+    const int nc = K.pre.nc, nr = K.pre.prog.nregs;
+    if (nc == 3 && nr == 4) circular_update_kernel<3, 4><<<grid, 256, 0, stream>>>(K, dc);
+    else if (nc == 4) circular_update_kernel<4, 4><<<grid, 256, 0, stream>>>(K, dc);
+    else circular_update_kernel<3, 3><<<grid, 256, 0, stream>>>(K, dc);
     count_launch();
     CVGS_CUDA(cudaGetLastError());
     t->next = (t->next + 1) % t->batch;  // circular_tensor.cuh:144

@@ -965,6 +965,35 @@ int cvgs_b200_preproc_launch_ex(const cvgs_crop_t* crops, const cvgs_parent_t* p
                                static_cast<cudaStream_t>(stream));
 }
 
+int cvgs_b200_preproc_launch_rects(const void* frame, int32_t frame_width, int32_t frame_height, int32_t frame_pitch,
+                                   const cvgs_rect_t* rects, int32_t n_planes, int32_t used, const cvgs_pipeline_t* pipeline,
+                                   void* stream) {
+    if (!pipeline) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
+    if (!frame || frame_width <= 0 || frame_height <= 0 || frame_pitch <= 0) return fail(CVGS_ERR_INVALID_VALUE, "bad frame");
+    if (used < 0 || n_planes <= 0) return fail(CVGS_ERR_INVALID_VALUE, "bad batch size");
+    if (used > n_planes) used = n_planes;
+    if (used > 0 && !rects) return fail(CVGS_ERR_INVALID_VALUE, "rects is NULL");
+    if (CVGS_IS_YUV(pipeline->src_type)) return fail(CVGS_ERR_NOT_SUPPORTED, "YUV frames are read whole: no rectangles");
+    const int px = pixel_bytes_of(pipeline->src_type);
+    if (static_cast<long long>(px) * frame_width > frame_pitch && frame_height > 1) return fail(CVGS_ERR_INVALID_VALUE, "frame pitch smaller than a row");
+    // fk::Crop: thread (x, y) of plane i reads (x + rect.x, y + rect.y) of the frame, rect.width x rect.height threads
+    // (crop.cuh:23-55) -- the ROI pointer form of the batch launch, with the frame named as the parent of every crop
+    std::vector<cvgs_crop_t> crops(static_cast<size_t>(used));
+    std::vector<cvgs_parent_t> parents(static_cast<size_t>(used), cvgs_parent_t{frame, frame_width, frame_height});
+    for (int i = 0; i < used; ++i) {
+        const cvgs_rect_t& r = rects[i];
+        if (r.x < 0 || r.y < 0 || r.width <= 0 || r.height <= 0 || r.x > frame_width - r.width || r.y > frame_height - r.height)
+            return fail(CVGS_ERR_INVALID_VALUE, "rect " + std::to_string(i) + " outside the frame");
+        crops[i].data = static_cast<const uint8_t*>(frame) + static_cast<size_t>(r.y) * frame_pitch + static_cast<size_t>(px) * r.x;
+        crops[i].width = r.width;
+        crops[i].height = r.height;
+        crops[i].pitch = frame_pitch;
+        crops[i].reserved = 0;
+    }
+    return preproc_launch_impl(crops.data(), pipeline->src_type == CVGS_8UC3 ? parents.data() : nullptr, n_planes, used, pipeline,
+                               static_cast<float*>(pipeline->out), static_cast<cudaStream_t>(stream));
+}
+
 int cvgs_b200_preproc_launch_replicated(const cvgs_crop_t* crops, const cvgs_parent_t* parents, int32_t n_planes, int32_t used,
                                         const cvgs_pipeline_t* pipeline, void* const* replicas, int32_t n_replicas,
                                         void* stream) {

@@ -55,6 +55,8 @@ inline void check(int rc, const char* what) {
         throw std::runtime_error(std::string(what) + ": " + cvgs_b200_last_error() + " (code " + std::to_string(rc) + ")");
 }
 struct ReadBatch {  // cvGS::resize(...) result
+    cv::cuda::GpuMat frame;            // crop(read, rects) form: the one image ...
+    std::vector<cvgs_rect_t> rects;    // ... and the rectangles cut from it (then crops / parents stay empty)
     int yuv_standard = 0;  // CVGS_NV12 sources
     std::vector<cvgs_crop_t> crops;
     std::vector<cvgs_parent_t> parents;  // the image each ROI was cut from (GpuMat::datastart / dataend)
@@ -195,6 +197,98 @@ inline detail::ReadBatch resize(const cv::cuda::GpuMat& input, const cv::Size& d
         d.height = static_cast<int>(fy * input.rows + 0.5);
     }
     return resize<T, INTER_F, 1>(std::array<cv::cuda::GpuMat, 1>{input}, d, 1);
+}
+
+// ---- crop (reference :247-265, :444 -> fk::Crop<BackIOp>, fkl/.../image_processing/crop.cuh:23-55) ---------------
+// The reference's crop() overloads build fk::Crop operations that are composed with fk-level reads and resizes
+// (fkl/tests/algorithm/test_crop.cu:24-45): readIOp.then(Crop<>::build(rects)).then(Resize<INTER_LINEAR>::build(size)).
+// The same composition here: cvGS::read<T>(frame) is the read of a whole image (what fk::PerThreadRead<_2D, CUDA_T(T)>::
+// build(gpuMat2RawPtr2D(frame)) is in the reference), crop(...) the rectangles, cvGS::resize<INTER>(size[, used, bg]) the
+// incomplete resize; the result is the batch read executeOperations takes, backed by ONE
+// cvgs_b200_preproc_launch_rects call (device frame + rectangle list).
+namespace detail {
+struct CropOp {  // crop(rect) / crop<BATCH>(rects): incomplete until it follows a read
+    std::vector<cvgs_rect_t> rects;
+};
+struct CroppedRead;
+struct ImageRead {  // read of a whole image
+    cv::cuda::GpuMat image;
+    int type = 0;
+    inline CroppedRead then(const CropOp& c) const;  // readIOp.then(crop(rects))
+};
+struct ResizeOp {  // resize<INTER, AR>(size, used, bg): incomplete until it follows a read
+    int dst_w = 0, dst_h = 0, aspect = CVGS_IGNORE_AR, used = -1;
+    float bg[4] = {0, 0, 0, 0};
+};
+struct CroppedRead {  // read.then(crop(...)) / crop(read, ...)
+    ImageRead src;
+    std::vector<cvgs_rect_t> rects;
+    // .then(resize(...)): the batch read of the hot path, one plane per rectangle
+    ReadBatch then(const ResizeOp& rs) const {
+        ReadBatch r;
+        r.n_planes = static_cast<int>(rects.size());
+        r.used = rs.used < 0 ? r.n_planes : std::min(rs.used, r.n_planes);
+        r.dst_w = rs.dst_w;
+        r.dst_h = rs.dst_h;
+        r.aspect = rs.aspect;
+        r.src_type = src.type;
+        for (int c = 0; c < 4; ++c) r.bg[c] = rs.bg[c];
+        r.frame = src.image;
+        r.rects = rects;
+        return r;
+    }
+    // without a resize: BatchRead of equally sized rectangles, pixels bit for bit (scale exactly 1)
+    operator ReadBatch() const {
+        if (rects.empty()) throw std::runtime_error("cvGS::crop: no rectangles");
+        for (const cvgs_rect_t& q : rects)
+            if (q.width != rects[0].width || q.height != rects[0].height)
+                throw std::runtime_error("cvGS::crop without a resize: the rectangles of a batch must have one size");
+        ResizeOp rs;
+        rs.dst_w = rects[0].width;
+        rs.dst_h = rects[0].height;
+        return then(rs);
+    }
+};
+inline CroppedRead ImageRead::then(const CropOp& c) const { return CroppedRead{*this, c.rects}; }
+inline cvgs_rect_t rect_of(const cv::Rect2d& r) {  // the casts of the reference (:248)
+    return cvgs_rect_t{static_cast<int32_t>(static_cast<unsigned>(r.x)), static_cast<int32_t>(static_cast<unsigned>(r.y)),
+                       static_cast<int32_t>(r.width), static_cast<int32_t>(r.height)};
+}
+}  // namespace detail
+template <int T>
+inline detail::ImageRead read(const cv::cuda::GpuMat& image) {
+    static_assert(T == CV_8UC3 || T == CV_16UC3 || T == CV_16SC3 || T == CV_8UC4 || T == CV_16UC4 || T == CV_16SC4,
+                  "cvGS (B200 build): CV_8U / CV_16U / CV_16S images with 3 or 4 channels");
+    return detail::ImageRead{image, T};
+}
+inline detail::CropOp crop(const cv::Rect2d& rect) { return detail::CropOp{{detail::rect_of(rect)}}; }
+template <int BATCH>
+inline detail::CropOp crop(const std::array<cv::Rect2d, BATCH>& rects) {
+    detail::CropOp c;
+    for (const cv::Rect2d& r : rects) c.rects.push_back(detail::rect_of(r));
+    return c;
+}
+inline detail::CroppedRead crop(const detail::ImageRead& backIOp, const cv::Rect2d& rect) {
+    return detail::CroppedRead{backIOp, {detail::rect_of(rect)}};
+}
+template <size_t BATCH>
+inline detail::CroppedRead crop(const detail::ImageRead& backIOp, const std::array<cv::Rect2d, BATCH>& rects) {
+    detail::CroppedRead c{backIOp, {}};
+    for (const cv::Rect2d& r : rects) c.rects.push_back(detail::rect_of(r));
+    return c;
+}
+// crop(backIOp, rects) of the reference is backIOp.then(crop(rects)) (:444)
+// the incomplete resize that follows a read (fk::Resize<INTER_LINEAR, AR>::build(size), resize.cuh:84-98)
+template <int INTER_F, AspectRatio AR_ = IGNORE_AR>
+inline detail::ResizeOp resize(const cv::Size& dsize, int usedPlanes = -1, const cv::Scalar& backgroundValue = cv::Scalar()) {
+    static_assert(INTER_F == cv::INTER_LINEAR, "cvGS (B200 build): only INTER_LINEAR is implemented (as in the reference)");
+    detail::ResizeOp r;
+    r.dst_w = dsize.width;
+    r.dst_h = dsize.height;
+    r.aspect = static_cast<int>(AR_);
+    r.used = usedPlanes;
+    for (int c = 0; c < 4; ++c) r.bg[c] = static_cast<float>(backgroundValue[c]);
+    return r;
 }
 
 // NV12 frames (decoder output) as sources.  The reference reaches this through its fk:: layer only
@@ -382,6 +476,13 @@ inline void executeOperations(const cv::cuda::Stream& stream, const detail::Read
     p.yuv_standard = read.yuv_standard;
     for (int c = 0; c < 4; ++c) p.background[c] = read.bg[c];
     (detail::append(p, iops), ...);
+    if (!read.rects.empty()) {  // crop(read, rects)[.then(resize)]: one device frame + its rectangles
+        detail::check(cvgs_b200_preproc_launch_rects(read.frame.data, read.frame.cols, read.frame.rows, static_cast<int32_t>(read.frame.step),
+                                                     read.rects.data(), read.n_planes, read.used, &p,
+                                                     cv::cuda::StreamAccessor::getStream(stream)),
+                      "cvGS::executeOperations");
+        return;
+    }
     detail::check(cvgs_b200_preproc_launch_ex(read.crops.data(), read.parents.empty() ? nullptr : read.parents.data(),
                                               read.n_planes, read.used, &p, cv::cuda::StreamAccessor::getStream(stream)),
                   "cvGS::executeOperations");
@@ -571,8 +672,14 @@ inline void executeOperations(const cv::cuda::GpuMat& input, cv::cuda::GpuMat& o
 template <int I, int O, int COLOR_PLANES, int BATCH, fk::CircularTensorOrder CT_ORDER,
           fk::ColorPlanes CP_MODE = fk::ColorPlanes::Standard>
 class CircularTensor {
-    static_assert((I == CV_8UC3 || I == CV_16UC3 || I == CV_16SC3) && CV_MAT_DEPTH(O) == CV_32F && COLOR_PLANES == 3,
-                  "cvGS (B200 build): CircularTensor<CV_8UC3 | CV_16UC3 | CV_16SC3, CV_32F, 3, ...> are the supported instantiations");
+    // O names the tensor's element: a depth (CV_32F: planes of floats, COLOR_PLANES of them) or, with COLOR_PLANES == 1, a
+    // packed pixel type (CV_32FC3 / CV_32FC4: TensorWrite, reference test_circularbatchread_x_write3D.cu:400-460)
+    static constexpr int kElemChannels = COLOR_PLANES == 1 ? CV_MAT_CN(O) : 1;
+    static_assert((I == CV_8UC3 || I == CV_16UC3 || I == CV_16SC3 || I == CV_8UC4 || I == CV_16UC4 || I == CV_16SC4) &&
+                      CV_MAT_DEPTH(O) == CV_32F && (COLOR_PLANES == 1 || COLOR_PLANES == 3 || COLOR_PLANES == 4) &&
+                      (kElemChannels == 1 || kElemChannels == 3 || kElemChannels == 4),
+                  "cvGS (B200 build): CircularTensor of CV_8U / CV_16U / CV_16S frames with 3 or 4 channels into 1, 3 or 4 float planes, or "
+                  "into one plane of CV_32FC3 / CV_32FC4 pixels");
 
 public:
     CircularTensor() = default;
@@ -587,11 +694,11 @@ public:
         h_ = nullptr;
         w_ = width_;
         hgt_ = height_;
-        detail::check(cvgs_b200_ct_create(&h_, static_cast<int>(width_), static_cast<int>(height_), COLOR_PLANES, BATCH,
-                                          CT_ORDER == fk::CircularTensorOrder::NewestFirst ? CVGS_CT_NEWEST_FIRST
-                                                                                           : CVGS_CT_OLDEST_FIRST,
-                                          CP_MODE == fk::ColorPlanes::Standard ? CVGS_CT_STANDARD : CVGS_CT_TRANSPOSED,
-                                          deviceID_),
+        detail::check(cvgs_b200_ct_create_ex(&h_, static_cast<int>(width_), static_cast<int>(height_), COLOR_PLANES, kElemChannels, BATCH,
+                                             CT_ORDER == fk::CircularTensorOrder::NewestFirst ? CVGS_CT_NEWEST_FIRST
+                                                                                              : CVGS_CT_OLDEST_FIRST,
+                                             CP_MODE == fk::ColorPlanes::Standard ? CVGS_CT_STANDARD : CVGS_CT_TRANSPOSED,
+                                             deviceID_),
                       "CircularTensor::Alloc");
     }
     // update(stream, frame, ops..., write): the trailing write names this tensor in the reference
@@ -619,7 +726,7 @@ public:
         r.dims = {w_, hgt_, BATCH, COLOR_PLANES};
         return r;
     }
-    size_t sizeInBytes() const { return sizeof(float) * w_ * hgt_ * BATCH * COLOR_PLANES; }
+    size_t sizeInBytes() const { return sizeof(float) * w_ * hgt_ * BATCH * COLOR_PLANES * kElemChannels; }
 
 private:
     void* h_ = nullptr;

@@ -79,6 +79,11 @@ struct Rect {
     Rect() = default;
     Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {}
 };
+struct Rect2d {
+    double x = 0, y = 0, width = 0, height = 0;
+    Rect2d() = default;
+    Rect2d(double x_, double y_, double w, double h) : x(x_), y(y_), width(w), height(h) {}
+};
 struct Scalar {
     double val[4] = {0, 0, 0, 0};
     Scalar() = default;

@@ -239,6 +239,17 @@ typedef struct cvgs_parent {
 int cvgs_b200_preproc_launch_ex(const cvgs_crop_t* crops, const cvgs_parent_t* parents, int32_t n_planes,
                                 int32_t used, const cvgs_pipeline_t* pipeline, void* stream);
 
+/* The same launch with the crops given as rectangles of ONE device frame: what
+ *   cvGS::crop(readOfFrame, rects) / readOfFrame.then(cvGS::crop<BATCH>(rects))   [.then(Resize)]
+ * builds (reference include/cvGPUSpeedup.cuh:247-265,444 -> fk::Crop<BackIOp>, fkl/.../image_processing/crop.cuh:23-55:
+ * thread (x, y) of plane i reads pixel (x + rect.x, y + rect.y), rect.width x rect.height of them).  Rectangles must lie
+ * inside the frame; the frame is named as every crop's parent, so the launch takes the cached per-image tensor maps.
+ * Without a resize the caller passes dst size == rect size (all rectangles equal), which reads the pixels bit for bit. */
+typedef struct cvgs_rect { int32_t x, y, width, height; } cvgs_rect_t;
+int cvgs_b200_preproc_launch_rects(const void* frame, int32_t frame_width, int32_t frame_height, int32_t frame_pitch,
+                                   const cvgs_rect_t* rects, int32_t n_planes, int32_t used,
+                                   const cvgs_pipeline_t* pipeline, void* stream);
+
 /* The same launch writing its tensor more than once: at pipeline->out and at each of replicas[0 .. n_replicas) (at most
  * 7), all with the layout the pipeline describes.  Meant for BASELINE config 5 -- crops sharded over the GPUs of one box,
  * every GPU ending with the whole [N][3][H][W] tensor: replicas are the other GPUs' tensors mapped into this process
@@ -285,7 +296,6 @@ int cvgs_b200_warp_launch(const cvgs_crop_t* images, const cvgs_warp_t* warps, i
  * `pipeline->out` is ignored; the result goes to host_out (tight layout; channels as the chain leaves them).
  * Device staging buffers are owned by the library and reused across calls.  The frame is copied with
  * cudaMemcpy2DAsync, whole rows from the first to the last row a crop touches (see cvgs_b200_set_host_upload). */
-typedef struct cvgs_rect { int32_t x, y, width, height; } cvgs_rect_t;
 int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t image_height,
                            int32_t image_pitch, const cvgs_rect_t* rects, int32_t n_planes,
                            int32_t used, const cvgs_pipeline_t* pipeline, float* host_out,
@@ -387,6 +397,13 @@ enum cvgs_ct_planes { CVGS_CT_STANDARD = 0, CVGS_CT_TRANSPOSED = 1 };      /* fk
 /* ctor / Alloc(width, height, deviceID) */
 int cvgs_b200_ct_create(void** handle, int32_t width, int32_t height, int32_t color_planes,
                         int32_t batch, int32_t order, int32_t plane_mode, int32_t device);
+/* The other instantiations of the reference (include/cvGPUSpeedup.cuh:600-627; tests/batchread/
+ * test_circularbatchread_x_write3D.cu:400-460): color_planes 1, 3 or 4 planes of floats (elem_channels 1: TensorSplit /
+ * TensorTSplit of a 1-, 3- or 4-channel pixel), or ONE plane of packed elem_channels = 3 / 4 float pixels (TensorWrite of
+ * float3 / float4: cvGS::CircularTensor<CV_8UC4, CV_32FC4, 1, ...>).  The update's chain must end with color_planes *
+ * elem_channels channels.  cvgs_b200_ct_create is the elem_channels = 1 form. */
+int cvgs_b200_ct_create_ex(void** handle, int32_t width, int32_t height, int32_t color_planes, int32_t elem_channels,
+                           int32_t batch, int32_t order, int32_t plane_mode, int32_t device);
 /* update(stream, frame, ops..., write): runs `pipeline` (its out/out_layout/out_plane_stride
  * fields are ignored, dst size must equal the tensor plane size) on the new frame, stores it
  * as the newest plane and shifts the other BATCH-1 planes by one position. */

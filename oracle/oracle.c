@@ -472,18 +472,23 @@ int oracle_warp(const cvgs_crop_t* images, const cvgs_warp_t* warps, int n_plane
  * Host memory; planes are [batch][color][H][W] (Standard) or [color][batch][H][W] (Transposed).
  * ------------------------------------------------------------------------------------------- */
 typedef struct oracle_ct {
-    int w, h, cp, batch, order, mode, next;
+    int w, h, cp, ec, batch, order, mode, next;  /* cp colour planes of ec-channel elements */
     float* pub;  /* `this` tensor  */
     float* tmp;  /* m_tempTensor   */
 } oracle_ct_t;
 
-oracle_ct_t* oracle_ct_create(int w, int h, int cp, int batch, int order, int mode) {
+/* cp in {1, 3, 4} planes of floats (ec = 1), or one plane of packed ec = 3 / 4 float pixels (TensorWrite; the
+ * reference's CircularTensor<CV_8UC4, CV_32FC4, 1, ...>, tests/batchread/test_circularbatchread_x_write3D.cu:400-460). */
+oracle_ct_t* oracle_ct_create_ex(int w, int h, int cp, int ec, int batch, int order, int mode) {
     oracle_ct_t* t = (oracle_ct_t*)calloc(1, sizeof *t);
-    t->w = w; t->h = h; t->cp = cp; t->batch = batch; t->order = order; t->mode = mode;
-    const size_t n = (size_t)w * h * cp * batch;
+    t->w = w; t->h = h; t->cp = cp; t->ec = ec; t->batch = batch; t->order = order; t->mode = mode;
+    const size_t n = (size_t)w * h * cp * ec * batch;
     t->pub = (float*)calloc(n, sizeof(float));
     t->tmp = (float*)calloc(n, sizeof(float));
     return t;
+}
+oracle_ct_t* oracle_ct_create(int w, int h, int cp, int batch, int order, int mode) {
+    return oracle_ct_create_ex(w, h, cp, 1, batch, order, mode);
 }
 void oracle_ct_destroy(oracle_ct_t* t) { if (t) { free(t->pub); free(t->tmp); free(t); } }
 float* oracle_ct_data(oracle_ct_t* t) { return t->pub; }
@@ -491,22 +496,23 @@ float* oracle_ct_data(oracle_ct_t* t) { return t->pub; }
 float* oracle_ct_temp(oracle_ct_t* t) { return t->tmp; }
 
 static float* ct_plane(const oracle_ct_t* t, float* base, int z, int c) {
-    const size_t px = (size_t)t->w * t->h;
+    const size_t px = (size_t)t->w * t->h * t->ec;
     return t->mode == CVGS_CT_STANDARD ? base + ((size_t)z * t->cp + c) * px
                                        : base + ((size_t)c * t->batch + z) * px;
 }
 
 int oracle_ct_update(oracle_ct_t* t, const cvgs_crop_t* frame, const cvgs_pipeline_t* p_in, int nthreads) {
-    if (!t || !frame || !p_in || p_in->dst_width != t->w || p_in->dst_height != t->h || t->cp != 3) return 1;
-    const size_t px = (size_t)t->w * t->h;
-    float* fresh = (float*)malloc(px * 3 * sizeof(float));
+    if (!t || !frame || !p_in || p_in->dst_width != t->w || p_in->dst_height != t->h) return 1;
+    const size_t px = (size_t)t->w * t->h * t->ec;  /* floats per colour plane */
+    float* fresh = (float*)malloc(px * t->cp * sizeof(float));
     cvgs_pipeline_t p = *p_in;
-    p.out = fresh; p.out_layout = CVGS_OUT_NCHW; p.out_plane_stride = 0;
+    /* the chain must end with cp * ec channels; packed elements are written pixel-interleaved */
+    p.out = fresh; p.out_layout = t->ec > 1 ? CVGS_OUT_NHWC : CVGS_OUT_NCHW; p.out_plane_stride = 0; p.dst_type = 0;
     const int rc = oracle_preproc(frame, 1, 1, &p, nthreads);
     if (rc) { free(fresh); return rc; }
     const int B = t->batch, first = t->next;
     const int upd = t->order == CVGS_CT_NEWEST_FIRST ? 0 : B - 1;
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < t->cp; ++c) {
         /* update sequence: MidWrite CircularTensorWrite<Ascendent> -> temp[(upd + first) mod B],
          * then the user's write -> this[upd]. */
         int zt = upd + first; if (zt >= B) zt -= B;

@@ -91,6 +91,27 @@ static int test_circular_tensor() {
     return 0;
 }
 
+// tests/batchread/test_circularbatchread_x_write3D.cu:400-460 (testOldestFirstCircularTensorcvGS_noSplit): CV_8UC4 frames
+// into ONE plane of packed CV_32FC4 pixels, OldestFirst; after 100 updates plane z holds 100 - (BATCH - z - 1).
+static int test_circular_tensor_no_split() {
+    constexpr int BATCH = 15, WIDTH = 128, HEIGHT = 128, ITERS = 100;
+    cvGS::CircularTensor<CV_8UC4, CV_32FC4, 1, BATCH, fk::CircularTensorOrder::OldestFirst> myTensor(WIDTH, HEIGHT);
+    REQUIRE(myTensor.sizeInBytes() == sizeof(float) * 4 * WIDTH * HEIGHT * BATCH);
+    cv::cuda::GpuMat input(HEIGHT, WIDTH, CV_8UC4);
+    cv::cuda::Stream cv_stream;
+    for (int i = 0; i < ITERS; ++i) {
+        input.setTo(cv::Scalar::all(i + 1));
+        myTensor.update(cv_stream, input, cvGS::convertTo<CV_8UC4, CV_32FC4>());
+        cv_stream.waitForCompletion();
+    }
+    std::vector<float> h(myTensor.sizeInBytes() / sizeof(float));
+    REQUIRE(cudaMemcpy(h.data(), myTensor.data(), myTensor.sizeInBytes(), cudaMemcpyDeviceToHost) == cudaSuccess);
+    const size_t px = static_cast<size_t>(WIDTH) * HEIGHT * 4;
+    for (int z = 0; z < BATCH; ++z)
+        for (size_t i = 0; i < px; ++i) REQUIRE(h[z * px + i] == static_cast<float>(ITERS - (BATCH - z - 1)));
+    return 0;
+}
+
 static int test_split() {
     cv::cuda::GpuMat d_input(16, 16, CV_8UC3, cv::Scalar(1, 2, 3));
     cv::cuda::GpuMat d_out(1, 16 * 16 * 3, CV_32FC1);
@@ -474,6 +495,74 @@ static int test_read_x_write_and_8uc4() {
     return 0;
 }
 
+// fkl/tests/algorithm/test_crop.cu:24-45 composed through the cvGS crop() overloads (include/cvGPUSpeedup.cuh:247-265,444):
+// read.then(crop(rects)).then(resize(Size(100, 100))) has 100 x 100 x 2 active threads; crop(read, rect) shifts the
+// thread by (rect.x, rect.y) and has rect.width x rect.height of them.  Values against the oracle.
+static int test_crop() {
+    constexpr int W = 128, H = 128;
+    std::mt19937 rng(11);
+    cv::cuda::GpuMat d_img(H, W, CV_8UC3);
+    std::vector<uchar> h_img(d_img.step * H);
+    for (auto& b : h_img) b = static_cast<uchar>(rng());
+    REQUIRE(cudaMemcpy(d_img.data, h_img.data(), h_img.size(), cudaMemcpyHostToDevice) == cudaSuccess);
+    cv::cuda::Stream st;
+    const auto readIOp = cvGS::read<CV_8UC3>(d_img);
+    const std::array<cv::Rect2d, 2> rects{cv::Rect2d(10, 12, 20, 30), cv::Rect2d(15, 15, 50, 20)};
+    auto oracle_of = [&](const cv::Rect2d* rs, int n, cv::Size dst, std::vector<float>& want) {
+        std::vector<cvgs_crop_t> hc(n);
+        for (int i = 0; i < n; ++i)
+            hc[i] = {h_img.data() + static_cast<int>(rs[i].y) * d_img.step + 3 * static_cast<int>(rs[i].x), static_cast<int>(rs[i].width),
+                     static_cast<int>(rs[i].height), static_cast<int32_t>(d_img.step), 0};
+        cvgs_pipeline_t p{};
+        p.src_type = CVGS_8UC3;
+        p.dst_width = dst.width;
+        p.dst_height = dst.height;
+        p.aspect_mode = CVGS_IGNORE_AR;
+        p.n_ops = 1;
+        p.ops[0].kind = CVGS_OP_MUL;
+        for (int c = 0; c < 3; ++c) p.ops[0].v[c] = 0.5f;
+        want.assign(static_cast<size_t>(n) * 3 * dst.width * dst.height, -1.f);
+        p.out = want.data();
+        return oracle_preproc(hc.data(), n, n, &p, 0);
+    };
+    // 1. batch crop + resize: both spellings of the reference
+    for (int spelling = 0; spelling < 2; ++spelling) {
+        const cv::Size dst(100, 100);
+        cv::cuda::GpuMat d_out(2, dst.width * dst.height * 3, CV_32FC1);
+        const cvGS::detail::CroppedRead cropped = spelling == 0 ? readIOp.then(cvGS::crop<2>(rects)) : cvGS::crop(readIOp, rects);
+        REQUIRE(cropped.rects.size() == 2 && cropped.rects[1].x == 15 && cropped.rects[1].width == 50);
+        cvGS::executeOperations(st, cropped.then(cvGS::resize<cv::INTER_LINEAR>(dst)), cvGS::multiply<CV_32FC3>(cv::Scalar(0.5, 0.5, 0.5)),
+                                cvGS::split<CV_32FC3>(d_out, dst));
+        st.waitForCompletion();
+        std::vector<float> got(static_cast<size_t>(2) * 3 * dst.width * dst.height), want;
+        REQUIRE(cudaMemcpy(got.data(), d_out.data, got.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess);
+        REQUIRE(oracle_of(rects.data(), 2, dst, want) == 0);
+        REQUIRE(std::memcmp(got.data(), want.data(), got.size() * 4) == 0);
+    }
+    // 2. one crop, no resize: the pixels of the rectangle, bit for bit (times 0.5)
+    {
+        const cv::Rect2d one(11, 9, 10, 10);
+        cv::cuda::GpuMat d_out(1, 10 * 10 * 3, CV_32FC1);
+        cvGS::executeOperations(st, cvGS::crop(readIOp, one), cvGS::multiply<CV_32FC3>(cv::Scalar(0.5, 0.5, 0.5)),
+                                cvGS::split<CV_32FC3>(d_out, cv::Size(10, 10)));
+        st.waitForCompletion();
+        std::vector<float> got(3 * 10 * 10);
+        REQUIRE(cudaMemcpy(got.data(), d_out.data, got.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess);
+        for (int c = 0; c < 3; ++c)
+            for (int y = 0; y < 10; ++y)
+                for (int x = 0; x < 10; ++x)
+                    REQUIRE(got[(c * 10 + y) * 10 + x] == 0.5f * h_img[(9 + y) * d_img.step + 3 * (11 + x) + c]);
+    }
+    // 3. a rectangle that leaves the image is an error (std::runtime_error, like gpuErrchk)
+    bool threw = false;
+    try {
+        cv::cuda::GpuMat d_out(1, 8 * 8 * 3, CV_32FC1);
+        cvGS::executeOperations(st, cvGS::crop(readIOp, cv::Rect2d(125, 0, 8, 8)), cvGS::split<CV_32FC3>(d_out, cv::Size(8, 8)));
+    } catch (const std::runtime_error&) { threw = true; }
+    REQUIRE(threw);
+    return 0;
+}
+
 static int test_error_convention() {
     cv::cuda::GpuMat d_input(16, 16, CV_8UC3, cv::Scalar(1, 2, 3));
     cv::cuda::GpuMat d_null;  // data == nullptr
@@ -496,6 +585,7 @@ int main() {
     failed += test_circular_tensor<fk::CircularTensorOrder::NewestFirst, fk::ColorPlanes::Transposed>();
     failed += test_circular_tensor<fk::CircularTensorOrder::OldestFirst, fk::ColorPlanes::Standard>();
     failed += test_circular_tensor<fk::CircularTensorOrder::OldestFirst, fk::ColorPlanes::Transposed>();
+    failed += test_circular_tensor_no_split();
     failed += test_split();
     failed += test_resize_x_split_write();
     failed += test_batchread_x_write3D();
@@ -504,6 +594,7 @@ int main() {
     failed += test_warping();
     failed += test_cvtcolor_channel_changes();
     failed += test_read_x_write_and_8uc4();
+    failed += test_crop();
     failed += test_error_convention();
     std::printf(failed ? "test_shim: %d FAILED\n" : "test_shim: all passed\n", failed);
     return failed ? 1 : 0;

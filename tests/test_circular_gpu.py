@@ -62,7 +62,7 @@ def test_errors():
     lib = _abi.load()
     h = C.c_void_p()
     assert lib.cvgs_b200_ct_create(C.byref(h), 0, 10, 3, 4, 0, 0, 0) == 1
-    assert lib.cvgs_b200_ct_create(C.byref(h), 16, 16, 4, 4, 0, 0, 0) == 801
+    assert lib.cvgs_b200_ct_create(C.byref(h), 16, 16, 2, 4, 0, 0, 0) == 801  # 1, 3 or 4 colour planes
     ct = cvgs.CircularTensor(16, 16, 3)
     frame = torch.zeros((16, 16, 3), dtype=torch.uint8, device="cuda")
     p = util.make_pipeline((8, 8), [])
@@ -169,3 +169,42 @@ def test_three_way_against_the_reference_kernel(order, depth, shape, swap):
     lib.oracle_ct_destroy(o)
     ct.close()
     ref.fkref_ct_destroy(h)
+
+
+@pytest.mark.parametrize("case", [
+    # (frame type, px bytes, colour planes, element channels, chain)  -- reference include/cvGPUSpeedup.cuh:600-627
+    ("8UC4->4 planes", _abi.CVGS_8UC4, 4, 4, 1, [("mul", (0.5, 0.25, 2.0, 1.0)), ("sub", (1.0, 2.0, 3.0, 4.0))]),
+    ("8UC4->packed float4 (test_circularbatchread_x_write3D.cu:400-460)", _abi.CVGS_8UC4, 4, 1, 4, [("mul", (0.5, 0.25, 2.0, 1.0))]),
+    ("8UC3->packed float3", _abi.CVGS_8UC3, 3, 1, 3, [("reorder", (2, 1, 0)), ("mul", (0.5, 0.25, 2.0))]),
+    ("8UC3->gray, one plane", _abi.CVGS_8UC3, 3, 1, 1, [("gray", (1,)), ("mul", (0.5,))]),
+    ("16UC4->4 planes", _abi.CVGS_16UC4, 8, 4, 1, [("mul", (0.001, 0.002, 0.003, 0.004))]),
+    ("8UC3->RGBA planes", _abi.CVGS_8UC3, 3, 4, 1, [("add_alpha", (255.0,)), ("mul", (0.5, 0.5, 0.5, 0.5))]),
+], ids=lambda c: c[0])
+@pytest.mark.parametrize("order", [_abi.CT_NEWEST_FIRST, _abi.CT_OLDEST_FIRST])
+@pytest.mark.parametrize("mode", [_abi.CT_STANDARD, _abi.CT_TRANSPOSED])
+def test_other_colour_plane_counts_and_packed_elements(case, order, mode):
+    """COLOR_PLANES 1 / 4, packed float3 / float4 elements and 4-channel frames against the oracle state machine."""
+    _name, src_type, px, cp, ec, ops = case
+    W, H, fw, fh, B = 40, 24, 100, 60, 3
+    lib, olib = _abi.load(), util.oracle_lib()
+    o = olib.oracle_ct_create_ex(W, H, cp, ec, B, order, mode)
+    h = C.c_void_p()
+    _abi.check(lib.cvgs_b200_ct_create_ex(C.byref(h), W, H, cp, ec, B, order, mode, 0))
+    rng = np.random.default_rng(8)
+    p = util.make_pipeline((W, H), ops, src_type=src_type)
+    n_floats = B * cp * ec * H * W
+    for i in range(2 * B + 1):
+        img = rng.integers(0, 256, size=(fh, px * fw), dtype=np.uint8)
+        d = torch.from_numpy(img).cuda()
+        assert olib.oracle_ct_update(o, util.host_crops(img, [(0, 0, fw, fh)], px_bytes=px), C.byref(p), 0) == 0
+        _abi.check(lib.cvgs_b200_ct_update(h, util.host_crops(img, [(0, 0, fw, fh)], base_ptr=d.data_ptr(), px_bytes=px), C.byref(p), None))
+        torch.cuda.synchronize()
+        got = cvgs.api.device_view(lib.cvgs_b200_ct_data(h), (n_floats,)).cpu().numpy()
+        want = np.ctypeslib.as_array(olib.oracle_ct_data(o), shape=(n_floats,))
+        util.assert_bit_equal(got, want, f"update {i}")
+    # a chain that ends with another channel count is refused
+    bad = util.make_pipeline((W, H), [("gray", (1,))] if cp * ec != 1 else [], src_type=src_type)
+    crop = util.host_crops(img, [(0, 0, fw, fh)], base_ptr=d.data_ptr(), px_bytes=px)
+    assert lib.cvgs_b200_ct_update(h, crop, C.byref(bad), None) == 1 and b"channels" in lib.cvgs_b200_last_error()
+    olib.oracle_ct_destroy(o)
+    lib.cvgs_b200_ct_destroy(h)

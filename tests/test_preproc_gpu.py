@@ -182,6 +182,32 @@ def test_host_buffer_entry_point():
         util.assert_bit_equal(h_out.numpy(), util.run_oracle(w.image, w.rects, w.dsize, w.ops), "host entry point")
 
 
+@pytest.mark.parametrize("src_type,px", [(_abi.CVGS_8UC3, 3), (_abi.CVGS_16UC3, 6), (_abi.CVGS_8UC4, 4)])
+def test_rectangles_of_a_device_frame(src_type, px):
+    """cvgs_b200_preproc_launch_rects (cvGS::crop(read, rects)[.then(resize)], fk::Crop crop.cuh:23-55): a device frame +
+    a rectangle list equals the ROI-pointer launch; partial batches, and rectangles outside the frame are refused."""
+    lib = _abi.load()
+    rng = np.random.default_rng(91)
+    fw, fh = 400, 300
+    pitch = (px * fw + 63) // 64 * 64
+    img = rng.integers(0, 256, size=(fh, pitch), dtype=np.uint8)
+    rects = [(0, 0, 400, 300), (399, 299, 1, 1), (17, 23, 100, 50), (200, 10, 64, 128), (3, 200, 333, 77), (50, 60, 70, 80)]
+    n = len(rects) + 2
+    nc = util.channels_of(src_type)
+    ops = [("mul", (0.5,) * nc), ("sub", (1.0, 2.0, 3.0, 4.0)[:nc])]
+    d_img = torch.from_numpy(img).cuda()
+    out = torch.full((n, nc, 128, 64), float("nan"), device="cuda")
+    p = util.make_pipeline((64, 128), ops, out_ptr=out.data_ptr(), src_type=src_type, background=(9, 8, 7, 6)[:nc])
+    r_arr = (_abi.Rect * len(rects))(*[_abi.Rect(*r) for r in rects])
+    _abi.check(lib.cvgs_b200_preproc_launch_rects(d_img.data_ptr(), fw, fh, pitch, r_arr, n, len(rects), C.byref(p), None))
+    torch.cuda.synchronize()
+    want = util.run_oracle(img, rects, (64, 128), ops, n_planes=n, used=len(rects), src_type=src_type, background=(9, 8, 7, 6)[:nc])
+    util.assert_bit_equal(out.cpu().numpy(), want, "rectangles of a device frame")
+    bad = (_abi.Rect * 1)(_abi.Rect(390, 0, 20, 20))
+    assert lib.cvgs_b200_preproc_launch_rects(d_img.data_ptr(), fw, fh, pitch, bad, 1, 1, C.byref(p), None) == 1
+    assert b"outside" in lib.cvgs_b200_last_error()
+
+
 @pytest.fixture()
 def tile_upload():
     lib = _abi.load()

@@ -39,6 +39,8 @@ def oracle_lib() -> C.CDLL:
         lib.oracle_resize_geometry.argtypes = [C.c_int] * 5 + [C.POINTER(Geom)]
         lib.oracle_ct_create.restype = C.c_void_p
         lib.oracle_ct_create.argtypes = [C.c_int] * 6
+        lib.oracle_ct_create_ex.restype = C.c_void_p
+        lib.oracle_ct_create_ex.argtypes = [C.c_int] * 7
         lib.oracle_ct_destroy.argtypes = [C.c_void_p]
         lib.oracle_ct_data.restype = C.POINTER(C.c_float)
         lib.oracle_ct_data.argtypes = [C.c_void_p]
