@@ -21,6 +21,7 @@
 #include "cvgs_runtime.hpp"
 #include "preproc_direct.cuh"
 #include "preproc_host.hpp"
+#include "preproc_tma.cuh"  // specialize_division
 
 namespace cvgs {
 
@@ -202,6 +203,7 @@ int cvgs_b200_ct_update(void* handle, const cvgs_crop_t* frame, const cvgs_pipel
     if (K.pre.prog.nc_out != t->cp * t->ec)
         return fail(CVGS_ERR_INVALID_VALUE, "the chain produces " + std::to_string(K.pre.prog.nc_out) + " channels, the tensor stores " +
                                                 std::to_string(t->cp * t->ec));
+    specialize_division(K.pre.prog, K.pre.nc, K.pre.bg);
     DevCrop dc;
     if (int rc = fill_crop(*frame, p, 0, dc)) return rc;
     K.ring = t->ring;

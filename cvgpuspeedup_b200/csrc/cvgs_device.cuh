@@ -37,7 +37,9 @@ static_assert(sizeof(DevCrop) == 48, "DevCrop layout");
 // DOP_GRAY: register 0 = float(int_rn(0.299 x + 0.587 y + 0.114 z)) with x, y, z = registers (kind >> 8) & 3, (kind >> 12) & 3,
 // (kind >> 16) & 3; bit 20: every product and sum rounded on its own (CVGS_FP_SEPARATE) instead of FMUL, FFMA, FFMA;
 // bit 21: the stand-alone FMUL is y * 0.587 (else x * 0.299).
-enum DevOpKind : int32_t { DOP_MUL = 1, DOP_ADD = 2, DOP_DIV = 3, DOP_FMA = 4, DOP_SET = 5, DOP_GRAY = 6 };
+// DOP_DIVC: x / d as RN(x * a[c] + RN(x * b[c])) with a + b = 1 / d split by the host (div_const.cpp), used where the host
+// has proven the two operations equal to IEEE division for this divisor and this chain (specialize_division).
+enum DevOpKind : int32_t { DOP_MUL = 1, DOP_ADD = 2, DOP_DIV = 3, DOP_FMA = 4, DOP_SET = 5, DOP_GRAY = 6, DOP_DIVC = 7 };
 struct DevOp {
     int32_t kind;
     float a[4];   // 3-channel launches use [0..2]
@@ -181,6 +183,12 @@ __device__ __forceinline__ void apply_program(const DevProgram& prog, float (&v)
                 for (int p = 0; p < NPIX; ++p)
 #pragma unroll
                     for (int c = 0; c < NC; ++c) v[p][c] = __fdiv_rn(v[p][c], op.a[c]);
+                break;
+            case DOP_DIVC:
+#pragma unroll
+                for (int p = 0; p < NPIX; ++p)
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) v[p][c] = __fmaf_rn(v[p][c], op.a[c], __fmul_rn(v[p][c], op.b[c]));
                 break;
             case DOP_SET:
 #pragma unroll

@@ -141,12 +141,12 @@ static void overlap_forget(cudaStream_t stream) {  // a launch of this library t
             k.unknown_pred = true;
         }
 }
-static MemRange crops_range(const DevCrop* c, int n) {
+static MemRange crops_range(const DevCrop* c, int n, int pb = 3) {
     MemRange r;
     r.lo = ~static_cast<uintptr_t>(0);
     for (int i = 0; i < n; ++i) {
         const uintptr_t lo = reinterpret_cast<uintptr_t>(c[i].data);
-        const uintptr_t hi = lo + static_cast<uintptr_t>(c[i].h - 1) * static_cast<uintptr_t>(c[i].pitch) + 3u * c[i].w;
+        const uintptr_t hi = lo + static_cast<uintptr_t>(c[i].h - 1) * static_cast<uintptr_t>(c[i].pitch) + static_cast<uintptr_t>(pb) * c[i].w;
         r.lo = std::min(r.lo, lo);
         r.hi = std::max(r.hi, hi);
     }
@@ -337,7 +337,9 @@ static int pick_bw_log2(int W) {
     return best;
 }
 
-static int launch_direct(const PreprocParams& P, const ParamCropTable* table, cudaStream_t stream) {
+static int launch_direct(const PreprocParams& P_in, const ParamCropTable* table, cudaStream_t stream) {
+    PreprocParams P = P_in;
+    specialize_division(P.prog, P.nc, P.bg);  // canonical chains: two-operation division by the launch constants
     const int l = pick_bw_log2(P.W);
     const int qw = (P.W + 3) / 4;
     const int rows = 256 >> l;
@@ -364,7 +366,7 @@ static int launch_direct(const PreprocParams& P, const ParamCropTable* table, cu
 // more maps than fit): the caller then falls back to one map per crop.  On failure the crops are left untouched.
 static thread_local ImageMapCache t_image_maps;
 static int prepare_image_maps(DevCrop* dc, const cvgs_parent_t* parents, int used, const TmaGeom& G, int W,
-                              CUtensorMap* maps, int max_maps) {
+                              CUtensorMap* maps, int max_maps, int pb = 3) {
     if (!parents || used <= 0) return -1;
     struct Slot { uintptr_t datastart; int rb; };
     Slot slots[kTmaImageMaps];
@@ -384,7 +386,7 @@ static int prepare_image_maps(DevCrop* dc, const cvgs_parent_t* parents, int use
     for (int i = 0; i < used; ++i) {
         const cvgs_parent_t& p = parents[i];
         if (!p.datastart || p.whole_width <= 0 || p.whole_height <= 0) return -1;
-        const int rb = rb_class(band_row_bytes(std::min(32 * G.NPB, W), dc[i].fx));
+        const int rb = rb_class(band_row_bytes(std::min(32 * G.NPB, W), dc[i].fx, pb));
         if (rb == 0 || 4 * rb + kSlotHeader > G.slot_bytes) return -1;
         const uintptr_t ds = reinterpret_cast<uintptr_t>(p.datastart);
         int k = last_k;
@@ -393,7 +395,7 @@ static int prepare_image_maps(DevCrop* dc, const cvgs_parent_t* parents, int use
                 if (slots[k].datastart == ds && slots[k].rb == rb) break;
             if (k == n_maps) {
                 if (n_maps == max_maps) return -1;
-                const CUtensorMap* m = t_image_maps.get(ds, dc[i].pitch, p.whole_width, p.whole_height, rb);
+                const CUtensorMap* m = t_image_maps.get(ds, dc[i].pitch, pb * p.whole_width, p.whole_height, rb);
                 if (!m) return -1;
                 maps[n_maps] = *m;
                 slots[n_maps++] = Slot{ds, rb};
@@ -402,7 +404,7 @@ static int prepare_image_maps(DevCrop* dc, const cvgs_parent_t* parents, int use
             last_rb = rb;
             last_k = k;
         }
-        if (!tma_place_in_image(dc[i], ds, p.whole_width, p.whole_height, rb, k, place[i].xb, place[i].y0, place[i].pad))
+        if (!tma_place_in_image(dc[i], ds, p.whole_width, p.whole_height, rb, k, place[i].xb, place[i].y0, place[i].pad, pb))
             return -1;
     }
     for (int i = 0; i < used; ++i) {
@@ -464,7 +466,17 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         if (!fast || variant == 1 || n_replicas + 1 > kMaxDest)
             return fail(CVGS_ERR_NOT_SUPPORTED, "replicated output: IGNORE_AR, every plane used, planar float tensors, at most 7 replicas");
     }
-    if (used <= kTmaParamCrops && !planes_out && n_replicas == 0) {
+    // CV_8UC4 batches the TMA-staged kernel can take go through the 256-crop table or the descriptor ring (the
+    // instantiations built for four channels, tma_launch_kernel); everything else of a small batch is decided here
+    bool small_batch = used <= kTmaParamCrops && !planes_out && n_replicas == 0;
+    if (small_batch && P.nc == 4 && variant != 1) {
+        DevCrop probe[kTmaParamCrops];
+        bool ok = true;
+        for (int i = 0; i < used && ok; ++i) ok = fill_crop(crops[i], *pipe, i, probe[i]) == CVGS_OK;
+        TmaGeom g;
+        if (ok && tma_plan(P, probe, used, n_planes, sms, parents != nullptr, 1, g)) small_batch = false;
+    }
+    if (small_batch) {
         // small batch: descriptors (and tensor maps) ride in the kernel parameters -- no staging copy,
         // graph-capturable
         alignas(64) TmaParamTable tt;  // also serves as the image-mode table (its first maps / same crop array offset
@@ -476,15 +488,16 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         TmaParams K;
         K.P = P;
         K.maps = nullptr;
-        if (variant != 1 && tma_plan(P, tt.c, used, n_planes, sms, parents != nullptr, items_per_warp(), K.G)) {
+        if (variant != 1 && P.nc == 3 && tma_plan(P, tt.c, used, n_planes, sms, parents != nullptr, items_per_warp(), K.G)) {
             const int chain = scaled_program(P, K);
-            const MemRange src = crops_range(tt.c, used);  // before the TMA fields overwrite the pointers
+            const int pb = 3;
+            const MemRange src = crops_range(tt.c, used, pb);  // before the TMA fields overwrite the pointers
             const double t2 = now_us();
             // image mode first (cached maps, small parameter block); else one map per crop
             alignas(64) TmaImageTable it;
             DevCrop saved[kTmaParamCrops];
             std::memcpy(saved, tt.c, static_cast<size_t>(used) * sizeof(DevCrop));
-            const int n_img = prepare_image_maps(tt.c, parents, used, K.G, P.W, it.m, kTmaImageMaps);
+            const int n_img = pb == 3 ? prepare_image_maps(tt.c, parents, used, K.G, P.W, it.m, kTmaImageMaps) : -1;
             int rc = -1;
             if (n_img >= 0) {
                 std::memcpy(it.c, tt.c, static_cast<size_t>(used) * sizeof(DevCrop));
@@ -497,7 +510,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
                 return rc;
             }
             bool ok = true;
-            for (int i = 0; i < used && ok; ++i) ok = tma_prepare_crop(tt.c[i], K.G, P.W, i, &tt.m[i]) == CVGS_OK;
+            for (int i = 0; i < used && ok; ++i) ok = pb == 3 && tma_prepare_crop(tt.c[i], K.G, P.W, i, &tt.m[i]) == CVGS_OK;
             const double t3 = now_us();
             if (ok) {
                 K.G.pdl_wait = overlap_needs_wait(stream, out_range(P), src) ? 1 : 0;
@@ -529,8 +542,9 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         K.maps = nullptr;
         if (tma_plan(P, lt.c, used, n_planes, sms, true, items_per_warp(), K.G)) {
             const int chain = scaled_program(P, K);
-            const MemRange src = crops_range(lt.c, used);
-            if (prepare_image_maps(lt.c, parents, used, K.G, P.W, lt.m, kTmaImageMaps) >= 0) {
+            const int pb = P.nc == 4 ? 4 : 3;
+            const MemRange src = crops_range(lt.c, used, pb);
+            if (prepare_image_maps(lt.c, parents, used, K.G, P.W, lt.m, kTmaImageMaps, pb) >= 0) {
                 K.G.pdl_wait = overlap_needs_wait(stream, out_range(P), src) ? 1 : 0;
                 return tma_launch_kernel<TmaImageTableL>(K, lt, chain, device, stream);
             }
@@ -554,11 +568,12 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         chain = scaled_program(P, K);
         CUtensorMap* hm = r.maps_h(slot);
         // maps sit in front of the crops in the slot; image mode needs only a few of them
-        const int n_img = prepare_image_maps(hc, parents, used, K.G, P.W, hm, kTmaImageMaps);
+        const int pb = P.nc == 4 ? 4 : 3;
+        const int n_img = prepare_image_maps(hc, parents, used, K.G, P.W, hm, kTmaImageMaps, pb);
         if (n_img >= 0) {
             map_bytes = static_cast<size_t>(n_img) * sizeof(CUtensorMap);
         } else {
-            for (int i = 0; i < used && use_tma; ++i) use_tma = tma_prepare_crop(hc[i], K.G, P.W, i, &hm[i]) == CVGS_OK;
+            for (int i = 0; i < used && use_tma; ++i) use_tma = tma_prepare_crop(hc[i], K.G, P.W, i, &hm[i], pb) == CVGS_OK;
             map_bytes = static_cast<size_t>(used) * sizeof(CUtensorMap);
             if (!use_tma)  // restore the pointers the failed preparation overwrote
                 for (int i = 0; i < used; ++i)
@@ -676,7 +691,7 @@ static int launch_multi(const MultiSet* sets, int G, const cvgs_pipeline_t* pipe
                 const uintptr_t ds = reinterpret_cast<uintptr_t>(p.datastart);
                 int idx = last_idx;
                 if (ds != last_ds || rb != last_rb) {
-                    idx = mc.get(ds, c.pitch, p.whole_width, p.whole_height, rb);
+                    idx = mc.get(ds, c.pitch, 3 * p.whole_width, p.whole_height, rb);
                     if (idx < 0) return kMultiDeclined;
                     if (mc.generation != gen) {  // the table started over: indices handed out so far are void
                         restart = true;
@@ -1050,6 +1065,7 @@ static int warp_launch_impl(const cvgs_crop_t* images, const cvgs_warp_t* warps,
     PreprocParams P;
     if (int rc = build_params(q, n_planes, used, static_cast<float*>(pipe->out), P)) return rc;
     if (P.prog.special) return fail(CVGS_ERR_NOT_SUPPORTED, "warp: conversions that change the channel count are not on this path");
+    specialize_division(P.prog, P.nc, P.bg);  // pixels outside the source image are 0, unused planes the background
     for (int i = 0; i < used; ++i) {
         DevCrop scratch;
         if (int rc = fill_crop(images[i], q, i, scratch)) return rc;

@@ -102,7 +102,7 @@ constexpr int kMaxDest = 8;  // replicas of the output tensor one launch can wri
 struct TmaParams {
     PreprocParams P;         // P.prog = unscaled chain (background values), P.crops = device table or nullptr
     DevProgram prog_img;     // chain for interpolated values (2^33 folded into its first op)
-    float zh[3], zl[3];      // CH_FMA_DIV: 1/d = zh + zl per source channel (div_const.cpp)
+    float zh[4], zl[4];      // CH_FMA_DIV: 1/d = zh + zl per source channel (div_const.cpp)
     TmaGeom G;
     const CUtensorMap* maps; // device table (nullptr when the maps ride in the kernel parameters)
     // PEER instantiation (cvgs_b200_preproc_launch_replicated): every value is stored n_dest times, at
@@ -280,6 +280,7 @@ struct BandOrigin {
     int32_t c0;       // box start coordinate (8-byte elements) in the crop's tensor map
     int32_t origin;   // crop-row byte that smem byte 0 of a staged row corresponds to (= 8*c0 - xb)
 };
+template <int PB = 3>  // bytes per source pixel
 __device__ __forceinline__ BandOrigin band_origin(const PreprocParams& P, const TmaGeom& G, const DevCrop& C, int txi) {
     BandOrigin b;
     const int tx0 = txi * (32 * G.NPB);
@@ -287,7 +288,7 @@ __device__ __forceinline__ BandOrigin band_origin(const PreprocParams& P, const 
     b.xe = min(min(tx0 + 32 * G.NPB, P.W) - 1, C.bx2);
     const AxisTap t = axis_tap(b.xa - C.bx1, C.fx);
     const int xb = C.m.xb;
-    b.c0 = ((xb + 3 * t.i1) >> 4) << 1;  // the box must start on a 16-byte boundary of global memory
+    b.c0 = ((xb + PB * t.i1) >> 4) << 1;  // the box must start on a 16-byte boundary of global memory
     b.origin = 8 * b.c0 - xb;
     return b;
 }
@@ -343,17 +344,27 @@ struct ItemCursor {
 // One output column of a row pair: taps of both rows from their staged source rows -> 3 interpolated channels,
 // row r in .x and row r+1 in .y (scaled by 2^-33).  Arithmetic per half = Interpolate<INTER_LINEAR>::exec in the
 // order nvcc emits for the reference: FMUL(p10*w10), FFMA(p00,w00), FFMA(p01,w01), FFMA(p11,w11).
+// NC = 4 (CV_8UC4): a pixel is one aligned word -- two loads per source row, no shifts.
+template <int NC>
 __device__ __forceinline__ void gather_pair(uint32_t A0, uint32_t B0, uint32_t A1, uint32_t B1, int shl, int shr, bool edge,
-                                            float wx0, float wx1, float2 wy0, float2 wy1, float2 (&v)[3]) {
-    const uint32_t am0 = lds32_tap(A0 - 4), a00 = lds32_tap(A0), a01 = lds32_tap(A0 + 4);
-    const uint32_t bm0 = lds32_tap(B0 - 4), b00 = lds32_tap(B0), b01 = lds32_tap(B0 + 4);
-    const uint32_t am1 = lds32_tap(A1 - 4), a10 = lds32_tap(A1), a11 = lds32_tap(A1 + 4);
-    const uint32_t bm1 = lds32_tap(B1 - 4), b10 = lds32_tap(B1), b11 = lds32_tap(B1 + 4);
-    // left pixel in bytes 0..2 (clamped shift: 32 = the word itself), right pixel in bytes 0..2
-    const uint32_t al0 = __funnelshift_rc(am0, a00, shl), bl0 = __funnelshift_rc(bm0, b00, shl);
-    const uint32_t al1 = __funnelshift_rc(am1, a10, shl), bl1 = __funnelshift_rc(bm1, b10, shl);
-    uint32_t ar0 = __funnelshift_r(a00, a01, shr), br0 = __funnelshift_r(b00, b01, shr);
-    uint32_t ar1 = __funnelshift_r(a10, a11, shr), br1 = __funnelshift_r(b10, b11, shr);
+                                            float wx0, float wx1, float2 wy0, float2 wy1, float2 (&v)[NC]) {
+    uint32_t al0, bl0, al1, bl1, ar0, br0, ar1, br1;
+    if constexpr (NC == 4) {
+        al0 = lds32_tap(A0), ar0 = lds32_tap(A0 + 4);
+        bl0 = lds32_tap(B0), br0 = lds32_tap(B0 + 4);
+        al1 = lds32_tap(A1), ar1 = lds32_tap(A1 + 4);
+        bl1 = lds32_tap(B1), br1 = lds32_tap(B1 + 4);
+    } else {
+        const uint32_t am0 = lds32_tap(A0 - 4), a00 = lds32_tap(A0), a01 = lds32_tap(A0 + 4);
+        const uint32_t bm0 = lds32_tap(B0 - 4), b00 = lds32_tap(B0), b01 = lds32_tap(B0 + 4);
+        const uint32_t am1 = lds32_tap(A1 - 4), a10 = lds32_tap(A1), a11 = lds32_tap(A1 + 4);
+        const uint32_t bm1 = lds32_tap(B1 - 4), b10 = lds32_tap(B1), b11 = lds32_tap(B1 + 4);
+        // left pixel in bytes 0..2 (clamped shift: 32 = the word itself), right pixel in bytes 0..2
+        al0 = __funnelshift_rc(am0, a00, shl), bl0 = __funnelshift_rc(bm0, b00, shl);
+        al1 = __funnelshift_rc(am1, a10, shl), bl1 = __funnelshift_rc(bm1, b10, shl);
+        ar0 = __funnelshift_r(a00, a01, shr), br0 = __funnelshift_r(b00, b01, shr);
+        ar1 = __funnelshift_r(a10, a11, shr), br1 = __funnelshift_r(b10, b11, shr);
+    }
     if (edge) {  // x2_read == x1 (interpolation.cuh:72): the right tap is the left pixel again
         ar0 = al0;
         br0 = bl0;
@@ -363,7 +374,7 @@ __device__ __forceinline__ void gather_pair(uint32_t A0, uint32_t B0, uint32_t A
     const float2 w00 = __fmul2_rn(make_float2(wx0, wx0), wy0), w10 = __fmul2_rn(make_float2(wx1, wx1), wy0);
     const float2 w01 = __fmul2_rn(make_float2(wx0, wx0), wy1), w11 = __fmul2_rn(make_float2(wx1, wx1), wy1);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < NC; ++c) {
         float2 t = __fmul2_rn(make_float2(u8_scaled(ar0, c), u8_scaled(ar1, c)), w10);
         t = __ffma2_rn(make_float2(u8_scaled(al0, c), u8_scaled(al1, c)), w00, t);
         t = __ffma2_rn(make_float2(u8_scaled(bl0, c), u8_scaled(bl1, c)), w01, t);
@@ -373,29 +384,34 @@ __device__ __forceinline__ void gather_pair(uint32_t A0, uint32_t B0, uint32_t A
 
 // The normalised chain on a row pair (same semantics as apply_program, two values per instruction where the
 // hardware has a packed form).
-__device__ __forceinline__ void apply_program_pair(const DevProgram& prog, float2 (&v)[3]) {
+template <int NC>
+__device__ __forceinline__ void apply_program_pair(const DevProgram& prog, float2 (&v)[NC]) {
     if (prog.round_u8) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = make_float2(round_sat_u8(v[c].x), round_sat_u8(v[c].y));
+        for (int c = 0; c < NC; ++c) v[c] = make_float2(round_sat_u8(v[c].x), round_sat_u8(v[c].y));
     }
     for (int i = 0; i < prog.n_ops; ++i) {
         const DevOp& op = prog.ops[i];
         switch (op.kind) {
             case DOP_FMA:
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[c] = __ffma2_rn(v[c], make_float2(op.a[c], op.a[c]), make_float2(op.b[c], op.b[c]));
+                for (int c = 0; c < NC; ++c) v[c] = __ffma2_rn(v[c], make_float2(op.a[c], op.a[c]), make_float2(op.b[c], op.b[c]));
                 break;
             case DOP_MUL:
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[c] = __fmul2_rn(v[c], make_float2(op.a[c], op.a[c]));
+                for (int c = 0; c < NC; ++c) v[c] = __fmul2_rn(v[c], make_float2(op.a[c], op.a[c]));
                 break;
             case DOP_ADD:
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[c] = make_float2(__fadd_rn(v[c].x, op.a[c]), __fadd_rn(v[c].y, op.a[c]));
+                for (int c = 0; c < NC; ++c) v[c] = make_float2(__fadd_rn(v[c].x, op.a[c]), __fadd_rn(v[c].y, op.a[c]));
                 break;
             case DOP_DIV:
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[c] = make_float2(__fdiv_rn(v[c].x, op.a[c]), __fdiv_rn(v[c].y, op.a[c]));
+                for (int c = 0; c < NC; ++c) v[c] = make_float2(__fdiv_rn(v[c].x, op.a[c]), __fdiv_rn(v[c].y, op.a[c]));
+                break;
+            case DOP_DIVC:
+#pragma unroll
+                for (int c = 0; c < NC; ++c) v[c] = div_by_const2(v[c], op.a[c], op.b[c]);
                 break;
             default:
                 break;
@@ -417,7 +433,8 @@ struct StageBand {
 // (1.81 against 1.80 us per frame: that workload is bound by DRAM traffic), so only kMaxNP is built.
 constexpr int kNarrowNP = 2;
 constexpr int kNarrowResident = 6;
-template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP>
+// NC: channels = bytes of the 8-bit source pixel (3: CV_8UC3, 4: CV_8UC4); registers, chain constants and planes follow it.
+template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3>
 __global__ void __launch_bounds__(kTmaThreads, MAXNP <= kNarrowNP ? kNarrowResident : kMaxResident)
 preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ Table T) {
     extern __shared__ uint8_t smem_raw[];
@@ -453,10 +470,10 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
     asm volatile("" : "+r"(recs));
 
     // chain constants of the specialised shape v = fma(v, ca, cb) / cd  (source-channel order)
-    float ca[3], cb[3], zh[3], zl[3];
+    float ca[NC], cb[NC], zh[NC], zl[NC];
     if (CHAIN == CH_FMA_DIV) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < NC; ++c) {
             ca[c] = K.prog_img.ops[0].a[c];
             cb[c] = K.prog_img.ops[0].b[c];
             zh[c] = K.zh[c];
@@ -464,13 +481,15 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         }
     }
     // chain(background): value of planes z >= used and of pixels outside the aspect-ratio band
-    float vb[1][3] = {{P.bg[0], P.bg[1], P.bg[2]}};
-    if (GEN) apply_program<1>(P.prog, vb);
+    float vb[1][NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) vb[0][c] = P.bg[c];
+    if (GEN) apply_program<1, NC>(P.prog, vb);
 
-    // plane offsets (floats) of the three source channels
-    const long long oc0 = (long long)P.prog.dst_chan[0] * P.out.c_stride;
-    const long long oc1 = (long long)P.prog.dst_chan[1] * P.out.c_stride;
-    const long long oc2 = (long long)P.prog.dst_chan[2] * P.out.c_stride;
+    // plane offsets (floats) of the source channels
+    long long oc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) oc[c] = (long long)P.prog.dst_chan[c] * P.out.c_stride;
     const int pxs = GEN ? P.out.px_stride : 1;
     int row_step = W * pxs;  // floats between vertically adjacent pixels
     if (!GEN) asm volatile("" : "+r"(row_step));  // in a register, not re-read from the parameters per item
@@ -569,7 +588,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             const int itx = (int)fast_div((uint32_t)(idx - iz * G.items_per_crop), G.d_HP);
             if (!GEN || iz < P.used) {
                 const DevCrop& C = tma_crop_of<Table>(K, T, iz);
-                const BandOrigin b = band_origin(P, G, C, itx);
+                const BandOrigin b = band_origin<NC>(P, G, C, itx);
                 // all lanes computed the same values; telling the compiler so keeps the TMA issue below loop-free
                 sb.c0 = uniform_i(b.c0);
                 sb.rb = uniform_i(crop_row_bytes(C));
@@ -623,7 +642,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             int bx1 = 0, wm1 = 0;
             if (active) {
                 const DevCrop& C = tma_crop_of<Table>(K, T, z);
-                b = band_origin(P, G, C, cc.txi);
+                b = band_origin<NC>(P, G, C, cc.txi);
                 fx = C.fx;
                 bx1 = C.bx1;
                 wm1 = C.w - 1;
@@ -642,32 +661,42 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                     m_in |= (in_p ? 1u : 0u) << p;
                     m_img |= (img_p ? 1u : 0u) << p;
                     m_edge |= (t.i1 + 1 > wm1 ? 1u : 0u) << p;
-                    const int o = 3 * t.i1 - b.origin;
-                    off[p] = ((o + 3) >> 2) * 4;
-                    shl[p] = (o & 3) ? (o & 3) * 8 : 32;
-                    shr[p] = ((o + 3) & 3) * 8;
+                    const int o = NC * t.i1 - b.origin;
+                    if (NC == 4) {  // word-aligned pixels (the plan requires 4-byte aligned rows)
+                        off[p] = o;
+                    } else {
+                        off[p] = ((o + 3) >> 2) * 4;
+                        shl[p] = (o & 3) ? (o & 3) * 8 : 32;
+                        shr[p] = ((o + 3) & 3) * 8;
+                    }
                 }
             }
         }
         // this lane's first column in rows 2*jp of the three channel planes of plane z
         asm volatile("" : "+r"(m_edge), "+r"(m_img), "+r"(m_in));
         const bool full_band = tx0 + 32 * np <= W;  // every lane owns a column in each of the band's np groups
-        float* s0 = tma_plane_base<Table>(K, T, z) + ((long long)(tx0 + lane) * pxs + (long long)(2 * cc.jp) * row_step);
-        float* s1 = s0 + oc1;
-        float* s2 = s0 + oc2;
-        s0 += oc0;
-        long long rs0 = row_step, rs1 = row_step, rs2 = row_step;  // floats between vertically adjacent pixels
+        float* sp[NC];  // this lane's first column in row 2*jp of each channel's plane
+        long long rs[NC];  // floats between vertically adjacent pixels
+        {
+            float* const base = tma_plane_base<Table>(K, T, z) + ((long long)(tx0 + lane) * pxs + (long long)(2 * cc.jp) * row_step);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                sp[c] = base + oc[c];
+                rs[c] = row_step;
+            }
+        }
         // 8-bit packed output (general instantiation only): byte address of this lane's first pixel in row 2*jp
         uint8_t* u8row = nullptr;
         if (GEN && P.out.u8)
             u8row = reinterpret_cast<uint8_t*>(P.out.base) + (long long)z * P.out.z_stride + (long long)(2 * cc.jp) * P.out.row_pitch +
-                    3LL * (tx0 + lane);
+                    (long long)NC * (tx0 + lane);
         if (GEN && P.out.planes) {  // per-plane destinations (fk::SplitWrite): own pointer and pitch per channel
-            const DevPlane p0 = P.out.planes[z * 3], p1 = P.out.planes[z * 3 + 1], p2 = P.out.planes[z * 3 + 2];
-            rs0 = p0.pitch, rs1 = p1.pitch, rs2 = p2.pitch;
-            s0 = p0.data + (tx0 + lane) + (long long)(2 * cc.jp) * rs0;
-            s1 = p1.data + (tx0 + lane) + (long long)(2 * cc.jp) * rs1;
-            s2 = p2.data + (tx0 + lane) + (long long)(2 * cc.jp) * rs2;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const DevPlane pl = P.out.planes[z * NC + c];
+                rs[c] = pl.pitch;
+                sp[c] = pl.data + (tx0 + lane) + (long long)(2 * cc.jp) * rs[c];
+            }
         }
 
         const int nitems = min(cc.left, G.HP - cc.jp);  // items of this band inside the warp's range
@@ -697,45 +726,47 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             uint32_t aA1 = sdata + (ra1 & 0xffffu), aB1 = sdata + (ra1 >> 16);
             // row pointers of the pair; opaque to the compiler so that they stay in registers instead of being
             // re-derived in front of every store
-            float* t0 = s0 + (GEN ? rs0 : (long long)row_step);
-            float* t1 = s1 + (GEN ? rs1 : (long long)row_step);
-            float* t2 = s2 + (GEN ? rs2 : (long long)row_step);
-            asm volatile("" : "+l"(s0), "+l"(s1), "+l"(s2), "+l"(t0), "+l"(t1), "+l"(t2));
+            float* tp[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                tp[c] = sp[c] + (GEN ? rs[c] : (long long)row_step);
+                asm volatile("" : "+l"(sp[c]), "+l"(tp[c]));
+            }
             asm volatile("" : "+r"(aA0), "+r"(aB0), "+r"(aA1), "+r"(aB1), "+f"(wy0.x), "+f"(wy0.y), "+f"(wy1.x), "+f"(wy1.y));
             {
 #pragma unroll
                 for (int p = 0; p < NPC; ++p) {
                     if (!CHECK || (m_in & (1u << p))) {  // lanes past the right border of the plane skip
-                        float2 v[3];
+                        float2 v[NC];
                         if (!GEN || im0 || im1) {
-                            gather_pair(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p],
+                            gather_pair<NC>(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p],
                                         (m_edge & (1u << p)) != 0, wxa[p], wxb[p], wy0, wy1, v);
                             if (CHAIN == CH_FMA_DIV) {
 #pragma unroll
-                                for (int c = 0; c < 3; ++c) {
+                                for (int c = 0; c < NC; ++c) {
                                     v[c] = __ffma2_rn(v[c], make_float2(ca[c], ca[c]), make_float2(cb[c], cb[c]));
                                     v[c] = div_by_const2(v[c], zh[c], zl[c]);
                                 }
                             } else {
                                 if (G.explicit_prescale) {
 #pragma unroll
-                                    for (int c = 0; c < 3; ++c) v[c] = __fmul2_rn(v[c], make_float2(kPreScale, kPreScale));
+                                    for (int c = 0; c < NC; ++c) v[c] = __fmul2_rn(v[c], make_float2(kPreScale, kPreScale));
                                 }
-                                apply_program_pair(K.prog_img, v);
+                                apply_program_pair<NC>(K.prog_img, v);
                             }
                         }
                         if (GEN) {
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) {
+                            for (int c = 0; c < NC; ++c) {
                                 if (!(im0 && (m_img & (1u << p)))) v[c].x = vb[0][c];
                                 if (!(im1 && (m_img & (1u << p)))) v[c].y = vb[0][c];
                             }
                         }
                         if (GEN && P.out.u8) {  // SaturateCast<float, uchar> (or fk::Cast) + packed pixels, 3 bytes each
-                            uint8_t* ub = u8row + 96 * p;
+                            uint8_t* ub = u8row + 32 * NC * p;
                             uint8_t* ub1 = ub + P.out.row_pitch;
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) {
+                            for (int c = 0; c < NC; ++c) {
                                 const int d = P.prog.dst_chan[c];
                                 const uint32_t a = P.out.u8 == 2 ? __float2uint_rz(v[c].x) : (uint32_t)round_sat_u8(v[c].x);
                                 const uint32_t b = P.out.u8 == 2 ? __float2uint_rz(v[c].y) : (uint32_t)round_sat_u8(v[c].y);
@@ -747,12 +778,10 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
 #pragma unroll 1
                             for (int d = 0; d < K.n_dest; ++d) {  // this GPU's tensor first, then the peers' over NVLink
                                 const long long dq = K.dest_delta[d] + q;
-                                st_cs_f32(s0 + dq, v[0].x);
-                                st_cs_f32(s1 + dq, v[1].x);
-                                st_cs_f32(s2 + dq, v[2].x);
-                                st_cs_f32_if(st1, t0 + dq, v[0].y);
-                                st_cs_f32_if(st1, t1 + dq, v[1].y);
-                                st_cs_f32_if(st1, t2 + dq, v[2].y);
+#pragma unroll
+                                for (int c = 0; c < NC; ++c) st_cs_f32(sp[c] + dq, v[c].x);
+#pragma unroll
+                                for (int c = 0; c < NC; ++c) st_cs_f32_if(st1, tp[c] + dq, v[c].y);
                             }
                         } else {
                             const int q = 32 * p * pxs;
@@ -760,20 +789,17 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                             if (v[0].x == 123456.0f)
 #endif
                             {
-                            st_cs_f32(s0 + q, v[0].x);
-                            st_cs_f32(s1 + q, v[1].x);
-                            st_cs_f32(s2 + q, v[2].x);
-                            st_cs_f32_if(st1, t0 + q, v[0].y);
-                            st_cs_f32_if(st1, t1 + q, v[1].y);
-                            st_cs_f32_if(st1, t2 + q, v[2].y);
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) st_cs_f32(sp[c] + q, v[c].x);
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) st_cs_f32_if(st1, tp[c] + q, v[c].y);
                             }
                         }
                     }
                 }
             }
-            s0 += 2 * (GEN ? rs0 : (long long)row_step);
-            s1 += 2 * (GEN ? rs1 : (long long)row_step);
-            s2 += 2 * (GEN ? rs2 : (long long)row_step);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) sp[c] += 2 * (GEN ? rs[c] : (long long)row_step);
             if (GEN && P.out.u8) u8row += 2 * P.out.row_pitch;
 
             // every lane has consumed its taps of this slot (their values fed the stores above): refill it
@@ -830,10 +856,10 @@ inline EncodeTiledFn encode_tiled_fn() {
 
 // Source bytes a staged row of a TW-wide band can span for scale factor fx (+ alignment slack), rounded to
 // the 64 bytes that keep every 2-row box 128-byte aligned in shared memory.
-inline int band_row_bytes(int TW, float fx) {
-    // taps of TW columns: floor((TW-1)*fx) + 2 pixels, +1 for the float rounding of the two products
+inline int band_row_bytes(int TW, float fx, int pb = 3) {
+    // taps of TW columns: floor((TW-1)*fx) + 2 pixels, +1 for the float rounding of the two products; pb bytes per pixel
     const double px = std::ceil(static_cast<double>(TW - 1) * static_cast<double>(fx)) + 3.0;
-    const long long bytes = static_cast<long long>(px) * 3 + 15 /*16-byte aligned start*/ + 4 /*w[+1] word*/;
+    const long long bytes = static_cast<long long>(px) * pb + 15 /*16-byte aligned start*/ + 4 /*w[+1] word*/;
     return static_cast<int>((bytes + 63) / 64 * 64);
 }
 
@@ -872,25 +898,30 @@ inline int rb_class(int rb, bool fine = false) {
 inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int n_planes, int sm_count, bool image_mode,
                      int items_per_warp, TmaGeom& G, bool need_driver = true, int grid_div = 1, int max_resident = kMaxResident) {
     if (need_driver && !encode_tiled_fn()) return false;
-    if (P.src_type != CVGS_8UC3) return false;  // the byte-level tap extraction is written for 3-byte pixels
-    if (P.out.u8 && P.prog.nc_out != 3) return false;
+    // the tap extraction is written for 3-byte pixels and for 4-byte pixels that are aligned words
+    if (P.src_type != CVGS_8UC3 && P.src_type != CVGS_8UC4) return false;
+    const int pb = P.src_type == CVGS_8UC4 ? 4 : 3;
+    if (P.out.u8 && P.prog.nc_out != pb) return false;
+    // four channels: built for the common geometry only (IGNORE_AR, every plane used, planar float tensors)
+    if (pb == 4 && (P.band_test || P.used != P.n_planes || P.out.px_stride != 1 || P.out.planes || P.out.u8)) return false;
     if (P.prog.special) return false;           // conversions that change the channel count: direct-gather kernel
     if (P.out.row_stride != static_cast<long long>(P.W) * P.out.px_stride) return false;  // padded packed rows: direct-gather kernel
     float fx_max = 0.f;
     for (int i = 0; i < used; ++i) {
         const DevCrop& c = crops[i];
         if (c.h > 1 && c.pitch % 16 != 0) return false;  // TMA: row stride must be a multiple of 16 bytes
+        if (pb == 4 && (reinterpret_cast<uintptr_t>(c.data) & 3)) return false;  // CV_8UC4: pixels are aligned words
         if (!(c.fx > 0.f) || !(c.fy > 0.f) || !std::isfinite(c.fx) || !std::isfinite(c.fy)) return false;
         fx_max = std::max(fx_max, c.fx);
     }
-    if (static_cast<long long>(P.W) * P.H * 3 * std::max<long long>(1, std::abs(P.out.px_stride)) > 0x3fffffffLL)
+    if (static_cast<long long>(P.W) * P.H * 4 * std::max<long long>(1, std::abs(P.out.px_stride)) > 0x3fffffffLL)
         return false;  // in-plane offsets are 32-bit in the kernel
     int NPB = std::min(kMaxNP, (P.W + 31) / 32);
     if (const char* e = std::getenv("CVGS_TMA_NPB")) {  // tuning override (profiling)
         const int v = std::atoi(e);
         if (v >= 1 && v <= kMaxNP) NPB = std::min(NPB, v);
     }
-    auto need = [&](int npb) { return used > 0 ? band_row_bytes(std::min(32 * npb, P.W), fx_max) : 64; };
+    auto need = [&](int npb) { return used > 0 ? band_row_bytes(std::min(32 * npb, P.W), fx_max, pb) : 64; };
     while (NPB > 1 && need(NPB) > kMaxBoxBytes) --NPB;
     if (need(NPB) > kMaxBoxBytes) return false;  // extreme down-scale: direct kernel
     // image mode rounds the staged row bytes up to a class (rb_class) so that crops share tensor maps
@@ -946,6 +977,42 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
     return true;
 }
 
+// The gather kernels (direct, warp, CircularTensor) run the chain from the runtime program; an IEEE division there is
+// MUFU.RCP + Newton + FCHK, ~12 instructions per value.  For the canonical chain  [MUL | FMA | ADD] DIV  (or DIV alone)
+// the division's numerator is fma(x, a, b) of an interpolated x in {0} U [2^-46, 2^16]: with 2^-24 <= |a|, |b|, |d| <= 2^24
+// (b may be zero) a non-zero numerator has magnitude in [2^-73, 2^41] -- the range on which div_const.cpp proves the
+// two-operation form exact per divisor (same argument as scaled_program below) -- and zeros are covered by the sign
+// conditions.  The background value takes the same program, so it must lie in the same range.  Returns true when the
+// program's DIV was replaced by DOP_DIVC.
+inline bool specialize_division(DevProgram& prog, int nc, const float* bg) {
+    if (prog.special) return false;
+    const int n = prog.n_ops;
+    DevOp* ops = prog.ops;
+    const bool first_lin = n == 2 && (ops[0].kind == DOP_MUL || ops[0].kind == DOP_FMA || ops[0].kind == DOP_ADD);
+    if (!((first_lin && ops[1].kind == DOP_DIV) || (n == 1 && ops[0].kind == DOP_DIV))) return false;
+    const DevOp div = ops[n - 1];
+    DivConst dc[4];
+    for (int c = 0; c < nc; ++c) {
+        const float a = n == 1 ? 1.0f : (ops[0].kind == DOP_ADD ? 1.0f : ops[0].a[c]);
+        const float b = n == 1 ? -0.0f : (ops[0].kind == DOP_MUL ? -0.0f : (ops[0].kind == DOP_ADD ? ops[0].a[c] : ops[0].b[c]));
+        const float aa = std::fabs(a), ab = std::fabs(b), ag = std::fabs(bg[c]);
+        const bool ok = std::isfinite(aa) && aa >= 5.9604644775390625e-08f && aa <= 16777216.0f &&
+                        (ab == 0.f || (std::isfinite(ab) && ab >= 5.9604644775390625e-08f && ab <= 16777216.0f)) &&
+                        (ag == 0.f || (ag >= 1.4210854715202004e-14f && ag <= 65536.0f));
+        if (!ok) return false;
+        dc[c] = div_const_prepare(div.a[c]);
+        const bool neg_zero_possible = ab == 0.f && std::signbit(b) && std::signbit(a);
+        if (!dc[c].exact || !div_const_pos_zero_ok(dc[c]) || (!neg_zero_possible ? false : !div_const_neg_zero_ok(dc[c]))) return false;
+    }
+    DevOp& d = ops[n - 1];
+    d.kind = DOP_DIVC;
+    for (int c = 0; c < 4; ++c) {
+        d.a[c] = c < nc ? dc[c].zh : 1.0f;
+        d.b[c] = c < nc ? dc[c].zl : 0.0f;
+    }
+    return true;
+}
+
 // Chain for interpolated values: the 2^33 that undoes the tap/weight scaling is folded into the first op when
 // that is exact for every input (MUL/FMA/DIV by a constant of moderate magnitude), else applied explicitly.
 inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K);
@@ -955,7 +1022,7 @@ inline int scaled_program(const PreprocParams& P, TmaParams& K) {
         bool valid = false;
         DevProgram key;
         DevProgram prog_img;
-        float zh[3], zl[3];
+        float zh[4], zl[4];
         int explicit_prescale, chain;
     };
     static thread_local Memo m;
@@ -966,7 +1033,7 @@ inline int scaled_program(const PreprocParams& P, TmaParams& K) {
         K.G.explicit_prescale = m.explicit_prescale;
         return m.chain;
     }
-    for (int c = 0; c < 3; ++c) K.zh[c] = K.zl[c] = 0.f;
+    for (int c = 0; c < 4; ++c) K.zh[c] = K.zl[c] = 0.f;
     const int chain = scaled_program_uncached(P, K);
     m.key = P.prog;
     m.prog_img = K.prog_img;
@@ -982,8 +1049,9 @@ inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
     K.G.explicit_prescale = 1;
     if (P.prog.round_u8 || P.prog.n_ops == 0) return CH_GENERIC;
     auto moderate = [](float a) { return a == 0.f || (std::fabs(a) > 1e-20f && std::fabs(a) < 1e20f); };
+    const int nc = P.nc;
     auto all_moderate = [&](const float* a, bool nonzero) {
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < nc; ++c)
             if (!moderate(a[c]) || (nonzero && a[c] == 0.f)) return false;
         return true;
     };
@@ -996,7 +1064,7 @@ inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
         DevOp lin{};
         lin.kind = DOP_FMA;
         const DevOp div = ops[n - 1];
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < nc; ++c) {
             lin.a[c] = n == 1 ? 1.0f : (ops[0].kind == DOP_ADD ? 1.0f : ops[0].a[c]);
             lin.b[c] = n == 1 ? -0.0f : (ops[0].kind == DOP_MUL ? -0.0f : (ops[0].kind == DOP_ADD ? ops[0].a[c] : ops[0].b[c]));
         }
@@ -1004,8 +1072,8 @@ inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
         // <= 2^24 (b may be zero) a non-zero fma(x, a, b) of an interpolated x in {0} U [2^-46, 255] has magnitude
         // in [2^-73, 2^33]: every intermediate stays normal.  Zeros are handled through the signs of zh / zl.
         bool ok = true;
-        DivConst dc[3];
-        for (int c = 0; c < 3 && ok; ++c) {
+        DivConst dc[4];
+        for (int c = 0; c < nc && ok; ++c) {
             const float aa = std::fabs(lin.a[c]), ab = std::fabs(lin.b[c]);
             ok = std::isfinite(aa) && aa >= 5.9604644775390625e-08f && aa <= 16777216.0f &&
                  (ab == 0.f || (std::isfinite(ab) && ab >= 5.9604644775390625e-08f && ab <= 16777216.0f));
@@ -1016,7 +1084,7 @@ inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
             ok = dc[c].exact && div_const_pos_zero_ok(dc[c]) && (!neg_zero_possible || div_const_neg_zero_ok(dc[c]));
         }
         if (ok) {
-            for (int c = 0; c < 3; ++c) {
+            for (int c = 0; c < nc; ++c) {
                 lin.a[c] *= kPreScale;
                 K.zh[c] = dc[c].zh;
                 K.zl[c] = dc[c].zl;
@@ -1031,11 +1099,11 @@ inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
     DevOp& op = ops[0];
     if (op.kind == DOP_MUL || op.kind == DOP_FMA) {
         if (!all_moderate(op.a, false)) return CH_GENERIC;
-        for (int c = 0; c < 3; ++c) op.a[c] *= kPreScale;
+        for (int c = 0; c < nc; ++c) op.a[c] *= kPreScale;
         K.G.explicit_prescale = 0;
     } else if (op.kind == DOP_DIV) {
         if (!all_moderate(op.a, true)) return CH_GENERIC;
-        for (int c = 0; c < 3; ++c) op.a[c] /= kPreScale;
+        for (int c = 0; c < nc; ++c) op.a[c] /= kPreScale;
         K.G.explicit_prescale = 0;
     }
     return CH_GENERIC;
@@ -1061,11 +1129,11 @@ inline int tma_encode(CUtensorMap* map, uintptr_t base16, long long row_bytes, i
 
 // Per-crop map: nothing is known about the memory around the crop, so the map's bounds are the crop's own (reads
 // never leave it by more than the 8-byte element that holds its last pixel; everything else is zero-filled).
-inline int tma_prepare_crop(DevCrop& c, const TmaGeom& G, int W, int map_index, CUtensorMap* map) {
+inline int tma_prepare_crop(DevCrop& c, const TmaGeom& G, int W, int map_index, CUtensorMap* map, int pb = 3) {
     const uintptr_t addr = reinterpret_cast<uintptr_t>(c.data);
     const int mis = static_cast<int>(addr & 15);
-    const int rb = band_row_bytes(std::min(32 * G.NPB, W), c.fx);
-    if (int rc = tma_encode(map, addr - mis, mis + 3LL * c.w, c.h, c.pitch, rb)) return rc;
+    const int rb = band_row_bytes(std::min(32 * G.NPB, W), c.fx, pb);
+    if (int rc = tma_encode(map, addr - mis, mis + static_cast<long long>(pb) * c.w, c.h, c.pitch, rb)) return rc;
     c.m.xb = mis;   // overwrites c.data (union)
     c.m.y0 = 0;
     c.pad = rb | (map_index << 16);
@@ -1083,12 +1151,13 @@ struct ImageMapCache {
     };
     static constexpr int kEntries = 512;
     Entry e[kEntries];
+    // width_bytes = pixel bytes x image width
     const CUtensorMap* get(uintptr_t datastart, int pitch, int width, int height, int rb) {
         const size_t hsh = (static_cast<size_t>(datastart >> 8) * 0x9E3779B97F4A7C15ull + static_cast<size_t>(rb) * 0xC2B2AE3D27D4EB4Full) >> 40;
         Entry& x = e[hsh % kEntries];
         if (x.datastart == datastart && x.pitch == pitch && x.width == width && x.height == height && x.rb == rb) return &x.map;
         const int mis = static_cast<int>(datastart & 15);
-        if (tma_encode(&x.map, datastart - mis, mis + 3LL * width, height, pitch, rb) != CVGS_OK) {
+        if (tma_encode(&x.map, datastart - mis, mis + static_cast<long long>(width), height, pitch, rb) != CVGS_OK) {
             x.datastart = 0;
             return nullptr;
         }
@@ -1164,7 +1233,7 @@ struct DevMapCache {
             return get(datastart, pitch, width, height, rb);
         }
         const int mis = static_cast<int>(datastart & 15);
-        if (tma_encode(&h[count], datastart - mis, mis + 3LL * width, height, pitch, rb) != CVGS_OK) return -1;
+        if (tma_encode(&h[count], datastart - mis, mis + static_cast<long long>(width), height, pitch, rb) != CVGS_OK) return -1;
         keys[count] = Key{datastart, pitch, width, height, rb};
         bucket[b] = count + 1;
         return count++;
@@ -1183,7 +1252,7 @@ struct DevMapCache {
 // Locate crop c (c.data valid) inside its parent image: byte offset within a map row, map row, and the pad word that
 // binds it to map `map_index` with row bytes rb.  The crop itself is not modified.
 inline bool tma_place_in_image(const DevCrop& c, uintptr_t datastart, int width, int height, int rb, int map_index,
-                               int32_t& xb, int32_t& y0_out, int32_t& pad) {
+                               int32_t& xb, int32_t& y0_out, int32_t& pad, int pb = 3) {
     const uintptr_t addr = reinterpret_cast<uintptr_t>(c.data);
     if (addr < datastart || c.pitch <= 0) return false;
     const uintptr_t off = addr - datastart;
@@ -1191,7 +1260,8 @@ inline bool tma_place_in_image(const DevCrop& c, uintptr_t datastart, int width,
     const unsigned long long y0 = off <= 0xffffffffull ? static_cast<uint32_t>(off) / static_cast<uint32_t>(c.pitch)
                                                        : off / static_cast<uintptr_t>(c.pitch);
     const long long xo = static_cast<long long>(off - y0 * static_cast<uintptr_t>(c.pitch));
-    if (xo + 3LL * c.w > 3LL * width || static_cast<long long>(y0) + c.h > height || (height > 1 && 3LL * width > c.pitch))
+    const long long PB = pb;
+    if (xo + PB * c.w > PB * width || static_cast<long long>(y0) + c.h > height || (height > 1 && PB * width > c.pitch))
         return false;
     xb = static_cast<int32_t>((datastart & 15) + xo);
     y0_out = static_cast<int32_t>(y0);
@@ -1203,12 +1273,12 @@ inline size_t tma_smem_bytes(const TmaGeom& G) {
     return static_cast<size_t>(kWarps) * G.slots * G.slot_bytes + kRingPad + 128;
 }
 
-template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP>
+template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3>
 inline int tma_launch_instance(const TmaParams& K, const Table& T, int device, cudaStream_t stream) {
     static thread_local size_t attr_set[64] = {};  // per device: dynamic shared memory opt-in already granted
     const size_t smem = tma_smem_bytes(K.G);
     const int slot = device & 63;
-    auto kernel = preproc_tma_kernel<Table, CHAIN, GEN, PEER, MAXNP>;
+    auto kernel = preproc_tma_kernel<Table, CHAIN, GEN, PEER, MAXNP, NC>;
     if (smem > attr_set[slot]) {
         const size_t want = std::max<size_t>(smem, 112 * 1024);
         CVGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(want)));
@@ -1249,6 +1319,15 @@ inline int tma_launch_kernel(const TmaParams& K, const Table& T, int chain, int 
     static_assert(sizeof(TmaParams) + sizeof(Table) <= 32 * 1024, "kernel parameters exceed 32 KB");
     const PreprocParams& P = K.P;
     const bool fast = !P.band_test && P.used == P.n_planes && P.out.px_stride == 1 && !P.out.planes && !P.out.u8;
+    if (P.nc == 4) {  // CV_8UC4: built for the common geometry and for the tables batches of such frames arrive in
+        if constexpr (std::is_same<Table, TmaImageTableL>::value || std::is_same<Table, TmaNoTable>::value) {
+            if (!fast) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel, CV_8UC4: common geometry only");
+            if (chain == CH_FMA_DIV) return tma_launch_instance<Table, CH_FMA_DIV, false, false, kMaxNP, 4>(K, T, device, stream);
+            return tma_launch_instance<Table, CH_GENERIC, false, false, kMaxNP, 4>(K, T, device, stream);
+        } else {
+            return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel, CV_8UC4: not built for this descriptor table");
+        }
+    }
     if (chain == CH_FMA_DIV)
         return fast ? tma_launch_instance<Table, CH_FMA_DIV, false>(K, T, device, stream)
                     : tma_launch_instance<Table, CH_FMA_DIV, true>(K, T, device, stream);

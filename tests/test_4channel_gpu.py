@@ -1,8 +1,11 @@
 """4-channel sources (CV_8UC4 / CV_16UC4 / CV_16SC4 -> CV_32FC4: the other half of the reference's type matrix,
 tests/batchresize/test_batchresize_x_split3D.cu:427-432, chain with cvtColor<COLOR_RGBA2BGRA>): bit-exact against the
 oracle and against the reference's own uchar4 / ushort4 / short4 instantiations."""
+import ctypes as C
+
 import numpy as np
 import pytest
+import torch
 
 from cvgpuspeedup_b200 import _abi
 from tests import gpu_util, util
@@ -47,10 +50,23 @@ def test_4channel_layouts_and_modes(src_type):
         util.assert_bit_equal(got, want, f"src_type {src_type} {kw}")
 
 
-def test_tma_kernel_declines_4channel_sources():
-    img = _img(90, _abi.CVGS_8UC4)
+def test_tma_kernel_declines_16bit_4channel_sources_and_unaligned_8uc4():
+    """The TMA-staged kernel takes CV_8UC4 whose pixels are aligned words; 16-bit pixels and 8UC4 images at odd byte
+    offsets belong to the direct-gather kernel (variant 2 = fail instead of falling back)."""
+    img = _img(90, _abi.CVGS_16UC4)
     with pytest.raises(_abi.CvgsError):
-        gpu_util.run_cvgs(img, [(0, 0, 64, 64)], (32, 32), [], variant=2, src_type=_abi.CVGS_8UC4)
+        gpu_util.run_cvgs(img, [(0, 0, 64, 64)], (32, 32), [], variant=2, src_type=_abi.CVGS_16UC4)
+    lib = _abi.load()
+    buf = torch.zeros(64 * 272 + 8, dtype=torch.uint8, device="cuda")
+    out = torch.empty((1, 4, 32, 32), device="cuda")
+    crop = (_abi.Crop * 1)()
+    crop[0].data, crop[0].width, crop[0].height, crop[0].pitch = buf.data_ptr() + 2, 64, 64, 272
+    p = util.make_pipeline((32, 32), [], out_ptr=out.data_ptr(), src_type=_abi.CVGS_8UC4)
+    prev = lib.cvgs_b200_set_kernel_variant(2)
+    try:
+        assert lib.cvgs_b200_preproc_launch(crop, 1, 1, C.byref(p), None) == 801
+    finally:
+        lib.cvgs_b200_set_kernel_variant(prev)
 
 
 @pytest.mark.parametrize("src_type,shifts", [(_abi.CVGS_8UC4, (0, 1, 2, 3)), (_abi.CVGS_16UC4, (0, 2, 4, 6)), (_abi.CVGS_16SC4, (0, 2))])
@@ -81,3 +97,34 @@ def test_4channel_taps_at_every_base_alignment(src_type, shifts):
             _abi.check(lib.cvgs_b200_preproc_launch(crops, 3, 3, C.byref(p), None))
             torch.cuda.synchronize()
             util.assert_bit_equal(out.cpu().numpy(), want, f"src {src_type} shift {shift} pitch {pitch}")
+
+
+@pytest.mark.parametrize("n,parents", [(8, True), (100, True), (300, True), (40, False), (300, False)])
+def test_tma_staged_kernel_takes_8uc4(n, parents):
+    """CV_8UC4 -> four float planes through the TMA-staged kernel (forced: variant 2 fails instead of falling back): pixels
+    are aligned words in shared memory, four channels through chain and stores.  Small batches, the 256-crop table and
+    the descriptor ring; with and without parent images; mixed up- and down-scales; the generic and the FMA-DIV chain."""
+    lib = _abi.load()
+    rng = np.random.default_rng(60 + n)
+    fw, fh = 640, 480
+    pitch = 4 * fw + 64
+    img = rng.integers(0, 256, size=(fh, pitch), dtype=np.uint8)
+    rects = []
+    for _ in range(n):
+        w, h = int(rng.integers(8, 300)), int(rng.integers(8, 300))
+        rects.append((int(rng.integers(0, fw - w + 1)), int(rng.integers(0, fh - h + 1)), w, h))
+    d_img = torch.from_numpy(img).cuda()
+    for dsize, ops in (((64, 128), [("reorder", (2, 1, 0, 3)), ("mul", (0.3, 0.3, 0.3, 0.5)), ("sub", (1.0, 4.0, 3.2, 0.25)), ("div", (3.2, 0.6, 11.8, 2.0))]),
+                       ((224, 224), [("mul", (0.5, 0.25, 2.0, 1.0)), ("add", (1.0, 2.0, 3.0, 4.0))]),
+                       ((33, 17), [])):
+        out = torch.full((n, 4, dsize[1], dsize[0]), float("nan"), device="cuda")
+        p = util.make_pipeline(dsize, ops, out_ptr=out.data_ptr(), src_type=_abi.CVGS_8UC4)
+        crops = util.host_crops(img, rects, base_ptr=d_img.data_ptr(), px_bytes=4)
+        par = util.host_parents(img, fw, fh, n, base_ptr=d_img.data_ptr()) if parents else None
+        prev = lib.cvgs_b200_set_kernel_variant(2)
+        try:
+            _abi.check(lib.cvgs_b200_preproc_launch_ex(crops, par, n, n, C.byref(p), None))
+        finally:
+            lib.cvgs_b200_set_kernel_variant(prev)
+        torch.cuda.synchronize()
+        util.assert_bit_equal(out.cpu().numpy(), util.run_oracle(img, rects, dsize, ops, src_type=_abi.CVGS_8UC4), f"8UC4 {dsize}")
