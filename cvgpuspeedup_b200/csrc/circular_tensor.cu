@@ -179,6 +179,7 @@ int cvgs_b200_ct_create(void** handle, int32_t width, int32_t height, int32_t co
 }
 
 int cvgs_b200_ct_update(void* handle, const cvgs_crop_t* frame, const cvgs_pipeline_t* pipeline, void* stream_) {
+    CVGS_RANGE("cvgs_b200_ct_update");
     CircularTensor* t = static_cast<CircularTensor*>(handle);
     if (!t) return fail(CVGS_ERR_INVALID_VALUE, "handle is NULL");
     if (!frame) return fail(CVGS_ERR_INVALID_VALUE, "frame is NULL");

@@ -15,6 +15,24 @@ int sm_count_of(int device);
 
 }  // namespace cvgs
 
+// NVTX ranges around the C-ABI entry points, compiled in with -DCVGS_NVTX (make NVTX=1), like the reference's test
+// harness does with its PUSH_RANGE / POP_RANGE macros (reference tests/nvtx.h:18-104).  Header-only NVTX v3: no
+// library to link; without a profiler attached a range costs a few nanoseconds, without the flag nothing.
+#ifdef CVGS_NVTX
+#include <nvtx3/nvToolsExt.h>
+namespace cvgs {
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+}  // namespace cvgs
+#define CVGS_RANGE(name) cvgs::NvtxRange cvgs_nvtx_range_(name)
+#else
+#define CVGS_RANGE(name) ((void)0)
+#endif
+
 // Same convention as the reference's gpuErrchk (fkl/.../core/utils/utils.h:42-60), but the C-ABI
 // returns the code instead of throwing; the header shim rethrows.
 #define CVGS_CUDA(call)                                           \

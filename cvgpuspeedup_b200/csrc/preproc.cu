@@ -968,6 +968,7 @@ int cvgs_b200_debug_host_profile(double* out5, int reset) {
 
 int cvgs_b200_preproc_launch(const cvgs_crop_t* crops, int32_t n_planes, int32_t used,
                              const cvgs_pipeline_t* pipeline, void* stream) {
+    CVGS_RANGE("cvgs_b200_preproc_launch");
     if (!pipeline) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
     return preproc_launch_impl(crops, nullptr, n_planes, used, pipeline, static_cast<float*>(pipeline->out),
                                static_cast<cudaStream_t>(stream));
@@ -975,6 +976,7 @@ int cvgs_b200_preproc_launch(const cvgs_crop_t* crops, int32_t n_planes, int32_t
 
 int cvgs_b200_preproc_launch_ex(const cvgs_crop_t* crops, const cvgs_parent_t* parents, int32_t n_planes, int32_t used,
                                 const cvgs_pipeline_t* pipeline, void* stream) {
+    CVGS_RANGE("cvgs_b200_preproc_launch_ex");
     if (!pipeline) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
     return preproc_launch_impl(crops, parents, n_planes, used, pipeline, static_cast<float*>(pipeline->out),
                                static_cast<cudaStream_t>(stream));
@@ -983,6 +985,7 @@ int cvgs_b200_preproc_launch_ex(const cvgs_crop_t* crops, const cvgs_parent_t* p
 int cvgs_b200_preproc_launch_rects(const void* frame, int32_t frame_width, int32_t frame_height, int32_t frame_pitch,
                                    const cvgs_rect_t* rects, int32_t n_planes, int32_t used, const cvgs_pipeline_t* pipeline,
                                    void* stream) {
+    CVGS_RANGE("cvgs_b200_preproc_launch_rects");
     if (!pipeline) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
     if (!frame || frame_width <= 0 || frame_height <= 0 || frame_pitch <= 0) return fail(CVGS_ERR_INVALID_VALUE, "bad frame");
     if (used < 0 || n_planes <= 0) return fail(CVGS_ERR_INVALID_VALUE, "bad batch size");
@@ -1012,6 +1015,7 @@ int cvgs_b200_preproc_launch_rects(const void* frame, int32_t frame_width, int32
 int cvgs_b200_preproc_launch_replicated(const cvgs_crop_t* crops, const cvgs_parent_t* parents, int32_t n_planes, int32_t used,
                                         const cvgs_pipeline_t* pipeline, void* const* replicas, int32_t n_replicas,
                                         void* stream) {
+    CVGS_RANGE("cvgs_b200_preproc_launch_replicated");
     if (!pipeline) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
     if (n_replicas < 0 || (n_replicas > 0 && !replicas)) return fail(CVGS_ERR_INVALID_VALUE, "bad replica list");
     return preproc_launch_impl(crops, parents, n_planes, used, pipeline, static_cast<float*>(pipeline->out),
@@ -1136,6 +1140,7 @@ static int warp_launch_impl(const cvgs_crop_t* images, const cvgs_warp_t* warps,
 
 int cvgs_b200_warp_launch(const cvgs_crop_t* images, const cvgs_warp_t* warps, int32_t n_planes, int32_t used,
                           const cvgs_pipeline_t* pipeline, void* stream) {
+    CVGS_RANGE("cvgs_b200_warp_launch");
     if (!pipeline) return fail(CVGS_ERR_INVALID_VALUE, "pipeline is NULL");
     return warp_launch_impl(images, warps, n_planes, used, pipeline, static_cast<cudaStream_t>(stream));
 }
@@ -1239,6 +1244,7 @@ static int preproc_host_impl(HostPath& h, const void* host_image, int32_t image_
 int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t image_height, int32_t image_pitch,
                            const cvgs_rect_t* rects, int32_t n_planes, int32_t used,
                            const cvgs_pipeline_t* pipeline, float* host_out, void* stream) {
+    CVGS_RANGE("cvgs_b200_preproc_host");
     return preproc_host_impl(t_ctx.host, host_image, image_width, image_height, image_pitch, rects, n_planes, used, pipeline,
                              host_out, stream);
 }
@@ -1246,6 +1252,7 @@ int cvgs_b200_preproc_host(const void* host_image, int32_t image_width, int32_t 
 int cvgs_b200_preproc_launch_sequence(const cvgs_crop_t* const* crops, const int32_t* n_planes, const int32_t* used,
                                       const cvgs_pipeline_t* const* pipelines, int32_t n_sets, int32_t steps,
                                       void* stream) {
+    CVGS_RANGE("cvgs_b200_preproc_launch_sequence");
     if (!crops || !n_planes || !used || !pipelines || n_sets <= 0 || steps < 0)
         return fail(CVGS_ERR_INVALID_VALUE, "bad sequence arguments");
     for (int i = 0; i < steps; ++i) {
@@ -1400,6 +1407,7 @@ int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const 
                                          const int32_t* n_planes, const int32_t* used,
                                          const cvgs_pipeline_t* const* pipelines, int32_t n_sets, int32_t steps,
                                          void* stream_) {
+    CVGS_RANGE("cvgs_b200_preproc_launch_sequence_ex");
     if (!crops || !parents || !n_planes || !used || !pipelines || n_sets <= 0 || steps < 0)
         return fail(CVGS_ERR_INVALID_VALUE, "bad sequence arguments");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -1503,6 +1511,7 @@ int cvgs_b200_preproc_host_sequence(const void* const* host_images, int32_t imag
                                     int32_t image_pitch, const cvgs_rect_t* const* rects, const int32_t* n_planes,
                                     const int32_t* used, const cvgs_pipeline_t* const* pipelines,
                                     float* const* host_outs, int32_t n_sets, int32_t steps, void* stream_) {
+    CVGS_RANGE("cvgs_b200_preproc_host_sequence");
     if (!host_images || !rects || !n_planes || !used || !pipelines || !host_outs || n_sets <= 0 || steps < 0)
         return fail(CVGS_ERR_INVALID_VALUE, "bad sequence arguments");
     // The frames are independent (each has its own host image and host tensor), so the loop keeps kHostLanes of

@@ -434,7 +434,8 @@ struct StageBand {
 constexpr int kNarrowNP = 2;
 constexpr int kNarrowResident = 6;
 // NC: channels = bytes of the 8-bit source pixel (3: CV_8UC3, 4: CV_8UC4); registers, chain constants and planes follow it.
-template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3>
+// U8 = true: the common geometry with packed 8-bit output (convertTo<CV_32FCn, CV_8UCn> + write<CV_8UCn>: a plain resize).
+template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3, bool U8 = false>
 __global__ void __launch_bounds__(kTmaThreads, MAXNP <= kNarrowNP ? kNarrowResident : kMaxResident)
 preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ Table T) {
     extern __shared__ uint8_t smem_raw[];
@@ -687,7 +688,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
         }
         // 8-bit packed output (general instantiation only): byte address of this lane's first pixel in row 2*jp
         uint8_t* u8row = nullptr;
-        if (GEN && P.out.u8)
+        if ((GEN || U8) && P.out.u8)
             u8row = reinterpret_cast<uint8_t*>(P.out.base) + (long long)z * P.out.z_stride + (long long)(2 * cc.jp) * P.out.row_pitch +
                     (long long)NC * (tx0 + lane);
         if (GEN && P.out.planes) {  // per-plane destinations (fk::SplitWrite): own pointer and pitch per channel
@@ -762,7 +763,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                                 if (!(im1 && (m_img & (1u << p)))) v[c].y = vb[0][c];
                             }
                         }
-                        if (GEN && P.out.u8) {  // SaturateCast<float, uchar> (or fk::Cast) + packed pixels, 3 bytes each
+                        if ((GEN || U8) && P.out.u8) {  // SaturateCast<float, uchar> (or fk::Cast) + packed pixels, NC bytes each
                             uint8_t* ub = u8row + 32 * NC * p;
                             uint8_t* ub1 = ub + P.out.row_pitch;
 #pragma unroll
@@ -800,7 +801,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             }
 #pragma unroll
             for (int c = 0; c < NC; ++c) sp[c] += 2 * (GEN ? rs[c] : (long long)row_step);
-            if (GEN && P.out.u8) u8row += 2 * P.out.row_pitch;
+            if ((GEN || U8) && P.out.u8) u8row += 2 * P.out.row_pitch;
 
             // every lane has consumed its taps of this slot (their values fed the stores above): refill it
             __syncwarp();
@@ -1273,12 +1274,12 @@ inline size_t tma_smem_bytes(const TmaGeom& G) {
     return static_cast<size_t>(kWarps) * G.slots * G.slot_bytes + kRingPad + 128;
 }
 
-template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3>
+template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3, bool U8 = false>
 inline int tma_launch_instance(const TmaParams& K, const Table& T, int device, cudaStream_t stream) {
     static thread_local size_t attr_set[64] = {};  // per device: dynamic shared memory opt-in already granted
     const size_t smem = tma_smem_bytes(K.G);
     const int slot = device & 63;
-    auto kernel = preproc_tma_kernel<Table, CHAIN, GEN, PEER, MAXNP, NC>;
+    auto kernel = preproc_tma_kernel<Table, CHAIN, GEN, PEER, MAXNP, NC, U8>;
     if (smem > attr_set[slot]) {
         const size_t want = std::max<size_t>(smem, 112 * 1024);
         CVGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(want)));
@@ -1327,6 +1328,11 @@ inline int tma_launch_kernel(const TmaParams& K, const Table& T, int chain, int 
         } else {
             return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel, CV_8UC4: not built for this descriptor table");
         }
+    }
+    // packed 8-bit output of the common geometry (a plain cv::cuda::resize on CV_8UC3 is this): its own fast instantiation
+    if (!P.band_test && P.used == P.n_planes && P.out.u8 && P.nc == 3 && !std::is_same<Table, TmaParamTable>::value) {
+        if (chain == CH_FMA_DIV) return tma_launch_instance<Table, CH_FMA_DIV, false, false, kMaxNP, 3, true>(K, T, device, stream);
+        return tma_launch_instance<Table, CH_GENERIC, false, false, kMaxNP, 3, true>(K, T, device, stream);
     }
     if (chain == CH_FMA_DIV)
         return fast ? tma_launch_instance<Table, CH_FMA_DIV, false>(K, T, device, stream)
