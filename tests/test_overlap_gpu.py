@@ -226,11 +226,40 @@ def test_frame_loop_shares_launches(overlap_on):
     # a second sequence on the same stream reuses the cached tensor maps
     for o in outs:
         o.fill_(float("nan"))
+    torch.cuda.synchronize()  # the fills ran on the default stream, the loop runs on st
     launches2, keep2 = _sequence(lib, ws, d_imgs, outs, len(ws), st)
     st.synchronize()
     assert launches2 <= 2
     for k, o in enumerate(outs):
         util.assert_bit_equal(o.cpu().numpy(), want[k], f"second sequence, set {k}")
+    del keep, keep2
+
+
+def test_frame_loop_shared_launches_overlap_and_rewrite(overlap_on):
+    """More sets than one launch takes (24 x 50 crops: 10 sets per launch) and several passes over them: consecutive
+    launches overlap (late griddepcontrol.wait) until one rewrites a tensor a launch possibly in flight wrote.  Between
+    passes the sources of half the sets change (device-side copy on the same stream), so a launch that ran ahead of the
+    stream order or a stale tensor would show."""
+    lib = overlap_on
+    st = torch.cuda.Stream()
+    n_sets = 24
+    ws_a = [util.workload_c2(seed=800 + k, n=50, frame=(960, 540), pitch=2880) for k in range(n_sets)]
+    ws_b = [util.workload_c2(seed=900 + k, n=50, frame=(960, 540), pitch=2880) for k in range(n_sets)]
+    for a, b in zip(ws_a, ws_b):
+        b.rects = a.rects  # same crops, other pixels
+    d_imgs = [torch.from_numpy(w.image).cuda() for w in ws_a]
+    d_alt = [torch.from_numpy(w.image).cuda() for w in ws_b]
+    outs = [torch.full((50, 3, 128, 64), float("nan"), device="cuda") for _ in ws_a]
+    with torch.cuda.stream(st):
+        launches, keep = _sequence(lib, ws_a, d_imgs, outs, 3 * n_sets + 7, st)
+        for k in range(0, n_sets, 2):
+            d_imgs[k].copy_(d_alt[k], non_blocking=True)   # stream-ordered behind the first loop
+        launches2, keep2 = _sequence(lib, ws_a, d_imgs, outs, 2 * n_sets, st)
+    st.synchronize()
+    assert launches <= 10 and launches2 <= 6, (launches, launches2)
+    for k in range(n_sets):
+        w = ws_b[k] if k % 2 == 0 else ws_a[k]
+        util.assert_bit_equal(outs[k].cpu().numpy(), util.run_oracle(w.image, w.rects, w.dsize, w.ops), f"set {k}")
     del keep, keep2
 
 
