@@ -469,7 +469,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
     // CV_8UC4 batches the TMA-staged kernel can take go through the 256-crop table or the descriptor ring (the
     // instantiations built for four channels, tma_launch_kernel); everything else of a small batch is decided here
     bool small_batch = used <= kTmaParamCrops && !planes_out && n_replicas == 0;
-    if (small_batch && P.nc == 4 && variant != 1) {
+    if (small_batch && P.src_type != CVGS_8UC3 && variant != 1) {
         DevCrop probe[kTmaParamCrops];
         bool ok = true;
         for (int i = 0; i < used && ok; ++i) ok = fill_crop(crops[i], *pipe, i, probe[i]) == CVGS_OK;
@@ -488,7 +488,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         TmaParams K;
         K.P = P;
         K.maps = nullptr;
-        if (variant != 1 && P.nc == 3 && tma_plan(P, tt.c, used, n_planes, sms, parents != nullptr, items_per_warp(), K.G)) {
+        if (variant != 1 && P.src_type == CVGS_8UC3 && tma_plan(P, tt.c, used, n_planes, sms, parents != nullptr, items_per_warp(), K.G)) {
             const int chain = scaled_program(P, K);
             const int pb = 3;
             const MemRange src = crops_range(tt.c, used, pb);  // before the TMA fields overwrite the pointers
@@ -542,7 +542,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         K.maps = nullptr;
         if (tma_plan(P, lt.c, used, n_planes, sms, true, items_per_warp(), K.G)) {
             const int chain = scaled_program(P, K);
-            const int pb = P.nc == 4 ? 4 : 3;
+            const int pb = pixel_bytes_of(P.src_type);
             const MemRange src = crops_range(lt.c, used, pb);
             if (prepare_image_maps(lt.c, parents, used, K.G, P.W, lt.m, kTmaImageMaps, pb) >= 0) {
                 K.G.pdl_wait = overlap_needs_wait(stream, out_range(P), src) ? 1 : 0;
@@ -568,7 +568,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         chain = scaled_program(P, K);
         CUtensorMap* hm = r.maps_h(slot);
         // maps sit in front of the crops in the slot; image mode needs only a few of them
-        const int pb = P.nc == 4 ? 4 : 3;
+        const int pb = pixel_bytes_of(P.src_type);
         const int n_img = prepare_image_maps(hc, parents, used, K.G, P.W, hm, kTmaImageMaps, pb);
         if (n_img >= 0) {
             map_bytes = static_cast<size_t>(n_img) * sizeof(CUtensorMap);

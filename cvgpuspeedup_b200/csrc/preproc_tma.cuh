@@ -49,7 +49,8 @@ constexpr int kSlotHeader = 128;        // per slot: room for the w[-1] over-rea
 constexpr int kRingPad = 128;           // bytes behind the last slot (w[+1] over-read)
 constexpr int kMaxBoxBytes = 2048;      // 256 elements x 8 bytes
 constexpr float kWeightScale = 1.2676506002282294e30f;  // 2^100
-constexpr float kPreScale = 8589934592.0f;              // 2^33  = 2^133 / 2^100
+constexpr float kPreScale = 8589934592.0f;              // 2^33  = 2^133 / 2^100   (8-bit sources)
+constexpr float kPreScale16 = 2199023255552.0f;         // 2^41  = 2^141 / 2^100   (16-bit sources: halfword at mantissa bits 8..23)
 constexpr uint32_t kRowFill = 0xFFFFFFF0u;  // RowTap::a: row lies outside the image band -> background
 constexpr uint32_t kRowSkip = 0xFFFFFFFFu;  // RowTap::a: row is below the plane (or past the warp's range) -> nothing to do
 
@@ -92,7 +93,8 @@ struct TmaGeom {
     int32_t np_last;         // 32-column groups of the last band of a plane (the others have NPB)
     int32_t w_full, w_crop;  // cost (column groups) of the full-width bands of a plane / of a whole plane
     int32_t share_q, share_r;  // total cost = share_q * (grid * kWarps) + share_r
-    int32_t explicit_prescale;  // 1: the kernel multiplies by 2^33 itself (no op to fold it into)
+    int32_t explicit_prescale;  // 1: the kernel multiplies by `prescale` itself (no op to fold it into)
+    float prescale;          // what undoes the tap / weight scaling: 2^33 for 8-bit sources, 2^41 for 16-bit ones
     int32_t pdl_wait;        // 1: wait for the preceding kernel before the first global access (stream order);
                              // 0: the host proved independence, wait only before exiting (completion order)
     FastDiv d_w_crop, d_NPB, d_np_last, d_items_per_crop, d_HP;  // divisions by the fields of those names
@@ -240,6 +242,10 @@ __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcon
 __device__ __forceinline__ float u8_scaled(uint32_t w, uint32_t k) {
     return __uint_as_float(__byte_perm(w, 0u, 0x4044u | (k << 8)));
 }
+// halfword k of w as the float h * 2^-141: placed at mantissa bits 8..23, any 24-bit pattern X is exactly X * 2^-149
+__device__ __forceinline__ float u16_scaled(uint32_t w, uint32_t k) {
+    return __uint_as_float(__byte_perm(w, 0u, k ? 0x4324u : 0x4104u));
+}
 
 template <typename Table>
 __device__ __forceinline__ const DevCrop& tma_crop_of(const TmaParams&, const Table& T, int z) {
@@ -345,9 +351,42 @@ struct ItemCursor {
 // row r in .x and row r+1 in .y (scaled by 2^-33).  Arithmetic per half = Interpolate<INTER_LINEAR>::exec in the
 // order nvcc emits for the reference: FMUL(p10*w10), FFMA(p00,w00), FFMA(p01,w01), FFMA(p11,w11).
 // NC = 4 (CV_8UC4): a pixel is one aligned word -- two loads per source row, no shifts.
-template <int NC>
+// DEPTH = 2 (CV_16UC3 / CV_16UC4): halfword samples; 6-byte pixels start on even bytes (one funnel shift by 0 or 16 bits
+// lines three words up on halfword pairs), 8-byte pixels are two aligned words.
+template <int NC, int DEPTH>
 __device__ __forceinline__ void gather_pair(uint32_t A0, uint32_t B0, uint32_t A1, uint32_t B1, int shl, int shr, bool edge,
                                             float wx0, float wx1, float2 wy0, float2 wy1, float2 (&v)[NC]) {
+    const float2 w00 = __fmul2_rn(make_float2(wx0, wx0), wy0), w10 = __fmul2_rn(make_float2(wx1, wx1), wy0);
+    const float2 w01 = __fmul2_rn(make_float2(wx0, wx0), wy1), w11 = __fmul2_rn(make_float2(wx1, wx1), wy1);
+    if constexpr (DEPTH == 2) {
+        // per source row: left / right pixel as NC halfword-floats each
+        float pl[4][NC], pr[4][NC];  // rows: A0, B0, A1, B1
+        const uint32_t base[4] = {A0, B0, A1, B1};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t w0 = lds32_tap(base[r]), w1 = lds32_tap(base[r] + 4), w2 = lds32_tap(base[r] + 8), w3 = lds32_tap(base[r] + 12);
+            if constexpr (NC == 3) {
+                const uint32_t L0 = __funnelshift_r(w0, w1, shl), L1 = __funnelshift_r(w1, w2, shl), L2 = __funnelshift_r(w2, w3, shl);
+                pl[r][0] = u16_scaled(L0, 0), pl[r][1] = u16_scaled(L0, 1), pl[r][2] = u16_scaled(L1, 0);
+                pr[r][0] = u16_scaled(L1, 1), pr[r][1] = u16_scaled(L2, 0), pr[r][2] = u16_scaled(L2, 1);
+            } else {
+                pl[r][0] = u16_scaled(w0, 0), pl[r][1] = u16_scaled(w0, 1), pl[r][2] = u16_scaled(w1, 0), pl[r][3] = u16_scaled(w1, 1);
+                pr[r][0] = u16_scaled(w2, 0), pr[r][1] = u16_scaled(w2, 1), pr[r][2] = u16_scaled(w3, 0), pr[r][3] = u16_scaled(w3, 1);
+            }
+            if (edge) {  // x2_read == x1 (interpolation.cuh:72): the right tap is the left pixel again
+#pragma unroll
+                for (int c = 0; c < NC; ++c) pr[r][c] = pl[r][c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            float2 t = __fmul2_rn(make_float2(pr[0][c], pr[2][c]), w10);
+            t = __ffma2_rn(make_float2(pl[0][c], pl[2][c]), w00, t);
+            t = __ffma2_rn(make_float2(pl[1][c], pl[3][c]), w01, t);
+            v[c] = __ffma2_rn(make_float2(pr[1][c], pr[3][c]), w11, t);
+        }
+        return;
+    }
     uint32_t al0, bl0, al1, bl1, ar0, br0, ar1, br1;
     if constexpr (NC == 4) {
         al0 = lds32_tap(A0), ar0 = lds32_tap(A0 + 4);
@@ -371,8 +410,6 @@ __device__ __forceinline__ void gather_pair(uint32_t A0, uint32_t B0, uint32_t A
         ar1 = al1;
         br1 = bl1;
     }
-    const float2 w00 = __fmul2_rn(make_float2(wx0, wx0), wy0), w10 = __fmul2_rn(make_float2(wx1, wx1), wy0);
-    const float2 w01 = __fmul2_rn(make_float2(wx0, wx0), wy1), w11 = __fmul2_rn(make_float2(wx1, wx1), wy1);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         float2 t = __fmul2_rn(make_float2(u8_scaled(ar0, c), u8_scaled(ar1, c)), w10);
@@ -388,7 +425,7 @@ template <int NC>
 __device__ __forceinline__ void apply_program_pair(const DevProgram& prog, float2 (&v)[NC]) {
     if (prog.round_u8) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) v[c] = make_float2(round_sat_u8(v[c].x), round_sat_u8(v[c].y));
+        for (int c = 0; c < NC; ++c) v[c] = make_float2(round_sat_kind(v[c].x, prog.round_u8), round_sat_kind(v[c].y, prog.round_u8));
     }
     for (int i = 0; i < prog.n_ops; ++i) {
         const DevOp& op = prog.ops[i];
@@ -435,7 +472,8 @@ constexpr int kNarrowNP = 2;
 constexpr int kNarrowResident = 6;
 // NC: channels = bytes of the 8-bit source pixel (3: CV_8UC3, 4: CV_8UC4); registers, chain constants and planes follow it.
 // U8 = true: the common geometry with packed 8-bit output (convertTo<CV_32FCn, CV_8UCn> + write<CV_8UCn>: a plain resize).
-template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3, bool U8 = false>
+// DEPTH: bytes per source sample (1: CV_8U, 2: CV_16U).
+template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3, bool U8 = false, int DEPTH = 1>
 __global__ void __launch_bounds__(kTmaThreads, MAXNP <= kNarrowNP ? kNarrowResident : kMaxResident)
 preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ Table T) {
     extern __shared__ uint8_t smem_raw[];
@@ -589,7 +627,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             const int itx = (int)fast_div((uint32_t)(idx - iz * G.items_per_crop), G.d_HP);
             if (!GEN || iz < P.used) {
                 const DevCrop& C = tma_crop_of<Table>(K, T, iz);
-                const BandOrigin b = band_origin<NC>(P, G, C, itx);
+                const BandOrigin b = band_origin<NC * DEPTH>(P, G, C, itx);
                 // all lanes computed the same values; telling the compiler so keeps the TMA issue below loop-free
                 sb.c0 = uniform_i(b.c0);
                 sb.rb = uniform_i(crop_row_bytes(C));
@@ -643,7 +681,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             int bx1 = 0, wm1 = 0;
             if (active) {
                 const DevCrop& C = tma_crop_of<Table>(K, T, z);
-                b = band_origin<NC>(P, G, C, cc.txi);
+                b = band_origin<NC * DEPTH>(P, G, C, cc.txi);
                 fx = C.fx;
                 bx1 = C.bx1;
                 wm1 = C.w - 1;
@@ -662,8 +700,11 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                     m_in |= (in_p ? 1u : 0u) << p;
                     m_img |= (img_p ? 1u : 0u) << p;
                     m_edge |= (t.i1 + 1 > wm1 ? 1u : 0u) << p;
-                    const int o = NC * t.i1 - b.origin;
-                    if (NC == 4) {  // word-aligned pixels (the plan requires 4-byte aligned rows)
+                    const int o = NC * DEPTH * t.i1 - b.origin;
+                    if (DEPTH == 2) {  // halfword samples: the word that holds the pixel's first sample, and 0 or 16 bits to shift
+                        off[p] = (o >> 2) * 4;
+                        shl[p] = (o & 2) * 8;
+                    } else if (NC == 4) {  // word-aligned pixels (the plan requires 4-byte aligned rows)
                         off[p] = o;
                     } else {
                         off[p] = ((o + 3) >> 2) * 4;
@@ -740,7 +781,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                     if (!CHECK || (m_in & (1u << p))) {  // lanes past the right border of the plane skip
                         float2 v[NC];
                         if (!GEN || im0 || im1) {
-                            gather_pair<NC>(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p],
+                            gather_pair<NC, DEPTH>(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p],
                                         (m_edge & (1u << p)) != 0, wxa[p], wxb[p], wy0, wy1, v);
                             if (CHAIN == CH_FMA_DIV) {
 #pragma unroll
@@ -751,7 +792,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                             } else {
                                 if (G.explicit_prescale) {
 #pragma unroll
-                                    for (int c = 0; c < NC; ++c) v[c] = __fmul2_rn(v[c], make_float2(kPreScale, kPreScale));
+                                    for (int c = 0; c < NC; ++c) v[c] = __fmul2_rn(v[c], make_float2(G.prescale, G.prescale));
                                 }
                                 apply_program_pair<NC>(K.prog_img, v);
                             }
@@ -899,12 +940,13 @@ inline int rb_class(int rb, bool fine = false) {
 inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int n_planes, int sm_count, bool image_mode,
                      int items_per_warp, TmaGeom& G, bool need_driver = true, int grid_div = 1, int max_resident = kMaxResident) {
     if (need_driver && !encode_tiled_fn()) return false;
-    // the tap extraction is written for 3-byte pixels and for 4-byte pixels that are aligned words
-    if (P.src_type != CVGS_8UC3 && P.src_type != CVGS_8UC4) return false;
-    const int pb = P.src_type == CVGS_8UC4 ? 4 : 3;
-    if (P.out.u8 && P.prog.nc_out != pb) return false;
-    // four channels: built for the common geometry only (IGNORE_AR, every plane used, planar float tensors)
-    if (pb == 4 && (P.band_test || P.used != P.n_planes || P.out.px_stride != 1 || P.out.planes || P.out.u8)) return false;
+    // the tap extraction is written for 3-byte pixels, for 4-byte pixels that are aligned words, and for unsigned 16-bit
+    // samples (6-byte pixels on even bytes, 8-byte pixels as aligned word pairs)
+    if (P.src_type != CVGS_8UC3 && P.src_type != CVGS_8UC4 && P.src_type != CVGS_16UC3 && P.src_type != CVGS_16UC4) return false;
+    const int pb = P.src_type == CVGS_8UC3 ? 3 : (P.src_type == CVGS_8UC4 ? 4 : (P.src_type == CVGS_16UC3 ? 6 : 8));
+    if (P.out.u8 && (pb != 3 || P.prog.nc_out != 3)) return false;
+    // everything but CV_8UC3: built for the common geometry only (IGNORE_AR, every plane used, planar float tensors)
+    if (pb != 3 && (P.band_test || P.used != P.n_planes || P.out.px_stride != 1 || P.out.planes || P.out.u8)) return false;
     if (P.prog.special) return false;           // conversions that change the channel count: direct-gather kernel
     if (P.out.row_stride != static_cast<long long>(P.W) * P.out.px_stride) return false;  // padded packed rows: direct-gather kernel
     float fx_max = 0.f;
@@ -912,6 +954,7 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
         const DevCrop& c = crops[i];
         if (c.h > 1 && c.pitch % 16 != 0) return false;  // TMA: row stride must be a multiple of 16 bytes
         if (pb == 4 && (reinterpret_cast<uintptr_t>(c.data) & 3)) return false;  // CV_8UC4: pixels are aligned words
+        if (pb == 8 && (reinterpret_cast<uintptr_t>(c.data) & 7)) return false;  // CV_16UC4: aligned word pairs
         if (!(c.fx > 0.f) || !(c.fy > 0.f) || !std::isfinite(c.fx) || !std::isfinite(c.fy)) return false;
         fx_max = std::max(fx_max, c.fx);
     }
@@ -937,6 +980,7 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
     G.total_items = static_cast<int32_t>(total);
     G.slot_bytes = kSlotHeader + 4 * rb_max;  // rb_max is a multiple of 64: slots stay 128-byte aligned
     G.explicit_prescale = 0;
+    G.prescale = pb >= 6 ? kPreScale16 : kPreScale;
     G.pdl_wait = 1;
     // ring depth: as deep as possible while kMaxResident CTAs stay resident per SM, but at least two slots
     const int smem_sm = 227 * 1024;
@@ -1025,9 +1069,10 @@ inline int scaled_program(const PreprocParams& P, TmaParams& K) {
         DevProgram prog_img;
         float zh[4], zl[4];
         int explicit_prescale, chain;
+        float prescale = 0.f;
     };
     static thread_local Memo m;
-    if (m.valid && std::memcmp(&m.key, &P.prog, sizeof(DevProgram)) == 0) {
+    if (m.valid && m.prescale == K.G.prescale && std::memcmp(&m.key, &P.prog, sizeof(DevProgram)) == 0) {
         K.prog_img = m.prog_img;
         std::memcpy(K.zh, m.zh, sizeof m.zh);
         std::memcpy(K.zl, m.zl, sizeof m.zl);
@@ -1041,6 +1086,7 @@ inline int scaled_program(const PreprocParams& P, TmaParams& K) {
     std::memcpy(m.zh, K.zh, sizeof m.zh);
     std::memcpy(m.zl, K.zl, sizeof m.zl);
     m.explicit_prescale = K.G.explicit_prescale;
+    m.prescale = K.G.prescale;
     m.chain = chain;
     m.valid = true;
     return chain;
@@ -1086,7 +1132,7 @@ inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
         }
         if (ok) {
             for (int c = 0; c < nc; ++c) {
-                lin.a[c] *= kPreScale;
+                lin.a[c] *= K.G.prescale;
                 K.zh[c] = dc[c].zh;
                 K.zl[c] = dc[c].zl;
             }
@@ -1100,11 +1146,11 @@ inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
     DevOp& op = ops[0];
     if (op.kind == DOP_MUL || op.kind == DOP_FMA) {
         if (!all_moderate(op.a, false)) return CH_GENERIC;
-        for (int c = 0; c < nc; ++c) op.a[c] *= kPreScale;
+        for (int c = 0; c < nc; ++c) op.a[c] *= K.G.prescale;
         K.G.explicit_prescale = 0;
     } else if (op.kind == DOP_DIV) {
         if (!all_moderate(op.a, true)) return CH_GENERIC;
-        for (int c = 0; c < nc; ++c) op.a[c] /= kPreScale;
+        for (int c = 0; c < nc; ++c) op.a[c] /= K.G.prescale;
         K.G.explicit_prescale = 0;
     }
     return CH_GENERIC;
@@ -1274,12 +1320,12 @@ inline size_t tma_smem_bytes(const TmaGeom& G) {
     return static_cast<size_t>(kWarps) * G.slots * G.slot_bytes + kRingPad + 128;
 }
 
-template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3, bool U8 = false>
+template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3, bool U8 = false, int DEPTH = 1>
 inline int tma_launch_instance(const TmaParams& K, const Table& T, int device, cudaStream_t stream) {
     static thread_local size_t attr_set[64] = {};  // per device: dynamic shared memory opt-in already granted
     const size_t smem = tma_smem_bytes(K.G);
     const int slot = device & 63;
-    auto kernel = preproc_tma_kernel<Table, CHAIN, GEN, PEER, MAXNP, NC, U8>;
+    auto kernel = preproc_tma_kernel<Table, CHAIN, GEN, PEER, MAXNP, NC, U8, DEPTH>;
     if (smem > attr_set[slot]) {
         const size_t want = std::max<size_t>(smem, 112 * 1024);
         CVGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(want)));
@@ -1320,13 +1366,24 @@ inline int tma_launch_kernel(const TmaParams& K, const Table& T, int chain, int 
     static_assert(sizeof(TmaParams) + sizeof(Table) <= 32 * 1024, "kernel parameters exceed 32 KB");
     const PreprocParams& P = K.P;
     const bool fast = !P.band_test && P.used == P.n_planes && P.out.px_stride == 1 && !P.out.planes && !P.out.u8;
-    if (P.nc == 4) {  // CV_8UC4: built for the common geometry and for the tables batches of such frames arrive in
+    if (P.src_type != CVGS_8UC3) {  // CV_8UC4, CV_16UC3, CV_16UC4: built for the common geometry and for the tables
+                                    // batches of such frames arrive in
         if constexpr (std::is_same<Table, TmaImageTableL>::value || std::is_same<Table, TmaNoTable>::value) {
-            if (!fast) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel, CV_8UC4: common geometry only");
-            if (chain == CH_FMA_DIV) return tma_launch_instance<Table, CH_FMA_DIV, false, false, kMaxNP, 4>(K, T, device, stream);
-            return tma_launch_instance<Table, CH_GENERIC, false, false, kMaxNP, 4>(K, T, device, stream);
+            if (!fast) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel: this pixel type takes the common geometry only");
+            const bool fd = chain == CH_FMA_DIV;
+            switch (P.src_type) {
+                case CVGS_8UC4:
+                    return fd ? tma_launch_instance<Table, CH_FMA_DIV, false, false, kMaxNP, 4>(K, T, device, stream)
+                              : tma_launch_instance<Table, CH_GENERIC, false, false, kMaxNP, 4>(K, T, device, stream);
+                case CVGS_16UC3:
+                    return fd ? tma_launch_instance<Table, CH_FMA_DIV, false, false, kMaxNP, 3, false, 2>(K, T, device, stream)
+                              : tma_launch_instance<Table, CH_GENERIC, false, false, kMaxNP, 3, false, 2>(K, T, device, stream);
+                default:
+                    return fd ? tma_launch_instance<Table, CH_FMA_DIV, false, false, kMaxNP, 4, false, 2>(K, T, device, stream)
+                              : tma_launch_instance<Table, CH_GENERIC, false, false, kMaxNP, 4, false, 2>(K, T, device, stream);
+            }
         } else {
-            return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel, CV_8UC4: not built for this descriptor table");
+            return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel: this pixel type is not built for this descriptor table");
         }
     }
     // packed 8-bit output of the common geometry (a plain cv::cuda::resize on CV_8UC3 is this): its own fast instantiation

@@ -52,7 +52,7 @@ def run(name, src_type, ops, px_bytes, image, crops_of, out_channels=3, out_byte
     par = (_abi.Parent * N)()  # the frame every crop was cut from (GpuMat::datastart / locateROI)
     for i in range(N):
         par[i].datastart, par[i].whole_width, par[i].whole_height = d_img.data_ptr(), FW, FH
-    use_par = px_bytes in (3, 4)
+    use_par = px_bytes in (3, 4, 6, 8)
 
     def launch():
         if use_par:

@@ -34,10 +34,12 @@ def test_16bit_sources_match_oracle(src_type, aspect):
             util.assert_bit_equal(got, want, f"src_type {src_type} aspect {aspect} {dsize} {kw}")
 
 
-def test_tma_kernel_declines_16bit_sources():
+def test_tma_kernel_declines_signed_16bit_sources():
+    """Unsigned 16-bit samples go through the TMA-staged kernel (tests/test_4channel_gpu.py); signed ones keep the
+    direct-gather kernel (variant 2 = fail instead of falling back)."""
     img = _image16(42, 64, 64, 384, False)
     with pytest.raises(_abi.CvgsError):
-        gpu_util.run_cvgs(img, [(0, 0, 64, 64)], (32, 32), [], variant=2, src_type=_abi.CVGS_16UC3)
+        gpu_util.run_cvgs(img, [(0, 0, 64, 64)], (32, 32), [], variant=2, src_type=_abi.CVGS_16SC3)
 
 
 def test_circular_tensor_with_16bit_frames():

@@ -50,12 +50,12 @@ def test_4channel_layouts_and_modes(src_type):
         util.assert_bit_equal(got, want, f"src_type {src_type} {kw}")
 
 
-def test_tma_kernel_declines_16bit_4channel_sources_and_unaligned_8uc4():
+def test_tma_kernel_declines_signed_16bit_sources_and_unaligned_8uc4():
     """The TMA-staged kernel takes CV_8UC4 whose pixels are aligned words; 16-bit pixels and 8UC4 images at odd byte
     offsets belong to the direct-gather kernel (variant 2 = fail instead of falling back)."""
-    img = _img(90, _abi.CVGS_16UC4)
+    img = _img(90, _abi.CVGS_16SC4)
     with pytest.raises(_abi.CvgsError):
-        gpu_util.run_cvgs(img, [(0, 0, 64, 64)], (32, 32), [], variant=2, src_type=_abi.CVGS_16UC4)
+        gpu_util.run_cvgs(img, [(0, 0, 64, 64)], (32, 32), [], variant=2, src_type=_abi.CVGS_16SC4)
     lib = _abi.load()
     buf = torch.zeros(64 * 272 + 8, dtype=torch.uint8, device="cuda")
     out = torch.empty((1, 4, 32, 32), device="cuda")
@@ -99,27 +99,34 @@ def test_4channel_taps_at_every_base_alignment(src_type, shifts):
             util.assert_bit_equal(out.cpu().numpy(), want, f"src {src_type} shift {shift} pitch {pitch}")
 
 
+@pytest.mark.parametrize("src_type,px", [(_abi.CVGS_8UC4, 4), (_abi.CVGS_16UC3, 6), (_abi.CVGS_16UC4, 8)])
 @pytest.mark.parametrize("n,parents", [(8, True), (100, True), (300, True), (40, False), (300, False)])
-def test_tma_staged_kernel_takes_8uc4(n, parents):
-    """CV_8UC4 -> four float planes through the TMA-staged kernel (forced: variant 2 fails instead of falling back): pixels
-    are aligned words in shared memory, four channels through chain and stores.  Small batches, the 256-crop table and
-    the descriptor ring; with and without parent images; mixed up- and down-scales; the generic and the FMA-DIV chain."""
+def test_tma_staged_kernel_takes_8uc4_and_16u(n, parents, src_type, px):
+    """CV_8UC4 / CV_16UC3 / CV_16UC4 through the TMA-staged kernel (forced: variant 2 fails instead of falling back):
+    aligned-word pixels, halfword samples (6-byte pixels at both word phases), three / four channels through chain and
+    stores.  Small batches, the 256-crop table and the descriptor ring; with and without parent images; mixed up- and
+    down-scales; the FMA-DIV chain, a generic chain, no chain, and the rounded-resize mode."""
     lib = _abi.load()
-    rng = np.random.default_rng(60 + n)
+    rng = np.random.default_rng(60 + n + px)
     fw, fh = 640, 480
-    pitch = 4 * fw + 64
+    pitch = px * fw + 64
     img = rng.integers(0, 256, size=(fh, pitch), dtype=np.uint8)
-    rects = []
-    for _ in range(n):
-        w, h = int(rng.integers(8, 300)), int(rng.integers(8, 300))
+    nc = util.channels_of(src_type)
+    rects = [(1, 0, 33, 20), (2, 1, 17, 9)]  # odd x: 6-byte pixels on the other word phase
+    top = 300 if px < 8 else 200  # 8-byte pixels: a 32-column band of a 9x down-scale would exceed the 2 KB TMA box row
+    for _ in range(n - 2):
+        w, h = int(rng.integers(8, top)), int(rng.integers(8, top))
         rects.append((int(rng.integers(0, fw - w + 1)), int(rng.integers(0, fh - h + 1)), w, h))
     d_img = torch.from_numpy(img).cuda()
-    for dsize, ops in (((64, 128), [("reorder", (2, 1, 0, 3)), ("mul", (0.3, 0.3, 0.3, 0.5)), ("sub", (1.0, 4.0, 3.2, 0.25)), ("div", (3.2, 0.6, 11.8, 2.0))]),
-                       ((224, 224), [("mul", (0.5, 0.25, 2.0, 1.0)), ("add", (1.0, 2.0, 3.0, 4.0))]),
-                       ((33, 17), [])):
-        out = torch.full((n, 4, dsize[1], dsize[0]), float("nan"), device="cuda")
-        p = util.make_pipeline(dsize, ops, out_ptr=out.data_ptr(), src_type=_abi.CVGS_8UC4)
-        crops = util.host_crops(img, rects, base_ptr=d_img.data_ptr(), px_bytes=4)
+    cases = [((64, 128), [("reorder", (2, 1, 0, 3)[:nc]), ("mul", (0.3, 0.3, 0.3, 0.5)[:nc]), ("sub", (1.0, 4.0, 3.2, 0.25)[:nc]),
+                          ("div", (3.2, 0.6, 11.8, 2.0)[:nc])], {}),
+             ((224, 224), [("mul", (0.5, 0.25, 2.0, 1.0)[:nc]), ("add", (1.0, 2.0, 3.0, 4.0)[:nc])], {}),
+             ((33, 17), [], {}),
+             ((48, 40), [("mul", (0.5, 0.25, 2.0, 1.0)[:nc])], dict(fp_contract=_abi.FP_SEPARATE, interp_mode=_abi.INTERP_ROUND_U8))]
+    for dsize, ops, kw in cases:
+        out = torch.full((n, nc, dsize[1], dsize[0]), float("nan"), device="cuda")
+        p = util.make_pipeline(dsize, ops, out_ptr=out.data_ptr(), src_type=src_type, **kw)
+        crops = util.host_crops(img, rects, base_ptr=d_img.data_ptr(), px_bytes=px)
         par = util.host_parents(img, fw, fh, n, base_ptr=d_img.data_ptr()) if parents else None
         prev = lib.cvgs_b200_set_kernel_variant(2)
         try:
@@ -127,4 +134,4 @@ def test_tma_staged_kernel_takes_8uc4(n, parents):
         finally:
             lib.cvgs_b200_set_kernel_variant(prev)
         torch.cuda.synchronize()
-        util.assert_bit_equal(out.cpu().numpy(), util.run_oracle(img, rects, dsize, ops, src_type=_abi.CVGS_8UC4), f"8UC4 {dsize}")
+        util.assert_bit_equal(out.cpu().numpy(), util.run_oracle(img, rects, dsize, ops, src_type=src_type, **kw), f"{src_type} {dsize}")
