@@ -305,7 +305,7 @@ def workload_config(n_frames: int):
             "fp_contract": "reference_fused", "interp_mode": "float", "sharding": "frames per GPU, no collective",
             "launch_api": "cvgs_b200_preproc_launch_sequence_ex (crops + parent frame per frame) with "
                           "cvgs_b200_set_overlap(1): the library proves the frames independent and lets consecutive "
-                          "frames share kernel launches (up to 512 crops / 32 frames per launch)",
+                          "frames share kernel launches (up to 928 crops / 32 frames per launch)",
             "host_threads": 1}
 
 
@@ -507,7 +507,7 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int):
                        "flight: upload / kernel / download overlap)"},
         "gpu_launches": int(launches_per_rep),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "preproc_tma_kernel (shared by up to 10 frames of 50 crops)",
+                     "traffic": traffic, "kernel": "preproc_tma_kernel (shared by up to 18 frames of 50 crops)",
                      "peak_source": peak_src, "unit_of_work": "one 50-crop frame",
                      "algorithmic_bytes_per_frame": bytes_in + bytes_out, "bytes_in": bytes_in, "bytes_out": bytes_out,
                      "us_per_frame": us_per_frame, "frames_per_launch": F * K / max(1, launches_per_rep),

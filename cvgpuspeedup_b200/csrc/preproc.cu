@@ -659,6 +659,9 @@ static int launch_multi(const MultiSet* sets, int G, const cvgs_pipeline_t* pipe
     DevMapCache& mc = t_dev_maps;
     if (int rc = mc.reserve(device)) return rc;
     alignas(64) TmaMultiTable mt;
+    static thread_local std::vector<DevCrop> full_tl;  // the crops in full form (planning, placement); 45 KB
+    full_tl.resize(kMultiCrops);
+    DevCrop* full = full_tl.data();
     TmaParams K;
     for (int attempt = 0;; ++attempt) {
         int z = 0;
@@ -666,7 +669,7 @@ static int launch_multi(const MultiSet* sets, int G, const cvgs_pipeline_t* pipe
             mt.out_base[g] = sets[g].out;
             mt.z_first[g] = z;
             for (int i = 0; i < sets[g].n; ++i, ++z)
-                if (int rc = fill_crop(sets[g].crops[i], *pipe, z, mt.c[z])) return rc;
+                if (int rc = fill_crop(sets[g].crops[i], *pipe, z, full[z])) return rc;
         }
         K.P = P;
         K.P.out.base = nullptr;  // every plane goes through out_base[]
@@ -674,7 +677,7 @@ static int launch_multi(const MultiSet* sets, int G, const cvgs_pipeline_t* pipe
             const char* e = std::getenv("CVGS_B200_MULTI_GRID_DIV");
             return e ? std::max(1, std::atoi(e)) : 1;
         }();
-        if (!tma_plan(P, mt.c, total, total, sms, true, 1, K.G, true, grid_div)) return kMultiDeclined;
+        if (!tma_plan(P, full, total, total, sms, true, 1, K.G, true, grid_div)) return kMultiDeclined;
         const uint32_t gen = mc.generation;
         const int TWp = std::min(32 * K.G.NPB, P.W);
         bool restart = false;
@@ -684,7 +687,7 @@ static int launch_multi(const MultiSet* sets, int G, const cvgs_pipeline_t* pipe
             int last_rb = -1, last_idx = -1;
             for (int i = 0; i < sets[g].n; ++i, ++z) {
                 const cvgs_parent_t& p = sets[g].parents[i];
-                DevCrop& c = mt.c[z];
+                const DevCrop& c = full[z];
                 if (!p.datastart || p.whole_width <= 0 || p.whole_height <= 0) return kMultiDeclined;
                 const int rb = rb_class(band_row_bytes(TWp, c.fx), true);
                 if (rb == 0 || 4 * rb + kSlotHeader > K.G.slot_bytes) return kMultiDeclined;
@@ -701,12 +704,13 @@ static int launch_multi(const MultiSet* sets, int G, const cvgs_pipeline_t* pipe
                     last_rb = rb;
                     last_idx = idx;
                 }
-                int32_t xb, y0, pad;
-                if (!tma_place_in_image(c, ds, p.whole_width, p.whole_height, rb, idx, xb, y0, pad)) return kMultiDeclined;
-                c.m.xb = xb;  // overwrites c.data (union)
-                c.m.y0 = y0;
-                c.pad = pad;
-                c.pitch = g;
+                DevCropC& o = mt.c[z];
+                if (!tma_place_in_image(c, ds, p.whole_width, p.whole_height, rb, idx, o.xb, o.y0, o.pad)) return kMultiDeclined;
+                o.w = c.w;
+                o.h = c.h;
+                o.fx = c.fx;
+                o.fy = c.fy;
+                o.group = g;
             }
         }
         if (!restart) break;

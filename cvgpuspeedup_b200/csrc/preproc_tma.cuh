@@ -133,10 +133,20 @@ struct TmaNoTable {
 // Coalesced frame groups (cvgs_b200_preproc_launch_sequence_ex): the crops of up to kMultiGroups independent argument
 // sets -- each with its own parent frame and its own output tensor -- ride in ONE launch.  Descriptors in the kernel
 // parameters, tensor maps in the device-resident cache (TmaParams::maps, DevMapCache below).
-constexpr int kMultiCrops = 512;
+constexpr int kMultiCrops = 928;
 constexpr int kMultiGroups = 32;
+// Shared launches take the common geometry only (IGNORE_AR: the image band is the whole plane), so a crop needs 32 bytes
+// instead of DevCrop's 48 -- 928 crops (18 frames of 50) instead of 600 fit the 32 KB of kernel parameters.
+struct __align__(16) DevCropC {
+    int32_t xb, y0;   // where the ROI sits inside its tensor map (DevCrop::m)
+    int32_t w, h;     // source size in pixels
+    float fx, fy;     // src_conv_factors
+    int32_t pad;      // bits 0..15 staged row bytes, bits 16..31 index of the tensor map
+    int32_t group;    // index of the crop's argument set
+};
+static_assert(sizeof(DevCropC) == 32, "DevCropC layout");
 struct alignas(64) TmaMultiTable {
-    DevCrop c[kMultiCrops];          // DevCrop::pitch = index of the crop's group (the TMA kernel never reads the pitch)
+    DevCropC c[kMultiCrops];
     float* out_base[kMultiGroups];   // output tensor of group g
     int32_t z_first[kMultiGroups];   // launch-wide plane index of the group's first crop
 };
@@ -247,13 +257,32 @@ __device__ __forceinline__ float u16_scaled(uint32_t w, uint32_t k) {
     return __uint_as_float(__byte_perm(w, 0u, k ? 0x4324u : 0x4104u));
 }
 
+// (decltype(auto): a reference into the table, or -- shared launches -- the descriptor expanded from its compact form)
 template <typename Table>
-__device__ __forceinline__ const DevCrop& tma_crop_of(const TmaParams&, const Table& T, int z) {
-    return T.c[z];
+__device__ __forceinline__ decltype(auto) tma_crop_of(const TmaParams&, const Table& T, int z) {
+    return (T.c[z]);
 }
 template <>
-__device__ __forceinline__ const DevCrop& tma_crop_of<TmaNoTable>(const TmaParams& K, const TmaNoTable&, int z) {
-    return K.P.crops[z];
+__device__ __forceinline__ decltype(auto) tma_crop_of<TmaNoTable>(const TmaParams& K, const TmaNoTable&, int z) {
+    return (K.P.crops[z]);
+}
+template <>
+__device__ __forceinline__ decltype(auto) tma_crop_of<TmaMultiTable>(const TmaParams& K, const TmaMultiTable& T, int z) {
+    const DevCropC& s = T.c[z];
+    DevCrop d;
+    d.m.xb = s.xb;
+    d.m.y0 = s.y0;
+    d.w = s.w;
+    d.h = s.h;
+    d.pitch = s.group;
+    d.fx = s.fx;
+    d.fy = s.fy;
+    d.bx1 = 0;
+    d.by1 = 0;
+    d.bx2 = K.P.W - 1;
+    d.by2 = K.P.H - 1;
+    d.pad = s.pad;
+    return d;
 }
 template <typename Table>
 __device__ __forceinline__ const CUtensorMap* tma_map_of(const TmaParams&, const Table& T, const DevCrop& C) {
@@ -274,7 +303,7 @@ __device__ __forceinline__ float* tma_plane_base(const TmaParams& K, const Table
 }
 template <>
 __device__ __forceinline__ float* tma_plane_base<TmaMultiTable>(const TmaParams& K, const TmaMultiTable& T, int z) {
-    const int g = T.c[z].pitch;
+    const int g = T.c[z].group;
     return T.out_base[g] + (long long)(z - T.z_first[g]) * K.P.out.z_stride;
 }
 

@@ -346,7 +346,7 @@ int cvgs_b200_set_overlap(int enable);
 /* Frame loops (cvgs_b200_preproc_launch_sequence_ex) with overlap enabled: when the argument sets are provably
  * independent, carry the same pipeline apart from the output pointer, name their parent frames and have the common
  * geometry (CV_8UC3 sources, IGNORE_AR, every plane used, NCHW float output), consecutive steps SHARE kernel launches:
- * up to 512 crops of up to 32 argument sets per launch, each crop writing into its own set's tensor, one host thread,
+ * up to 928 crops of up to 32 argument sets per launch, each crop writing into its own set's tensor, one host thread,
  * the caller's stream.  A 50-crop frame is 7.5 MB of traffic (~1.5 us of HBM time), less than one kernel launch costs
  * the host and the GPU front end; ten frames per launch are bound by the GPU instead.  Results are identical.  Default
  * 1 (on; CVGS_B200_SEQ_COALESCE=0 turns it off at load time); 0 = one launch per step as before, driven by several
