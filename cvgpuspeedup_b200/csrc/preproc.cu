@@ -35,6 +35,7 @@
 #include "preproc_host.hpp"
 #include "preproc_direct.cuh"
 #include "preproc_tma.cuh"
+#include "preproc_yuv_tma.cuh"
 #include "preproc_warp.cuh"
 
 namespace cvgs {
@@ -415,6 +416,12 @@ static int prepare_image_maps(DevCrop* dc, const cvgs_parent_t* parents, int use
     return n_maps;
 }
 
+static int ring_reserve(struct Ring& r, size_t n, int device);
+// NV12 / NV21 frames through the TMA-staged kernel (preproc_yuv_tma.cuh).  taken = false: the batch is not of the
+// shape that kernel is built for and nothing was launched (the caller falls back to the direct-gather kernel).
+static int launch_yuv_tma(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_pipeline_t* pipe, const PreprocParams& P,
+                          int device, int sms, cudaStream_t stream, bool& taken);
+
 // Shared by the batch entry points and the host-buffer entry point.
 // replicas / n_replicas: cvgs_b200_preproc_launch_replicated -- the tensor is written at out and at every replicas[d].
 static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* parents, int n_planes, int used,
@@ -461,6 +468,12 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
     const int sms = sm_count_of(device);
 
     const bool planes_out = pipe->out_layout == CVGS_OUT_PLANES;  // needs a device table of destinations: ring path
+    if ((P.src_type == CVGS_NV12 || P.src_type == CVGS_NV21) && variant != 1 && n_replicas == 0) {
+        bool taken = false;
+        if (int rc = launch_yuv_tma(crops, n_planes, used, pipe, P, device, sms, stream, taken)) return rc;
+        if (taken) return CVGS_OK;
+        if (variant == 2) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel cannot take this input");
+    }
     if (n_replicas > 0) {
         const bool fast = !P.band_test && P.used == P.n_planes && P.out.px_stride == 1 && !planes_out && !P.out.u8;
         if (!fast || variant == 1 || n_replicas + 1 > kMaxDest)
@@ -639,6 +652,79 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
 // launch granularity; ten frames per launch are not.  Used by cvgs_b200_preproc_launch_sequence_ex.
 // ------------------------------------------------------------------------------------------------
 static thread_local DevMapCache t_dev_maps;
+
+static int launch_yuv_tma(const cvgs_crop_t* crops, int n_planes, int used, const cvgs_pipeline_t* pipe, const PreprocParams& P,
+                          int device, int sms, cudaStream_t stream, bool& taken) {
+    taken = false;
+    if (used != n_planes || used <= 0) return CVGS_OK;
+    Ring& r = t_ctx.ring;
+    if (int rc = ring_reserve(r, static_cast<size_t>(n_planes), device)) return rc;
+    const int slot = r.next;
+    std::vector<DevCrop> dc(static_cast<size_t>(used));
+    for (int i = 0; i < used; ++i)
+        if (int rc = fill_crop(crops[i], *pipe, i, dc[i])) return rc;
+    YuvParams K;
+    K.P = P;
+    if (!yuv_tma_plan(P, dc.data(), used, n_planes, sms, K.G)) return CVGS_OK;
+    DevMapCache& mc = t_dev_maps;
+    if (int rc = mc.reserve(device)) return rc;
+    if (r.pending[slot]) { CVGS_CUDA(cudaEventSynchronize(r.ev[slot])); r.pending[slot] = false; }
+    static_assert(sizeof(DevYuv) == sizeof(DevCrop), "the frame table lives in the ring's crop region");
+    DevYuv* hf = reinterpret_cast<DevYuv*>(r.crops_h(slot));
+    const int TWp = std::min(32 * K.G.NPB, P.W);
+    for (int attempt = 0;; ++attempt) {
+        const uint32_t gen = mc.generation;
+        bool restart = false;
+        for (int i = 0; i < used && !restart; ++i) {
+            const DevCrop& c = dc[i];
+            DevYuv& f = hf[i];
+            const uintptr_t luma = reinterpret_cast<uintptr_t>(c.data);
+            const uintptr_t chroma = luma + static_cast<uintptr_t>(c.pitch) * static_cast<uintptr_t>(c.h);
+            f.xbL = static_cast<int32_t>(luma & 15);
+            f.xbC = static_cast<int32_t>(chroma & 15);
+            f.w = c.w;
+            f.h = c.h;
+            f.fx = c.fx;
+            f.fy = c.fy;
+            f.rbL = yuv_rb_luma(TWp, c.fx);
+            f.rbC = yuv_rb_chroma(TWp, c.fx);
+            f.pad0 = f.pad1 = 0;
+            f.mapL = mc.get(luma, c.pitch, c.w, c.h, f.rbL);          // luma plane: w bytes x h rows
+            f.mapC = f.mapL < 0 ? -1 : mc.get(chroma, c.pitch, c.w, c.h / 2, f.rbC);  // chroma: w / 2 pairs of 2 bytes x h / 2 rows
+            if (f.mapL < 0 || f.mapC < 0) return CVGS_OK;  // the driver refused the geometry: direct-gather kernel
+            if (mc.generation != gen) restart = true;      // the table started over: indices handed out so far are void
+        }
+        if (!restart) break;
+        if (attempt > 0) return CVGS_OK;
+    }
+    if (int rc = mc.flush()) return rc;
+    // chain for interpolated values (2^33 folded into its first op), division constants
+    TmaParams tmp;
+    tmp.P = P;
+    tmp.G = K.G;
+    const int chain = scaled_program(P, tmp);
+    K.prog_img = tmp.prog_img;
+    std::memcpy(K.zh, tmp.zh, sizeof K.zh);
+    std::memcpy(K.zl, tmp.zl, sizeof K.zl);
+    K.G.explicit_prescale = tmp.G.explicit_prescale;
+    for (int i = 0; i < 9; ++i) K.m[i] = std::ldexp(P.yuv[i], 100);
+    K.yoff = std::ldexp(P.yuv[9], -133);
+    K.coff = std::ldexp(P.yuv[10], -133);
+    const uint32_t kU = P.src_type == CVGS_NV12 ? 0u : 1u;
+    K.selU1 = 0x4044u | kU << 8;
+    K.selV1 = 0x4044u | (kU ^ 1u) << 8;
+    K.maps = mc.d;
+    K.frames = reinterpret_cast<const DevYuv*>(r.crops_d(slot));
+    r.next = (r.next + 1) % Ring::kSlots;
+    CVGS_CUDA(cudaMemcpyAsync(r.crops_d(slot), hf, static_cast<size_t>(used) * sizeof(DevYuv), cudaMemcpyHostToDevice, stream));
+    overlap_forget(stream);
+    const int rc = chain == CH_FMA_DIV ? yuv_launch_instance<CH_FMA_DIV>(K, device, stream) : yuv_launch_instance<CH_GENERIC>(K, device, stream);
+    CVGS_CUDA(cudaEventRecord(r.ev[slot], stream));
+    r.pending[slot] = true;
+    taken = rc == CVGS_OK;
+    return rc;
+}
+
 struct MultiSet {
     const cvgs_crop_t* crops;
     const cvgs_parent_t* parents;

@@ -963,6 +963,52 @@ inline int rb_class(int rb, bool fine = false) {
     return 0;
 }
 
+// Second half of a launch plan, shared by the kernels built on the item / ring scheme: given the band width (G.NPB,
+// G.tiles_x, G.HP, G.items_per_crop, G.total_items) and the bytes of a staging slot (G.slot_bytes), choose the ring depth,
+// the CTAs per SM and the grid, and cut the items into per-warp ranges of equal cost.
+inline bool tma_plan_items(TmaGeom& G, int W, int n_planes, int sm_count, int items_per_warp, int grid_div, int max_resident) {
+    const int NPB = G.NPB, TW = 32 * G.NPB;
+    const long long total = G.total_items;
+    // ring depth: as deep as possible while kMaxResident CTAs stay resident per SM, but at least two slots
+    const int smem_sm = 227 * 1024;
+    // dynamic ring + static (tap tables, barriers) + the 1 KB the driver reserves per CTA
+    auto cta_bytes = [&](int slots) {
+        return kWarps * slots * G.slot_bytes + kRingPad + 128 + kWarps * 4 * kTapBlock * static_cast<int>(sizeof(RowTap)) + 256 + 1024;
+    };
+    int slots = kMaxSlots;
+    while (slots > 2 && smem_sm / cta_bytes(slots) < max_resident) --slots;
+    if (const char* e = std::getenv("CVGS_TMA_SLOTS")) {  // tuning override (tests / profiling)
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= kMaxSlots) slots = v;
+    }
+    if (cta_bytes(slots) > smem_sm) return false;
+    G.slots = slots;
+    G.resident = std::min(max_resident, smem_sm / cta_bytes(slots));
+    // Small launches: one item per warp spreads the work over the most SMs (shortest isolated launch); when
+    // consecutive launches overlap, several items per warp amortise the staging latency and leave CTA slots free
+    // for the next launch, which raises back-to-back throughput (items_per_warp > 1, cvgs_b200_set_overlap).
+    const long long warps_wanted = std::max<long long>(1, (total + items_per_warp - 1) / items_per_warp);
+    const long long ctas_wanted = (warps_wanted + kWarps - 1) / kWarps;
+    G.grid = static_cast<int32_t>(std::min<long long>(
+        ctas_wanted, std::max<long long>(1, static_cast<long long>(G.resident) * sm_count / std::max(1, grid_div))));
+    G.np_last = (std::min(TW, W - (G.tiles_x - 1) * TW) + 31) / 32;
+    const long long w_full = static_cast<long long>(G.tiles_x - 1) * G.HP * NPB;
+    const long long w_crop = w_full + static_cast<long long>(G.HP) * G.np_last;
+    const long long w_total = w_crop * n_planes;
+    if (w_total > 0x7fffffffLL) return false;
+    G.w_full = static_cast<int32_t>(w_full);
+    G.w_crop = static_cast<int32_t>(w_crop);
+    const long long n_warps = static_cast<long long>(G.grid) * kWarps;
+    G.share_q = static_cast<int32_t>(w_total / n_warps);
+    G.share_r = static_cast<int32_t>(w_total % n_warps);
+    G.d_w_crop = fast_div_make(static_cast<uint32_t>(G.w_crop));
+    G.d_NPB = fast_div_make(static_cast<uint32_t>(G.NPB));
+    G.d_np_last = fast_div_make(static_cast<uint32_t>(G.np_last));
+    G.d_items_per_crop = fast_div_make(static_cast<uint32_t>(G.items_per_crop));
+    G.d_HP = fast_div_make(static_cast<uint32_t>(G.HP));
+    return true;
+}
+
 // Can this launch take the TMA kernel, and with which geometry?  crops = host copies of the DevCrops.
 // grid_div > 1: the launch takes only 1/grid_div of the CTA slots of the device, so that consecutive launches of a
 // stream (chained by programmatic dependent launch) are co-resident and each one's ramp-up and tail overlap its neighbours.
@@ -1011,44 +1057,7 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
     G.explicit_prescale = 0;
     G.prescale = pb >= 6 ? kPreScale16 : kPreScale;
     G.pdl_wait = 1;
-    // ring depth: as deep as possible while kMaxResident CTAs stay resident per SM, but at least two slots
-    const int smem_sm = 227 * 1024;
-    // dynamic ring + static (tap tables, barriers) + the 1 KB the driver reserves per CTA
-    auto cta_bytes = [&](int slots) {
-        return kWarps * slots * G.slot_bytes + kRingPad + 128 + kWarps * 4 * kTapBlock * static_cast<int>(sizeof(RowTap)) + 256 + 1024;
-    };
-    int slots = kMaxSlots;
-    while (slots > 2 && smem_sm / cta_bytes(slots) < max_resident) --slots;
-    if (const char* e = std::getenv("CVGS_TMA_SLOTS")) {  // tuning override (tests / profiling)
-        const int v = std::atoi(e);
-        if (v >= 1 && v <= kMaxSlots) slots = v;
-    }
-    if (cta_bytes(slots) > smem_sm) return false;
-    G.slots = slots;
-    G.resident = std::min(max_resident, smem_sm / cta_bytes(slots));
-    // Small launches: one item per warp spreads the work over the most SMs (shortest isolated launch); when
-    // consecutive launches overlap, several items per warp amortise the staging latency and leave CTA slots free
-    // for the next launch, which raises back-to-back throughput (items_per_warp > 1, cvgs_b200_set_overlap).
-    const long long warps_wanted = std::max<long long>(1, (total + items_per_warp - 1) / items_per_warp);
-    const long long ctas_wanted = (warps_wanted + kWarps - 1) / kWarps;
-    G.grid = static_cast<int32_t>(std::min<long long>(
-        ctas_wanted, std::max<long long>(1, static_cast<long long>(G.resident) * sm_count / std::max(1, grid_div))));
-    G.np_last = (std::min(TW, P.W - (G.tiles_x - 1) * TW) + 31) / 32;
-    const long long w_full = static_cast<long long>(G.tiles_x - 1) * G.HP * NPB;
-    const long long w_crop = w_full + static_cast<long long>(G.HP) * G.np_last;
-    const long long w_total = w_crop * n_planes;
-    if (w_total > 0x7fffffffLL) return false;
-    G.w_full = static_cast<int32_t>(w_full);
-    G.w_crop = static_cast<int32_t>(w_crop);
-    const long long n_warps = static_cast<long long>(G.grid) * kWarps;
-    G.share_q = static_cast<int32_t>(w_total / n_warps);
-    G.share_r = static_cast<int32_t>(w_total % n_warps);
-    G.d_w_crop = fast_div_make(static_cast<uint32_t>(G.w_crop));
-    G.d_NPB = fast_div_make(static_cast<uint32_t>(G.NPB));
-    G.d_np_last = fast_div_make(static_cast<uint32_t>(G.np_last));
-    G.d_items_per_crop = fast_div_make(static_cast<uint32_t>(G.items_per_crop));
-    G.d_HP = fast_div_make(static_cast<uint32_t>(G.HP));
-    return true;
+    return tma_plan_items(G, P.W, n_planes, sm_count, items_per_warp, grid_div, max_resident);
 }
 
 // The gather kernels (direct, warp, CircularTensor) run the chain from the runtime program; an IEEE division there is

@@ -61,7 +61,9 @@ extern "C" {
  * of height/2 rows at data + pitch * height, read as fk::ReadYUV<fk::NV12> and converted per tap by
  * fk::ConvertYUVToRGB<NV12, range, primaries, false, float3> in front of the resize (reference
  * fkl/.../image_processing/color_conversion.cuh:235-362; tests/resize/test_fused_resize.cu:73-76,141-143).  A crop
- * of this type is a whole frame {Y plane, width, height, pitch}; the pipeline sees float RGB.  Direct-gather kernel. */
+ * of this type is a whole frame {Y plane, width, height, pitch}; the pipeline sees float RGB.  Batches of even-sized
+ * NV12 / NV21 frames in the common geometry (IGNORE_AR, every plane used, planar float tensor, pitch a multiple of 16)
+ * take the TMA-staged kernel (csrc/preproc_yuv_tma.cuh), everything else the direct-gather kernel. */
 #define CVGS_NV12 0x1001
 /* The other fk::PixelFormat readers the reference can instantiate (color_conversion.cuh:89-98,296-345), same contract:
  *   CVGS_NV21  as NV12 with the chroma bytes in V, U order

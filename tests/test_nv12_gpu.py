@@ -161,3 +161,47 @@ def test_random_yuv_frames_against_oracle(seed):
     p = util.make_pipeline(dsize, ops, out_ptr=want.ctypes.data, src_type=fmt, yuv_standard=standard, **kw)
     assert util.oracle_lib().oracle_preproc(crops_h, n, n, C.byref(p), 0) == 0
     util.assert_bit_equal(out.cpu().numpy(), want, f"seed {seed} fmt {fmt:#x} sizes {sizes} pitch {pitch} dsize {dsize} std {standard} ops {ops} {kw}")
+
+
+@pytest.mark.parametrize("src_type", [_abi.CVGS_NV12, _abi.CVGS_NV21])
+@pytest.mark.parametrize("standard", [0, 1, 2, 3])
+def test_tma_staged_kernel_takes_nv12_and_nv21(src_type, standard):
+    """Batches of even-sized NV12 / NV21 frames in the common geometry go through the TMA-staged kernel
+    (preproc_yuv_tma.cuh; forced: variant 2 fails instead of falling back): luma and chroma planes staged through their own
+    tensor maps, conversion of every tap in the scaled domain.  Up- and down-scales, frame bases at every 16-byte phase,
+    several destination sizes (one / several column bands, odd heights), the FMA-DIV chain, a generic chain and no chain;
+    against the oracle, and against the reference's own kernel for NV12."""
+    lib = _abi.load()
+    pitch = 512
+    sizes = [(320, 240), (322, 242), (160, 120), (64, 36), (2, 2), (500, 300), (96, 400)]
+    frames = [_frame(70 * standard + i, w, h, pitch) for i, (w, h) in enumerate(sizes)]
+    prev = lib.cvgs_b200_set_kernel_variant(2)
+    try:
+        for dsize, ops in [((64, 128), OPS), ((400, 300), OPS), ((33, 7), [("mul", (0.5, 0.25, 2.0)), ("add", (1.0, 2.0, 3.0))]),
+                           ((224, 225), [])]:
+            ours = _ours(frames, sizes, pitch, dsize, standard, ops, src_type=src_type)
+            orc = _oracle(frames, sizes, pitch, dsize, standard, ops, src_type=src_type)
+            util.assert_bit_equal(ours, orc, f"standard {standard} dsize {dsize}: TMA-staged kernel vs oracle")
+            if src_type == _abi.CVGS_NV12 and ops is OPS and gpu_util.fkref_lib(16) is not None:
+                for i, (f, (w, h)) in enumerate(zip(frames, sizes)):
+                    ref = gpu_util.run_fkref_nv12(f, w, h, dsize, standard, MUL, SUB, DIV)
+                    util.assert_bit_equal(ours[i], ref, f"standard {standard} dsize {dsize} frame {i}: vs reference kernel")
+        # frames at odd byte offsets of their buffer (plane bases at other 16-byte phases)
+        n = 5
+        big = torch.from_numpy(np.random.default_rng(5).integers(0, 256, size=(n * 400 * pitch + 64,), dtype=np.uint8)).cuda()
+        host = big.cpu().numpy()
+        crops, ocrops = (_abi.Crop * n)(), (_abi.Crop * n)()
+        for i in range(n):
+            off = i * 400 * pitch + 3 * i + 1
+            crops[i].data, crops[i].width, crops[i].height, crops[i].pitch = big.data_ptr() + off, 200, 120, pitch
+            ocrops[i].data, ocrops[i].width, ocrops[i].height, ocrops[i].pitch = host.ctypes.data + off, 200, 120, pitch
+        out = torch.full((n, 3, 60, 100), float("nan"), device="cuda")
+        want = np.full((n, 3, 60, 100), np.nan, dtype=np.float32)
+        p = util.make_pipeline((100, 60), OPS, out_ptr=out.data_ptr(), src_type=src_type, yuv_standard=standard)
+        po = util.make_pipeline((100, 60), OPS, out_ptr=want.ctypes.data, src_type=src_type, yuv_standard=standard)
+        _abi.check(lib.cvgs_b200_preproc_launch(crops, n, n, C.byref(p), None))
+        torch.cuda.synchronize()
+        assert util.oracle_lib().oracle_preproc(ocrops, n, n, C.byref(po), 0) == 0
+        util.assert_bit_equal(out.cpu().numpy(), want, "unaligned plane bases")
+    finally:
+        lib.cvgs_b200_set_kernel_variant(prev)
