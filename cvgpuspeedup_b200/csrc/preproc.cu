@@ -523,7 +523,8 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
                 return rc;
             }
             bool ok = true;
-            for (int i = 0; i < used && ok; ++i) ok = pb == 3 && tma_prepare_crop(tt.c[i], K.G, P.W, i, &tt.m[i]) == CVGS_OK;
+            // (one map per crop: the gray instantiation is not built for that table -- such batches take the direct kernel)
+            for (int i = 0; i < used && ok; ++i) ok = pb == 3 && chain != CH_GRAY && tma_prepare_crop(tt.c[i], K.G, P.W, i, &tt.m[i]) == CVGS_OK;
             const double t3 = now_us();
             if (ok) {
                 K.G.pdl_wait = overlap_needs_wait(stream, out_range(P), src) ? 1 : 0;

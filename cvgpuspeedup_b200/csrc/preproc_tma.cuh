@@ -331,7 +331,9 @@ __device__ __forceinline__ BandOrigin band_origin(const PreprocParams& P, const 
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-enum ChainKind : int { CH_GENERIC = 0, CH_FMA_DIV = 1 };
+// CH_GRAY: cvtColor<*2GRAY> first (registers -> one luminance, rounded to an integer like the reference's RGB2Gray<I, float>),
+// then any per-channel ops on that one value; one plane is stored.
+enum ChainKind : int { CH_GENERIC = 0, CH_FMA_DIV = 1, CH_GRAY = 2 };
 
 // x / d for both halves with 1/d = zh + zl (div_const.cpp): FMUL2 + FFMA2.
 __device__ __forceinline__ float2 div_by_const2(float2 x, float zh, float zl) {
@@ -818,6 +820,42 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                                     v[c] = __ffma2_rn(v[c], make_float2(ca[c], ca[c]), make_float2(cb[c], cb[c]));
                                     v[c] = div_by_const2(v[c], zh[c], zl[c]);
                                 }
+                            } else if (CHAIN == CH_GRAY) {
+                                // 0.299 x + 0.587 y + 0.114 z in the order the program names (cvgs_device.cuh: DOP_GRAY); the
+                                // 2^33 that undoes the tap / weight scaling is folded into the coefficients (exact)
+                                const int kind = K.prog_img.ops[0].kind;
+                                const int rx = (kind >> 8) & 3, ry = (kind >> 12) & 3, rz = (kind >> 16) & 3;
+                                auto pick = [&](int r) {
+                                    float2 t = v[0];
+#pragma unroll
+                                    for (int c = 1; c < NC; ++c) t = r == c ? v[c] : t;
+                                    return t;
+                                };
+                                const float2 x = pick(rx), y = pick(ry), z = pick(rz);
+                                constexpr float kx = 0.299f * kPreScale, ky = 0.587f * kPreScale, kz = 0.114f * kPreScale;
+                                float2 t;
+                                if ((kind >> 20) & 1) {  // CVGS_FP_SEPARATE: every product and sum rounded on its own
+                                    const float2 a = __fmul2_rn(x, make_float2(kx, kx)), b = __fmul2_rn(y, make_float2(ky, ky));
+                                    const float2 c2 = __fmul2_rn(z, make_float2(kz, kz));
+                                    t = make_float2(__fadd_rn(__fadd_rn(a.x, b.x), c2.x), __fadd_rn(__fadd_rn(a.y, b.y), c2.y));
+                                } else if ((kind >> 21) & 1) {
+                                    t = __ffma2_rn(z, make_float2(kz, kz), __ffma2_rn(x, make_float2(kx, kx), __fmul2_rn(y, make_float2(ky, ky))));
+                                } else {
+                                    t = __ffma2_rn(z, make_float2(kz, kz), __ffma2_rn(y, make_float2(ky, ky), __fmul2_rn(x, make_float2(kx, kx))));
+                                }
+                                float2 g = make_float2(static_cast<float>(__float2int_rn(t.x)), static_cast<float>(__float2int_rn(t.y)));
+                                for (int i = 1; i < K.prog_img.n_ops; ++i) {  // the ops behind the conversion, on the one channel
+                                    const DevOp& op = K.prog_img.ops[i];
+                                    const float a = op.a[0], b = op.b[0];
+                                    switch (op.kind) {
+                                        case DOP_FMA: g = __ffma2_rn(g, make_float2(a, a), make_float2(b, b)); break;
+                                        case DOP_MUL: g = __fmul2_rn(g, make_float2(a, a)); break;
+                                        case DOP_ADD: g = make_float2(__fadd_rn(g.x, a), __fadd_rn(g.y, a)); break;
+                                        case DOP_DIV: g = make_float2(__fdiv_rn(g.x, a), __fdiv_rn(g.y, a)); break;
+                                        default: break;
+                                    }
+                                }
+                                v[0] = g;
                             } else {
                                 if (G.explicit_prescale) {
 #pragma unroll
@@ -861,9 +899,9 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
 #endif
                             {
 #pragma unroll
-                            for (int c = 0; c < NC; ++c) st_cs_f32(sp[c] + q, v[c].x);
+                            for (int c = 0; c < (CHAIN == CH_GRAY ? 1 : NC); ++c) st_cs_f32(sp[c] + q, v[c].x);
 #pragma unroll
-                            for (int c = 0; c < NC; ++c) st_cs_f32_if(st1, tp[c] + q, v[c].y);
+                            for (int c = 0; c < (CHAIN == CH_GRAY ? 1 : NC); ++c) st_cs_f32_if(st1, tp[c] + q, v[c].y);
                             }
                         }
                     }
@@ -963,6 +1001,17 @@ inline int rb_class(int rb, bool fine = false) {
     return 0;
 }
 
+// cvtColor<*2GRAY> as the first op of the chain, in the geometry the CH_GRAY instantiation is built for: CV_8UC3 source,
+// float interpolation, common geometry, one float plane out.
+inline bool gray_program(const PreprocParams& P) {
+    const DevProgram& g = P.prog;
+    if (P.src_type != CVGS_8UC3 || !g.special || g.nc_out != 1 || g.nregs != 3 || g.round_u8 || g.n_ops < 1) return false;
+    if ((g.ops[0].kind & 0xff) != DOP_GRAY || g.dst_chan[0] != 0) return false;
+    for (int i = 1; i < g.n_ops; ++i)
+        if (g.ops[i].kind != DOP_FMA && g.ops[i].kind != DOP_MUL && g.ops[i].kind != DOP_ADD && g.ops[i].kind != DOP_DIV) return false;
+    return !P.band_test && P.used == P.n_planes && P.out.px_stride == 1 && !P.out.planes && !P.out.u8;
+}
+
 // Second half of a launch plan, shared by the kernels built on the item / ring scheme: given the band width (G.NPB,
 // G.tiles_x, G.HP, G.items_per_crop, G.total_items) and the bytes of a staging slot (G.slot_bytes), choose the ring depth,
 // the CTAs per SM and the grid, and cut the items into per-warp ranges of equal cost.
@@ -1022,7 +1071,7 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
     if (P.out.u8 && (pb != 3 || P.prog.nc_out != 3)) return false;
     // everything but CV_8UC3: built for the common geometry only (IGNORE_AR, every plane used, planar float tensors)
     if (pb != 3 && (P.band_test || P.used != P.n_planes || P.out.px_stride != 1 || P.out.planes || P.out.u8)) return false;
-    if (P.prog.special) return false;           // conversions that change the channel count: direct-gather kernel
+    if (P.prog.special && !gray_program(P)) return false;  // other conversions that change the channel count: direct-gather kernel
     if (P.out.row_stride != static_cast<long long>(P.W) * P.out.px_stride) return false;  // padded packed rows: direct-gather kernel
     float fx_max = 0.f;
     for (int i = 0; i < used; ++i) {
@@ -1132,6 +1181,10 @@ inline int scaled_program(const PreprocParams& P, TmaParams& K) {
 inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
     K.prog_img = P.prog;
     K.G.explicit_prescale = 1;
+    if (gray_program(P)) {  // the conversion's coefficients carry the 2^33
+        K.G.explicit_prescale = 0;
+        return CH_GRAY;
+    }
     if (P.prog.round_u8 || P.prog.n_ops == 0) return CH_GENERIC;
     auto moderate = [](float a) { return a == 0.f || (std::fabs(a) > 1e-20f && std::fabs(a) < 1e20f); };
     const int nc = P.nc;
@@ -1423,6 +1476,12 @@ inline int tma_launch_kernel(const TmaParams& K, const Table& T, int chain, int 
         } else {
             return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel: this pixel type is not built for this descriptor table");
         }
+    }
+    if (chain == CH_GRAY) {
+        if constexpr (std::is_same<Table, TmaMultiTable>::value || std::is_same<Table, TmaParamTable>::value)
+            return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel: gray conversion is not built for this descriptor table");
+        else
+            return tma_launch_instance<Table, CH_GRAY, false>(K, T, device, stream);
     }
     // packed 8-bit output of the common geometry (a plain cv::cuda::resize on CV_8UC3 is this): its own fast instantiation
     if (!P.band_test && P.used == P.n_planes && P.out.u8 && P.nc == 3 && !std::is_same<Table, TmaParamTable>::value) {

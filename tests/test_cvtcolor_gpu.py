@@ -148,3 +148,31 @@ def test_unused_planes_take_the_converted_default():
     assert got[2, :, 0, 0].tolist() == [119.0, 59.0, 19.0, 250.0]
     got0 = gpu_util.run_cvgs(img, [], (16, 12), [("gray", (0,))], n_planes=2, used=0, background=(100.0, 100.0, 100.0))
     assert got0.shape == (2, 1, 12, 16) and (got0 == 100.0).all()
+
+
+@pytest.mark.parametrize("n", [20, 100, 300])
+@pytest.mark.parametrize("ops", [
+    [("gray", (1,))],                                                            # RGB2GRAY
+    [("reorder", (2, 1, 0)), ("gray", (0,)), ("mul", (1 / 255.0,))],             # BGR2GRAY + scale
+    [("gray", (1,)), ("mul", (0.5,)), ("sub", (3.0,)), ("div", (7.0,))],         # RGB2GRAY + a whole chain on the one channel
+])
+def test_tma_staged_kernel_takes_gray_chains(n, ops):
+    """cvtColor<*2GRAY> first in the chain, one float plane out, crops with their parent frame named: the TMA-staged
+    kernel's CH_GRAY instantiation (forced: variant 2 fails instead of falling back), bit-equal to the oracle in both
+    floating-point contracts."""
+    import ctypes as C
+    lib = _abi.load()
+    w = util.workload_c2(seed=50 + n, n=n, frame=(960, 540), pitch=2880)
+    d_img = torch.from_numpy(w.image).cuda()
+    for kw in ({}, dict(fp_contract=_abi.FP_SEPARATE)):
+        out = torch.full((n, 1, 128, 64), float("nan"), device="cuda")
+        p = util.make_pipeline((64, 128), ops, out_ptr=out.data_ptr(), **kw)
+        crops = util.host_crops(w.image, w.rects, base_ptr=d_img.data_ptr())
+        par = util.host_parents(w.image, w.width, w.height, n, base_ptr=d_img.data_ptr())
+        prev = lib.cvgs_b200_set_kernel_variant(2)
+        try:
+            _abi.check(lib.cvgs_b200_preproc_launch_ex(crops, par, n, n, C.byref(p), None))
+        finally:
+            lib.cvgs_b200_set_kernel_variant(prev)
+        torch.cuda.synchronize()
+        util.assert_bit_equal(out.cpu().numpy(), util.run_oracle(w.image, w.rects, (64, 128), ops, **kw), f"gray chain {ops} {kw}")
