@@ -1041,6 +1041,10 @@ int cvgs_b200_debug_overlap_query(void* stream_key, uint64_t out_lo, uint64_t ou
     return overlap_needs_wait(static_cast<cudaStream_t>(stream_key), o, s) ? 1 : 0;
 }
 
+uint32_t cvgs_b200_debug_fast_div(uint32_t n, uint32_t d) {
+    return d ? fast_div(n, fast_div_make(d)) : 0u;
+}
+
 int cvgs_b200_debug_host_bytes(uint64_t* h2d, uint64_t* d2h, int reset) {
     if (h2d) *h2d = t_h2d_bytes;
     if (d2h) *d2h = t_d2h_bytes;

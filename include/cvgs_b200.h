@@ -362,6 +362,9 @@ int cvgs_b200_set_coalesce(int enable);
 int cvgs_b200_set_host_upload(int mode);
 /* Number of kernel launches issued by this library on the calling thread so far. */
 int64_t cvgs_b200_launch_count(void);
+/* Diagnostics (no device needed): n / d as the kernels' prologues compute it (multiply-shift by a launch constant,
+ * FastDiv in csrc/preproc_tma.cuh); exact for n < 2^31. */
+uint32_t cvgs_b200_debug_fast_div(uint32_t n, uint32_t d);
 /* Diagnostics: bytes the host-buffer entry points moved host -> device and device -> host on the calling thread so far
  * (uploads count whole tiles / rows as issued). */
 int cvgs_b200_debug_host_bytes(uint64_t* h2d, uint64_t* d2h, int reset);

@@ -141,3 +141,18 @@ def test_program_rejects_inconsistent_chains():
                     ([("gray", (2,))], {}), ([("reorder", (0, 0, 1))], {})]:
         with pytest.raises(_abi.CvgsError):
             _program(ops, **kw)
+
+
+def test_fast_division_by_launch_constants_is_exact():
+    """The warps' prologues divide item and cost indices (< 2^31) by the plan's constants with multiply-shift (FastDiv,
+    csrc/preproc_tma.cuh); the per-warp item ranges tile the launch only if that equals integer division."""
+    lib = _abi.load()
+    rng = np.random.default_rng(12)
+    divisors = [1, 2, 3, 4, 5, 7, 64, 112, 113, 224, 225, 1000, 57344, 65535, 65536, 2 ** 20 + 1, 2 ** 30, 2 ** 31 - 1]
+    divisors += [int(v) for v in rng.integers(1, 2 ** 31 - 1, size=60)] + [int(v) for v in rng.integers(1, 5000, size=60)]
+    for d in divisors:
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 2 ** 31 - 1, (2 ** 31 - 1) // d * d, max(0, (2 ** 31 - 1) // d * d - 1)]
+        ns += [int(v) for v in rng.integers(0, 2 ** 31 - 1, size=200)]
+        for n in ns:
+            if 0 <= n < 2 ** 31:
+                assert lib.cvgs_b200_debug_fast_div(n, d) == n // d, (n, d)
