@@ -232,11 +232,14 @@ __device__ __forceinline__ void st_cs_f32x4(float* p, float a, float b, float c,
                  : "memory");
 }
 // predicated store (no branch: keeps the surrounding code in one basic block)
+#ifndef CVGS_ST_F32  // diagnostic builds try other cache policies (scripts/diag_build.sh)
+#define CVGS_ST_F32 "st.global.cs.f32"
+#endif
 __device__ __forceinline__ void st_cs_f32_if(bool pred, float* p, float a) {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.global.cs.f32 [%1], %2;\n}" ::"r"((unsigned)pred), "l"(p), "f"(a) : "memory");
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q " CVGS_ST_F32 " [%1], %2;\n}" ::"r"((unsigned)pred), "l"(p), "f"(a) : "memory");
 }
 __device__ __forceinline__ void st_cs_f32(float* p, float a) {
-    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+    asm volatile(CVGS_ST_F32 " [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
 // Store NPIX x-adjacent pixels (first one at column x) of row y, plane z.

@@ -8,5 +8,6 @@ SRCS="csrc/preproc.cu csrc/circular_tensor.cu csrc/selftest.cu csrc/div_const.o"
 mkdir -p ../gpurun_out
 nvcc $FLAGS -DCVGS_DIAG_SKIP_STORES -o /tmp/libcvgs_diag_nostore.so $SRCS &
 nvcc $FLAGS -DCVGS_DIAG_SKIP_LOADS -o /tmp/libcvgs_diag_noload.so $SRCS &
+# other cache policies of the output stores: add e.g.  nvcc $FLAGS '-DCVGS_ST_F32="st.global.cg.f32"' -o diag/lib_st_cg.so $SRCS
 wait
 mkdir -p diag && cp /tmp/libcvgs_diag_nostore.so /tmp/libcvgs_diag_noload.so diag/
