@@ -1038,8 +1038,12 @@ inline bool tma_plan_items(TmaGeom& G, int W, int n_planes, int sm_count, int it
     // for the next launch, which raises back-to-back throughput (items_per_warp > 1, cvgs_b200_set_overlap).
     const long long warps_wanted = std::max<long long>(1, (total + items_per_warp - 1) / items_per_warp);
     const long long ctas_wanted = (warps_wanted + kWarps - 1) / kWarps;
+    static const int grid_mult = [] {  // tuning override (profiling): more CTAs than fit at once (waves instead of persistence)
+        const char* e = std::getenv("CVGS_TMA_GRID_MULT");
+        return e ? std::max(1, std::atoi(e)) : 1;
+    }();
     G.grid = static_cast<int32_t>(std::min<long long>(
-        ctas_wanted, std::max<long long>(1, static_cast<long long>(G.resident) * sm_count / std::max(1, grid_div))));
+        ctas_wanted, std::max<long long>(1, static_cast<long long>(G.resident) * sm_count * grid_mult / std::max(1, grid_div))));
     G.np_last = (std::min(TW, W - (G.tiles_x - 1) * TW) + 31) / 32;
     const long long w_full = static_cast<long long>(G.tiles_x - 1) * G.HP * NPB;
     const long long w_crop = w_full + static_cast<long long>(G.HP) * G.np_last;
