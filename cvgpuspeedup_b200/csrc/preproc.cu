@@ -63,10 +63,13 @@ static std::atomic<int> g_coalesce{[] {
     const char* e = std::getenv("CVGS_B200_SEQ_COALESCE");
     return e && e[0] == '0' ? 0 : 1;
 }()};
+// 0 off; 1 = inside the library's own frame loops, where it controls the whole stream segment; 2 = also between
+// individual launches (the caller asserts that nothing it enqueues between two launches of the library produces a source)
 static std::atomic<int> g_overlap{[] {
     const char* e = std::getenv("CVGS_B200_OVERLAP");
-    return e && e[0] == '1' ? 1 : 0;
+    return e && e[0] == '1' ? 1 : (e && e[0] == '2' ? 2 : 0);
 }()};
+static thread_local bool t_in_frame_loop = false;  // set by the multi-threaded frame loop around the launches it issues
 
 // ------------------------------------------------------------------------------------------------
 // Overlap of consecutive launches (cvgs_b200_set_overlap).  The TMA kernel is launched with programmatic stream
@@ -102,12 +105,16 @@ static int items_per_warp() {
     }();
     if (forced) return forced;
     if (t_items_hint) return t_items_hint;
-    return g_overlap.load(std::memory_order_relaxed) ? 4 : 1;
+    return g_overlap.load(std::memory_order_relaxed) == 2 ? 4 : 1;
 }
 
 // true: this launch must wait for the preceding kernel up front.
 static bool overlap_needs_wait(cudaStream_t stream, const MemRange& out, const MemRange& src) {
-    if (!g_overlap.load(std::memory_order_relaxed)) return true;
+    const int mode = g_overlap.load(std::memory_order_relaxed);
+    // Between individual launches the library cannot see what else the caller enqueued (a foreign kernel that produces
+    // the next source would be ordered only by the implicit trigger at its exit, which guarantees nothing about the
+    // visibility of its writes without a griddepcontrol.wait): the early wait is dropped there only on the caller's word.
+    if (mode == 0 || (mode == 1 && !t_in_frame_loop)) return true;
     std::lock_guard<std::mutex> lock(g_track_mu);
     StreamTrack* t = nullptr;
     for (auto& k : g_tracks)
@@ -971,7 +978,7 @@ extern "C" {
 int cvgs_b200_version(void) { return CVGS_B200_VERSION; }
 const char* cvgs_b200_last_error(void) { return t_last_error.c_str(); }
 int cvgs_b200_set_kernel_variant(int variant) { return g_variant.exchange(variant); }
-int cvgs_b200_set_overlap(int enable) { return g_overlap.exchange(enable ? 1 : 0); }
+int cvgs_b200_set_overlap(int mode) { return g_overlap.exchange(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); }
 int cvgs_b200_set_coalesce(int enable) { return g_coalesce.exchange(enable ? 1 : 0); }
 int cvgs_b200_set_host_upload(int mode) { return g_host_tiles.exchange(mode ? 1 : 0); }
 int64_t cvgs_b200_launch_count(void) { return t_launch_count; }
@@ -1523,11 +1530,21 @@ int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const 
     std::unique_lock<std::mutex> seq_lock(g_seq_mu, std::defer_lock);
     if (workers > 1 && !seq_lock.try_lock()) workers = 1;
     if (workers <= 1) {
-        for (int i = 0; i < steps; ++i) {
+        // one thread, the caller's stream: still a segment the library controls from its first launch to its last
+        // (the first launch waits up front: what precedes the loop is unknown)
+        overlap_forget(stream);
+        const bool may_overlap = g_overlap.load(std::memory_order_relaxed) != 0;
+        t_in_frame_loop = may_overlap;
+        if (may_overlap) t_items_hint = 4;  // fewer, longer-lived CTAs per launch leave room for the next launch (see items_per_warp)
+        int rc = CVGS_OK;
+        for (int i = 0; i < steps && rc == CVGS_OK; ++i) {
             const int s = i % n_sets;
-            if (int rc = cvgs_b200_preproc_launch_ex(crops[s], parents[s], n_planes[s], used[s], pipelines[s], stream)) return rc;
+            rc = cvgs_b200_preproc_launch_ex(crops[s], parents[s], n_planes[s], used[s], pipelines[s], stream);
         }
-        return CVGS_OK;
+        t_in_frame_loop = false;
+        t_items_hint = 0;
+        overlap_forget(stream);
+        return rc;
     }
 
     int device = 0;
@@ -1553,6 +1570,7 @@ int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const 
     Result res[kSeqMaxWorkers];
     auto run = [&](int w, cudaStream_t st) {
         t_items_hint = 8;
+        t_in_frame_loop = true;  // the loop owns its streams between fork and join: consecutive launches may overlap
         int rc = CVGS_OK;
         for (int i = 0; i < steps && rc == CVGS_OK; ++i) {
             const int s = i % n_sets;
@@ -1560,6 +1578,7 @@ int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const 
             rc = cvgs_b200_preproc_launch_ex(crops[s], parents[s], n_planes[s], used[s], pipelines[s], st);
         }
         t_items_hint = 0;
+        t_in_frame_loop = false;
         return rc;
     };
     seq_pool()->run(

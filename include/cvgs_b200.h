@@ -334,17 +334,21 @@ int cvgs_b200_preproc_host_sequence(const void* const* host_images, int32_t imag
 /* Kernel-selection override, for tests and profiling: 0 = automatic, 1 = direct-gather kernel,
  * 2 = TMA-staged kernel.  Returns the previous value. */
 int cvgs_b200_set_kernel_variant(int variant);
-/* Overlap of consecutive launches on one stream (default 0 = off; the environment variable CVGS_B200_OVERLAP=1
- * turns it on at load time).  The fused kernel is always launched with programmatic stream serialisation and, by
- * default, waits for the preceding kernel of the stream before its first global-memory access: plain stream order.
- * With overlap enabled the library drops that early wait for a launch whose source images and output tensor are
- * disjoint from the outputs (and whose output is disjoint from the sources) of its own recent launches on that
- * stream, so that back-to-back frames overlap instead of paying one launch latency each; every kernel still
- * waits for its predecessor before it completes, so later stream operations observe the usual order.
- * Requirement on the caller: kernels of other libraries that trigger programmatic launch completion early
- * (cudaTriggerProgrammaticLaunchCompletion) must not be the direct producers of a source image.  The reference
- * has no equivalent (it launches plain kernels, executors.cuh:133-156).  Returns the previous value. */
-int cvgs_b200_set_overlap(int enable);
+/* Overlap of consecutive launches (default 0 = off; the environment variable CVGS_B200_OVERLAP=1 / 2 selects a mode at
+ * load time).  The fused kernel is always launched with programmatic stream serialisation and, by default, waits for the
+ * preceding kernel of the stream before its first global-memory access: plain stream order.
+ *   mode 1  inside the library's own frame loops (cvgs_b200_preproc_launch_sequence_ex), where the library controls the
+ *           whole stream segment: independent frames share launches (cvgs_b200_set_coalesce) or are driven from several
+ *           host threads, and consecutive launches drop the early wait when the library proves them independent (their
+ *           sources and outputs disjoint from the outputs -- and their outputs from the sources -- of the launches
+ *           possibly still in flight).  Individual launches keep plain stream order.
+ *   mode 2  additionally between individual launches of one stream (cvgs_b200_preproc_launch[_ex]), tracked per stream
+ *           over the library's own last 8 launches.  The CALLER asserts that nothing it enqueues between two launches of
+ *           the library produces a source image of the later one: the library cannot see foreign kernels, and a kernel
+ *           that is ordered only by the implicit completion trigger of its predecessor is not guaranteed to see its writes.
+ * Every kernel still waits for its predecessor before it completes, so later stream operations observe the usual order.
+ * The reference has no equivalent (it launches plain kernels, executors.cuh:133-156).  Returns the previous mode. */
+int cvgs_b200_set_overlap(int mode);
 /* Frame loops (cvgs_b200_preproc_launch_sequence_ex) with overlap enabled: when the argument sets are provably
  * independent, carry the same pipeline apart from the output pointer, name their parent frames and have the common
  * geometry (CV_8UC3 sources, IGNORE_AR, every plane used, NCHW float output), consecutive steps SHARE kernel launches:

@@ -67,6 +67,8 @@ def test_overlap_bookkeeping():
     try:
         assert q(0x10, (0, 100), (1000, 2000)) == 1                      # overlap off: always plain stream order
         lib.cvgs_b200_set_overlap(1)
+        assert q(0x20, (0, 100), (1000, 2000)) == 1 and q(0x20, (100, 200), (1000, 2000)) == 1  # mode 1: individual launches keep stream order
+        lib.cvgs_b200_set_overlap(2)                                     # mode 2: the caller vouches for what sits between launches
         key = 0x7770
         assert q(key, (0, 100), (1000, 2000)) == 1                       # first launch seen on a stream: unknown past
         assert q(key, (100, 200), (1000, 2000)) == 0                     # disjoint output, same source: independent

@@ -1,4 +1,4 @@
-"""cvgs_b200_set_overlap(1): consecutive launches may overlap when the library proves them independent.  Stream
+"""cvgs_b200_set_overlap(1 / 2): consecutive launches may overlap when the library proves them independent.  Stream
 semantics must be unchanged: hazards between launches (same output, output used as a source) are ordered, and
 whatever follows on the stream sees every earlier launch complete."""
 import ctypes as C
@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture()
 def overlap_on():
     lib = _abi.load()
-    prev = lib.cvgs_b200_set_overlap(1)
+    prev = lib.cvgs_b200_set_overlap(2)  # mode 2: individual launches may overlap too (the tests enqueue nothing foreign in between)
     yield lib
     lib.cvgs_b200_set_overlap(prev)
 
@@ -109,7 +109,7 @@ def test_later_stream_work_sees_every_launch_complete(overlap_on):
         del k1, k2
 
 
-@pytest.mark.parametrize("overlap", [0, 1])
+@pytest.mark.parametrize("overlap", [0, 1, 2])
 def test_launches_are_graph_capturable(overlap):
     """Batches whose descriptors ride in the kernel parameters involve no copy and no allocation on the hot call, so a
     frame loop can be captured into a CUDA graph and replayed (graph replay figure for config 2)."""
@@ -141,7 +141,7 @@ def test_concurrent_host_threads():
     contexts (descriptor ring, tensor-map cache, memos) and the shared bookkeeping must not interfere."""
     import threading
     lib = _abi.load()
-    prev = lib.cvgs_b200_set_overlap(1)
+    prev = lib.cvgs_b200_set_overlap(2)
     errors = []
 
     def worker(k):
