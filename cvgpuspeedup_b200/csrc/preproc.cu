@@ -1155,6 +1155,30 @@ int cvgs_b200_ipc_close(void* ptr) {
     return CVGS_OK;
 }
 
+// Perspective: the denominator m6 x + m7 y + m8 is linear in the destination pixel, so over the (padded) destination
+// rectangle its extremes sit at the corners.  True when every float denominator the kernel computes is finite, of one sign
+// and of magnitude in [2^-100, 2^100] -- the range where the correctly rounded reciprocal needs no special cases (the fast
+// kernel then skips the range check of __frcp_rn).  The float evaluation FADD(FFMA(m6, x, FMUL(m7, y)), m8) is within
+// 3 * 2^-24 * S of the exact value, S = |m6| xmax + |m7| ymax + |m8|; the margin below is 2^-20 * S.
+static bool warp_denominators_normal(const float* m, int w_padded, int h) {
+    const double a = m[6], b = m[7], c = m[8];
+    if (!std::isfinite(a) || !std::isfinite(b) || !std::isfinite(c)) return false;
+    const double xs[2] = {0.0, static_cast<double>(w_padded - 1)}, ys[2] = {0.0, static_cast<double>(h - 1)};
+    const double S = std::fabs(a) * xs[1] + std::fabs(b) * ys[1] + std::fabs(c);
+    double lo = INFINITY, hi = 0.0;
+    int sign = 0;
+    for (double x : xs)
+        for (double y : ys) {
+            const double e = a * x + b * y + c;  // exact enough: doubles carry 53 bits, the products of floats and ints < 2^24 are exact
+            const int sg = e > 0 ? 1 : (e < 0 ? -1 : 0);
+            if (sg == 0 || (sign != 0 && sg != sign)) return false;
+            sign = sg;
+            lo = std::min(lo, std::fabs(e));
+            hi = std::max(hi, std::fabs(e));
+        }
+    return lo >= S * 9.5367431640625e-07 && lo >= 7.888609052210118e-31 && hi <= 1.2676506002282294e+30;
+}
+
 // Batched warp: descriptors ride in the kernel parameters, kWarpParamPlanes planes per launch.
 static int warp_launch_impl(const cvgs_crop_t* images, const cvgs_warp_t* warps, int n_planes, int used,
                             const cvgs_pipeline_t* pipe, cudaStream_t stream) {
@@ -1204,6 +1228,39 @@ static int warp_launch_impl(const cvgs_crop_t* images, const cvgs_warp_t* warps,
         CVGS_CUDA(cudaEventRecord(r.ev[slot], stream));  // re-recorded after the kernels below
         r.pending[slot] = true;
     }
+    // fast instantiation (preproc_warp.cuh): float tensor rows, chain = [MUL | FMA | ADD] [two-operation DIV]
+    WarpFastParams F{};
+    int fast = 0;  // 1: linear chain, 2: linear chain + division
+    {
+        const DevProgram& g = P.prog;
+        const bool lin0 = g.n_ops >= 1 && (g.ops[0].kind == DOP_MUL || g.ops[0].kind == DOP_FMA || g.ops[0].kind == DOP_ADD);
+        const bool shape = g.n_ops == 0 || (g.n_ops == 1 && (lin0 || g.ops[0].kind == DOP_DIVC)) ||
+                           (g.n_ops == 2 && lin0 && g.ops[1].kind == DOP_DIVC);
+        bool ok = shape && !g.round_u8 && !P.out.u8 && !P.out.planes && P.out.px_stride == 1 && g_variant.load(std::memory_order_relaxed) != 1;  // variant 1: the general kernel (tests)
+        // offsets inside a destination plane are 32-bit in the kernel
+        ok = ok && std::llabs(P.out.row_stride) * P.H + P.W < 0x1fffffffLL;
+        for (int c = 0; c < P.nc && ok; ++c) ok = std::llabs(P.out.c_off[c]) < (1LL << 40);
+        for (int i = 0; i < used && ok; ++i)  // float(width), float(height) exact
+            ok = images[i].width <= (1 << 24) && images[i].height <= (1 << 24);
+        if (ok) {
+            const bool has_div = g.n_ops > 0 && g.ops[g.n_ops - 1].kind == DOP_DIVC;
+            fast = has_div ? 2 : 1;
+            for (int c = 0; c < 4; ++c) {
+                F.a[c] = lin0 && g.ops[0].kind != DOP_ADD ? g.ops[0].a[c] : 1.0f;  // MUL(a) == FMA(a, -0), ADD(b) == FMA(1, b)
+                F.b[c] = !lin0 || g.ops[0].kind == DOP_MUL ? -0.0f : (g.ops[0].kind == DOP_ADD ? g.ops[0].a[c] : g.ops[0].b[c]);
+                F.zh[c] = has_div ? g.ops[g.n_ops - 1].a[c] : 1.0f;
+                F.zl[c] = has_div ? g.ops[g.n_ops - 1].b[c] : 0.0f;
+                F.bg[c] = P.bg[c];
+                F.c_off[c] = c < P.nc ? P.out.c_off[c] : 0;
+            }
+            F.W = P.W;
+            F.H = P.H;
+            F.used = used;
+            F.base = P.out.base;
+            F.z_stride = P.out.z_stride;
+            F.row_stride = P.out.row_stride;
+        }
+    }
     const dim3 block(256);
     for (int z0 = 0; z0 < n_planes; z0 += kWarpParamPlanes) {
         const int nz = std::min(kWarpParamPlanes, n_planes - z0);
@@ -1217,10 +1274,32 @@ static int warp_launch_impl(const cvgs_crop_t* images, const cvgs_warp_t* warps,
             d.pitch = c.pitch;
             d.type = warps[z0 + i].type;
             std::memcpy(d.m, warps[z0 + i].m, sizeof d.m);
-            d.pad = 0;
+            d.pad = d.type == CVGS_WARP_AFFINE ? WM_AFFINE : warp_denominators_normal(d.m, (P.W + 127) / 128 * 128, P.H) ? WM_PERSPECTIVE_NORMAL : WM_PERSPECTIVE;
         }
         // four pixels per thread measured best from 640x640 planes up and within 10% below (1, 2 and 4 tried on B200)
         const dim3 grid((P.W + 127) / 128, (P.H + 7) / 8, nz);
+        if (fast) {
+            // two rows per warp halve the per-thread set-up per pixel; worth it once the launch still fills the GPU several times
+            const long long ctas1 = static_cast<long long>(grid.x) * grid.y * nz;
+            F.rows = ctas1 >= 8LL * 5 * sm_count_of(device) ? 2 : 1;
+            if (const char* e = std::getenv("CVGS_WARP_ROWS")) F.rows = std::max(1, std::atoi(e));  // tuning override (profiling)
+            const dim3 grid(((P.W + 127) / 128), (P.H + 8 * F.rows - 1) / (8 * F.rows), nz);
+#define CVGS_WARP_FAST(T_, NC_)                                                                         \
+    if (fast == 2) preproc_warp_fast_kernel<T_, NC_, true><<<grid, block, 0, stream>>>(F, T, z0);       \
+    else preproc_warp_fast_kernel<T_, NC_, false><<<grid, block, 0, stream>>>(F, T, z0)
+            switch (pipe->src_type) {
+                case CVGS_8UC3: CVGS_WARP_FAST(unsigned char, 3); break;
+                case CVGS_8UC4: CVGS_WARP_FAST(unsigned char, 4); break;
+                case CVGS_16UC3: CVGS_WARP_FAST(unsigned short, 3); break;
+                case CVGS_16UC4: CVGS_WARP_FAST(unsigned short, 4); break;
+                case CVGS_16SC3: CVGS_WARP_FAST(short, 3); break;
+                default: CVGS_WARP_FAST(short, 4); break;
+            }
+#undef CVGS_WARP_FAST
+            CVGS_CUDA(cudaGetLastError());
+            ++t_launch_count;
+            continue;
+        }
         switch (pipe->src_type) {
             case CVGS_8UC3: preproc_warp_kernel<4, unsigned char, 3><<<grid, block, 0, stream>>>(P, T, z0); break;
             case CVGS_8UC4: preproc_warp_kernel<4, unsigned char, 4><<<grid, block, 0, stream>>>(P, T, z0); break;

@@ -56,6 +56,9 @@ def timed(pipe, label):
 
 timed(p, "mul, sub, div, split")
 us = timed(util.make_pipeline((W, H), ops[:1], out_ptr=out.data_ptr()), "mul, split")
+prev = lib.cvgs_b200_set_kernel_variant(1)
+timed(p, "general kernel: mul, sub, div, split")
+lib.cvgs_b200_set_kernel_variant(prev)
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libfkref_16.so")
 if os.path.exists(path):
     ref = C.CDLL(path)

@@ -258,6 +258,14 @@ def test_wild_matrices_against_oracle(seed):
     ours = _launch([d] * n, [(w, h)] * n, pitch, inverses, warp_type, dsize, ops)
     orc = _oracle([img] * n, [(w, h)] * n, pitch, inverses, warp_type, dsize, ops)
     util.assert_bit_equal(ours, orc, f"seed {seed} type {warp_type} image {w}x{h} dsize {dsize}")
+    # the same launch through the general kernel (variant 1 keeps the chain interpreter and four pixels per lane)
+    lib = _abi.load()
+    prev = lib.cvgs_b200_set_kernel_variant(1)
+    try:
+        general = _launch([d] * n, [(w, h)] * n, pitch, inverses, warp_type, dsize, ops)
+    finally:
+        lib.cvgs_b200_set_kernel_variant(prev)
+    util.assert_bit_equal(general, orc, f"general kernel, seed {seed}")
 
 
 TYPED = [_abi.CVGS_8UC4, _abi.CVGS_16UC3, _abi.CVGS_16SC4]
@@ -347,3 +355,38 @@ def test_warp_into_per_plane_images(src_type):
     for z in range(n):
         for c in range(nc):
             util.assert_bit_equal(planes[z * nc + c][:, :W].cpu().numpy(), want[z, c], f"plane {z} channel {c}")
+
+
+@pytest.mark.parametrize("src_type", [_abi.CVGS_8UC3, _abi.CVGS_8UC4, _abi.CVGS_16UC3, _abi.CVGS_16UC4, _abi.CVGS_16SC3, _abi.CVGS_16SC4])
+def test_fast_and_general_warp_kernels_agree(src_type):
+    """Chains of the shape [MUL | FMA | ADD] [DIV] with a float tensor behind them take the instantiation without the
+    chain interpreter (lane-strided pixels); everything else, and kernel variant 1, the general kernel.  Both against the
+    oracle: ragged widths (tail groups of a 128-pixel span), unused planes, every chain shape, strided planes, pixels
+    outside the source."""
+    nc = util.channels_of(src_type)
+    px = util.px_bytes_of(src_type)
+    rng = np.random.default_rng(4100 + src_type)
+    w, h = 150, 90
+    pitch = px * w + 10 * (px // nc)
+    img = rng.integers(0, 256, size=(h, pitch), dtype=np.uint8)
+    d = gpu_util.device_image(img)
+    n = 6
+    lib = _abi.load()
+    chains = [[], [("mul", (0.5, 0.25, 2.0, 1.5)[:nc])], [("add", (1.0, -2.0, 3.0, 0.5)[:nc])], [("div", (3.2, 0.6, 11.8, 2.0)[:nc])],
+              [("mul", (0.3,) * nc), ("sub", (1.0, 4.0, 3.2, 0.5)[:nc]), ("div", (3.2, 0.6, 11.8, 2.0)[:nc])],
+              [("reorder", (2, 1, 0, 3)[:nc]), ("sub", (1.0, 4.0, 3.2, 0.5)[:nc]), ("div", (3.0, 7.0, 0.1, 2.5)[:nc])],
+              [("div", (3.2, 0.6, 11.8, 2.0)[:nc]), ("mul", (0.3,) * nc)]]  # not the canonical shape: general kernel
+    for k, ops in enumerate(chains):
+        for warp_type in (cvgs.WARP_AFFINE, cvgs.WARP_PERSPECTIVE):
+            dsize = [(131, 37), (128, 8), (33, 9), (257, 3)][k % 4]
+            inverses = [cvgs.api.invert_warp_matrix(m, warp_type) for m in _matrices(rng, n, warp_type, w, h)]
+            inverses[1] = np.array([1.5, 0.2, -40.0, -0.1, 1.2, -20.0, 0.0, 0.0, 1.0], dtype=np.float32)  # partly outside
+            kw = dict(n_planes=n + 2, used=n, background=(7.0, 3.5, 250.0, 1.0)[:nc], src_type=src_type)
+            orc = _oracle([img] * n, [(w, h)] * n, pitch, inverses, warp_type, dsize, ops, **kw)
+            for variant in (0, 1):
+                prev = lib.cvgs_b200_set_kernel_variant(variant)
+                try:
+                    got = _launch([d] * n, [(w, h)] * n, pitch, inverses, warp_type, dsize, ops, **kw)
+                finally:
+                    lib.cvgs_b200_set_kernel_variant(prev)
+                util.assert_bit_equal(got, orc, f"src {src_type} chain {k} type {warp_type} variant {variant}")
