@@ -475,7 +475,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
     const int sms = sm_count_of(device);
 
     const bool planes_out = pipe->out_layout == CVGS_OUT_PLANES;  // needs a device table of destinations: ring path
-    if ((P.src_type == CVGS_NV12 || P.src_type == CVGS_NV21) && variant != 1 && n_replicas == 0) {
+    if ((P.src_type == CVGS_NV12 || P.src_type == CVGS_NV21 || P.src_type == CVGS_P010 || P.src_type == CVGS_P210) && variant != 1 && n_replicas == 0) {
         bool taken = false;
         if (int rc = launch_yuv_tma(crops, n_planes, used, pipe, P, device, sms, stream, taken)) return rc;
         if (taken) return CVGS_OK;
@@ -680,6 +680,8 @@ static int launch_yuv_tma(const cvgs_crop_t* crops, int n_planes, int used, cons
     static_assert(sizeof(DevYuv) == sizeof(DevCrop), "the frame table lives in the ring's crop region");
     DevYuv* hf = reinterpret_cast<DevYuv*>(r.crops_h(slot));
     const int TWp = std::min(32 * K.G.NPB, P.W);
+    const int depth = yuv_depth_of(P.src_type);
+    const int csh = P.src_type == CVGS_P210 ? 0 : 1;
     for (int attempt = 0;; ++attempt) {
         const uint32_t gen = mc.generation;
         bool restart = false;
@@ -694,11 +696,11 @@ static int launch_yuv_tma(const cvgs_crop_t* crops, int n_planes, int used, cons
             f.h = c.h;
             f.fx = c.fx;
             f.fy = c.fy;
-            f.rbL = yuv_rb_luma(TWp, c.fx);
-            f.rbC = yuv_rb_chroma(TWp, c.fx);
+            f.rbL = yuv_rb_luma(TWp, c.fx, depth);
+            f.rbC = yuv_rb_chroma(TWp, c.fx, depth);
             f.pad0 = f.pad1 = 0;
-            f.mapL = mc.get(luma, c.pitch, c.w, c.h, f.rbL);          // luma plane: w bytes x h rows
-            f.mapC = f.mapL < 0 ? -1 : mc.get(chroma, c.pitch, c.w, c.h / 2, f.rbC);  // chroma: w / 2 pairs of 2 bytes x h / 2 rows
+            f.mapL = mc.get(luma, c.pitch, depth * c.w, c.h, f.rbL);          // luma plane: w samples x h rows
+            f.mapC = f.mapL < 0 ? -1 : mc.get(chroma, c.pitch, depth * c.w, c.h >> csh, f.rbC);  // chroma: w / 2 pairs x h / 2 (4:2:0) or h rows
             if (f.mapL < 0 || f.mapC < 0) return CVGS_OK;  // the driver refused the geometry: direct-gather kernel
             if (mc.generation != gen) restart = true;      // the table started over: indices handed out so far are void
         }
@@ -715,18 +717,28 @@ static int launch_yuv_tma(const cvgs_crop_t* crops, int n_planes, int used, cons
     std::memcpy(K.zh, tmp.zh, sizeof K.zh);
     std::memcpy(K.zl, tmp.zl, sizeof K.zl);
     K.G.explicit_prescale = tmp.G.explicit_prescale;
-    for (int i = 0; i < 9; ++i) K.m[i] = std::ldexp(P.yuv[i], 100);
-    K.yoff = std::ldexp(P.yuv[9], -133);
-    K.coff = std::ldexp(P.yuv[10], -133);
-    const uint32_t kU = P.src_type == CVGS_NV12 ? 0u : 1u;
-    K.selU1 = 0x4044u | kU << 8;
-    K.selV1 = 0x4044u | (kU ^ 1u) << 8;
+    if (depth == 1) {
+        for (int i = 0; i < 9; ++i) K.m[i] = std::ldexp(P.yuv[i], 100);
+        K.yoff = std::ldexp(P.yuv[9], -133);
+        K.coff = std::ldexp(P.yuv[10], -133);
+        const uint32_t kU = P.src_type == CVGS_NV12 ? 0u : 1u;
+        K.selU1 = 0x4044u | kU << 8;
+        K.selV1 = 0x4044u | (kU ^ 1u) << 8;
+    } else {  // sample * 2^-135 in, (RGB * 64) * 2^-33 out (P.yuv[11] = 64 is in the exponent)
+        for (int i = 0; i < 9; ++i) K.m[i] = std::ldexp(P.yuv[i], 108);
+        K.yoff = std::ldexp(P.yuv[9], -135);
+        K.coff = std::ldexp(P.yuv[10], -135);
+        K.selU1 = 0x4104u;
+        K.selV1 = 0x4324u;
+    }
+    K.csh = csh;
     K.maps = mc.d;
     K.frames = reinterpret_cast<const DevYuv*>(r.crops_d(slot));
     r.next = (r.next + 1) % Ring::kSlots;
     CVGS_CUDA(cudaMemcpyAsync(r.crops_d(slot), hf, static_cast<size_t>(used) * sizeof(DevYuv), cudaMemcpyHostToDevice, stream));
     overlap_forget(stream);
-    const int rc = chain == CH_FMA_DIV ? yuv_launch_instance<CH_FMA_DIV>(K, device, stream) : yuv_launch_instance<CH_GENERIC>(K, device, stream);
+    const int rc = depth == 1 ? (chain == CH_FMA_DIV ? yuv_launch_instance<CH_FMA_DIV>(K, device, stream) : yuv_launch_instance<CH_GENERIC>(K, device, stream))
+                              : (chain == CH_FMA_DIV ? yuv_launch_instance<CH_FMA_DIV, 2>(K, device, stream) : yuv_launch_instance<CH_GENERIC, 2>(K, device, stream));
     CVGS_CUDA(cudaEventRecord(r.ev[slot], stream));
     r.pending[slot] = true;
     taken = rc == CVGS_OK;

@@ -14,8 +14,12 @@
 // the same one-PRMT trick (byte at mantissa bits 16..23 = b * 2^-133); here the compensating 2^100 sits in the colour
 // matrix (the offsets 16 / 128 are subtracted exactly in the scaled domain, the first product of every channel brings the
 // value back into the normal range before anything is rounded) and the remaining 2^33 in the first op of the chain, so
-// every rounding is the reference's.  The 10-bit formats and aspect-ratio / partial-batch / packed forms stay with the
-// direct-gather kernel.
+// every rounding is the reference's.
+// DEPTH = 2: P010 / P210 frames (16-bit words, the 10-bit sample in the high bits; P210 has a chroma row per luma row).
+// The reference shifts the samples down by 6, converts in the 10-bit range and multiplies the float RGB by 64; here the
+// low six bits are masked off and the halfword lands at mantissa bits 8..23 (= sample * 2^-135), the matrix carries 2^108
+// (2^100, the 64 and the 2^2 between the two placements) -- the same values at the same 2^-33 scale, every rounding in
+// the normal range.  Y210 (packed) and the aspect-ratio / partial-batch / packed-output forms stay with the direct kernel.
 #pragma once
 #include "preproc_tma.cuh"
 
@@ -40,7 +44,9 @@ struct YuvParams {
     const DevYuv* frames;      // device table, one entry per plane
     float m[9];                // YCbCr -> RGB matrix x 2^100
     float yoff, coff;          // luma / chroma offsets x 2^-133
-    uint32_t selU1, selV1;     // PRMT selectors of U / V of the first chroma pair of a staged word (NV12: bytes 0, 1; NV21: 1, 0)
+    uint32_t selU1, selV1;     // PRMT selectors of U / V of the first chroma pair of a staged word (NV12: bytes 0, 1; NV21: 1, 0;
+                               // 16-bit: halfwords 0, 1)
+    int32_t csh;               // chroma rows: luma row >> csh (1 for 4:2:0, 0 for 4:2:2)
 };
 
 // (Y, U, V) of one tap for both rows of the pair -> float RGB at scale 2^-33
@@ -56,9 +62,10 @@ __device__ __forceinline__ void yuv_to_rgb2(const YuvParams& K, float2 y, float2
     }
 }
 
-template <int CHAIN>
+template <int CHAIN, int DEPTH = 1>
 __global__ void __launch_bounds__(kTmaThreads, kMaxResident)
 preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
+    constexpr int B = DEPTH;  // bytes per sample
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[kWarps * kMaxSlots];
 
@@ -130,8 +137,8 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
             sb.txi = ic.txi;
             const DevYuv& F = K.frames[ic.z];
             const AxisTap tb = axis_tap(ic.txi * TW, F.fx);
-            sb.c0L = uniform_i(((F.xbL + tb.i1) >> 4) << 1);
-            sb.c0C = uniform_i(((F.xbC + 2 * (tb.i1 >> 1)) >> 4) << 1);
+            sb.c0L = uniform_i(((F.xbL + B * tb.i1) >> 4) << 1);
+            sb.c0C = uniform_i(((F.xbC + 2 * B * (tb.i1 >> 1)) >> 4) << 1);
             sb.rbL = uniform_i(F.rbL);
             sb.rbC = uniform_i(F.rbC);
             sb.fy = __uint_as_float(uniform_u(__float_as_uint(F.fy)));
@@ -151,10 +158,10 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive_expect_tx(full, two ? 2u * rs : rs);
             tma_load_2d(sdst, sb.mapL, sb.c0L, y1a, full);
-            tma_load_2d(sdst + 2 * sb.rbL, sb.mapC, sb.c0C, y1a >> 1, full);
+            tma_load_2d(sdst + 2 * sb.rbL, sb.mapC, sb.c0C, y1a >> K.csh, full);
             if (two) {
                 tma_load_2d(sdst + rs, sb.mapL, sb.c0L, y1b, full);
-                tma_load_2d(sdst + rs + 2 * sb.rbL, sb.mapC, sb.c0C, y1b >> 1, full);
+                tma_load_2d(sdst + rs + 2 * sb.rbL, sb.mapC, sb.c0C, y1b >> K.csh, full);
             }
         }
         ic.next(G);
@@ -178,8 +185,8 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
         uint32_t m_in = 0;
         {
             const AxisTap tb = axis_tap(tx0, F.fx);
-            const int originL = 8 * (((F.xbL + tb.i1) >> 4) << 1) - F.xbL;              // luma-row byte smem byte 0 stands for
-            const int originC = 8 * (((F.xbC + 2 * (tb.i1 >> 1)) >> 4) << 1) - F.xbC;  // same for the chroma row
+            const int originL = 8 * (((F.xbL + B * tb.i1) >> 4) << 1) - F.xbL;              // luma-row byte smem byte 0 stands for
+            const int originC = 8 * (((F.xbC + 2 * B * (tb.i1 >> 1)) >> 4) << 1) - F.xbC;  // same for the chroma row
             const int wm1 = F.w - 1;
             const uint32_t kU = (K.selU1 >> 8) & 7u;  // byte of U within a pair
 #pragma unroll
@@ -195,12 +202,17 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
                     wxb[p] = t.w1;
                     m_in |= (in_p ? 1u : 0u) << p;
                     const int x2 = min(t.i1 + 1, wm1);  // interpolation.cuh:72: the right tap is clamped to the last pixel
-                    const int oL = t.i1 - originL, oC = 2 * (t.i1 >> 1) - originC;
+                    const int oL = B * t.i1 - originL, oC = 2 * B * (t.i1 >> 1) - originC;
                     offL[p] = (oL >> 2) * 4;
                     offC[p] = (oC >> 2) * 4;
                     cfg[p] = (uint32_t)((oL & 3) * 8) | (uint32_t)((oC & 3) * 8) << 8;  // funnel shifts: luma in bits 0..4, chroma 8..12
-                    selY2[p] = 0x4044u | (uint32_t)(x2 - t.i1) << 8;
-                    selU2[p] = 0x4044u | (uint32_t)(2 * ((x2 >> 1) - (t.i1 >> 1)) + (int)kU) << 8;
+                    if (DEPTH == 1) {
+                        selY2[p] = 0x4044u | (uint32_t)(x2 - t.i1) << 8;
+                        selU2[p] = 0x4044u | (uint32_t)(2 * ((x2 >> 1) - (t.i1 >> 1)) + (int)kU) << 8;
+                    } else {  // halfword 0 / 1 of the lined-up luma word; which of two chroma words holds the right tap's pair
+                        selY2[p] = x2 != t.i1 ? 0x4324u : 0x4104u;
+                        selU2[p] = (x2 >> 1) != (t.i1 >> 1) ? 0x7654u : 0x3210u;
+                    }
                 }
             }
         }
@@ -229,9 +241,10 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
                 const uint32_t r1 = st1 ? rs : 0u;  // a missing second row borrows the first one's taps (not stored)
                 // luma rows y1 / y2 and chroma rows (y1 >> 1) / (y2 >> 1) of both output rows
                 uint32_t LA0 = sdata, LB0 = sdata + (y2a != ta.i1 ? (uint32_t)rbL : 0u);
-                uint32_t CA0 = sdata + 2 * (uint32_t)rbL, CB0 = CA0 + ((y2a >> 1) != (ta.i1 >> 1) ? (uint32_t)rbC : 0u);
+                const int csh = K.csh;
+                uint32_t CA0 = sdata + 2 * (uint32_t)rbL, CB0 = CA0 + ((y2a >> csh) != (ta.i1 >> csh) ? (uint32_t)rbC : 0u);
                 uint32_t LA1 = sdata + r1, LB1 = LA1 + (y2b != tb2.i1 ? (uint32_t)rbL : 0u);
-                uint32_t CA1 = LA1 + 2 * (uint32_t)rbL, CB1 = CA1 + ((y2b >> 1) != (tb2.i1 >> 1) ? (uint32_t)rbC : 0u);
+                uint32_t CA1 = LA1 + 2 * (uint32_t)rbL, CB1 = CA1 + ((y2b >> csh) != (tb2.i1 >> csh) ? (uint32_t)rbC : 0u);
                 float* tp[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -244,21 +257,45 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
                 for (int p = 0; p < NPC; ++p) {
                     if (!CHECK || (m_in & (1u << p))) {
                         const int sL = (int)(cfg[p] & 31u), sC = (int)(cfg[p] >> 8);
-                        const uint32_t selV1 = K.selV1, selU1 = K.selU1, selV2 = selU2[p] ^ 0x100u;
-                        // staged words lined up on the left tap: luma [Y(x1) Y(x1+1) ..], chroma [pair(x1 >> 1) pair(+1)]
                         auto lineup = [&](uint32_t a, int sh) { return __funnelshift_r(lds32_tap(a), lds32_tap(a + 4), sh); };
-                        const uint32_t la0 = lineup(LA0 + offL[p], sL), lb0 = lineup(LB0 + offL[p], sL);
-                        const uint32_t la1 = lineup(LA1 + offL[p], sL), lb1 = lineup(LB1 + offL[p], sL);
-                        const uint32_t cA0 = lineup(CA0 + offC[p], sC), cB0 = lineup(CB0 + offC[p], sC);
-                        const uint32_t cA1 = lineup(CA1 + offC[p], sC), cB1 = lineup(CB1 + offC[p], sC);
                         auto px = [](uint32_t w0, uint32_t w1, uint32_t sel) {
                             return make_float2(__uint_as_float(__byte_perm(w0, 0u, sel)), __uint_as_float(__byte_perm(w1, 0u, sel)));
                         };
                         float2 p00[3], p10[3], p01[3], p11[3];  // taps (x1, y1), (x2, y1), (x1, y2), (x2, y2) as RGB x 2^-33
-                        yuv_to_rgb2(K, px(la0, la1, 0x4044u), px(cA0, cA1, selU1), px(cA0, cA1, selV1), p00);
-                        yuv_to_rgb2(K, px(la0, la1, selY2[p]), px(cA0, cA1, selU2[p]), px(cA0, cA1, selV2), p10);
-                        yuv_to_rgb2(K, px(lb0, lb1, 0x4044u), px(cB0, cB1, selU1), px(cB0, cB1, selV1), p01);
-                        yuv_to_rgb2(K, px(lb0, lb1, selY2[p]), px(cB0, cB1, selU2[p]), px(cB0, cB1, selV2), p11);
+                        if (DEPTH == 1) {
+                            const uint32_t selV1 = K.selV1, selU1 = K.selU1, selV2 = selU2[p] ^ 0x100u;
+                            // staged words lined up on the left tap: luma [Y(x1) Y(x1+1) ..], chroma [pair(x1 >> 1) pair(+1)]
+                            const uint32_t la0 = lineup(LA0 + offL[p], sL), lb0 = lineup(LB0 + offL[p], sL);
+                            const uint32_t la1 = lineup(LA1 + offL[p], sL), lb1 = lineup(LB1 + offL[p], sL);
+                            const uint32_t cA0 = lineup(CA0 + offC[p], sC), cB0 = lineup(CB0 + offC[p], sC);
+                            const uint32_t cA1 = lineup(CA1 + offC[p], sC), cB1 = lineup(CB1 + offC[p], sC);
+                            yuv_to_rgb2(K, px(la0, la1, 0x4044u), px(cA0, cA1, selU1), px(cA0, cA1, selV1), p00);
+                            yuv_to_rgb2(K, px(la0, la1, selY2[p]), px(cA0, cA1, selU2[p]), px(cA0, cA1, selV2), p10);
+                            yuv_to_rgb2(K, px(lb0, lb1, 0x4044u), px(cB0, cB1, selU1), px(cB0, cB1, selV1), p01);
+                            yuv_to_rgb2(K, px(lb0, lb1, selY2[p]), px(cB0, cB1, selU2[p]), px(cB0, cB1, selV2), p11);
+                        } else {
+                            // luma: [Y(x1) Y(x1+1)] halfwords lined up (the shift is 0 or 16); chroma: pair(x1 >> 1) is one
+                            // aligned word, the right tap's pair that word or the next; the low six bits of every sample go
+                            constexpr uint32_t kTen = 0xffc0ffc0u;
+                            const uint32_t selV1 = K.selV1, selU1 = K.selU1, selC = selU2[p];
+                            const uint32_t la0 = lineup(LA0 + offL[p], sL) & kTen, lb0 = lineup(LB0 + offL[p], sL) & kTen;
+                            const uint32_t la1 = lineup(LA1 + offL[p], sL) & kTen, lb1 = lineup(LB1 + offL[p], sL) & kTen;
+                            auto pairs = [&](uint32_t a, uint32_t& left, uint32_t& right) {
+                                const uint32_t w0 = lds32_tap(a), w1 = lds32_tap(a + 4);
+                                left = w0 & kTen;
+                                right = __byte_perm(w0, w1, selC) & kTen;
+                            };
+                            uint32_t cA0, cA0r, cB0, cB0r, cA1, cA1r, cB1, cB1r;
+                            pairs(CA0 + offC[p], cA0, cA0r);
+                            pairs(CB0 + offC[p], cB0, cB0r);
+                            pairs(CA1 + offC[p], cA1, cA1r);
+                            pairs(CB1 + offC[p], cB1, cB1r);
+                            (void)sC;
+                            yuv_to_rgb2(K, px(la0, la1, 0x4104u), px(cA0, cA1, selU1), px(cA0, cA1, selV1), p00);
+                            yuv_to_rgb2(K, px(la0, la1, selY2[p]), px(cA0r, cA1r, selU1), px(cA0r, cA1r, selV1), p10);
+                            yuv_to_rgb2(K, px(lb0, lb1, 0x4104u), px(cB0, cB1, selU1), px(cB0, cB1, selV1), p01);
+                            yuv_to_rgb2(K, px(lb0, lb1, selY2[p]), px(cB0r, cB1r, selU1), px(cB0r, cB1r, selV1), p11);
+                        }
                         const float2 wxa2 = make_float2(wxa[p], wxa[p]), wxb2 = make_float2(wxb[p], wxb[p]);
                         const float2 w00 = __fmul2_rn(wxa2, wy0), w10 = __fmul2_rn(wxb2, wy0);
                         const float2 w01 = __fmul2_rn(wxa2, wy1), w11 = __fmul2_rn(wxb2, wy1);
@@ -326,24 +363,27 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
 // ------------------------------------------------------------------------------------------------
 // Staged row bytes of the two planes for a band of TW columns at scale fx: luma 1 byte per pixel; the chroma row spans
 // the same bytes (2 bytes per pixel pair) plus one pair on either side.
-inline int yuv_rb_luma(int TW, float fx) { return band_row_bytes(TW, fx, 1); }
-inline int yuv_rb_chroma(int TW, float fx) { return band_row_bytes(TW, fx, 1) + 64; }
+inline int yuv_rb_luma(int TW, float fx, int depth = 1) { return band_row_bytes(TW, fx, depth); }
+inline int yuv_rb_chroma(int TW, float fx, int depth = 1) { return band_row_bytes(TW, fx, depth) + 64; }
+inline int yuv_depth_of(int src_type) { return src_type == CVGS_P010 || src_type == CVGS_P210 ? 2 : 1; }
 
 // Can a batch of NV12 / NV21 frames take this kernel, and with which geometry?
 inline bool yuv_tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int n_planes, int sm_count, TmaGeom& G) {
     if (!encode_tiled_fn()) return false;
-    if (P.src_type != CVGS_NV12 && P.src_type != CVGS_NV21) return false;
+    if (P.src_type != CVGS_NV12 && P.src_type != CVGS_NV21 && P.src_type != CVGS_P010 && P.src_type != CVGS_P210) return false;
+    const int depth = yuv_depth_of(P.src_type);
     if (P.band_test || P.used != P.n_planes || used != n_planes || P.out.px_stride != 1 || P.out.planes || P.out.u8 || P.prog.special) return false;
     float fx_max = 0.f;
     for (int i = 0; i < used; ++i) {
         const DevCrop& c = crops[i];
-        if ((c.w & 1) || (c.h & 1) || c.w < 2 || c.h < 2 || c.pitch % 16 != 0 || c.pitch < c.w) return false;
+        if ((c.w & 1) || (c.h & 1) || c.w < 2 || c.h < 2 || c.pitch % 16 != 0 || c.pitch < depth * c.w) return false;
+        if (depth == 2 && (reinterpret_cast<uintptr_t>(c.data) & 3)) return false;  // chroma pairs are aligned words
         if (!(c.fx > 0.f) || !(c.fy > 0.f) || !std::isfinite(c.fx) || !std::isfinite(c.fy)) return false;
         fx_max = std::max(fx_max, c.fx);
     }
     if (static_cast<long long>(P.W) * P.H * 4 > 0x3fffffffLL) return false;
     int NPB = std::min(kMaxNP, (P.W + 31) / 32);
-    auto need = [&](int npb) { return yuv_rb_chroma(std::min(32 * npb, P.W), fx_max); };
+    auto need = [&](int npb) { return yuv_rb_chroma(std::min(32 * npb, P.W), fx_max, depth); };
     while (NPB > 1 && need(NPB) > kMaxBoxBytes) --NPB;
     if (need(NPB) > kMaxBoxBytes) return false;
     const int TW = 32 * NPB;
@@ -355,19 +395,19 @@ inline bool yuv_tma_plan(const PreprocParams& P, const DevCrop* crops, int used,
     const long long total = static_cast<long long>(n_planes) * G.items_per_crop;
     if (total > 0x7fffffffLL) return false;
     G.total_items = static_cast<int32_t>(total);
-    G.slot_bytes = kSlotHeader + 2 * (2 * yuv_rb_luma(std::min(TW, P.W), fx_max) + 2 * need(NPB));
+    G.slot_bytes = kSlotHeader + 2 * (2 * yuv_rb_luma(std::min(TW, P.W), fx_max, depth) + 2 * need(NPB));
     G.explicit_prescale = 0;
     G.prescale = kPreScale;
     G.pdl_wait = 1;
     return tma_plan_items(G, P.W, n_planes, sm_count, 1, 1, kMaxResident);
 }
 
-template <int CHAIN>
+template <int CHAIN, int DEPTH = 1>
 inline int yuv_launch_instance(const YuvParams& K, int device, cudaStream_t stream) {
     static thread_local size_t attr_set[64] = {};
     const size_t smem = tma_smem_bytes(K.G);
     const int slot = device & 63;
-    auto kernel = preproc_yuv_tma_kernel<CHAIN>;
+    auto kernel = preproc_yuv_tma_kernel<CHAIN, DEPTH>;
     if (smem > attr_set[slot]) {
         const size_t want = std::max<size_t>(smem, 112 * 1024);
         CVGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(want)));

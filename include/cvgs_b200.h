@@ -62,8 +62,9 @@ extern "C" {
  * fk::ConvertYUVToRGB<NV12, range, primaries, false, float3> in front of the resize (reference
  * fkl/.../image_processing/color_conversion.cuh:235-362; tests/resize/test_fused_resize.cu:73-76,141-143).  A crop
  * of this type is a whole frame {Y plane, width, height, pitch}; the pipeline sees float RGB.  Batches of even-sized
- * NV12 / NV21 frames in the common geometry (IGNORE_AR, every plane used, planar float tensor, pitch a multiple of 16)
- * take the TMA-staged kernel (csrc/preproc_yuv_tma.cuh), everything else the direct-gather kernel. */
+ * NV12 / NV21 / P010 / P210 frames in the common geometry (IGNORE_AR, every plane used, planar float tensor, pitch a
+ * multiple of 16; 16-bit formats: base a multiple of 4) take the TMA-staged kernel (csrc/preproc_yuv_tma.cuh),
+ * everything else the direct-gather kernel. */
 #define CVGS_NV12 0x1001
 /* The other fk::PixelFormat readers the reference can instantiate (color_conversion.cuh:89-98,296-345), same contract:
  *   CVGS_NV21  as NV12 with the chroma bytes in V, U order
@@ -331,7 +332,7 @@ int cvgs_b200_preproc_host_sequence(const void* const* host_images, int32_t imag
                                     float* const* host_outs, int32_t n_sets, int32_t steps,
                                     void* stream);
 
-/* Kernel-selection override, for tests and profiling: 0 = automatic, 1 = direct-gather kernel,
+/* Kernel-selection override, for tests and profiling: 0 = automatic, 1 = direct-gather kernel (warp: the general kernel),
  * 2 = TMA-staged kernel.  Returns the previous value. */
 int cvgs_b200_set_kernel_variant(int variant);
 /* Overlap of consecutive launches (default 0 = off; the environment variable CVGS_B200_OVERLAP=1 / 2 selects a mode at
