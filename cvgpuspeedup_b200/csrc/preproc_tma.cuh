@@ -382,9 +382,11 @@ struct ItemCursor {
 // row r in .x and row r+1 in .y (scaled by 2^-33).  Arithmetic per half = Interpolate<INTER_LINEAR>::exec in the
 // order nvcc emits for the reference: FMUL(p10*w10), FFMA(p00,w00), FFMA(p01,w01), FFMA(p11,w11).
 // NC = 4 (CV_8UC4): a pixel is one aligned word -- two loads per source row, no shifts.
+// S16 (CV_16SC3 / CV_16SC4): the sign bit of every halfword is flipped (sample + 32768, an unsigned halfword), converted
+// like an unsigned one, and 32768 * 2^-141 = 2^-126 is subtracted again: exact, all values are multiples of 2^-141 below 2^-125.
 // DEPTH = 2 (CV_16UC3 / CV_16UC4): halfword samples; 6-byte pixels start on even bytes (one funnel shift by 0 or 16 bits
 // lines three words up on halfword pairs), 8-byte pixels are two aligned words.
-template <int NC, int DEPTH>
+template <int NC, int DEPTH, bool S16 = false>
 __device__ __forceinline__ void gather_pair(uint32_t A0, uint32_t B0, uint32_t A1, uint32_t B1, int shl, int shr, bool edge,
                                             float wx0, float wx1, float2 wy0, float2 wy1, float2 (&v)[NC]) {
     const float2 w00 = __fmul2_rn(make_float2(wx0, wx0), wy0), w10 = __fmul2_rn(make_float2(wx1, wx1), wy0);
@@ -395,7 +397,9 @@ __device__ __forceinline__ void gather_pair(uint32_t A0, uint32_t B0, uint32_t A
         const uint32_t base[4] = {A0, B0, A1, B1};
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const uint32_t w0 = lds32_tap(base[r]), w1 = lds32_tap(base[r] + 4), w2 = lds32_tap(base[r] + 8), w3 = lds32_tap(base[r] + 12);
+            constexpr uint32_t kFlip = S16 ? 0x80008000u : 0u;
+            const uint32_t w0 = lds32_tap(base[r]) ^ kFlip, w1 = lds32_tap(base[r] + 4) ^ kFlip, w2 = lds32_tap(base[r] + 8) ^ kFlip,
+                           w3 = lds32_tap(base[r] + 12) ^ kFlip;
             if constexpr (NC == 3) {
                 const uint32_t L0 = __funnelshift_r(w0, w1, shl), L1 = __funnelshift_r(w1, w2, shl), L2 = __funnelshift_r(w2, w3, shl);
                 pl[r][0] = u16_scaled(L0, 0), pl[r][1] = u16_scaled(L0, 1), pl[r][2] = u16_scaled(L1, 0);
@@ -409,12 +413,17 @@ __device__ __forceinline__ void gather_pair(uint32_t A0, uint32_t B0, uint32_t A
                 for (int c = 0; c < NC; ++c) pr[r][c] = pl[r][c];
             }
         }
+        auto rows = [](float a, float b) {  // the sample of both rows of the pair; signed: minus the 32768 added by the flip
+            float2 t = make_float2(a, b);
+            if (S16) t = __fadd2_rn(t, make_float2(-1.1754943508222875e-38f, -1.1754943508222875e-38f));  // 2^-126
+            return t;
+        };
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            float2 t = __fmul2_rn(make_float2(pr[0][c], pr[2][c]), w10);
-            t = __ffma2_rn(make_float2(pl[0][c], pl[2][c]), w00, t);
-            t = __ffma2_rn(make_float2(pl[1][c], pl[3][c]), w01, t);
-            v[c] = __ffma2_rn(make_float2(pr[1][c], pr[3][c]), w11, t);
+            float2 t = __fmul2_rn(rows(pr[0][c], pr[2][c]), w10);
+            t = __ffma2_rn(rows(pl[0][c], pl[2][c]), w00, t);
+            t = __ffma2_rn(rows(pl[1][c], pl[3][c]), w01, t);
+            v[c] = __ffma2_rn(rows(pr[1][c], pr[3][c]), w11, t);
         }
         return;
     }
@@ -503,8 +512,8 @@ constexpr int kNarrowNP = 2;
 constexpr int kNarrowResident = 6;
 // NC: channels = bytes of the 8-bit source pixel (3: CV_8UC3, 4: CV_8UC4); registers, chain constants and planes follow it.
 // U8 = true: the common geometry with packed 8-bit output (convertTo<CV_32FCn, CV_8UCn> + write<CV_8UCn>: a plain resize).
-// DEPTH: bytes per source sample (1: CV_8U, 2: CV_16U).
-template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3, bool U8 = false, int DEPTH = 1>
+// DEPTH: bytes per source sample (1: CV_8U, 2: CV_16U / CV_16S); S16: the samples are signed.
+template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3, bool U8 = false, int DEPTH = 1, bool S16 = false>
 __global__ void __launch_bounds__(kTmaThreads, MAXNP <= kNarrowNP ? kNarrowResident : kMaxResident)
 preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ Table T) {
     extern __shared__ uint8_t smem_raw[];
@@ -812,7 +821,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                     if (!CHECK || (m_in & (1u << p))) {  // lanes past the right border of the plane skip
                         float2 v[NC];
                         if (!GEN || im0 || im1) {
-                            gather_pair<NC, DEPTH>(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p],
+                            gather_pair<NC, DEPTH, S16>(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p],
                                         (m_edge & (1u << p)) != 0, wxa[p], wxb[p], wy0, wy1, v);
                             if (CHAIN == CH_FMA_DIV) {
 #pragma unroll
@@ -1068,10 +1077,12 @@ inline bool tma_plan_items(TmaGeom& G, int W, int n_planes, int sm_count, int it
 inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int n_planes, int sm_count, bool image_mode,
                      int items_per_warp, TmaGeom& G, bool need_driver = true, int grid_div = 1, int max_resident = kMaxResident) {
     if (need_driver && !encode_tiled_fn()) return false;
-    // the tap extraction is written for 3-byte pixels, for 4-byte pixels that are aligned words, and for unsigned 16-bit
-    // samples (6-byte pixels on even bytes, 8-byte pixels as aligned word pairs)
-    if (P.src_type != CVGS_8UC3 && P.src_type != CVGS_8UC4 && P.src_type != CVGS_16UC3 && P.src_type != CVGS_16UC4) return false;
-    const int pb = P.src_type == CVGS_8UC3 ? 3 : (P.src_type == CVGS_8UC4 ? 4 : (P.src_type == CVGS_16UC3 ? 6 : 8));
+    // the tap extraction is written for 3-byte pixels, for 4-byte pixels that are aligned words, and for 16-bit samples
+    // (6-byte pixels on even bytes, 8-byte pixels as aligned word pairs)
+    if (P.src_type != CVGS_8UC3 && P.src_type != CVGS_8UC4 && P.src_type != CVGS_16UC3 && P.src_type != CVGS_16UC4 &&
+        P.src_type != CVGS_16SC3 && P.src_type != CVGS_16SC4)
+        return false;
+    const int pb = P.src_type == CVGS_8UC3 ? 3 : (P.src_type == CVGS_8UC4 ? 4 : (P.src_type == CVGS_16UC3 || P.src_type == CVGS_16SC3 ? 6 : 8));
     if (P.out.u8 && (pb != 3 || P.prog.nc_out != 3)) return false;
     // everything but CV_8UC3: built for the common geometry only (IGNORE_AR, every plane used, planar float tensors)
     if (pb != 3 && (P.band_test || P.used != P.n_planes || P.out.px_stride != 1 || P.out.planes || P.out.u8)) return false;
@@ -1415,12 +1426,12 @@ inline size_t tma_smem_bytes(const TmaGeom& G) {
     return static_cast<size_t>(kWarps) * G.slots * G.slot_bytes + kRingPad + 128;
 }
 
-template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3, bool U8 = false, int DEPTH = 1>
+template <typename Table, int CHAIN, bool GEN, bool PEER = false, int MAXNP = kMaxNP, int NC = 3, bool U8 = false, int DEPTH = 1, bool S16 = false>
 inline int tma_launch_instance(const TmaParams& K, const Table& T, int device, cudaStream_t stream) {
     static thread_local size_t attr_set[64] = {};  // per device: dynamic shared memory opt-in already granted
     const size_t smem = tma_smem_bytes(K.G);
     const int slot = device & 63;
-    auto kernel = preproc_tma_kernel<Table, CHAIN, GEN, PEER, MAXNP, NC, U8, DEPTH>;
+    auto kernel = preproc_tma_kernel<Table, CHAIN, GEN, PEER, MAXNP, NC, U8, DEPTH, S16>;
     if (smem > attr_set[slot]) {
         const size_t want = std::max<size_t>(smem, 112 * 1024);
         CVGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(want)));
@@ -1473,6 +1484,12 @@ inline int tma_launch_kernel(const TmaParams& K, const Table& T, int chain, int 
                 case CVGS_16UC3:
                     return fd ? tma_launch_instance<Table, CH_FMA_DIV, false, false, kMaxNP, 3, false, 2>(K, T, device, stream)
                               : tma_launch_instance<Table, CH_GENERIC, false, false, kMaxNP, 3, false, 2>(K, T, device, stream);
+                case CVGS_16SC3:
+                    return fd ? tma_launch_instance<Table, CH_FMA_DIV, false, false, kMaxNP, 3, false, 2, true>(K, T, device, stream)
+                              : tma_launch_instance<Table, CH_GENERIC, false, false, kMaxNP, 3, false, 2, true>(K, T, device, stream);
+                case CVGS_16SC4:
+                    return fd ? tma_launch_instance<Table, CH_FMA_DIV, false, false, kMaxNP, 4, false, 2, true>(K, T, device, stream)
+                              : tma_launch_instance<Table, CH_GENERIC, false, false, kMaxNP, 4, false, 2, true>(K, T, device, stream);
                 default:
                     return fd ? tma_launch_instance<Table, CH_FMA_DIV, false, false, kMaxNP, 4, false, 2>(K, T, device, stream)
                               : tma_launch_instance<Table, CH_GENERIC, false, false, kMaxNP, 4, false, 2>(K, T, device, stream);

@@ -259,7 +259,7 @@ __device__ __forceinline__ void warp_fast_pixels(const WarpFastParams& K, const 
 }
 
 template <typename T, int NC, bool DIV>
-__global__ void __launch_bounds__(256, CVGS_WARP_MINB)
+__global__ void __launch_bounds__(256, NC == 4 ? 4 : CVGS_WARP_MINB)  // four channels: 64 registers, no spills
 preproc_warp_fast_kernel(const __grid_constant__ WarpFastParams K, const __grid_constant__ WarpTable Tb, int z0) {
     const int xb = blockIdx.x * 128 + (threadIdx.x & 31);
     const int y = blockIdx.y * (8 * K.rows) + (threadIdx.x >> 5);

@@ -48,12 +48,12 @@ extern "C" {
 /* ---- pixel types: same numeric values as OpenCV's CV_MAKETYPE(depth, cn) ---- */
 #define CVGS_8UC3 16  /* CV_8UC3  */
 #define CVGS_16UC3 18 /* CV_16UC3: source only (SaturateCast saturate.cuh:267-298); TMA-staged kernel in the common geometry */
-#define CVGS_16SC3 19 /* CV_16SC3: source only; taken by the direct-gather kernel (saturate.cuh:358-378)             */
+#define CVGS_16SC3 19 /* CV_16SC3: source only (saturate.cuh:358-378); TMA-staged kernel in the common geometry          */
 #define CVGS_32FC1 5  /* CV_32FC1: output of a chain that ends in one channel (CVGS_OP_GRAY) */
 #define CVGS_32FC3 21 /* CV_32FC3 */
 #define CVGS_8UC4 24  /* CV_8UC4, CV_16UC4, CV_16SC4: 4-channel sources (the reference's test matrix,            */
 #define CVGS_16UC4 26 /* tests/batchresize/test_batchresize_x_split3D.cu:427-432): four output channels, four      */
-#define CVGS_16SC4 27 /* constants per operation, REORDER over four channels; 8UC4 / 16UC4 in the common geometry
+#define CVGS_16SC4 27 /* constants per operation, REORDER over four channels; all three in the common geometry
                          (IGNORE_AR, all planes used, planar float output) go through the TMA-staged kernel, the rest
                          through the direct-gather kernel                                                              */
 #define CVGS_32FC4 29 /* CV_32FC4 */

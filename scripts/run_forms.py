@@ -108,6 +108,7 @@ run("CV_8UC3 -> RGBA float (BGR2RGBA)", _abi.CVGS_8UC3, [("reorder", (2, 1, 0)),
 pitch = 6 * FW
 img6 = rng.integers(0, 256, size=(FH, pitch), dtype=np.uint8)
 run("CV_16UC3 -> NCHW float", _abi.CVGS_16UC3, NORM, 6, img6, rgb_crops(6))
+run("CV_16SC3 -> NCHW float", _abi.CVGS_16SC3, NORM, 6, img6, rgb_crops(6))
 pitch = 4 * FW
 img4 = rng.integers(0, 256, size=(FH, pitch), dtype=np.uint8)
 run("CV_8UC4 -> NCHW float (4 planes)", _abi.CVGS_8UC4, NORM4, 4, img4, rgb_crops(4), out_channels=4)

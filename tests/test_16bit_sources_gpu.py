@@ -34,12 +34,26 @@ def test_16bit_sources_match_oracle(src_type, aspect):
             util.assert_bit_equal(got, want, f"src_type {src_type} aspect {aspect} {dsize} {kw}")
 
 
-def test_tma_kernel_declines_signed_16bit_sources():
-    """Unsigned 16-bit samples go through the TMA-staged kernel (tests/test_4channel_gpu.py); signed ones keep the
-    direct-gather kernel (variant 2 = fail instead of falling back)."""
-    img = _image16(42, 64, 64, 384, False)
-    with pytest.raises(_abi.CvgsError):
-        gpu_util.run_cvgs(img, [(0, 0, 64, 64)], (32, 32), [], variant=2, src_type=_abi.CVGS_16SC3)
+def test_tma_kernel_takes_signed_16bit_sources_bit_exact_with_the_reference_kernel():
+    """Signed 16-bit samples through the TMA-staged kernel (forced: variant 2): extreme values (-32768, 32767, 0, -1) next to
+    each other, against the oracle and -- where built -- the reference's own short3 instantiation."""
+    w, h, pitch = 96, 64, 6 * 96 + 16
+    vals = np.array([-32768, 32767, 0, -1, 1, -12345, 12345, 255, -256], dtype=np.int16)
+    rng = np.random.default_rng(43)
+    img16 = vals[rng.integers(0, len(vals), size=(h, pitch // 2))]
+    img = img16.view(np.uint8).reshape(h, pitch)
+    rects = [(0, 0, 96, 64), (3, 5, 40, 50), (95, 0, 1, 64), (10, 10, 64, 32)]
+    mul, sub, div = (1 / 257.0,) * 3, (1.0, 4.0, 3.2), (3.2, 0.6, 11.8)
+    ops = [("reorder", (2, 1, 0)), ("mul", mul), ("sub", sub), ("div", div)]
+    for dsize in [(64, 128), (33, 7), (200, 100)]:
+        got = gpu_util.run_cvgs(img, rects, dsize, ops, variant=2, src_type=_abi.CVGS_16SC3)
+        want = util.run_oracle(img, rects, dsize, ops, src_type=_abi.CVGS_16SC3)
+        util.assert_bit_equal(got, want, f"signed 16-bit, TMA-staged kernel vs oracle {dsize}")
+    if gpu_util.fkref_lib(16) is not None:
+        rects16 = rects * 4
+        ref = gpu_util.run_fkref(img, rects16, (64, 128), 1, mul, sub, div, batch=16, used=16, src_type=_abi.CVGS_16SC3)
+        got = gpu_util.run_cvgs(img, rects16, (64, 128), ops, variant=2, src_type=_abi.CVGS_16SC3)
+        util.assert_bit_equal(got, ref, "signed 16-bit, TMA-staged kernel vs reference kernel")
 
 
 def test_circular_tensor_with_16bit_frames():

@@ -50,12 +50,13 @@ def test_4channel_layouts_and_modes(src_type):
         util.assert_bit_equal(got, want, f"src_type {src_type} {kw}")
 
 
-def test_tma_kernel_declines_signed_16bit_sources_and_unaligned_8uc4():
-    """The TMA-staged kernel takes CV_8UC4 whose pixels are aligned words; 16-bit pixels and 8UC4 images at odd byte
-    offsets belong to the direct-gather kernel (variant 2 = fail instead of falling back)."""
+def test_tma_kernel_declines_other_geometries_of_16bit_sources_and_unaligned_8uc4():
+    """The TMA-staged kernel takes CV_8UC4 whose pixels are aligned words and 16-bit pixels in the common geometry; the
+    aspect-ratio modes of 16-bit sources and 8UC4 images at odd byte offsets belong to the direct-gather kernel (variant 2 =
+    fail instead of falling back)."""
     img = _img(90, _abi.CVGS_16SC4)
     with pytest.raises(_abi.CvgsError):
-        gpu_util.run_cvgs(img, [(0, 0, 64, 64)], (32, 32), [], variant=2, src_type=_abi.CVGS_16SC4)
+        gpu_util.run_cvgs(img, [(0, 0, 64, 64)], (32, 32), [], variant=2, src_type=_abi.CVGS_16SC4, aspect=_abi.PRESERVE_AR)
     lib = _abi.load()
     buf = torch.zeros(64 * 272 + 8, dtype=torch.uint8, device="cuda")
     out = torch.empty((1, 4, 32, 32), device="cuda")
@@ -99,10 +100,11 @@ def test_4channel_taps_at_every_base_alignment(src_type, shifts):
             util.assert_bit_equal(out.cpu().numpy(), want, f"src {src_type} shift {shift} pitch {pitch}")
 
 
-@pytest.mark.parametrize("src_type,px", [(_abi.CVGS_8UC4, 4), (_abi.CVGS_16UC3, 6), (_abi.CVGS_16UC4, 8)])
+@pytest.mark.parametrize("src_type,px", [(_abi.CVGS_8UC4, 4), (_abi.CVGS_16UC3, 6), (_abi.CVGS_16UC4, 8), (_abi.CVGS_16SC3, 6), (_abi.CVGS_16SC4, 8)])
 @pytest.mark.parametrize("n,parents", [(8, True), (100, True), (300, True), (40, False), (300, False)])
 def test_tma_staged_kernel_takes_8uc4_and_16u(n, parents, src_type, px):
-    """CV_8UC4 / CV_16UC3 / CV_16UC4 through the TMA-staged kernel (forced: variant 2 fails instead of falling back):
+    """CV_8UC4 / CV_16UC3 / CV_16UC4 / CV_16SC3 / CV_16SC4 through the TMA-staged kernel (forced: variant 2 fails instead of
+    falling back; signed samples: sign bit flipped, converted as unsigned, 2^-126 subtracted in the scaled domain):
     aligned-word pixels, halfword samples (6-byte pixels at both word phases), three / four channels through chain and
     stores.  Small batches, the 256-crop table and the descriptor ring; with and without parent images; mixed up- and
     down-scales; the FMA-DIV chain, a generic chain, no chain, and the rounded-resize mode."""
