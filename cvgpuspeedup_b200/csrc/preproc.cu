@@ -475,7 +475,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
     const int sms = sm_count_of(device);
 
     const bool planes_out = pipe->out_layout == CVGS_OUT_PLANES;  // needs a device table of destinations: ring path
-    if ((P.src_type == CVGS_NV12 || P.src_type == CVGS_NV21 || P.src_type == CVGS_P010 || P.src_type == CVGS_P210) && variant != 1 && n_replicas == 0) {
+    if (CVGS_IS_YUV(P.src_type) && variant != 1 && n_replicas == 0) {
         bool taken = false;
         if (int rc = launch_yuv_tma(crops, n_planes, used, pipe, P, device, sms, stream, taken)) return rc;
         if (taken) return CVGS_OK;
@@ -680,7 +680,8 @@ static int launch_yuv_tma(const cvgs_crop_t* crops, int n_planes, int used, cons
     static_assert(sizeof(DevYuv) == sizeof(DevCrop), "the frame table lives in the ring's crop region");
     DevYuv* hf = reinterpret_cast<DevYuv*>(r.crops_h(slot));
     const int TWp = std::min(32 * K.G.NPB, P.W);
-    const int depth = yuv_depth_of(P.src_type);
+    const bool packed = P.src_type == CVGS_Y210;
+    const int depth = packed ? 2 : yuv_depth_of(P.src_type);
     const int csh = P.src_type == CVGS_P210 ? 0 : 1;
     for (int attempt = 0;; ++attempt) {
         const uint32_t gen = mc.generation;
@@ -696,11 +697,11 @@ static int launch_yuv_tma(const cvgs_crop_t* crops, int n_planes, int used, cons
             f.h = c.h;
             f.fx = c.fx;
             f.fy = c.fy;
-            f.rbL = yuv_rb_luma(TWp, c.fx, depth);
-            f.rbC = yuv_rb_chroma(TWp, c.fx, depth);
+            f.rbL = packed ? yuv_rb_packed(TWp, c.fx) : yuv_rb_luma(TWp, c.fx, depth);
+            f.rbC = packed ? 0 : yuv_rb_chroma(TWp, c.fx, depth);
             f.pad0 = f.pad1 = 0;
-            f.mapL = mc.get(luma, c.pitch, depth * c.w, c.h, f.rbL);          // luma plane: w samples x h rows
-            f.mapC = f.mapL < 0 ? -1 : mc.get(chroma, c.pitch, depth * c.w, c.h >> csh, f.rbC);  // chroma: w / 2 pairs x h / 2 (4:2:0) or h rows
+            f.mapL = mc.get(luma, c.pitch, (packed ? 4 : depth) * c.w, c.h, f.rbL);  // luma plane: w samples x h rows (Y210: w / 2 groups)
+            f.mapC = f.mapL < 0 ? -1 : packed ? f.mapL : mc.get(chroma, c.pitch, depth * c.w, c.h >> csh, f.rbC);  // chroma: w / 2 pairs x h / 2 (4:2:0) or h rows
             if (f.mapL < 0 || f.mapC < 0) return CVGS_OK;  // the driver refused the geometry: direct-gather kernel
             if (mc.generation != gen) restart = true;      // the table started over: indices handed out so far are void
         }
@@ -737,8 +738,9 @@ static int launch_yuv_tma(const cvgs_crop_t* crops, int n_planes, int used, cons
     r.next = (r.next + 1) % Ring::kSlots;
     CVGS_CUDA(cudaMemcpyAsync(r.crops_d(slot), hf, static_cast<size_t>(used) * sizeof(DevYuv), cudaMemcpyHostToDevice, stream));
     overlap_forget(stream);
-    const int rc = depth == 1 ? (chain == CH_FMA_DIV ? yuv_launch_instance<CH_FMA_DIV>(K, device, stream) : yuv_launch_instance<CH_GENERIC>(K, device, stream))
-                              : (chain == CH_FMA_DIV ? yuv_launch_instance<CH_FMA_DIV, 2>(K, device, stream) : yuv_launch_instance<CH_GENERIC, 2>(K, device, stream));
+    const int rc = packed       ? (chain == CH_FMA_DIV ? yuv_launch_instance<CH_FMA_DIV, 2, true>(K, device, stream) : yuv_launch_instance<CH_GENERIC, 2, true>(K, device, stream))
+                   : depth == 1 ? (chain == CH_FMA_DIV ? yuv_launch_instance<CH_FMA_DIV>(K, device, stream) : yuv_launch_instance<CH_GENERIC>(K, device, stream))
+                                : (chain == CH_FMA_DIV ? yuv_launch_instance<CH_FMA_DIV, 2>(K, device, stream) : yuv_launch_instance<CH_GENERIC, 2>(K, device, stream));
     CVGS_CUDA(cudaEventRecord(r.ev[slot], stream));
     r.pending[slot] = true;
     taken = rc == CVGS_OK;

@@ -19,7 +19,11 @@
 // The reference shifts the samples down by 6, converts in the 10-bit range and multiplies the float RGB by 64; here the
 // low six bits are masked off and the halfword lands at mantissa bits 8..23 (= sample * 2^-135), the matrix carries 2^108
 // (2^100, the 64 and the 2^2 between the two placements) -- the same values at the same 2^-33 scale, every rounding in
-// the normal range.  Y210 (packed) and the aspect-ratio / partial-batch / packed-output forms stay with the direct kernel.
+// the normal range.
+// PACKED: Y210 frames ({Y0, U, Y1, V} 16-bit words per pixel pair, one plane, one tensor map): a tap is the 8-byte group of
+// its pixel pair, fetched with one 64-bit shared-memory load; its three samples are halfwords 0 / 2 (Y), 1 (U) and 3 (V) of
+// the group, each placed with one two-source PRMT and cleaned (neighbour bytes and the low six bits) with one LOP3.
+// The aspect-ratio / partial-batch / packed-output forms stay with the direct kernel.
 #pragma once
 #include "preproc_tma.cuh"
 
@@ -62,10 +66,16 @@ __device__ __forceinline__ void yuv_to_rgb2(const YuvParams& K, float2 y, float2
     }
 }
 
-template <int CHAIN, int DEPTH = 1>
+__device__ __forceinline__ uint2 lds64_tap(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+
+template <int CHAIN, int DEPTH = 1, bool PACKED = false>
 __global__ void __launch_bounds__(kTmaThreads, kMaxResident)
 preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
-    constexpr int B = DEPTH;  // bytes per sample
+    constexpr int B = PACKED ? 4 : DEPTH;  // bytes per luma sample step (packed: a pixel pair is 8 bytes)
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[kWarps * kMaxSlots];
 
@@ -137,7 +147,7 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
             sb.txi = ic.txi;
             const DevYuv& F = K.frames[ic.z];
             const AxisTap tb = axis_tap(ic.txi * TW, F.fx);
-            sb.c0L = uniform_i(((F.xbL + B * tb.i1) >> 4) << 1);
+            sb.c0L = uniform_i(((F.xbL + (PACKED ? 8 * (tb.i1 >> 1) : B * tb.i1)) >> 4) << 1);
             sb.c0C = uniform_i(((F.xbC + 2 * B * (tb.i1 >> 1)) >> 4) << 1);
             sb.rbL = uniform_i(F.rbL);
             sb.rbC = uniform_i(F.rbC);
@@ -152,16 +162,16 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
         const int y1b = uniform_i(axis_tap(y + 1, sb.fy).i1);
         const bool two = y + 1 < H;
         if (elect_one_sync()) {
-            const uint32_t rs = (uint32_t)(2 * sb.rbL + 2 * sb.rbC);
+            const uint32_t rs = (uint32_t)(2 * sb.rbL + (PACKED ? 0 : 2 * sb.rbC));
             const uint32_t sdst = ring + (uint32_t)slot * slot_bytes + kSlotHeader;
             const uint32_t full = bars + 8 * slot;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive_expect_tx(full, two ? 2u * rs : rs);
             tma_load_2d(sdst, sb.mapL, sb.c0L, y1a, full);
-            tma_load_2d(sdst + 2 * sb.rbL, sb.mapC, sb.c0C, y1a >> K.csh, full);
+            if (!PACKED) tma_load_2d(sdst + 2 * sb.rbL, sb.mapC, sb.c0C, y1a >> K.csh, full);
             if (two) {
                 tma_load_2d(sdst + rs, sb.mapL, sb.c0L, y1b, full);
-                tma_load_2d(sdst + rs + 2 * sb.rbL, sb.mapC, sb.c0C, y1b >> K.csh, full);
+                if (!PACKED) tma_load_2d(sdst + rs + 2 * sb.rbL, sb.mapC, sb.c0C, y1b >> K.csh, full);
             }
         }
         ic.next(G);
@@ -185,7 +195,7 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
         uint32_t m_in = 0;
         {
             const AxisTap tb = axis_tap(tx0, F.fx);
-            const int originL = 8 * (((F.xbL + B * tb.i1) >> 4) << 1) - F.xbL;              // luma-row byte smem byte 0 stands for
+            const int originL = 8 * (((F.xbL + (PACKED ? 8 * (tb.i1 >> 1) : B * tb.i1)) >> 4) << 1) - F.xbL;  // luma-row byte smem byte 0 stands for
             const int originC = 8 * (((F.xbC + 2 * B * (tb.i1 >> 1)) >> 4) << 1) - F.xbC;  // same for the chroma row
             const int wm1 = F.w - 1;
             const uint32_t kU = (K.selU1 >> 8) & 7u;  // byte of U within a pair
@@ -206,7 +216,12 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
                     offL[p] = (oL >> 2) * 4;
                     offC[p] = (oC >> 2) * 4;
                     cfg[p] = (uint32_t)((oL & 3) * 8) | (uint32_t)((oC & 3) * 8) << 8;  // funnel shifts: luma in bits 0..4, chroma 8..12
-                    if (DEPTH == 1) {
+                    if (PACKED) {  // byte offsets of the two taps' groups; halfword 0 or 2 of a group is the pixel's Y
+                        offL[p] = 8 * (t.i1 >> 1) - originL;
+                        offC[p] = 8 * (x2 >> 1) - originL;
+                        selY2[p] = (t.i1 & 1) ? 0x0540u : 0x0100u;  // left tap:  bytes (4, 5) or (0, 1) of the group -> bytes 1, 2
+                        selU2[p] = (x2 & 1) ? 0x0540u : 0x0100u;    // right tap
+                    } else if (DEPTH == 1) {
                         selY2[p] = 0x4044u | (uint32_t)(x2 - t.i1) << 8;
                         selU2[p] = 0x4044u | (uint32_t)(2 * ((x2 >> 1) - (t.i1 >> 1)) + (int)kU) << 8;
                     } else {  // halfword 0 / 1 of the lined-up luma word; which of two chroma words holds the right tap's pair
@@ -236,7 +251,7 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
                 const AxisTap ta = axis_tap(y, fy), tb2 = axis_tap(st1 ? y + 1 : y, fy);
                 const float2 wy0 = make_float2(ta.w0, tb2.w0), wy1 = make_float2(ta.w1, tb2.w1);
                 const int y2a = min(ta.i1 + 1, hm1), y2b = min(tb2.i1 + 1, hm1);
-                const uint32_t rs = (uint32_t)(2 * rbL + 2 * rbC);
+                const uint32_t rs = (uint32_t)(2 * rbL + (PACKED ? 0 : 2 * rbC));
                 const uint32_t sdata = ring + (uint32_t)slot * slot_bytes + kSlotHeader;
                 const uint32_t r1 = st1 ? rs : 0u;  // a missing second row borrows the first one's taps (not stored)
                 // luma rows y1 / y2 and chroma rows (y1 >> 1) / (y2 >> 1) of both output rows
@@ -262,7 +277,24 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
                             return make_float2(__uint_as_float(__byte_perm(w0, 0u, sel)), __uint_as_float(__byte_perm(w1, 0u, sel)));
                         };
                         float2 p00[3], p10[3], p01[3], p11[3];  // taps (x1, y1), (x2, y1), (x1, y2), (x2, y2) as RGB x 2^-33
-                        if (DEPTH == 1) {
+                        if (PACKED) {
+                            // one 8-byte group per tap and row: {Y0 U | Y1 V}; sample -> bytes 1, 2 of a float word, the rest cleared
+                            constexpr uint32_t kKeep = 0x00ffc000u;
+                            auto tap = [&](uint32_t rowA, uint32_t rowB, int32_t off, uint32_t selY, float2 (&rgb)[3]) {
+                                const uint2 ga = lds64_tap(rowA + off), gb = lds64_tap(rowB + off);
+                                auto smp = [&](uint32_t sel) {
+                                    return make_float2(__uint_as_float(__byte_perm(ga.x, ga.y, sel) & kKeep),
+                                                       __uint_as_float(__byte_perm(gb.x, gb.y, sel) & kKeep));
+                                };
+                                yuv_to_rgb2(K, smp(selY), smp(0x0320u), smp(0x0760u), rgb);  // U: bytes 2, 3; V: bytes 6, 7
+                            };
+                            tap(LA0, LA1, offL[p], selY2[p], p00);
+                            tap(LA0, LA1, offC[p], selU2[p], p10);
+                            tap(LB0, LB1, offL[p], selY2[p], p01);
+                            tap(LB0, LB1, offC[p], selU2[p], p11);
+                            (void)sL;
+                            (void)sC;
+                        } else if (DEPTH == 1) {
                             const uint32_t selV1 = K.selV1, selU1 = K.selU1, selV2 = selU2[p] ^ 0x100u;
                             // staged words lined up on the left tap: luma [Y(x1) Y(x1+1) ..], chroma [pair(x1 >> 1) pair(+1)]
                             const uint32_t la0 = lineup(LA0 + offL[p], sL), lb0 = lineup(LB0 + offL[p], sL);
@@ -366,18 +398,23 @@ preproc_yuv_tma_kernel(const __grid_constant__ YuvParams K) {
 inline int yuv_rb_luma(int TW, float fx, int depth = 1) { return band_row_bytes(TW, fx, depth); }
 inline int yuv_rb_chroma(int TW, float fx, int depth = 1) { return band_row_bytes(TW, fx, depth) + 64; }
 inline int yuv_depth_of(int src_type) { return src_type == CVGS_P010 || src_type == CVGS_P210 ? 2 : 1; }
+// Y210: 4 bytes per pixel; a tap's 8-byte group can start one pixel before it and end one pixel after it
+inline int yuv_rb_packed(int TW, float fx) { return band_row_bytes(TW, fx, 4) + 64; }
 
 // Can a batch of NV12 / NV21 frames take this kernel, and with which geometry?
 inline bool yuv_tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int n_planes, int sm_count, TmaGeom& G) {
     if (!encode_tiled_fn()) return false;
-    if (P.src_type != CVGS_NV12 && P.src_type != CVGS_NV21 && P.src_type != CVGS_P010 && P.src_type != CVGS_P210) return false;
-    const int depth = yuv_depth_of(P.src_type);
+    if (P.src_type != CVGS_NV12 && P.src_type != CVGS_NV21 && P.src_type != CVGS_P010 && P.src_type != CVGS_P210 && P.src_type != CVGS_Y210)
+        return false;
+    const bool packed = P.src_type == CVGS_Y210;
+    const int depth = packed ? 4 : yuv_depth_of(P.src_type);  // bytes per pixel of the (luma) plane
     if (P.band_test || P.used != P.n_planes || used != n_planes || P.out.px_stride != 1 || P.out.planes || P.out.u8 || P.prog.special) return false;
     float fx_max = 0.f;
     for (int i = 0; i < used; ++i) {
         const DevCrop& c = crops[i];
         if ((c.w & 1) || (c.h & 1) || c.w < 2 || c.h < 2 || c.pitch % 16 != 0 || c.pitch < depth * c.w) return false;
         if (depth == 2 && (reinterpret_cast<uintptr_t>(c.data) & 3)) return false;  // chroma pairs are aligned words
+        if (packed && (reinterpret_cast<uintptr_t>(c.data) & 7)) return false;      // pixel pairs are aligned 8-byte groups
         if (!(c.fx > 0.f) || !(c.fy > 0.f) || !std::isfinite(c.fx) || !std::isfinite(c.fy)) return false;
         fx_max = std::max(fx_max, c.fx);
     }
@@ -395,19 +432,20 @@ inline bool yuv_tma_plan(const PreprocParams& P, const DevCrop* crops, int used,
     const long long total = static_cast<long long>(n_planes) * G.items_per_crop;
     if (total > 0x7fffffffLL) return false;
     G.total_items = static_cast<int32_t>(total);
-    G.slot_bytes = kSlotHeader + 2 * (2 * yuv_rb_luma(std::min(TW, P.W), fx_max, depth) + 2 * need(NPB));
+    G.slot_bytes = kSlotHeader + (packed ? 4 * yuv_rb_packed(std::min(TW, P.W), fx_max)
+                                         : 2 * (2 * yuv_rb_luma(std::min(TW, P.W), fx_max, depth) + 2 * need(NPB)));
     G.explicit_prescale = 0;
     G.prescale = kPreScale;
     G.pdl_wait = 1;
     return tma_plan_items(G, P.W, n_planes, sm_count, 1, 1, kMaxResident);
 }
 
-template <int CHAIN, int DEPTH = 1>
+template <int CHAIN, int DEPTH = 1, bool PACKED = false>
 inline int yuv_launch_instance(const YuvParams& K, int device, cudaStream_t stream) {
     static thread_local size_t attr_set[64] = {};
     const size_t smem = tma_smem_bytes(K.G);
     const int slot = device & 63;
-    auto kernel = preproc_yuv_tma_kernel<CHAIN, DEPTH>;
+    auto kernel = preproc_yuv_tma_kernel<CHAIN, DEPTH, PACKED>;
     if (smem > attr_set[slot]) {
         const size_t want = std::max<size_t>(smem, 112 * 1024);
         CVGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(want)));

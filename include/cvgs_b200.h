@@ -62,8 +62,8 @@ extern "C" {
  * fk::ConvertYUVToRGB<NV12, range, primaries, false, float3> in front of the resize (reference
  * fkl/.../image_processing/color_conversion.cuh:235-362; tests/resize/test_fused_resize.cu:73-76,141-143).  A crop
  * of this type is a whole frame {Y plane, width, height, pitch}; the pipeline sees float RGB.  Batches of even-sized
- * NV12 / NV21 / P010 / P210 frames in the common geometry (IGNORE_AR, every plane used, planar float tensor, pitch a
- * multiple of 16; 16-bit formats: base a multiple of 4) take the TMA-staged kernel (csrc/preproc_yuv_tma.cuh),
+ * Frames of every format below in the common geometry (IGNORE_AR, every plane used, planar float tensor, even sizes, pitch
+ * a multiple of 16; P010 / P210: base a multiple of 4, Y210: of 8) take the TMA-staged kernel (csrc/preproc_yuv_tma.cuh),
  * everything else the direct-gather kernel. */
 #define CVGS_NV12 0x1001
 /* The other fk::PixelFormat readers the reference can instantiate (color_conversion.cuh:89-98,296-345), same contract:

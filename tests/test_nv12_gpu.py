@@ -252,3 +252,46 @@ def test_tma_staged_kernel_takes_p010_and_p210(src_type, standard):
         assert lib.cvgs_b200_preproc_launch(crops, 1, 1, C.byref(p), None) != 0
     finally:
         lib.cvgs_b200_set_kernel_variant(prev)
+
+
+@pytest.mark.parametrize("standard", [0, 1, 2, 3])
+def test_tma_staged_kernel_takes_y210(standard):
+    """Packed Y210 frames through the TMA-staged kernel (PACKED instantiation; forced: variant 2): a tap is the 8-byte
+    group of its pixel pair, Y at halfword 0 or 2, U and V at halfwords 1 and 3, noise in the low six bits of every word.
+    Against the oracle, and for the matrices the reference harness holds against the reference's own kernel."""
+    lib = _abi.load()
+    src_type = _abi.CVGS_Y210
+    pitch = 2048
+    sizes = [(320, 240), (322, 242), (160, 120), (64, 36), (2, 2), (500, 300), (96, 400)]
+    frames = [_yuv_frame(190 * standard + i, src_type, w, h, pitch) for i, (w, h) in enumerate(sizes)]
+    prev = lib.cvgs_b200_set_kernel_variant(2)
+    try:
+        for dsize, ops in [((64, 128), OPS), ((400, 300), OPS), ((33, 7), [("mul", (0.5, 0.25, 2.0)), ("add", (1.0, 2.0, 3.0))]),
+                           ((224, 225), [])]:
+            ours = _ours(frames, sizes, pitch, dsize, standard, ops, src_type=src_type)
+            orc = _oracle(frames, sizes, pitch, dsize, standard, ops, src_type=src_type)
+            util.assert_bit_equal(ours, orc, f"Y210 standard {standard} dsize {dsize}: TMA-staged kernel vs oracle")
+            if standard in (0, 3) and ops is OPS and gpu_util.fkref_lib(16) is not None:
+                for i, (f, (w, h)) in enumerate(zip(frames, sizes)):
+                    ref = gpu_util.run_fkref_yuv(src_type, f, w, h, dsize, standard, MUL, SUB, DIV)
+                    util.assert_bit_equal(ours[i], ref, f"Y210 standard {standard} dsize {dsize} frame {i}: vs reference kernel")
+        # frames at the other 8-byte phase of a 16-byte line
+        n = 3
+        rows = 200
+        big = torch.from_numpy(np.random.default_rng(7).integers(0, 256, size=(n * rows * pitch + 64,), dtype=np.uint8)).cuda()
+        host = big.cpu().numpy()
+        crops, ocrops = (_abi.Crop * n)(), (_abi.Crop * n)()
+        for i in range(n):
+            off = i * rows * pitch + 8 * i
+            crops[i].data, crops[i].width, crops[i].height, crops[i].pitch = big.data_ptr() + off, 200, 120, pitch
+            ocrops[i].data, ocrops[i].width, ocrops[i].height, ocrops[i].pitch = host.ctypes.data + off, 200, 120, pitch
+        out = torch.full((n, 3, 60, 100), float("nan"), device="cuda")
+        want = np.full((n, 3, 60, 100), np.nan, dtype=np.float32)
+        p = util.make_pipeline((100, 60), OPS, out_ptr=out.data_ptr(), src_type=src_type, yuv_standard=standard)
+        po = util.make_pipeline((100, 60), OPS, out_ptr=want.ctypes.data, src_type=src_type, yuv_standard=standard)
+        _abi.check(lib.cvgs_b200_preproc_launch(crops, n, n, C.byref(p), None))
+        torch.cuda.synchronize()
+        assert util.oracle_lib().oracle_preproc(ocrops, n, n, C.byref(po), 0) == 0
+        util.assert_bit_equal(out.cpu().numpy(), want, "frames at the other 8-byte phase")
+    finally:
+        lib.cvgs_b200_set_kernel_variant(prev)
