@@ -509,7 +509,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         K.P = P;
         K.maps = nullptr;
         if (variant != 1 && P.src_type == CVGS_8UC3 && tma_plan(P, tt.c, used, n_planes, sms, parents != nullptr, items_per_warp(), K.G)) {
-            const int chain = scaled_program(P, K);
+            const int chain = scaled_program_for(P, K);
             const int pb = 3;
             const MemRange src = crops_range(tt.c, used, pb);  // before the TMA fields overwrite the pointers
             const double t2 = now_us();
@@ -531,7 +531,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
             }
             bool ok = true;
             // (one map per crop: the gray instantiation is not built for that table -- such batches take the direct kernel)
-            for (int i = 0; i < used && ok; ++i) ok = pb == 3 && chain != CH_GRAY && tma_prepare_crop(tt.c[i], K.G, P.W, i, &tt.m[i]) == CVGS_OK;
+            for (int i = 0; i < used && ok; ++i) ok = pb == 3 && !chain_needs_image_table(chain) && tma_prepare_crop(tt.c[i], K.G, P.W, i, &tt.m[i]) == CVGS_OK;
             const double t3 = now_us();
             if (ok) {
                 K.G.pdl_wait = overlap_needs_wait(stream, out_range(P), src) ? 1 : 0;
@@ -562,7 +562,7 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
         K.P = P;
         K.maps = nullptr;
         if (tma_plan(P, lt.c, used, n_planes, sms, true, items_per_warp(), K.G)) {
-            const int chain = scaled_program(P, K);
+            const int chain = scaled_program_for(P, K);
             const int pb = pixel_bytes_of(P.src_type);
             const MemRange src = crops_range(lt.c, used, pb);
             if (prepare_image_maps(lt.c, parents, used, K.G, P.W, lt.m, kTmaImageMaps, pb) >= 0) {
@@ -586,7 +586,9 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
     int chain = CH_GENERIC;
     size_t map_bytes = 0;
     if (use_tma) {
-        chain = scaled_program(P, K);
+        chain = scaled_program_for(P, K);
+        if (chain_needs_image_table(chain) && n_replicas > 0)  // no peer-store instantiation of these chains
+            return fail(CVGS_ERR_NOT_SUPPORTED, "replicated launches take chains that keep the channel count");
         CUtensorMap* hm = r.maps_h(slot);
         // maps sit in front of the crops in the slot; image mode needs only a few of them
         const int pb = pixel_bytes_of(P.src_type);

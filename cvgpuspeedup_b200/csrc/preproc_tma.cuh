@@ -105,6 +105,8 @@ struct TmaParams {
     PreprocParams P;         // P.prog = unscaled chain (background values), P.crops = device table or nullptr
     DevProgram prog_img;     // chain for interpolated values (2^33 folded into its first op)
     float zh[4], zl[4];      // CH_FMA_DIV: 1/d = zh + zl per source channel (div_const.cpp)
+    float alpha;             // CH_*_ALPHA: value of the alpha plane
+    long long alpha_delta;   //             floats from the plane of source channel 0 to the alpha plane
     TmaGeom G;
     const CUtensorMap* maps; // device table (nullptr when the maps ride in the kernel parameters)
     // PEER instantiation (cvgs_b200_preproc_launch_replicated): every value is stored n_dest times, at
@@ -333,7 +335,11 @@ __device__ __forceinline__ BandOrigin band_origin(const PreprocParams& P, const 
 // ------------------------------------------------------------------------------------------------
 // CH_GRAY: cvtColor<*2GRAY> first (registers -> one luminance, rounded to an integer like the reference's RGB2Gray<I, float>),
 // then any per-channel ops on that one value; one plane is stored.
-enum ChainKind : int { CH_GENERIC = 0, CH_FMA_DIV = 1, CH_GRAY = 2 };
+// CH_*_ALPHA: cvtColor<*2*A> in a chain on a 3-channel source (a fourth, constant channel): the chain runs on the three
+// source channels as CH_FMA_DIV / CH_GENERIC, the alpha plane receives the value the host computed by running the
+// constant through the same ops (TmaParams::alpha).
+enum ChainKind : int { CH_GENERIC = 0, CH_FMA_DIV = 1, CH_GRAY = 2, CH_FMA_DIV_ALPHA = 3, CH_GENERIC_ALPHA = 4 };
+inline bool chain_needs_image_table(int chain) { return chain >= CH_GRAY; }  // instantiated for the image-mode tables only
 
 // x / d for both halves with 1/d = zh + zl (div_const.cpp): FMUL2 + FFMA2.
 __device__ __forceinline__ float2 div_by_const2(float2 x, float zh, float zl) {
@@ -549,8 +555,10 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
     asm volatile("" : "+r"(recs));
 
     // chain constants of the specialised shape v = fma(v, ca, cb) / cd  (source-channel order)
+    constexpr bool kFmaDiv = CHAIN == CH_FMA_DIV || CHAIN == CH_FMA_DIV_ALPHA;
+    constexpr bool kAlpha = CHAIN == CH_FMA_DIV_ALPHA || CHAIN == CH_GENERIC_ALPHA;
     float ca[NC], cb[NC], zh[NC], zl[NC];
-    if (CHAIN == CH_FMA_DIV) {
+    if (kFmaDiv) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             ca[c] = K.prog_img.ops[0].a[c];
@@ -823,7 +831,7 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                         if (!GEN || im0 || im1) {
                             gather_pair<NC, DEPTH, S16>(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p],
                                         (m_edge & (1u << p)) != 0, wxa[p], wxb[p], wy0, wy1, v);
-                            if (CHAIN == CH_FMA_DIV) {
+                            if (kFmaDiv) {
 #pragma unroll
                                 for (int c = 0; c < NC; ++c) {
                                     v[c] = __ffma2_rn(v[c], make_float2(ca[c], ca[c]), make_float2(cb[c], cb[c]));
@@ -911,6 +919,10 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                             for (int c = 0; c < (CHAIN == CH_GRAY ? 1 : NC); ++c) st_cs_f32(sp[c] + q, v[c].x);
 #pragma unroll
                             for (int c = 0; c < (CHAIN == CH_GRAY ? 1 : NC); ++c) st_cs_f32_if(st1, tp[c] + q, v[c].y);
+                            if (kAlpha) {  // the constant fourth plane
+                                st_cs_f32(sp[0] + K.alpha_delta + q, K.alpha);
+                                st_cs_f32_if(st1, tp[0] + K.alpha_delta + q, K.alpha);
+                            }
                             }
                         }
                     }
@@ -1021,6 +1033,42 @@ inline bool gray_program(const PreprocParams& P) {
     return !P.band_test && P.used == P.n_planes && P.out.px_stride == 1 && !P.out.planes && !P.out.u8;
 }
 
+// cvtColor<*2*A> (AddOpaqueAlpha) in a chain on a CV_8UC3 source, in the geometry the CH_*_ALPHA instantiations are built
+// for: the program starts with the hoisted DOP_SET of register 3 (preproc_host.hpp: build_program), everything behind it is
+// per-channel arithmetic, four planes of a float tensor are written.
+inline bool alpha_program(const PreprocParams& P) {
+    const DevProgram& g = P.prog;
+    if (P.src_type != CVGS_8UC3 || !g.special || g.nc_out != 4 || g.nregs != 4 || g.n_ops < 1 || g.ops[0].kind != DOP_SET) return false;
+    if (g.ops[0].b[0] != 0.f || g.ops[0].b[1] != 0.f || g.ops[0].b[2] != 0.f || g.ops[0].b[3] == 0.f) return false;
+    for (int r = 0; r < 4; ++r)
+        if (g.dst_chan[r] < 0) return false;
+    for (int i = 1; i < g.n_ops; ++i)
+        if (g.ops[i].kind != DOP_FMA && g.ops[i].kind != DOP_MUL && g.ops[i].kind != DOP_ADD && g.ops[i].kind != DOP_DIV) return false;
+    return !P.band_test && P.used == P.n_planes && P.out.px_stride == 1 && !P.out.planes && !P.out.u8;
+}
+// The program of an alpha_program without its DOP_SET (the three source channels' chain) and the alpha register run through
+// the ops on the host: the same IEEE single-precision operations the direct-gather kernel applies to it per pixel.
+inline float alpha_strip(const PreprocParams& P, PreprocParams& Q) {
+    Q = P;
+    volatile float a = P.prog.ops[0].a[3];
+    for (int i = 1; i < P.prog.n_ops; ++i) {
+        const DevOp& op = P.prog.ops[i];
+        const float x = a;
+        switch (op.kind) {
+            case DOP_FMA: a = std::fmaf(x, op.a[3], op.b[3]); break;
+            case DOP_MUL: a = x * op.a[3]; break;
+            case DOP_ADD: a = x + op.a[3]; break;
+            default: a = x / op.a[3]; break;
+        }
+        Q.prog.ops[i - 1] = op;
+    }
+    Q.prog.n_ops = P.prog.n_ops - 1;
+    Q.prog.special = 0;
+    Q.prog.nc_out = 3;
+    Q.prog.nregs = 3;
+    return a;
+}
+
 // Second half of a launch plan, shared by the kernels built on the item / ring scheme: given the band width (G.NPB,
 // G.tiles_x, G.HP, G.items_per_crop, G.total_items) and the bytes of a staging slot (G.slot_bytes), choose the ring depth,
 // the CTAs per SM and the grid, and cut the items into per-warp ranges of equal cost.
@@ -1086,7 +1134,7 @@ inline bool tma_plan(const PreprocParams& P, const DevCrop* crops, int used, int
     if (P.out.u8 && (pb != 3 || P.prog.nc_out != 3)) return false;
     // everything but CV_8UC3: built for the common geometry only (IGNORE_AR, every plane used, planar float tensors)
     if (pb != 3 && (P.band_test || P.used != P.n_planes || P.out.px_stride != 1 || P.out.planes || P.out.u8)) return false;
-    if (P.prog.special && !gray_program(P)) return false;  // other conversions that change the channel count: direct-gather kernel
+    if (P.prog.special && !gray_program(P) && !alpha_program(P)) return false;  // other conversions that change the channel count: direct-gather kernel
     if (P.out.row_stride != static_cast<long long>(P.W) * P.out.px_stride) return false;  // padded packed rows: direct-gather kernel
     float fx_max = 0.f;
     for (int i = 0; i < used; ++i) {
@@ -1260,6 +1308,19 @@ inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
         K.G.explicit_prescale = 0;
     }
     return CH_GENERIC;
+}
+
+// scaled_program for every chain the kernel takes: a chain that adds an alpha channel is the three-channel chain behind
+// the DOP_SET plus the constant plane.
+inline int scaled_program_for(const PreprocParams& P, TmaParams& K) {
+    K.alpha = 0.f;
+    K.alpha_delta = 0;
+    if (!alpha_program(P)) return scaled_program(P, K);
+    PreprocParams Q;
+    K.alpha = alpha_strip(P, Q);
+    K.alpha_delta = (static_cast<long long>(P.prog.dst_chan[3]) - P.prog.dst_chan[0]) * P.out.c_stride;
+    const int chain = scaled_program(Q, K);
+    return chain == CH_FMA_DIV ? CH_FMA_DIV_ALPHA : CH_GENERIC_ALPHA;
 }
 
 inline int tma_encode(CUtensorMap* map, uintptr_t base16, long long row_bytes, int rows, long long pitch, int rb) {
@@ -1498,11 +1559,15 @@ inline int tma_launch_kernel(const TmaParams& K, const Table& T, int chain, int 
             return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel: this pixel type is not built for this descriptor table");
         }
     }
-    if (chain == CH_GRAY) {
-        if constexpr (std::is_same<Table, TmaMultiTable>::value || std::is_same<Table, TmaParamTable>::value)
-            return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel: gray conversion is not built for this descriptor table");
-        else
-            return tma_launch_instance<Table, CH_GRAY, false>(K, T, device, stream);
+    if (chain_needs_image_table(chain)) {
+        if constexpr (std::is_same<Table, TmaMultiTable>::value || std::is_same<Table, TmaParamTable>::value) {
+            return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel: gray / alpha conversions are not built for this descriptor table");
+        } else {
+            if (chain == CH_GRAY) return tma_launch_instance<Table, CH_GRAY, false>(K, T, device, stream);
+            if (!fast) return fail(CVGS_ERR_NOT_SUPPORTED, "TMA-staged kernel: alpha conversions take the common geometry only");
+            return chain == CH_FMA_DIV_ALPHA ? tma_launch_instance<Table, CH_FMA_DIV_ALPHA, false>(K, T, device, stream)
+                                             : tma_launch_instance<Table, CH_GENERIC_ALPHA, false>(K, T, device, stream);
+        }
     }
     // packed 8-bit output of the common geometry (a plain cv::cuda::resize on CV_8UC3 is this): its own fast instantiation
     if (!P.band_test && P.used == P.n_planes && P.out.u8 && P.nc == 3 && !std::is_same<Table, TmaParamTable>::value) {

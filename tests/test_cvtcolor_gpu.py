@@ -176,3 +176,35 @@ def test_tma_staged_kernel_takes_gray_chains(n, ops):
             lib.cvgs_b200_set_kernel_variant(prev)
         torch.cuda.synchronize()
         util.assert_bit_equal(out.cpu().numpy(), util.run_oracle(w.image, w.rects, (64, 128), ops, **kw), f"gray chain {ops} {kw}")
+
+
+@pytest.mark.parametrize("n,parents", [(20, True), (100, True), (300, True), (300, False)])
+@pytest.mark.parametrize("ops", [
+    [("add_alpha", (255.0,))],                                                                          # RGB2RGBA
+    [("reorder", (2, 1, 0)), ("add_alpha", (255.0,)), ("mul", (1 / 255.0,) * 4), ("sub", (0.485, 0.456, 0.406, 0.5)),
+     ("div", (0.229, 0.224, 0.225, 0.25))],                                                             # BGR2RGBA + normalisation
+    [("mul", MUL[:3]), ("add_alpha", (1.0,)), ("sub", SUB)],                                            # the FMA spans the conversion
+    [("add_alpha", (7.0,)), ("reorder", (3, 0, 1, 2)), ("mul", MUL), ("add", SUB), ("mul", (2.0, 0.5, 1.5, 3.0))],  # alpha first, generic chain
+])
+def test_tma_staged_kernel_takes_alpha_chains(n, parents, ops):
+    """cvtColor<*2*A> in the chain of a CV_8UC3 source, four float planes out: the TMA-staged kernel's CH_*_ALPHA
+    instantiations (forced: variant 2 fails instead of falling back) -- the chain on the three source channels, the alpha plane
+    filled with the value the host computed by running the constant through the same ops.  Bit-equal to the oracle in both
+    floating-point contracts, NCHW and CNHW."""
+    import ctypes as C
+    lib = _abi.load()
+    w = util.workload_c2(seed=60 + n, n=n, frame=(960, 540), pitch=2880)
+    d_img = torch.from_numpy(w.image).cuda()
+    for kw in ({}, dict(fp_contract=_abi.FP_SEPARATE), dict(layout=_abi.OUT_CNHW)):
+        shape = (4, n, 128, 64) if kw.get("layout") == _abi.OUT_CNHW else (n, 4, 128, 64)
+        out = torch.full(shape, float("nan"), device="cuda")
+        p = util.make_pipeline((64, 128), ops, out_ptr=out.data_ptr(), **kw)
+        crops = util.host_crops(w.image, w.rects, base_ptr=d_img.data_ptr())
+        par = util.host_parents(w.image, w.width, w.height, n, base_ptr=d_img.data_ptr()) if parents else None
+        prev = lib.cvgs_b200_set_kernel_variant(2)
+        try:
+            _abi.check(lib.cvgs_b200_preproc_launch_ex(crops, par, n, n, C.byref(p), None))
+        finally:
+            lib.cvgs_b200_set_kernel_variant(prev)
+        torch.cuda.synchronize()
+        util.assert_bit_equal(out.cpu().numpy(), util.run_oracle(w.image, w.rects, (64, 128), ops, **kw), f"alpha chain {ops} {kw}")
