@@ -254,6 +254,13 @@ __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcon
 __device__ __forceinline__ float u8_scaled(uint32_t w, uint32_t k) {
     return __uint_as_float(__byte_perm(w, 0u, 0x4044u | (k << 8)));
 }
+// SaturateCast<float, uchar> in one conversion: round to nearest even, clamp to [0, 255], NaN -> 0 (what __float2uint_rn
+// followed by min(., 255) gives, saturate.cuh:127-147)
+__device__ __forceinline__ uint32_t f32_to_u8_sat(float v) {
+    uint32_t u;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return u;
+}
 // halfword k of w as the float h * 2^-141: placed at mantissa bits 8..23, any 24-bit pattern X is exactly X * 2^-149
 __device__ __forceinline__ float u16_scaled(uint32_t w, uint32_t k) {
     return __uint_as_float(__byte_perm(w, 0u, k ? 0x4324u : 0x4104u));
@@ -776,10 +783,14 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             }
         }
         // 8-bit packed output (general instantiation only): byte address of this lane's first pixel in row 2*jp
-        uint8_t* u8row = nullptr;
-        if ((GEN || U8) && P.out.u8)
-            u8row = reinterpret_cast<uint8_t*>(P.out.base) + (long long)z * P.out.z_stride + (long long)(2 * cc.jp) * P.out.row_pitch +
-                    (long long)NC * (tx0 + lane);
+        uint8_t* u8c[NC];  // per source channel: its byte in this lane's first pixel of row 2*jp
+        const long long u8pitch = P.out.row_pitch;
+        if ((GEN || U8) && P.out.u8) {
+            uint8_t* const u8row = reinterpret_cast<uint8_t*>(P.out.base) + (long long)z * P.out.z_stride + (long long)(2 * cc.jp) * u8pitch +
+                                   (long long)NC * (tx0 + lane);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) u8c[c] = u8row + P.prog.dst_chan[c];
+        }
         if (GEN && P.out.planes) {  // per-plane destinations (fk::SplitWrite): own pointer and pitch per channel
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
@@ -889,15 +900,22 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                             }
                         }
                         if ((GEN || U8) && P.out.u8) {  // SaturateCast<float, uchar> (or fk::Cast) + packed pixels, NC bytes each
-                            uint8_t* ub = u8row + 32 * NC * p;
-                            uint8_t* ub1 = ub + P.out.row_pitch;
+                            // the byte of source channel c sits at u8c[c] (= row + dst_chan[c]); which cast is a uniform branch,
+                            // not a select over both conversions
+                            if (P.out.u8 == 2) {
 #pragma unroll
-                            for (int c = 0; c < NC; ++c) {
-                                const int d = P.prog.dst_chan[c];
-                                const uint32_t a = P.out.u8 == 2 ? __float2uint_rz(v[c].x) : (uint32_t)round_sat_u8(v[c].x);
-                                const uint32_t b = P.out.u8 == 2 ? __float2uint_rz(v[c].y) : (uint32_t)round_sat_u8(v[c].y);
-                                ub[d] = (uint8_t)a;
-                                if (st1) ub1[d] = (uint8_t)b;
+                                for (int c = 0; c < NC; ++c) {
+                                    uint8_t* ub = u8c[c] + 32 * NC * p;
+                                    *ub = (uint8_t)__float2uint_rz(v[c].x);
+                                    if (st1) ub[u8pitch] = (uint8_t)__float2uint_rz(v[c].y);
+                                }
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < NC; ++c) {
+                                    uint8_t* ub = u8c[c] + 32 * NC * p;
+                                    *ub = (uint8_t)f32_to_u8_sat(v[c].x);
+                                    if (st1) ub[u8pitch] = (uint8_t)f32_to_u8_sat(v[c].y);
+                                }
                             }
                         } else if (PEER) {
                             const int q = 32 * p * pxs;
@@ -930,7 +948,10 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             }
 #pragma unroll
             for (int c = 0; c < NC; ++c) sp[c] += 2 * (GEN ? rs[c] : (long long)row_step);
-            if ((GEN || U8) && P.out.u8) u8row += 2 * P.out.row_pitch;
+            if ((GEN || U8) && P.out.u8) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) u8c[c] += 2 * u8pitch;
+            }
 
             // every lane has consumed its taps of this slot (their values fed the stores above): refill it
             __syncwarp();
@@ -1248,7 +1269,7 @@ inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
         K.G.explicit_prescale = 0;
         return CH_GRAY;
     }
-    if (P.prog.round_u8 || P.prog.n_ops == 0) return CH_GENERIC;
+    if (P.prog.round_u8) return CH_GENERIC;
     auto moderate = [](float a) { return a == 0.f || (std::fabs(a) > 1e-20f && std::fabs(a) < 1e20f); };
     const int nc = P.nc;
     auto all_moderate = [&](const float* a, bool nonzero) {
@@ -1260,14 +1281,22 @@ inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
     const int n = K.prog_img.n_ops;
     // canonical shape  v = fma(v, a, b) / d : [MUL|FMA|ADD] DIV  or  DIV alone.  MUL(a) == FMA(a, -0) and
     // ADD(b) == FMA(1, b) bit for bit (x + -0 == x for every x; x * 1 is exact).
-    const bool first_lin = ops[0].kind == DOP_MUL || ops[0].kind == DOP_FMA || ops[0].kind == DOP_ADD;
-    if ((n == 2 && first_lin && ops[1].kind == DOP_DIV) || (n == 1 && ops[0].kind == DOP_DIV)) {
+    // No op at all and a lone [MUL|FMA|ADD] are the same shape with a division by 1 (zh = 1, zl = 0: fma(x, 1, x * 0) == x bit
+    // for bit, and no -0 can reach it): a plain resize and convertTo-with-scale chains then run on the specialised instantiation
+    // instead of the interpreter (whose code -- every op kind in every column of every band shape -- is three times as long).
+    const bool first_lin = n >= 1 && (ops[0].kind == DOP_MUL || ops[0].kind == DOP_FMA || ops[0].kind == DOP_ADD);
+    const bool lin_only = n == 0 || (n == 1 && first_lin);
+    if (lin_only || (n == 2 && first_lin && ops[1].kind == DOP_DIV) || (n == 1 && ops[0].kind == DOP_DIV)) {
         DevOp lin{};
         lin.kind = DOP_FMA;
-        const DevOp div = ops[n - 1];
+        DevOp div{};
+        div.kind = DOP_DIV;
+        for (int c = 0; c < 4; ++c) div.a[c] = 1.0f;
+        if (!lin_only) div = ops[n - 1];
+        const bool has_lin = first_lin;
         for (int c = 0; c < nc; ++c) {
-            lin.a[c] = n == 1 ? 1.0f : (ops[0].kind == DOP_ADD ? 1.0f : ops[0].a[c]);
-            lin.b[c] = n == 1 ? -0.0f : (ops[0].kind == DOP_MUL ? -0.0f : (ops[0].kind == DOP_ADD ? ops[0].a[c] : ops[0].b[c]));
+            lin.a[c] = !has_lin ? 1.0f : (ops[0].kind == DOP_ADD ? 1.0f : ops[0].a[c]);
+            lin.b[c] = !has_lin ? -0.0f : (ops[0].kind == DOP_MUL ? -0.0f : (ops[0].kind == DOP_ADD ? ops[0].a[c] : ops[0].b[c]));
         }
         // The two-operation division is proven for normal numerators (div_const.cpp).  With 2^-24 <= |a|, |b|, |d|
         // <= 2^24 (b may be zero) a non-zero fma(x, a, b) of an interpolated x in {0} U [2^-46, 255] has magnitude
