@@ -146,3 +146,49 @@ def test_random_source_types_chains_and_outputs(seed):
         assert np.array_equal(got.cpu().numpy(), want), what
     else:
         util.assert_bit_equal(got.cpu().numpy(), want, what)
+
+
+@pytest.mark.parametrize("seed", range(36 + _EXTRA))
+def test_random_common_geometry_every_source_type(seed):
+    """The geometry the TMA-staged instantiations of the wider pixel types are built for (IGNORE_AR, every plane used,
+    planar float tensors or -- CV_8UC3 -- packed 8-bit pixels): every source type, chains with and without the alpha / gray
+    conversions, image bases at random aligned offsets, with and without parent images, small and large batches.  The
+    automatic kernel choice and the direct-gather kernel against the oracle."""
+    rng = np.random.default_rng(9000 + seed)
+    src_type = SRC_TYPES[seed % len(SRC_TYPES)]
+    px, nc = util.px_bytes_of(src_type), util.channels_of(src_type)
+    fw, fh = int(rng.integers(20, 500)), int(rng.integers(20, 300))
+    pitch = (px * fw + 15) // 16 * 16 + 16 * int(rng.integers(0, 3))
+    shift = 8 * int(rng.integers(0, 2)) if seed % 2 else 0
+    back = rng.integers(0, 256, size=fh * pitch + 64, dtype=np.uint8)
+    img = back[shift:shift + fh * pitch].reshape(fh, pitch)
+    d_back = torch.from_numpy(back).cuda()
+    d_img = d_back[shift:shift + fh * pitch].view(fh, pitch)
+    n = int(rng.integers(1, 60)) if seed % 3 else int(rng.integers(65, 300))
+    rects = []
+    for _ in range(n):
+        w, h = int(rng.integers(1, fw + 1)), int(rng.integers(1, fh + 1))
+        rects.append((int(rng.integers(0, fw - w + 1)), int(rng.integers(0, fh - h + 1)), w, h))
+    dsize = (int(rng.integers(1, 260)), int(rng.integers(1, 160)))
+    if nc == 3 and seed % 4 == 1:   # alpha in the chain
+        tail = [[], [("mul", (0.5, 0.25, 2.0, 1.5))], [("mul", (1 / 255.0,) * 4), ("sub", (0.4, 0.5, 0.6, 0.7)), ("div", (0.2, 0.3, 0.4, 0.5))],
+                [("add", (1.0, 2.0, 3.0, 4.0)), ("mul", (2.0, 3.0, 4.0, 5.0)), ("sub", (1.0, 1.0, 1.0, 1.0))]][int(rng.integers(0, 4))]
+        ops = [("reorder", tuple(int(v) for v in rng.permutation(3))), ("add_alpha", (float(rng.choice([255.0, 1.0])),))] + tail
+    elif nc == 3 and seed % 4 == 3:  # gray first
+        ops = [("gray", (int(rng.integers(0, 2)),))] + [[], [("mul", (1 / 255.0,))], [("sub", (3.0,)), ("div", (7.0,))]][int(rng.integers(0, 3))]
+    else:
+        ops = [(k, tuple(v[:nc]) if k != "reorder" else tuple(int(x) for x in rng.permutation(nc)))
+               for (k, v) in [[], [("mul", (0.5, 0.25, 2.0, 1.5))], [("mul", (0.3,) * 4), ("sub", (1.0, 4.0, 3.2, 0.5)), ("div", (3.2, 0.6, 11.8, 2.0))],
+                              [("reorder", ()), ("add", (1.5, -2.5, 3.5, 0.5)), ("mul", (2.0, 3.0, -4.0, 1.0)), ("add", (0.1, 0.2, 0.3, 0.4))],
+                              [("sub", (127.5,) * 4), ("div", (127.5,) * 4)]][int(rng.integers(0, 5))]]
+    kw = dict(src_type=src_type, layout=int(rng.choice([_abi.OUT_NCHW, _abi.OUT_CNHW])))
+    if rng.random() < 0.25:
+        kw.update(fp_contract=_abi.FP_SEPARATE)
+    if rng.random() < 0.2:
+        kw.update(interp_mode=_abi.INTERP_ROUND_U8)
+    want = util.run_oracle(img, rects, dsize, ops, **kw)
+    parents = (fw, fh) if src_type == _abi.CVGS_8UC3 or seed % 2 == 0 else None
+    for variant in (0, 1):
+        got = gpu_util.run_cvgs(img, rects, dsize, ops, variant=variant, d_image=d_img, parents=parents if variant == 0 else None, **kw)
+        util.assert_bit_equal(got, want, f"seed {seed} src {src_type} variant {variant} frame {fw}x{fh} pitch {pitch} shift {shift} "
+                                         f"n {n} dsize {dsize} ops {ops} {kw}")
