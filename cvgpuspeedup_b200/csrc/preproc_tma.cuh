@@ -43,7 +43,10 @@ constexpr int kTmaParamCrops = 64;      // crops (descriptor + tensor map) that 
 constexpr int kWarps = 4;               // warps per CTA, each with its own slot ring
 constexpr int kTmaThreads = kWarps * 32;
 constexpr int kMaxSlots = 4;            // slots per warp
-constexpr int kMaxResident = 5;         // CTAs per SM the kernel is compiled for (<= 102 registers per thread)
+#ifndef CVGS_MAX_RESIDENT  // diagnostic builds (scripts/diag_build.sh): 4 lets the compiler use 128 registers
+#define CVGS_MAX_RESIDENT 5
+#endif
+constexpr int kMaxResident = CVGS_MAX_RESIDENT;  // CTAs per SM the kernel is compiled for (5: <= 102 registers per thread)
 constexpr int kMaxNP = 4;               // 32-column groups per band: a band is at most 128 output columns
 constexpr int kSlotHeader = 128;        // per slot: room for the w[-1] over-read in front of the staged rows
 constexpr int kRingPad = 128;           // bytes behind the last slot (w[+1] over-read)
