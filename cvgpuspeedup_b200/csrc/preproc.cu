@@ -489,7 +489,9 @@ static int preproc_launch_impl(const cvgs_crop_t* crops, const cvgs_parent_t* pa
     // CV_8UC4 batches the TMA-staged kernel can take go through the 256-crop table or the descriptor ring (the
     // instantiations built for four channels, tma_launch_kernel); everything else of a small batch is decided here
     bool small_batch = used <= kTmaParamCrops && !planes_out && n_replicas == 0;
-    if (small_batch && P.src_type != CVGS_8UC3 && variant != 1) {
+    // (so do gray / alpha chains on crops without a parent image: their instantiations exist for the image-mode tables and
+    // the descriptor ring, not for one-map-per-crop parameter tables)
+    if (small_batch && variant != 1 && (P.src_type != CVGS_8UC3 || (!parents && (gray_program(P) || alpha_program(P))))) {
         DevCrop probe[kTmaParamCrops];
         bool ok = true;
         for (int i = 0; i < used && ok; ++i) ok = fill_crop(crops[i], *pipe, i, probe[i]) == CVGS_OK;

@@ -150,13 +150,13 @@ def test_unused_planes_take_the_converted_default():
     assert got0.shape == (2, 1, 12, 16) and (got0 == 100.0).all()
 
 
-@pytest.mark.parametrize("n", [20, 100, 300])
+@pytest.mark.parametrize("n,parents", [(20, True), (100, True), (300, True), (20, False), (300, False)])
 @pytest.mark.parametrize("ops", [
     [("gray", (1,))],                                                            # RGB2GRAY
     [("reorder", (2, 1, 0)), ("gray", (0,)), ("mul", (1 / 255.0,))],             # BGR2GRAY + scale
     [("gray", (1,)), ("mul", (0.5,)), ("sub", (3.0,)), ("div", (7.0,))],         # RGB2GRAY + a whole chain on the one channel
 ])
-def test_tma_staged_kernel_takes_gray_chains(n, ops):
+def test_tma_staged_kernel_takes_gray_chains(n, parents, ops):
     """cvtColor<*2GRAY> first in the chain, one float plane out, crops with their parent frame named: the TMA-staged
     kernel's CH_GRAY instantiation (forced: variant 2 fails instead of falling back), bit-equal to the oracle in both
     floating-point contracts."""
@@ -168,7 +168,7 @@ def test_tma_staged_kernel_takes_gray_chains(n, ops):
         out = torch.full((n, 1, 128, 64), float("nan"), device="cuda")
         p = util.make_pipeline((64, 128), ops, out_ptr=out.data_ptr(), **kw)
         crops = util.host_crops(w.image, w.rects, base_ptr=d_img.data_ptr())
-        par = util.host_parents(w.image, w.width, w.height, n, base_ptr=d_img.data_ptr())
+        par = util.host_parents(w.image, w.width, w.height, n, base_ptr=d_img.data_ptr()) if parents else None
         prev = lib.cvgs_b200_set_kernel_variant(2)
         try:
             _abi.check(lib.cvgs_b200_preproc_launch_ex(crops, par, n, n, C.byref(p), None))
@@ -178,7 +178,7 @@ def test_tma_staged_kernel_takes_gray_chains(n, ops):
         util.assert_bit_equal(out.cpu().numpy(), util.run_oracle(w.image, w.rects, (64, 128), ops, **kw), f"gray chain {ops} {kw}")
 
 
-@pytest.mark.parametrize("n,parents", [(20, True), (100, True), (300, True), (300, False)])
+@pytest.mark.parametrize("n,parents", [(20, True), (100, True), (300, True), (300, False), (20, False), (64, False)])
 @pytest.mark.parametrize("ops", [
     [("add_alpha", (255.0,))],                                                                          # RGB2RGBA
     [("reorder", (2, 1, 0)), ("add_alpha", (255.0,)), ("mul", (1 / 255.0,) * 4), ("sub", (0.485, 0.456, 0.406, 0.5)),
