@@ -108,6 +108,14 @@ struct TmaParams {
     PreprocParams P;         // P.prog = unscaled chain (background values), P.crops = device table or nullptr
     DevProgram prog_img;     // chain for interpolated values (2^33 folded into its first op)
     float zh[4], zl[4];      // CH_FMA_DIV: 1/d = zh + zl per source channel (div_const.cpp)
+    // CH_GRAY (gray_setup): PRMT selectors that fetch the conversion's first / second / third operand channel from a pixel
+    // word (the gather then delivers v[0..2] in operand order: no selects in the loop), their coefficients x 2^33, whether
+    // the products are rounded on their own (CVGS_FP_SEPARATE), and the ops behind the conversion in the canonical form
+    // g = fma(g, ga, gb) / d (two-operation division; gmode 2) or left to the interpreter (gmode 3)
+    uint32_t gsel[3];
+    float gk[3];
+    int32_t gsep, gmode;
+    float ga, gb, gzh, gzl;
     float alpha;             // CH_*_ALPHA: value of the alpha plane
     long long alpha_delta;   //             floats from the plane of source channel 0 to the alpha plane
     TmaGeom G;
@@ -402,9 +410,11 @@ struct ItemCursor {
 // like an unsigned one, and 32768 * 2^-141 = 2^-126 is subtracted again: exact, all values are multiples of 2^-141 below 2^-125.
 // DEPTH = 2 (CV_16UC3 / CV_16UC4): halfword samples; 6-byte pixels start on even bytes (one funnel shift by 0 or 16 bits
 // lines three words up on halfword pairs), 8-byte pixels are two aligned words.
-template <int NC, int DEPTH, bool S16 = false>
+// PERM (CH_GRAY): v[c] is the channel PRMT selector csel[c] fetches instead of channel c.
+template <int NC, int DEPTH, bool S16 = false, bool PERM = false>
 __device__ __forceinline__ void gather_pair(uint32_t A0, uint32_t B0, uint32_t A1, uint32_t B1, int shl, int shr, bool edge,
-                                            float wx0, float wx1, float2 wy0, float2 wy1, float2 (&v)[NC]) {
+                                            float wx0, float wx1, float2 wy0, float2 wy1, float2 (&v)[NC],
+                                            const uint32_t* csel = nullptr) {
     const float2 w00 = __fmul2_rn(make_float2(wx0, wx0), wy0), w10 = __fmul2_rn(make_float2(wx1, wx1), wy0);
     const float2 w01 = __fmul2_rn(make_float2(wx0, wx0), wy1), w11 = __fmul2_rn(make_float2(wx1, wx1), wy1);
     if constexpr (DEPTH == 2) {
@@ -468,10 +478,11 @@ __device__ __forceinline__ void gather_pair(uint32_t A0, uint32_t B0, uint32_t A
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        float2 t = __fmul2_rn(make_float2(u8_scaled(ar0, c), u8_scaled(ar1, c)), w10);
-        t = __ffma2_rn(make_float2(u8_scaled(al0, c), u8_scaled(al1, c)), w00, t);
-        t = __ffma2_rn(make_float2(u8_scaled(bl0, c), u8_scaled(bl1, c)), w01, t);
-        v[c] = __ffma2_rn(make_float2(u8_scaled(br0, c), u8_scaled(br1, c)), w11, t);
+        auto smp = [&](uint32_t w) { return PERM ? __uint_as_float(__byte_perm(w, 0u, csel[c])) : u8_scaled(w, c); };
+        float2 t = __fmul2_rn(make_float2(smp(ar0), smp(ar1)), w10);
+        t = __ffma2_rn(make_float2(smp(al0), smp(al1)), w00, t);
+        t = __ffma2_rn(make_float2(smp(bl0), smp(bl1)), w01, t);
+        v[c] = __ffma2_rn(make_float2(smp(br0), smp(br1)), w11, t);
     }
 }
 
@@ -575,6 +586,15 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
             cb[c] = K.prog_img.ops[0].b[c];
             zh[c] = K.zh[c];
             zl[c] = K.zl[c];
+        }
+    }
+    uint32_t gsel[3] = {0u, 0u, 0u};
+    float gk[3] = {0.f, 0.f, 0.f};
+    if (CHAIN == CH_GRAY) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            gsel[c] = K.gsel[c];
+            gk[c] = K.gk[c];
         }
     }
     // chain(background): value of planes z >= used and of pixels outside the aspect-ratio band
@@ -843,8 +863,8 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                     if (!CHECK || (m_in & (1u << p))) {  // lanes past the right border of the plane skip
                         float2 v[NC];
                         if (!GEN || im0 || im1) {
-                            gather_pair<NC, DEPTH, S16>(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p],
-                                        (m_edge & (1u << p)) != 0, wxa[p], wxb[p], wy0, wy1, v);
+                            gather_pair<NC, DEPTH, S16, CHAIN == CH_GRAY>(aA0 + off[p], aB0 + off[p], aA1 + off[p], aB1 + off[p], shl[p], shr[p],
+                                        (m_edge & (1u << p)) != 0, wxa[p], wxb[p], wy0, wy1, v, gsel);
                             if (kFmaDiv) {
 #pragma unroll
                                 for (int c = 0; c < NC; ++c) {
@@ -852,38 +872,33 @@ preproc_tma_kernel(const __grid_constant__ TmaParams K, const __grid_constant__ 
                                     v[c] = div_by_const2(v[c], zh[c], zl[c]);
                                 }
                             } else if (CHAIN == CH_GRAY) {
-                                // 0.299 x + 0.587 y + 0.114 z in the order the program names (cvgs_device.cuh: DOP_GRAY); the
-                                // 2^33 that undoes the tap / weight scaling is folded into the coefficients (exact)
-                                const int kind = K.prog_img.ops[0].kind;
-                                const int rx = (kind >> 8) & 3, ry = (kind >> 12) & 3, rz = (kind >> 16) & 3;
-                                auto pick = [&](int r) {
-                                    float2 t = v[0];
-#pragma unroll
-                                    for (int c = 1; c < NC; ++c) t = r == c ? v[c] : t;
-                                    return t;
-                                };
-                                const float2 x = pick(rx), y = pick(ry), z = pick(rz);
-                                constexpr float kx = 0.299f * kPreScale, ky = 0.587f * kPreScale, kz = 0.114f * kPreScale;
+                                // v[0..2] arrive in operand order (gsel): FMUL on the first, FFMA on the second and third -- or, under
+                                // CVGS_FP_SEPARATE, every product and sum rounded on its own; the 2^33 that undoes the tap / weight
+                                // scaling is folded into the coefficients (exact)
                                 float2 t;
-                                if ((kind >> 20) & 1) {  // CVGS_FP_SEPARATE: every product and sum rounded on its own
-                                    const float2 a = __fmul2_rn(x, make_float2(kx, kx)), b = __fmul2_rn(y, make_float2(ky, ky));
-                                    const float2 c2 = __fmul2_rn(z, make_float2(kz, kz));
+                                if (K.gsep) {
+                                    const float2 a = __fmul2_rn(v[0], make_float2(gk[0], gk[0])), b = __fmul2_rn(v[1], make_float2(gk[1], gk[1]));
+                                    const float2 c2 = __fmul2_rn(v[2], make_float2(gk[2], gk[2]));
                                     t = make_float2(__fadd_rn(__fadd_rn(a.x, b.x), c2.x), __fadd_rn(__fadd_rn(a.y, b.y), c2.y));
-                                } else if ((kind >> 21) & 1) {
-                                    t = __ffma2_rn(z, make_float2(kz, kz), __ffma2_rn(x, make_float2(kx, kx), __fmul2_rn(y, make_float2(ky, ky))));
                                 } else {
-                                    t = __ffma2_rn(z, make_float2(kz, kz), __ffma2_rn(y, make_float2(ky, ky), __fmul2_rn(x, make_float2(kx, kx))));
+                                    t = __ffma2_rn(v[2], make_float2(gk[2], gk[2]),
+                                                   __ffma2_rn(v[1], make_float2(gk[1], gk[1]), __fmul2_rn(v[0], make_float2(gk[0], gk[0]))));
                                 }
                                 float2 g = make_float2(static_cast<float>(__float2int_rn(t.x)), static_cast<float>(__float2int_rn(t.y)));
-                                for (int i = 1; i < K.prog_img.n_ops; ++i) {  // the ops behind the conversion, on the one channel
-                                    const DevOp& op = K.prog_img.ops[i];
-                                    const float a = op.a[0], b = op.b[0];
-                                    switch (op.kind) {
-                                        case DOP_FMA: g = __ffma2_rn(g, make_float2(a, a), make_float2(b, b)); break;
-                                        case DOP_MUL: g = __fmul2_rn(g, make_float2(a, a)); break;
-                                        case DOP_ADD: g = make_float2(__fadd_rn(g.x, a), __fadd_rn(g.y, a)); break;
-                                        case DOP_DIV: g = make_float2(__fdiv_rn(g.x, a), __fdiv_rn(g.y, a)); break;
-                                        default: break;
+                                if (K.gmode == 2) {  // the ops behind the conversion in canonical form
+                                    g = __ffma2_rn(g, make_float2(K.ga, K.ga), make_float2(K.gb, K.gb));
+                                    g = div_by_const2(g, K.gzh, K.gzl);
+                                } else {
+                                    for (int i = 1; i < K.prog_img.n_ops; ++i) {  // ... or one by one, on the one channel
+                                        const DevOp& op = K.prog_img.ops[i];
+                                        const float a = op.a[0], b = op.b[0];
+                                        switch (op.kind) {
+                                            case DOP_FMA: g = __ffma2_rn(g, make_float2(a, a), make_float2(b, b)); break;
+                                            case DOP_MUL: g = __fmul2_rn(g, make_float2(a, a)); break;
+                                            case DOP_ADD: g = make_float2(__fadd_rn(g.x, a), __fadd_rn(g.y, a)); break;
+                                            case DOP_DIV: g = make_float2(__fdiv_rn(g.x, a), __fdiv_rn(g.y, a)); break;
+                                            default: break;
+                                        }
                                     }
                                 }
                                 v[0] = g;
@@ -1055,6 +1070,49 @@ inline bool gray_program(const PreprocParams& P) {
     for (int i = 1; i < g.n_ops; ++i)
         if (g.ops[i].kind != DOP_FMA && g.ops[i].kind != DOP_MUL && g.ops[i].kind != DOP_ADD && g.ops[i].kind != DOP_DIV) return false;
     return !P.band_test && P.used == P.n_planes && P.out.px_stride == 1 && !P.out.planes && !P.out.u8;
+}
+
+// Launch constants of the CH_GRAY instantiation (TmaParams::gsel ...): operand order and coefficients of the conversion
+// (cvgs_device.cuh: DOP_GRAY -- bits 8..19 name the registers of x, y, z, bit 20 separate roundings, bit 21 "the FMUL is
+// y * 0.587"), and the ops behind it in canonical form where the two-operation division is proven (same conditions as
+// scaled_program: |a|, |b| in [2^-24, 2^24] or b zero, the luminance an integer in [0, 255]).
+inline void gray_setup(const DevProgram& g, TmaParams& K) {
+    const int kind = g.ops[0].kind;
+    const int rx = (kind >> 8) & 3, ry = (kind >> 12) & 3, rz = (kind >> 16) & 3;
+    const bool separate = (kind >> 20) & 1, y_first = (kind >> 21) & 1;
+    const float kx = 0.299f * kPreScale, ky = 0.587f * kPreScale, kz = 0.114f * kPreScale;
+    const int reg[3] = {y_first && !separate ? ry : rx, y_first && !separate ? rx : ry, rz};
+    const float kk[3] = {y_first && !separate ? ky : kx, y_first && !separate ? kx : ky, kz};
+    for (int c = 0; c < 3; ++c) {
+        K.gsel[c] = 0x4044u | static_cast<uint32_t>(reg[c]) << 8;
+        K.gk[c] = kk[c];
+    }
+    K.gsep = separate ? 1 : 0;
+    K.gmode = 3;
+    K.ga = 1.f;
+    K.gb = -0.f;
+    K.gzh = 1.f;
+    K.gzl = 0.f;
+    const int n = g.n_ops - 1;
+    const DevOp* ops = g.ops + 1;
+    const bool first_lin = n >= 1 && (ops[0].kind == DOP_MUL || ops[0].kind == DOP_FMA || ops[0].kind == DOP_ADD);
+    const bool lin_only = n == 0 || (n == 1 && first_lin);
+    if (!(lin_only || (n == 2 && first_lin && ops[1].kind == DOP_DIV) || (n == 1 && ops[0].kind == DOP_DIV))) return;
+    const float a = !first_lin ? 1.0f : (ops[0].kind == DOP_ADD ? 1.0f : ops[0].a[0]);
+    const float b = !first_lin ? -0.0f : (ops[0].kind == DOP_MUL ? -0.0f : (ops[0].kind == DOP_ADD ? ops[0].a[0] : ops[0].b[0]));
+    const float d = lin_only ? 1.0f : ops[n - 1].a[0];
+    const float aa = std::fabs(a), ab = std::fabs(b);
+    if (!(std::isfinite(aa) && aa >= 5.9604644775390625e-08f && aa <= 16777216.0f &&
+          (ab == 0.f || (std::isfinite(ab) && ab >= 5.9604644775390625e-08f && ab <= 16777216.0f))))
+        return;
+    const DivConst dc = div_const_prepare(d);
+    const bool neg_zero_possible = ab == 0.f && std::signbit(b) && std::signbit(a);
+    if (!dc.exact || !div_const_pos_zero_ok(dc) || (neg_zero_possible && !div_const_neg_zero_ok(dc))) return;
+    K.gmode = 2;
+    K.ga = a;
+    K.gb = b;
+    K.gzh = dc.zh;
+    K.gzl = dc.zl;
 }
 
 // cvtColor<*2*A> (AddOpaqueAlpha) in a chain on a CV_8UC3 source, in the geometry the CH_*_ALPHA instantiations are built
@@ -1251,6 +1309,7 @@ inline int scaled_program(const PreprocParams& P, TmaParams& K) {
         std::memcpy(K.zh, m.zh, sizeof m.zh);
         std::memcpy(K.zl, m.zl, sizeof m.zl);
         K.G.explicit_prescale = m.explicit_prescale;
+        if (m.chain == CH_GRAY) gray_setup(P.prog, K);  // a handful of launch constants, not memoised
         return m.chain;
     }
     for (int c = 0; c < 4; ++c) K.zh[c] = K.zl[c] = 0.f;
@@ -1270,6 +1329,7 @@ inline int scaled_program_uncached(const PreprocParams& P, TmaParams& K) {
     K.G.explicit_prescale = 1;
     if (gray_program(P)) {  // the conversion's coefficients carry the 2^33
         K.G.explicit_prescale = 0;
+        gray_setup(P.prog, K);
         return CH_GRAY;
     }
     if (P.prog.round_u8) return CH_GENERIC;
