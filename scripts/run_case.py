@@ -15,7 +15,14 @@ lib.cvgs_b200_set_overlap(overlap)
 nsets = 2 if case == "c3" else 32
 sets = []
 for k in range(nsets):
-    w = util.workload_c3(seed=3 + k) if case == "c3" else util.workload_c2(seed=2 + k)
+    # C3_LO / C3_HI: crop-size range of the c3 workload (default 224..896); C3_FORCE_BIG=1 makes crop 0 an 896x896 one, so
+    # that workloads of one scale run with the ring geometry (and residency) of the mixed workload
+    if case == "c3":
+        w = util.workload_c3(seed=3 + k, lo=int(os.environ.get("C3_LO", "224")), hi=int(os.environ.get("C3_HI", "896")))
+        if os.environ.get("C3_FORCE_BIG"):
+            w.rects[0] = (100, 100, 896, 896)
+    else:
+        w = util.workload_c2(seed=2 + k)
     d_img = torch.from_numpy(w.image).cuda()
     d_out = torch.empty((len(w.rects), 3, w.dsize[1], w.dsize[0]), dtype=torch.float32, device="cuda")
     sets.append((w, d_img, d_out, util.host_crops(w.image, w.rects, base_ptr=d_img.data_ptr()),
