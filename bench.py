@@ -617,7 +617,7 @@ def c2_latency_extra(lib, torch, _abi, wl, stream, reps=200):
                     "stream order", "latency_us_min": lat[0], "latency_us_median": lat[len(lat) // 2], "launches": len(lat)}
 
 
-def c3_extra(lib, torch, _abi, marshal, util, stream, reps=20):
+def c3_extra(lib, torch, _abi, marshal, util, stream, reps=100):
     """BASELINE configs[2]: 256 crops (224..896 px) of a 3840x2160 frame -> 224x224, BGR2RGB, ImageNet mean/std,
     NCHW.  154 MB of output per launch, 2 rotating (frame, tensor) sets > L2.  One launch per 256-crop batch."""
     sets = []
@@ -632,7 +632,8 @@ def c3_extra(lib, torch, _abi, marshal, util, stream, reps=20):
     prev = lib.cvgs_b200_set_coalesce(0)  # 256 crops per launch, as the config says
     try:
         fs.launch_sequence(lib, 4, sp)
-        us = _event_us(torch, stream, lambda: fs.launch_sequence(lib, reps, sp), reps)
+        # 100 launches = 4 ms per timed call: the host's first plan (20-30 us before the first kernel starts) is 0.3 us per launch
+        us = sorted(_event_us(torch, stream, lambda: fs.launch_sequence(lib, reps, sp), reps) for _ in range(3))[1]
     finally:
         lib.cvgs_b200_set_coalesce(prev)
     img0, rects0, _d, out0 = sets[0]
@@ -646,6 +647,8 @@ def c3_extra(lib, torch, _abi, marshal, util, stream, reps=20):
                               "launches per 256 crops, same frames, oracle/_ref/libfkref_128.so",
             "workload": "c3: 256 crops (224..896 px) from 3840x2160 -> 224x224 + BGR2RGB + mean/std + NCHW, one launch",
             "parity": "all 256 planes of the timed tensor bit-equal to the oracle",
+            "timing": "median of 3 timed calls of 100 launches each (one host thread, consecutive launches chained by programmatic "
+                      "dependent launch without the early wait: the library proves the two sets independent)",
             "us_per_launch": us, "crops_per_s": 256 / (us * 1e-6), "algorithmic_bytes_per_launch": b_in + b_out,
             "bytes_in": b_in, "bytes_out": b_out, "achieved_gbs": gbs}
 

@@ -1610,7 +1610,21 @@ int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const 
     if (!crops || !parents || !n_planes || !used || !pipelines || n_sets <= 0 || steps < 0)
         return fail(CVGS_ERR_INVALID_VALUE, "bad sequence arguments");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (steps >= 2 && g_overlap.load(std::memory_order_relaxed) && g_variant.load(std::memory_order_relaxed) != 1) {
+    // Sets whose single launch fills the GPU several times over (c3: 256 crops -> 224x224 is 57 K items for 2 960 warps) gain
+    // nothing from sharing launches or from helper threads -- measured 46.9 us per 256-crop set in shared launches against
+    // 39.7-40.9 us launched per set from one thread with the early wait dropped (two launch threads: 39.7-40.5 us once their
+    // streams exist, 7 ms to set them up; plain stream order: 42.2 us).
+    static const bool big_rule = [] { const char* e = std::getenv("CVGS_B200_SEQ_BIG"); return !(e && e[0] == '0'); }();  // tuning override
+    bool big_sets = big_rule;
+    if (big_sets) {
+        int device = 0;
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+        const long long fill = 4LL * sm_count_of(device) * kMaxResident * kWarps;
+        for (int s = 0; s < n_sets && big_sets; ++s)
+            big_sets = pipelines[s] && static_cast<long long>(used[s]) * ((pipelines[s]->dst_height + 1) / 2) *
+                                               ((pipelines[s]->dst_width + 127) / 128) >= fill;
+    }
+    if (!big_sets && steps >= 2 && g_overlap.load(std::memory_order_relaxed) && g_variant.load(std::memory_order_relaxed) != 1) {
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone &&
             sequence_sets_independent(crops, n_planes, used, pipelines, n_sets) &&
@@ -1618,7 +1632,7 @@ int cvgs_b200_preproc_launch_sequence_ex(const cvgs_crop_t* const* crops, const 
             return sequence_coalesced(crops, parents, n_planes, pipelines, n_sets, steps, stream);
     }
     int workers = std::min(seq_workers(), static_cast<int>(n_sets));
-    if (workers > 1 && (steps < 16 || !g_overlap.load(std::memory_order_relaxed))) workers = 1;
+    if (workers > 1 && (big_sets || steps < 16 || !g_overlap.load(std::memory_order_relaxed))) workers = 1;
     if (workers > 1) {
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) workers = 1;
