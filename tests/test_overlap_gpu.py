@@ -158,12 +158,15 @@ def test_concurrent_host_threads():
             for rep in range(15):
                 outs, keep = [], []
                 for w, d in zip((small, big, ring), ds):
-                    o = torch.full((len(w.rects), 3, 48, 32), float("nan"), device="cuda")
+                    with torch.cuda.stream(st):  # the fill is ordered in front of the launch (st does not sync with the default stream)
+                        o = torch.full((len(w.rects), 3, 48, 32), float("nan"), device="cuda")
                     keep.append(_launch(lib, w, d, o, st))
                     outs.append(o)
                 st.synchronize()
                 for o, want in zip(outs, wants):
-                    util.assert_bit_equal(o.cpu().numpy(), want, f"thread {k} rep {rep}")
+                    with torch.cuda.stream(st):
+                        got = o.cpu().numpy()
+                    util.assert_bit_equal(got, want, f"thread {k} rep {rep}")
         except Exception as e:  # noqa: BLE001
             errors.append(f"thread {k}: {e}")
 
