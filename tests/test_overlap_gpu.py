@@ -36,6 +36,7 @@ def test_many_independent_launches(overlap_on):
     ws = [util.workload_c2(seed=300 + k, n=20, frame=(640, 480), pitch=1920) for k in range(6)]
     d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
     outs = [torch.full((20, 3, 128, 64), float("nan"), device="cuda") for _ in range(40)]
+    torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
     keep = [_launch(lib, ws[i % 6], d_imgs[i % 6], outs[i], st) for i in range(40)]  # > the 8-launch window
     st.synchronize()
     want = [util.run_oracle(w.image, w.rects, w.dsize, w.ops) for w in ws]
@@ -50,6 +51,7 @@ def test_same_output_is_written_in_launch_order(overlap_on):
     ws = [util.workload_c2(seed=310 + k, n=50, pitch=6144) for k in range(2)]
     d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
     out = torch.full((50, 3, 128, 64), float("nan"), device="cuda")
+    torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
     keep = []
     for rep in range(25):
         for k in range(2):
@@ -65,10 +67,12 @@ def test_output_of_one_launch_as_source_of_the_next(overlap_on):
     wa = util.workload_c3(seed=320, n=64, frame=(1920, 1080), dsize=(224, 224), lo=200, hi=800)
     d_img = torch.from_numpy(wa.image).cuda()
     t = torch.zeros((64, 3, 224, 224), dtype=torch.float32, device="cuda")      # A's output = B's "image"
+    torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
     pitch = 3 * 224 * 4                                                          # one float row triple = 896 pixels
     rows = t.numel() * 4 // pitch
     rects = [(5 * i, 3 * i, 200 + i, 100 + 2 * i) for i in range(30)]
     out_b = torch.full((30, 3, 128, 64), float("nan"), device="cuda")
+    torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
     keep = []
     for rep in range(3):
         keep.append(_launch(lib, wa, d_img, t, st))
@@ -94,6 +98,7 @@ def test_later_stream_work_sees_every_launch_complete(overlap_on):
     d_big, d_small = torch.from_numpy(big.image).cuda(), torch.from_numpy(small.image).cuda()
     out_big = torch.full((256, 3, 224, 224), float("nan"), device="cuda")
     out_small = torch.full((2, 3, 128, 64), float("nan"), device="cuda")
+    torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
     host = torch.empty(out_big.shape, dtype=torch.float32).pin_memory()
     want = util.run_oracle(big.image, big.rects[:8], big.dsize, big.ops)
     for rep in range(5):
@@ -119,6 +124,7 @@ def test_launches_are_graph_capturable(overlap):
         ws = [util.workload_c2(seed=340 + k, n=50, pitch=6144) for k in range(3)]
         d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
         outs = [torch.full((50, 3, 128, 64), float("nan"), device="cuda") for _ in ws]
+        torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
         st = torch.cuda.Stream()
         keep = [_launch(lib, w, d, o, st) for w, d, o in zip(ws, d_imgs, outs)]  # warm-up: attributes, proofs, map cache
         st.synchronize()
@@ -216,6 +222,7 @@ def test_frame_loop_shares_launches(overlap_on):
     ws = [util.workload_c2(seed=740 + k, n=n, pitch=6144) for k, n in enumerate(sizes)]
     d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
     outs = [torch.full((len(w.rects), 3, 128, 64), float("nan"), device="cuda") for w in ws]
+    torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
     want = [util.run_oracle(w.image, w.rects, w.dsize, w.ops) for w in ws]
     steps = len(ws) * 9 + 5
     with torch.cuda.stream(st):
@@ -253,6 +260,7 @@ def test_frame_loop_shared_launches_overlap_and_rewrite(overlap_on):
     d_imgs = [torch.from_numpy(w.image).cuda() for w in ws_a]
     d_alt = [torch.from_numpy(w.image).cuda() for w in ws_b]
     outs = [torch.full((50, 3, 128, 64), float("nan"), device="cuda") for _ in ws_a]
+    torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
     with torch.cuda.stream(st):
         launches, keep = _sequence(lib, ws_a, d_imgs, outs, 3 * n_sets + 7, st)
         for k in range(0, n_sets, 2):
@@ -273,6 +281,7 @@ def test_frame_loop_shared_launch_c3_shape(overlap_on):
     ws = [util.workload_c3(seed=760 + k, n=40) for k in range(3)]
     d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
     outs = [torch.full((40, 3, 224, 224), float("nan"), device="cuda") for _ in ws]
+    torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
     launches, keep = _sequence(lib, ws, d_imgs, outs, 6, st)
     st.synchronize()
     assert launches == 2
@@ -289,6 +298,7 @@ def test_frame_loop_declines_to_share_what_the_tma_kernel_cannot_take(overlap_on
     ws = [util.workload_c2(seed=770 + k, n=20, frame=(640, 480), pitch=1920 if k != 2 else 1923) for k in range(5)]
     d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
     outs = [torch.full((20, 3, 128, 64), float("nan"), device="cuda") for _ in ws]
+    torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
     launches, keep = _sequence(lib, ws, d_imgs, outs, 10, st)
     st.synchronize()
     assert launches == 10
@@ -305,6 +315,7 @@ def test_frame_loop_over_several_host_threads(per_step_launches):
     ws = [util.workload_c2(seed=700 + k, n=50, pitch=6144) for k in range(7)]
     d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
     outs = [torch.full((50, 3, 128, 64), float("nan"), device="cuda") for _ in ws]
+    torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
     want = [util.run_oracle(w.image, w.rects, w.dsize, w.ops) for w in ws]
     with torch.cuda.stream(st):
         launches, keep = _sequence(lib, ws, d_imgs, outs, 7 * 30, st)
@@ -326,6 +337,7 @@ def test_frame_loop_with_dependent_sets_stays_in_order(overlap_on):
     ws = [util.workload_c2(seed=720 + k, n=50, pitch=6144) for k in range(2)]
     d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
     out = torch.full((50, 3, 128, 64), float("nan"), device="cuda")
+    torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
     launches, keep = _sequence(lib, ws, d_imgs, [out, out], 2 * 80, st)
     st.synchronize()
     assert launches == 160
@@ -341,6 +353,7 @@ def test_frame_loop_error_is_reported(overlap_on, coalesce):
     ws = [util.workload_c2(seed=730 + k, n=10, frame=(640, 480), pitch=1920) for k in range(4)]
     d_imgs = [torch.from_numpy(w.image).cuda() for w in ws]
     outs = [torch.zeros((10, 3, 128, 64), device="cuda") for _ in ws]
+    torch.cuda.synchronize()  # the fills ran on the default stream, the launches go to a non-blocking one
     n = 4
     keep = []
     for i, (w, d, o) in enumerate(zip(ws, d_imgs, outs)):
