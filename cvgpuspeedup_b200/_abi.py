@@ -104,6 +104,8 @@ SYMBOLS = {
     "cvgs_b200_launch_count": (C.c_int64, []),
     "cvgs_b200_debug_host_profile": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     "cvgs_b200_debug_fast_div": (C.c_uint32, [C.c_uint32, C.c_uint32]),
+    "cvgs_b200_debug_warp_mode": (C.c_int, [C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_int32]),
+    "cvgs_b200_debug_chain_kind": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cvgs_b200_debug_host_bytes": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]),
     "cvgs_b200_debug_program": (C.c_int, [C.POINTER(Pipeline), C.POINTER(C.c_float)]),
     "cvgs_b200_debug_plan": (C.c_int, [C.POINTER(Crop), C.c_int32, C.c_int32, C.POINTER(Pipeline), C.c_int32, C.c_int32,

@@ -1066,6 +1066,28 @@ int cvgs_b200_debug_overlap_query(void* stream_key, uint64_t out_lo, uint64_t ou
     return overlap_needs_wait(static_cast<cudaStream_t>(stream_key), o, s) ? 1 : 0;
 }
 
+static bool warp_denominators_normal(const float* m, int w_padded, int h);
+int cvgs_b200_debug_warp_mode(const float* m9, int32_t warp_type, int32_t dst_width, int32_t dst_height) {
+    if (!m9 || dst_width <= 0 || dst_height <= 0) return -1;
+    if (warp_type == CVGS_WARP_AFFINE) return WM_AFFINE;
+    return warp_denominators_normal(m9, (dst_width + 127) / 128 * 128, dst_height) ? WM_PERSPECTIVE_NORMAL : WM_PERSPECTIVE;
+}
+
+int cvgs_b200_debug_chain_kind(const cvgs_pipeline_t* pipeline, float* alpha) {
+    if (int rc = validate_pipeline(pipeline)) return -rc;
+    float dummy = 0.f;
+    PreprocParams P;
+    if (int rc = build_params(*pipeline, 1, 1, &dummy, P)) return -rc;
+    TmaParams K;
+    K.P = P;
+    std::memset(&K.G, 0, sizeof K.G);
+    const int pb = pixel_bytes_of(P.src_type);
+    K.G.prescale = pb >= 6 ? kPreScale16 : kPreScale;
+    const int chain = scaled_program_for(P, K);
+    if (alpha) *alpha = K.alpha;
+    return chain;
+}
+
 uint32_t cvgs_b200_debug_fast_div(uint32_t n, uint32_t d) {
     return d ? fast_div(n, fast_div_make(d)) : 0u;
 }

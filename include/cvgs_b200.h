@@ -367,6 +367,14 @@ int cvgs_b200_set_coalesce(int enable);
 int cvgs_b200_set_host_upload(int mode);
 /* Number of kernel launches issued by this library on the calling thread so far. */
 int64_t cvgs_b200_launch_count(void);
+/* Diagnostics (no device needed): how the fast warp kernel would form the source coordinate for this inverse matrix and
+ * destination size -- 0 affine, 1 perspective with every denominator proven finite, of one sign and of magnitude in
+ * [2^-100, 2^100] (reciprocal without the range check), 2 perspective in general; -1 on bad arguments. */
+int cvgs_b200_debug_warp_mode(const float* m9, int32_t warp_type, int32_t dst_width, int32_t dst_height);
+/* Diagnostics (no device needed): the chain kind the TMA-staged kernel would run this pipeline's chain with -- 0 interpreter,
+ * 1 fma + two-operation division, 2 gray, 3 / 4 the former two plus a constant alpha plane (whose value goes to *alpha) --
+ * or the negated error code. */
+int cvgs_b200_debug_chain_kind(const cvgs_pipeline_t* pipeline, float* alpha);
 /* Diagnostics (no device needed): n / d as the kernels' prologues compute it (multiply-shift by a launch constant,
  * FastDiv in csrc/preproc_tma.cuh); exact for n < 2^31. */
 uint32_t cvgs_b200_debug_fast_div(uint32_t n, uint32_t d);

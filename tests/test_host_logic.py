@@ -158,3 +158,60 @@ def test_fast_division_by_launch_constants_is_exact():
         for n in ns:
             if 0 <= n < 2 ** 31:
                 assert lib.cvgs_b200_debug_fast_div(n, d) == n // d, (n, d)
+
+
+def test_warp_mode_of_the_fast_kernel():
+    """Host side of the fast warp kernel: the reciprocal of the perspective denominator skips its range check only when
+    every denominator over the (padded) destination is finite, of one sign and comfortably inside the normal range."""
+    import ctypes as C
+    lib = _abi.load()
+    f9 = lambda v: (C.c_float * 9)(*v)  # noqa: E731
+    ident = [1, 0, 0, 0, 1, 0, 0, 0, 1]
+    assert lib.cvgs_b200_debug_warp_mode(f9(ident), 0, 640, 480) == 0          # affine
+    assert lib.cvgs_b200_debug_warp_mode(f9(ident), 1, 640, 480) == 1          # denominator 1 everywhere
+    assert lib.cvgs_b200_debug_warp_mode(f9([1, 0, 0, 0, 1, 0, 1e-4, -2e-4, 1]), 1, 640, 480) == 1
+    assert lib.cvgs_b200_debug_warp_mode(f9([1, 0, 0, 0, 1, 0, -1e-3, 0, -0.5]), 1, 640, 480) == 1   # negative throughout
+    assert lib.cvgs_b200_debug_warp_mode(f9([1, 0, 0, 0, 1, 0, -1e-2, 0, 1]), 1, 640, 480) == 2      # crosses zero at x = 100
+    assert lib.cvgs_b200_debug_warp_mode(f9([1, 0, 0, 0, 1, 0, -1e-2, 0, 1]), 1, 64, 480) == 2       # ... also inside the padded width (128)
+    assert lib.cvgs_b200_debug_warp_mode(f9([1, 0, 0, 0, 1, 0, -1e-3, 0, 1]), 1, 640, 480) == 1      # zero at x = 1000: outside 640 (padded) columns
+    assert lib.cvgs_b200_debug_warp_mode(f9([1, 0, 0, 0, 1, 0, 0, 0, 0]), 1, 640, 480) == 2          # 0 / 0
+    assert lib.cvgs_b200_debug_warp_mode(f9([1, 0, 0, 0, 1, 0, 0, 0, 1e-35]), 1, 640, 480) == 2      # too small
+    assert lib.cvgs_b200_debug_warp_mode(f9([1, 0, 0, 0, 1, 0, 0, 0, 1e35]), 1, 640, 480) == 2       # too large
+    assert lib.cvgs_b200_debug_warp_mode(f9([1, 0, 0, 0, 1, 0, float("nan"), 0, 1]), 1, 640, 480) == 2
+    assert lib.cvgs_b200_debug_warp_mode(f9([1, 0, 0, 0, 1, 0, 1.0, 1.0, 1e-9]), 1, 640, 480) == 2   # near-cancellation at (0, 0): margin
+    assert lib.cvgs_b200_debug_warp_mode(None, 1, 640, 480) == -1
+
+
+def test_chain_kinds_of_the_tma_kernel():
+    """Which instantiation a chain runs on (scaled_program): no op and lone linear ops are the specialised shape with a
+    division by 1, rounded interpolation and long chains the interpreter, gray / alpha conversions their own kinds; the
+    alpha plane's value is the constant run through the ops behind the conversion in IEEE single precision."""
+    import ctypes as C
+    import numpy as np
+    lib = _abi.load()
+
+    def kind(ops, **kw):
+        p = util.make_pipeline((64, 64), ops, out_ptr=0x1000, **kw)
+        a = C.c_float(0)
+        return lib.cvgs_b200_debug_chain_kind(C.byref(p), C.byref(a)), a.value
+
+    assert kind([])[0] == 1
+    assert kind([("mul", (0.5, 0.25, 2.0))])[0] == 1
+    assert kind([("mul", (0.5, 0.25, 2.0)), ("sub", (1.0, 2.0, 3.0))])[0] == 1          # contracted into one FMA
+    assert kind([("mul", (1 / 255.0,) * 3), ("sub", (0.485, 0.456, 0.406)), ("div", (0.229, 0.224, 0.225))])[0] == 1
+    assert kind([("div", (3.0, 5.0, 7.0))])[0] == 1
+    assert kind([("mul", (0.5, 0.25, 2.0)), ("sub", (1.0, 2.0, 3.0))], fp_contract=_abi.FP_SEPARATE)[0] == 0   # two roundings: two ops
+    assert kind([("div", (3.0, 5.0, 7.0)), ("mul", (0.5, 0.25, 2.0))])[0] == 0
+    assert kind([("mul", (0.5, 0.25, 2.0))], interp_mode=_abi.INTERP_ROUND_U8)[0] == 0
+    assert kind([("mul", (1e30, 1.0, 1.0)), ("div", (3.0, 5.0, 7.0))])[0] == 0          # outside the proven range
+    assert kind([("gray", (1,)), ("mul", (1 / 255.0,))])[0] == 2
+    k, a = kind([("add_alpha", (255.0,))])
+    assert (k, a) == (3, 255.0)
+    k, a = kind([("reorder", (2, 1, 0)), ("add_alpha", (255.0,)), ("mul", (1 / 255.0,) * 4), ("sub", (0.485, 0.456, 0.406, 0.5)),
+                 ("div", (0.229, 0.224, 0.225, 0.25))])
+    # mul + sub contract into one FMA (one rounding: the product of two floats is exact in double), then an IEEE division
+    want = np.float32(255.0 * float(np.float32(1 / 255.0)) - 0.5)
+    want = np.float32(want / np.float32(0.25))
+    assert k == 3 and np.float32(a) == want, (k, a, want)
+    k, a = kind([("add_alpha", (7.0,)), ("mul", (2.0, 2.0, 2.0, 3.0)), ("add", (1.0, 1.0, 1.0, 0.5)), ("mul", (1.0, 1.0, 1.0, 2.0))])
+    assert k == 4 and a == (7.0 * 3.0 + 0.5) * 2.0
