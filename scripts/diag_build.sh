@@ -3,7 +3,7 @@
 # to see which side of the memory system bounds a workload.  Use with CVGS_B200_LIB=<path> (results are garbage).
 set -e
 cd "$(dirname "$0")/../cvgpuspeedup_b200"
-FLAGS="-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared"
+FLAGS="-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -split-compile 8 -Xcompiler -fPIC -shared"
 SRCS="csrc/preproc.cu csrc/circular_tensor.cu csrc/selftest.cu csrc/div_const.o"
 mkdir -p ../gpurun_out
 nvcc $FLAGS -DCVGS_DIAG_SKIP_STORES -o /tmp/libcvgs_diag_nostore.so $SRCS &
